@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""Benchmark of the Wave-Mamba forward hot path (BASELINE.json: 3840x2160 images/s, forward).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A "step" is one forward of one synthetic 3840x2160 low-light image per GPU through the
+reference-facing class (``WaveMamba.restoration_network``), UHD-LL weights.  N>1 is launched by
+torchrun, one rank per GPU; images are independent, so ranks share nothing on the data path
+(weak scaling, NCCL only for the one-off weight broadcast and the timing reduction).
+
+One JSON line on stdout (rank 0):
+  value        images/s, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e          same, but every step copies its input from pinned host memory and reads the full
+               output image back (what inference_wavemamba.py does per image)
+  roofline     the dominant hand-written kernel group (SS2D core): algorithmic bytes / measured
+               duration vs the measured HBM peak (MEASURED_PEAKS.json), plus per-kernel rows
+  cpu_baseline the CPU oracle (port of the reference forward) timed on this box's host cores on a
+               bounded sample
+``--impl reference`` times the reference's CPU implementation of the path (the oracle port:
+the reference has no compilable native sources and mamba_ssm is absent) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "3840x2160 images/sec fwd"
+UNIT = "images/s"
+H4K, W4K = 2160, 3840
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--height", type=int, default=H4K)
+    ap.add_argument("--width", type=int, default=W4K)
+    ap.add_argument("--tf32", type=int, default=0,
+                    help="1: let cuDNN use TF32 for the dense 3x3 convs (the reference's default)")
+    ap.add_argument("--ckpt", default="UHDLL")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def load_params(name):
+    return torch.load(os.path.join(ROOT, "ckpt", f"WaveMamba_{name}.pth"), map_location="cpu")["params"]
+
+
+def measured_hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU baseline (oracle port of the reference forward), bounded sample
+# ----------------------------------------------------------------------------------------------
+def cpu_forward_sample(params, h, w, reps=1, seed=1234):
+    from oracle import model as om
+    torch.set_num_threads(os.cpu_count() or 1)
+    x, _ = om.synth_lowlight(1, h, w, seed)
+    best = float("inf")
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        om.unet_forward(params, x)
+        best = min(best, time.perf_counter() - t0)
+    return best
+
+
+def cpu_baseline(params, H, W, frac_side=2):
+    """Time the oracle on a (H/frac_side) x (W/frac_side) image and scale by pixel count."""
+    h = max(8, (H // frac_side + 7) // 8 * 8)
+    w = max(8, (W // frac_side + 7) // 8 * 8)
+    sec = cpu_forward_sample(params, h, w)
+    scale = (H * W) / float(h * w)
+    return {
+        "value": 1.0 / (sec * scale), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+        "sample": f"one {w}x{h} synthetic image ({sec:.2f} s), scaled x{scale:.2f} by pixel count to "
+                  f"{W}x{H}; oracle = functional torch-CPU restatement + C/OpenMP sequential scan",
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    params = load_params(args.ckpt)
+    H, W = args.height, args.width
+    h = max(8, (H // 4 + 7) // 8 * 8)
+    w = max(8, (W // 4 + 7) // 8 * 8)
+    scale = (H * W) / float(h * w)
+    for _ in range(args.warmup):
+        cpu_forward_sample(params, h, w)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_forward_sample(params, h, w)
+    sec = (time.perf_counter() - t0) / max(args.steps, 1)
+    value = 1.0 / (sec * scale)
+    cores = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * scale * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"UHD-LL {W}x{H} batch=1 forward, CPU oracle port of the reference",
+                   "sample": f"{w}x{h} per step, scaled x{scale:.2f} by pixel count"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} steps of one {w}x{h} image, scaled x{scale:.2f}"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks sampler
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [c.strip() for c in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                  "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# per-kernel CUDA-event instrumentation of wave_mamba_b200.ops
+# ----------------------------------------------------------------------------------------------
+class OpTimer:
+    """Wraps the ops entry points with CUDA events on the current stream."""
+
+    def __init__(self, ops):
+        self.ops = ops
+        self.records = []   # (name, bytes, start_event, end_event)
+        self.enabled = False
+        self._orig = {}
+
+    @staticmethod
+    def _numel_bytes(*tensors):
+        return sum(t.numel() * t.element_size() for t in tensors if isinstance(t, torch.Tensor))
+
+    def install(self):
+        ops = self.ops
+
+        def wrap(name, bytes_fn):
+            orig = getattr(ops, name)
+            self._orig[name] = orig
+
+            def inner(*a, **k):
+                if not self.enabled:
+                    return orig(*a, **k)
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                out = orig(*a, **k)
+                e.record()
+                self.records.append((name, bytes_fn(a, k, out), s, e))
+                return out
+            setattr(ops, name, inner)
+
+        nb = self._numel_bytes
+        # algorithmic bytes: every input activation read once, every output written once
+        wrap("dwt_haar", lambda a, k, o: nb(a[0]) + nb(*o))
+        wrap("iwt_haar", lambda a, k, o: nb(a[0], a[1]) + nb(o))
+        wrap("iwt_haar_cat", lambda a, k, o: nb(a[0]) + nb(o))
+        wrap("ss2d_core", lambda a, k, o: nb(a[0]) + nb(o))      # 512*B*L  
+        wrap("layernorm2d", lambda a, k, o: nb(a[0]) + nb(o))
+        wrap("pw_dw", lambda a, k, o: nb(a[0]) + nb(o))
+        wrap("dw_act_pw", lambda a, k, o: nb(a[0]) + nb(o) + nb(k.get("residual"),
+                                                                  a[6] if len(a) > 6 else None))
+        wrap("pw", lambda a, k, o: nb(a[0]) + nb(o) + nb(k.get("residual")))
+        wrap("paconv_gate", lambda a, k, o: nb(a[0]) + 2 * nb(o))
+
+    def summary(self, peak_gbs):
+        agg = {}
+        for name, nbytes, s, e in self.records:
+            ms = s.elapsed_time(e)
+            d = agg.setdefault(name, {"calls": 0, "ms": 0.0, "bytes": 0})
+            d["calls"] += 1; d["ms"] += ms; d["bytes"] += nbytes
+        rows = []
+        for name, d in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
+            gbs = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else 0.0
+            rows.append({"kernel": name, "calls": d["calls"], "ms_total": round(d["ms"], 4),
+                         "algorithmic_gb": round(d["bytes"] / 1e9, 4), "achieved_gbs": round(gbs, 1),
+                         "frac_of_hbm_peak": round(gbs / peak_gbs, 4)})
+        return rows
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, (world, args.gpus)
+
+    torch.backends.cudnn.benchmark = True          # as the reference drivers set it
+    torch.backends.cudnn.allow_tf32 = bool(args.tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+    import wave_mamba_b200 as wm
+    from wave_mamba_b200 import ops, parallel
+    from oracle import model as om   # synthetic-input generator + cpu_baseline only
+
+    H, W = args.height, args.width
+    params = load_params(args.ckpt) if rank == 0 else None
+    net = wm.WaveMamba(in_chn=3, wf=32, n_l_blocks=[1, 2, 4], n_h_blocks=[1, 1, 2], ffn_scale=2.0)
+    if rank == 0:
+        net.load_state_dict(params, strict=True)
+    net = net.to(dev).eval()
+    if world > 1:
+        parallel.broadcast_parameters(net, src=0)     # NCCL, once, outside the timed region
+
+    x_host, _ = om.synth_lowlight(1, H, W, seed=1234 + rank)   # each rank owns one image (shard)
+    x_host = x_host.pin_memory()
+    x_dev = x_host.to(dev, non_blocking=True)
+    y_host = torch.empty_like(x_host).pin_memory()
+    torch.cuda.synchronize()
+
+    timer = OpTimer(ops)
+    timer.install()
+    peak_gbs, peak_src = measured_hbm_peak()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    fwd = net.restoration_network
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            y = fwd(x_dev)
+        # ---- device-resident timing ------------------------------------------------------
+        barrier()
+        clocks = ClockSampler(local_rank)
+        if rank == 0:
+            clocks.start()
+        launches0 = ops.launch_count
+        timer.enabled = True
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(args.steps):
+            y = fwd(x_dev)
+        e.record()
+        barrier()
+        timer.enabled = False
+        launches = ops.launch_count - launches0
+        ms_dev = max_over_ranks(s.elapsed_time(e))
+        # ---- end to end: pinned host -> device -> forward -> pinned host ----------------------
+        for _ in range(2):
+            y_host.copy_(fwd(x_host.to(dev, non_blocking=True)), non_blocking=True)
+        barrier()
+        s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s2.record()
+        for _ in range(args.steps):
+            xd = x_host.to(dev, non_blocking=True)
+            y_host.copy_(fwd(xd), non_blocking=True)
+        e2.record()
+        barrier()
+        ms_e2e = max_over_ranks(s2.elapsed_time(e2))
+        clk = clocks.stop() if rank == 0 else None
+    checksum = float(y_host.double().mean())
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    rows = timer.summary(peak_gbs)
+    ss = next((r for r in rows if r["kernel"] == "ss2d_core"), None)
+    L_total = sum((H // (2 ** l)) * (W // (2 ** l)) * n for l, n in ((1, 2), (2, 4), (3, 8)))
+    roofline = None
+    if ss:
+        roofline = {
+            "kernel": "ss2d_core (pass1 + carry + pass2A + pass2B + combine)", "bound": "hbm",
+            "achieved": ss["achieved_gbs"], "peak": peak_gbs, "unit": "GB/s",
+            "frac": ss["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src,
+            "bytes_definition": "512*B*L per call (x read once + merged y written once), SURVEY 8d",
+            "ms_per_image": round(ss["ms_total"] / args.steps, 4),
+            "scan_operand_bytes_frac": round(ss["frac_of_hbm_peak"] * 7.0, 4),
+            "note": "instruction-bound (one MUFU ex2 + ~4 FMA per state update, evaluated twice), "
+                    "not HBM-bound: see DESIGN.md section 4",
+            "state_updates_per_s": round(L_total * 4096 * args.steps / (ss["ms_total"] * 1e-3), 1),
+        }
+    n_img = world * args.steps
+    line = {
+        "metric": METRIC, "value": n_img / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"UHD-LL {W}x{H} batch=1 per GPU forward (BASELINE configs[2])",
+                   "weights": f"WaveMamba_{args.ckpt}.pth", "cudnn_tf32": bool(args.tf32),
+                   "l2": "inputs and activations (>=1 GB per level-1 tensor) exceed the 126 MB L2",
+                   "parallelism": f"batch-sharded x{world}, no data-path collective"},
+        "e2e": {"value": n_img / (ms_e2e * 1e-3), "unit": UNIT,
+                "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": y_host.numel() * 4},
+        "gpu_launches": launches,
+        "clocks": clk,
+        "roofline": roofline,
+        "kernels": rows,
+        "output_mean": checksum,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(params, H, W)
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,114 @@
+/*
+ * wavemamba_b200 -- C ABI of the B200-native Wave-Mamba forward hot path.
+ *
+ * This is the drop-in boundary.  The reference has no native code;
+ * its hot path is Python in basicsr/archs/wavemamba_arch.py plus one third-party CUDA
+ * extension (mamba_ssm.selective_scan_fn).  Each entry point below replaces the Python
+ * function (file:line in /root/reference) named in its comment.  The reference-side
+ * binding is a ctypes stub; wave_mamba_b200/_cabi.py is that stub.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to float32 data on the current CUDA device,
+ *     contiguous NCHW unless stated; the caller owns all buffers (inputs, outputs,
+ *     workspaces); nothing is allocated or freed by the library;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); kernels
+ *     are enqueued asynchronously on it and the call returns immediately;
+ *   - return value: 0 on success, a negative WM_E* code on failure; the message for the
+ *     calling thread's last failure is wm_last_error().  There is no CPU fallback.
+ */
+#ifndef WAVEMAMBA_B200_H
+#define WAVEMAMBA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WM_OK 0
+#define WM_EINVAL (-1)    /* bad shape / null pointer / misaligned or too-small workspace */
+#define WM_ECUDA (-2)     /* a CUDA runtime call or kernel launch failed               */
+#define WM_ENODEVICE (-3) /* no sm_100-class CUDA device is current                     */
+
+#define WM_ABI_VERSION 1
+
+typedef void *wm_stream_t;
+
+int wm_abi_version(void);
+const char *wm_last_error(void);
+/* 0 when the current device can run this library (compute capability 10.x), else WM_ENODEVICE. */
+int wm_device_check(void);
+
+/* ---- Haar DWT -- dwt_init / DWT.forward, wavemamba_arch.py:97-110,133-139 -------------
+ * x: (planes, H, W) with planes = B*C, H and W even.  ll/hl/lh/hh: (planes, H/2, W/2).
+ * Bit-exact with the reference (same /2 and the same left-to-right association). */
+int wm_dwt_haar_fwd(const float *x, float *ll, float *hl, float *lh, float *hh,
+                    int64_t planes, int64_t H, int64_t W, wm_stream_t stream);
+
+/* ---- Haar IWT -- iwt_init / IWT.forward, wavemamba_arch.py:113-130,142-148 -------------
+ * The reference takes torch.cat([x_l, x_h], 1) (B,4C,h,w) (wavemamba_arch.py:1006); here
+ * the two halves are passed separately so the cat copy is never made:
+ *   low : B planes-groups of C planes (LL),  batch stride low_bstride  (floats)
+ *   high: B groups of 3C planes (HL|LH|HH),  batch stride high_bstride (floats)
+ * Passing low = cat, high = cat + C*h*w, both strides 4*C*h*w reproduces the cat form.
+ * y: (B, C, 2h, 2w) contiguous.  Bit-exact with the reference. */
+int wm_iwt_haar_fwd(const float *low, int64_t low_bstride, const float *high,
+                    int64_t high_bstride, float *y, int64_t B, int64_t C, int64_t h, int64_t w,
+                    wm_stream_t stream);
+
+/* ---- SS2D core -- SS2D.forward_core + the 4-way sum of SS2D.forward,
+ *      wavemamba_arch.py:446-478,490 (cross-scan, x_proj, dt_proj, softplus,
+ *      selective_scan_fn, flips/transposes, y1+y2+y3+y4) ------------------------------------
+ * x: (B, 64, h, w) (output of conv2d+SiLU).  y: (B, 64, h, w) = merged scan output.
+ * x_proj_weight (4,34,64), dt_projs_weight (4,64,2), dt_projs_bias (4,64), A_logs (256,16),
+ * Ds (256): the module's parameters as stored in the checkpoint.
+ * workspace: >= wm_ss2d_core_workspace_bytes(B,h,w) bytes, 256-byte aligned.
+ * Fixed model constants: d_inner 64, d_state 16, dt_rank 2, 4 directions. */
+size_t wm_ss2d_core_workspace_bytes(int64_t B, int64_t h, int64_t w);
+int wm_ss2d_core_fwd(const float *x, const float *x_proj_weight, const float *dt_projs_weight,
+                     const float *dt_projs_bias, const float *A_logs, const float *Ds, float *y,
+                     void *workspace, size_t workspace_bytes, int64_t B, int64_t h, int64_t w,
+                     wm_stream_t stream);
+
+/* ---- fused pointwise (1x1) / depthwise (3x3) convolution groups ----------------------------
+ * HFEBlock / CMTAttention / FeedForward / PAConv / LFSSBlock.ffn pieces,
+ * wavemamba_arch.py:214-231,687,694-697,729-742,756-764,775,797,826-851.
+ * All tensors NCHW float32; weights in PyTorch conv layout (Cout,Cin,1,1) / (C,1,3,3).
+ * `ln_w`/`ln_b` non-NULL fuses LayerNorm2d (wavemamba_arch.py:535-543, biased variance over
+ * the channel axis, eps) in front of the 1x1.  Depthwise convs use zero padding 1.          */
+
+/* LayerNorm2d alone: y = ln(x).  C <= 64. */
+int wm_layernorm2d_fwd(const float *x, const float *ln_w, const float *ln_b, float eps, float *y,
+                       int64_t B, int64_t C, int64_t h, int64_t w, wm_stream_t stream);
+
+/* y = dw3x3( pw1x1( ln?(x) ) ) : Cin=32 -> Cout in {32,64,96}.
+ * Used for qkv+qkv_dwconv (:775), FeedForward.project_in (:729-732,745), ffn.conv1+conv2 (:226). */
+int wm_pw_dw_fwd(const float *x, const float *ln_w, const float *ln_b, float eps,
+                 const float *pw_w, const float *pw_b, const float *dw_w, const float *dw_b,
+                 float *y, int64_t B, int64_t Cin, int64_t Cout, int64_t h, int64_t w,
+                 wm_stream_t stream);
+
+/* y = residual? + pw1x1( act( dw3x3(x) ) ), act: 0 none, 1 exact (erf) GELU.   C=32 -> 32.
+ * FeedForward.project_out (:739-742,750) fused with the HFEBlock residual add (:851). */
+int wm_dw_act_pw_fwd(const float *x, const float *dw_w, const float *dw_b, const float *pw_w,
+                     const float *pw_b, int act, const float *residual, float *y, int64_t B,
+                     int64_t C, int64_t h, int64_t w, wm_stream_t stream);
+
+/* y = residual? + pw1x1(x) + bias : Cin -> Cout, both <= 64.
+ * CMTAttention.project_out (:797) fused with the HFEBlock residual add (:849);
+ * also ffn.conv3 after the gate.  gate_mode 0: plain; 1: input is (B,2*Cin,h,w) and the 1x1
+ * sees gelu(x[:, :Cin]) * x[:, Cin:]  (ffn gate, :227-228). */
+int wm_pw_fwd(const float *x, const float *pw_w, const float *pw_b, int gate_mode,
+              const float *residual, float *y, int64_t B, int64_t Cin, int64_t Cout, int64_t h,
+              int64_t w, wm_stream_t stream);
+
+/* PAConv gate: y = k3out * sigmoid( pw1x1(x) + b ), x and k3out and y all (B,64,h,w)
+ * (PAConv.k2 + sigmoid + mul, :694-697).  In-place on k3out allowed (y == k3out). */
+int wm_paconv_gate_fwd(const float *x, const float *k2_w, const float *k2_b, const float *k3out,
+                       float *y, int64_t B, int64_t C, int64_t h, int64_t w, wm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WAVEMAMBA_B200_H */

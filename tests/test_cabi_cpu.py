@@ -1,0 +1,146 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol
+include/*.h declares, the host-side mirror has the reference's constructor / state dict, and
+the product refuses to run without a GPU (no fallback).  No compute calls here."""
+import ctypes
+import glob
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from conftest import ROOT, load_params
+
+
+def _declared_symbols():
+    names = set()
+    for hdr in glob.glob(os.path.join(ROOT, "include", "*.h")):
+        text = open(hdr).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names |= set(re.findall(r"\b(wm_[a-z0-9_]+)\s*\(", text))
+    return names
+
+
+@pytest.fixture(scope="module")
+def lib_path():
+    from wave_mamba_b200 import build
+    return build.build()
+
+
+def test_library_exports_every_declared_symbol(lib_path):
+    lib = ctypes.CDLL(lib_path)
+    declared = _declared_symbols()
+    assert len(declared) >= 12
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/ but not exported"
+
+
+def test_binding_table_matches_header(lib_path):
+    from wave_mamba_b200 import _cabi
+    assert set(_cabi.SIGNATURES) == _declared_symbols()
+    lib = _cabi.load()
+    assert lib.wm_abi_version() == _cabi.ABI_VERSION
+
+
+def test_library_is_sm100a_only(lib_path):
+    out = subprocess.run(["cuobjdump", "-lelf", lib_path], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    archs = set(re.findall(r"sm_(\d+a?)", out.stdout))
+    assert archs == {"100a"}, archs
+
+
+def test_no_gpu_means_loud_failure(lib_path):
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from wave_mamba_b200 import _cabi, ops, WaveMambaNativeError
+    lib = _cabi.load()
+    assert lib.wm_device_check() == -3
+    assert b"no CPU fallback" in lib.wm_last_error()
+    with pytest.raises(WaveMambaNativeError):
+        ops.dwt_haar(torch.randn(1, 1, 4, 4))
+
+
+def test_size_queries_need_no_gpu(lib_path):
+    from wave_mamba_b200 import _cabi
+    lib = _cabi.load()
+    assert lib.wm_ss2d_core_workspace_bytes(0, 8, 8) == 0
+    n = lib.wm_ss2d_core_workspace_bytes(1, 1080, 1920)
+    plane = 64 * 1080 * 1920 * 4
+    assert plane < n < 2 * plane  # tmp plane + chunk aggregates, well under 2x the activation
+    assert lib.wm_ss2d_core_workspace_bytes(2, 135, 240) > 2 * 64 * 135 * 240 * 4
+
+
+@pytest.mark.parametrize("ckpt", ["LOLv1", "UHDLL", "UHDLOL4K"])
+def test_shipped_checkpoints_load_strict(ckpt):
+    import wave_mamba_b200 as wm
+    net = wm.WaveMamba(in_chn=3, wf=32, n_l_blocks=[1, 2, 4], n_h_blocks=[1, 1, 2], ffn_scale=2.0,
+                       some_ignored_yaml_key=1)
+    sd = load_params(ckpt)
+    assert len(sd) == 591
+    res = net.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert sum(p.numel() for p in net.parameters()) == 1512718
+    assert all(k.startswith("restoration_network.") for k in net.state_dict())
+    ss = net.restoration_network.down_group1.l_blk[0].self_attention
+    assert getattr(ss.A_logs, "_no_weight_decay", False) and getattr(ss.Ds, "_no_weight_decay", False)
+
+
+def test_cpu_forward_raises_instead_of_falling_back():
+    import wave_mamba_b200 as wm
+    net = wm.WaveMamba(in_chn=3, wf=32, n_l_blocks=[1, 1, 1], n_h_blocks=[1, 1, 1]).eval()
+    with pytest.raises(wm.WaveMambaNativeError):
+        net(torch.rand(1, 3, 16, 16))
+
+
+def test_unsupported_width_is_rejected():
+    import wave_mamba_b200 as wm
+    with pytest.raises(NotImplementedError):
+        wm.WaveMamba(in_chn=3, wf=48)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "wave_mamba_b200")
+    for path in glob.glob(os.path.join(pkg, "**", "*.py"), recursive=True) + \
+            glob.glob(os.path.join(ROOT, "plugin", "**", "*.py"), recursive=True):
+        src = open(path).read()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), path
+        assert "/root/reference" not in src, path
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/basicsr"), reason="reference tree not mounted")
+def test_plugin_overlays_the_reference_registry(tmp_path):
+    """Overlay plugin/basicsr/archs/wavemamba_arch.py on a (symlinked) reference checkout and
+    build the network through the reference's own build_network / ARCH_REGISTRY."""
+    ref = "/root/reference"
+    over = tmp_path / "overlay"
+    (over / "basicsr" / "archs").mkdir(parents=True)
+    for entry in os.listdir(f"{ref}/basicsr"):
+        if entry not in ("archs", "__pycache__"):
+            os.symlink(f"{ref}/basicsr/{entry}", over / "basicsr" / entry)
+    for entry in os.listdir(f"{ref}/basicsr/archs"):
+        if entry not in ("wavemamba_arch.py", "__pycache__"):
+            os.symlink(f"{ref}/basicsr/archs/{entry}", over / "basicsr" / "archs" / entry)
+    os.symlink(os.path.join(ROOT, "plugin", "basicsr", "archs", "wavemamba_arch.py"),
+               over / "basicsr" / "archs" / "wavemamba_arch.py")
+    code = f"""
+import sys
+sys.path.insert(0, {str(ROOT)!r})
+from tools import ref_shims
+ref_shims.install({str(over)!r})
+import torch
+from basicsr.archs import build_network
+from basicsr.utils.registry import ARCH_REGISTRY
+opt = dict(type='WaveMamba', in_chn=3, wf=32, n_l_blocks=[1,2,4], n_h_blocks=[1,1,2], ffn_scale=2.0)
+net = build_network(opt)
+assert type(net).__mro__[1].__module__ == 'wave_mamba_b200.arch', type(net).__mro__
+from basicsr.archs.wavemamba_arch import WaveMamba
+assert ARCH_REGISTRY.get('WaveMamba') is WaveMamba
+sd = torch.load({os.path.join(ROOT, 'ckpt', 'WaveMamba_LOLv1.pth')!r}, map_location='cpu')['params']
+print(net.load_state_dict(sd, strict=True))
+"""
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "All keys matched" in out.stdout

@@ -1,0 +1,253 @@
+"""GPU parity tests: every kernel is called through the C ABI (wave_mamba_b200.ops -> ctypes ->
+libwavemamba_b200.so) and compared with the CPU oracle on the same seeded inputs.
+
+Tolerances (stated per test):
+  * DWT / IWT: bit-exact.
+  * SS2D core: |gpu - fp64 arbiter| <= 2e-5 * max(1, max|y|)  (fp32 recurrence; the CPU fp32
+    oracle itself sits at ~1e-6 from the arbiter; the GPU uses ex2.approx and a chunked carry).
+  * pointwise / depthwise groups: 2e-5 absolute on O(1) activations (different FMA order).
+"""
+import ctypes
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+from oracle import model as om  # noqa: E402
+from oracle import scan as oscan  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def ops(dev):
+    from wave_mamba_b200 import ops as _ops
+    return _ops
+
+
+# ------------------------------------------------------------------------------- DWT / IWT
+@pytest.mark.parametrize("shape", [(2, 5, 6, 10), (1, 3, 16, 24), (2, 32, 40, 64), (1, 7, 2, 2),
+                                   (1, 32, 270, 480), (3, 4, 10, 14)])
+def test_dwt_bit_exact(ops, dev, shape):
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(*shape, generator=g)
+    want = om.haar_dwt(x)
+    got = ops.dwt_haar(x.to(dev))
+    for a, b, name in zip(got, want, ("ll", "hl", "lh", "hh")):
+        assert torch.equal(a.cpu(), b), name
+
+
+def test_dwt_golden(ops, dev):
+    g = load_golden("dwt")
+    got = ops.dwt_haar(g["x"].to(dev))
+    for a, key in zip(got, ("ll", "hl", "lh", "hh")):
+        assert torch.equal(a.cpu(), g[key])
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 3, 7), (1, 32, 20, 32), (2, 8, 5, 12), (1, 1, 1, 1),
+                                   (1, 32, 135, 240)])
+def test_iwt_bit_exact(ops, dev, shape):
+    B, C, h, w = shape
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(B, 4 * C, h, w, generator=g)
+    want = om.haar_iwt(x)
+    assert torch.equal(ops.iwt_haar_cat(x.to(dev)).cpu(), want)
+    low, high = x[:, :C].contiguous(), x[:, C:].contiguous()
+    assert torch.equal(ops.iwt_haar(low.to(dev), high.to(dev)).cpu(), want)
+
+
+def test_iwt_golden(ops, dev):
+    g = load_golden("iwt")
+    assert torch.equal(ops.iwt_haar_cat(g["x"].to(dev)).cpu(), g["y"])
+
+
+def test_dwt_iwt_round_trip_full_4k_level1(ops, dev):
+    """Size-independent property at BASELINE.json's full size: IWT(DWT(x)) == x (to rounding)."""
+    x = torch.randn(1, 32, 2160, 3840, device=dev)
+    ll, hl, lh, hh = ops.dwt_haar(x)
+    back = ops.iwt_haar(ll, torch.cat([hl, lh, hh], dim=1))
+    assert (back - x).abs().max().item() <= 1e-6 * max(1.0, x.abs().max().item())
+    # energy preservation (orthonormal transform)
+    e_in = x.double().pow(2).sum()
+    e_out = sum(t.double().pow(2).sum() for t in (ll, hl, lh, hh))
+    assert abs((e_out / e_in).item() - 1.0) < 1e-6
+
+
+def test_empty_inputs_are_noops(ops, dev):
+    x = torch.empty(0, 4, 8, 8, device=dev)
+    assert ops.dwt_haar(x)[0].shape == (0, 4, 4, 4)
+
+
+# ------------------------------------------------------------------------------- SS2D core
+def _ss_params(params_cache, ckpt="UHDLOL4K", block="down_group1.l_blk.0"):
+    p = om.sub(om.strip_prefix(params_cache(ckpt)), block + ".self_attention")
+    return [p[k] for k in ("x_proj_weight", "dt_projs_weight", "dt_projs_bias", "A_logs", "Ds")]
+
+
+def _arbiter(x, prm):
+    """fp64 evaluation of the whole core (projections and recurrence in double)."""
+    return om.ss2d_core(x.double(), *[t.double() for t in prm], scan_fn=oscan.selective_scan_c)
+
+
+@pytest.mark.parametrize("shape", [(1, 64, 6, 10), (2, 64, 9, 5), (1, 64, 40, 56), (1, 64, 50, 75),
+                                   (2, 64, 33, 64), (1, 64, 135, 240), (1, 64, 1, 1), (1, 64, 3, 130)])
+def test_ss2d_core_vs_oracle(ops, dev, params_cache, shape):
+    g = torch.Generator().manual_seed(0)
+    x = F.silu(0.5 * torch.randn(*shape, generator=g))
+    prm = _ss_params(params_cache)
+    want64 = _arbiter(x, prm)
+    want32 = om.ss2d_core(x, *prm)
+    got = ops.ss2d_core(x.to(dev), *[t.to(dev) for t in prm]).cpu()
+    scale = max(1.0, want64.abs().max().item())
+    err_gpu = (got.double() - want64).abs().max().item()
+    err_cpu = (want32.double() - want64).abs().max().item()
+    print(f"{shape}: gpu-vs-f64 {err_gpu:.2e}  cpu32-vs-f64 {err_cpu:.2e}  scale {scale:.2f}")
+    assert err_gpu <= 2e-5 * scale
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_ss2d_core_golden(ops, dev, params_cache, tag):
+    g = load_golden(f"ss2d_core_{tag}")
+    prm = _ss_params(params_cache, g["ckpt"], g["block"])
+    got = ops.ss2d_core(g["x"].to(dev), *[t.to(dev) for t in prm]).cpu()
+    torch.testing.assert_close(got, g["y"], rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("ckpt,block", [("LOLv1", "down_group3.l_blk.3"), ("UHDLL", "up_group2.l_blk.1")])
+def test_ss2d_core_other_checkpoints(ops, dev, params_cache, ckpt, block):
+    g = torch.Generator().manual_seed(5)
+    x = F.silu(0.7 * torch.randn(1, 64, 24, 40, generator=g))
+    prm = _ss_params(params_cache, ckpt, block)
+    want64 = _arbiter(x, prm)
+    got = ops.ss2d_core(x.to(dev), *[t.to(dev) for t in prm]).cpu()
+    assert (got.double() - want64).abs().max().item() <= 2e-5 * max(1.0, want64.abs().max().item())
+
+
+def test_ss2d_core_is_deterministic(ops, dev, params_cache):
+    x = F.silu(torch.randn(2, 64, 48, 72, device=dev))
+    prm = [t.to(dev) for t in _ss_params(params_cache)]
+    a = ops.ss2d_core(x, *prm)
+    b = ops.ss2d_core(x, *prm)
+    assert torch.equal(a, b)
+
+
+def test_ss2d_core_symmetries_at_full_4k_level1_size(ops, dev, params_cache):
+    """Size-independent properties on the full (1,64,1080,1920) map: with the four directions
+    sharing one weight set, the operator commutes with a 180-degree rotation (dir0<->dir2,
+    dir1<->dir3) and with a transpose (dir0<->dir1, dir2<->dir3)."""
+    xp, dw, db, al, ds = [t.to(dev) for t in _ss_params(params_cache)]
+    xp = xp[:1].repeat(4, 1, 1).contiguous()
+    dw = dw[:1].repeat(4, 1, 1).contiguous()
+    db = db[:1].repeat(4, 1).contiguous()
+    al = al[:64].repeat(4, 1).contiguous()
+    ds = ds[:64].repeat(4).contiguous()
+    x = F.silu(0.5 * torch.randn(1, 64, 1080, 1920, device=dev))
+    y = ops.ss2d_core(x, xp, dw, db, al, ds)
+    assert torch.isfinite(y).all()
+    y_rot = ops.ss2d_core(x.flip(2, 3).contiguous(), xp, dw, db, al, ds).flip(2, 3)
+    y_tr = ops.ss2d_core(x.transpose(2, 3).contiguous(), xp, dw, db, al, ds).transpose(2, 3)
+    scale = y.abs().max().item()
+    assert (y - y_rot).abs().max().item() <= 2e-5 * scale
+    assert (y - y_tr).abs().max().item() <= 2e-5 * scale
+
+
+# ------------------------------------------------------------------------------- pointwise / depthwise
+def _rand(*shape, g, s=1.0):
+    return s * torch.randn(*shape, generator=g)
+
+
+@pytest.mark.parametrize("cout", [32, 64, 96])
+@pytest.mark.parametrize("use_ln", [False, True])
+@pytest.mark.parametrize("hw", [(13, 37), (8, 32), (24, 70)])
+def test_pw_dw(ops, dev, cout, use_ln, hw):
+    g = torch.Generator().manual_seed(7)
+    h, w = hw
+    x = _rand(2, 32, h, w, g=g)
+    pw_w, pw_b = _rand(cout, 32, 1, 1, g=g, s=0.2), _rand(cout, g=g, s=0.1)
+    dw_w, dw_b = _rand(cout, 1, 3, 3, g=g, s=0.3), _rand(cout, g=g, s=0.1)
+    ln_w, ln_b = (1 + _rand(32, g=g, s=0.1), _rand(32, g=g, s=0.1)) if use_ln else (None, None)
+    t = om.layer_norm_2d(x, ln_w, ln_b, 1e-6) if use_ln else x
+    want = F.conv2d(F.conv2d(t, pw_w, pw_b), dw_w, dw_b, padding=1, groups=cout)
+    d = lambda v: None if v is None else v.to(dev)
+    got = ops.pw_dw(d(x), d(pw_w), d(pw_b), d(dw_w), d(dw_b), d(ln_w), d(ln_b), 1e-6).cpu()
+    torch.testing.assert_close(got, want, rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("hw", [(13, 37), (16, 64)])
+@pytest.mark.parametrize("with_res", [False, True])
+def test_dw_act_pw(ops, dev, hw, with_res):
+    g = torch.Generator().manual_seed(8)
+    h, w = hw
+    x = _rand(2, 32, h, w, g=g)
+    dw_w, dw_b = _rand(32, 1, 3, 3, g=g, s=0.3), _rand(32, g=g, s=0.1)
+    pw_w, pw_b = _rand(32, 32, 1, 1, g=g, s=0.2), _rand(32, g=g, s=0.1)
+    res = _rand(2, 32, h, w, g=g) if with_res else None
+    want = F.conv2d(F.gelu(F.conv2d(x, dw_w, dw_b, padding=1, groups=32)), pw_w, pw_b)
+    if with_res:
+        want = want + res
+    d = lambda v: None if v is None else v.to(dev)
+    got = ops.dw_act_pw(d(x), d(dw_w), d(dw_b), d(pw_w), d(pw_b), "gelu", d(res)).cpu()
+    torch.testing.assert_close(got, want, rtol=2e-5, atol=2e-5)
+
+
+def test_pw_plain_gate_and_residual(ops, dev):
+    g = torch.Generator().manual_seed(9)
+    d = lambda v: None if v is None else v.to(dev)
+    for cin, cout in ((32, 32), (32, 64), (64, 32)):
+        x = _rand(2, cin, 11, 29, g=g)
+        w_, b_ = _rand(cout, cin, 1, 1, g=g, s=0.2), _rand(cout, g=g, s=0.1)
+        res = _rand(2, cout, 11, 29, g=g)
+        want = F.conv2d(x, w_, b_) + res
+        torch.testing.assert_close(ops.pw(d(x), d(w_), d(b_), residual=d(res)).cpu(), want,
+                                   rtol=2e-5, atol=2e-5)
+    x = _rand(2, 64, 11, 29, g=g)
+    w_, b_ = _rand(32, 32, 1, 1, g=g, s=0.2), _rand(32, g=g, s=0.1)
+    a, b2 = x.chunk(2, dim=1)
+    want = F.conv2d(F.gelu(a) * b2, w_, b_)
+    torch.testing.assert_close(ops.pw(d(x), d(w_), d(b_), gate=True).cpu(), want, rtol=2e-5, atol=2e-5)
+
+
+def test_paconv_gate_and_layernorm2d(ops, dev):
+    g = torch.Generator().manual_seed(10)
+    x = _rand(2, 64, 9, 21, g=g)
+    k2w, k2b = _rand(64, 64, 1, 1, g=g, s=0.2), _rand(64, g=g, s=0.1)
+    k3 = _rand(2, 64, 9, 21, g=g)
+    want = k3 * torch.sigmoid(F.conv2d(x, k2w, k2b))
+    got = ops.paconv_gate(x.to(dev), k2w.to(dev), k2b.to(dev), k3.to(dev), inplace=True).cpu()
+    torch.testing.assert_close(got, want, rtol=2e-5, atol=2e-5)
+    for c in (32, 64):
+        xx = _rand(2, c, 7, 19, g=g, s=2.0)
+        w_, b_ = 1 + _rand(c, g=g, s=0.1), _rand(c, g=g, s=0.1)
+        torch.testing.assert_close(ops.layernorm2d(xx.to(dev), w_.to(dev), b_.to(dev), 1e-6).cpu(),
+                                   om.layer_norm_2d(xx, w_, b_, 1e-6), rtol=2e-5, atol=2e-5)
+
+
+# ------------------------------------------------------------------------------- error behaviour
+def test_cpu_tensor_raises_no_fallback(ops):
+    from wave_mamba_b200 import WaveMambaNativeError
+    with pytest.raises(WaveMambaNativeError):
+        ops.dwt_haar(torch.randn(1, 2, 4, 4))
+
+
+def test_bad_arguments_are_rejected(ops, dev):
+    with pytest.raises(ValueError):
+        ops.dwt_haar(torch.randn(1, 2, 5, 4, device=dev))
+    with pytest.raises(TypeError):
+        ops.dwt_haar(torch.randn(1, 2, 4, 4, device=dev).double())
+    from wave_mamba_b200 import _cabi
+    lib = _cabi.load()
+    x = torch.randn(1, 64, 8, 8, device=dev)
+    rc = lib.wm_ss2d_core_fwd(x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(),
+                              x.data_ptr(), x.data_ptr(), None, 0, 1, 8, 8, None)
+    assert rc == -1 and b"workspace" in lib.wm_last_error()

@@ -1,0 +1,13 @@
+"""wave_mamba_b200 -- B200-native (sm_100a) forward path for Wave-Mamba.
+
+Public surface:
+  * ``WaveMamba``  -- the reference's registry class (same constructor / state dict);
+  * ``ops``        -- tensor-level wrappers of the C ABI in include/wavemamba_b200.h;
+  * ``build``      -- compiles csrc/*.cu into libwavemamba_b200.so (nvcc, sm_100a).
+Importing the package does not need a GPU; calling any op without one raises.
+"""
+from ._cabi import WaveMambaNativeError, LIB_PATH  # noqa: F401
+from . import ops  # noqa: F401
+from .arch import WaveMamba, UNet  # noqa: F401
+
+__version__ = "0.1.0"

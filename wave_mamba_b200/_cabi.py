@@ -1,0 +1,67 @@
+"""ctypes binding of include/wavemamba_b200.h -- the stub a reference maintainer would add.
+
+The library is built in-tree by wave_mamba_b200/build.py.  There is NO fallback: if the
+shared object is missing or a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libwavemamba_b200.so")
+
+ABI_VERSION = 1
+
+# name -> (restype, argtypes); mirrors include/wavemamba_b200.h one to one
+SIGNATURES = {
+    "wm_abi_version": (c_int, []),
+    "wm_last_error": (c_char_p, []),
+    "wm_device_check": (c_int, []),
+    "wm_dwt_haar_fwd": (c_int, [c_void_p] * 5 + [c_int64] * 3 + [c_void_p]),
+    "wm_iwt_haar_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p] + [c_int64] * 4 + [c_void_p]),
+    "wm_ss2d_core_workspace_bytes": (c_size_t, [c_int64] * 3),
+    "wm_ss2d_core_fwd": (c_int, [c_void_p] * 8 + [c_size_t] + [c_int64] * 3 + [c_void_p]),
+    "wm_layernorm2d_fwd": (c_int, [c_void_p] * 3 + [c_float, c_void_p] + [c_int64] * 4 + [c_void_p]),
+    "wm_pw_dw_fwd": (c_int, [c_void_p] * 3 + [c_float] + [c_void_p] * 5 + [c_int64] * 5 + [c_void_p]),
+    "wm_dw_act_pw_fwd": (c_int, [c_void_p] * 5 + [c_int] + [c_void_p] * 2 + [c_int64] * 4 + [c_void_p]),
+    "wm_pw_fwd": (c_int, [c_void_p] * 3 + [c_int] + [c_void_p] * 2 + [c_int64] * 5 + [c_void_p]),
+    "wm_paconv_gate_fwd": (c_int, [c_void_p] * 5 + [c_int64] * 4 + [c_void_p]),
+}
+
+
+class WaveMambaNativeError(RuntimeError):
+    """Raised when the CUDA library is missing or one of its entry points fails."""
+
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise WaveMambaNativeError(
+            f"{LIB_PATH} is missing. Build it with `python -m wave_mamba_b200.build` "
+            "(needs nvcc). wave_mamba_b200 has no CPU or PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as exc:
+            raise WaveMambaNativeError(f"{LIB_PATH} does not export {name}; rebuild it") from exc
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if lib.wm_abi_version() != ABI_VERSION:
+        raise WaveMambaNativeError(
+            f"ABI mismatch: library {lib.wm_abi_version()} vs binding {ABI_VERSION}; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().wm_last_error()
+        raise WaveMambaNativeError(f"{what} failed ({rc}): {msg.decode() if msg else 'unknown'}")

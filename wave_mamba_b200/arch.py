@@ -1,0 +1,406 @@
+"""Host-side mirror of the reference's Wave-Mamba arch interface, driving the sm_100a kernels.
+
+Drop-in contract (reference basicsr/archs/wavemamba_arch.py:1066-1176):
+  * ``WaveMamba(*, in_chn, wf, n_l_blocks, n_h_blocks, ffn_scale, **ignored)`` with the
+    attribute ``restoration_network`` (an nn.Module called directly by inference_wavemamba.py),
+    methods ``forward / test / test_tile / encode_and_decode / check_image_size / print_network``;
+  * the parameter tree has exactly the reference's 591 state-dict keys and shapes, so the shipped
+    checkpoints load with ``strict=True``.
+
+Module classes below are parameter containers whose names reproduce that key schema; their
+forwards call ``wave_mamba_b200.ops`` (hand-written CUDA through the C ABI) for the hot path
+-- Haar DWT/IWT, the SS2D core, the HFEBlock / ffn pointwise + depthwise groups -- and library
+ops (cuDNN / cuBLAS through torch) for what SURVEY.md section 8f schedules as "next": the
+dense 3x3 convolutions, channel matching, the CxC attention and SKFF.
+
+Inference only in this round: running with autograd enabled raises (no backward kernels yet).
+There is no CPU path: tensors that are not on a CUDA device raise.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Sequence
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from ._cabi import WaveMambaNativeError
+
+__all__ = ["WaveMamba", "UNet", "DownFRG", "upFRG", "LFSSBlock", "SS2D", "HFEBlock", "SKFF",
+           "DWT", "IWT"]
+
+
+def _require_inference(module: nn.Module, t: torch.Tensor) -> None:
+    if not t.is_cuda:
+        raise WaveMambaNativeError(
+            f"input is on {t.device}: the B200 Wave-Mamba path has no CPU fallback; move the "
+            "module and its input to a CUDA device")
+    if torch.is_grad_enabled() and (module.training or t.requires_grad):
+        raise NotImplementedError(
+            "wave_mamba_b200 implements the forward (inference) path only; backward kernels for "
+            "DWT/IWT/SS2D are scheduled next (SURVEY.md 8f-3). Use .eval() / torch.no_grad().")
+
+
+# --------------------------------------------------------------------------------------
+# wavelets                                                      reference :133-148
+# --------------------------------------------------------------------------------------
+class DWT(nn.Module):
+    def forward(self, x):
+        return ops.dwt_haar(x.contiguous())
+
+
+class IWT(nn.Module):
+    """Accepts the reference's concatenated (B,4C,h,w) tensor, or (low, high) without a cat."""
+
+    def forward(self, x, high=None):
+        if high is None:
+            return ops.iwt_haar_cat(x.contiguous())
+        return ops.iwt_haar(x.contiguous(), high.contiguous())
+
+
+# --------------------------------------------------------------------------------------
+# low-frequency branch                                          reference :214-231,316-528
+# --------------------------------------------------------------------------------------
+class _FFN(nn.Module):
+    """reference ``ffn`` (:214-231): 1x1 C->2C, dw3x3, gelu(x1)*x2, 1x1 C->C."""
+
+    def __init__(self, num_feat: int, ffn_expand: int = 2):
+        super().__init__()
+        mid = num_feat * ffn_expand
+        self.conv1 = nn.Conv2d(num_feat, mid, 1)
+        self.conv2 = nn.Conv2d(mid, mid, 3, padding=1, groups=mid)
+        self.conv3 = nn.Conv2d(mid // 2, num_feat, 1)
+
+    def forward(self, x, ln_w=None, ln_b=None, eps=1e-5):
+        t = ops.pw_dw(x, self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias,
+                      ln_w, ln_b, eps)
+        return ops.pw(t, self.conv3.weight, self.conv3.bias, gate=True)
+
+
+class SS2D(nn.Module):
+    """reference ``SS2D`` (:316-497).  Parameters and their initialisation follow :345-387."""
+
+    def __init__(self, d_model: int, d_state: int = 16, d_conv: int = 3, expand: float = 2.0,
+                 dt_min: float = 0.001, dt_max: float = 0.1, dt_scale: float = 1.0,
+                 dt_init_floor: float = 1e-4, **_unused):
+        super().__init__()
+        self.d_model, self.d_state = d_model, d_state
+        self.d_inner = int(expand * d_model)
+        self.dt_rank = math.ceil(d_model / 16)
+        D, R, N, K = self.d_inner, self.dt_rank, d_state, 4
+
+        self.in_proj = nn.Linear(d_model, 2 * D, bias=False)
+        self.conv2d = nn.Conv2d(D, D, d_conv, padding=(d_conv - 1) // 2, groups=D, bias=True)
+
+        bound = 1.0 / math.sqrt(D)  # nn.Linear default init of the four x_proj layers (:357-363)
+        self.x_proj_weight = nn.Parameter(torch.empty(K, R + 2 * N, D).uniform_(-bound, bound))
+        std = R ** -0.5 * dt_scale  # :395-399
+        self.dt_projs_weight = nn.Parameter(torch.empty(K, D, R).uniform_(-std, std))
+        dt = torch.exp(torch.rand(K, D) * (math.log(dt_max) - math.log(dt_min))
+                       + math.log(dt_min)).clamp(min=dt_init_floor)        # :404-407
+        self.dt_projs_bias = nn.Parameter(dt + torch.log(-torch.expm1(-dt)))  # inverse softplus :409
+        a = torch.arange(1, N + 1, dtype=torch.float32).log()               # S4D-real :420-425
+        self.A_logs = nn.Parameter(a.repeat(K * D, 1))
+        self.Ds = nn.Parameter(torch.ones(K * D))
+        self.A_logs._no_weight_decay = True
+        self.Ds._no_weight_decay = True
+
+        self.out_norm = nn.LayerNorm(D)
+        self.out_proj = nn.Linear(D, d_model, bias=False)
+
+    def forward_core(self, x: torch.Tensor) -> torch.Tensor:
+        """(B,D,h,w) -> merged (B,D,h,w): reference forward_core + y1+y2+y3+y4 (:446-478,490)."""
+        return ops.ss2d_core(x.contiguous(), self.x_proj_weight, self.dt_projs_weight,
+                             self.dt_projs_bias, self.A_logs, self.Ds)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """x (B,h,w,C) channels-last, as the reference (:480-497)."""
+        xz = self.in_proj(x)
+        xp, z = xz.chunk(2, dim=-1)
+        xc = xp.permute(0, 3, 1, 2).contiguous()
+        xc = F.silu(F.conv2d(xc, self.conv2d.weight, self.conv2d.bias, padding=1,
+                             groups=self.d_inner))
+        y = self.forward_core(xc)
+        y = y.permute(0, 2, 3, 1)
+        y = F.layer_norm(y, (self.d_inner,), self.out_norm.weight, self.out_norm.bias, 1e-5)
+        return self.out_proj(y * F.silu(z))
+
+
+class LFSSBlock(nn.Module):
+    """reference ``LFSSBlock`` (:499-528); input/output (B, h*w, C) like the reference."""
+
+    def __init__(self, hidden_dim: int, d_state: int = 16, expand: float = 2.0, **_unused):
+        super().__init__()
+        self.ln_1 = nn.LayerNorm(hidden_dim, eps=1e-6)
+        self.self_attention = SS2D(d_model=hidden_dim, d_state=d_state, expand=expand)
+        self.skip_scale = nn.Parameter(torch.ones(hidden_dim))
+        self.conv_blk = _FFN(hidden_dim)
+        self.ln_2 = nn.LayerNorm(hidden_dim)
+        self.skip_scale2 = nn.Parameter(torch.ones(hidden_dim))
+
+    def forward(self, inp: torch.Tensor, x_size: Sequence[int]) -> torch.Tensor:
+        B, L, C = inp.shape
+        x = inp.view(B, x_size[0], x_size[1], C)
+        t = F.layer_norm(x, (C,), self.ln_1.weight, self.ln_1.bias, 1e-6)
+        x = x * self.skip_scale + self.self_attention(t)
+        # ln_2 (eps 1e-5, :516) is fused into the ffn's first kernel (LayerNorm over channels)
+        f = self.conv_blk(x.permute(0, 3, 1, 2).contiguous(), self.ln_2.weight, self.ln_2.bias, 1e-5)
+        x = x * self.skip_scale2 + f.permute(0, 2, 3, 1)
+        return x.reshape(B, L, C)
+
+
+# --------------------------------------------------------------------------------------
+# high-frequency branch                                         reference :560-854
+# --------------------------------------------------------------------------------------
+class LayerNorm2d(nn.Module):
+    def __init__(self, channels: int, eps: float = 1e-6):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(channels))
+        self.bias = nn.Parameter(torch.zeros(channels))
+        self.eps = eps
+
+    def forward(self, x):
+        return ops.layernorm2d(x.contiguous(), self.weight, self.bias, self.eps)
+
+
+class PAConv(nn.Module):
+    def __init__(self, nf: int):
+        super().__init__()
+        self.k2 = nn.Conv2d(nf, nf, 1)
+        self.k3 = nn.Conv2d(nf, nf, 3, padding=1, bias=False)
+        self.k4 = nn.Conv2d(nf, nf // 2, 3, padding=1, bias=False)
+
+    def forward(self, x):
+        t = F.conv2d(x, self.k3.weight, None, padding=1)                    # dense 3x3: cuDNN ("next")
+        t = ops.paconv_gate(x, self.k2.weight, self.k2.bias, t, inplace=True)
+        return F.conv2d(t, self.k4.weight, None, padding=1)
+
+
+def nearest_channel_index(x: torch.Tensor, perception: torch.Tensor) -> torch.Tensor:
+    """reference Matching (:618-680) with match_factor=1: argmin over candidate channel maps of
+    the L2 distance between whole maps.  Same ``torch.cdist`` call as the reference."""
+    dist = torch.cdist(x.flatten(2, 3), perception.flatten(2, 3))
+    return dist.topk(k=1, largest=False).indices.squeeze(-1)
+
+
+class Matching_transformation(nn.Module):
+    def __init__(self, dim: int):
+        super().__init__()
+        self.paconv = PAConv(dim * 2)
+        self.last_index = None  # kept for parity tests (argmin indices)
+
+    def forward(self, x, perception):
+        B, C, h, w = x.shape
+        idx = nearest_channel_index(x, perception)
+        self.last_index = idx
+        cat = torch.empty(B, 2 * C, h, w, device=x.device, dtype=x.dtype)
+        cat[:, :C] = x
+        picked = torch.gather(perception.flatten(2, 3), 1, idx[:, :, None].expand(-1, -1, h * w))
+        cat[:, C:] = picked.view(B, C, h, w)
+        return self.paconv(cat)
+
+
+class FeedForward(nn.Module):
+    def __init__(self, dim: int):
+        super().__init__()
+        self.project_in = nn.Sequential(nn.Conv2d(dim, dim, 1), nn.Conv2d(dim, dim, 3, padding=1, groups=dim))
+        self.matching_transformation = Matching_transformation(dim)
+        self.project_out = nn.Sequential(nn.Conv2d(dim, dim, 3, padding=1, groups=dim), nn.GELU(),
+                                         nn.Conv2d(dim, dim, 1))
+
+    def forward(self, x, perception, norm: LayerNorm2d, residual):
+        pi0, pi1 = self.project_in[0], self.project_in[1]
+        t = ops.pw_dw(x, pi0.weight, pi0.bias, pi1.weight, pi1.bias, norm.weight, norm.bias, norm.eps)
+        t = self.matching_transformation(t, perception)
+        po0, po2 = self.project_out[0], self.project_out[2]
+        return ops.dw_act_pw(t, po0.weight, po0.bias, po2.weight, po2.bias, "gelu", residual)
+
+
+class CMTAttention(nn.Module):
+    def __init__(self, dim: int, num_heads: int = 1):
+        super().__init__()
+        if num_heads != 1:
+            raise NotImplementedError("Wave-Mamba uses a single head")
+        self.temperature = nn.Parameter(torch.ones(num_heads, 1, 1))
+        self.qkv = nn.Conv2d(dim, dim * 3, 1)
+        self.qkv_dwconv = nn.Conv2d(dim * 3, dim * 3, 3, padding=1, groups=dim * 3)
+        self.project_out = nn.Conv2d(dim, dim, 1)
+        self.matching_transformation = Matching_transformation(dim)
+
+    def forward(self, x, perception, norm: LayerNorm2d, residual):
+        B, C, h, w = x.shape
+        qkv = ops.pw_dw(x, self.qkv.weight, self.qkv.bias, self.qkv_dwconv.weight,
+                        self.qkv_dwconv.bias, norm.weight, norm.bias, norm.eps)
+        q, k, v = qkv.chunk(3, dim=1)
+        q = self.matching_transformation(q, perception)
+        q = F.normalize(q.flatten(2, 3), dim=-1)
+        k = F.normalize(k.flatten(2, 3), dim=-1)
+        attn = ((q @ k.transpose(-2, -1)) * self.temperature).softmax(dim=-1)
+        out = (attn @ v.flatten(2, 3)).view(B, C, h, w)
+        return ops.pw(out, self.project_out.weight, self.project_out.bias, residual=residual)
+
+
+class HFEBlock(nn.Module):
+    def __init__(self, dim: int, **_unused):
+        super().__init__()
+        self.norm1 = LayerNorm2d(dim)
+        self.attn = CMTAttention(dim)
+        self.norm2 = LayerNorm2d(dim)
+        self.ffn = FeedForward(dim)
+        self.LayerNorm = LayerNorm2d(dim)
+
+    def forward(self, x, perception):
+        x = x.contiguous()
+        per = self.LayerNorm(perception)
+        x = self.attn(x, per, self.norm1, x)      # x + attn(norm1(x), per)   (:849)
+        x = self.ffn(x, per, self.norm2, x)       # x + ffn(norm2(x), per)    (:851)
+        return x
+
+
+class SKFF(nn.Module):
+    """reference :923-959; library ops for now (fusion with the DWT epilogue is 8f-4)."""
+
+    def __init__(self, in_channels: int, height: int = 3, reduction: int = 8):
+        super().__init__()
+        d = max(int(in_channels / reduction), 4)
+        self.conv_du = nn.Sequential(nn.Conv2d(in_channels, d, 1, bias=False), nn.PReLU())
+        self.fcs = nn.ModuleList([nn.Conv2d(d, in_channels, 1, bias=False) for _ in range(height)])
+
+    def forward(self, feats: List[torch.Tensor]):
+        pooled = (feats[0] + feats[1] + feats[2]).mean(dim=(2, 3), keepdim=True)
+        z = self.conv_du(pooled)
+        att = torch.stack([fc(z) for fc in self.fcs], dim=1).softmax(dim=1)
+        return feats[0] * att[:, 0] + feats[1] * att[:, 1] + feats[2] * att[:, 2]
+
+
+# --------------------------------------------------------------------------------------
+# groups and the network                                        reference :962-1176
+# --------------------------------------------------------------------------------------
+def _run_low(blocks, x):
+    B, C, h, w = x.shape
+    t = x.permute(0, 2, 3, 1).reshape(B, h * w, C)
+    for blk in blocks:
+        t = blk(t, [h, w])
+    return t.view(B, h, w, C).permute(0, 3, 1, 2).contiguous()
+
+
+class DownFRG(nn.Module):
+    def __init__(self, dim, n_l_blocks=1, n_h_blocks=1, expand=2):
+        super().__init__()
+        self.dwt = DWT()
+        self.l_conv = nn.Conv2d(dim * 2, dim, 3, 1, 1)
+        self.l_blk = nn.Sequential(*[LFSSBlock(dim, expand=expand) for _ in range(n_l_blocks)])
+        self.h_fusion = SKFF(dim, height=3, reduction=8)
+        self.h_blk = nn.Sequential(*[HFEBlock(dim) for _ in range(n_h_blocks)])
+
+    def forward(self, x, x_d):
+        ll, hl, lh, hh = self.dwt(x)
+        low = self.l_conv(torch.cat([ll, x_d], dim=1))
+        low = _run_low(self.l_blk, low)
+        high = self.h_fusion([hl, lh, hh])
+        for blk in self.h_blk:
+            high = blk(high, low)
+        return low, high
+
+
+class upFRG(nn.Module):
+    def __init__(self, dim, n_l_blocks=1, n_h_blocks=1, expand=2):
+        super().__init__()
+        self.iwt = IWT()
+        self.l_blk = nn.Sequential(*[LFSSBlock(dim, expand=expand) for _ in range(n_l_blocks)])
+        self.h_out_conv = nn.Conv2d(dim, dim * 3, 3, 1, 1)
+        self.h_blk = nn.Sequential(*[HFEBlock(dim) for _ in range(n_h_blocks)])
+
+    def forward(self, x_l, x_h):
+        x_l = _run_low(self.l_blk, x_l)
+        for blk in self.h_blk:
+            x_h = blk(x_h, x_l)
+        x_h = self.h_out_conv(x_h)
+        return self.iwt(x_l, x_h)  # IWT of cat([x_l, x_h]) without the cat (:1006)
+
+
+class UNet(nn.Module):
+    def __init__(self, in_chn=3, wf=48, n_l_blocks=(1, 1, 2), n_h_blocks=(1, 1, 1), ffn_scale=2):
+        super().__init__()
+        if wf != 32 or float(ffn_scale) != 2.0:
+            raise NotImplementedError(
+                "the sm_100a kernels are specialised for wf=32, ffn_scale=2 (d_inner=64), the "
+                "configuration of every shipped checkpoint and YAML")
+        for lvl, r in ((1, 2), (2, 4), (3, 8)):
+            setattr(self, f"ps_down{lvl}", nn.Sequential(nn.PixelUnshuffle(r),
+                                                          nn.Conv2d(r * r * in_chn, wf, 1, 1, 0)))
+        self.conv_01 = nn.Conv2d(in_chn, wf, 3, 1, 1)
+        for i in range(3):
+            setattr(self, f"down_group{i + 1}", DownFRG(wf, n_l_blocks[i], n_h_blocks[i], ffn_scale))
+        for i in (2, 1, 0):
+            setattr(self, f"up_group{i + 1}", upFRG(wf, n_l_blocks[i], n_h_blocks[i], ffn_scale))
+        self.last = nn.Conv2d(wf, in_chn, 3, 1, 1, bias=True)
+
+    def forward(self, x):
+        _require_inference(self, x)
+        if x.dtype != torch.float32:
+            raise TypeError(f"expected a float32 image tensor, got {x.dtype}")
+        if x.dim() != 4 or x.shape[2] % 8 or x.shape[3] % 8:
+            raise ValueError(f"input must be (B,C,H,W) with H and W multiples of 8, got {tuple(x.shape)}")
+        with torch.no_grad():
+            x = x.contiguous()
+            side = [getattr(self, f"ps_down{l}")(x) for l in (1, 2, 3)]
+            t = self.conv_01(x)
+            low, h1 = self.down_group1(t, side[0])
+            low, h2 = self.down_group2(low, side[1])
+            low, h3 = self.down_group3(low, side[2])
+            low = self.up_group3(low, h3)
+            low = self.up_group2(low, h2)
+            low = self.up_group1(low, h1)
+            return self.last(low) + x
+
+
+class WaveMamba(nn.Module):
+    """Registry class; basicsr/archs/wavemamba_arch.py in plugin/ registers it in ARCH_REGISTRY."""
+
+    def __init__(self, *, in_chn, wf, n_l_blocks=[1, 1, 2], n_h_blocks=[1, 1, 1], ffn_scale=2.0,
+                 **ignore_kwargs):
+        super().__init__()
+        self.restoration_network = UNet(in_chn=in_chn, wf=wf, n_l_blocks=n_l_blocks,
+                                        n_h_blocks=n_h_blocks, ffn_scale=ffn_scale)
+
+    def print_network(self, model):
+        print(model)
+        print("The number of parameters: {}".format(sum(p.numel() for p in model.parameters())))
+
+    def encode_and_decode(self, input, current_iter=None):
+        return self.restoration_network(input)
+
+    def check_image_size(self, x, window_size=8):
+        _, _, h, w = x.size()
+        pad_h = (window_size - h % window_size) % window_size
+        pad_w = (window_size - w % window_size) % window_size
+        return F.pad(x, (0, pad_w, 0, pad_h), "reflect")
+
+    @torch.no_grad()
+    def test(self, input):
+        return self.encode_and_decode(input)
+
+    @torch.no_grad()
+    def test_tile(self, input, tile_size=240, tile_pad=16):
+        """Spatial tiling (reference :1091-1151 reads an undefined ``self.scale_factor`` and
+        crashes; the enhancement network is 1:1, so the scale factor is 1 here)."""
+        B, C, H, W = input.shape
+        out = input.new_zeros(B, C, H, W)
+        for y0 in range(0, H, tile_size):
+            for x0 in range(0, W, tile_size):
+                y1, x1 = min(y0 + tile_size, H), min(x0 + tile_size, W)
+                py0, px0 = max(y0 - tile_pad, 0), max(x0 - tile_pad, 0)
+                py1, px1 = min(y1 + tile_pad, H), min(x1 + tile_pad, W)
+                tile = input[:, :, py0:py1, px0:px1]
+                th, tw = tile.shape[2:]
+                tile = F.pad(tile, (0, (8 - tw % 8) % 8, 0, (8 - th % 8) % 8), "reflect")
+                res = self.test(tile)[:, :, :th, :tw]
+                out[:, :, y0:y1, x0:x1] = res[:, :, y0 - py0:y0 - py0 + (y1 - y0),
+                                              x0 - px0:x0 - px0 + (x1 - x0)]
+        return out
+
+    def forward(self, input):
+        return self.encode_and_decode(input)

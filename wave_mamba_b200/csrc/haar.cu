@@ -1,0 +1,203 @@
+// Haar DWT / IWT for sm_100a -- one streaming pass each, HBM-bound.
+//
+// Replaces dwt_init / iwt_init (reference wavemamba_arch.py:97-130).  Algorithmic bytes per
+// call = 2 * planes * H * W * 4 (every input element read once, every output written once).
+// Arithmetic is bit-exact with the reference: the four taps are halved first (exact in
+// binary floating point) and summed in the reference's left-to-right order.
+//
+// Vector path: each thread owns a 2 x 8 input patch (two 128-bit loads per row) and emits
+// one 128-bit store per band (DWT), or the mirror image (IWT).  Loads use the read-only,
+// no-L1-allocate path; stores are evict-first.  Persistent grid-stride over
+// SMs x 8 CTAs x 256 threads keeps >= 128 KB of loads in flight per SM.
+#include "common.cuh"
+
+namespace wm {
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ void haar_analysis(float a, float b, float c, float d, float &ll,
+                                              float &hl, float &lh, float &hh)
+{
+    // a=(even row, even col) b=(odd row, even col) c=(even row, odd col) d=(odd row, odd col),
+    // all already halved.  reference :105-108
+    ll = ((a + b) + c) + d;
+    hl = (((-a) - b) + c) + d;
+    lh = (((-a) + b) - c) + d;
+    hh = ((a - b) - c) + d;
+}
+
+__global__ void __launch_bounds__(kThreads)
+dwt_vec_kernel(const float *__restrict__ x, float *__restrict__ ll, float *__restrict__ hl,
+               float *__restrict__ lh, float *__restrict__ hh, int64_t out_rows, int w4, int64_t W)
+{
+    // out_rows = planes * h ; input row index of output row r is 2r (planes are contiguous).
+    const int64_t items = out_rows * w4;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t it = (int64_t)blockIdx.x * kThreads + threadIdx.x; it < items; it += stride) {
+        const int64_t r = it / w4;
+        const int q = (int)(it - r * w4);
+        const float *top = x + (2 * r) * W + 8 * q;
+        const float4 t0 = ld_stream4(top), t1 = ld_stream4(top + 4);
+        const float4 b0 = ld_stream4(top + W), b1 = ld_stream4(top + W + 4);
+        float4 oll, ohl, olh, ohh;
+        haar_analysis(t0.x * 0.5f, b0.x * 0.5f, t0.y * 0.5f, b0.y * 0.5f, oll.x, ohl.x, olh.x, ohh.x);
+        haar_analysis(t0.z * 0.5f, b0.z * 0.5f, t0.w * 0.5f, b0.w * 0.5f, oll.y, ohl.y, olh.y, ohh.y);
+        haar_analysis(t1.x * 0.5f, b1.x * 0.5f, t1.y * 0.5f, b1.y * 0.5f, oll.z, ohl.z, olh.z, ohh.z);
+        haar_analysis(t1.z * 0.5f, b1.z * 0.5f, t1.w * 0.5f, b1.w * 0.5f, oll.w, ohl.w, olh.w, ohh.w);
+        const int64_t o = r * (4 * (int64_t)w4) + 4 * q;
+        st_stream4(ll + o, oll);
+        st_stream4(hl + o, ohl);
+        st_stream4(lh + o, olh);
+        st_stream4(hh + o, ohh);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+dwt_scalar_kernel(const float *__restrict__ x, float *__restrict__ ll, float *__restrict__ hl,
+                  float *__restrict__ lh, float *__restrict__ hh, int64_t out_rows, int64_t w,
+                  int64_t W)
+{
+    const int64_t items = out_rows * w;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t it = (int64_t)blockIdx.x * kThreads + threadIdx.x; it < items; it += stride) {
+        const int64_t r = it / w, j = it - r * w;
+        const float *top = x + (2 * r) * W + 2 * j;
+        float a = top[0] * 0.5f, c = top[1] * 0.5f, b = top[W] * 0.5f, d = top[W + 1] * 0.5f;
+        haar_analysis(a, b, c, d, ll[it], hl[it], lh[it], hh[it]);
+    }
+}
+
+__device__ __forceinline__ void haar_synthesis(float p, float q, float r, float s, float &ee,
+                                               float &oe, float &eo, float &oo)
+{
+    // p,q,r,s = LL,HL,LH,HH halved.  ee=(even row, even col) oe=(odd row, even col) ...
+    // reference :125-128
+    ee = ((p - q) - r) + s;
+    oe = ((p - q) + r) - s;
+    eo = ((p + q) - r) - s;
+    oo = ((p + q) + r) + s;
+}
+
+__global__ void __launch_bounds__(kThreads)
+iwt_vec_kernel(const float *__restrict__ low, int64_t low_bstride, const float *__restrict__ high,
+               int64_t high_bstride, float *__restrict__ y, int64_t B, int C, int h, int w4)
+{
+    const int64_t w = 4 * (int64_t)w4, hw = (int64_t)h * w;
+    const int64_t items = B * C * h * w4;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t it = (int64_t)blockIdx.x * kThreads + threadIdx.x; it < items; it += stride) {
+        int64_t t = it;
+        const int q = (int)(t % w4); t /= w4;
+        const int i = (int)(t % h);  t /= h;
+        const int c = (int)(t % C);
+        const int64_t b = t / C;
+        const int64_t in_off = (int64_t)i * w + 4 * q;
+        const float4 vp = ld_stream4(low + b * low_bstride + c * hw + in_off);
+        const float *hb = high + b * high_bstride + in_off;
+        const float4 vq = ld_stream4(hb + (int64_t)c * hw);
+        const float4 vr = ld_stream4(hb + (int64_t)(C + c) * hw);
+        const float4 vs = ld_stream4(hb + (int64_t)(2 * C + c) * hw);
+        float4 e0, e1, o0, o1;  // even output row (8 floats) / odd output row
+        haar_synthesis(vp.x * 0.5f, vq.x * 0.5f, vr.x * 0.5f, vs.x * 0.5f, e0.x, o0.x, e0.y, o0.y);
+        haar_synthesis(vp.y * 0.5f, vq.y * 0.5f, vr.y * 0.5f, vs.y * 0.5f, e0.z, o0.z, e0.w, o0.w);
+        haar_synthesis(vp.z * 0.5f, vq.z * 0.5f, vr.z * 0.5f, vs.z * 0.5f, e1.x, o1.x, e1.y, o1.y);
+        haar_synthesis(vp.w * 0.5f, vq.w * 0.5f, vr.w * 0.5f, vs.w * 0.5f, e1.z, o1.z, e1.w, o1.w);
+        float *out = y + ((b * C + c) * (2 * (int64_t)h) + 2 * i) * (2 * w) + 8 * q;
+        st_stream4(out, e0);
+        st_stream4(out + 4, e1);
+        st_stream4(out + 2 * w, o0);
+        st_stream4(out + 2 * w + 4, o1);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+iwt_scalar_kernel(const float *__restrict__ low, int64_t low_bstride,
+                  const float *__restrict__ high, int64_t high_bstride, float *__restrict__ y,
+                  int64_t B, int C, int h, int w)
+{
+    const int64_t hw = (int64_t)h * w;
+    const int64_t items = B * C * hw;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t it = (int64_t)blockIdx.x * kThreads + threadIdx.x; it < items; it += stride) {
+        int64_t t = it;
+        const int j = (int)(t % w); t /= w;
+        const int i = (int)(t % h); t /= h;
+        const int c = (int)(t % C);
+        const int64_t b = t / C;
+        const int64_t in_off = (int64_t)i * w + j;
+        const float p = low[b * low_bstride + c * hw + in_off] * 0.5f;
+        const float *hb = high + b * high_bstride + in_off;
+        const float q = hb[(int64_t)c * hw] * 0.5f;
+        const float r = hb[(int64_t)(C + c) * hw] * 0.5f;
+        const float s = hb[(int64_t)(2 * C + c) * hw] * 0.5f;
+        float ee, oe, eo, oo;
+        haar_synthesis(p, q, r, s, ee, oe, eo, oo);
+        float *out = y + ((b * C + c) * (2 * (int64_t)h) + 2 * i) * (2 * (int64_t)w) + 2 * j;
+        out[0] = ee;
+        out[1] = eo;
+        out[2 * w] = oe;
+        out[2 * w + 1] = oo;
+    }
+}
+
+inline int stream_grid(int64_t items)
+{
+    const int64_t want = (items + kThreads - 1) / kThreads;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+}  // namespace
+}  // namespace wm
+
+extern "C" int wm_dwt_haar_fwd(const float *x, float *ll, float *hl, float *lh, float *hh,
+                               int64_t planes, int64_t H, int64_t W, wm_stream_t stream)
+{
+    using namespace wm;
+    WM_REQUIRE(x && ll && hl && lh && hh, "wm_dwt_haar_fwd: null pointer");
+    WM_REQUIRE(planes >= 0 && H >= 0 && W >= 0, "wm_dwt_haar_fwd: negative size");
+    WM_REQUIRE(H % 2 == 0 && W % 2 == 0, "wm_dwt_haar_fwd: H=%lld W=%lld must be even",
+               (long long)H, (long long)W);
+    if (planes == 0 || H == 0 || W == 0) return WM_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t h = H / 2, w = W / 2, out_rows = planes * h;
+    const bool vec = (W % 8 == 0) && aligned16(x) && aligned16(ll) && aligned16(hl) &&
+                     aligned16(lh) && aligned16(hh);
+    if (vec) {
+        const int w4 = (int)(w / 4);
+        dwt_vec_kernel<<<stream_grid(out_rows * w4), kThreads, 0, s>>>(x, ll, hl, lh, hh, out_rows,
+                                                                        w4, W);
+    } else {
+        dwt_scalar_kernel<<<stream_grid(out_rows * w), kThreads, 0, s>>>(x, ll, hl, lh, hh,
+                                                                          out_rows, w, W);
+    }
+    WM_LAUNCH_OK("dwt kernel");
+    return WM_OK;
+}
+
+extern "C" int wm_iwt_haar_fwd(const float *low, int64_t low_bstride, const float *high,
+                               int64_t high_bstride, float *y, int64_t B, int64_t C, int64_t h,
+                               int64_t w, wm_stream_t stream)
+{
+    using namespace wm;
+    WM_REQUIRE(low && high && y, "wm_iwt_haar_fwd: null pointer");
+    WM_REQUIRE(B >= 0 && C >= 0 && h >= 0 && w >= 0, "wm_iwt_haar_fwd: negative size");
+    WM_REQUIRE(C < (1 << 20) && h < (1 << 30) && w < (1 << 30), "wm_iwt_haar_fwd: size too large");
+    if (B == 0 || C == 0 || h == 0 || w == 0) return WM_OK;
+    WM_REQUIRE(low_bstride >= C * h * w && high_bstride >= 3 * C * h * w,
+               "wm_iwt_haar_fwd: batch strides smaller than one sample");
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool vec = (w % 4 == 0) && aligned16(low) && aligned16(high) && aligned16(y) &&
+                     (low_bstride % 4 == 0) && (high_bstride % 4 == 0);
+    if (vec) {
+        const int w4 = (int)(w / 4);
+        iwt_vec_kernel<<<stream_grid(B * C * h * w4), kThreads, 0, s>>>(
+            low, low_bstride, high, high_bstride, y, B, (int)C, (int)h, w4);
+    } else {
+        iwt_scalar_kernel<<<stream_grid(B * C * h * w), kThreads, 0, s>>>(
+            low, low_bstride, high, high_bstride, y, B, (int)C, (int)h, (int)w);
+    }
+    WM_LAUNCH_OK("iwt kernel");
+    return WM_OK;
+}

@@ -1,0 +1,220 @@
+"""Tensor-level wrappers over the C ABI (include/wavemamba_b200.h).
+
+PyTorch is plumbing here: it owns device memory (caching allocator) and the current stream.
+Every function checks that its tensors are CUDA / float32 / contiguous and raises otherwise;
+nothing silently falls back to a PyTorch or CPU implementation.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _cabi
+
+# number of CUDA kernels this module has enqueued (bench.py reports it as gpu_launches)
+launch_count = 0
+
+
+def _count(n: int) -> None:
+    global launch_count
+    launch_count += n
+
+
+def _chk(t: torch.Tensor, name: str, shape: Optional[Tuple[int, ...]] = None) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor, got {type(t)}")
+    if not t.is_cuda:
+        raise _cabi.WaveMambaNativeError(
+            f"{name} is on {t.device}; wave_mamba_b200 runs on CUDA (sm_100a) only -- no CPU fallback")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name}: expected float32, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: expected a contiguous tensor, got strides {t.stride()}")
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(t.shape)}")
+    return t
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def dwt_haar(x: torch.Tensor):
+    """(B,C,H,W) -> LL, HL, LH, HH each (B,C,H/2,W/2).  reference dwt_init :97-110."""
+    _chk(x, "x")
+    if x.dim() != 4:
+        raise ValueError(f"x: expected 4 dims, got {x.dim()}")
+    B, C, H, W = x.shape
+    if H % 2 or W % 2:
+        raise ValueError(f"DWT needs even H and W, got {H}x{W}")
+    outs = [torch.empty(B, C, H // 2, W // 2, device=x.device, dtype=x.dtype) for _ in range(4)]
+    lib = _cabi.load()
+    with torch.cuda.device(x.device):
+        rc = lib.wm_dwt_haar_fwd(x.data_ptr(), *[o.data_ptr() for o in outs], B * C, H, W, _stream(x))
+    _cabi.check(rc, "wm_dwt_haar_fwd")
+    _count(1)
+    return tuple(outs)
+
+
+def iwt_haar(low: torch.Tensor, high: torch.Tensor) -> torch.Tensor:
+    """low (B,C,h,w) = LL, high (B,3C,h,w) = [HL|LH|HH] -> (B,C,2h,2w).
+    reference iwt_init :113-130 applied to cat([low, high], 1) (:1006), without the cat."""
+    _chk(low, "low")
+    _chk(high, "high")
+    B, C, h, w = low.shape
+    if tuple(high.shape) != (B, 3 * C, h, w):
+        raise ValueError(f"high: expected {(B, 3 * C, h, w)}, got {tuple(high.shape)}")
+    y = torch.empty(B, C, 2 * h, 2 * w, device=low.device, dtype=low.dtype)
+    lib = _cabi.load()
+    with torch.cuda.device(low.device):
+        rc = lib.wm_iwt_haar_fwd(low.data_ptr(), C * h * w, high.data_ptr(), 3 * C * h * w,
+                                 y.data_ptr(), B, C, h, w, _stream(low))
+    _cabi.check(rc, "wm_iwt_haar_fwd")
+    _count(1)
+    return y
+
+
+def iwt_haar_cat(x: torch.Tensor) -> torch.Tensor:
+    """The reference's calling convention: x = (B,4C,h,w) = [LL|HL|LH|HH]."""
+    _chk(x, "x")
+    B, C4, h, w = x.shape
+    if C4 % 4:
+        raise ValueError("IWT input channels must be a multiple of 4")
+    C = C4 // 4
+    y = torch.empty(B, C, 2 * h, 2 * w, device=x.device, dtype=x.dtype)
+    lib = _cabi.load()
+    with torch.cuda.device(x.device):
+        rc = lib.wm_iwt_haar_fwd(x.data_ptr(), C4 * h * w, x.data_ptr() + 4 * C * h * w,
+                                 C4 * h * w, y.data_ptr(), B, C, h, w, _stream(x))
+    _cabi.check(rc, "wm_iwt_haar_fwd")
+    _count(1)
+    return y
+
+
+def ss2d_core(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds) -> torch.Tensor:
+    """SS2D.forward_core + 4-way sum (reference :446-478,490).  x (B,64,h,w) -> y (B,64,h,w)."""
+    _chk(x, "x")
+    B, D, h, w = x.shape
+    if D != 64:
+        raise ValueError(f"ss2d_core supports d_inner=64 (wf=32, expand=2); got {D}")
+    _chk(x_proj_weight, "x_proj_weight", (4, 34, 64))
+    _chk(dt_projs_weight, "dt_projs_weight", (4, 64, 2))
+    _chk(dt_projs_bias, "dt_projs_bias", (4, 64))
+    _chk(A_logs, "A_logs", (256, 16))
+    _chk(Ds, "Ds", (256,))
+    lib = _cabi.load()
+    y = torch.empty_like(x)
+    nbytes = lib.wm_ss2d_core_workspace_bytes(B, h, w)
+    ws = torch.empty(max(nbytes, 256), device=x.device, dtype=torch.uint8)
+    with torch.cuda.device(x.device):
+        rc = lib.wm_ss2d_core_fwd(x.data_ptr(), x_proj_weight.data_ptr(), dt_projs_weight.data_ptr(),
+                                  dt_projs_bias.data_ptr(), A_logs.data_ptr(), Ds.data_ptr(),
+                                  y.data_ptr(), ws.data_ptr(), nbytes, B, h, w, _stream(x))
+    _cabi.check(rc, "wm_ss2d_core_fwd")
+    _count(5)
+    return y
+
+
+def layernorm2d(x, weight, bias, eps: float = 1e-6) -> torch.Tensor:
+    """LayerNorm2d (reference :535-543) on NCHW."""
+    _chk(x, "x")
+    B, C, h, w = x.shape
+    _chk(weight, "weight", (C,))
+    _chk(bias, "bias", (C,))
+    y = torch.empty_like(x)
+    lib = _cabi.load()
+    with torch.cuda.device(x.device):
+        rc = lib.wm_layernorm2d_fwd(x.data_ptr(), weight.data_ptr(), bias.data_ptr(), eps,
+                                    y.data_ptr(), B, C, h, w, _stream(x))
+    _cabi.check(rc, "wm_layernorm2d_fwd")
+    _count(1)
+    return y
+
+
+def pw_dw(x, pw_w, pw_b, dw_w, dw_b, ln_w=None, ln_b=None, eps: float = 1e-6) -> torch.Tensor:
+    """y = dw3x3(pw1x1(ln?(x))): (B,32,h,w) -> (B,Cout,h,w), Cout in {32,64,96}."""
+    _chk(x, "x")
+    B, Cin, h, w = x.shape
+    Cout = pw_w.shape[0]
+    _chk(pw_w, "pw_w", (Cout, Cin, 1, 1))
+    _chk(pw_b, "pw_b", (Cout,))
+    _chk(dw_w, "dw_w", (Cout, 1, 3, 3))
+    _chk(dw_b, "dw_b", (Cout,))
+    if ln_w is not None:
+        _chk(ln_w, "ln_w", (Cin,))
+        _chk(ln_b, "ln_b", (Cin,))
+    y = torch.empty(B, Cout, h, w, device=x.device, dtype=x.dtype)
+    lib = _cabi.load()
+    with torch.cuda.device(x.device):
+        rc = lib.wm_pw_dw_fwd(x.data_ptr(), _ptr(ln_w), _ptr(ln_b), eps, pw_w.data_ptr(),
+                              pw_b.data_ptr(), dw_w.data_ptr(), dw_b.data_ptr(), y.data_ptr(),
+                              B, Cin, Cout, h, w, _stream(x))
+    _cabi.check(rc, "wm_pw_dw_fwd")
+    _count(1)
+    return y
+
+
+def dw_act_pw(x, dw_w, dw_b, pw_w, pw_b, act: str = "gelu", residual=None) -> torch.Tensor:
+    """y = residual? + pw1x1(act(dw3x3(x))), C=32."""
+    _chk(x, "x")
+    B, C, h, w = x.shape
+    _chk(dw_w, "dw_w", (C, 1, 3, 3))
+    _chk(dw_b, "dw_b", (C,))
+    _chk(pw_w, "pw_w", (C, C, 1, 1))
+    _chk(pw_b, "pw_b", (C,))
+    if residual is not None:
+        _chk(residual, "residual", tuple(x.shape))
+    y = torch.empty_like(x)
+    lib = _cabi.load()
+    with torch.cuda.device(x.device):
+        rc = lib.wm_dw_act_pw_fwd(x.data_ptr(), dw_w.data_ptr(), dw_b.data_ptr(), pw_w.data_ptr(),
+                                  pw_b.data_ptr(), {"none": 0, "gelu": 1}[act], _ptr(residual),
+                                  y.data_ptr(), B, C, h, w, _stream(x))
+    _cabi.check(rc, "wm_dw_act_pw_fwd")
+    _count(1)
+    return y
+
+
+def pw(x, pw_w, pw_b=None, gate: bool = False, residual=None) -> torch.Tensor:
+    """y = residual? + pw1x1(x) (+bias).  gate=True: x is (B,2*Cin,h,w) and the conv sees
+    gelu(x[:, :Cin]) * x[:, Cin:]  (reference ffn :227-228)."""
+    _chk(x, "x")
+    B, Cx, h, w = x.shape
+    Cout, Cin = pw_w.shape[0], pw_w.shape[1]
+    if Cx != (2 * Cin if gate else Cin):
+        raise ValueError(f"x has {Cx} channels, weight expects {2 * Cin if gate else Cin}")
+    _chk(pw_w, "pw_w", (Cout, Cin, 1, 1))
+    if pw_b is not None:
+        _chk(pw_b, "pw_b", (Cout,))
+    if residual is not None:
+        _chk(residual, "residual", (B, Cout, h, w))
+    y = torch.empty(B, Cout, h, w, device=x.device, dtype=x.dtype)
+    lib = _cabi.load()
+    with torch.cuda.device(x.device):
+        rc = lib.wm_pw_fwd(x.data_ptr(), pw_w.data_ptr(), _ptr(pw_b), 1 if gate else 0,
+                           _ptr(residual), y.data_ptr(), B, Cin, Cout, h, w, _stream(x))
+    _cabi.check(rc, "wm_pw_fwd")
+    _count(1)
+    return y
+
+
+def paconv_gate(x, k2_w, k2_b, k3out, inplace: bool = True) -> torch.Tensor:
+    """y = k3out * sigmoid(pw1x1(x) + b)  (reference PAConv :694-697), all (B,64,h,w)."""
+    _chk(x, "x")
+    B, C, h, w = x.shape
+    _chk(k2_w, "k2_w", (C, C, 1, 1))
+    _chk(k2_b, "k2_b", (C,))
+    _chk(k3out, "k3out", tuple(x.shape))
+    y = k3out if inplace else torch.empty_like(k3out)
+    lib = _cabi.load()
+    with torch.cuda.device(x.device):
+        rc = lib.wm_paconv_gate_fwd(x.data_ptr(), k2_w.data_ptr(), k2_b.data_ptr(),
+                                    k3out.data_ptr(), y.data_ptr(), B, C, h, w, _stream(x))
+    _cabi.check(rc, "wm_paconv_gate_fwd")
+    _count(1)
+    return y
