@@ -53,6 +53,8 @@ def parse_args():
                     help="1: let cuDNN use TF32 for the dense 3x3 convs (the reference's default)")
     ap.add_argument("--ckpt", default="UHDLL")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true", help="do not spawn the nvidia-smi sampler "
+                    "(use under ncu, which waits for child processes)")
     return ap.parse_args()
 
 
@@ -145,8 +147,10 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                # `timeout` bounds the sampler's life even if this process dies before stop()
+                ["timeout", "600", "nvidia-smi", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:
@@ -310,7 +314,7 @@ def main():
         # ---- device-resident timing ------------------------------------------------------
         barrier()
         clocks = ClockSampler(local_rank)
-        if rank == 0:
+        if rank == 0 and not args.no_clocks:
             clocks.start()
         launches0 = ops.launch_count
         timer.enabled = True

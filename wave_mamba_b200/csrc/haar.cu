@@ -155,11 +155,11 @@ extern "C" int wm_dwt_haar_fwd(const float *x, float *ll, float *hl, float *lh, 
                                int64_t planes, int64_t H, int64_t W, wm_stream_t stream)
 {
     using namespace wm;
-    WM_REQUIRE(x && ll && hl && lh && hh, "wm_dwt_haar_fwd: null pointer");
     WM_REQUIRE(planes >= 0 && H >= 0 && W >= 0, "wm_dwt_haar_fwd: negative size");
     WM_REQUIRE(H % 2 == 0 && W % 2 == 0, "wm_dwt_haar_fwd: H=%lld W=%lld must be even",
                (long long)H, (long long)W);
-    if (planes == 0 || H == 0 || W == 0) return WM_OK;
+    if (planes == 0 || H == 0 || W == 0) return WM_OK;  // empty: nothing to do, pointers unused
+    WM_REQUIRE(x && ll && hl && lh && hh, "wm_dwt_haar_fwd: null pointer");
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t h = H / 2, w = W / 2, out_rows = planes * h;
     const bool vec = (W % 8 == 0) && aligned16(x) && aligned16(ll) && aligned16(hl) &&
@@ -181,10 +181,10 @@ extern "C" int wm_iwt_haar_fwd(const float *low, int64_t low_bstride, const floa
                                int64_t w, wm_stream_t stream)
 {
     using namespace wm;
-    WM_REQUIRE(low && high && y, "wm_iwt_haar_fwd: null pointer");
     WM_REQUIRE(B >= 0 && C >= 0 && h >= 0 && w >= 0, "wm_iwt_haar_fwd: negative size");
     WM_REQUIRE(C < (1 << 20) && h < (1 << 30) && w < (1 << 30), "wm_iwt_haar_fwd: size too large");
     if (B == 0 || C == 0 || h == 0 || w == 0) return WM_OK;
+    WM_REQUIRE(low && high && y, "wm_iwt_haar_fwd: null pointer");
     WM_REQUIRE(low_bstride >= C * h * w && high_bstride >= 3 * C * h * w,
                "wm_iwt_haar_fwd: batch strides smaller than one sample");
     cudaStream_t s = (cudaStream_t)stream;
