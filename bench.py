@@ -232,6 +232,8 @@ class OpTimer:
                                                                   a[6] if len(a) > 6 else None))
         wrap("pw", lambda a, k, o: nb(a[0]) + nb(o) + nb(k.get("residual")))
         wrap("paconv_gate", lambda a, k, o: nb(a[0]) + 2 * nb(o))
+        wrap("lfss_z", lambda a, k, o: nb(a[0]) + nb(o))
+        wrap("lfss_out", lambda a, k, o: nb(a[0], a[1], a[6]) + nb(o) + nb(k.get("y2")))
 
     def summary(self, peak_gbs):
         agg = {}

@@ -31,7 +31,7 @@ extern "C" {
 #define WM_ECUDA (-2)     /* a CUDA runtime call or kernel launch failed               */
 #define WM_ENODEVICE (-3) /* no sm_100-class CUDA device is current                     */
 
-#define WM_ABI_VERSION 1
+#define WM_ABI_VERSION 2
 
 typedef void *wm_stream_t;
 
@@ -82,11 +82,13 @@ int wm_ss2d_core_fwd(const float *x, const float *x_proj_weight, const float *dt
 int wm_layernorm2d_fwd(const float *x, const float *ln_w, const float *ln_b, float eps, float *y,
                        int64_t B, int64_t C, int64_t h, int64_t w, wm_stream_t stream);
 
-/* y = dw3x3( pw1x1( ln?(x) ) ) : Cin=32 -> Cout in {32,64,96}.
- * Used for qkv+qkv_dwconv (:775), FeedForward.project_in (:729-732,745), ffn.conv1+conv2 (:226). */
+/* y = act( dw3x3( pw1x1( ln?(x) ) ) ) : Cin=32 -> Cout in {32,64,96}; pw_b may be NULL;
+ * act: 0 none, 1 SiLU.
+ * Used for qkv+qkv_dwconv (:775), FeedForward.project_in (:729-732,745), ffn.conv1+conv2 (:226)
+ * and, with ln_1 + in_proj[:64] + conv2d + SiLU, the x branch of SS2D.forward (:483-487, :524). */
 int wm_pw_dw_fwd(const float *x, const float *ln_w, const float *ln_b, float eps,
                  const float *pw_w, const float *pw_b, const float *dw_w, const float *dw_b,
-                 float *y, int64_t B, int64_t Cin, int64_t Cout, int64_t h, int64_t w,
+                 int act, float *y, int64_t B, int64_t Cin, int64_t Cout, int64_t h, int64_t w,
                  wm_stream_t stream);
 
 /* y = residual? + pw1x1( act( dw3x3(x) ) ), act: 0 none, 1 exact (erf) GELU.   C=32 -> 32.
@@ -95,13 +97,27 @@ int wm_dw_act_pw_fwd(const float *x, const float *dw_w, const float *dw_b, const
                      const float *pw_b, int act, const float *residual, float *y, int64_t B,
                      int64_t C, int64_t h, int64_t w, wm_stream_t stream);
 
-/* y = residual? + pw1x1(x) + bias : Cin -> Cout, both <= 64.
+/* y = residual?*res_scale? + pw1x1(x) + bias? : Cin -> Cout, both <= 64.
  * CMTAttention.project_out (:797) fused with the HFEBlock residual add (:849);
- * also ffn.conv3 after the gate.  gate_mode 0: plain; 1: input is (B,2*Cin,h,w) and the 1x1
- * sees gelu(x[:, :Cin]) * x[:, Cin:]  (ffn gate, :227-228). */
+ * ffn.conv3 after the gate fused with `x*skip_scale2 +` (:526).  gate_mode 0: plain; 1: input is
+ * (B,2*Cin,h,w) and the 1x1 sees gelu(x[:, :Cin]) * x[:, Cin:]  (ffn gate, :227-228).
+ * res_scale: optional (Cout) per-channel multiplier of the residual. */
 int wm_pw_fwd(const float *x, const float *pw_w, const float *pw_b, int gate_mode,
-              const float *residual, float *y, int64_t B, int64_t Cin, int64_t Cout, int64_t h,
-              int64_t w, wm_stream_t stream);
+              const float *residual, const float *res_scale, float *y, int64_t B, int64_t Cin,
+              int64_t Cout, int64_t h, int64_t w, wm_stream_t stream);
+
+/* SS2D z branch: zs = silu( in_proj.weight[64:128] . LayerNorm_c(x) ), x (B,32,h,w) -> (B,64,h,w)
+ * (ln_1 :524, in_proj + chunk :483-484, F.silu(z) :493).  w_z points at row 64 of in_proj.weight. */
+int wm_lfss_z_fwd(const float *x, const float *ln_w, const float *ln_b, float eps, const float *w_z,
+                  float *zs, int64_t B, int64_t h, int64_t w, wm_stream_t stream);
+
+/* SS2D tail + LFSSBlock residual: out = x*skip_scale + out_proj( out_norm(y [+ y2]) * zs )
+ * (out_norm :492, gate :493, out_proj :494, residual :525).  y, y2 (optional second addend, e.g.
+ * the scan's column-direction plane), zs: (B,64,h,w); x, out: (B,32,h,w). */
+int wm_lfss_out_fwd(const float *y, const float *y2, const float *zs, const float *on_w,
+                    const float *on_b, float eps, const float *w_out, const float *x,
+                    const float *skip_scale, float *out, int64_t B, int64_t h, int64_t w,
+                    wm_stream_t stream);
 
 /* PAConv gate: y = k3out * sigmoid( pw1x1(x) + b ), x and k3out and y all (B,64,h,w)
  * (PAConv.k2 + sigmoid + mul, :694-697).  In-place on k3out allowed (y == k3out). */

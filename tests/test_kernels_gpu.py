@@ -251,3 +251,67 @@ def test_bad_arguments_are_rejected(ops, dev):
     rc = lib.wm_ss2d_core_fwd(x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(),
                               x.data_ptr(), x.data_ptr(), None, 0, 1, 8, 8, None)
     assert rc == -1 and b"workspace" in lib.wm_last_error()
+
+
+# ------------------------------------------------------------------------------- fused LFSS glue
+def test_pw_dw_silu_without_bias(ops, dev):
+    g = torch.Generator().manual_seed(11)
+    x = _rand(2, 32, 13, 37, g=g)
+    pw_w = _rand(64, 32, g=g, s=0.2)
+    dw_w, dw_b = _rand(64, 1, 3, 3, g=g, s=0.3), _rand(64, g=g, s=0.1)
+    ln_w, ln_b = 1 + _rand(32, g=g, s=0.1), _rand(32, g=g, s=0.1)
+    t = om.layer_norm_2d(x, ln_w, ln_b, 1e-6)
+    want = F.silu(F.conv2d(F.conv2d(t, pw_w[:, :, None, None]), dw_w, dw_b, padding=1, groups=64))
+    got = ops.pw_dw(x.to(dev), pw_w.to(dev), None, dw_w.to(dev), dw_b.to(dev), ln_w.to(dev),
+                    ln_b.to(dev), 1e-6, act="silu").cpu()
+    torch.testing.assert_close(got, want, rtol=2e-5, atol=2e-5)
+
+
+def test_lfss_z_and_out(ops, dev):
+    g = torch.Generator().manual_seed(12)
+    B, h, w = 2, 9, 23
+    x = _rand(B, 32, h, w, g=g)
+    ln_w, ln_b = 1 + _rand(32, g=g, s=0.1), _rand(32, g=g, s=0.1)
+    w_in = _rand(128, 32, g=g, s=0.2)
+    t = om.layer_norm_2d(x, ln_w, ln_b, 1e-6)
+    want_z = F.silu(F.conv2d(t, w_in[64:, :, None, None]))
+    zs = ops.lfss_z(x.to(dev), ln_w.to(dev), ln_b.to(dev), 1e-6, w_in.to(dev))
+    torch.testing.assert_close(zs.cpu(), want_z, rtol=2e-5, atol=2e-5)
+
+    y, y2 = _rand(B, 64, h, w, g=g), _rand(B, 64, h, w, g=g)
+    on_w, on_b = 1 + _rand(64, g=g, s=0.1), _rand(64, g=g, s=0.1)
+    w_out = _rand(32, 64, g=g, s=0.2)
+    skip = 1 + _rand(32, g=g, s=0.2)
+    for second in (None, y2):
+        ysum = y if second is None else y + second
+        yn = F.layer_norm(ysum.permute(0, 2, 3, 1), (64,), on_w, on_b, 1e-5)
+        want = x * skip.view(1, -1, 1, 1) + F.linear(yn * want_z.permute(0, 2, 3, 1), w_out).permute(0, 3, 1, 2)
+        got = ops.lfss_out(y.to(dev), zs, on_w.to(dev), on_b.to(dev), 1e-5, w_out.to(dev), x.to(dev),
+                           skip.to(dev), y2=None if second is None else second.to(dev)).cpu()
+        torch.testing.assert_close(got, want, rtol=3e-5, atol=3e-5)
+
+
+def test_pw_gate_with_scaled_residual(ops, dev):
+    g = torch.Generator().manual_seed(13)
+    x = _rand(2, 64, 11, 29, g=g)
+    w_, b_ = _rand(32, 32, 1, 1, g=g, s=0.2), _rand(32, g=g, s=0.1)
+    res, sc = _rand(2, 32, 11, 29, g=g), 1 + _rand(32, g=g, s=0.2)
+    a, b2 = x.chunk(2, dim=1)
+    want = res * sc.view(1, -1, 1, 1) + F.conv2d(F.gelu(a) * b2, w_, b_)
+    got = ops.pw(x.to(dev), w_.to(dev), b_.to(dev), gate=True, residual=res.to(dev),
+                 res_scale=sc.to(dev)).cpu()
+    torch.testing.assert_close(got, want, rtol=2e-5, atol=2e-5)
+
+
+def test_lfss_block_fused_path_vs_golden_and_oracle(dev, params_cache):
+    """LFSSBlock through the reference calling convention (B, L, C) -> fused NCHW kernels."""
+    import wave_mamba_b200.arch as arch
+    g = load_golden("lfss_block")
+    p = om.sub(om.strip_prefix(params_cache(g["ckpt"])), g["block"])
+    blk = arch.LFSSBlock(32)
+    blk.load_state_dict(p, strict=True)
+    blk = blk.to(dev).eval()
+    h, w = int(g["h"]), int(g["w"])
+    with torch.no_grad():
+        got = blk(g["x"].to(dev), [h, w]).cpu()
+    torch.testing.assert_close(got, g["y"], rtol=3e-5, atol=3e-5)

@@ -73,10 +73,12 @@ class _FFN(nn.Module):
         self.conv2 = nn.Conv2d(mid, mid, 3, padding=1, groups=mid)
         self.conv3 = nn.Conv2d(mid // 2, num_feat, 1)
 
-    def forward(self, x, ln_w=None, ln_b=None, eps=1e-5):
+    def forward(self, x, ln_w=None, ln_b=None, eps=1e-5, residual=None, res_scale=None):
+        """ln?(x) -> conv1 -> conv2 -> gate -> conv3 (+ residual*res_scale), two kernels."""
         t = ops.pw_dw(x, self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias,
                       ln_w, ln_b, eps)
-        return ops.pw(t, self.conv3.weight, self.conv3.bias, gate=True)
+        return ops.pw(t, self.conv3.weight, self.conv3.bias, gate=True, residual=residual,
+                      res_scale=res_scale)
 
 
 class SS2D(nn.Module):
@@ -115,21 +117,37 @@ class SS2D(nn.Module):
         return ops.ss2d_core(x.contiguous(), self.x_proj_weight, self.dt_projs_weight,
                              self.dt_projs_bias, self.A_logs, self.Ds)
 
+    def forward_nchw(self, x, ln_w, ln_b, ln_eps, skip_scale):
+        """Fused NCHW form of ``x*skip_scale + SS2D(ln_1(x))`` (reference :524-525, :480-497):
+        three kernels around the scan, no permutes, no channels-last round trips.
+            xc = silu(dwconv3x3(in_proj[:D] . ln(x)))          [pw_dw, LN prologue, SiLU epilogue]
+            zs = silu(in_proj[D:] . ln(x))                      [lfss_z]
+            y  = forward_core(xc)                               [ss2d_core]
+            out = x*skip_scale + out_proj(out_norm(y) * zs)     [lfss_out]"""
+        D = self.d_inner
+        xc = ops.pw_dw(x, self.in_proj.weight[:D], None, self.conv2d.weight, self.conv2d.bias,
+                       ln_w, ln_b, ln_eps, act="silu")
+        zs = ops.lfss_z(x, ln_w, ln_b, ln_eps, self.in_proj.weight)
+        y = self.forward_core(xc)
+        return ops.lfss_out(y, zs, self.out_norm.weight, self.out_norm.bias, self.out_norm.eps,
+                            self.out_proj.weight, x, skip_scale)
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        """x (B,h,w,C) channels-last, as the reference (:480-497)."""
-        xz = self.in_proj(x)
+        """Reference calling convention: x (B,h,w,C) channels-last -> (B,h,w,C) (:480-497)."""
+        # The fused kernels take the LayerNorm with them, so this un-normalised entry point runs
+        # the glue through library ops; the network itself uses forward_nchw.
+        xz = F.linear(x, self.in_proj.weight)
         xp, z = xz.chunk(2, dim=-1)
         xc = xp.permute(0, 3, 1, 2).contiguous()
         xc = F.silu(F.conv2d(xc, self.conv2d.weight, self.conv2d.bias, padding=1,
                              groups=self.d_inner))
-        y = self.forward_core(xc)
-        y = y.permute(0, 2, 3, 1)
+        y = self.forward_core(xc).permute(0, 2, 3, 1)
         y = F.layer_norm(y, (self.d_inner,), self.out_norm.weight, self.out_norm.bias, 1e-5)
-        return self.out_proj(y * F.silu(z))
+        return F.linear(y * F.silu(z), self.out_proj.weight)
 
 
 class LFSSBlock(nn.Module):
-    """reference ``LFSSBlock`` (:499-528); input/output (B, h*w, C) like the reference."""
+    """reference ``LFSSBlock`` (:499-528)."""
 
     def __init__(self, hidden_dim: int, d_state: int = 16, expand: float = 2.0, **_unused):
         super().__init__()
@@ -140,15 +158,18 @@ class LFSSBlock(nn.Module):
         self.ln_2 = nn.LayerNorm(hidden_dim)
         self.skip_scale2 = nn.Parameter(torch.ones(hidden_dim))
 
+    def forward_nchw(self, x: torch.Tensor) -> torch.Tensor:
+        """(B,C,h,w) -> (B,C,h,w); five kernels + the scan, all NCHW."""
+        x = self.self_attention.forward_nchw(x, self.ln_1.weight, self.ln_1.bias, self.ln_1.eps,
+                                             self.skip_scale)                       # :524-525
+        return self.conv_blk(x, self.ln_2.weight, self.ln_2.bias, self.ln_2.eps,
+                             residual=x, res_scale=self.skip_scale2)                # :526
+
     def forward(self, inp: torch.Tensor, x_size: Sequence[int]) -> torch.Tensor:
+        """Reference calling convention: (B, h*w, C) in and out."""
         B, L, C = inp.shape
-        x = inp.view(B, x_size[0], x_size[1], C)
-        t = F.layer_norm(x, (C,), self.ln_1.weight, self.ln_1.bias, 1e-6)
-        x = x * self.skip_scale + self.self_attention(t)
-        # ln_2 (eps 1e-5, :516) is fused into the ffn's first kernel (LayerNorm over channels)
-        f = self.conv_blk(x.permute(0, 3, 1, 2).contiguous(), self.ln_2.weight, self.ln_2.bias, 1e-5)
-        x = x * self.skip_scale2 + f.permute(0, 2, 3, 1)
-        return x.reshape(B, L, C)
+        x = inp.view(B, x_size[0], x_size[1], C).permute(0, 3, 1, 2).contiguous()
+        return self.forward_nchw(x).permute(0, 2, 3, 1).reshape(B, L, C)
 
 
 # --------------------------------------------------------------------------------------
@@ -279,11 +300,11 @@ class SKFF(nn.Module):
 # groups and the network                                        reference :962-1176
 # --------------------------------------------------------------------------------------
 def _run_low(blocks, x):
-    B, C, h, w = x.shape
-    t = x.permute(0, 2, 3, 1).reshape(B, h * w, C)
+    """reference :976-979 / :998-1001 without the NCHW <-> (B,L,C) round trips."""
+    x = x.contiguous()
     for blk in blocks:
-        t = blk(t, [h, w])
-    return t.view(B, h, w, C).permute(0, 3, 1, 2).contiguous()
+        x = blk.forward_nchw(x)
+    return x
 
 
 class DownFRG(nn.Module):

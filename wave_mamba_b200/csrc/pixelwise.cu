@@ -1,0 +1,256 @@
+// Position-wise (1x1) kernels of the Wave-Mamba forward for sm_100a: everything that mixes
+// channels at one pixel without a spatial neighbourhood.  NCHW float32, one HBM round trip.
+//
+// One template covers the reference call sites (wavemamba_arch.py):
+//   * CMTAttention.project_out + residual                                  (:797, :849)
+//   * ffn gate gelu(x1)*x2 + conv3 + scaled residual                       (:227-230, :526)
+//   * PAConv k2 + sigmoid + multiply with the k3 output                    (:694-697)
+//   * SS2D z branch: silu(in_proj[64:] . ln_1(x))                          (:483-484,493, :524)
+//   * SS2D tail: out_norm + *silu(z) + out_proj + skip_scale residual      (:492-494, :525)
+//   * LayerNorm2d                                                          (:535-543)
+//
+// Thread = one pixel.  Its CIN input values live in registers (the prologue -- LayerNorm over
+// channels, GELU gate, elementwise multiply -- runs there); outputs are produced 8 at a time
+// with the weight row broadcast from shared memory as two 128-bit loads per input channel.
+// Global accesses are coalesced along the pixel index for every channel plane.
+#include "common.cuh"
+
+namespace wm {
+namespace px {
+
+constexpr int kThreads = 256;
+
+enum Pre { kPreNone = 0, kPreGate = 1, kPreLN = 2, kPreLNMul = 3 };
+enum Post { kPostNone = 0, kPostSilu = 1, kPostSigmoidMul = 2 };
+
+__device__ __forceinline__ float gelu_erf(float v)
+{
+    return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float silu(float v) { return v / (1.0f + expf(-v)); }
+
+struct Args {
+    const float *x;          // (B, CIN or 2*CIN, hw)
+    const float *x2;         // optional second addend for x (same shape), e.g. the scan's tmp plane
+    const float *ln_w, *ln_b;
+    float eps;
+    const float *mul;        // kPreLNMul: (B, CIN, hw) multiplied after the LayerNorm
+    const float *w;          // (COUT, CIN)
+    const float *b;          // (COUT) or null
+    const float *res;        // optional residual (B, COUT, hw)
+    const float *res_scale;  // optional per-channel scale of the residual (COUT)
+    const float *mul_out;    // kPostSigmoidMul: (B, COUT, hw); may alias y
+    float *y;                // (B, COUT, hw)
+    int64_t hw;
+};
+
+template <int CIN, int COUT, int PRE, int POST>
+__global__ void __launch_bounds__(kThreads, CIN <= 32 ? 3 : 2)
+pixel_kernel(const Args a)
+{
+    __shared__ __align__(16) float wt[CIN * COUT];  // [ci][co]
+    __shared__ float pb[COUT], rs[COUT], lw[CIN], lb[CIN];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < CIN * COUT; i += kThreads) {
+        const int co = i / CIN, ci = i - co * CIN;
+        wt[ci * COUT + co] = __ldg(a.w + i);
+    }
+    for (int i = tid; i < COUT; i += kThreads) {
+        pb[i] = a.b ? __ldg(a.b + i) : 0.0f;
+        rs[i] = a.res_scale ? __ldg(a.res_scale + i) : 1.0f;
+    }
+    if (PRE == kPreLN || PRE == kPreLNMul)
+        for (int i = tid; i < CIN; i += kThreads) { lw[i] = __ldg(a.ln_w + i); lb[i] = __ldg(a.ln_b + i); }
+    __syncthreads();
+
+    const int64_t hw = a.hw;
+    const int64_t b = blockIdx.y;
+    constexpr int XCH = PRE == kPreGate ? 2 * CIN : CIN;
+    const float *xb = a.x + b * XCH * hw;
+    const float *x2b = a.x2 ? a.x2 + b * XCH * hw : nullptr;
+    for (int64_t p = (int64_t)blockIdx.x * kThreads + tid; p < hw;
+         p += (int64_t)gridDim.x * kThreads) {
+        float xv[CIN];
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) {
+            if (PRE == kPreGate) {
+                xv[ci] = gelu_erf(__ldg(xb + ci * hw + p)) * __ldg(xb + (CIN + ci) * hw + p);
+            } else {
+                xv[ci] = __ldg(xb + ci * hw + p);
+                if (x2b) xv[ci] += __ldg(x2b + ci * hw + p);
+            }
+        }
+        if (PRE == kPreLN || PRE == kPreLNMul) {
+            float mu = 0.0f;
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci) mu += xv[ci];
+            mu *= (1.0f / CIN);
+            float var = 0.0f;
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci) { const float dlt = xv[ci] - mu; var = fmaf(dlt, dlt, var); }
+            var *= (1.0f / CIN);
+            const float rstd = 1.0f / sqrtf(var + a.eps);
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci) {
+                xv[ci] = fmaf((xv[ci] - mu) * rstd, lw[ci], lb[ci]);
+                if (PRE == kPreLNMul) xv[ci] *= __ldg(a.mul + (b * CIN + ci) * hw + p);
+            }
+        }
+#pragma unroll 1
+        for (int g = 0; g < COUT / 8; ++g) {
+            float acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = pb[g * 8 + j];
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci) {
+                const float4 w0 = *reinterpret_cast<const float4 *>(wt + ci * COUT + g * 8);
+                const float4 w1 = *reinterpret_cast<const float4 *>(wt + ci * COUT + g * 8 + 4);
+                acc[0] = fmaf(xv[ci], w0.x, acc[0]); acc[1] = fmaf(xv[ci], w0.y, acc[1]);
+                acc[2] = fmaf(xv[ci], w0.z, acc[2]); acc[3] = fmaf(xv[ci], w0.w, acc[3]);
+                acc[4] = fmaf(xv[ci], w1.x, acc[4]); acc[5] = fmaf(xv[ci], w1.y, acc[5]);
+                acc[6] = fmaf(xv[ci], w1.z, acc[6]); acc[7] = fmaf(xv[ci], w1.w, acc[7]);
+            }
+            const int64_t o = (b * COUT + g * 8) * hw + p;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float v = acc[j];
+                if (POST == kPostSilu) v = silu(v);
+                if (POST == kPostSigmoidMul) v = a.mul_out[o + j * hw] * (1.0f / (1.0f + expf(-v)));
+                if (a.res) v = fmaf(a.res[o + j * hw], rs[g * 8 + j], v);
+                a.y[o + j * hw] = v;
+            }
+        }
+    }
+}
+
+template <int C>
+__global__ void __launch_bounds__(kThreads)
+layernorm2d_kernel(const float *__restrict__ x, const float *__restrict__ ln_w,
+                   const float *__restrict__ ln_b, float eps, float *__restrict__ y, int64_t hw)
+{
+    const int64_t b = blockIdx.y;
+    const float *xb = x + b * C * hw;
+    float *yb = y + b * C * hw;
+    for (int64_t p = (int64_t)blockIdx.x * kThreads + threadIdx.x; p < hw;
+         p += (int64_t)gridDim.x * kThreads) {
+        float v[C];
+        float mu = 0.0f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) { v[c] = __ldg(xb + c * hw + p); mu += v[c]; }
+        mu *= (1.0f / C);
+        float var = 0.0f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) { const float dlt = v[c] - mu; var = fmaf(dlt, dlt, var); }
+        var *= (1.0f / C);
+        const float rstd = 1.0f / sqrtf(var + eps);
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+            yb[c * hw + p] = fmaf((v[c] - mu) * rstd, __ldg(ln_w + c), __ldg(ln_b + c));
+    }
+}
+
+inline int flat_grid(int64_t hw)
+{
+    const int64_t want = (hw + kThreads - 1) / kThreads;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+inline bool dims_ok(int64_t B, int64_t h, int64_t w)
+{
+    return B >= 0 && B <= 65535 && h >= 0 && w >= 0 && h < (1 << 24) && w < (1 << 24);
+}
+
+template <int CIN, int COUT, int PRE, int POST>
+int launch(const Args &a, int64_t B, cudaStream_t s, const char *what)
+{
+    dim3 grid(flat_grid(a.hw), (unsigned)B);
+    pixel_kernel<CIN, COUT, PRE, POST><<<grid, kThreads, 0, s>>>(a);
+    WM_LAUNCH_OK(what);
+    return WM_OK;
+}
+
+}  // namespace px
+}  // namespace wm
+
+using namespace wm;
+using namespace wm::px;
+
+extern "C" int wm_layernorm2d_fwd(const float *x, const float *ln_w, const float *ln_b, float eps,
+                                  float *y, int64_t B, int64_t C, int64_t h, int64_t w,
+                                  wm_stream_t stream)
+{
+    WM_REQUIRE(dims_ok(B, h, w), "wm_layernorm2d_fwd: bad sizes");
+    WM_REQUIRE(C == 32 || C == 64, "wm_layernorm2d_fwd: C=%lld unsupported (32 or 64)", (long long)C);
+    if (B == 0 || h == 0 || w == 0) return WM_OK;
+    WM_REQUIRE(x && ln_w && ln_b && y, "wm_layernorm2d_fwd: null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t hw = h * w;
+    dim3 grid(flat_grid(hw), (unsigned)B);
+    if (C == 32) layernorm2d_kernel<32><<<grid, kThreads, 0, s>>>(x, ln_w, ln_b, eps, y, hw);
+    else layernorm2d_kernel<64><<<grid, kThreads, 0, s>>>(x, ln_w, ln_b, eps, y, hw);
+    WM_LAUNCH_OK("layernorm2d");
+    return WM_OK;
+}
+
+extern "C" int wm_pw_fwd(const float *x, const float *pw_w, const float *pw_b, int gate_mode,
+                         const float *residual, const float *res_scale, float *y, int64_t B,
+                         int64_t Cin, int64_t Cout, int64_t h, int64_t w, wm_stream_t stream)
+{
+    WM_REQUIRE(dims_ok(B, h, w), "wm_pw_fwd: bad sizes");
+    WM_REQUIRE(gate_mode == 0 || gate_mode == 1, "wm_pw_fwd: gate_mode must be 0 or 1");
+    WM_REQUIRE(!(res_scale && !residual), "wm_pw_fwd: res_scale without residual");
+    if (B == 0 || h == 0 || w == 0) return WM_OK;
+    WM_REQUIRE(x && pw_w && y, "wm_pw_fwd: null pointer");
+    Args a = {};
+    a.x = x; a.w = pw_w; a.b = pw_b; a.res = residual; a.res_scale = res_scale; a.y = y;
+    a.hw = h * w;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (gate_mode == 0 && Cin == 32 && Cout == 32) return launch<32, 32, kPreNone, kPostNone>(a, B, s, "pw 32->32");
+    if (gate_mode == 0 && Cin == 32 && Cout == 64) return launch<32, 64, kPreNone, kPostNone>(a, B, s, "pw 32->64");
+    if (gate_mode == 0 && Cin == 64 && Cout == 32) return launch<64, 32, kPreNone, kPostNone>(a, B, s, "pw 64->32");
+    if (gate_mode == 1 && Cin == 32 && Cout == 32) return launch<32, 32, kPreGate, kPostNone>(a, B, s, "pw gate 32->32");
+    WM_REQUIRE(false, "wm_pw_fwd: Cin=%lld Cout=%lld gate_mode=%d unsupported", (long long)Cin,
+               (long long)Cout, gate_mode);
+    return WM_EINVAL;
+}
+
+extern "C" int wm_paconv_gate_fwd(const float *x, const float *k2_w, const float *k2_b,
+                                  const float *k3out, float *y, int64_t B, int64_t C, int64_t h,
+                                  int64_t w, wm_stream_t stream)
+{
+    WM_REQUIRE(dims_ok(B, h, w), "wm_paconv_gate_fwd: bad sizes");
+    WM_REQUIRE(C == 64, "wm_paconv_gate_fwd: C=%lld unsupported (64)", (long long)C);
+    if (B == 0 || h == 0 || w == 0) return WM_OK;
+    WM_REQUIRE(x && k2_w && k2_b && k3out && y, "wm_paconv_gate_fwd: null pointer");
+    Args a = {};
+    a.x = x; a.w = k2_w; a.b = k2_b; a.mul_out = k3out; a.y = y; a.hw = h * w;
+    return launch<64, 64, kPreNone, kPostSigmoidMul>(a, B, (cudaStream_t)stream, "paconv gate");
+}
+
+extern "C" int wm_lfss_z_fwd(const float *x, const float *ln_w, const float *ln_b, float eps,
+                             const float *w_z, float *zs, int64_t B, int64_t h, int64_t w,
+                             wm_stream_t stream)
+{
+    WM_REQUIRE(dims_ok(B, h, w), "wm_lfss_z_fwd: bad sizes");
+    if (B == 0 || h == 0 || w == 0) return WM_OK;
+    WM_REQUIRE(x && ln_w && ln_b && w_z && zs, "wm_lfss_z_fwd: null pointer");
+    Args a = {};
+    a.x = x; a.ln_w = ln_w; a.ln_b = ln_b; a.eps = eps; a.w = w_z; a.y = zs; a.hw = h * w;
+    return launch<32, 64, kPreLN, kPostSilu>(a, B, (cudaStream_t)stream, "lfss z");
+}
+
+extern "C" int wm_lfss_out_fwd(const float *y, const float *y2, const float *zs, const float *on_w,
+                               const float *on_b, float eps, const float *w_out, const float *x,
+                               const float *skip_scale, float *out, int64_t B, int64_t h, int64_t w,
+                               wm_stream_t stream)
+{
+    WM_REQUIRE(dims_ok(B, h, w), "wm_lfss_out_fwd: bad sizes");
+    if (B == 0 || h == 0 || w == 0) return WM_OK;
+    WM_REQUIRE(y && zs && on_w && on_b && w_out && x && skip_scale && out,
+               "wm_lfss_out_fwd: null pointer");
+    Args a = {};
+    a.x = y; a.x2 = y2; a.ln_w = on_w; a.ln_b = on_b; a.eps = eps; a.mul = zs; a.w = w_out;
+    a.res = x; a.res_scale = skip_scale; a.y = out; a.hw = h * w;
+    return launch<64, 32, kPreLNMul, kPostNone>(a, B, (cudaStream_t)stream, "lfss out");
+}

@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(kThreads)
 pw_dw_kernel(const float *__restrict__ x, const float *__restrict__ ln_w,
              const float *__restrict__ ln_b, float eps, const float *__restrict__ pw_w,
              const float *__restrict__ pw_b, const float *__restrict__ dw_w,
-             const float *__restrict__ dw_b, float *__restrict__ y, int h, int w)
+             const float *__restrict__ dw_b, int act, float *__restrict__ y, int h, int w)
 {
     constexpr int CIN = 32;
     extern __shared__ __align__(16) float smem[];
@@ -90,7 +90,10 @@ pw_dw_kernel(const float *__restrict__ x, const float *__restrict__ ln_w,
         const int co = i / CIN, ci = i - co * CIN;
         wt[ci * COUT + co] = __ldg(pw_w + i);
     }
-    for (int i = tid; i < COUT; i += kThreads) { pb[i] = __ldg(pw_b + i); dwb[i] = __ldg(dw_b + i); }
+    for (int i = tid; i < COUT; i += kThreads) {
+        pb[i] = pw_b ? __ldg(pw_b + i) : 0.0f;
+        dwb[i] = __ldg(dw_b + i);
+    }
     for (int i = tid; i < COUT * 9; i += kThreads) dww[i] = __ldg(dw_w + i);
     if (ln_w != nullptr && tid < CIN) { lnw[tid] = __ldg(ln_w + tid); lnb[tid] = __ldg(ln_b + tid); }
     load_halo32(x, xs, b, CIN, h, w, ty0, tx0);
@@ -164,6 +167,7 @@ pw_dw_kernel(const float *__restrict__ x, const float *__restrict__ ln_w,
                 o = fmaf(k[0], r0[0], o); o = fmaf(k[1], r0[1], o); o = fmaf(k[2], r0[2], o);
                 o = fmaf(k[3], r1[0], o); o = fmaf(k[4], r1[1], o); o = fmaf(k[5], r1[2], o);
                 o = fmaf(k[6], r2[0], o); o = fmaf(k[7], r2[1], o); o = fmaf(k[8], r2[2], o);
+                if (act == 1) o = o / (1.0f + expf(-o));  // SiLU (SS2D.act, reference :487)
                 if (gx < w && ty0 + row < h) yo[(int64_t)row * w] = o;
 #pragma unroll
                 for (int dx = 0; dx < 3; ++dx) { r0[dx] = r1[dx]; r1[dx] = r2[dx]; }
@@ -261,105 +265,6 @@ dw_act_pw_kernel(const float *__restrict__ x, const float *__restrict__ dw_w,
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Position-wise kernels on flat pixel indices: thread = pixel, channels in registers.
-//   MODE 0: y = res? + W x + b                      (x has CIN channels)
-//   MODE 1: y = res? + W (gelu(x[:CIN]) * x[CIN:]) + b   (x has 2*CIN channels)
-//   MODE 2: y = mul * sigmoid(W x + b)              (PAConv gate; mul has COUT channels)
-// ---------------------------------------------------------------------------------------------
-template <int CIN, int COUT, int MODE>
-__global__ void __launch_bounds__(kThreads)
-pointwise_kernel(const float *__restrict__ x, const float *__restrict__ pw_w,
-                 const float *__restrict__ pw_b, const float *extra, float *y, int64_t hw)
-{
-    __shared__ __align__(16) float wt[CIN * COUT];  // [ci][co]
-    __shared__ float pb[COUT];
-    const int tid = threadIdx.x;
-    for (int i = tid; i < CIN * COUT; i += kThreads) {
-        const int co = i / CIN, ci = i - co * CIN;
-        wt[ci * COUT + co] = __ldg(pw_w + i);
-    }
-    for (int i = tid; i < COUT; i += kThreads) pb[i] = pw_b ? __ldg(pw_b + i) : 0.0f;
-    __syncthreads();
-
-    const int64_t b = blockIdx.y;
-    constexpr int XCH = MODE == 1 ? 2 * CIN : CIN;
-    const float *xb = x + b * XCH * hw;
-    for (int64_t p = (int64_t)blockIdx.x * kThreads + tid; p < hw; p += (int64_t)gridDim.x * kThreads) {
-        float xv[CIN];
-#pragma unroll
-        for (int ci = 0; ci < CIN; ++ci) {
-            if (MODE == 1) {
-                xv[ci] = gelu_erf(__ldg(xb + ci * hw + p)) * __ldg(xb + (CIN + ci) * hw + p);
-            } else {
-                xv[ci] = __ldg(xb + ci * hw + p);
-            }
-        }
-#pragma unroll 1
-        for (int g = 0; g < COUT / 32; ++g) {
-            float acc[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) acc[j] = pb[g * 32 + j];
-#pragma unroll
-            for (int ci = 0; ci < CIN; ++ci) {
-                const float4 *wr = reinterpret_cast<const float4 *>(wt + ci * COUT + g * 32);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 wv = wr[j];
-                    acc[4 * j + 0] = fmaf(xv[ci], wv.x, acc[4 * j + 0]);
-                    acc[4 * j + 1] = fmaf(xv[ci], wv.y, acc[4 * j + 1]);
-                    acc[4 * j + 2] = fmaf(xv[ci], wv.z, acc[4 * j + 2]);
-                    acc[4 * j + 3] = fmaf(xv[ci], wv.w, acc[4 * j + 3]);
-                }
-            }
-            const int64_t o = (b * COUT + g * 32) * hw + p;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                float v = acc[j];
-                if (MODE == 2) {
-                    v = extra[o + j * hw] * (1.0f / (1.0f + expf(-v)));  // may alias y (in place)
-                } else if (extra != nullptr) {
-                    v += extra[o + j * hw];
-                }
-                y[o + j * hw] = v;
-            }
-        }
-    }
-}
-
-template <int C>
-__global__ void __launch_bounds__(kThreads)
-layernorm2d_kernel(const float *__restrict__ x, const float *__restrict__ ln_w,
-                   const float *__restrict__ ln_b, float eps, float *__restrict__ y, int64_t hw)
-{
-    const int64_t b = blockIdx.y;
-    const float *xb = x + b * C * hw;
-    float *yb = y + b * C * hw;
-    for (int64_t p = (int64_t)blockIdx.x * kThreads + threadIdx.x; p < hw;
-         p += (int64_t)gridDim.x * kThreads) {
-        float v[C];
-        float mu = 0.0f;
-#pragma unroll
-        for (int c = 0; c < C; ++c) { v[c] = __ldg(xb + c * hw + p); mu += v[c]; }
-        mu *= (1.0f / C);
-        float var = 0.0f;
-#pragma unroll
-        for (int c = 0; c < C; ++c) { const float dlt = v[c] - mu; var = fmaf(dlt, dlt, var); }
-        var *= (1.0f / C);
-        const float rstd = 1.0f / sqrtf(var + eps);
-#pragma unroll
-        for (int c = 0; c < C; ++c)
-            yb[c * hw + p] = fmaf((v[c] - mu) * rstd, __ldg(ln_w + c), __ldg(ln_b + c));
-    }
-}
-
-inline int flat_grid(int64_t hw)
-{
-    const int64_t want = (hw + kThreads - 1) / kThreads;
-    const int64_t cap = (int64_t)sm_count() * 8;
-    return (int)(want < cap ? (want > 0 ? want : 1) : cap);
-}
-
 inline bool dims_ok(int64_t B, int64_t h, int64_t w)
 {
     return B >= 0 && B <= 65535 && h >= 0 && w >= 0 && h < (1 << 24) && w < (1 << 24);
@@ -377,44 +282,28 @@ inline cudaError_t opt_in_smem(KernelT kernel, size_t bytes)
 using namespace wm;
 using namespace wm::pw;
 
-extern "C" int wm_layernorm2d_fwd(const float *x, const float *ln_w, const float *ln_b, float eps,
-                                  float *y, int64_t B, int64_t C, int64_t h, int64_t w,
-                                  wm_stream_t stream)
-{
-    WM_REQUIRE(x && ln_w && ln_b && y, "wm_layernorm2d_fwd: null pointer");
-    WM_REQUIRE(dims_ok(B, h, w), "wm_layernorm2d_fwd: bad sizes");
-    WM_REQUIRE(C == 32 || C == 64, "wm_layernorm2d_fwd: C=%lld unsupported (32 or 64)", (long long)C);
-    if (B == 0 || h == 0 || w == 0) return WM_OK;
-    cudaStream_t s = (cudaStream_t)stream;
-    const int64_t hw = h * w;
-    dim3 grid(flat_grid(hw), (unsigned)B);
-    if (C == 32) layernorm2d_kernel<32><<<grid, kThreads, 0, s>>>(x, ln_w, ln_b, eps, y, hw);
-    else layernorm2d_kernel<64><<<grid, kThreads, 0, s>>>(x, ln_w, ln_b, eps, y, hw);
-    WM_LAUNCH_OK("layernorm2d");
-    return WM_OK;
-}
-
 template <int COUT>
 static int launch_pw_dw(const float *x, const float *ln_w, const float *ln_b, float eps,
                         const float *pw_w, const float *pw_b, const float *dw_w,
-                        const float *dw_b, float *y, int64_t B, int64_t h, int64_t w,
+                        const float *dw_b, int act, float *y, int64_t B, int64_t h, int64_t w,
                         cudaStream_t s)
 {
     const size_t smem = sizeof(float) * (32 * kXP * 2 + 32 * COUT + COUT + COUT * 9 + COUT + 64);
     WM_CUDA_OK(opt_in_smem(pw_dw_kernel<COUT>, smem));
     dim3 grid((unsigned)((w + kTW - 1) / kTW), (unsigned)((h + kTH - 1) / kTH), (unsigned)B);
-    pw_dw_kernel<COUT><<<grid, kThreads, smem, s>>>(x, ln_w, ln_b, eps, pw_w, pw_b, dw_w, dw_b, y,
-                                                    (int)h, (int)w);
+    pw_dw_kernel<COUT><<<grid, kThreads, smem, s>>>(x, ln_w, ln_b, eps, pw_w, pw_b, dw_w, dw_b, act,
+                                                    y, (int)h, (int)w);
     WM_LAUNCH_OK("pw_dw");
     return WM_OK;
 }
 
 extern "C" int wm_pw_dw_fwd(const float *x, const float *ln_w, const float *ln_b, float eps,
                             const float *pw_w, const float *pw_b, const float *dw_w,
-                            const float *dw_b, float *y, int64_t B, int64_t Cin, int64_t Cout,
-                            int64_t h, int64_t w, wm_stream_t stream)
+                            const float *dw_b, int act, float *y, int64_t B, int64_t Cin,
+                            int64_t Cout, int64_t h, int64_t w, wm_stream_t stream)
 {
-    WM_REQUIRE(x && pw_w && pw_b && dw_w && dw_b && y, "wm_pw_dw_fwd: null pointer");
+    WM_REQUIRE(x && pw_w && dw_w && dw_b && y, "wm_pw_dw_fwd: null pointer");
+    WM_REQUIRE(act == 0 || act == 1, "wm_pw_dw_fwd: act must be 0 (none) or 1 (SiLU)");
     WM_REQUIRE((ln_w == nullptr) == (ln_b == nullptr), "wm_pw_dw_fwd: ln_w/ln_b must come together");
     WM_REQUIRE(dims_ok(B, h, w), "wm_pw_dw_fwd: bad sizes");
     WM_REQUIRE(Cin == 32 && (Cout == 32 || Cout == 64 || Cout == 96),
@@ -423,9 +312,9 @@ extern "C" int wm_pw_dw_fwd(const float *x, const float *ln_w, const float *ln_b
     WM_REQUIRE((h + kTH - 1) / kTH <= 65535, "wm_pw_dw_fwd: image too tall");
     if (B == 0 || h == 0 || w == 0) return WM_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    if (Cout == 32) return launch_pw_dw<32>(x, ln_w, ln_b, eps, pw_w, pw_b, dw_w, dw_b, y, B, h, w, s);
-    if (Cout == 64) return launch_pw_dw<64>(x, ln_w, ln_b, eps, pw_w, pw_b, dw_w, dw_b, y, B, h, w, s);
-    return launch_pw_dw<96>(x, ln_w, ln_b, eps, pw_w, pw_b, dw_w, dw_b, y, B, h, w, s);
+    if (Cout == 32) return launch_pw_dw<32>(x, ln_w, ln_b, eps, pw_w, pw_b, dw_w, dw_b, act, y, B, h, w, s);
+    if (Cout == 64) return launch_pw_dw<64>(x, ln_w, ln_b, eps, pw_w, pw_b, dw_w, dw_b, act, y, B, h, w, s);
+    return launch_pw_dw<96>(x, ln_w, ln_b, eps, pw_w, pw_b, dw_w, dw_b, act, y, B, h, w, s);
 }
 
 extern "C" int wm_dw_act_pw_fwd(const float *x, const float *dw_w, const float *dw_b,
@@ -449,45 +338,3 @@ extern "C" int wm_dw_act_pw_fwd(const float *x, const float *dw_w, const float *
     return WM_OK;
 }
 
-extern "C" int wm_pw_fwd(const float *x, const float *pw_w, const float *pw_b, int gate_mode,
-                         const float *residual, float *y, int64_t B, int64_t Cin, int64_t Cout,
-                         int64_t h, int64_t w, wm_stream_t stream)
-{
-    WM_REQUIRE(x && pw_w && y, "wm_pw_fwd: null pointer");
-    WM_REQUIRE(dims_ok(B, h, w), "wm_pw_fwd: bad sizes");
-    WM_REQUIRE(gate_mode == 0 || gate_mode == 1, "wm_pw_fwd: gate_mode must be 0 or 1");
-    if (B == 0 || h == 0 || w == 0) return WM_OK;
-    cudaStream_t s = (cudaStream_t)stream;
-    const int64_t hw = h * w;
-    dim3 grid(flat_grid(hw), (unsigned)B);
-    if (gate_mode == 0 && Cin == 32 && Cout == 32) {
-        pointwise_kernel<32, 32, 0><<<grid, kThreads, 0, s>>>(x, pw_w, pw_b, residual, y, hw);
-    } else if (gate_mode == 0 && Cin == 32 && Cout == 64) {
-        pointwise_kernel<32, 64, 0><<<grid, kThreads, 0, s>>>(x, pw_w, pw_b, residual, y, hw);
-    } else if (gate_mode == 0 && Cin == 64 && Cout == 32) {
-        pointwise_kernel<64, 32, 0><<<grid, kThreads, 0, s>>>(x, pw_w, pw_b, residual, y, hw);
-    } else if (gate_mode == 1 && Cin == 32 && Cout == 32) {
-        pointwise_kernel<32, 32, 1><<<grid, kThreads, 0, s>>>(x, pw_w, pw_b, residual, y, hw);
-    } else {
-        WM_REQUIRE(false, "wm_pw_fwd: Cin=%lld Cout=%lld gate_mode=%d unsupported", (long long)Cin,
-                   (long long)Cout, gate_mode);
-    }
-    WM_LAUNCH_OK("pointwise");
-    return WM_OK;
-}
-
-extern "C" int wm_paconv_gate_fwd(const float *x, const float *k2_w, const float *k2_b,
-                                  const float *k3out, float *y, int64_t B, int64_t C, int64_t h,
-                                  int64_t w, wm_stream_t stream)
-{
-    WM_REQUIRE(x && k2_w && k2_b && k3out && y, "wm_paconv_gate_fwd: null pointer");
-    WM_REQUIRE(dims_ok(B, h, w), "wm_paconv_gate_fwd: bad sizes");
-    WM_REQUIRE(C == 64, "wm_paconv_gate_fwd: C=%lld unsupported (64)", (long long)C);
-    if (B == 0 || h == 0 || w == 0) return WM_OK;
-    cudaStream_t s = (cudaStream_t)stream;
-    const int64_t hw = h * w;
-    dim3 grid(flat_grid(hw), (unsigned)B);
-    pointwise_kernel<64, 64, 2><<<grid, kThreads, 0, s>>>(x, k2_w, k2_b, k3out, y, hw);
-    WM_LAUNCH_OK("paconv gate");
-    return WM_OK;
-}

@@ -136,13 +136,19 @@ def layernorm2d(x, weight, bias, eps: float = 1e-6) -> torch.Tensor:
     return y
 
 
-def pw_dw(x, pw_w, pw_b, dw_w, dw_b, ln_w=None, ln_b=None, eps: float = 1e-6) -> torch.Tensor:
-    """y = dw3x3(pw1x1(ln?(x))): (B,32,h,w) -> (B,Cout,h,w), Cout in {32,64,96}."""
+def pw_dw(x, pw_w, pw_b, dw_w, dw_b, ln_w=None, ln_b=None, eps: float = 1e-6,
+          act: str = "none") -> torch.Tensor:
+    """y = act(dw3x3(pw1x1(ln?(x)))): (B,32,h,w) -> (B,Cout,h,w), Cout in {32,64,96}.
+    pw_w may be (Cout,Cin,1,1) or (Cout,Cin); pw_b may be None; act in {"none","silu"}."""
     _chk(x, "x")
     B, Cin, h, w = x.shape
     Cout = pw_w.shape[0]
-    _chk(pw_w, "pw_w", (Cout, Cin, 1, 1))
-    _chk(pw_b, "pw_b", (Cout,))
+    if pw_w.dim() == 2:
+        _chk(pw_w, "pw_w", (Cout, Cin))
+    else:
+        _chk(pw_w, "pw_w", (Cout, Cin, 1, 1))
+    if pw_b is not None:
+        _chk(pw_b, "pw_b", (Cout,))
     _chk(dw_w, "dw_w", (Cout, 1, 3, 3))
     _chk(dw_b, "dw_b", (Cout,))
     if ln_w is not None:
@@ -152,8 +158,9 @@ def pw_dw(x, pw_w, pw_b, dw_w, dw_b, ln_w=None, ln_b=None, eps: float = 1e-6) ->
     lib = _cabi.load()
     with torch.cuda.device(x.device):
         rc = lib.wm_pw_dw_fwd(x.data_ptr(), _ptr(ln_w), _ptr(ln_b), eps, pw_w.data_ptr(),
-                              pw_b.data_ptr(), dw_w.data_ptr(), dw_b.data_ptr(), y.data_ptr(),
-                              B, Cin, Cout, h, w, _stream(x))
+                              _ptr(pw_b), dw_w.data_ptr(), dw_b.data_ptr(),
+                              {"none": 0, "silu": 1}[act], y.data_ptr(), B, Cin, Cout, h, w,
+                              _stream(x))
     _cabi.check(rc, "wm_pw_dw_fwd")
     _count(1)
     return y
@@ -180,9 +187,9 @@ def dw_act_pw(x, dw_w, dw_b, pw_w, pw_b, act: str = "gelu", residual=None) -> to
     return y
 
 
-def pw(x, pw_w, pw_b=None, gate: bool = False, residual=None) -> torch.Tensor:
-    """y = residual? + pw1x1(x) (+bias).  gate=True: x is (B,2*Cin,h,w) and the conv sees
-    gelu(x[:, :Cin]) * x[:, Cin:]  (reference ffn :227-228)."""
+def pw(x, pw_w, pw_b=None, gate: bool = False, residual=None, res_scale=None) -> torch.Tensor:
+    """y = residual?*res_scale? + pw1x1(x) (+bias).  gate=True: x is (B,2*Cin,h,w) and the conv
+    sees gelu(x[:, :Cin]) * x[:, Cin:]  (reference ffn :227-228)."""
     _chk(x, "x")
     B, Cx, h, w = x.shape
     Cout, Cin = pw_w.shape[0], pw_w.shape[1]
@@ -193,11 +200,14 @@ def pw(x, pw_w, pw_b=None, gate: bool = False, residual=None) -> torch.Tensor:
         _chk(pw_b, "pw_b", (Cout,))
     if residual is not None:
         _chk(residual, "residual", (B, Cout, h, w))
+    if res_scale is not None:
+        _chk(res_scale, "res_scale", (Cout,))
     y = torch.empty(B, Cout, h, w, device=x.device, dtype=x.dtype)
     lib = _cabi.load()
     with torch.cuda.device(x.device):
         rc = lib.wm_pw_fwd(x.data_ptr(), pw_w.data_ptr(), _ptr(pw_b), 1 if gate else 0,
-                           _ptr(residual), y.data_ptr(), B, Cin, Cout, h, w, _stream(x))
+                           _ptr(residual), _ptr(res_scale), y.data_ptr(), B, Cin, Cout, h, w,
+                           _stream(x))
     _cabi.check(rc, "wm_pw_fwd")
     _count(1)
     return y
@@ -218,3 +228,46 @@ def paconv_gate(x, k2_w, k2_b, k3out, inplace: bool = True) -> torch.Tensor:
     _cabi.check(rc, "wm_paconv_gate_fwd")
     _count(1)
     return y
+
+
+def lfss_z(x, ln_w, ln_b, eps, in_proj_weight) -> torch.Tensor:
+    """zs = silu(in_proj.weight[64:] . LayerNorm_c(x)): (B,32,h,w) -> (B,64,h,w)
+    (reference ln_1 :524, in_proj/chunk :483-484, F.silu(z) :493)."""
+    _chk(x, "x")
+    B, C, h, w = x.shape
+    _chk(in_proj_weight, "in_proj_weight", (4 * C, C))
+    _chk(ln_w, "ln_w", (C,))
+    _chk(ln_b, "ln_b", (C,))
+    zs = torch.empty(B, 2 * C, h, w, device=x.device, dtype=x.dtype)
+    lib = _cabi.load()
+    w_z = in_proj_weight.data_ptr() + 2 * C * C * 4  # rows 64..127
+    with torch.cuda.device(x.device):
+        rc = lib.wm_lfss_z_fwd(x.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), eps, w_z,
+                               zs.data_ptr(), B, h, w, _stream(x))
+    _cabi.check(rc, "wm_lfss_z_fwd")
+    _count(1)
+    return zs
+
+
+def lfss_out(y, zs, on_w, on_b, eps, out_proj_weight, x, skip_scale, y2=None) -> torch.Tensor:
+    """out = x*skip_scale + out_proj(out_norm(y [+ y2]) * zs)  (reference :492-494, :525)."""
+    _chk(y, "y")
+    B, D, h, w = y.shape
+    _chk(zs, "zs", (B, D, h, w))
+    if y2 is not None:
+        _chk(y2, "y2", (B, D, h, w))
+    C = out_proj_weight.shape[0]
+    _chk(out_proj_weight, "out_proj_weight", (C, D))
+    _chk(on_w, "on_w", (D,))
+    _chk(on_b, "on_b", (D,))
+    _chk(x, "x", (B, C, h, w))
+    _chk(skip_scale, "skip_scale", (C,))
+    out = torch.empty_like(x)
+    lib = _cabi.load()
+    with torch.cuda.device(x.device):
+        rc = lib.wm_lfss_out_fwd(y.data_ptr(), _ptr(y2), zs.data_ptr(), on_w.data_ptr(),
+                                 on_b.data_ptr(), eps, out_proj_weight.data_ptr(), x.data_ptr(),
+                                 skip_scale.data_ptr(), out.data_ptr(), B, h, w, _stream(x))
+    _cabi.check(rc, "wm_lfss_out_fwd")
+    _count(1)
+    return out
