@@ -233,7 +233,8 @@ class OpTimer:
         wrap("pw", lambda a, k, o: nb(a[0]) + nb(o) + nb(k.get("residual")))
         wrap("paconv_gate", lambda a, k, o: nb(a[0]) + 2 * nb(o))
         wrap("lfss_z", lambda a, k, o: nb(a[0]) + nb(o))
-        wrap("lfss_out", lambda a, k, o: nb(a[0], a[1], a[6]) + nb(o) + nb(k.get("y2")))
+        wrap("lfss_out", lambda a, k, o: nb(a[0], a[1], a[6]) + nb(o) + nb(*k.get("extra", ())))
+        wrap("ss2d_dirs", lambda a, k, o: 2 * nb(a[0]))           # 512*B*L
 
     def summary(self, peak_gbs):
         agg = {}
@@ -350,12 +351,12 @@ def main():
         return
 
     rows = timer.summary(peak_gbs)
-    ss = next((r for r in rows if r["kernel"] == "ss2d_core"), None)
+    ss = next((r for r in rows if r["kernel"] in ("ss2d_dirs", "ss2d_core")), None)
     L_total = sum((H // (2 ** l)) * (W // (2 ** l)) * n for l, n in ((1, 2), (2, 4), (3, 8)))
     roofline = None
     if ss:
         roofline = {
-            "kernel": "ss2d_core (pass1 + carry + pass2A + pass2B + combine)", "bound": "hbm",
+            "kernel": "ss2d_dirs (pass 1 + carry + pass 2; the 4-way sum is fused into lfss_out)", "bound": "hbm",
             "achieved": ss["achieved_gbs"], "peak": peak_gbs, "unit": "GB/s",
             "frac": ss["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src,
             "bytes_definition": "512*B*L per call (x read once + merged y written once), SURVEY 8d",

@@ -31,7 +31,7 @@ extern "C" {
 #define WM_ECUDA (-2)     /* a CUDA runtime call or kernel launch failed               */
 #define WM_ENODEVICE (-3) /* no sm_100-class CUDA device is current                     */
 
-#define WM_ABI_VERSION 2
+#define WM_ABI_VERSION 3
 
 typedef void *wm_stream_t;
 
@@ -66,6 +66,14 @@ int wm_iwt_haar_fwd(const float *low, int64_t low_bstride, const float *high,
  * workspace: >= wm_ss2d_core_workspace_bytes(B,h,w) bytes, 256-byte aligned.
  * Fixed model constants: d_inner 64, d_state 16, dt_rank 2, 4 directions. */
 size_t wm_ss2d_core_workspace_bytes(int64_t B, int64_t h, int64_t w);
+/* Same computation without the final 4-way sum: on return the first 4*B*64*h*w floats of
+ * `workspace` hold the four direction outputs as planes[k][b][d][i][j] (pixel order, k = 0..3 in
+ * the reference's direction order); the consumer sums them as ((p0 + p2) + p1) + p3, which is the
+ * reference's y1+y2+y3+y4 (wavemamba_arch.py:474-478,490).  wm_lfss_out_fwd does that sum. */
+int wm_ss2d_dirs_fwd(const float *x, const float *x_proj_weight, const float *dt_projs_weight,
+                     const float *dt_projs_bias, const float *A_logs, const float *Ds,
+                     void *workspace, size_t workspace_bytes, int64_t B, int64_t h, int64_t w,
+                     wm_stream_t stream);
 int wm_ss2d_core_fwd(const float *x, const float *x_proj_weight, const float *dt_projs_weight,
                      const float *dt_projs_bias, const float *A_logs, const float *Ds, float *y,
                      void *workspace, size_t workspace_bytes, int64_t B, int64_t h, int64_t w,
@@ -111,13 +119,15 @@ int wm_pw_fwd(const float *x, const float *pw_w, const float *pw_b, int gate_mod
 int wm_lfss_z_fwd(const float *x, const float *ln_w, const float *ln_b, float eps, const float *w_z,
                   float *zs, int64_t B, int64_t h, int64_t w, wm_stream_t stream);
 
-/* SS2D tail + LFSSBlock residual: out = x*skip_scale + out_proj( out_norm(y [+ y2]) * zs )
- * (out_norm :492, gate :493, out_proj :494, residual :525).  y, y2 (optional second addend, e.g.
- * the scan's column-direction plane), zs: (B,64,h,w); x, out: (B,32,h,w). */
-int wm_lfss_out_fwd(const float *y, const float *y2, const float *zs, const float *on_w,
-                    const float *on_b, float eps, const float *w_out, const float *x,
-                    const float *skip_scale, float *out, int64_t B, int64_t h, int64_t w,
-                    wm_stream_t stream);
+/* SS2D tail + LFSSBlock residual:
+ *   out = x*skip_scale + out_proj( out_norm(((y + ya) + yb) + yc) * zs )
+ * (4-way sum :490, out_norm :492, gate :493, out_proj :494, residual :525).  ya/yb/yc are optional
+ * (NULL) extra addends: pass the planes of wm_ss2d_dirs_fwd as y=p0, ya=p2, yb=p1, yc=p3.
+ * y*, zs: (B,64,h,w); x, out: (B,32,h,w). */
+int wm_lfss_out_fwd(const float *y, const float *ya, const float *yb, const float *yc,
+                    const float *zs, const float *on_w, const float *on_b, float eps,
+                    const float *w_out, const float *x, const float *skip_scale, float *out,
+                    int64_t B, int64_t h, int64_t w, wm_stream_t stream);
 
 /* PAConv gate: y = k3out * sigmoid( pw1x1(x) + b ), x and k3out and y all (B,64,h,w)
  * (PAConv.k2 + sigmoid + mul, :694-697).  In-place on k3out allowed (y == k3out). */

@@ -287,7 +287,7 @@ def test_lfss_z_and_out(ops, dev):
         yn = F.layer_norm(ysum.permute(0, 2, 3, 1), (64,), on_w, on_b, 1e-5)
         want = x * skip.view(1, -1, 1, 1) + F.linear(yn * want_z.permute(0, 2, 3, 1), w_out).permute(0, 3, 1, 2)
         got = ops.lfss_out(y.to(dev), zs, on_w.to(dev), on_b.to(dev), 1e-5, w_out.to(dev), x.to(dev),
-                           skip.to(dev), y2=None if second is None else second.to(dev)).cpu()
+                           skip.to(dev), extra=() if second is None else (second.to(dev),)).cpu()
         torch.testing.assert_close(got, want, rtol=3e-5, atol=3e-5)
 
 

@@ -122,15 +122,17 @@ class SS2D(nn.Module):
         three kernels around the scan, no permutes, no channels-last round trips.
             xc = silu(dwconv3x3(in_proj[:D] . ln(x)))          [pw_dw, LN prologue, SiLU epilogue]
             zs = silu(in_proj[D:] . ln(x))                      [lfss_z]
-            y  = forward_core(xc)                               [ss2d_core]
-            out = x*skip_scale + out_proj(out_norm(y) * zs)     [lfss_out]"""
+            p  = the four direction planes of the scan           [ss2d_dirs]
+            out = x*skip_scale + out_proj(out_norm(sum p) * zs)  [lfss_out]"""
         D = self.d_inner
         xc = ops.pw_dw(x, self.in_proj.weight[:D], None, self.conv2d.weight, self.conv2d.bias,
                        ln_w, ln_b, ln_eps, act="silu")
         zs = ops.lfss_z(x, ln_w, ln_b, ln_eps, self.in_proj.weight)
-        y = self.forward_core(xc)
-        return ops.lfss_out(y, zs, self.out_norm.weight, self.out_norm.bias, self.out_norm.eps,
-                            self.out_proj.weight, x, skip_scale)
+        p = ops.ss2d_dirs(xc, self.x_proj_weight, self.dt_projs_weight, self.dt_projs_bias,
+                          self.A_logs, self.Ds)
+        # reference sum order y1+y2+y3+y4 = ((dir0 + dir2) + dir1) + dir3, folded into lfss_out
+        return ops.lfss_out(p[0], zs, self.out_norm.weight, self.out_norm.bias, self.out_norm.eps,
+                            self.out_proj.weight, x, skip_scale, extra=(p[2], p[1], p[3]))
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """Reference calling convention: x (B,h,w,C) channels-last -> (B,h,w,C) (:480-497)."""

@@ -31,7 +31,7 @@ __device__ __forceinline__ float silu(float v) { return v / (1.0f + expf(-v)); }
 
 struct Args {
     const float *x;          // (B, CIN or 2*CIN, hw)
-    const float *x2;         // optional second addend for x (same shape), e.g. the scan's tmp plane
+    const float *xa, *xb_, *xc;  // optional addends, summed in this order: ((x + xa) + xb_) + xc
     const float *ln_w, *ln_b;
     float eps;
     const float *mul;        // kPreLNMul: (B, CIN, hw) multiplied after the LayerNorm
@@ -67,7 +67,9 @@ pixel_kernel(const Args a)
     const int64_t b = blockIdx.y;
     constexpr int XCH = PRE == kPreGate ? 2 * CIN : CIN;
     const float *xb = a.x + b * XCH * hw;
-    const float *x2b = a.x2 ? a.x2 + b * XCH * hw : nullptr;
+    const float *xa = a.xa ? a.xa + b * XCH * hw : nullptr;
+    const float *xb2 = a.xb_ ? a.xb_ + b * XCH * hw : nullptr;
+    const float *xc = a.xc ? a.xc + b * XCH * hw : nullptr;
     for (int64_t p = (int64_t)blockIdx.x * kThreads + tid; p < hw;
          p += (int64_t)gridDim.x * kThreads) {
         float xv[CIN];
@@ -77,7 +79,9 @@ pixel_kernel(const Args a)
                 xv[ci] = gelu_erf(__ldg(xb + ci * hw + p)) * __ldg(xb + (CIN + ci) * hw + p);
             } else {
                 xv[ci] = __ldg(xb + ci * hw + p);
-                if (x2b) xv[ci] += __ldg(x2b + ci * hw + p);
+                if (xa) xv[ci] += __ldg(xa + ci * hw + p);
+                if (xb2) xv[ci] += __ldg(xb2 + ci * hw + p);
+                if (xc) xv[ci] += __ldg(xc + ci * hw + p);
             }
         }
         if (PRE == kPreLN || PRE == kPreLNMul) {
@@ -240,17 +244,17 @@ extern "C" int wm_lfss_z_fwd(const float *x, const float *ln_w, const float *ln_
     return launch<32, 64, kPreLN, kPostSilu>(a, B, (cudaStream_t)stream, "lfss z");
 }
 
-extern "C" int wm_lfss_out_fwd(const float *y, const float *y2, const float *zs, const float *on_w,
-                               const float *on_b, float eps, const float *w_out, const float *x,
-                               const float *skip_scale, float *out, int64_t B, int64_t h, int64_t w,
-                               wm_stream_t stream)
+extern "C" int wm_lfss_out_fwd(const float *y, const float *ya, const float *yb, const float *yc,
+                               const float *zs, const float *on_w, const float *on_b, float eps,
+                               const float *w_out, const float *x, const float *skip_scale,
+                               float *out, int64_t B, int64_t h, int64_t w, wm_stream_t stream)
 {
     WM_REQUIRE(dims_ok(B, h, w), "wm_lfss_out_fwd: bad sizes");
     if (B == 0 || h == 0 || w == 0) return WM_OK;
     WM_REQUIRE(y && zs && on_w && on_b && w_out && x && skip_scale && out,
                "wm_lfss_out_fwd: null pointer");
     Args a = {};
-    a.x = y; a.x2 = y2; a.ln_w = on_w; a.ln_b = on_b; a.eps = eps; a.mul = zs; a.w = w_out;
+    a.x = y; a.xa = ya; a.xb_ = yb; a.xc = yc; a.ln_w = on_w; a.ln_b = on_b; a.eps = eps; a.mul = zs; a.w = w_out;
     a.res = x; a.res_scale = skip_scale; a.y = out; a.hw = h * w;
     return launch<64, 32, kPreLNMul, kPostNone>(a, B, (cudaStream_t)stream, "lfss out");
 }

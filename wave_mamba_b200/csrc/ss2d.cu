@@ -10,22 +10,28 @@
 //     k=0/2 (row-major, forward/backward): chunk = row_T consecutive positions of the
 //            flattened map (element stride +-1);
 //     k=1/3 (column-major, forward/backward): chunk = one image column (element stride +-w).
-//   One CTA (256 threads) owns NSEQ=4 neighbouring chunks ("strands") of one direction and all
-//   64 channels x 16 states of them: thread = (strand s, channel d) keeps h[16] in registers
-//   and walks its strand sequentially, TP=16 steps per tile.  For column directions the four
-//   strands are four adjacent columns, so a tile row is one 16-byte segment per channel.
-//   Per tile: stage x (64 ch x 64 positions) in shared memory -> per-position projection
-//   (34x64 mat-vec -> dt_low(2), B(16), C(16)) into shared memory -> 16 recurrence steps.
+//   One CTA (512 threads, 2 CTAs/SM) owns 4 neighbouring chunks ("strands") of one direction
+//   and all 64 channels x 16 states of them.  thread = (strand s, channel d, state half):
+//   8 states in registers, walked sequentially, 16 steps per tile.  For column directions the
+//   four strands are four adjacent columns, so a tile row is one 16-byte segment per channel.
+//
+// Per tile (64 positions x 64 channels), five phases separated by __syncthreads:
+//   load     cp.async 16-byte chunks -> xs[d][p]      (issued one tile ahead, overlaps the scan)
+//   project  pj[p][B16|C16|dt2] = W_k (34x64) . x[:,p]   on the tensor cores: mma.sync m16n8k8
+//            TF32 with the 3xTF32 split (a_lo*b_hi + a_hi*b_lo + a_hi*b_hi), fp32 accumulate
+//   delta    dd[d][p] = (dt, dt*u), dt = softplus(dt_proj . dt_low + bias); ys[d][p] = D*u
+//   scan     h = exp2(dt*A2)*h + dt*u*B ; y += C.h    packed FFMA2/FMUL2, MUFU ex2.approx
+//   store    ys[d][p] -> 16-byte coalesced stores into this direction's output plane (pass 2)
 //
 // Chunks are made independent with a three-phase carry scheme (the recurrence is linear):
 //   pass 1  every chunk from h=0: aggregate (P = prod a = exp2(A2*sum dt), H = local end state)
 //   carry   per (b,k,d,n): h_in[c] = P[c-1]*h_in[c-1] + H[c-1]          (tiny, sequential in c)
-//   pass 2  every chunk again from its true h_in, emitting y.
-// Merge order: launch A writes y <- dir0 and tmp <- dir1, launch B adds dir2 into y and dir3
-// into tmp (same thread, same element: deterministic), then y += tmp.
+//   pass 2  every chunk again from its true h_in, emitting y into one plane per direction.
+// The four planes are summed in the reference's order ((y0+y2)+y1)+y3 by the consumer
+// (wm_lfss_out_fwd) or by the combine kernel of wm_ss2d_core_fwd.  No atomics: deterministic.
 //
-// Roofline: not HBM-bound.  Each state update needs one MUFU ex2 and ~4 FMA-pipe ops and every
-// exp is evaluated twice (pass 1 and pass 2); see DESIGN.md section 4.
+// Roofline: not HBM-bound.  Each state update costs one MUFU ex2 (16/clk/SM) and every exp is
+// evaluated twice (pass 1 and pass 2); see DESIGN.md section 4.
 #include <initializer_list>
 
 #include "common.cuh"
@@ -40,11 +46,23 @@ constexpr int kProj = 34;    // dt_rank(2) + 2*d_state
 constexpr int kSeq = 4;      // strands per CTA
 constexpr int kTP = 16;      // steps per tile
 constexpr int kPos = kSeq * kTP;  // 64 positions per tile
-constexpr int kXS = 68;      // smem row stride of the x tile  [position][channel]
-constexpr int kPJ = 36;      // smem row stride of projections [position][B16|C16|dt2|pad2]
-constexpr int kWT = 40;      // smem row stride of weights     [channel][B16|C16|dt2|pad6]
-constexpr int kThreads = kSeq * kD;  // 256
+constexpr int kXS = 72;      // xs row stride  [channel][position]  (== 8 mod 32: mma A loads)
+constexpr int kPJ = 36;      // pj row stride  [position][B16|C16|dt2|pad2]
+constexpr int kDS = 65;      // dd row stride  [channel][position] float2 (odd: scan reads)
+constexpr int kYS = 65;      // ys row stride  [channel][position]
+constexpr int kThreads = 512;
 constexpr int kChains = kD * kN;     // 1024 (d,n) chains per direction
+constexpr int kNTiles = 5;           // mma n-tiles: B0-7, B8-15, C0-7, C8-15, dt(2)+pad
+
+// shared memory carve-up (floats)
+constexpr int kOffXs = 0;
+constexpr int kOffPj = kOffXs + kD * kXS;               // 4608
+constexpr int kOffDd = kOffPj + kPos * kPJ;             // +2304
+constexpr int kOffYs = kOffDd + kD * kDS * 2;           // +8320
+constexpr int kOffWf = kOffYs + kD * kYS;               // +4160
+constexpr int kOffCst = kOffWf + 8 * kNTiles * 32 * 4;  // +5120
+constexpr int kSmemFloats = kOffCst + 4 * kD;           // +256
+constexpr size_t kSmemBytes = sizeof(float) * kSmemFloats;   // 99,072 B -> 2 CTAs per SM
 
 struct Geom {
     int B, h, w;
@@ -54,7 +72,8 @@ struct Geom {
     int row_ctas;    // ceil(row_chunks / kSeq)
     int col_ctas;    // ceil(w / kSeq)
     int max_chunks;  // max(row_chunks, w): chunk stride of the aggregate arrays
-    int vec_rows;    // 1 when row tiles may use 128-bit global accesses
+    int vec_rows;    // 1 when row tiles may use 16-byte global accesses (L % 4 == 0)
+    int vec_cols;    // 1 when column tiles may (w % 4 == 0)
 };
 
 struct Launch {
@@ -70,272 +89,431 @@ struct Params {
     const float *dt_b;         // (4,64)
     const float *A_logs;       // (256,16)
     const float *Ds;           // (256)
-    float *y;                  // (B,64,L)  dirs 0,2
-    float *tmp;                // (B,64,L)  dirs 1,3
+    float *planes;             // (4,B,64,L) per-direction outputs, pixel-major
     float *aggP;               // (B,4,max_chunks,1024)
     float *aggH;               // (B,4,max_chunks,1024)  pass 1: local end state; after carry: h_in
 };
 
-__device__ __forceinline__ float softplus_ref(float v)
+// ---- packed fp32x2 helpers (Blackwell FFMA2 / FMUL2) ---------------------------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi)
 {
-    // torch softplus (beta 1, threshold 20) == mamba's `x <= 20 ? log1pf(expf(x)) : x`
-    return v > 20.0f ? v : log1pf(expf(v));
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fmul2(f32x2 a, f32x2 b)
+{
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 ex2_2(f32x2 v)
+{
+    float lo, hi;
+    unpack2(v, lo, hi);
+    return pack2(ex2_approx(lo), ex2_approx(hi));
 }
 
-struct Strand {
-    int64_t base;  // element offset (inside one channel plane) of step 0
-    int64_t step;  // element stride per step: +-1 or +-w
-    int len;       // number of steps (0: strand does not exist)
-    int chunk;     // chunk index in sequence order
+// ---- tensor-core helpers ------------------------------------------------------------------
+__device__ __forceinline__ uint32_t to_tf32(float v)
+{
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0,
+                                         uint32_t b1)
+{
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
+        "{%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async16(float *smem_dst, const float *gmem_src)
+{
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// softplus (torch: beta 1, threshold 20) = max(v,0) + log1p(exp(-|v|)), with
+// log1p(e) = 2 atanh(e / (2 + e)), e in (0,1]: odd series in s = e/(2+e) <= 1/3 up to s^13.
+// Relative error <= 2e-7 for |v| < 15 (8e-7 worst case from the ex2 argument rounding beyond).
+__device__ __forceinline__ float softplus_fast(float v)
+{
+    const float e = ex2_approx(-fabsf(v) * 1.4426950408889634f);
+    const float s = __fdividef(e, 2.0f + e);
+    const float t = s * s;
+    float p = fmaf(t, 0.07692307692f, 0.09090909091f);
+    p = fmaf(p, t, 0.11111111111f);
+    p = fmaf(p, t, 0.14285714286f);
+    p = fmaf(p, t, 0.2f);
+    p = fmaf(p, t, 0.33333333333f);
+    p = fmaf(p, t, 1.0f);
+    const float sp = fmaf(2.0f * s, p, fmaxf(v, 0.0f));
+    return v > 20.0f ? v : sp;
+}
+
+struct TileGeom {
+    // this CTA's 4 strands live in one memory band; tile ti covers steps [16 ti, 16 ti + 16)
+    int k;          // direction
+    bool col;       // column-major direction
+    bool fwd;       // forward direction (0 or 1)
+    int chunk0;     // sequence-order chunk index of strand 0
+    int maxlen;     // steps per full chunk (row_T or h)
 };
 
-__device__ __forceinline__ Strand make_strand(const Geom &g, int k, int q, int s)
+// number of valid steps of strand s
+__device__ __forceinline__ int strand_len(const Geom &g, const TileGeom &tg, int s)
 {
-    Strand st;
-    st.chunk = q * kSeq + s;
-    if ((k & 1) == 0) {  // row-major directions
-        const int64_t start = (int64_t)st.chunk * g.row_T;
-        int64_t rem = g.L - start;
-        st.len = rem <= 0 ? 0 : (rem < g.row_T ? (int)rem : g.row_T);
-        st.base = (k == 0) ? start : g.L - 1 - start;
-        st.step = (k == 0) ? 1 : -1;
-    } else {  // column-major directions: chunk = one column
-        st.len = st.chunk < g.w ? g.h : 0;
-        const int j = (k == 1) ? st.chunk : g.w - 1 - st.chunk;
-        st.base = (k == 1) ? (int64_t)j : (int64_t)(g.h - 1) * g.w + j;
-        st.step = (k == 1) ? (int64_t)g.w : -(int64_t)g.w;
-    }
-    return st;
+    const int c = tg.chunk0 + s;
+    if (tg.col) return c < g.w ? g.h : 0;
+    const int64_t rem = g.L - (int64_t)c * g.row_T;
+    return rem <= 0 ? 0 : (rem < g.row_T ? (int)rem : g.row_T);
 }
 
-__device__ __forceinline__ void load_tile(const float *__restrict__ plane, const Strand &st,
-                                          int ti, bool vec_rows, float (&u)[kTP])
+// element offset (inside a channel plane) of step t of strand s
+__device__ __forceinline__ int64_t strand_elem(const Geom &g, const TileGeom &tg, int s, int t)
 {
-    const int t0 = ti * kTP;
-    int nvalid = st.len - t0;
-    nvalid = nvalid < 0 ? 0 : (nvalid > kTP ? kTP : nvalid);
-    if (nvalid == kTP && vec_rows && st.step == 1) {
-        const float4 *p = reinterpret_cast<const float4 *>(plane + st.base + t0);
+    const int c = tg.chunk0 + s;
+    if (!tg.col) {
+        const int64_t l = (int64_t)c * g.row_T + t;       // sequence index
+        return tg.fwd ? l : g.L - 1 - l;
+    }
+    const int j = tg.fwd ? c : g.w - 1 - c;
+    const int i = tg.fwd ? t : g.h - 1 - t;
+    return (int64_t)i * g.w + j;
+}
+
+// smem position index of (strand s, step e within the tile): mirrors memory order so that
+// 16-byte global chunks land contiguously
+__device__ __forceinline__ int tile_pos(const TileGeom &tg, int s, int e)
+{
+    if (!tg.col) return s * kTP + (tg.fwd ? e : kTP - 1 - e);
+    return e * kSeq + (tg.fwd ? s : kSeq - 1 - s);
+}
+
+// Is tile ti a full, 16-byte-addressable tile?  (all 4 strands present, 16 valid steps)
+__device__ __forceinline__ bool tile_is_vec(const Geom &g, const TileGeom &tg, int ti)
+{
+    const int t_end = ti * kTP + kTP;
+    if (tg.col)
+        return g.vec_cols && tg.chunk0 + kSeq <= g.w && t_end <= g.h;
+    return g.vec_rows && (int64_t)(tg.chunk0 + kSeq - 1) * g.row_T + t_end <= g.L;
+}
+
+// Global offset (inside a channel plane) of the 16-byte chunk `cidx` (0..15) of a vec tile and
+// the smem position of its first element.  Rows: chunk = (s, v) -> 4 consecutive steps.
+// Columns: chunk = e -> the 4 strands of one image row.
+__device__ __forceinline__ void vec_chunk(const Geom &g, const TileGeom &tg, int ti, int cidx,
+                                          int64_t &goff, int &p0)
+{
+    if (!tg.col) {
+        const int s = cidx >> 2, v = cidx & 3;
+        const int64_t l0 = (int64_t)(tg.chunk0 + s) * g.row_T + ti * kTP;  // first step of the tile
+        // memory-ascending chunk v of the 16 elements of this strand's tile
+        goff = tg.fwd ? l0 + 4 * v : g.L - 1 - l0 - (kTP - 1) + 4 * v;
+        p0 = s * kTP + 4 * v;
+    } else {
+        const int e = cidx;
+        const int i = tg.fwd ? ti * kTP + e : g.h - 1 - (ti * kTP + e);
+        const int jlow = tg.fwd ? tg.chunk0 : g.w - kSeq - tg.chunk0;
+        goff = (int64_t)i * g.w + jlow;
+        p0 = e * kSeq;
+    }
+}
+
+__device__ __forceinline__ void load_tile(const Geom &g, const TileGeom &tg, int ti,
+                                          const float *__restrict__ xb, float *xs)
+{
+    const int tid = threadIdx.x;
+    if (tile_is_vec(g, tg, ti)) {
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-            const float4 f = __ldg(p + v);
-            u[4 * v + 0] = f.x; u[4 * v + 1] = f.y; u[4 * v + 2] = f.z; u[4 * v + 3] = f.w;
+        for (int r = 0; r < 2; ++r) {
+            const int idx = tid + r * kThreads;      // 0..1023 = (d, chunk)
+            const int d = idx >> 4, cidx = idx & 15;
+            int64_t goff; int p0;
+            vec_chunk(g, tg, ti, cidx, goff, p0);
+            cp_async16(xs + d * kXS + p0, xb + (int64_t)d * g.L + goff);
         }
-    } else if (nvalid == kTP && vec_rows && st.step == -1) {
-        const float4 *p = reinterpret_cast<const float4 *>(plane + st.base - t0 - (kTP - 1));
+    } else {
+        // ragged tile: scalar loads, zero fill
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-            const float4 f = __ldg(p + v);  // ascending memory = descending step
-            u[15 - 4 * v] = f.x; u[14 - 4 * v] = f.y; u[13 - 4 * v] = f.z; u[12 - 4 * v] = f.w;
+        for (int r = 0; r < 8; ++r) {
+            const int idx = tid + r * kThreads;      // 0..4095 = (d, s, e)
+            const int d = idx >> 6, s = (idx >> 4) & 3, e = idx & 15;
+            const int t = ti * kTP + e;
+            float v = 0.0f;
+            if (t < strand_len(g, tg, s)) v = __ldg(xb + (int64_t)d * g.L + strand_elem(g, tg, s, t));
+            xs[d * kXS + tile_pos(tg, s, e)] = v;
+        }
+    }
+    cp_async_commit();
+}
+
+__device__ __forceinline__ void store_tile(const Geom &g, const TileGeom &tg, int ti,
+                                           float *__restrict__ ob, const float *ys)
+{
+    const int tid = threadIdx.x;
+    if (tile_is_vec(g, tg, ti)) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int idx = tid + r * kThreads;
+            const int d = idx >> 4, cidx = idx & 15;
+            int64_t goff; int p0;
+            vec_chunk(g, tg, ti, cidx, goff, p0);
+            const float *src = ys + d * kYS + p0;
+            const float4 v = make_float4(src[0], src[1], src[2], src[3]);
+            *reinterpret_cast<float4 *>(ob + (int64_t)d * g.L + goff) = v;
         }
     } else {
 #pragma unroll
-        for (int e = 0; e < kTP; ++e)
-            u[e] = e < nvalid ? __ldg(plane + st.base + (int64_t)(t0 + e) * st.step) : 0.0f;
+        for (int r = 0; r < 8; ++r) {
+            const int idx = tid + r * kThreads;
+            const int d = idx >> 6, s = (idx >> 4) & 3, e = idx & 15;
+            const int t = ti * kTP + e;
+            if (t < strand_len(g, tg, s))
+                ob[(int64_t)d * g.L + strand_elem(g, tg, s, t)] = ys[d * kYS + tile_pos(tg, s, e)];
+        }
     }
 }
 
-template <bool ACCUM>
-__device__ __forceinline__ void store_tile(float *__restrict__ plane, const Strand &st, int ti,
-                                           bool vec_rows, const float (&yv)[kTP])
-{
-    const int t0 = ti * kTP;
-    int nvalid = st.len - t0;
-    nvalid = nvalid < 0 ? 0 : (nvalid > kTP ? kTP : nvalid);
-    if (nvalid == kTP && vec_rows && (st.step == 1 || st.step == -1)) {
-        const bool fwd = st.step == 1;
-        float4 *p = reinterpret_cast<float4 *>(fwd ? plane + st.base + t0
-                                                   : plane + st.base - t0 - (kTP - 1));
-        float4 old[4];
-        if (ACCUM) {
-#pragma unroll
-            for (int v = 0; v < 4; ++v) old[v] = p[v];
-        }
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
-            float4 f;
-            if (fwd) {
-                f = make_float4(yv[4 * v], yv[4 * v + 1], yv[4 * v + 2], yv[4 * v + 3]);
-            } else {
-                f = make_float4(yv[15 - 4 * v], yv[14 - 4 * v], yv[13 - 4 * v], yv[12 - 4 * v]);
-            }
-            if (ACCUM) { f.x += old[v].x; f.y += old[v].y; f.z += old[v].z; f.w += old[v].w; }
-            p[v] = f;
-        }
-    } else {
-        float old[kTP];
-        if (ACCUM) {
-#pragma unroll
-            for (int e = 0; e < kTP; ++e)
-                old[e] = e < nvalid ? plane[st.base + (int64_t)(t0 + e) * st.step] : 0.0f;
-        }
-#pragma unroll
-        for (int e = 0; e < kTP; ++e)
-            if (e < nvalid)
-                plane[st.base + (int64_t)(t0 + e) * st.step] = ACCUM ? old[e] + yv[e] : yv[e];
-    }
-}
-
-// FINAL=false: pass 1 (aggregates).  FINAL=true: pass 2 (outputs); ACCUM adds into the
-// destination instead of overwriting it.
-template <bool FINAL, bool ACCUM>
+// FINAL=false: pass 1 (aggregates).  FINAL=true: pass 2 (outputs).
+template <bool FINAL>
 __global__ void __launch_bounds__(kThreads, 2)
 ss2d_pass_kernel(const Params prm, const Geom g, const Launch ln)
 {
-    __shared__ __align__(16) float xs[kPos * kXS];
-    __shared__ __align__(16) float pj[kPos * kPJ];
-    __shared__ __align__(16) float wt[kD * kWT];
+    extern __shared__ __align__(16) float smem[];
+    float *xs = smem + kOffXs;
+    float *pj = smem + kOffPj;
+    float2 *dd = reinterpret_cast<float2 *>(smem + kOffDd);
+    float *ys = smem + kOffYs;
+    float4 *wf = reinterpret_cast<float4 *>(smem + kOffWf);
+    float *cst = smem + kOffCst;   // [dtw0 | dtw1 | dtb | Dskip] x 64
 
     const int tid = threadIdx.x;
-    const int s = tid >> 6, d = tid & 63;
+    const int lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y;
 
-    // which direction / which CTA inside that direction
     int slot = 0;
 #pragma unroll
     for (int i = 1; i < 4; ++i)
         if (i < ln.ndirs && (int)blockIdx.x >= ln.cta_begin[i]) slot = i;
-    const int k = ln.dir[slot];
-    const int q = blockIdx.x - ln.cta_begin[slot];
+    TileGeom tg;
+    tg.k = ln.dir[slot];
+    tg.col = (tg.k & 1) != 0;
+    tg.fwd = tg.k < 2;
+    tg.chunk0 = (blockIdx.x - ln.cta_begin[slot]) * kSeq;
+    tg.maxlen = tg.col ? g.h : g.row_T;
+    const int k = tg.k;
+    const int ntiles = (tg.maxlen + kTP - 1) / kTP;
 
-    // ---- per-CTA weights: wt[d][0..15]=B rows, [16..31]=C rows, [32..33]=dt rows ------------
-    // x_proj_weight[k] is (34,64) with rows [dt(2) | B(16) | C(16)]  (reference :454 split)
-    for (int i = tid; i < kProj * kD; i += kThreads) {
-        const int row = i / kD, col = i - row * kD;
-        const int dst = row < 2 ? 32 + row : row - 2;
-        wt[col * kWT + dst] = __ldg(prm.x_proj_w + (int64_t)k * kProj * kD + i);
+    const float *xb = prm.x + (int64_t)b * kD * g.L;
+    load_tile(g, tg, 0, xb, xs);   // in flight while the weights are prepared
+
+    // ---- mma B fragments of W_k, pre-split into tf32 hi/lo -----------------------------------
+    // n-tile nt, column n (0..7) -> row of x_proj_weight[k] (34,64) = [dt(2) | B(16) | C(16)]
+    for (int i = tid; i < 8 * kNTiles * 32; i += kThreads) {
+        const int ln_ = i & 31, nt = (i >> 5) % kNTiles, ks = i / (32 * kNTiles);
+        const int gq = ln_ >> 2, t4 = ln_ & 3;
+        int row;  // source row for output column n = gq of n-tile nt
+        if (nt < 4) row = 2 + nt * 8 + gq;            // B0..15 -> rows 2..17, C0..15 -> rows 18..33
+        else row = gq < 2 ? gq : -1;                  // dt rows 0,1; rest zero padding
+        float w0 = 0.0f, w1 = 0.0f;
+        if (row >= 0) {
+            const float *wr = prm.x_proj_w + ((int64_t)k * kProj + row) * kD + ks * 8;
+            w0 = __ldg(wr + t4);
+            w1 = __ldg(wr + t4 + 4);
+        }
+        const uint32_t h0 = to_tf32(w0), h1 = to_tf32(w1);
+        const uint32_t l0 = to_tf32(w0 - __uint_as_float(h0)), l1 = to_tf32(w1 - __uint_as_float(h1));
+        wf[i] = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(l0),
+                            __uint_as_float(l1));
+    }
+    if (tid < kD) {
+        const int ch = k * kD + tid;
+        cst[tid] = __ldg(prm.dt_w + ch * 2 + 0);
+        cst[kD + tid] = __ldg(prm.dt_w + ch * 2 + 1);
+        cst[2 * kD + tid] = __ldg(prm.dt_b + ch);
+        cst[3 * kD + tid] = __ldg(prm.Ds + ch);
     }
 
-    // ---- per-thread constants ---------------------------------------------------------------
+    // ---- scan-thread identity: (strand, channel, state half) -------------------------------
+    const int s = tid >> 7, d = (tid & 127) >> 1, half = tid & 1;
     const int ch = k * kD + d;
-    float A2[kN];  // A * log2(e), A = -exp(A_log)   (reference :462)
+    f32x2 A2[4];  // A * log2(e), A = -exp(A_log)   (reference :462)
 #pragma unroll
-    for (int n = 0; n < kN; ++n)
-        A2[n] = -expf(__ldg(prm.A_logs + (int64_t)ch * kN + n)) * 1.4426950408889634f;
-    const float dtw0 = __ldg(prm.dt_w + ch * 2 + 0), dtw1 = __ldg(prm.dt_w + ch * 2 + 1);
-    const float dtb = __ldg(prm.dt_b + ch);
-    const float skipD = __ldg(prm.Ds + ch);
-
-    const Strand st = make_strand(g, k, q, s);
-    const int maxlen = (k & 1) ? g.h : g.row_T;
-    const int ntiles = (maxlen + kTP - 1) / kTP;
-    const bool vec_rows = g.vec_rows != 0;
-
-    const int64_t plane_off = ((int64_t)b * kD + d) * g.L;
-    const float *xplane = prm.x + plane_off;
+    for (int j = 0; j < 4; ++j) {
+        const float *ap = prm.A_logs + (int64_t)ch * kN + half * 8 + 2 * j;
+        A2[j] = pack2(-expf(__ldg(ap)) * 1.4426950408889634f,
+                      -expf(__ldg(ap + 1)) * 1.4426950408889634f);
+    }
+    const int my_len = strand_len(g, tg, s);
+    const int my_chunk = tg.chunk0 + s;
     const int64_t agg_off =
-        (((int64_t)b * kK + k) * g.max_chunks + st.chunk) * kChains + (int64_t)d * kN;
+        (((int64_t)b * kK + k) * g.max_chunks + my_chunk) * kChains + (int64_t)d * kN + half * 8;
 
-    float hst[kN];
+    f32x2 hst[4];
 #pragma unroll
-    for (int n = 0; n < kN; ++n) hst[n] = 0.0f;
-    if (FINAL && st.len > 0 && st.chunk > 0) {
+    for (int j = 0; j < 4; ++j) hst[j] = pack2(0.0f, 0.0f);
+    if (FINAL && my_len > 0 && my_chunk > 0) {
         const float4 *hp = reinterpret_cast<const float4 *>(prm.aggH + agg_off);
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
-            const float4 f = hp[v];
-            hst[4 * v] = f.x; hst[4 * v + 1] = f.y; hst[4 * v + 2] = f.z; hst[4 * v + 3] = f.w;
-        }
+        const float4 f0 = hp[0], f1 = hp[1];
+        hst[0] = pack2(f0.x, f0.y); hst[1] = pack2(f0.z, f0.w);
+        hst[2] = pack2(f1.x, f1.y); hst[3] = pack2(f1.z, f1.w);
     }
     double sum_dt = 0.0;
 
-    float unext[kTP];
-    load_tile(xplane, st, 0, vec_rows, unext);
+    float *oplane = FINAL ? prm.planes + (((int64_t)k * g.B + b) * kD) * g.L : nullptr;
 
-    const int pp = tid & 63, og = tid >> 6;  // projection mapping: position, output octet
+    // projection role of this warp: m-tile (16 positions) and a set of n-tiles
+    const int mt = warp & 3, nq = warp >> 2;
+    int nt_first, nt_count;
+    if (FINAL) { nt_first = nq; nt_count = 1; }                 // q: B0-7 | B8-15 | C0-7 | C8-15
+    else { nt_first = nq < 2 ? nq : 4; nt_count = nq < 3 ? 1 : 0; }  // B0-7 | B8-15 | dt | idle
+    const bool also_dt = FINAL && nq == 0;                      // pass 2: warps 0-3 add the dt tile
 
     for (int ti = 0; ti < ntiles; ++ti) {
-        // stage this tile's x: xs[position][channel]
-#pragma unroll
-        for (int e = 0; e < kTP; ++e) xs[(s * kTP + e) * kXS + d] = unext[e];
-        __syncthreads();
-        if (ti + 1 < ntiles) load_tile(xplane, st, ti + 1, vec_rows, unext);
+        cp_async_wait_all();
+        __syncthreads();                       // xs(ti) landed; previous tile fully consumed
 
-        // ---- projection: pj[p][c] = sum_d W[c][d] * x[d][p]            (reference :453) ----
-        {
-            float acc[8];
+        // ---- projection on tensor cores (reference :453) ---------------------------------
+        if (nt_count > 0) {
+            float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+            const int gq = lane >> 2, t4 = lane & 3;
+            const float *abase = xs + t4 * kXS + mt * 16 + gq;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
-            float accdt = 0.0f;
-            const float *xrow = xs + pp * kXS;
-#pragma unroll 4
-            for (int d4 = 0; d4 < kD; d4 += 4) {
-                const float4 xv = *reinterpret_cast<const float4 *>(xrow + d4);
-                const float xe[4] = {xv.x, xv.y, xv.z, xv.w};
+            for (int ks = 0; ks < 8; ++ks) {
+                const float *ap = abase + ks * 8 * kXS;
+                const float av[4] = {ap[0], ap[8], ap[4 * kXS], ap[4 * kXS + 8]};
+                uint32_t ahi[4], alo[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float *wr = wt + (d4 + j) * kWT;
-                    const float4 w0 = *reinterpret_cast<const float4 *>(wr + og * 8);
-                    const float4 w1 = *reinterpret_cast<const float4 *>(wr + og * 8 + 4);
-                    acc[0] = fmaf(xe[j], w0.x, acc[0]); acc[1] = fmaf(xe[j], w0.y, acc[1]);
-                    acc[2] = fmaf(xe[j], w0.z, acc[2]); acc[3] = fmaf(xe[j], w0.w, acc[3]);
-                    acc[4] = fmaf(xe[j], w1.x, acc[4]); acc[5] = fmaf(xe[j], w1.y, acc[5]);
-                    acc[6] = fmaf(xe[j], w1.z, acc[6]); acc[7] = fmaf(xe[j], w1.w, acc[7]);
-                    if (og < 2) accdt = fmaf(xe[j], wr[32 + og], accdt);
+                for (int i = 0; i < 4; ++i) {
+                    ahi[i] = to_tf32(av[i]);
+                    alo[i] = to_tf32(av[i] - __uint_as_float(ahi[i]));
+                }
+                const float4 bw = wf[(ks * kNTiles + nt_first) * 32 + lane];
+                mma_tf32(c0, alo, __float_as_uint(bw.x), __float_as_uint(bw.y));
+                mma_tf32(c0, ahi, __float_as_uint(bw.z), __float_as_uint(bw.w));
+                mma_tf32(c0, ahi, __float_as_uint(bw.x), __float_as_uint(bw.y));
+                if (also_dt) {
+                    const float4 bd = wf[(ks * kNTiles + 4) * 32 + lane];
+                    mma_tf32(c1, alo, __float_as_uint(bd.x), __float_as_uint(bd.y));
+                    mma_tf32(c1, ahi, __float_as_uint(bd.z), __float_as_uint(bd.w));
+                    mma_tf32(c1, ahi, __float_as_uint(bd.x), __float_as_uint(bd.y));
                 }
             }
-            float *pr = pj + pp * kPJ;
-            *reinterpret_cast<float4 *>(pr + og * 8) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-            *reinterpret_cast<float4 *>(pr + og * 8 + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
-            if (og < 2) pr[32 + og] = accdt;
+            float *pr = pj + (mt * 16 + gq) * kPJ;
+            if (nt_first < 4) {
+                *reinterpret_cast<float2 *>(pr + nt_first * 8 + 2 * t4) = make_float2(c0[0], c0[1]);
+                *reinterpret_cast<float2 *>(pr + 8 * kPJ + nt_first * 8 + 2 * t4) = make_float2(c0[2], c0[3]);
+            } else if (t4 == 0) {
+                *reinterpret_cast<float2 *>(pr + 32) = make_float2(c0[0], c0[1]);
+                *reinterpret_cast<float2 *>(pr + 8 * kPJ + 32) = make_float2(c0[2], c0[3]);
+            }
+            if (also_dt && t4 == 0) {
+                *reinterpret_cast<float2 *>(pr + 32) = make_float2(c1[0], c1[1]);
+                *reinterpret_cast<float2 *>(pr + 8 * kPJ + 32) = make_float2(c1[2], c1[3]);
+            }
         }
         __syncthreads();
 
-        // ---- recurrence over the 16 steps of this tile                (reference :465-471) ----
-        float yv[kTP];
-        const int nvalid = st.len - ti * kTP;  // warp-uniform (a warp lies inside one strand)
+        // ---- delta phase: dt = softplus(dt_proj . dt_low + bias)  (reference :455, scan_fn) --
+        // warp w owns channels 4w..4w+3; lane = position within a 32-position round
 #pragma unroll
-        for (int e = 0; e < kTP; ++e) {
-            yv[e] = 0.0f;
-            if (e < nvalid) {
-                const int p = s * kTP + e;
-                const float *pr = pj + p * kPJ;
-                const float u = xs[p * kXS + d];
-                const float2 dlow = *reinterpret_cast<const float2 *>(pr + 32);
-                // dt_proj (reference :455) then + bias, softplus (selective_scan_fn)
-                const float dt = softplus_ref(fmaf(dtw1, dlow.y, dtw0 * dlow.x) + dtb);
-                const float dtu = dt * u;
-                if (!FINAL) sum_dt += (double)dt;
-                float acc = 0.0f;
+        for (int rnd = 0; rnd < 2; ++rnd) {
+            const int p = rnd * 32 + lane;
+            const float2 dlow = *reinterpret_cast<const float2 *>(pj + p * kPJ + 32);
 #pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    const float4 bq = *reinterpret_cast<const float4 *>(pr + 4 * v);
-                    const float bb[4] = {bq.x, bq.y, bq.z, bq.w};
-                    float cc[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int i = 0; i < 4; ++i) {
+                const int dc = warp * 4 + i;
+                const float u = xs[dc * kXS + p];
+                const float raw = fmaf(cst[kD + dc], dlow.y, cst[dc] * dlow.x) + cst[2 * kD + dc];
+                const float dt = softplus_fast(raw);
+                dd[dc * kDS + p] = make_float2(dt, dt * u);
+                if (FINAL) ys[dc * kYS + p] = cst[3 * kD + dc] * u;
+            }
+        }
+        __syncthreads();                       // xs is dead from here on
+
+        if (ti + 1 < ntiles) load_tile(g, tg, ti + 1, xb, xs);
+
+        // ---- recurrence over the 16 steps of this tile        (reference :465-471) --------
+        {
+            const int nvalid = my_len - ti * kTP;          // warp-uniform
+            const float2 *ddrow = dd + d * kDS;
+            float *ysrow = ys + d * kYS;
+#pragma unroll 4
+            for (int e = 0; e < kTP; ++e) {
+                if (e < nvalid) {
+                    const int p = tile_pos(tg, s, e);
+                    const float2 dv = ddrow[p];
+                    const float *pr = pj + p * kPJ + half * 8;
+                    const float4 b0 = *reinterpret_cast<const float4 *>(pr);
+                    const float4 b1 = *reinterpret_cast<const float4 *>(pr + 4);
+                    const f32x2 dt2 = pack2(dv.x, dv.x), du2 = pack2(dv.y, dv.y);
+                    const f32x2 bb[4] = {pack2(b0.x, b0.y), pack2(b0.z, b0.w), pack2(b1.x, b1.y),
+                                         pack2(b1.z, b1.w)};
+                    if (!FINAL) sum_dt += (double)dv.x;
+                    f32x2 acc = pack2(0.0f, 0.0f);
+                    f32x2 cc[4];
                     if (FINAL) {
-                        const float4 cq = *reinterpret_cast<const float4 *>(pr + 16 + 4 * v);
-                        cc[0] = cq.x; cc[1] = cq.y; cc[2] = cq.z; cc[3] = cq.w;
+                        const float4 c0 = *reinterpret_cast<const float4 *>(pr + 16);
+                        const float4 c1 = *reinterpret_cast<const float4 *>(pr + 20);
+                        cc[0] = pack2(c0.x, c0.y); cc[1] = pack2(c0.z, c0.w);
+                        cc[2] = pack2(c1.x, c1.y); cc[3] = pack2(c1.z, c1.w);
                     }
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const int n = 4 * v + j;
-                        const float a = ex2_approx(dt * A2[n]);
-                        hst[n] = fmaf(a, hst[n], dtu * bb[j]);
-                        if (FINAL) acc = fmaf(hst[n], cc[j], acc);
+                        const f32x2 a = ex2_2(fmul2(dt2, A2[j]));
+                        hst[j] = ffma2(a, hst[j], fmul2(du2, bb[j]));
+                        if (FINAL) acc = ffma2(hst[j], cc[j], acc);
+                    }
+                    if (FINAL) {
+                        float lo, hi;
+                        unpack2(acc, lo, hi);
+                        float y = lo + hi;
+                        y += __shfl_xor_sync(0xffffffffu, y, 1);
+                        if (half == 0) ysrow[p] += y;     // ys held D*u
                     }
                 }
-                if (FINAL) yv[e] = fmaf(skipD, u, acc);
             }
         }
         if (FINAL) {
-            float *oplane = ((k & 1) ? prm.tmp : prm.y) + plane_off;
-            store_tile<ACCUM>(oplane, st, ti, vec_rows, yv);
+            __syncthreads();
+            store_tile(g, tg, ti, oplane, ys);
         }
-        __syncthreads();  // xs / pj are rewritten by the next tile
     }
 
-    if (!FINAL && st.len > 0) {
+    if (!FINAL && my_len > 0) {
         float4 *pp4 = reinterpret_cast<float4 *>(prm.aggP + agg_off);
         float4 *hp4 = reinterpret_cast<float4 *>(prm.aggH + agg_off);
+        float pv[8], hv[8];
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-            float pv[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                pv[j] = ex2_approx((float)((double)A2[4 * v + j] * sum_dt));
-            pp4[v] = make_float4(pv[0], pv[1], pv[2], pv[3]);
-            hp4[v] = make_float4(hst[4 * v], hst[4 * v + 1], hst[4 * v + 2], hst[4 * v + 3]);
+        for (int j = 0; j < 4; ++j) {
+            float a_lo, a_hi;
+            unpack2(A2[j], a_lo, a_hi);
+            pv[2 * j] = ex2_approx((float)((double)a_lo * sum_dt));
+            pv[2 * j + 1] = ex2_approx((float)((double)a_hi * sum_dt));
+            unpack2(hst[j], hv[2 * j], hv[2 * j + 1]);
         }
+        pp4[0] = make_float4(pv[0], pv[1], pv[2], pv[3]);
+        pp4[1] = make_float4(pv[4], pv[5], pv[6], pv[7]);
+        hp4[0] = make_float4(hv[0], hv[1], hv[2], hv[3]);
+        hp4[1] = make_float4(hv[4], hv[5], hv[6], hv[7]);
     }
 }
 
@@ -351,15 +529,15 @@ ss2d_carry_kernel(const float *__restrict__ aggP, float *__restrict__ aggH, Geom
     float *H = aggH + off;
     float carry = 0.0f;
     int c = 0;
-    for (; c + 4 <= nchunks; c += 4) {
-        float p[4], hv[4];
+    for (; c + 8 <= nchunks; c += 8) {
+        float p[8], hv[8];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 8; ++i) {
             p[i] = P[(int64_t)(c + i) * kChains];
             hv[i] = H[(int64_t)(c + i) * kChains];
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 8; ++i) {
             H[(int64_t)(c + i) * kChains] = carry;
             carry = fmaf(p[i], carry, hv[i]);
         }
@@ -371,22 +549,25 @@ ss2d_carry_kernel(const float *__restrict__ aggP, float *__restrict__ aggH, Geom
     }
 }
 
+// y = ((p0 + p2) + p1) + p3   -- the reference's y1 + y2 + y3 + y4 order (:474-478,490)
 __global__ void __launch_bounds__(256)
-ss2d_combine_kernel(float *__restrict__ y, const float *__restrict__ tmp, int64_t n, int vec)
+ss2d_combine_kernel(float *__restrict__ y, const float *__restrict__ planes, int64_t n, int vec)
 {
     const int64_t stride = (int64_t)gridDim.x * 256;
+    const float *p0 = planes, *p1 = planes + n, *p2 = planes + 2 * n, *p3 = planes + 3 * n;
     if (vec) {
         const int64_t n4 = n >> 2;
-        float4 *y4 = reinterpret_cast<float4 *>(y);
-        const float4 *t4 = reinterpret_cast<const float4 *>(tmp);
         for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += stride) {
-            float4 a = y4[i];
-            const float4 t = ld_stream4(reinterpret_cast<const float *>(t4 + i));
-            a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
-            y4[i] = a;
+            const float4 a = ld_stream4(p0 + 4 * i), b = ld_stream4(p1 + 4 * i);
+            const float4 c = ld_stream4(p2 + 4 * i), dq = ld_stream4(p3 + 4 * i);
+            float4 r;
+            r.x = ((a.x + c.x) + b.x) + dq.x; r.y = ((a.y + c.y) + b.y) + dq.y;
+            r.z = ((a.z + c.z) + b.z) + dq.z; r.w = ((a.w + c.w) + b.w) + dq.w;
+            *reinterpret_cast<float4 *>(y + 4 * i) = r;
         }
     } else {
-        for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) y[i] += tmp[i];
+        for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride)
+            y[i] = ((p0[i] + p2[i]) + p1[i]) + p3[i];
     }
 }
 
@@ -408,23 +589,84 @@ Geom make_geom(int64_t B, int64_t h, int64_t w)
     g.row_ctas = (g.row_chunks + kSeq - 1) / kSeq;
     g.max_chunks = g.row_chunks > g.w ? g.row_chunks : g.w;
     g.vec_rows = (g.L % 4 == 0) ? 1 : 0;
+    g.vec_cols = (w % 4 == 0) ? 1 : 0;
     return g;
 }
 
 struct Workspace {
-    int64_t tmp_off, aggP_off, aggH_off, total;
+    int64_t planes_off, aggP_off, aggH_off, total;
 };
 
 Workspace plan_workspace(const Geom &g)
 {
     Workspace ws;
-    const int64_t plane_bytes = align_up((int64_t)g.B * kD * g.L * 4, 256);
+    const int64_t planes_bytes = align_up((int64_t)kK * g.B * kD * g.L * 4, 256);
     const int64_t agg_bytes = align_up((int64_t)g.B * kK * g.max_chunks * kChains * 4, 256);
-    ws.tmp_off = 0;
-    ws.aggP_off = plane_bytes;
-    ws.aggH_off = plane_bytes + agg_bytes;
-    ws.total = plane_bytes + 2 * agg_bytes;
+    ws.planes_off = 0;
+    ws.aggP_off = planes_bytes;
+    ws.aggH_off = planes_bytes + agg_bytes;
+    ws.total = planes_bytes + 2 * agg_bytes;
     return ws;
+}
+
+Launch make_launch(const Geom &g, std::initializer_list<int> dirs)
+{
+    Launch ln;
+    ln.ndirs = 0;
+    int acc = 0;
+    for (int k : dirs) {
+        ln.dir[ln.ndirs] = k;
+        ln.cta_begin[ln.ndirs] = acc;
+        acc += (k & 1) ? g.col_ctas : g.row_ctas;
+        ++ln.ndirs;
+    }
+    for (int i = ln.ndirs; i < 4; ++i) { ln.dir[i] = 0; ln.cta_begin[i] = acc; }
+    ln.cta_begin[4] = acc;
+    return ln;
+}
+
+// Runs pass 1, carry, pass 2; leaves the four direction planes at workspace[0 : 4*B*64*L].
+int run_dirs(const float *x, const float *x_proj_weight, const float *dt_projs_weight,
+             const float *dt_projs_bias, const float *A_logs, const float *Ds, void *workspace,
+             size_t workspace_bytes, int64_t B, int64_t h, int64_t w, cudaStream_t s,
+             const char *who)
+{
+    WM_REQUIRE(x && x_proj_weight && dt_projs_weight && dt_projs_bias && A_logs && Ds,
+               "%s: null pointer", who);
+    WM_REQUIRE(B <= 65535, "%s: batch %lld exceeds 65535", who, (long long)B);
+    WM_REQUIRE(h * w < (int64_t)1 << 31, "%s: h*w too large", who);
+    WM_REQUIRE(aligned16(x), "%s: x must be 16-byte aligned", who);
+    const Geom g = make_geom(B, h, w);
+    const Workspace ws = plan_workspace(g);
+    WM_REQUIRE(workspace && workspace_bytes >= (size_t)ws.total,
+               "%s: workspace too small (%zu < %lld bytes)", who, workspace_bytes,
+               (long long)ws.total);
+    WM_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0,
+               "%s: workspace must be 256-byte aligned", who);
+    char *wsb = static_cast<char *>(workspace);
+
+    Params prm;
+    prm.x = x; prm.x_proj_w = x_proj_weight; prm.dt_w = dt_projs_weight; prm.dt_b = dt_projs_bias;
+    prm.A_logs = A_logs; prm.Ds = Ds;
+    prm.planes = reinterpret_cast<float *>(wsb + ws.planes_off);
+    prm.aggP = reinterpret_cast<float *>(wsb + ws.aggP_off);
+    prm.aggH = reinterpret_cast<float *>(wsb + ws.aggH_off);
+
+    WM_CUDA_OK(cudaFuncSetAttribute(ss2d_pass_kernel<false>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    WM_CUDA_OK(cudaFuncSetAttribute(ss2d_pass_kernel<true>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    // interleave row and column CTAs of the same cost so waves stay balanced
+    const Launch ln = make_launch(g, {0, 1, 2, 3});
+    dim3 grid(ln.cta_begin[4], (unsigned)B);
+    ss2d_pass_kernel<false><<<grid, kThreads, kSmemBytes, s>>>(prm, g, ln);
+    WM_LAUNCH_OK("ss2d pass 1");
+    dim3 cgrid(kChains / 256, kK, (unsigned)B);
+    ss2d_carry_kernel<<<cgrid, 256, 0, s>>>(prm.aggP, prm.aggH, g);
+    WM_LAUNCH_OK("ss2d carry");
+    ss2d_pass_kernel<true><<<grid, kThreads, kSmemBytes, s>>>(prm, g, ln);
+    WM_LAUNCH_OK("ss2d pass 2");
+    return WM_OK;
 }
 
 }  // namespace ss2d
@@ -436,6 +678,19 @@ extern "C" size_t wm_ss2d_core_workspace_bytes(int64_t B, int64_t h, int64_t w)
     return (size_t)wm::ss2d::plan_workspace(wm::ss2d::make_geom(B, h, w)).total;
 }
 
+extern "C" int wm_ss2d_dirs_fwd(const float *x, const float *x_proj_weight,
+                                const float *dt_projs_weight, const float *dt_projs_bias,
+                                const float *A_logs, const float *Ds, void *workspace,
+                                size_t workspace_bytes, int64_t B, int64_t h, int64_t w,
+                                wm_stream_t stream)
+{
+    using namespace wm;
+    WM_REQUIRE(B >= 0 && h >= 0 && w >= 0, "wm_ss2d_dirs_fwd: negative size");
+    if (B == 0 || h == 0 || w == 0) return WM_OK;
+    return ss2d::run_dirs(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, workspace,
+                          workspace_bytes, B, h, w, (cudaStream_t)stream, "wm_ss2d_dirs_fwd");
+}
+
 extern "C" int wm_ss2d_core_fwd(const float *x, const float *x_proj_weight,
                                 const float *dt_projs_weight, const float *dt_projs_bias,
                                 const float *A_logs, const float *Ds, float *y, void *workspace,
@@ -444,76 +699,18 @@ extern "C" int wm_ss2d_core_fwd(const float *x, const float *x_proj_weight,
 {
     using namespace wm;
     using namespace wm::ss2d;
-    WM_REQUIRE(x && x_proj_weight && dt_projs_weight && dt_projs_bias && A_logs && Ds && y,
-               "wm_ss2d_core_fwd: null pointer");
     WM_REQUIRE(B >= 0 && h >= 0 && w >= 0, "wm_ss2d_core_fwd: negative size");
     if (B == 0 || h == 0 || w == 0) return WM_OK;
-    WM_REQUIRE(B <= 65535, "wm_ss2d_core_fwd: batch %lld exceeds 65535", (long long)B);
-    WM_REQUIRE(h * w < (int64_t)1 << 31, "wm_ss2d_core_fwd: h*w too large");
-    WM_REQUIRE(aligned16(x) && aligned16(y) && aligned16(A_logs),
-               "wm_ss2d_core_fwd: x, y and A_logs must be 16-byte aligned");
-    const Geom g = make_geom(B, h, w);
-    const Workspace ws = plan_workspace(g);
-    WM_REQUIRE(workspace && workspace_bytes >= (size_t)ws.total,
-               "wm_ss2d_core_fwd: workspace too small (%zu < %lld bytes)", workspace_bytes,
-               (long long)ws.total);
-    WM_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0,
-               "wm_ss2d_core_fwd: workspace must be 256-byte aligned");
-    cudaStream_t s = (cudaStream_t)stream;
-    char *wsb = static_cast<char *>(workspace);
-
-    Params prm;
-    prm.x = x; prm.x_proj_w = x_proj_weight; prm.dt_w = dt_projs_weight; prm.dt_b = dt_projs_bias;
-    prm.A_logs = A_logs; prm.Ds = Ds; prm.y = y;
-    prm.tmp = reinterpret_cast<float *>(wsb + ws.tmp_off);
-    prm.aggP = reinterpret_cast<float *>(wsb + ws.aggP_off);
-    prm.aggH = reinterpret_cast<float *>(wsb + ws.aggH_off);
-
-    auto make_launch = [&](std::initializer_list<int> dirs) {
-        Launch ln;
-        ln.ndirs = 0;
-        int acc = 0;
-        for (int k : dirs) {
-            ln.dir[ln.ndirs] = k;
-            ln.cta_begin[ln.ndirs] = acc;
-            acc += (k & 1) ? g.col_ctas : g.row_ctas;
-            ++ln.ndirs;
-        }
-        for (int i = ln.ndirs; i < 4; ++i) { ln.dir[i] = 0; ln.cta_begin[i] = acc; }
-        ln.cta_begin[4] = acc;
-        return ln;
-    };
-
-    {   // pass 1: all four directions
-        const Launch ln = make_launch({0, 2, 1, 3});
-        dim3 grid(ln.cta_begin[4], (unsigned)B);
-        ss2d_pass_kernel<false, false><<<grid, kThreads, 0, s>>>(prm, g, ln);
-        WM_LAUNCH_OK("ss2d pass 1");
-    }
-    {
-        dim3 grid(kChains / 256, kK, (unsigned)B);
-        ss2d_carry_kernel<<<grid, 256, 0, s>>>(prm.aggP, prm.aggH, g);
-        WM_LAUNCH_OK("ss2d carry");
-    }
-    {   // pass 2A: dir 0 -> y, dir 1 -> tmp
-        const Launch ln = make_launch({0, 1});
-        dim3 grid(ln.cta_begin[4], (unsigned)B);
-        ss2d_pass_kernel<true, false><<<grid, kThreads, 0, s>>>(prm, g, ln);
-        WM_LAUNCH_OK("ss2d pass 2A");
-    }
-    {   // pass 2B: dir 2 += y, dir 3 += tmp
-        const Launch ln = make_launch({2, 3});
-        dim3 grid(ln.cta_begin[4], (unsigned)B);
-        ss2d_pass_kernel<true, true><<<grid, kThreads, 0, s>>>(prm, g, ln);
-        WM_LAUNCH_OK("ss2d pass 2B");
-    }
-    {
-        const int64_t n = B * kD * g.L;
-        const int vec = (n % 4 == 0) ? 1 : 0;
-        const int64_t want = ((vec ? n / 4 : n) + 255) / 256;
-        const int64_t cap = (int64_t)sm_count() * 8;
-        ss2d_combine_kernel<<<(int)(want < cap ? want : cap), 256, 0, s>>>(y, prm.tmp, n, vec);
-        WM_LAUNCH_OK("ss2d combine");
-    }
+    WM_REQUIRE(y != nullptr, "wm_ss2d_core_fwd: null pointer");
+    const int rc = run_dirs(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, workspace,
+                            workspace_bytes, B, h, w, (cudaStream_t)stream, "wm_ss2d_core_fwd");
+    if (rc != WM_OK) return rc;
+    const int64_t n = B * kD * h * w;
+    const int vec = (n % 4 == 0 && aligned16(y)) ? 1 : 0;
+    const int64_t want = ((vec ? n / 4 : n) + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    ss2d_combine_kernel<<<(int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(
+        y, static_cast<const float *>(workspace), n, vec);
+    WM_LAUNCH_OK("ss2d combine");
     return WM_OK;
 }

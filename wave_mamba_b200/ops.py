@@ -116,8 +116,32 @@ def ss2d_core(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds) -> t
                                   dt_projs_bias.data_ptr(), A_logs.data_ptr(), Ds.data_ptr(),
                                   y.data_ptr(), ws.data_ptr(), nbytes, B, h, w, _stream(x))
     _cabi.check(rc, "wm_ss2d_core_fwd")
-    _count(5)
+    _count(4)
     return y
+
+
+def ss2d_dirs(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds) -> torch.Tensor:
+    """Un-merged SS2D core: returns the four direction outputs as a (4,B,64,h,w) view of the
+    workspace (pixel order).  The reference sum y1+y2+y3+y4 is ((p[0]+p[2])+p[1])+p[3]."""
+    _chk(x, "x")
+    B, D, h, w = x.shape
+    if D != 64:
+        raise ValueError(f"ss2d_dirs supports d_inner=64 (wf=32, expand=2); got {D}")
+    _chk(x_proj_weight, "x_proj_weight", (4, 34, 64))
+    _chk(dt_projs_weight, "dt_projs_weight", (4, 64, 2))
+    _chk(dt_projs_bias, "dt_projs_bias", (4, 64))
+    _chk(A_logs, "A_logs", (256, 16))
+    _chk(Ds, "Ds", (256,))
+    lib = _cabi.load()
+    nbytes = lib.wm_ss2d_core_workspace_bytes(B, h, w)
+    ws = torch.empty(max(nbytes, 256) // 4, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        rc = lib.wm_ss2d_dirs_fwd(x.data_ptr(), x_proj_weight.data_ptr(), dt_projs_weight.data_ptr(),
+                                  dt_projs_bias.data_ptr(), A_logs.data_ptr(), Ds.data_ptr(),
+                                  ws.data_ptr(), nbytes, B, h, w, _stream(x))
+    _cabi.check(rc, "wm_ss2d_dirs_fwd")
+    _count(3)
+    return ws[:4 * B * D * h * w].view(4, B, D, h, w)
 
 
 def layernorm2d(x, weight, bias, eps: float = 1e-6) -> torch.Tensor:
@@ -249,13 +273,16 @@ def lfss_z(x, ln_w, ln_b, eps, in_proj_weight) -> torch.Tensor:
     return zs
 
 
-def lfss_out(y, zs, on_w, on_b, eps, out_proj_weight, x, skip_scale, y2=None) -> torch.Tensor:
-    """out = x*skip_scale + out_proj(out_norm(y [+ y2]) * zs)  (reference :492-494, :525)."""
+def lfss_out(y, zs, on_w, on_b, eps, out_proj_weight, x, skip_scale, extra=()) -> torch.Tensor:
+    """out = x*skip_scale + out_proj(out_norm(((y + e0) + e1) + e2) * zs)  (reference :490-494,
+    :525).  ``extra``: up to three more (B,64,h,w) addends, summed in the given order."""
     _chk(y, "y")
     B, D, h, w = y.shape
     _chk(zs, "zs", (B, D, h, w))
-    if y2 is not None:
-        _chk(y2, "y2", (B, D, h, w))
+    extra = list(extra) + [None] * (3 - len(extra))
+    for i, t in enumerate(extra):
+        if t is not None:
+            _chk(t, f"extra[{i}]", (B, D, h, w))
     C = out_proj_weight.shape[0]
     _chk(out_proj_weight, "out_proj_weight", (C, D))
     _chk(on_w, "on_w", (D,))
@@ -265,7 +292,8 @@ def lfss_out(y, zs, on_w, on_b, eps, out_proj_weight, x, skip_scale, y2=None) ->
     out = torch.empty_like(x)
     lib = _cabi.load()
     with torch.cuda.device(x.device):
-        rc = lib.wm_lfss_out_fwd(y.data_ptr(), _ptr(y2), zs.data_ptr(), on_w.data_ptr(),
+        rc = lib.wm_lfss_out_fwd(y.data_ptr(), _ptr(extra[0]), _ptr(extra[1]), _ptr(extra[2]),
+                                 zs.data_ptr(), on_w.data_ptr(),
                                  on_b.data_ptr(), eps, out_proj_weight.data_ptr(), x.data_ptr(),
                                  skip_scale.data_ptr(), out.data_ptr(), B, h, w, _stream(x))
     _cabi.check(rc, "wm_lfss_out_fwd")
