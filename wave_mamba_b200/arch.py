@@ -258,11 +258,21 @@ class CMTAttention(nn.Module):
                         self.qkv_dwconv.bias, norm.weight, norm.bias, norm.eps)
         q, k, v = qkv.chunk(3, dim=1)
         q = self.matching_transformation(q, perception)
-        q = F.normalize(q.flatten(2, 3), dim=-1)
-        k = F.normalize(k.flatten(2, 3), dim=-1)
-        attn = ((q @ k.transpose(-2, -1)) * self.temperature).softmax(dim=-1)
-        out = (attn @ v.flatten(2, 3)).view(B, C, h, w)
-        return ops.pw(out, self.project_out.weight, self.project_out.bias, residual=residual)
+        # normalize(q) @ normalize(k)^T (:787-790) == (q @ k^T) / (|q| |k|^T): one Gram matrix and
+        # two norm reductions instead of materialising the normalised copies (eps 1e-12 as F.normalize)
+        qf, kf = q.flatten(2, 3), k.flatten(2, 3)
+        gram = qf @ kf.transpose(-2, -1)
+        nq = qf.norm(dim=-1).clamp_min(1e-12)
+        nk = kf.norm(dim=-1).clamp_min(1e-12)
+        attn = (gram / (nq[:, :, None] * nk[:, None, :]) * self.temperature).softmax(dim=-1)
+        # project_out(attn @ v) == (W_po @ attn) @ v: fold the CxC attention into the 1x1 weights
+        # so `attn @ v` (:793), project_out (:797) and the residual (:849) are ONE pass over v.
+        mixed = torch.matmul(self.project_out.weight.view(C, C), attn)          # (B, C, C)
+        out = torch.empty_like(residual)
+        for b in range(B):
+            ops.pw(v[b:b + 1], mixed[b], self.project_out.bias, residual=residual[b:b + 1],
+                   out=out[b:b + 1])
+        return out
 
 
 class HFEBlock(nn.Module):

@@ -236,22 +236,54 @@ __device__ __forceinline__ void vec_chunk(const Geom &g, const TileGeom &tg, int
     }
 }
 
-__device__ __forceinline__ void load_tile(const Geom &g, const TileGeom &tg, int ti,
-                                          const float *__restrict__ xb, float *xs)
+// Per-thread addressing of the two 16-byte chunks it moves per full tile (x in, y out).
+struct ChunkMap {
+    int64_t goff;      // element offset inside a channel plane for tile 0 (channel d0)
+    int64_t gstep;     // added per tile
+    uint32_t xs_dst;   // shared address of xs[d0][p0]
+    int ys_idx;        // index of ys[d0][p0]
+    int d0;            // first channel (second chunk: d0 + 32)
+};
+
+__device__ __forceinline__ ChunkMap make_chunk_map(const Geom &g, const TileGeom &tg, float *xs)
 {
+    ChunkMap cm;
     const int tid = threadIdx.x;
+    const int cidx = tid & 15;
+    cm.d0 = tid >> 4;
+    int p0;
+    if (!tg.col) {
+        const int s = cidx >> 2, v = cidx & 3;
+        const int64_t l0 = (int64_t)(tg.chunk0 + s) * g.row_T;
+        cm.goff = tg.fwd ? l0 + 4 * v : g.L - 1 - l0 - (kTP - 1) + 4 * v;
+        cm.gstep = tg.fwd ? kTP : -kTP;
+        p0 = s * kTP + 4 * v;
+    } else {
+        const int e = cidx;
+        const int i = tg.fwd ? e : g.h - 1 - e;
+        const int jlow = tg.fwd ? tg.chunk0 : g.w - kSeq - tg.chunk0;
+        cm.goff = (int64_t)i * g.w + jlow;
+        cm.gstep = tg.fwd ? (int64_t)kTP * g.w : -(int64_t)kTP * g.w;
+        p0 = e * kSeq;
+    }
+    cm.xs_dst = (uint32_t)__cvta_generic_to_shared(xs + cm.d0 * kXS + p0);
+    cm.ys_idx = cm.d0 * kYS + p0;
+    return cm;
+}
+
+__device__ __forceinline__ void load_tile(const Geom &g, const TileGeom &tg, const ChunkMap &cm,
+                                          int ti, const float *__restrict__ xb, float *xs)
+{
     if (tile_is_vec(g, tg, ti)) {
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const int idx = tid + r * kThreads;      // 0..1023 = (d, chunk)
-            const int d = idx >> 4, cidx = idx & 15;
-            int64_t goff; int p0;
-            vec_chunk(g, tg, ti, cidx, goff, p0);
-            cp_async16(xs + d * kXS + p0, xb + (int64_t)d * g.L + goff);
-        }
+        const float *src = xb + (int64_t)cm.d0 * g.L + cm.goff + (int64_t)ti * cm.gstep;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(cm.xs_dst), "l"(src) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(cm.xs_dst + 32 * kXS * 4),
+                     "l"(src + 32 * g.L)
+                     : "memory");
     } else {
         // ragged tile: scalar loads, zero fill
-#pragma unroll
+        const int tid = threadIdx.x;
+#pragma unroll 1
         for (int r = 0; r < 8; ++r) {
             const int idx = tid + r * kThreads;      // 0..4095 = (d, s, e)
             const int d = idx >> 6, s = (idx >> 4) & 3, e = idx & 15;
@@ -264,23 +296,17 @@ __device__ __forceinline__ void load_tile(const Geom &g, const TileGeom &tg, int
     cp_async_commit();
 }
 
-__device__ __forceinline__ void store_tile(const Geom &g, const TileGeom &tg, int ti,
-                                           float *__restrict__ ob, const float *ys)
+__device__ __forceinline__ void store_tile(const Geom &g, const TileGeom &tg, const ChunkMap &cm,
+                                           int ti, float *__restrict__ ob, const float *ys)
 {
-    const int tid = threadIdx.x;
     if (tile_is_vec(g, tg, ti)) {
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const int idx = tid + r * kThreads;
-            const int d = idx >> 4, cidx = idx & 15;
-            int64_t goff; int p0;
-            vec_chunk(g, tg, ti, cidx, goff, p0);
-            const float *src = ys + d * kYS + p0;
-            const float4 v = make_float4(src[0], src[1], src[2], src[3]);
-            *reinterpret_cast<float4 *>(ob + (int64_t)d * g.L + goff) = v;
-        }
+        float *dst = ob + (int64_t)cm.d0 * g.L + cm.goff + (int64_t)ti * cm.gstep;
+        const float *a = ys + cm.ys_idx, *b = a + 32 * kYS;
+        *reinterpret_cast<float4 *>(dst) = make_float4(a[0], a[1], a[2], a[3]);
+        *reinterpret_cast<float4 *>(dst + 32 * g.L) = make_float4(b[0], b[1], b[2], b[3]);
     } else {
-#pragma unroll
+        const int tid = threadIdx.x;
+#pragma unroll 1
         for (int r = 0; r < 8; ++r) {
             const int idx = tid + r * kThreads;
             const int d = idx >> 6, s = (idx >> 4) & 3, e = idx & 15;
@@ -291,12 +317,46 @@ __device__ __forceinline__ void store_tile(const Geom &g, const TileGeom &tg, in
     }
 }
 
-// FINAL=false: pass 1 (aggregates).  FINAL=true: pass 2 (outputs).
+// One recurrence step.  DP = smem position stride per step (+1 row fwd, -1 row bwd, +4 column).
 template <bool FINAL>
-__global__ void __launch_bounds__(kThreads, 2)
-ss2d_pass_kernel(const Params prm, const Geom g, const Launch ln)
+__device__ __forceinline__ void scan_step(const float2 *ddp, const float *pjp, float *ysp,
+                                          f32x2 (&hst)[4], const f32x2 (&A2)[4], float &sdt,
+                                          bool writer)
 {
-    extern __shared__ __align__(16) float smem[];
+    const float2 dv = *ddp;                       // (dt, dt*u)
+    const float4 b0 = *reinterpret_cast<const float4 *>(pjp);
+    const float4 b1 = *reinterpret_cast<const float4 *>(pjp + 4);
+    const f32x2 dt2 = pack2(dv.x, dv.x), du2 = pack2(dv.y, dv.y);
+    const f32x2 bb[4] = {pack2(b0.x, b0.y), pack2(b0.z, b0.w), pack2(b1.x, b1.y), pack2(b1.z, b1.w)};
+    if (!FINAL) sdt += dv.x;
+    f32x2 cc[4];
+    if (FINAL) {
+        const float4 c0 = *reinterpret_cast<const float4 *>(pjp + 16);
+        const float4 c1 = *reinterpret_cast<const float4 *>(pjp + 20);
+        cc[0] = pack2(c0.x, c0.y); cc[1] = pack2(c0.z, c0.w);
+        cc[2] = pack2(c1.x, c1.y); cc[3] = pack2(c1.z, c1.w);
+    }
+    f32x2 acc = pack2(0.0f, 0.0f);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const f32x2 a = ex2_2(fmul2(dt2, A2[j]));
+        hst[j] = ffma2(a, hst[j], fmul2(du2, bb[j]));
+        if (FINAL) acc = ffma2(hst[j], cc[j], acc);
+    }
+    if (FINAL) {
+        float lo, hi;
+        unpack2(acc, lo, hi);
+        float y = lo + hi;
+        y += __shfl_xor_sync(0xffffffffu, y, 1);
+        if (writer) *ysp += y;                    // ys held D*u
+    }
+}
+
+// The whole tile loop of one CTA, specialised on the pass and on the scan's smem stride.
+template <bool FINAL, int DP>
+__device__ __forceinline__ void run_cta(const Params &prm, const Geom &g, const TileGeom &tg,
+                                        float *smem, int b)
+{
     float *xs = smem + kOffXs;
     float *pj = smem + kOffPj;
     float2 *dd = reinterpret_cast<float2 *>(smem + kOffDd);
@@ -306,23 +366,12 @@ ss2d_pass_kernel(const Params prm, const Geom g, const Launch ln)
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const int b = blockIdx.y;
-
-    int slot = 0;
-#pragma unroll
-    for (int i = 1; i < 4; ++i)
-        if (i < ln.ndirs && (int)blockIdx.x >= ln.cta_begin[i]) slot = i;
-    TileGeom tg;
-    tg.k = ln.dir[slot];
-    tg.col = (tg.k & 1) != 0;
-    tg.fwd = tg.k < 2;
-    tg.chunk0 = (blockIdx.x - ln.cta_begin[slot]) * kSeq;
-    tg.maxlen = tg.col ? g.h : g.row_T;
     const int k = tg.k;
     const int ntiles = (tg.maxlen + kTP - 1) / kTP;
 
     const float *xb = prm.x + (int64_t)b * kD * g.L;
-    load_tile(g, tg, 0, xb, xs);   // in flight while the weights are prepared
+    const ChunkMap cm = make_chunk_map(g, tg, xs);
+    load_tile(g, tg, cm, 0, xb, xs);   // in flight while the weights are prepared
 
     // ---- mma B fragments of W_k, pre-split into tf32 hi/lo -----------------------------------
     // n-tile nt, column n (0..7) -> row of x_proj_weight[k] (34,64) = [dt(2) | B(16) | C(16)]
@@ -344,20 +393,19 @@ ss2d_pass_kernel(const Params prm, const Geom g, const Launch ln)
                             __uint_as_float(l1));
     }
     if (tid < kD) {
-        const int ch = k * kD + tid;
-        cst[tid] = __ldg(prm.dt_w + ch * 2 + 0);
-        cst[kD + tid] = __ldg(prm.dt_w + ch * 2 + 1);
-        cst[2 * kD + tid] = __ldg(prm.dt_b + ch);
-        cst[3 * kD + tid] = __ldg(prm.Ds + ch);
+        const int chn = k * kD + tid;
+        cst[tid] = __ldg(prm.dt_w + chn * 2 + 0);
+        cst[kD + tid] = __ldg(prm.dt_w + chn * 2 + 1);
+        cst[2 * kD + tid] = __ldg(prm.dt_b + chn);
+        cst[3 * kD + tid] = __ldg(prm.Ds + chn);
     }
 
     // ---- scan-thread identity: (strand, channel, state half) -------------------------------
     const int s = tid >> 7, d = (tid & 127) >> 1, half = tid & 1;
-    const int ch = k * kD + d;
     f32x2 A2[4];  // A * log2(e), A = -exp(A_log)   (reference :462)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const float *ap = prm.A_logs + (int64_t)ch * kN + half * 8 + 2 * j;
+        const float *ap = prm.A_logs + (int64_t)(k * kD + d) * kN + half * 8 + 2 * j;
         A2[j] = pack2(-expf(__ldg(ap)) * 1.4426950408889634f,
                       -expf(__ldg(ap + 1)) * 1.4426950408889634f);
     }
@@ -377,6 +425,13 @@ ss2d_pass_kernel(const Params prm, const Geom g, const Launch ln)
     }
     double sum_dt = 0.0;
 
+    // smem position of step 0 of my strand; step e sits at p0 + e*DP
+    const int p0 = tile_pos(tg, s, 0);
+    const float2 *dd0 = dd + d * kDS + p0;
+    const float *pj0 = pj + p0 * kPJ + half * 8;
+    float *ys0 = ys + d * kYS + p0;
+    const bool writer = half == 0;
+
     float *oplane = FINAL ? prm.planes + (((int64_t)k * g.B + b) * kD) * g.L : nullptr;
 
     // projection role of this warp: m-tile (16 positions) and a set of n-tiles
@@ -386,6 +441,7 @@ ss2d_pass_kernel(const Params prm, const Geom g, const Launch ln)
     else { nt_first = nq < 2 ? nq : 4; nt_count = nq < 3 ? 1 : 0; }  // B0-7 | B8-15 | dt | idle
     const bool also_dt = FINAL && nq == 0;                      // pass 2: warps 0-3 add the dt tile
 
+#pragma unroll 1
     for (int ti = 0; ti < ntiles; ++ti) {
         cp_async_wait_all();
         __syncthreads();                       // xs(ti) landed; previous tile fully consumed
@@ -395,6 +451,7 @@ ss2d_pass_kernel(const Params prm, const Geom g, const Launch ln)
             float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
             const int gq = lane >> 2, t4 = lane & 3;
             const float *abase = xs + t4 * kXS + mt * 16 + gq;
+            const float4 *wfp = wf + nt_first * 32 + lane;
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
                 const float *ap = abase + ks * 8 * kXS;
@@ -405,7 +462,7 @@ ss2d_pass_kernel(const Params prm, const Geom g, const Launch ln)
                     ahi[i] = to_tf32(av[i]);
                     alo[i] = to_tf32(av[i] - __uint_as_float(ahi[i]));
                 }
-                const float4 bw = wf[(ks * kNTiles + nt_first) * 32 + lane];
+                const float4 bw = wfp[ks * kNTiles * 32];
                 mma_tf32(c0, alo, __float_as_uint(bw.x), __float_as_uint(bw.y));
                 mma_tf32(c0, ahi, __float_as_uint(bw.z), __float_as_uint(bw.w));
                 mma_tf32(c0, ahi, __float_as_uint(bw.x), __float_as_uint(bw.y));
@@ -433,68 +490,46 @@ ss2d_pass_kernel(const Params prm, const Geom g, const Launch ln)
 
         // ---- delta phase: dt = softplus(dt_proj . dt_low + bias)  (reference :455, scan_fn) --
         // warp w owns channels 4w..4w+3; lane = position within a 32-position round
+        {
+            const float *xw = xs + warp * 4 * kXS + lane;
+            float2 *dw = dd + warp * 4 * kDS + lane;
+            float *yw = ys + warp * 4 * kYS + lane;
+            const float *cw = cst + warp * 4;
 #pragma unroll
-        for (int rnd = 0; rnd < 2; ++rnd) {
-            const int p = rnd * 32 + lane;
-            const float2 dlow = *reinterpret_cast<const float2 *>(pj + p * kPJ + 32);
+            for (int rnd = 0; rnd < 2; ++rnd) {
+                const float2 dlow = *reinterpret_cast<const float2 *>(pj + (rnd * 32 + lane) * kPJ + 32);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int dc = warp * 4 + i;
-                const float u = xs[dc * kXS + p];
-                const float raw = fmaf(cst[kD + dc], dlow.y, cst[dc] * dlow.x) + cst[2 * kD + dc];
-                const float dt = softplus_fast(raw);
-                dd[dc * kDS + p] = make_float2(dt, dt * u);
-                if (FINAL) ys[dc * kYS + p] = cst[3 * kD + dc] * u;
+                for (int i = 0; i < 4; ++i) {
+                    const float u = xw[i * kXS + rnd * 32];
+                    const float raw = fmaf(cw[kD + i], dlow.y, cw[i] * dlow.x) + cw[2 * kD + i];
+                    const float dt = softplus_fast(raw);
+                    dw[i * kDS + rnd * 32] = make_float2(dt, dt * u);
+                    if (FINAL) yw[i * kYS + rnd * 32] = cw[3 * kD + i] * u;
+                }
             }
         }
         __syncthreads();                       // xs is dead from here on
 
-        if (ti + 1 < ntiles) load_tile(g, tg, ti + 1, xb, xs);
+        if (ti + 1 < ntiles) load_tile(g, tg, cm, ti + 1, xb, xs);
 
         // ---- recurrence over the 16 steps of this tile        (reference :465-471) --------
         {
             const int nvalid = my_len - ti * kTP;          // warp-uniform
-            const float2 *ddrow = dd + d * kDS;
-            float *ysrow = ys + d * kYS;
-#pragma unroll 4
-            for (int e = 0; e < kTP; ++e) {
-                if (e < nvalid) {
-                    const int p = tile_pos(tg, s, e);
-                    const float2 dv = ddrow[p];
-                    const float *pr = pj + p * kPJ + half * 8;
-                    const float4 b0 = *reinterpret_cast<const float4 *>(pr);
-                    const float4 b1 = *reinterpret_cast<const float4 *>(pr + 4);
-                    const f32x2 dt2 = pack2(dv.x, dv.x), du2 = pack2(dv.y, dv.y);
-                    const f32x2 bb[4] = {pack2(b0.x, b0.y), pack2(b0.z, b0.w), pack2(b1.x, b1.y),
-                                         pack2(b1.z, b1.w)};
-                    if (!FINAL) sum_dt += (double)dv.x;
-                    f32x2 acc = pack2(0.0f, 0.0f);
-                    f32x2 cc[4];
-                    if (FINAL) {
-                        const float4 c0 = *reinterpret_cast<const float4 *>(pr + 16);
-                        const float4 c1 = *reinterpret_cast<const float4 *>(pr + 20);
-                        cc[0] = pack2(c0.x, c0.y); cc[1] = pack2(c0.z, c0.w);
-                        cc[2] = pack2(c1.x, c1.y); cc[3] = pack2(c1.z, c1.w);
-                    }
+            float sdt = 0.0f;
+            if (nvalid >= kTP) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const f32x2 a = ex2_2(fmul2(dt2, A2[j]));
-                        hst[j] = ffma2(a, hst[j], fmul2(du2, bb[j]));
-                        if (FINAL) acc = ffma2(hst[j], cc[j], acc);
-                    }
-                    if (FINAL) {
-                        float lo, hi;
-                        unpack2(acc, lo, hi);
-                        float y = lo + hi;
-                        y += __shfl_xor_sync(0xffffffffu, y, 1);
-                        if (half == 0) ysrow[p] += y;     // ys held D*u
-                    }
-                }
+                for (int e = 0; e < kTP; ++e)
+                    scan_step<FINAL>(dd0 + e * DP, pj0 + e * DP * kPJ, ys0 + e * DP, hst, A2, sdt, writer);
+            } else {
+#pragma unroll 1
+                for (int e = 0; e < nvalid; ++e)
+                    scan_step<FINAL>(dd0 + e * DP, pj0 + e * DP * kPJ, ys0 + e * DP, hst, A2, sdt, writer);
             }
+            if (!FINAL) sum_dt += (double)sdt;
         }
         if (FINAL) {
             __syncthreads();
-            store_tile(g, tg, ti, oplane, ys);
+            store_tile(g, tg, cm, ti, oplane, ys);
         }
     }
 
@@ -515,6 +550,28 @@ ss2d_pass_kernel(const Params prm, const Geom g, const Launch ln)
         hp4[0] = make_float4(hv[0], hv[1], hv[2], hv[3]);
         hp4[1] = make_float4(hv[4], hv[5], hv[6], hv[7]);
     }
+}
+
+// FINAL=false: pass 1 (aggregates).  FINAL=true: pass 2 (outputs).
+template <bool FINAL>
+__global__ void __launch_bounds__(kThreads, 2)
+ss2d_pass_kernel(const Params prm, const Geom g, const Launch ln)
+{
+    extern __shared__ __align__(16) float smem[];
+    int k = ln.dir[0], begin = 0;
+    if (ln.ndirs > 1 && (int)blockIdx.x >= ln.cta_begin[1]) { k = ln.dir[1]; begin = ln.cta_begin[1]; }
+    if (ln.ndirs > 2 && (int)blockIdx.x >= ln.cta_begin[2]) { k = ln.dir[2]; begin = ln.cta_begin[2]; }
+    if (ln.ndirs > 3 && (int)blockIdx.x >= ln.cta_begin[3]) { k = ln.dir[3]; begin = ln.cta_begin[3]; }
+    TileGeom tg;
+    tg.k = k;
+    tg.col = (k & 1) != 0;
+    tg.fwd = k < 2;
+    tg.chunk0 = (blockIdx.x - begin) * kSeq;
+    tg.maxlen = tg.col ? g.h : g.row_T;
+    const int b = blockIdx.y;
+    if (tg.col) run_cta<FINAL, kSeq>(prm, g, tg, smem, b);
+    else if (tg.fwd) run_cta<FINAL, 1>(prm, g, tg, smem, b);
+    else run_cta<FINAL, -1>(prm, g, tg, smem, b);
 }
 
 // h_in[c] = P[c-1]*h_in[c-1] + H[c-1], h_in[0] = 0; written over aggH in place.

@@ -211,7 +211,7 @@ def dw_act_pw(x, dw_w, dw_b, pw_w, pw_b, act: str = "gelu", residual=None) -> to
     return y
 
 
-def pw(x, pw_w, pw_b=None, gate: bool = False, residual=None, res_scale=None) -> torch.Tensor:
+def pw(x, pw_w, pw_b=None, gate: bool = False, residual=None, res_scale=None, out=None) -> torch.Tensor:
     """y = residual?*res_scale? + pw1x1(x) (+bias).  gate=True: x is (B,2*Cin,h,w) and the conv
     sees gelu(x[:, :Cin]) * x[:, Cin:]  (reference ffn :227-228)."""
     _chk(x, "x")
@@ -219,14 +219,17 @@ def pw(x, pw_w, pw_b=None, gate: bool = False, residual=None, res_scale=None) ->
     Cout, Cin = pw_w.shape[0], pw_w.shape[1]
     if Cx != (2 * Cin if gate else Cin):
         raise ValueError(f"x has {Cx} channels, weight expects {2 * Cin if gate else Cin}")
-    _chk(pw_w, "pw_w", (Cout, Cin, 1, 1))
+    _chk(pw_w, "pw_w", (Cout, Cin) if pw_w.dim() == 2 else (Cout, Cin, 1, 1))
     if pw_b is not None:
         _chk(pw_b, "pw_b", (Cout,))
     if residual is not None:
         _chk(residual, "residual", (B, Cout, h, w))
     if res_scale is not None:
         _chk(res_scale, "res_scale", (Cout,))
-    y = torch.empty(B, Cout, h, w, device=x.device, dtype=x.dtype)
+    if out is None:
+        y = torch.empty(B, Cout, h, w, device=x.device, dtype=x.dtype)
+    else:
+        y = _chk(out, "out", (B, Cout, h, w))
     lib = _cabi.load()
     with torch.cuda.device(x.device):
         rc = lib.wm_pw_fwd(x.data_ptr(), pw_w.data_ptr(), _ptr(pw_b), 1 if gate else 0,
