@@ -49,10 +49,16 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--height", type=int, default=H4K)
     ap.add_argument("--width", type=int, default=W4K)
-    ap.add_argument("--tf32", type=int, default=0,
-                    help="1: let cuDNN use TF32 for the dense 3x3 convs (the reference's default)")
+    ap.add_argument("--tf32", type=int, default=1,
+                    help="1 (default, = the reference's own default torch.backends.cudnn.allow_tf32): "
+                         "cuDNN may use TF32 tensor cores for the dense 3x3 convs that are still "
+                         "library calls; 0: strict fp32 everywhere.  Hand-written kernels are fp32 "
+                         "either way (PSNR parity under TF32 is tested in tests/test_model_gpu.py)")
     ap.add_argument("--ckpt", default="UHDLL")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profiler-window", action="store_true",
+                    help="bracket the timed region with cudaProfilerStart/Stop "
+                         "(for `ncu --profile-from-start off`)")
     ap.add_argument("--no-clocks", action="store_true", help="do not spawn the nvidia-smi sampler "
                     "(use under ncu, which waits for child processes)")
     return ap.parse_args()
@@ -232,6 +238,7 @@ class OpTimer:
                                                                   a[6] if len(a) > 6 else None))
         wrap("pw", lambda a, k, o: nb(a[0]) + nb(o) + nb(k.get("residual")))
         wrap("paconv_gate", lambda a, k, o: nb(a[0]) + 2 * nb(o))
+        wrap("gram32", lambda a, k, o: 2 * 32 * a[0].shape[0] * a[0].shape[2] * a[0].shape[3] * 4)
         wrap("lfss_z", lambda a, k, o: nb(a[0]) + nb(o))
         wrap("lfss_out", lambda a, k, o: nb(a[0], a[1], a[6]) + nb(o) + nb(*k.get("extra", ())))
         wrap("ss2d_dirs", lambda a, k, o: 2 * nb(a[0]))           # 512*B*L
@@ -322,11 +329,15 @@ def main():
         launches0 = ops.launch_count
         timer.enabled = True
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if args.profiler_window:
+            torch.cuda.profiler.start()
         s.record()
         for _ in range(args.steps):
             y = fwd(x_dev)
         e.record()
         barrier()
+        if args.profiler_window:
+            torch.cuda.profiler.stop()
         timer.enabled = False
         launches = ops.launch_count - launches0
         ms_dev = max_over_ranks(s.elapsed_time(e))

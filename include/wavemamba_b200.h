@@ -31,7 +31,7 @@ extern "C" {
 #define WM_ECUDA (-2)     /* a CUDA runtime call or kernel launch failed               */
 #define WM_ENODEVICE (-3) /* no sm_100-class CUDA device is current                     */
 
-#define WM_ABI_VERSION 3
+#define WM_ABI_VERSION 4
 
 typedef void *wm_stream_t;
 
@@ -128,6 +128,18 @@ int wm_lfss_out_fwd(const float *y, const float *ya, const float *yb, const floa
                     const float *zs, const float *on_w, const float *on_b, float eps,
                     const float *w_out, const float *x, const float *skip_scale, float *out,
                     int64_t B, int64_t h, int64_t w, wm_stream_t stream);
+
+/* ---- 32x32 Gram matrix + squared norms of two 32-channel stacks, one pass -----------------
+ * out[b] = [ G (32x32, row-major, G[i][j] = sum_p X[b][i][p]*Y[b][j][p]) | |X_i|^2 (32) | |Y_j|^2 (32) ]
+ * (1088 floats per batch item).  X, Y: 32 channel planes of hw contiguous floats each, batch
+ * strides x_bstride / y_bstride in floats (so a 32-channel slice of a wider NCHW tensor works).
+ * Replaces torch.cdist in Matching (:664; dist^2 = |x|^2 + |p|^2 - 2G, argmin :624) and
+ * normalize(q) @ normalize(k)^T in CMTAttention (:787-790).  Accumulates 128-pixel tiles in fp32
+ * and tile sums in fp64; deterministic.  workspace >= wm_gram32_workspace_bytes(B, hw), 8-aligned. */
+size_t wm_gram32_workspace_bytes(int64_t B, int64_t hw);
+int wm_gram32_fwd(const float *x, int64_t x_bstride, const float *y, int64_t y_bstride, float *out,
+                  void *workspace, size_t workspace_bytes, int64_t B, int64_t hw,
+                  wm_stream_t stream);
 
 /* PAConv gate: y = k3out * sigmoid( pw1x1(x) + b ), x and k3out and y all (B,64,h,w)
  * (PAConv.k2 + sigmoid + mul, :694-697).  In-place on k3out allowed (y == k3out). */

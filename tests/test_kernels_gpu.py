@@ -315,3 +315,37 @@ def test_lfss_block_fused_path_vs_golden_and_oracle(dev, params_cache):
     with torch.no_grad():
         got = blk(g["x"].to(dev), [h, w]).cpu()
     torch.testing.assert_close(got, g["y"], rtol=3e-5, atol=3e-5)
+
+
+# ------------------------------------------------------------------------------- Gram / norms
+@pytest.mark.parametrize("shape", [(1, 32, 8, 12), (2, 32, 33, 37), (1, 32, 135, 240), (2, 32, 64, 130)])
+def test_gram32_vs_float64(ops, dev, shape):
+    g = torch.Generator().manual_seed(21)
+    B, C, h, w = shape
+    wide = _rand(B, 96, h, w, g=g)                  # x is a channel slice (batch stride 96*h*w)
+    y = _rand(B, 32, h, w, g=g)
+    xd = wide.to(dev)[:, 32:64]
+    G, nx, ny = ops.gram32(xd, y.to(dev))
+    x64 = wide[:, 32:64].double().flatten(2, 3)
+    y64 = y.double().flatten(2, 3)
+    want = x64 @ y64.transpose(1, 2)
+    scale = want.abs().max().item()
+    # tolerance: fp32 products, 128-term fp32 tile sums, fp64 across tiles -> ~1e-6 relative
+    assert (G.cpu().double() - want).abs().max().item() <= 2e-6 * scale + 1e-6
+    torch.testing.assert_close(nx.cpu().double(), x64.pow(2).sum(-1), rtol=2e-6, atol=1e-6)
+    torch.testing.assert_close(ny.cpu().double(), y64.pow(2).sum(-1), rtol=2e-6, atol=1e-6)
+    G2, _, _ = ops.gram32(xd, y.to(dev))
+    assert torch.equal(G, G2)                       # deterministic
+
+
+def test_gram32_argmin_matches_cdist_oracle(ops, dev):
+    """The Matching decision (argmin over candidate channels) from the Gram pass equals the
+    oracle's torch.cdist + topk on the same maps."""
+    g = torch.Generator().manual_seed(22)
+    x, p = _rand(2, 32, 40, 56, g=g), _rand(2, 32, 40, 56, g=g)
+    p[:, 5] = x[:, 9] + 1e-3 * _rand(2, 40, 56, g=g)        # a near-duplicate pair
+    G, nx, ny = ops.gram32(x.to(dev), p.to(dev))
+    d2 = (nx[:, :, None] + ny[:, None, :] - 2 * G).cpu()
+    want = torch.cdist(x.flatten(2, 3), p.flatten(2, 3)).topk(k=1, largest=False).indices.squeeze(-1)
+    assert torch.equal(d2.argmin(-1), want)
+    assert int(want[0, 9]) == 5

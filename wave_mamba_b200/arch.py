@@ -203,9 +203,11 @@ class PAConv(nn.Module):
 
 def nearest_channel_index(x: torch.Tensor, perception: torch.Tensor) -> torch.Tensor:
     """reference Matching (:618-680) with match_factor=1: argmin over candidate channel maps of
-    the L2 distance between whole maps.  Same ``torch.cdist`` call as the reference."""
-    dist = torch.cdist(x.flatten(2, 3), perception.flatten(2, 3))
-    return dist.topk(k=1, largest=False).indices.squeeze(-1)
+    the L2 distance between whole maps, from one Gram pass (fp64 tile accumulation)."""
+    gram, nx, ny = ops.gram32(x, perception)
+    # torch.cdist's mm mode: dist^2 = |x_i|^2 + |p_j|^2 - 2 x_i.p_j (sqrt/clamp are monotone)
+    dist2 = nx[:, :, None] + ny[:, None, :] - 2.0 * gram
+    return dist2.topk(k=1, largest=False).indices.squeeze(-1)
 
 
 class Matching_transformation(nn.Module):
@@ -260,10 +262,9 @@ class CMTAttention(nn.Module):
         q = self.matching_transformation(q, perception)
         # normalize(q) @ normalize(k)^T (:787-790) == (q @ k^T) / (|q| |k|^T): one Gram matrix and
         # two norm reductions instead of materialising the normalised copies (eps 1e-12 as F.normalize)
-        qf, kf = q.flatten(2, 3), k.flatten(2, 3)
-        gram = qf @ kf.transpose(-2, -1)
-        nq = qf.norm(dim=-1).clamp_min(1e-12)
-        nk = kf.norm(dim=-1).clamp_min(1e-12)
+        gram, nq2, nk2 = ops.gram32(q, k)
+        nq = nq2.sqrt().clamp_min(1e-12)
+        nk = nk2.sqrt().clamp_min(1e-12)
         attn = (gram / (nq[:, :, None] * nk[:, None, :]) * self.temperature).softmax(dim=-1)
         # project_out(attn @ v) == (W_po @ attn) @ v: fold the CxC attention into the 1x1 weights
         # so `attn @ v` (:793), project_out (:797) and the residual (:849) are ONE pass over v.

@@ -302,3 +302,40 @@ def lfss_out(y, zs, on_w, on_b, eps, out_proj_weight, x, skip_scale, extra=()) -
     _cabi.check(rc, "wm_lfss_out_fwd")
     _count(1)
     return out
+
+
+def _chk_planes32(t: torch.Tensor, name: str):
+    """(B,32,h,w) float32 CUDA tensor whose 32 planes are contiguous (batch stride free)."""
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _cabi.WaveMambaNativeError(f"{name}: expected a CUDA tensor (no CPU fallback)")
+    if t.dtype != torch.float32 or t.dim() != 4 or t.shape[1] != 32:
+        raise TypeError(f"{name}: expected float32 (B,32,h,w), got {t.dtype} {tuple(t.shape)}")
+    B, C, h, w = t.shape
+    if t.numel() and (t.stride(3) != 1 or t.stride(2) != w or t.stride(1) != h * w):
+        raise ValueError(f"{name}: channel planes must be contiguous, got strides {t.stride()}")
+    return t
+
+
+def gram32(x: torch.Tensor, y: torch.Tensor):
+    """G = X Y^T over all pixels plus squared row norms.  x, y: (B,32,h,w) (channel slices of a
+    wider tensor are fine).  Returns G (B,32,32), |x_i|^2 (B,32), |y_j|^2 (B,32).
+    Reference: the mm-mode torch.cdist of Matching (:664) and the q.k^T / F.normalize of
+    CMTAttention (:787-790)."""
+    _chk_planes32(x, "x")
+    _chk_planes32(y, "y")
+    if x.shape != y.shape:
+        raise ValueError(f"x {tuple(x.shape)} and y {tuple(y.shape)} must match")
+    B, C, h, w = x.shape
+    hw = h * w
+    lib = _cabi.load()
+    out = torch.empty(B, 32 * 32 + 64, device=x.device, dtype=torch.float32)
+    nbytes = lib.wm_gram32_workspace_bytes(B, hw)
+    ws = torch.empty(max(nbytes, 8) // 8, device=x.device, dtype=torch.float64)
+    xb = x.stride(0) if B > 1 else 32 * hw
+    yb = y.stride(0) if B > 1 else 32 * hw
+    with torch.cuda.device(x.device):
+        rc = lib.wm_gram32_fwd(x.data_ptr(), xb, y.data_ptr(), yb, out.data_ptr(), ws.data_ptr(),
+                               nbytes, B, hw, _stream(x))
+    _cabi.check(rc, "wm_gram32_fwd")
+    _count(2)
+    return out[:, :1024].view(B, 32, 32), out[:, 1024:1056], out[:, 1056:1088]
