@@ -49,11 +49,11 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--height", type=int, default=H4K)
     ap.add_argument("--width", type=int, default=W4K)
-    ap.add_argument("--tf32", type=int, default=1,
-                    help="1 (default, = the reference's own default torch.backends.cudnn.allow_tf32): "
-                         "cuDNN may use TF32 tensor cores for the dense 3x3 convs that are still "
-                         "library calls; 0: strict fp32 everywhere.  Hand-written kernels are fp32 "
-                         "either way (PSNR parity under TF32 is tested in tests/test_model_gpu.py)")
+    ap.add_argument("--tf32", type=int, default=0,
+                    help="0 (default): strict fp32 everywhere -- required for the 1e-3 dB PSNR budget "
+                         "(tests/test_model_gpu.py measured 2.8e-3 dB with TF32).  1: let cuDNN use "
+                         "TF32 for the dense 3x3 convs that are still library calls (the reference's "
+                         "own GPU default); reported for information only")
     ap.add_argument("--ckpt", default="UHDLL")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profiler-window", action="store_true",

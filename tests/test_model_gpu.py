@@ -107,33 +107,26 @@ def test_full_4k_forward_is_finite_and_deterministic(dev, params_cache):
     assert torch.equal(a, b)
 
 
-def test_cudnn_tf32_for_library_convs_keeps_psnr_parity(dev, params_cache):
-    """bench.py's default lets cuDNN use TF32 for the dense 3x3 convs that are still library calls
-    (the reference's own default).  The BASELINE criterion must hold in that mode too:
-    |PSNR - PSNR_reference| <= 1e-3 dB against the fp32 reference goldens / oracle."""
-    torch.backends.cudnn.allow_tf32 = True
-    try:
-        g = load_golden("e2e_synth48x80_UHDLL")
-        net = _net(params_cache(g["ckpt"]), dev)
-        with torch.no_grad():
-            y = net.restoration_network(g["x"].to(dev)).cpu()
-        print(f"tf32 convs: max abs err vs fp32 reference {(y - g['y']).abs().max().item():.3e}")
-        for i in range(y.shape[0]):
-            gt = om.to_uint8_bgr(g["gt"][i])
-            d = abs(om.psnr_y(om.to_uint8_bgr(y[i]), gt) - om.psnr_y(om.to_uint8_bgr(g["y"][i]), gt))
-            assert d <= 1e-3, d
-        # a larger image with more texture
-        params = params_cache("UHDLL")
-        x, gt = om.synth_lowlight(1, 256, 384, seed=7)
-        want = om.unet_forward(params, x)
-        net = _net(params, dev)
-        with torch.no_grad():
-            y = net.restoration_network(x.to(dev)).cpu()
-        g8 = om.to_uint8_bgr(gt[0])
-        d = abs(om.psnr_y(om.to_uint8_bgr(y[0]), g8) - om.psnr_y(om.to_uint8_bgr(want[0]), g8))
-        diff_px = int((om.to_uint8_bgr(y[0]) != om.to_uint8_bgr(want[0])).sum())
-        print(f"256x384 tf32: |dPSNR| {d:.2e} dB, differing uint8 values {diff_px}, "
-              f"max abs {(y - want).abs().max().item():.3e}")
-        assert d <= 1e-3, d
-    finally:
-        torch.backends.cudnn.allow_tf32 = False
+def test_cudnn_tf32_for_library_convs_is_measured_not_assumed(dev, params_cache):
+    """The dense 3x3 convs are still library calls.  cuDNN's TF32 mode (the reference's own default
+    on GPU) was measured to move the PSNR by 2.8e-3 dB on this input -- outside the 1e-3 dB budget
+    -- so bench.py defaults to strict fp32 (--tf32 0).  This test pins both facts: fp32 mode meets
+    the budget; TF32 mode stays a small, bounded deviation (and is reported, not hidden)."""
+    params = params_cache("UHDLL")
+    x, gt = om.synth_lowlight(1, 256, 384, seed=7)
+    want = om.unet_forward(params, x)
+    g8 = om.to_uint8_bgr(gt[0])
+    deltas = {}
+    for tf32 in (False, True):
+        torch.backends.cudnn.allow_tf32 = tf32
+        try:
+            net = _net(params, dev)
+            with torch.no_grad():
+                y = net.restoration_network(x.to(dev)).cpu()
+        finally:
+            torch.backends.cudnn.allow_tf32 = False
+        deltas[tf32] = abs(om.psnr_y(om.to_uint8_bgr(y[0]), g8) - om.psnr_y(om.to_uint8_bgr(want[0]), g8))
+        print(f"cudnn tf32={tf32}: |dPSNR| {deltas[tf32]:.2e} dB, max abs {(y - want).abs().max().item():.3e}, "
+              f"differing uint8 values {int((om.to_uint8_bgr(y[0]) != om.to_uint8_bgr(want[0])).sum())}")
+    assert deltas[False] <= 1e-3, deltas
+    assert deltas[True] <= 5e-2, deltas
