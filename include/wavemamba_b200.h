@@ -31,7 +31,7 @@ extern "C" {
 #define WM_ECUDA (-2)     /* a CUDA runtime call or kernel launch failed               */
 #define WM_ENODEVICE (-3) /* no sm_100-class CUDA device is current                     */
 
-#define WM_ABI_VERSION 4
+#define WM_ABI_VERSION 5
 
 typedef void *wm_stream_t;
 
@@ -140,6 +140,26 @@ size_t wm_gram32_workspace_bytes(int64_t B, int64_t hw);
 int wm_gram32_fwd(const float *x, int64_t x_bstride, const float *y, int64_t y_bstride, float *out,
                   void *workspace, size_t workspace_bytes, int64_t B, int64_t hw,
                   wm_stream_t stream);
+
+/* ---- dense 3x3 convolution (stride 1, zero pad 1), implicit GEMM on tensor cores, 3xTF32 ----
+ * PAConv.k3/k4 (:689-698), DownFRG.l_conv (:966,975), upFRG.h_out_conv (:993,1005).
+ * Weights are pre-packed once per layer (mma fragment order, tf32 hi/lo split):
+ *   wm_conv3x3_prepack(w3x3 (Cout,Cin,3,3), w1x1 (Cout,Cin) or NULL, packed, Cin, Cout)
+ *   with `packed` >= wm_conv3x3_packed_bytes(Cin, Cout, w1x1 != NULL) bytes, 16-byte aligned.
+ * Forward: the Cin input channels are the first Ca channels of in_a followed by Cin-Ca channels of
+ * in_b selected per batch item through chan_map (B, Cin-Ca) int32 (NULL = identity) -- the
+ * torch.cat([x, matched]) of :716 / cat([LL, x_d]) of :975 is never materialised.
+ *   gate_bias == NULL: out = conv3x3(in) + bias?            (Cin,Cout) in {(64,32),(64,64),(32,96),(32,32)}
+ *   gate_bias != NULL: out = conv3x3(in) * sigmoid(conv1x1(in) + gate_bias)   PAConv :694-697, 64->64,
+ *                      `packed` must have been built with the 1x1 weights.
+ * fp32 accuracy (a_lo*b_hi + a_hi*b_lo + a_hi*b_hi, fp32 accumulate). */
+size_t wm_conv3x3_packed_bytes(int64_t Cin, int64_t Cout, int with_gate);
+int wm_conv3x3_prepack(const float *w3x3, const float *w1x1, void *packed, int64_t Cin, int64_t Cout,
+                       wm_stream_t stream);
+int wm_conv3x3_fwd(const float *in_a, int64_t a_bstride, int64_t Ca, const float *in_b,
+                   int64_t b_bstride, const int *chan_map, const void *packed, const float *bias,
+                   const float *gate_bias, float *out, int64_t B, int64_t Cin, int64_t Cout,
+                   int64_t h, int64_t w, wm_stream_t stream);
 
 /* PAConv gate: y = k3out * sigmoid( pw1x1(x) + b ), x and k3out and y all (B,64,h,w)
  * (PAConv.k2 + sigmoid + mul, :694-697).  In-place on k3out allowed (y == k3out). */

@@ -349,3 +349,51 @@ def test_gram32_argmin_matches_cdist_oracle(ops, dev):
     want = torch.cdist(x.flatten(2, 3), p.flatten(2, 3)).topk(k=1, largest=False).indices.squeeze(-1)
     assert torch.equal(d2.argmin(-1), want)
     assert int(want[0, 9]) == 5
+
+
+# ------------------------------------------------------------------------------- dense 3x3 conv
+@pytest.mark.parametrize("cin,cout", [(64, 32), (64, 64), (32, 96), (32, 32)])
+@pytest.mark.parametrize("hw", [(13, 37), (8, 32), (40, 70)])
+def test_conv3x3_plain(ops, dev, cin, cout, hw):
+    """3xTF32 tensor-core conv vs float64 F.conv2d: fp32-level accuracy (not TF32-level)."""
+    g = torch.Generator().manual_seed(31)
+    h, w = hw
+    x = _rand(2, cin, h, w, g=g)
+    wt = _rand(cout, cin, 3, 3, g=g, s=0.1)
+    bias = _rand(cout, g=g, s=0.1)
+    want = F.conv2d(x.double(), wt.double(), bias.double(), padding=1)
+    got = ops.conv3x3(x.to(dev), wt.to(dev), bias.to(dev)).cpu().double()
+    err = (got - want).abs().max().item()
+    tf32_like = (F.conv2d(x.bfloat16().float(), wt, bias, padding=1).double() - want).abs().max().item()
+    print(f"{cin}->{cout} {hw}: max err {err:.2e} (scale {want.abs().max().item():.2f}; bf16-input err {tf32_like:.2e})")
+    assert err <= 2e-5 * max(1.0, want.abs().max().item())
+
+
+def test_conv3x3_two_inputs_with_channel_gather(ops, dev):
+    g = torch.Generator().manual_seed(32)
+    B, h, w = 2, 19, 45
+    xa = _rand(B, 32, h, w, g=g)
+    wide = _rand(B, 40, h, w, g=g)
+    idx = torch.stack([torch.randperm(40, generator=g)[:32] for _ in range(B)]).to(torch.int32)
+    wt = _rand(32, 64, 3, 3, g=g, s=0.1)
+    gathered = torch.stack([wide[b, idx[b].long()] for b in range(B)])
+    want = F.conv2d(torch.cat([xa, gathered], 1).double(), wt.double(), None, padding=1)
+    got = ops.conv3x3(xa.to(dev), wt.to(dev), x_b=wide.to(dev), chan_map=idx.to(dev)).cpu().double()
+    assert (got - want).abs().max().item() <= 2e-5 * max(1.0, want.abs().max().item())
+    # identity second input (the cat([LL, x_d]) of DownFRG)
+    xb = _rand(B, 32, h, w, g=g)
+    want = F.conv2d(torch.cat([xa, xb], 1).double(), wt.double(), None, padding=1)
+    got = ops.conv3x3(xa.to(dev), wt.to(dev), x_b=xb.to(dev)).cpu().double()
+    assert (got - want).abs().max().item() <= 2e-5 * max(1.0, want.abs().max().item())
+
+
+def test_conv3x3_paconv_gate(ops, dev):
+    """PAConv stage A: k3(x) * sigmoid(k2(x) + b) in one kernel (reference :694-697)."""
+    g = torch.Generator().manual_seed(33)
+    x = _rand(2, 64, 21, 50, g=g)
+    k3 = _rand(64, 64, 3, 3, g=g, s=0.1)
+    k2w, k2b = _rand(64, 64, 1, 1, g=g, s=0.2), _rand(64, g=g, s=0.1)
+    want = F.conv2d(x.double(), k3.double(), None, padding=1) * torch.sigmoid(
+        F.conv2d(x.double(), k2w.double(), k2b.double()))
+    got = ops.conv3x3(x.to(dev), k3.to(dev), gate_w=k2w.to(dev), gate_b=k2b.to(dev)).cpu().double()
+    assert (got - want).abs().max().item() <= 2e-5 * max(1.0, want.abs().max().item())

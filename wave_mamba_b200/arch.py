@@ -189,16 +189,19 @@ class LayerNorm2d(nn.Module):
 
 
 class PAConv(nn.Module):
+    """reference :683-700.  Two tensor-core kernels: k3 (+ the 1x1 k2 sigmoid gate) and k4."""
+
     def __init__(self, nf: int):
         super().__init__()
         self.k2 = nn.Conv2d(nf, nf, 1)
         self.k3 = nn.Conv2d(nf, nf, 3, padding=1, bias=False)
         self.k4 = nn.Conv2d(nf, nf // 2, 3, padding=1, bias=False)
 
-    def forward(self, x):
-        t = F.conv2d(x, self.k3.weight, None, padding=1)                    # dense 3x3: cuDNN ("next")
-        t = ops.paconv_gate(x, self.k2.weight, self.k2.bias, t, inplace=True)
-        return F.conv2d(t, self.k4.weight, None, padding=1)
+    def forward(self, x, x_b=None, chan_map=None):
+        """x (+ x_b gathered by chan_map) are the 2*dim input channels (the reference's cat)."""
+        t = ops.conv3x3(x, self.k3.weight, x_b=x_b, chan_map=chan_map, gate_w=self.k2.weight,
+                        gate_b=self.k2.bias)                                   # :694-697
+        return ops.conv3x3(t, self.k4.weight)                                  # :698
 
 
 def nearest_channel_index(x: torch.Tensor, perception: torch.Tensor) -> torch.Tensor:
@@ -217,14 +220,10 @@ class Matching_transformation(nn.Module):
         self.last_index = None  # kept for parity tests (argmin indices)
 
     def forward(self, x, perception):
-        B, C, h, w = x.shape
         idx = nearest_channel_index(x, perception)
         self.last_index = idx
-        cat = torch.empty(B, 2 * C, h, w, device=x.device, dtype=x.dtype)
-        cat[:, :C] = x
-        picked = torch.gather(perception.flatten(2, 3), 1, idx[:, :, None].expand(-1, -1, h * w))
-        cat[:, C:] = picked.view(B, C, h, w)
-        return self.paconv(cat)
+        # cat([x, perception[idx]]) (:716) is expressed as a channel gather inside the conv
+        return self.paconv(x, perception, idx.to(torch.int32).contiguous())
 
 
 class FeedForward(nn.Module):
@@ -331,7 +330,7 @@ class DownFRG(nn.Module):
 
     def forward(self, x, x_d):
         ll, hl, lh, hh = self.dwt(x)
-        low = self.l_conv(torch.cat([ll, x_d], dim=1))
+        low = ops.conv3x3(ll, self.l_conv.weight, self.l_conv.bias, x_b=x_d.contiguous())  # cat-free :975
         low = _run_low(self.l_blk, low)
         high = self.h_fusion([hl, lh, hh])
         for blk in self.h_blk:
@@ -351,7 +350,7 @@ class upFRG(nn.Module):
         x_l = _run_low(self.l_blk, x_l)
         for blk in self.h_blk:
             x_h = blk(x_h, x_l)
-        x_h = self.h_out_conv(x_h)
+        x_h = ops.conv3x3(x_h, self.h_out_conv.weight, self.h_out_conv.bias)       # :1005
         return self.iwt(x_l, x_h)  # IWT of cat([x_l, x_h]) without the cat (:1006)
 
 

@@ -1,0 +1,309 @@
+// Dense 3x3 convolution (stride 1, zero padding 1) as an implicit GEMM on the tensor cores,
+// fp32-accurate through the 3xTF32 split, NCHW in and out -- no layout transposes, no im2col.
+//
+// Serves (reference wavemamba_arch.py): PAConv.k3 / k4 (:689-698, 1.49 of ~2.05 TFLOP per 4K
+// image), DownFRG.l_conv (:966,975) and upFRG.h_out_conv (:993,1005).  cuDNN runs these either in
+// fp32 SIMT (66 ms per 4K image) or in TF32 (fast, but measured 2.8e-3 dB outside the 1e-3 dB PSNR
+// budget); the split a = a_hi + a_lo, b = b_hi + b_lo with a_lo*b_hi + a_hi*b_lo + a_hi*b_hi
+// accumulated in fp32 keeps fp32 accuracy on the tensor pipe.
+//
+// GEMM view per CTA: M = 8 x 32 output pixels, N = COUT, K = 9 taps x CIN.
+//   * the CIN-channel input tile with a 1-pixel halo is staged once in shared memory as
+//     xs[ci][position] (row stride == 8 mod 32 so mma A-fragment loads are conflict-free);
+//     a tap is just a constant offset into it;
+//   * weights are pre-packed once per layer into mma B-fragment order, already split into
+//     tf32 hi/lo (wm_conv3x3_prepack), and streamed tap by tap with cp.async double buffering;
+//   * warp w owns tile row w: 2 m-tiles x COUT/8 n-tiles of m16n8k8 accumulators in registers.
+// Fusions: the input may come from two tensors with a per-batch channel gather for the second
+//   (torch.cat([x, matched perception]) of Matching_transformation :716 is never materialised);
+//   PAConv stage A adds the 1x1 k2 as a 10th "tap" and applies  k3(x) * sigmoid(k2(x) + b)  in
+//   the epilogue (:694-697); plain mode adds the conv bias.
+#include "common.cuh"
+
+namespace wm {
+namespace conv {
+
+constexpr int kTH = 8, kTW = 32;
+constexpr int kHW = kTW + 2;            // halo row length 34
+constexpr int kHalo = (kTH + 2) * kHW;  // 340
+constexpr int kPS = 360;                // xs row stride (== 8 mod 32)
+constexpr int kThreads = 256;
+
+struct Args {
+    const float *in_a;       // first Ca channels: (B, >=Ca, h, w), batch stride a_bstride
+    int64_t a_bstride;
+    int Ca;
+    const float *in_b;       // remaining Cin-Ca channels, gathered through chan_map (or identity)
+    int64_t b_bstride;
+    const int *chan_map;     // (B, Cin-Ca) channel indices into in_b, or null
+    const float4 *packed;    // [ntaps][CIN/8][COUT/8][32] {b0_hi, b1_hi, b0_lo, b1_lo}
+    const float *bias;       // (COUT) or null
+    const float *gate_bias;  // (COUT): PAConv stage A
+    float *out;              // (B, COUT, h, w)
+    int h, w;
+};
+
+__device__ __forceinline__ uint32_t to_tf32(float v)
+{
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0,
+                                         uint32_t b1)
+{
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
+        "{%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int CIN, int COUT>
+__device__ __forceinline__ void issue_weights(float4 *dst, const float4 *src)
+{
+    constexpr int kF4 = (CIN / 8) * (COUT / 8) * 32;
+    for (int i = threadIdx.x; i < kF4; i += kThreads) {
+        const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst + i);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + i) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// One tap: acc[mt][nt] += A(tap) * W(tap) over all CIN, 3xTF32.
+template <int CIN, int COUT>
+__device__ __forceinline__ void tap_mma(const float *abase, const float4 *wb, int lane,
+                                        float (&acc)[2][COUT / 8][4])
+{
+    constexpr int KS = CIN / 8, NT = COUT / 8;
+#pragma unroll 2
+    for (int ks = 0; ks < KS; ++ks) {
+        uint32_t ahi[2][4], alo[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            const float *ap = abase + ks * 8 * kPS + mt * 16;
+            const float av[4] = {ap[0], ap[8], ap[4 * kPS], ap[4 * kPS + 8]};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                ahi[mt][i] = to_tf32(av[i]);
+                alo[mt][i] = to_tf32(av[i] - __uint_as_float(ahi[mt][i]));
+            }
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const float4 bw = wb[(ks * NT + nt) * 32 + lane];
+            const uint32_t bh0 = __float_as_uint(bw.x), bh1 = __float_as_uint(bw.y);
+            const uint32_t bl0 = __float_as_uint(bw.z), bl1 = __float_as_uint(bw.w);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                mma_tf32(acc[mt][nt], alo[mt], bh0, bh1);
+                mma_tf32(acc[mt][nt], ahi[mt], bl0, bl1);
+                mma_tf32(acc[mt][nt], ahi[mt], bh0, bh1);
+            }
+        }
+    }
+}
+
+// GATE: PAConv stage A (10 taps, sigmoid gate).  Otherwise 9 taps (+ optional bias).
+template <int CIN, int COUT, bool GATE>
+__global__ void __launch_bounds__(kThreads, 1)
+conv3x3_kernel(const Args a)
+{
+    constexpr int KS = CIN / 8, NT = COUT / 8;
+    constexpr int kF4 = KS * NT * 32;          // float4 per tap
+    extern __shared__ __align__(16) float smem[];
+    float *xs = smem;                           // [CIN][kPS]
+    float4 *wbuf = reinterpret_cast<float4 *>(smem + CIN * kPS);   // [2][kF4]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gq = lane >> 2, t4 = lane & 3;
+    const int tx0 = blockIdx.x * kTW, ty0 = blockIdx.y * kTH;
+    const int64_t b = blockIdx.z;
+    const int h = a.h, w = a.w;
+    const int64_t hw = (int64_t)h * w;
+
+    issue_weights<CIN, COUT>(wbuf, a.packed);   // tap 0 in flight during the halo load
+
+    // ---- stage the input tile (zero padding outside the image) ----------------------------
+    for (int c = warp; c < CIN; c += kThreads / 32) {
+        const float *plane;
+        if (c < a.Ca) {
+            plane = a.in_a + b * a.a_bstride + (int64_t)c * hw;
+        } else {
+            const int cb = a.chan_map ? __ldg(a.chan_map + b * (CIN - a.Ca) + (c - a.Ca)) : c - a.Ca;
+            plane = a.in_b + b * a.b_bstride + (int64_t)cb * hw;
+        }
+        float *dst = xs + c * kPS;
+        for (int pos = lane; pos < kHalo; pos += 32) {
+            const int py = pos / kHW, px = pos - py * kHW;
+            const int gy = ty0 - 1 + py, gx = tx0 - 1 + px;
+            float v = 0.0f;
+            if (gy >= 0 && gy < h && gx >= 0 && gx < w) v = __ldg(plane + (int64_t)gy * w + gx);
+            dst[pos] = v;
+        }
+    }
+
+    float acc[2][NT][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.0f;
+
+    constexpr int NTAPS = GATE ? 10 : 9;
+#pragma unroll 1
+    for (int tap = 0; tap < 9; ++tap) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();   // weights[tap] (and, at tap 0, the halo) visible; buffer (tap+1)&1 free
+        if (tap + 1 < NTAPS)
+            issue_weights<CIN, COUT>(wbuf + ((tap + 1) & 1) * kF4, a.packed + (int64_t)(tap + 1) * kF4);
+        const int dy = tap / 3, dx = tap - dy * 3;
+        const float *abase = xs + t4 * kPS + (warp + dy) * kHW + gq + dx;
+        tap_mma<CIN, COUT>(abase, wbuf + (tap & 1) * kF4, lane, acc);
+    }
+
+    if (GATE) {
+        // 10th tap: the 1x1 k2 on the centre position, into its own accumulators
+        float gate[2][NT][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) gate[mt][nt][i] = 0.0f;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        const float *abase = xs + t4 * kPS + (warp + 1) * kHW + gq + 1;
+        tap_mma<CIN, COUT>(abase, wbuf + (9 & 1) * kF4, lane, gate);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int co = nt * 8 + 2 * t4 + (i & 1);
+                    const float z = gate[mt][nt][i] + __ldg(a.gate_bias + co);
+                    acc[mt][nt][i] *= 1.0f / (1.0f + expf(-z));
+                }
+    }
+
+    // ---- epilogue: fragments -> NCHW -----------------------------------------------------
+    const int gy = ty0 + warp;
+    if (gy < h) {
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int co = nt * 8 + 2 * t4 + (i & 1);
+                    const int gx = tx0 + mt * 16 + gq + ((i & 2) ? 8 : 0);
+                    if (gx < w) {
+                        float v = acc[mt][nt][i];
+                        if (!GATE && a.bias) v += __ldg(a.bias + co);
+                        a.out[(b * COUT + co) * hw + (int64_t)gy * w + gx] = v;
+                    }
+                }
+    }
+}
+
+// w3: (COUT, CIN, 3, 3); w1: (COUT, CIN) or null -> packed[tap][ks][nt][lane] float4
+__global__ void __launch_bounds__(256)
+prepack_kernel(const float *__restrict__ w3, const float *__restrict__ w1, float4 *__restrict__ out,
+               int CIN, int COUT, int ntaps)
+{
+    const int KS = CIN / 8, NT = COUT / 8;
+    const int total = ntaps * KS * NT * 32;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
+        const int lane = i & 31;
+        int r = i >> 5;
+        const int nt = r % NT; r /= NT;
+        const int ks = r % KS;
+        const int tap = r / KS;
+        const int gq = lane >> 2, t4 = lane & 3;
+        const int co = nt * 8 + gq, ci0 = ks * 8 + t4, ci1 = ci0 + 4;
+        float v0, v1;
+        if (tap < 9) {
+            v0 = w3[((int64_t)co * CIN + ci0) * 9 + tap];
+            v1 = w3[((int64_t)co * CIN + ci1) * 9 + tap];
+        } else {
+            v0 = w1[(int64_t)co * CIN + ci0];
+            v1 = w1[(int64_t)co * CIN + ci1];
+        }
+        const uint32_t h0 = to_tf32(v0), h1 = to_tf32(v1);
+        const uint32_t l0 = to_tf32(v0 - __uint_as_float(h0)), l1 = to_tf32(v1 - __uint_as_float(h1));
+        out[i] = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(l0),
+                             __uint_as_float(l1));
+    }
+}
+
+template <int CIN, int COUT, bool GATE>
+int launch(const Args &a, int64_t B, cudaStream_t s)
+{
+    constexpr size_t smem = sizeof(float) * (CIN * kPS) + 2 * sizeof(float4) * (CIN / 8) * (COUT / 8) * 32;
+    WM_CUDA_OK(cudaFuncSetAttribute(conv3x3_kernel<CIN, COUT, GATE>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((a.w + kTW - 1) / kTW, (a.h + kTH - 1) / kTH, (unsigned)B);
+    conv3x3_kernel<CIN, COUT, GATE><<<grid, kThreads, smem, s>>>(a);
+    WM_LAUNCH_OK("conv3x3");
+    return WM_OK;
+}
+
+}  // namespace conv
+}  // namespace wm
+
+extern "C" size_t wm_conv3x3_packed_bytes(int64_t Cin, int64_t Cout, int with_gate)
+{
+    if (Cin <= 0 || Cout <= 0 || Cin % 8 || Cout % 8) return 0;
+    return (size_t)(with_gate ? 10 : 9) * (Cin / 8) * (Cout / 8) * 32 * sizeof(float4);
+}
+
+extern "C" int wm_conv3x3_prepack(const float *w3x3, const float *w1x1, void *packed, int64_t Cin,
+                                  int64_t Cout, wm_stream_t stream)
+{
+    using namespace wm;
+    WM_REQUIRE(w3x3 && packed, "wm_conv3x3_prepack: null pointer");
+    WM_REQUIRE(Cin > 0 && Cout > 0 && Cin % 8 == 0 && Cout % 8 == 0 && Cin <= 512 && Cout <= 512,
+               "wm_conv3x3_prepack: Cin=%lld Cout=%lld must be multiples of 8", (long long)Cin,
+               (long long)Cout);
+    WM_REQUIRE(aligned16(packed), "wm_conv3x3_prepack: packed must be 16-byte aligned");
+    const int ntaps = w1x1 ? 10 : 9;
+    const int total = ntaps * (int)(Cin / 8) * (int)(Cout / 8) * 32;
+    conv::prepack_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        w3x3, w1x1, static_cast<float4 *>(packed), (int)Cin, (int)Cout, ntaps);
+    WM_LAUNCH_OK("conv3x3 prepack");
+    return WM_OK;
+}
+
+extern "C" int wm_conv3x3_fwd(const float *in_a, int64_t a_bstride, int64_t Ca, const float *in_b,
+                              int64_t b_bstride, const int *chan_map, const void *packed,
+                              const float *bias, const float *gate_bias, float *out, int64_t B,
+                              int64_t Cin, int64_t Cout, int64_t h, int64_t w, wm_stream_t stream)
+{
+    using namespace wm;
+    using namespace wm::conv;
+    WM_REQUIRE(B >= 0 && B <= 65535 && h >= 0 && w >= 0 && h < (1 << 24) && w < (1 << 24),
+               "wm_conv3x3_fwd: bad sizes");
+    if (B == 0 || h == 0 || w == 0) return WM_OK;
+    WM_REQUIRE(in_a && packed && out, "wm_conv3x3_fwd: null pointer");
+    WM_REQUIRE(Ca > 0 && Ca <= Cin && (Ca == Cin || in_b != nullptr),
+               "wm_conv3x3_fwd: Ca=%lld of Cin=%lld needs a second input", (long long)Ca, (long long)Cin);
+    WM_REQUIRE((h + kTH - 1) / kTH <= 65535, "wm_conv3x3_fwd: image too tall");
+    WM_REQUIRE(aligned16(packed), "wm_conv3x3_fwd: packed weights must be 16-byte aligned");
+    Args a;
+    a.in_a = in_a; a.a_bstride = a_bstride; a.Ca = (int)Ca; a.in_b = in_b; a.b_bstride = b_bstride;
+    a.chan_map = chan_map; a.packed = static_cast<const float4 *>(packed); a.bias = bias;
+    a.gate_bias = gate_bias; a.out = out; a.h = (int)h; a.w = (int)w;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (gate_bias) {
+        WM_REQUIRE(Cin == 64 && Cout == 64, "wm_conv3x3_fwd: gated mode supports 64->64 only");
+        return launch<64, 64, true>(a, B, s);
+    }
+    if (Cin == 64 && Cout == 32) return launch<64, 32, false>(a, B, s);
+    if (Cin == 64 && Cout == 64) return launch<64, 64, false>(a, B, s);
+    if (Cin == 32 && Cout == 96) return launch<32, 96, false>(a, B, s);
+    if (Cin == 32 && Cout == 32) return launch<32, 32, false>(a, B, s);
+    WM_REQUIRE(false, "wm_conv3x3_fwd: Cin=%lld Cout=%lld unsupported", (long long)Cin, (long long)Cout);
+    return WM_EINVAL;
+}

@@ -339,3 +339,89 @@ def gram32(x: torch.Tensor, y: torch.Tensor):
     _cabi.check(rc, "wm_gram32_fwd")
     _count(2)
     return out[:, :1024].view(B, 32, 32), out[:, 1024:1056], out[:, 1056:1088]
+
+
+_packed_cache = {}
+
+
+def conv3x3_pack(w3x3: torch.Tensor, w1x1: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Pre-pack (Cout,Cin,3,3) weights (+ optional (Cout,Cin[,1,1]) 1x1 gate weights) into mma
+    fragment order with the tf32 hi/lo split.  Cached per (storage, version)."""
+    _chk(w3x3, "w3x3")
+    Cout, Cin = w3x3.shape[0], w3x3.shape[1]
+    key = (w3x3.data_ptr(), w3x3._version, None if w1x1 is None else (w1x1.data_ptr(), w1x1._version),
+           str(w3x3.device))
+    hit = _packed_cache.get(key)
+    if hit is not None:
+        return hit
+    if w1x1 is not None:
+        _chk(w1x1, "w1x1")
+        if w1x1.numel() != Cout * Cin:
+            raise ValueError("w1x1 must be (Cout, Cin[,1,1])")
+    lib = _cabi.load()
+    nbytes = lib.wm_conv3x3_packed_bytes(Cin, Cout, 1 if w1x1 is not None else 0)
+    if nbytes == 0:
+        raise ValueError(f"conv3x3: Cin={Cin} Cout={Cout} must be multiples of 8")
+    packed = torch.empty(nbytes // 4, device=w3x3.device, dtype=torch.float32)
+    with torch.cuda.device(w3x3.device):
+        rc = lib.wm_conv3x3_prepack(w3x3.data_ptr(), _ptr(w1x1), packed.data_ptr(), Cin, Cout,
+                                    _stream(w3x3))
+    _cabi.check(rc, "wm_conv3x3_prepack")
+    _count(1)
+    if len(_packed_cache) > 256:
+        _packed_cache.clear()
+    _packed_cache[key] = packed
+    return packed
+
+
+def conv3x3(x_a, w3x3, bias=None, x_b=None, chan_map=None, gate_w=None, gate_b=None) -> torch.Tensor:
+    """Dense 3x3 conv, stride 1, zero pad 1 (3xTF32 tensor-core implicit GEMM, fp32-accurate).
+
+    Input channels = x_a's channels followed by x_b's (optionally gathered per batch item through
+    ``chan_map`` (B, Cb) int32) -- the reference's torch.cat is not materialised.
+    ``gate_w``/``gate_b``: PAConv stage A, returns conv3x3(x) * sigmoid(conv1x1(x; gate_w) + gate_b)."""
+    _chk_planes(x_a, "x_a")
+    B, Ca, h, w = x_a.shape
+    Cout, Cin = w3x3.shape[0], w3x3.shape[1]
+    Cb = Cin - Ca
+    if Cb < 0 or (Cb > 0 and x_b is None):
+        raise ValueError(f"conv3x3: weight expects {Cin} input channels, got {Ca} (+ x_b)")
+    if x_b is not None:
+        _chk_planes(x_b, "x_b")
+        if x_b.shape[0] != B or tuple(x_b.shape[2:]) != (h, w):
+            raise ValueError("x_b must match x_a in batch and spatial size")
+        if chan_map is None and x_b.shape[1] != Cb:
+            raise ValueError(f"x_b has {x_b.shape[1]} channels, expected {Cb}")
+    if chan_map is not None:
+        if chan_map.dtype != torch.int32 or tuple(chan_map.shape) != (B, Cb) or not chan_map.is_cuda \
+                or not chan_map.is_contiguous():
+            raise ValueError("chan_map must be a contiguous CUDA int32 tensor of shape (B, Cin - Ca)")
+    if bias is not None:
+        _chk(bias, "bias", (Cout,))
+    if (gate_w is None) != (gate_b is None):
+        raise ValueError("gate_w and gate_b come together")
+    if gate_b is not None:
+        _chk(gate_b, "gate_b", (Cout,))
+    packed = conv3x3_pack(w3x3, gate_w)
+    out = torch.empty(B, Cout, h, w, device=x_a.device, dtype=torch.float32)
+    lib = _cabi.load()
+    with torch.cuda.device(x_a.device):
+        rc = lib.wm_conv3x3_fwd(x_a.data_ptr(), x_a.stride(0) if B > 1 else Ca * h * w, Ca,
+                                _ptr(x_b), 0 if x_b is None else (x_b.stride(0) if B > 1 else 0),
+                                _ptr(chan_map), packed.data_ptr(), _ptr(bias), _ptr(gate_b),
+                                out.data_ptr(), B, Cin, Cout, h, w, _stream(x_a))
+    _cabi.check(rc, "wm_conv3x3_fwd")
+    _count(1)
+    return out
+
+
+def _chk_planes(t: torch.Tensor, name: str):
+    """(B,C,h,w) float32 CUDA tensor whose channel planes are contiguous (batch stride free)."""
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _cabi.WaveMambaNativeError(f"{name}: expected a CUDA tensor (no CPU fallback)")
+    if t.dtype != torch.float32 or t.dim() != 4:
+        raise TypeError(f"{name}: expected float32 (B,C,h,w), got {t.dtype} {tuple(t.shape)}")
+    B, C, h, w = t.shape
+    if t.numel() and (t.stride(3) != 1 or t.stride(2) != w or t.stride(1) != h * w):
+        raise ValueError(f"{name}: channel planes must be contiguous, got strides {t.stride()}")
+    return t
