@@ -89,18 +89,26 @@ __device__ __forceinline__ void tap_mma(const float *abase, const float4 *wb, in
                 alo[mt][i] = to_tf32(av[i] - __uint_as_float(ahi[mt][i]));
             }
         }
+        // the three partial products of one (mt, nt) accumulator are issued NT*2 MMAs apart so
+        // consecutive tensor-core instructions never depend on each other
+        float4 bw[NT];
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-            const float4 bw = wb[(ks * NT + nt) * 32 + lane];
-            const uint32_t bh0 = __float_as_uint(bw.x), bh1 = __float_as_uint(bw.y);
-            const uint32_t bl0 = __float_as_uint(bw.z), bl1 = __float_as_uint(bw.w);
+        for (int nt = 0; nt < NT; ++nt) bw[nt] = wb[(ks * NT + nt) * 32 + lane];
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
-                mma_tf32(acc[mt][nt], alo[mt], bh0, bh1);
-                mma_tf32(acc[mt][nt], ahi[mt], bl0, bl1);
-                mma_tf32(acc[mt][nt], ahi[mt], bh0, bh1);
-            }
-        }
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+                mma_tf32(acc[mt][nt], alo[mt], __float_as_uint(bw[nt].x), __float_as_uint(bw[nt].y));
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+                mma_tf32(acc[mt][nt], ahi[mt], __float_as_uint(bw[nt].z), __float_as_uint(bw[nt].w));
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+                mma_tf32(acc[mt][nt], ahi[mt], __float_as_uint(bw[nt].x), __float_as_uint(bw[nt].y));
     }
 }
 

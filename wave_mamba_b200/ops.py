@@ -6,6 +6,7 @@ nothing silently falls back to a PyTorch or CPU implementation.
 """
 from __future__ import annotations
 
+import weakref
 from typing import Optional, Tuple
 
 import torch
@@ -341,19 +342,23 @@ def gram32(x: torch.Tensor, y: torch.Tensor):
     return out[:, :1024].view(B, 32, 32), out[:, 1024:1056], out[:, 1056:1088]
 
 
-_packed_cache = {}
+_packed_cache = {}   # id(weight tensor) -> (weakref to it, versions, gate-weight ref, packed)
 
 
 def conv3x3_pack(w3x3: torch.Tensor, w1x1: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Pre-pack (Cout,Cin,3,3) weights (+ optional (Cout,Cin[,1,1]) 1x1 gate weights) into mma
-    fragment order with the tf32 hi/lo split.  Cached per (storage, version)."""
+    fragment order with the tf32 hi/lo split.  Cached per weight tensor object (weakly) and
+    invalidated when either tensor is modified in place (``_version``)."""
     _chk(w3x3, "w3x3")
     Cout, Cin = w3x3.shape[0], w3x3.shape[1]
-    key = (w3x3.data_ptr(), w3x3._version, None if w1x1 is None else (w1x1.data_ptr(), w1x1._version),
-           str(w3x3.device))
+    key = id(w3x3)
     hit = _packed_cache.get(key)
     if hit is not None:
-        return hit
+        ref3, ver3, ref1, ver1, packed = hit
+        same_gate = (ref1 is None and w1x1 is None) or (ref1 is not None and ref1() is w1x1)
+        if ref3() is w3x3 and ver3 == w3x3._version and same_gate and \
+                (w1x1 is None or ver1 == w1x1._version):
+            return packed
     if w1x1 is not None:
         _chk(w1x1, "w1x1")
         if w1x1.numel() != Cout * Cin:
@@ -368,9 +373,9 @@ def conv3x3_pack(w3x3: torch.Tensor, w1x1: Optional[torch.Tensor] = None) -> tor
                                     _stream(w3x3))
     _cabi.check(rc, "wm_conv3x3_prepack")
     _count(1)
-    if len(_packed_cache) > 256:
-        _packed_cache.clear()
-    _packed_cache[key] = packed
+    _packed_cache[key] = (weakref.ref(w3x3, lambda _r, k=key: _packed_cache.pop(k, None)),
+                          w3x3._version, None if w1x1 is None else weakref.ref(w1x1),
+                          None if w1x1 is None else w1x1._version, packed)
     return packed
 
 
