@@ -13,7 +13,7 @@
 //     a tap is just a constant offset into it;
 //   * weights are pre-packed once per layer into mma B-fragment order, already split into
 //     tf32 hi/lo (wm_conv3x3_prepack), and streamed tap by tap with cp.async double buffering;
-//   * warp w owns tile row w: 2 m-tiles x COUT/8 n-tiles of m16n8k8 accumulators in registers.
+//   * 16 warps: warp = (tile row, 16-pixel half) owns COUT/8 m16n8k8 accumulators in registers.
 // Fusions: the input may come from two tensors with a per-batch channel gather for the second
 //   (torch.cat([x, matched perception]) of Matching_transformation :716 is never materialised);
 //   PAConv stage A adds the 1x1 k2 as a 10th "tap" and applies  k3(x) * sigmoid(k2(x) + b)  in
@@ -27,7 +27,7 @@ constexpr int kTH = 8, kTW = 32;
 constexpr int kHW = kTW + 2;            // halo row length 34
 constexpr int kHalo = (kTH + 2) * kHW;  // 340
 constexpr int kPS = 360;                // xs row stride (== 8 mod 32)
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;   // 16 warps: warp = (tile row, 16-pixel half)
 
 struct Args {
     const float *in_a;       // first Ca channels: (B, >=Ca, h, w), batch stride a_bstride
@@ -70,45 +70,36 @@ __device__ __forceinline__ void issue_weights(float4 *dst, const float4 *src)
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-// One tap: acc[mt][nt] += A(tap) * W(tap) over all CIN, 3xTF32.
+// One tap: acc[nt] += A(tap) * W(tap) over all CIN, 3xTF32.  One 16-pixel m-tile per warp.
 template <int CIN, int COUT>
 __device__ __forceinline__ void tap_mma(const float *abase, const float4 *wb, int lane,
-                                        float (&acc)[2][COUT / 8][4])
+                                        float (&acc)[COUT / 8][4])
 {
     constexpr int KS = CIN / 8, NT = COUT / 8;
 #pragma unroll 2
     for (int ks = 0; ks < KS; ++ks) {
-        uint32_t ahi[2][4], alo[2][4];
+        uint32_t ahi[4], alo[4];
+        const float *ap = abase + ks * 8 * kPS;
+        const float av[4] = {ap[0], ap[8], ap[4 * kPS], ap[4 * kPS + 8]};
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-            const float *ap = abase + ks * 8 * kPS + mt * 16;
-            const float av[4] = {ap[0], ap[8], ap[4 * kPS], ap[4 * kPS + 8]};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                ahi[mt][i] = to_tf32(av[i]);
-                alo[mt][i] = to_tf32(av[i] - __uint_as_float(ahi[mt][i]));
-            }
+        for (int i = 0; i < 4; ++i) {
+            ahi[i] = to_tf32(av[i]);
+            alo[i] = to_tf32(av[i] - __uint_as_float(ahi[i]));
         }
-        // the three partial products of one (mt, nt) accumulator are issued NT*2 MMAs apart so
-        // consecutive tensor-core instructions never depend on each other
+        // the three partial products of one accumulator are issued NT MMAs apart so consecutive
+        // tensor-core instructions never depend on each other
         float4 bw[NT];
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) bw[nt] = wb[(ks * NT + nt) * 32 + lane];
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
-                mma_tf32(acc[mt][nt], alo[mt], __float_as_uint(bw[nt].x), __float_as_uint(bw[nt].y));
+            mma_tf32(acc[nt], alo, __float_as_uint(bw[nt].x), __float_as_uint(bw[nt].y));
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
-                mma_tf32(acc[mt][nt], ahi[mt], __float_as_uint(bw[nt].z), __float_as_uint(bw[nt].w));
+            mma_tf32(acc[nt], ahi, __float_as_uint(bw[nt].z), __float_as_uint(bw[nt].w));
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
-                mma_tf32(acc[mt][nt], ahi[mt], __float_as_uint(bw[nt].x), __float_as_uint(bw[nt].y));
+            mma_tf32(acc[nt], ahi, __float_as_uint(bw[nt].x), __float_as_uint(bw[nt].y));
     }
 }
 
@@ -124,6 +115,7 @@ conv3x3_kernel(const Args a)
     float4 *wbuf = reinterpret_cast<float4 *>(smem + CIN * kPS);   // [2][kF4]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int trow = warp >> 1, mhalf = warp & 1;      // my output row in the tile, my 16-px half
     const int gq = lane >> 2, t4 = lane & 3;
     const int tx0 = blockIdx.x * kTW, ty0 = blockIdx.y * kTH;
     const int64_t b = blockIdx.z;
@@ -133,31 +125,50 @@ conv3x3_kernel(const Args a)
     issue_weights<CIN, COUT>(wbuf, a.packed);   // tap 0 in flight during the halo load
 
     // ---- stage the input tile (zero padding outside the image) ----------------------------
-    for (int c = warp; c < CIN; c += kThreads / 32) {
-        const float *plane;
-        if (c < a.Ca) {
-            plane = a.in_a + b * a.a_bstride + (int64_t)c * hw;
-        } else {
-            const int cb = a.chan_map ? __ldg(a.chan_map + b * (CIN - a.Ca) + (c - a.Ca)) : c - a.Ca;
-            plane = a.in_b + b * a.b_bstride + (int64_t)cb * hw;
-        }
-        float *dst = xs + c * kPS;
-        for (int pos = lane; pos < kHalo; pos += 32) {
-            const int py = pos / kHW, px = pos - py * kHW;
-            const int gy = ty0 - 1 + py, gx = tx0 - 1 + px;
-            float v = 0.0f;
-            if (gy >= 0 && gy < h && gx >= 0 && gx < w) v = __ldg(plane + (int64_t)gy * w + gx);
-            dst[pos] = v;
+    // Row-wise: a warp owns (channel, halo-row) pairs; lanes run along the row (34 floats: the
+    // first two lanes take the tail), four rows of loads in flight before the first store.
+    {
+        constexpr int kRows = CIN * (kTH + 2);
+        const int gx0 = tx0 - 1 + lane;           // lanes 0..31 -> halo columns 0..31
+        const int gx1 = tx0 + 31 + lane;          // lanes 0,1   -> halo columns 32,33
+        const bool ok0 = gx0 >= 0 && gx0 < w;
+        const bool ok1 = lane < 2 && gx1 < w;
+#pragma unroll 1
+        for (int r0 = warp * 4; r0 < kRows; r0 += (kThreads / 32) * 4) {
+            float v0[4], v1[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = r0 + i;              // kRows (320 | 640) is a multiple of 16*4
+                const int c = r / (kTH + 2), py = r - c * (kTH + 2);
+                const int gy = ty0 - 1 + py;
+                const float *plane;
+                if (c < a.Ca) {
+                    plane = a.in_a + b * a.a_bstride + (int64_t)c * hw;
+                } else {
+                    const int cb = a.chan_map ? __ldg(a.chan_map + b * (CIN - a.Ca) + (c - a.Ca))
+                                              : c - a.Ca;
+                    plane = a.in_b + b * a.b_bstride + (int64_t)cb * hw;
+                }
+                const bool oky = gy >= 0 && gy < h;
+                v0[i] = (oky && ok0) ? __ldg(plane + (int64_t)gy * w + gx0) : 0.0f;
+                v1[i] = (oky && ok1) ? __ldg(plane + (int64_t)gy * w + gx1) : 0.0f;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = r0 + i;
+                const int c = r / (kTH + 2), py = r - c * (kTH + 2);
+                float *dst = xs + c * kPS + py * kHW;
+                dst[lane] = v0[i];
+                if (lane < 2) dst[32 + lane] = v1[i];
+            }
         }
     }
 
-    float acc[2][NT][4];
+    float acc[NT][4];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.0f;
+        for (int i = 0; i < 4; ++i) acc[nt][i] = 0.0f;
 
     constexpr int NTAPS = GATE ? 10 : 9;
 #pragma unroll 1
@@ -167,52 +178,46 @@ conv3x3_kernel(const Args a)
         if (tap + 1 < NTAPS)
             issue_weights<CIN, COUT>(wbuf + ((tap + 1) & 1) * kF4, a.packed + (int64_t)(tap + 1) * kF4);
         const int dy = tap / 3, dx = tap - dy * 3;
-        const float *abase = xs + t4 * kPS + (warp + dy) * kHW + gq + dx;
+        const float *abase = xs + t4 * kPS + (trow + dy) * kHW + mhalf * 16 + gq + dx;
         tap_mma<CIN, COUT>(abase, wbuf + (tap & 1) * kF4, lane, acc);
     }
 
     if (GATE) {
         // 10th tap: the 1x1 k2 on the centre position, into its own accumulators
-        float gate[2][NT][4];
+        float gate[NT][4];
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+        for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) gate[mt][nt][i] = 0.0f;
+            for (int i = 0; i < 4; ++i) gate[nt][i] = 0.0f;
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
-        const float *abase = xs + t4 * kPS + (warp + 1) * kHW + gq + 1;
+        const float *abase = xs + t4 * kPS + (trow + 1) * kHW + mhalf * 16 + gq + 1;
         tap_mma<CIN, COUT>(abase, wbuf + (9 & 1) * kF4, lane, gate);
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+        for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int co = nt * 8 + 2 * t4 + (i & 1);
-                    const float z = gate[mt][nt][i] + __ldg(a.gate_bias + co);
-                    acc[mt][nt][i] *= 1.0f / (1.0f + expf(-z));
-                }
+            for (int i = 0; i < 4; ++i) {
+                const int co = nt * 8 + 2 * t4 + (i & 1);
+                const float z = gate[nt][i] + __ldg(a.gate_bias + co);
+                acc[nt][i] *= 1.0f / (1.0f + expf(-z));
+            }
     }
 
     // ---- epilogue: fragments -> NCHW -----------------------------------------------------
-    const int gy = ty0 + warp;
+    const int gy = ty0 + trow;
     if (gy < h) {
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+        for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int co = nt * 8 + 2 * t4 + (i & 1);
-                    const int gx = tx0 + mt * 16 + gq + ((i & 2) ? 8 : 0);
-                    if (gx < w) {
-                        float v = acc[mt][nt][i];
-                        if (!GATE && a.bias) v += __ldg(a.bias + co);
-                        a.out[(b * COUT + co) * hw + (int64_t)gy * w + gx] = v;
-                    }
+            for (int i = 0; i < 4; ++i) {
+                const int co = nt * 8 + 2 * t4 + (i & 1);
+                const int gx = tx0 + mhalf * 16 + gq + ((i & 2) ? 8 : 0);
+                if (gx < w) {
+                    float v = acc[nt][i];
+                    if (!GATE && a.bias) v += __ldg(a.bias + co);
+                    a.out[(b * COUT + co) * hw + (int64_t)gy * w + gx] = v;
                 }
+            }
     }
 }
 
