@@ -241,6 +241,8 @@ class OpTimer:
         wrap("conv3x3", lambda a, k, o: nb(a[0]) + nb(o) + (
             0 if k.get("x_b") is None else (a[1].shape[1] - a[0].shape[1]) * a[0].shape[0]
             * a[0].shape[2] * a[0].shape[3] * 4))
+        wrap("stem_conv3x3", lambda a, k, o: nb(a[0]) + nb(o))
+        wrap("head_conv3x3", lambda a, k, o: nb(a[0]) + nb(o) + nb(k.get("residual")))
         wrap("gram32", lambda a, k, o: 2 * 32 * a[0].shape[0] * a[0].shape[2] * a[0].shape[3] * 4)
         wrap("lfss_z", lambda a, k, o: nb(a[0]) + nb(o))
         wrap("lfss_out", lambda a, k, o: nb(a[0], a[1], a[6]) + nb(o) + nb(*k.get("extra", ())))

@@ -31,7 +31,7 @@ extern "C" {
 #define WM_ECUDA (-2)     /* a CUDA runtime call or kernel launch failed               */
 #define WM_ENODEVICE (-3) /* no sm_100-class CUDA device is current                     */
 
-#define WM_ABI_VERSION 5
+#define WM_ABI_VERSION 6
 
 typedef void *wm_stream_t;
 
@@ -160,6 +160,14 @@ int wm_conv3x3_fwd(const float *in_a, int64_t a_bstride, int64_t Ca, const float
                    int64_t b_bstride, const int *chan_map, const void *packed, const float *bias,
                    const float *gate_bias, float *out, int64_t B, int64_t Cin, int64_t Cout,
                    int64_t h, int64_t w, wm_stream_t stream);
+
+/* Stem / head 3x3 convs with 3 channels on one side (direct FFMA, fp32):
+ *   stem: UNet.conv_01 (:1026,1048)  x (B,3,h,w)  -> y (B,32,h,w) = conv3x3(x) + bias
+ *   head: UNet.last + global residual (:1039,1061)  x (B,32,h,w) -> y (B,3,h,w) = conv3x3(x)+bias+residual? */
+int wm_stem_conv3x3_fwd(const float *x, const float *w3x3, const float *bias, float *y, int64_t B,
+                        int64_t h, int64_t w, wm_stream_t stream);
+int wm_head_conv3x3_fwd(const float *x, const float *w3x3, const float *bias, const float *residual,
+                        float *y, int64_t B, int64_t h, int64_t w, wm_stream_t stream);
 
 /* PAConv gate: y = k3out * sigmoid( pw1x1(x) + b ), x and k3out and y all (B,64,h,w)
  * (PAConv.k2 + sigmoid + mul, :694-697).  In-place on k3out allowed (y == k3out). */

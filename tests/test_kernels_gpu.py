@@ -397,3 +397,17 @@ def test_conv3x3_paconv_gate(ops, dev):
         F.conv2d(x.double(), k2w.double(), k2b.double()))
     got = ops.conv3x3(x.to(dev), k3.to(dev), gate_w=k2w.to(dev), gate_b=k2b.to(dev)).cpu().double()
     assert (got - want).abs().max().item() <= 2e-5 * max(1.0, want.abs().max().item())
+
+
+def test_stem_and_head_conv(ops, dev):
+    g = torch.Generator().manual_seed(41)
+    x = torch.rand(2, 3, 21, 45, generator=g)
+    w1, b1 = _rand(32, 3, 3, 3, g=g, s=0.2), _rand(32, g=g, s=0.1)
+    want = F.conv2d(x, w1, b1, padding=1)
+    torch.testing.assert_close(ops.stem_conv3x3(x.to(dev), w1.to(dev), b1.to(dev)).cpu(), want,
+                               rtol=2e-5, atol=2e-5)
+    f = _rand(2, 32, 21, 45, g=g)
+    w2, b2 = _rand(3, 32, 3, 3, g=g, s=0.1), _rand(3, g=g, s=0.1)
+    want = F.conv2d(f, w2, b2, padding=1) + x
+    got = ops.head_conv3x3(f.to(dev), w2.to(dev), b2.to(dev), residual=x.to(dev)).cpu()
+    torch.testing.assert_close(got, want, rtol=2e-5, atol=2e-5)

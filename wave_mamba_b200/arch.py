@@ -380,14 +380,14 @@ class UNet(nn.Module):
         with torch.no_grad():
             x = x.contiguous()
             side = [getattr(self, f"ps_down{l}")(x) for l in (1, 2, 3)]
-            t = self.conv_01(x)
+            t = ops.stem_conv3x3(x, self.conv_01.weight, self.conv_01.bias)
             low, h1 = self.down_group1(t, side[0])
             low, h2 = self.down_group2(low, side[1])
             low, h3 = self.down_group3(low, side[2])
             low = self.up_group3(low, h3)
             low = self.up_group2(low, h2)
             low = self.up_group1(low, h1)
-            return self.last(low) + x
+            return ops.head_conv3x3(low, self.last.weight, self.last.bias, residual=x)
 
 
 class WaveMamba(nn.Module):

@@ -338,3 +338,128 @@ extern "C" int wm_dw_act_pw_fwd(const float *x, const float *dw_w, const float *
     return WM_OK;
 }
 
+
+// =============================================================================================
+// Stem / head 3x3 convolutions with a tiny channel count on one side (UNet.conv_01 3->32,
+// reference :1026,1048; UNet.last 32->3 + the global residual, :1039,1061).  Direct FFMA over an
+// 8x32 tile with halo in shared memory; thread = output pixel; weights broadcast from smem.
+// =============================================================================================
+namespace wm {
+namespace pw {
+
+// out[co] = bias[co] + sum_{ci,tap} w[co][ci][tap] * in[ci][tap]   (CIN = 3, COUT = 32)
+__global__ void __launch_bounds__(kThreads)
+stem_conv3x3_kernel(const float *__restrict__ x, const float *__restrict__ wgt,
+                    const float *__restrict__ bias, float *__restrict__ y, int h, int w)
+{
+    constexpr int CIN = 3, COUT = 32;
+    __shared__ __align__(16) float xs[CIN * kXP];
+    __shared__ __align__(16) float wt[CIN * 9 * COUT];   // [ci*9+tap][co]
+    __shared__ float bs[COUT];
+    const int tid = threadIdx.x;
+    const int tx0 = blockIdx.x * kTW, ty0 = blockIdx.y * kTH;
+    const int64_t b = blockIdx.z;
+    const int64_t hw = (int64_t)h * w;
+    for (int i = tid; i < COUT * CIN * 9; i += kThreads) {
+        const int co = i / (CIN * 9), r = i - co * (CIN * 9);
+        wt[r * COUT + co] = __ldg(wgt + i);
+    }
+    if (tid < COUT) bs[tid] = bias ? __ldg(bias + tid) : 0.0f;
+    load_halo32(x, xs, b, CIN, h, w, ty0, tx0);
+    __syncthreads();
+    const int col = tid & 31, row = tid >> 5;
+    float acc[COUT];
+#pragma unroll
+    for (int j = 0; j < COUT; ++j) acc[j] = bs[j];
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const float xv = xs[ci * kXP + (row + t / 3) * kHW + col + t % 3];
+            const float4 *wr = reinterpret_cast<const float4 *>(wt + (ci * 9 + t) * COUT);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 wv = wr[j];
+                acc[4 * j + 0] = fmaf(xv, wv.x, acc[4 * j + 0]);
+                acc[4 * j + 1] = fmaf(xv, wv.y, acc[4 * j + 1]);
+                acc[4 * j + 2] = fmaf(xv, wv.z, acc[4 * j + 2]);
+                acc[4 * j + 3] = fmaf(xv, wv.w, acc[4 * j + 3]);
+            }
+        }
+    const int gy = ty0 + row, gx = tx0 + col;
+    if (gy < h && gx < w) {
+        float *o = y + b * COUT * hw + (int64_t)gy * w + gx;
+#pragma unroll
+        for (int j = 0; j < COUT; ++j) o[j * hw] = acc[j];
+    }
+}
+
+// out[co] = residual[co] + bias[co] + sum_{ci,tap} w[co][ci][tap] * in[ci][tap]  (CIN = 32, COUT = 3)
+__global__ void __launch_bounds__(kThreads)
+head_conv3x3_kernel(const float *__restrict__ x, const float *__restrict__ wgt,
+                    const float *__restrict__ bias, const float *__restrict__ residual,
+                    float *__restrict__ y, int h, int w)
+{
+    constexpr int CIN = 32, COUT = 3;
+    extern __shared__ __align__(16) float smem[];
+    float *xs = smem;                                   // [32][kXP]
+    float4 *wt = reinterpret_cast<float4 *>(xs + CIN * kXP);   // [ci*9+tap] -> (w0, w1, w2, 0)
+    const int tid = threadIdx.x;
+    const int tx0 = blockIdx.x * kTW, ty0 = blockIdx.y * kTH;
+    const int64_t b = blockIdx.z;
+    const int64_t hw = (int64_t)h * w;
+    for (int i = tid; i < CIN * 9; i += kThreads)
+        wt[i] = make_float4(__ldg(wgt + i), __ldg(wgt + CIN * 9 + i), __ldg(wgt + 2 * CIN * 9 + i), 0.0f);
+    load_halo32(x, xs, b, CIN, h, w, ty0, tx0);
+    __syncthreads();
+    const int col = tid & 31, row = tid >> 5;
+    float a0 = bias ? __ldg(bias + 0) : 0.0f, a1 = bias ? __ldg(bias + 1) : 0.0f,
+          a2 = bias ? __ldg(bias + 2) : 0.0f;
+#pragma unroll 4
+    for (int ci = 0; ci < CIN; ++ci) {
+        const float *xc = xs + ci * kXP + row * kHW + col;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const float xv = xc[(t / 3) * kHW + t % 3];
+            const float4 wv = wt[ci * 9 + t];
+            a0 = fmaf(xv, wv.x, a0); a1 = fmaf(xv, wv.y, a1); a2 = fmaf(xv, wv.z, a2);
+        }
+    }
+    const int gy = ty0 + row, gx = tx0 + col;
+    if (gy < h && gx < w) {
+        const int64_t o = b * COUT * hw + (int64_t)gy * w + gx;
+        if (residual) { a0 += __ldg(residual + o); a1 += __ldg(residual + o + hw); a2 += __ldg(residual + o + 2 * hw); }
+        y[o] = a0; y[o + hw] = a1; y[o + 2 * hw] = a2;
+    }
+}
+
+}  // namespace pw
+}  // namespace wm
+
+extern "C" int wm_stem_conv3x3_fwd(const float *x, const float *w3x3, const float *bias, float *y,
+                                   int64_t B, int64_t h, int64_t w, wm_stream_t stream)
+{
+    WM_REQUIRE(dims_ok(B, h, w) && (h + kTH - 1) / kTH <= 65535, "wm_stem_conv3x3_fwd: bad sizes");
+    if (B == 0 || h == 0 || w == 0) return WM_OK;
+    WM_REQUIRE(x && w3x3 && y, "wm_stem_conv3x3_fwd: null pointer");
+    dim3 grid((unsigned)((w + kTW - 1) / kTW), (unsigned)((h + kTH - 1) / kTH), (unsigned)B);
+    stem_conv3x3_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, w3x3, bias, y, (int)h, (int)w);
+    WM_LAUNCH_OK("stem conv3x3");
+    return WM_OK;
+}
+
+extern "C" int wm_head_conv3x3_fwd(const float *x, const float *w3x3, const float *bias,
+                                   const float *residual, float *y, int64_t B, int64_t h, int64_t w,
+                                   wm_stream_t stream)
+{
+    WM_REQUIRE(dims_ok(B, h, w) && (h + kTH - 1) / kTH <= 65535, "wm_head_conv3x3_fwd: bad sizes");
+    if (B == 0 || h == 0 || w == 0) return WM_OK;
+    WM_REQUIRE(x && w3x3 && y, "wm_head_conv3x3_fwd: null pointer");
+    const size_t smem = sizeof(float) * 32 * kXP + sizeof(float4) * 32 * 9;
+    WM_CUDA_OK(opt_in_smem(head_conv3x3_kernel, smem));
+    dim3 grid((unsigned)((w + kTW - 1) / kTW), (unsigned)((h + kTH - 1) / kTH), (unsigned)B);
+    head_conv3x3_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(x, w3x3, bias, residual, y,
+                                                                        (int)h, (int)w);
+    WM_LAUNCH_OK("head conv3x3");
+    return WM_OK;
+}

@@ -132,6 +132,15 @@ __device__ __forceinline__ uint32_t to_tf32(float v)
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
     return r;
 }
+// Activation-side split for 3xTF32: hi = a with the 13 low mantissa bits cleared (what the
+// tensor core would read anyway), lo = a - hi (exact; the tensor core truncates it to tf32).
+// One LOP3 + one FADD per element -- cvt.rna.tf32 has no native SASS on sm_100 (it expands to
+// FSETP+IADD3+SEL+LOP3).  |a - hi - tf32(lo)| <= 2^-20 |a|, same order as the dropped lo*lo term.
+__device__ __forceinline__ void split_tf32(float a, uint32_t &hi, uint32_t &lo)
+{
+    hi = __float_as_uint(a) & 0xffffe000u;
+    lo = __float_as_uint(a - __uint_as_float(hi));
+}
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0,
                                          uint32_t b1)
 {
@@ -458,10 +467,7 @@ __device__ __forceinline__ void run_cta(const Params &prm, const Geom &g, const 
                 const float av[4] = {ap[0], ap[8], ap[4 * kXS], ap[4 * kXS + 8]};
                 uint32_t ahi[4], alo[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    ahi[i] = to_tf32(av[i]);
-                    alo[i] = to_tf32(av[i] - __uint_as_float(ahi[i]));
-                }
+                for (int i = 0; i < 4; ++i) split_tf32(av[i], ahi[i], alo[i]);
                 const float4 bw = wfp[ks * kNTiles * 32];
                 mma_tf32(c0, alo, __float_as_uint(bw.x), __float_as_uint(bw.y));
                 mma_tf32(c0, ahi, __float_as_uint(bw.z), __float_as_uint(bw.w));

@@ -430,3 +430,41 @@ def _chk_planes(t: torch.Tensor, name: str):
     if t.numel() and (t.stride(3) != 1 or t.stride(2) != w or t.stride(1) != h * w):
         raise ValueError(f"{name}: channel planes must be contiguous, got strides {t.stride()}")
     return t
+
+
+def stem_conv3x3(x, weight, bias=None) -> torch.Tensor:
+    """UNet.conv_01 (reference :1026,1048): (B,3,h,w) -> (B,32,h,w)."""
+    _chk(x, "x")
+    B, C, h, w = x.shape
+    _chk(weight, "weight", (32, 3, 3, 3))
+    if C != 3:
+        raise ValueError(f"stem conv expects 3 input channels, got {C}")
+    if bias is not None:
+        _chk(bias, "bias", (32,))
+    y = torch.empty(B, 32, h, w, device=x.device, dtype=x.dtype)
+    lib = _cabi.load()
+    with torch.cuda.device(x.device):
+        rc = lib.wm_stem_conv3x3_fwd(x.data_ptr(), weight.data_ptr(), _ptr(bias), y.data_ptr(),
+                                     B, h, w, _stream(x))
+    _cabi.check(rc, "wm_stem_conv3x3_fwd")
+    _count(1)
+    return y
+
+
+def head_conv3x3(x, weight, bias=None, residual=None) -> torch.Tensor:
+    """UNet.last + global residual (reference :1039,1061): (B,32,h,w) -> (B,3,h,w)."""
+    _chk(x, "x")
+    B, C, h, w = x.shape
+    _chk(weight, "weight", (3, 32, 3, 3))
+    if bias is not None:
+        _chk(bias, "bias", (3,))
+    if residual is not None:
+        _chk(residual, "residual", (B, 3, h, w))
+    y = torch.empty(B, 3, h, w, device=x.device, dtype=x.dtype)
+    lib = _cabi.load()
+    with torch.cuda.device(x.device):
+        rc = lib.wm_head_conv3x3_fwd(x.data_ptr(), weight.data_ptr(), _ptr(bias), _ptr(residual),
+                                     y.data_ptr(), B, h, w, _stream(x))
+    _cabi.check(rc, "wm_head_conv3x3_fwd")
+    _count(1)
+    return y
