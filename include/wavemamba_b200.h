@@ -31,7 +31,7 @@ extern "C" {
 #define WM_ECUDA (-2)     /* a CUDA runtime call or kernel launch failed               */
 #define WM_ENODEVICE (-3) /* no sm_100-class CUDA device is current                     */
 
-#define WM_ABI_VERSION 6
+#define WM_ABI_VERSION 7
 
 typedef void *wm_stream_t;
 
@@ -154,6 +154,11 @@ int wm_gram32_fwd(const float *x, int64_t x_bstride, const float *y, int64_t y_b
  *                      `packed` must have been built with the 1x1 weights.
  * fp32 accuracy (a_lo*b_hi + a_hi*b_lo + a_hi*b_hi, fp32 accumulate). */
 size_t wm_conv3x3_packed_bytes(int64_t Cin, int64_t Cout, int with_gate);
+/* Two implementations share the entry points and the packed buffer (it holds both weight orders):
+ * 0 = mma.sync m16n8k8 TF32 (legacy tensor path), 1 = tcgen05.mma kind::tf32 with TMEM
+ * accumulators.  Process-wide switch; returns WM_EINVAL for other values. */
+int wm_conv3x3_set_impl(int impl);
+int wm_conv3x3_get_impl(void);
 int wm_conv3x3_prepack(const float *w3x3, const float *w1x1, void *packed, int64_t Cin, int64_t Cout,
                        wm_stream_t stream);
 int wm_conv3x3_fwd(const float *in_a, int64_t a_bstride, int64_t Ca, const float *in_b,

@@ -352,9 +352,18 @@ def test_gram32_argmin_matches_cdist_oracle(ops, dev):
 
 
 # ------------------------------------------------------------------------------- dense 3x3 conv
+@pytest.fixture(params=["mma", "tcgen05"])
+def conv_impl(request, ops):
+    """Both implementations behind wm_conv3x3_fwd: mma.sync and tcgen05/TMEM."""
+    prev = ops.get_conv_impl()
+    ops.set_conv_impl(request.param)
+    yield request.param
+    ops.set_conv_impl(prev)
+
+
 @pytest.mark.parametrize("cin,cout", [(64, 32), (64, 64), (32, 96), (32, 32)])
 @pytest.mark.parametrize("hw", [(13, 37), (8, 32), (40, 70)])
-def test_conv3x3_plain(ops, dev, cin, cout, hw):
+def test_conv3x3_plain(ops, dev, conv_impl, cin, cout, hw):
     """3xTF32 tensor-core conv vs float64 F.conv2d: fp32-level accuracy (not TF32-level)."""
     g = torch.Generator().manual_seed(31)
     h, w = hw
@@ -369,7 +378,7 @@ def test_conv3x3_plain(ops, dev, cin, cout, hw):
     assert err <= 2e-5 * max(1.0, want.abs().max().item())
 
 
-def test_conv3x3_two_inputs_with_channel_gather(ops, dev):
+def test_conv3x3_two_inputs_with_channel_gather(ops, dev, conv_impl):
     g = torch.Generator().manual_seed(32)
     B, h, w = 2, 19, 45
     xa = _rand(B, 32, h, w, g=g)
@@ -387,7 +396,7 @@ def test_conv3x3_two_inputs_with_channel_gather(ops, dev):
     assert (got - want).abs().max().item() <= 2e-5 * max(1.0, want.abs().max().item())
 
 
-def test_conv3x3_paconv_gate(ops, dev):
+def test_conv3x3_paconv_gate(ops, dev, conv_impl):
     """PAConv stage A: k3(x) * sigmoid(k2(x) + b) in one kernel (reference :694-697)."""
     g = torch.Generator().manual_seed(33)
     x = _rand(2, 64, 21, 50, g=g)

@@ -272,10 +272,41 @@ int launch(const Args &a, int64_t B, cudaStream_t s)
 }  // namespace conv
 }  // namespace wm
 
+namespace wm {
+namespace tc5 {   // conv3x3_tc5.cu
+size_t packed_bytes(int64_t Cin, int64_t Cout, int with_gate);
+int prepack(const float *w3x3, const float *w1x1, void *packed, int64_t Cin, int64_t Cout,
+            cudaStream_t s);
+int forward(const float *in_a, int64_t a_bstride, int64_t Ca, const float *in_b, int64_t b_bstride,
+            const int *chan_map, const void *packed, const float *bias, const float *gate_bias,
+            float *out, int64_t B, int64_t Cin, int64_t Cout, int64_t h, int64_t w, cudaStream_t s);
+}  // namespace tc5
+namespace conv {
+static int g_impl = 0;   // 0: mma.sync m16n8k8 (legacy tensor path), 1: tcgen05 + TMEM
+inline size_t mma_part_bytes(int64_t Cin, int64_t Cout, int with_gate)
+{
+    const size_t n = (size_t)(with_gate ? 10 : 9) * (Cin / 8) * (Cout / 8) * 32 * sizeof(float4);
+    return (n + 255) / 256 * 256;
+}
+}  // namespace conv
+}  // namespace wm
+
+extern "C" int wm_conv3x3_set_impl(int impl)
+{
+    if (impl != 0 && impl != 1) {
+        wm::set_error("wm_conv3x3_set_impl: impl must be 0 (mma.sync) or 1 (tcgen05)");
+        return WM_EINVAL;
+    }
+    wm::conv::g_impl = impl;
+    return WM_OK;
+}
+
+extern "C" int wm_conv3x3_get_impl(void) { return wm::conv::g_impl; }
+
 extern "C" size_t wm_conv3x3_packed_bytes(int64_t Cin, int64_t Cout, int with_gate)
 {
     if (Cin <= 0 || Cout <= 0 || Cin % 8 || Cout % 8) return 0;
-    return (size_t)(with_gate ? 10 : 9) * (Cin / 8) * (Cout / 8) * 32 * sizeof(float4);
+    return wm::conv::mma_part_bytes(Cin, Cout, with_gate) + wm::tc5::packed_bytes(Cin, Cout, with_gate);
 }
 
 extern "C" int wm_conv3x3_prepack(const float *w3x3, const float *w1x1, void *packed, int64_t Cin,
@@ -292,7 +323,10 @@ extern "C" int wm_conv3x3_prepack(const float *w3x3, const float *w1x1, void *pa
     conv::prepack_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
         w3x3, w1x1, static_cast<float4 *>(packed), (int)Cin, (int)Cout, ntaps);
     WM_LAUNCH_OK("conv3x3 prepack");
-    return WM_OK;
+    // second half of the buffer: the same weights in tcgen05 (UMMA K-major) order
+    return tc5::prepack(w3x3, w1x1,
+                        static_cast<char *>(packed) + conv::mma_part_bytes(Cin, Cout, w1x1 != nullptr),
+                        Cin, Cout, (cudaStream_t)stream);
 }
 
 extern "C" int wm_conv3x3_fwd(const float *in_a, int64_t a_bstride, int64_t Ca, const float *in_b,
@@ -310,6 +344,11 @@ extern "C" int wm_conv3x3_fwd(const float *in_a, int64_t a_bstride, int64_t Ca, 
                "wm_conv3x3_fwd: Ca=%lld of Cin=%lld needs a second input", (long long)Ca, (long long)Cin);
     WM_REQUIRE((h + kTH - 1) / kTH <= 65535, "wm_conv3x3_fwd: image too tall");
     WM_REQUIRE(aligned16(packed), "wm_conv3x3_fwd: packed weights must be 16-byte aligned");
+    if (g_impl == 1) {
+        const void *tc = static_cast<const char *>(packed) + mma_part_bytes(Cin, Cout, gate_bias != nullptr);
+        return tc5::forward(in_a, a_bstride, Ca, in_b, b_bstride, chan_map, tc, bias, gate_bias, out,
+                            B, Cin, Cout, h, w, (cudaStream_t)stream);
+    }
     Args a;
     a.in_a = in_a; a.a_bstride = a_bstride; a.Ca = (int)Ca; a.in_b = in_b; a.b_bstride = b_bstride;
     a.chan_map = chan_map; a.packed = static_cast<const float4 *>(packed); a.bias = bias;

@@ -468,3 +468,13 @@ def head_conv3x3(x, weight, bias=None, residual=None) -> torch.Tensor:
     _cabi.check(rc, "wm_head_conv3x3_fwd")
     _count(1)
     return y
+
+
+def set_conv_impl(name: str) -> None:
+    """Select the dense-3x3 implementation: "mma" (mma.sync, legacy tensor path) or "tcgen05"
+    (5th-gen tensor cores, TMEM accumulators).  Process-wide."""
+    _cabi.check(_cabi.load().wm_conv3x3_set_impl({"mma": 0, "tcgen05": 1}[name]), "wm_conv3x3_set_impl")
+
+
+def get_conv_impl() -> str:
+    return ("mma", "tcgen05")[_cabi.load().wm_conv3x3_get_impl()]
