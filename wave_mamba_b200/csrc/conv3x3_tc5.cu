@@ -28,6 +28,7 @@ constexpr int kHaloPos = (kR + 2) * kHW;    // 306 real halo positions
 constexpr int kNPos = 328;                  // + zero tail read by the dropped M rows (max 325)
 constexpr int kQ0 = kHW + 1;                // halo position of output (0,0) of the tile
 constexpr int kThreads = 256;
+constexpr int kStages = 3;                  // weight-chunk ring depth
 
 struct Args {
     const float *in_a;
@@ -118,20 +119,38 @@ conv3x3_tc5_kernel(const Args a)
     constexpr int KS = CIN / 8;                 // MMA k-steps (K = 8 for tf32)
     constexpr int NTAPS = GATE ? 10 : 9;
     constexpr int kWF4 = KC * COUT;             // float4 per weight part (hi or lo) per tap
+    constexpr int NCH = CIN >= 64 ? 2 : 1;      // weight chunks per tap (K split so 2 buffers fit)
+    constexpr int KSC = KS / NCH;               // k-steps per chunk
+    constexpr int kCF4 = 2 * kWF4 / NCH;        // float4 per chunk: [hi | lo][2*KSC kc][COUT]
     constexpr int kCols = tmem_cols<COUT, GATE>();
     extern __shared__ __align__(128) float smem[];
     float4 *xhi = reinterpret_cast<float4 *>(smem);          // [KC][kNPos]
     float4 *xlo = xhi + KC * kNPos;                          // [KC][kNPos]
-    float4 *whi = xlo + KC * kNPos;                          // [KC][COUT]
-    float4 *wlo = whi + kWF4;                                // [KC][COUT]
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(wlo + kWF4);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mbar + 1);
+    float4 *wbuf = xlo + KC * kNPos;                         // [kStages][kCF4]
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(wbuf + kStages * kCF4);   // [kStages]: chunk's MMAs done
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mbar + kStages);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx0 = blockIdx.x * kTW, ty0 = blockIdx.y * kR;
     const int64_t b = blockIdx.z;
     const int h = a.h, w = a.w;
     const int64_t hw = (int64_t)h * w;
+
+    // chunk c of the packed weights: tap = c / NCH, K part = c % NCH.  Packed per tap as
+    // [hi|lo][kc][co]; a chunk takes kc in [part*2*KSC, (part+1)*2*KSC) of both hi and lo.
+    auto issue_chunk = [&](int c) {
+        const int tap = c / NCH, part = c - tap * NCH;
+        const float4 *src = a.packed + (int64_t)tap * 2 * kWF4 + part * (2 * KSC * COUT);
+        float4 *dst = wbuf + (c % kStages) * kCF4;
+        constexpr int kHalf = 2 * KSC * COUT;               // float4 of hi (or lo) per chunk
+        for (int i = tid; i < kCF4; i += kThreads) {
+            const int hl = i / kHalf, r = i - hl * kHalf;
+            const uint32_t d = smem_u32(dst + i);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + hl * kWF4 + r)
+                         : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
 
     // ---- one-time setup: TMEM allocation (warp 0), mbarrier init (one thread) ---------------
     if (warp == 0) {
@@ -142,39 +161,55 @@ conv3x3_tc5_kernel(const Args a)
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 32) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)) : "memory");
+#pragma unroll
+        for (int i = 0; i < kStages; ++i)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar + i)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    issue_chunk(0);                              // the first two weight chunks fly during staging
+    issue_chunk(1);
 
     // ---- stage the halo tile: X[kc][pos] = 4 consecutive channels of one position ------------
-    for (int idx = tid; idx < KC * kNPos; idx += kThreads) {
-        const int kc = idx / kNPos, pos = idx - kc * kNPos;
-        float v[4] = {0.f, 0.f, 0.f, 0.f};
-        if (pos < kHaloPos) {
-            const int py = pos / kHW, px = pos - py * kHW;
-            const int gy = ty0 - 1 + py, gx = tx0 - 1 + px;
-            if (gy >= 0 && gy < h && gx >= 0 && gx < w) {
+    // warp w stages kc = w, w+8 (, ...); lanes run along positions; 4 positions x 4 channels of
+    // loads are issued before the first use.
+    for (int kc = warp; kc < KC; kc += kThreads / 32) {
+        const float *plane[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int c = kc * 4 + j;
-                    const float *plane;
-                    if (c < a.Ca) {
-                        plane = a.in_a + b * a.a_bstride + (int64_t)c * hw;
-                    } else {
-                        const int cb = a.chan_map ? __ldg(a.chan_map + b * (CIN - a.Ca) + (c - a.Ca))
-                                                  : c - a.Ca;
-                        plane = a.in_b + b * a.b_bstride + (int64_t)cb * hw;
-                    }
-                    v[j] = __ldg(plane + (int64_t)gy * w + gx);
+        for (int j = 0; j < 4; ++j) {
+            const int c = kc * 4 + j;
+            if (c < a.Ca) {
+                plane[j] = a.in_a + b * a.a_bstride + (int64_t)c * hw;
+            } else {
+                const int cb = a.chan_map ? __ldg(a.chan_map + b * (CIN - a.Ca) + (c - a.Ca)) : c - a.Ca;
+                plane[j] = a.in_b + b * a.b_bstride + (int64_t)cb * hw;
+            }
+        }
+#pragma unroll 1
+        for (int p0 = 0; p0 < kNPos; p0 += 128) {
+            float v[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int pos = p0 + i * 32 + lane;
+                const int py = pos / kHW, px = pos - py * kHW;
+                const int gy = ty0 - 1 + py, gx = tx0 - 1 + px;
+                const bool ok = pos < kHaloPos && gy >= 0 && gy < h && gx >= 0 && gx < w;
+                const int64_t off = (int64_t)gy * w + gx;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[i][j] = ok ? __ldg(plane[j] + off) : 0.0f;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int pos = p0 + i * 32 + lane;
+                if (pos < kNPos) {
+                    float lo[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        lo[j] = v[i][j] - __uint_as_float(__float_as_uint(v[i][j]) & 0xffffe000u);
+                    xhi[kc * kNPos + pos] = make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
+                    xlo[kc * kNPos + pos] = make_float4(lo[0], lo[1], lo[2], lo[3]);
                 }
             }
         }
-        float lo[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            lo[j] = v[j] - __uint_as_float(__float_as_uint(v[j]) & 0xffffe000u);
-        xhi[idx] = make_float4(v[0], v[1], v[2], v[3]);
-        xlo[idx] = make_float4(lo[0], lo[1], lo[2], lo[3]);
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -186,31 +221,37 @@ conv3x3_tc5_kernel(const Args a)
     constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(COUT >> 3) << 17) |
                                ((uint32_t)(128 >> 4) << 24);
     const uint32_t xhi_s = smem_u32(xhi), xlo_s = smem_u32(xlo);
-    const uint32_t whi_s = smem_u32(whi), wlo_s = smem_u32(wlo);
-    const uint32_t mbar_s = smem_u32(mbar);
+    const uint32_t wbuf_s = smem_u32(wbuf);
 
-    uint32_t parity = 0;
+    // Pipeline over weight chunks, 3-deep ring: the MMAs of chunk c run while chunks c+1 and c+2
+    // are copied; buffer (c+2)%3 is free once the MMAs of chunk c-1 (committed to
+    // mbar[(c-1)%3]) have completed.
+    constexpr int NCHUNK = NTAPS * NCH;
+    static_assert(NCHUNK >= 3, "pipeline prologue assumes at least three chunks");
+    uint32_t phase_bits = 0u;                               // bit i: parity to wait for on mbar[i]
 #pragma unroll 1
-    for (int tap = 0; tap < NTAPS; ++tap) {
-        // ---- this tap's weights (hi | lo), already in UMMA order -----------------------------
-        const float4 *src = a.packed + (int64_t)tap * 2 * kWF4;
-        for (int i = tid; i < 2 * kWF4; i += kThreads) whi[i] = __ldg(src + i);   // whi|wlo contiguous
+    for (int c = 0; c < NCHUNK; ++c) {
+        if (c + 1 < NCHUNK) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
-
+        __syncthreads();                                    // chunk c weights (and X) visible
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int tap = c / NCH, part = c - tap * NCH;
             const bool gate_tap = GATE && tap == 9;
             const int dy = gate_tap ? 1 : tap / 3, dx = gate_tap ? 1 : tap - (tap / 3) * 3;
             const uint32_t shift = (uint32_t)(dy * kHW + dx) * 16u;      // bytes
+            const uint32_t whi_s = wbuf_s + (uint32_t)(c % kStages) * kCF4 * 16u;
+            const uint32_t wlo_s = whi_s + (uint32_t)(2 * KSC * COUT) * 16u;
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
                 const uint32_t dcol = tmem_base + (uint32_t)((gate_tap ? 2 * COUT : 0) + mt * COUT);
                 const uint32_t arow = shift + (uint32_t)mt * 128u * 16u;
 #pragma unroll
-                for (int ks = 0; ks < KS; ++ks) {
+                for (int kl = 0; kl < KSC; ++kl) {
+                    const int ks = part * KSC + kl;
                     const uint32_t aoff = (uint32_t)(2 * ks) * kNPos * 16u + arow;
-                    const uint32_t boff = (uint32_t)(2 * ks) * COUT * 16u;
+                    const uint32_t boff = (uint32_t)(2 * kl) * COUT * 16u;
                     const uint64_t a_hi = make_desc(xhi_s + aoff, kNPos * 16u, 128u);
                     const uint64_t a_lo = make_desc(xlo_s + aoff, kNPos * 16u, 128u);
                     const uint64_t b_hi = make_desc(whi_s + boff, COUT * 16u, 128u);
@@ -222,12 +263,25 @@ conv3x3_tc5_kernel(const Args a)
                 }
             }
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                             mbar_s)
+                             smem_u32(mbar + (c % kStages)))
                          : "memory");
         }
-        // the weight buffer is reused by the next tap: wait until this tap's MMAs have read it
-        mbar_wait(mbar_s, parity);
-        parity ^= 1u;
+        if (c + 2 < NCHUNK) {
+            if (c >= 1) {                                   // buffer (c+2)%3 was read by chunk c-1
+                const int i = (c - 1) % kStages;
+                mbar_wait(smem_u32(mbar + i), (phase_bits >> i) & 1u);
+                phase_bits ^= 1u << i;
+            }
+            issue_chunk(c + 2);
+        }
+    }
+    // drain: chunks whose completion has not been observed yet are NCHUNK-3 .. NCHUNK-1
+    // (in-loop waits covered chunks 0 .. NCHUNK-4)
+#pragma unroll 1
+    for (int c = NCHUNK - 3; c < NCHUNK; ++c) {
+        const int i = c % kStages;
+        mbar_wait(smem_u32(mbar + i), (phase_bits >> i) & 1u);
+        phase_bits ^= 1u << i;
     }
 
     // ---- epilogue: TMEM -> registers -> NCHW -----------------------------------------------
@@ -307,7 +361,7 @@ prepack_tc5_kernel(const float *__restrict__ w3, const float *__restrict__ w1,
 template <int CIN, int COUT, bool GATE>
 int launch(const Args &a, int64_t B, cudaStream_t s)
 {
-    constexpr size_t smem = sizeof(float4) * (2 * (CIN / 4) * kNPos + 2 * (CIN / 4) * COUT) + 64;
+    constexpr size_t smem = sizeof(float4) * (2 * (CIN / 4) * kNPos + kStages * (2 * (CIN / 4) * COUT / (CIN >= 64 ? 2 : 1))) + 64;
     WM_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc5_kernel<CIN, COUT, GATE>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((a.w + kTW - 1) / kTW, (a.h + kR - 1) / kR, (unsigned)B);
