@@ -159,6 +159,9 @@ size_t wm_conv3x3_packed_bytes(int64_t Cin, int64_t Cout, int with_gate);
  * accumulators.  Process-wide switch; returns WM_EINVAL for other values. */
 int wm_conv3x3_set_impl(int impl);
 int wm_conv3x3_get_impl(void);
+/* Developer aid: non-NULL device buffer of 6*SMs int64 -> the tcgen05 kernel writes per-CTA phase
+ * cycle counts (wait-X, lo-split, MMA loop, drain, next-stage issue, epilogue); NULL disables. */
+int wm_conv3x3_debug_timing(void *device_buffer);
 int wm_conv3x3_prepack(const float *w3x3, const float *w1x1, void *packed, int64_t Cin, int64_t Cout,
                        wm_stream_t stream);
 int wm_conv3x3_fwd(const float *in_a, int64_t a_bstride, int64_t Ca, const float *in_b,

@@ -19,7 +19,7 @@ ap.add_argument("--tf32", type=int, default=0)
 ap.add_argument("--height", type=int, default=2160)
 ap.add_argument("--width", type=int, default=3840)
 ap.add_argument("--rows", type=int, default=45)
-ap.add_argument("--conv-impl", default="mma", choices=["mma", "tcgen05"])
+ap.add_argument("--conv-impl", default="tcgen05", choices=["mma", "tcgen05"])
 args = ap.parse_args()
 
 torch.backends.cudnn.benchmark = True

@@ -275,6 +275,7 @@ int launch(const Args &a, int64_t B, cudaStream_t s)
 namespace wm {
 namespace tc5 {   // conv3x3_tc5.cu
 size_t packed_bytes(int64_t Cin, int64_t Cout, int with_gate);
+void set_debug(long long *p);
 int prepack(const float *w3x3, const float *w1x1, void *packed, int64_t Cin, int64_t Cout,
             cudaStream_t s);
 int forward(const float *in_a, int64_t a_bstride, int64_t Ca, const float *in_b, int64_t b_bstride,
@@ -282,7 +283,7 @@ int forward(const float *in_a, int64_t a_bstride, int64_t Ca, const float *in_b,
             float *out, int64_t B, int64_t Cin, int64_t Cout, int64_t h, int64_t w, cudaStream_t s);
 }  // namespace tc5
 namespace conv {
-static int g_impl = 0;   // 0: mma.sync m16n8k8 (legacy tensor path), 1: tcgen05 + TMEM
+static int g_impl = 1;   // 0: mma.sync m16n8k8 (legacy tensor path), 1: tcgen05 + TMEM (default)
 inline size_t mma_part_bytes(int64_t Cin, int64_t Cout, int with_gate)
 {
     const size_t n = (size_t)(with_gate ? 10 : 9) * (Cin / 8) * (Cout / 8) * 32 * sizeof(float4);
@@ -302,6 +303,14 @@ extern "C" int wm_conv3x3_set_impl(int impl)
 }
 
 extern "C" int wm_conv3x3_get_impl(void) { return wm::conv::g_impl; }
+
+/* Developer aid (not part of the reference-facing surface): when `device_buffer` is non-NULL the
+ * tcgen05 kernel adds per-CTA phase cycle counts into it (6 int64 per CTA, 148 CTAs max). */
+extern "C" int wm_conv3x3_debug_timing(void *device_buffer)
+{
+    wm::tc5::set_debug(static_cast<long long *>(device_buffer));
+    return WM_OK;
+}
 
 extern "C" size_t wm_conv3x3_packed_bytes(int64_t Cin, int64_t Cout, int with_gate)
 {

@@ -15,8 +15,11 @@
 // activation and only lo = a - trunc(a) needs a second copy; weights are split (rna) at prepack.
 //   acc += a_lo*b_hi ; acc += a_hi*b_lo ; acc += a_hi*b_hi     (fp32 accumulate in TMEM)
 //
-// One CTA per SM (201 KB of shared memory), 256 threads: all stage, one thread issues the MMAs
-// (tcgen05.commit -> mbarrier), warps 0-3 drain TMEM with tcgen05.ld.32x32b and run the epilogue.
+// Persistent: one CTA per SM (217 KB of shared memory, TMEM allocated once) loops over tiles.
+// Per tile: finish the cp.async halo staging -> MMA pipeline over a 3-deep cp.async weight ring
+// (one thread issues tcgen05.mma, tcgen05.commit -> mbarrier frees ring slots) -> start the NEXT
+// tile's halo loads -> all 8 warps drain TMEM with tcgen05.ld.32x32b and run the epilogue while
+// those loads are in flight.
 #include "common.cuh"
 
 namespace wm {
@@ -25,12 +28,19 @@ namespace tc5 {
 constexpr int kR = 7, kTW = 32;             // tile: 7 rows x 32 columns
 constexpr int kHW = kTW + 2;                // halo row length 34
 constexpr int kHaloPos = (kR + 2) * kHW;    // 306 real halo positions
-constexpr int kNPos = 328;                  // + zero tail read by the dropped M rows (max 325)
+constexpr int kNPos = kHaloPos;             // rows m > 235 of the M window are dropped: their reads
+                                            // may run past a K-chunk block into the next one (still
+                                            // inside this CTA's shared memory), harmless garbage
 constexpr int kQ0 = kHW + 1;                // halo position of output (0,0) of the tile
 constexpr int kThreads = 256;
-constexpr int kStages = 3;                  // weight-chunk ring depth
+constexpr int kStages = 4;                  // weight-chunk ring depth (prefetch distance 3)
+
+// optional per-CTA phase timing (cycles), enabled with wm_conv3x3_debug_timing(ptr != NULL):
+// [0] wait for staged X  [1] xlo  [2] chunk loop  [3] drain  [4] issue next stage  [5] epilogue
+static long long *g_dbg = nullptr;
 
 struct Args {
+    long long *dbg;
     const float *in_a;
     int64_t a_bstride;
     int Ca;
@@ -113,16 +123,18 @@ constexpr int tmem_cols()
 
 template <int CIN, int COUT, bool GATE>
 __global__ void __launch_bounds__(kThreads, 1)
-conv3x3_tc5_kernel(const Args a)
+conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
 {
     constexpr int KC = CIN / 4;                 // 16-byte K chunks
     constexpr int KS = CIN / 8;                 // MMA k-steps (K = 8 for tf32)
     constexpr int NTAPS = GATE ? 10 : 9;
     constexpr int kWF4 = KC * COUT;             // float4 per weight part (hi or lo) per tap
-    constexpr int NCH = CIN >= 64 ? 2 : 1;      // weight chunks per tap (K split so 2 buffers fit)
+    constexpr int NCH = CIN >= 64 ? 2 : 1;      // weight chunks per tap (K split so the ring fits)
     constexpr int KSC = KS / NCH;               // k-steps per chunk
     constexpr int kCF4 = 2 * kWF4 / NCH;        // float4 per chunk: [hi | lo][2*KSC kc][COUT]
     constexpr int kCols = tmem_cols<COUT, GATE>();
+    constexpr int NCHUNK = NTAPS * NCH;
+    static_assert(NCHUNK >= 4, "pipeline prologue assumes at least four chunks");
     extern __shared__ __align__(128) float smem[];
     float4 *xhi = reinterpret_cast<float4 *>(smem);          // [KC][kNPos]
     float4 *xlo = xhi + KC * kNPos;                          // [KC][kNPos]
@@ -131,8 +143,6 @@ conv3x3_tc5_kernel(const Args a)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mbar + kStages);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tx0 = blockIdx.x * kTW, ty0 = blockIdx.y * kR;
-    const int64_t b = blockIdx.z;
     const int h = a.h, w = a.w;
     const int64_t hw = (int64_t)h * w;
 
@@ -152,6 +162,49 @@ conv3x3_tc5_kernel(const Args a)
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
+    // Halo tile of `tile` -> xhi via 4-byte cp.async (zero fill outside the image): no register
+    // staging, every load of the tile in flight at once.  Warp w takes channels w, w+8, ...; lanes
+    // run along a halo row (34 floats: lanes 0,1 also take the tail).  One commit group.
+    auto issue_stage = [&](int tile) {
+        const int txi = tile % tiles_x, tyi = (tile / tiles_x) % tiles_y;
+        const int64_t b = tile / (tiles_x * tiles_y);
+        const int tx0 = txi * kTW, ty0 = tyi * kR;
+        const uint32_t xhi_base = smem_u32(xhi);
+        const int gx0 = tx0 - 1 + lane, gx1 = tx0 + 31 + lane;
+        const bool okx0 = gx0 >= 0 && gx0 < w;
+        const bool okx1 = lane < 2 && gx1 < w;
+#pragma unroll 1
+        for (int c = warp; c < CIN; c += kThreads / 32) {
+            const float *plane;
+            if (c < a.Ca) {
+                plane = a.in_a + b * a.a_bstride + (int64_t)c * hw;
+            } else {
+                const int cb = a.chan_map ? __ldg(a.chan_map + b * (CIN - a.Ca) + (c - a.Ca)) : c - a.Ca;
+                plane = a.in_b + b * a.b_bstride + (int64_t)cb * hw;
+            }
+            // element (c, pos) lives at float index ((c/4)*kNPos + pos)*4 + c%4
+            const uint32_t dst_c = xhi_base + (uint32_t)(((c >> 2) * kNPos) * 4 + (c & 3)) * 4u;
+#pragma unroll
+            for (int py = 0; py < kR + 2; ++py) {
+                const int gy = ty0 - 1 + py;
+                const bool oky = gy >= 0 && gy < h;
+                const float *row = plane + (int64_t)(oky ? gy : 0) * w;
+                const uint32_t dst = dst_c + (uint32_t)(py * kHW + lane) * 16u;
+                const bool ok0 = oky && okx0;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst),
+                             "l"(ok0 ? row + gx0 : plane), "r"(ok0 ? 4u : 0u)
+                             : "memory");
+                if (lane < 2) {
+                    const bool ok1 = oky && okx1;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + 32u * 16u),
+                                 "l"(ok1 ? row + gx1 : plane), "r"(ok1 ? 4u : 0u)
+                                 : "memory");
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
     // ---- one-time setup: TMEM allocation (warp 0), mbarrier init (one thread) ---------------
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -166,51 +219,8 @@ conv3x3_tc5_kernel(const Args a)
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar + i)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    issue_chunk(0);                              // the first two weight chunks fly during staging
-    issue_chunk(1);
-
-    // ---- stage the halo tile: X[kc][pos] = 4 consecutive channels of one position ------------
-    // warp w stages kc = w, w+8 (, ...); lanes run along positions; 4 positions x 4 channels of
-    // loads are issued before the first use.
-    for (int kc = warp; kc < KC; kc += kThreads / 32) {
-        const float *plane[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int c = kc * 4 + j;
-            if (c < a.Ca) {
-                plane[j] = a.in_a + b * a.a_bstride + (int64_t)c * hw;
-            } else {
-                const int cb = a.chan_map ? __ldg(a.chan_map + b * (CIN - a.Ca) + (c - a.Ca)) : c - a.Ca;
-                plane[j] = a.in_b + b * a.b_bstride + (int64_t)cb * hw;
-            }
-        }
-#pragma unroll 1
-        for (int p0 = 0; p0 < kNPos; p0 += 128) {
-            float v[4][4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int pos = p0 + i * 32 + lane;
-                const int py = pos / kHW, px = pos - py * kHW;
-                const int gy = ty0 - 1 + py, gx = tx0 - 1 + px;
-                const bool ok = pos < kHaloPos && gy >= 0 && gy < h && gx >= 0 && gx < w;
-                const int64_t off = (int64_t)gy * w + gx;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) v[i][j] = ok ? __ldg(plane[j] + off) : 0.0f;
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int pos = p0 + i * 32 + lane;
-                if (pos < kNPos) {
-                    float lo[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        lo[j] = v[i][j] - __uint_as_float(__float_as_uint(v[i][j]) & 0xffffe000u);
-                    xhi[kc * kNPos + pos] = make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
-                    xlo[kc * kNPos + pos] = make_float4(lo[0], lo[1], lo[2], lo[3]);
-                }
-            }
-        }
-    }
+    int tile = blockIdx.x;
+    if (tile < total_tiles) issue_stage(tile);
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -220,106 +230,158 @@ conv3x3_tc5_kernel(const Args a)
     // instruction descriptor: D=f32, A=B=tf32, both K-major, N = COUT, M = 128
     constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(COUT >> 3) << 17) |
                                ((uint32_t)(128 >> 4) << 24);
-    const uint32_t xhi_s = smem_u32(xhi), xlo_s = smem_u32(xlo);
-    const uint32_t wbuf_s = smem_u32(wbuf);
-
-    // Pipeline over weight chunks, 3-deep ring: the MMAs of chunk c run while chunks c+1 and c+2
-    // are copied; buffer (c+2)%3 is free once the MMAs of chunk c-1 (committed to
-    // mbar[(c-1)%3]) have completed.
-    constexpr int NCHUNK = NTAPS * NCH;
-    static_assert(NCHUNK >= 3, "pipeline prologue assumes at least three chunks");
+    // descriptors differ only in the 14-bit start-address field (bytes >> 4): build the bases once
+    // and add offsets per MMA (all of this CTA's shared memory is below 256 KB, no carry out)
+    const uint64_t a_hi0 = make_desc(smem_u32(xhi), kNPos * 16u, 128u);
+    const uint64_t a_lo0 = make_desc(smem_u32(xlo), kNPos * 16u, 128u);
+    const uint64_t b_00 = make_desc(smem_u32(wbuf), COUT * 16u, 128u);
     uint32_t phase_bits = 0u;                               // bit i: parity to wait for on mbar[i]
-#pragma unroll 1
-    for (int c = 0; c < NCHUNK; ++c) {
-        if (c + 1 < NCHUNK) asm volatile("cp.async.wait_group 1;" ::: "memory");
-        else asm volatile("cp.async.wait_group 0;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();                                    // chunk c weights (and X) visible
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int tap = c / NCH, part = c - tap * NCH;
-            const bool gate_tap = GATE && tap == 9;
-            const int dy = gate_tap ? 1 : tap / 3, dx = gate_tap ? 1 : tap - (tap / 3) * 3;
-            const uint32_t shift = (uint32_t)(dy * kHW + dx) * 16u;      // bytes
-            const uint32_t whi_s = wbuf_s + (uint32_t)(c % kStages) * kCF4 * 16u;
-            const uint32_t wlo_s = whi_s + (uint32_t)(2 * KSC * COUT) * 16u;
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
-                const uint32_t dcol = tmem_base + (uint32_t)((gate_tap ? 2 * COUT : 0) + mt * COUT);
-                const uint32_t arow = shift + (uint32_t)mt * 128u * 16u;
-#pragma unroll
-                for (int kl = 0; kl < KSC; ++kl) {
-                    const int ks = part * KSC + kl;
-                    const uint32_t aoff = (uint32_t)(2 * ks) * kNPos * 16u + arow;
-                    const uint32_t boff = (uint32_t)(2 * kl) * COUT * 16u;
-                    const uint64_t a_hi = make_desc(xhi_s + aoff, kNPos * 16u, 128u);
-                    const uint64_t a_lo = make_desc(xlo_s + aoff, kNPos * 16u, 128u);
-                    const uint64_t b_hi = make_desc(whi_s + boff, COUT * 16u, 128u);
-                    const uint64_t b_lo = make_desc(wlo_s + boff, COUT * 16u, 128u);
-                    const uint32_t first = (ks == 0 && (tap == 0 || gate_tap)) ? 0u : 1u;
-                    mma_tf32_ss(dcol, a_lo, b_hi, idesc, first);
-                    mma_tf32_ss(dcol, a_hi, b_lo, idesc, 1u);
-                    mma_tf32_ss(dcol, a_hi, b_hi, idesc, 1u);
-                }
-            }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                             smem_u32(mbar + (c % kStages)))
-                         : "memory");
-        }
-        if (c + 2 < NCHUNK) {
-            if (c >= 1) {                                   // buffer (c+2)%3 was read by chunk c-1
-                const int i = (c - 1) % kStages;
-                mbar_wait(smem_u32(mbar + i), (phase_bits >> i) & 1u);
-                phase_bits ^= 1u << i;
-            }
-            issue_chunk(c + 2);
-        }
-    }
-    // drain: chunks whose completion has not been observed yet are NCHUNK-3 .. NCHUNK-1
-    // (in-loop waits covered chunks 0 .. NCHUNK-4)
-#pragma unroll 1
-    for (int c = NCHUNK - 3; c < NCHUNK; ++c) {
-        const int i = c % kStages;
-        mbar_wait(smem_u32(mbar + i), (phase_bits >> i) & 1u);
-        phase_bits ^= 1u << i;
-    }
+    long long tacc[6] = {0, 0, 0, 0, 0, 0}, tprev = clock64();
+#define WM_TICK(k) do { if (a.dbg) { const long long _t = clock64(); tacc[k] += _t - tprev; tprev = _t; } } while (0)
 
-    // ---- epilogue: TMEM -> registers -> NCHW -----------------------------------------------
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (warp < 4) {
+    // Persistent loop over this CTA's tiles.  Per tile: [finish staging X] -> [MMA pipeline over
+    // weight chunks] -> [start staging the NEXT tile's X, asynchronously] -> [epilogue from TMEM].
 #pragma unroll 1
-        for (int mt = 0; mt < 2; ++mt) {
-            const int m = mt * 128 + warp * 32 + lane;
-            const int q = kQ0 + m;
-            const int py = q / kHW, px = q - py * kHW;
-            const int gy = ty0 + py - 1, gx = tx0 + px - 1;
-            const bool ok = px >= 1 && px <= kTW && py <= kR && gy < h && gx < w;
-            const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (; tile < total_tiles; tile += gridDim.x) {
+        const int txi = tile % tiles_x, tyi = (tile / tiles_x) % tiles_y;
+        const int64_t b = tile / (tiles_x * tiles_y);
+        const int tx0 = txi * kTW, ty0 = tyi * kR;
+
+        issue_chunk(0);                          // first three weight chunks of this tile
+        issue_chunk(1);
+        issue_chunk(2);
+        if (a.dbg) tprev = clock64();
+        asm volatile("cp.async.wait_group 3;" ::: "memory");   // X(tile) landed (older than all three)
+        __syncthreads();
+        WM_TICK(0);
+        for (int i = tid; i < KC * kNPos; i += kThreads) {      // xlo = a - trunc_tf32(a)
+            const float4 v = xhi[i];
+            float4 lo;
+            lo.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+            lo.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+            lo.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+            lo.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+            xlo[i] = lo;
+        }
+        WM_TICK(1);
+
+        // 4-deep weight ring: the MMAs of chunk c run while chunks c+1..c+3 are copied; slot
+        // (c+3)%4 is free once the MMAs of chunk c-1 (committed to mbar[(c-1)%4]) completed.
 #pragma unroll 1
-            for (int c0 = 0; c0 < COUT; c0 += 32) {
-                uint32_t acc[32];
-                tmem_ld32(lane_addr + (uint32_t)(mt * COUT + c0), acc);
-                if (GATE) {
-                    uint32_t gt[32];
-                    tmem_ld32(lane_addr + (uint32_t)(2 * COUT + mt * COUT + c0), gt);
+        for (int c = 0; c < NCHUNK; ++c) {
+            // groups issued so far: chunks 0 .. min(c+2, NCHUNK-1); chunk c must have landed
+            if (c + 2 < NCHUNK) asm volatile("cp.async.wait_group 2;" ::: "memory");
+            else if (c + 1 < NCHUNK) asm volatile("cp.async.wait_group 1;" ::: "memory");
+            else asm volatile("cp.async.wait_group 0;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();                                // chunk c weights (and X) visible
+            if (tid == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const int tap = c / NCH, part = c - tap * NCH;
+                const bool gate_tap = GATE && tap == 9;
+                const int dy = gate_tap ? 1 : tap / 3, dx = gate_tap ? 1 : tap - (tap / 3) * 3;
+                // offsets in 16-byte units (= float4 = one (kc, position) or (kc, co) element)
+                const uint32_t shift = (uint32_t)(dy * kHW + dx);
+                const uint64_t b_hi0 = b_00 + (uint32_t)(c % kStages) * kCF4;
+                const uint64_t b_lo0 = b_hi0 + (uint32_t)(2 * KSC * COUT);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float z = __uint_as_float(gt[j]) + __ldg(a.gate_bias + c0 + j);
-                        acc[j] = __float_as_uint(__uint_as_float(acc[j]) * (1.0f / (1.0f + expf(-z))));
+                for (int mt = 0; mt < 2; ++mt) {
+                    const uint32_t dcol = tmem_base + (uint32_t)((gate_tap ? 2 * COUT : 0) + mt * COUT);
+                    const uint32_t arow = shift + (uint32_t)mt * 128u;
+#pragma unroll
+                    for (int kl = 0; kl < KSC; ++kl) {
+                        const int ks = part * KSC + kl;
+                        const uint32_t aoff = (uint32_t)(2 * ks) * kNPos + arow;
+                        const uint32_t boff = (uint32_t)(2 * kl) * COUT;
+                        const uint64_t a_hi = a_hi0 + aoff, a_lo = a_lo0 + aoff;
+                        const uint64_t b_hi = b_hi0 + boff, b_lo = b_lo0 + boff;
+                        const uint32_t first = (ks == 0 && (tap == 0 || gate_tap)) ? 0u : 1u;
+                        mma_tf32_ss(dcol, a_lo, b_hi, idesc, first);
+                        mma_tf32_ss(dcol, a_hi, b_lo, idesc, 1u);
+                        mma_tf32_ss(dcol, a_hi, b_hi, idesc, 1u);
                     }
                 }
-                if (ok) {
-                    float *o = a.out + (b * COUT + c0) * hw + (int64_t)gy * w + gx;
+                asm volatile(
+                    "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                        smem_u32(mbar + (c % kStages)))
+                    : "memory");
+            }
+            if (c + 3 < NCHUNK) {
+                if (c >= 1) {                               // slot (c+3)%4 was read by chunk c-1
+                    const int i = (c - 1) % kStages;
+                    mbar_wait(smem_u32(mbar + i), (phase_bits >> i) & 1u);
+                    phase_bits ^= 1u << i;
+                }
+                issue_chunk(c + 3);
+            }
+        }
+        WM_TICK(2);
+        // drain: chunks NCHUNK-4 .. NCHUNK-1 (in-loop waits covered 0 .. NCHUNK-5)
+#pragma unroll 1
+        for (int c = NCHUNK - 4; c < NCHUNK; ++c) {
+            const int i = c % kStages;
+            mbar_wait(smem_u32(mbar + i), (phase_bits >> i) & 1u);
+            phase_bits ^= 1u << i;
+        }
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        WM_TICK(3);
+
+        // every MMA of this tile has completed: X is free -> start fetching the next tile's halo
+        // now; the loads fly while the accumulators are drained below
+        if (tile + (int)gridDim.x < total_tiles) issue_stage(tile + gridDim.x);
+        WM_TICK(4);
+
+        // ---- epilogue: TMEM -> registers -> NCHW -------------------------------------------
+        {
+            // warp w drains TMEM lane quarter w % 4; warps w and w+4 split the 32-channel groups
+            const int quarter = warp & 3, whalf = warp >> 2;
+            constexpr int NG = COUT / 32;                   // 32-channel groups per accumulator
+#pragma unroll 1
+            for (int mt = 0; mt < 2; ++mt) {
+                const int m = mt * 128 + quarter * 32 + lane;
+                const int q = kQ0 + m;
+                const int py = q / kHW, px = q - py * kHW;
+                const int gy = ty0 + py - 1, gx = tx0 + px - 1;
+                const bool ok = px >= 1 && px <= kTW && py <= kR && gy < h && gx < w;
+                const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+                for (int g = whalf; g < NG; g += 2) {
+                    const int c0 = g * 32;
+                    uint32_t acc[32];
+                    tmem_ld32(lane_addr + (uint32_t)(mt * COUT + c0), acc);
+                    if (GATE) {
+                        uint32_t gt[32];
+                        tmem_ld32(lane_addr + (uint32_t)(2 * COUT + mt * COUT + c0), gt);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float v = __uint_as_float(acc[j]);
-                        if (!GATE && a.bias) v += __ldg(a.bias + c0 + j);
-                        o[(int64_t)j * hw] = v;
+                        for (int j = 0; j < 32; ++j) {
+                            const float z = __uint_as_float(gt[j]) + __ldg(a.gate_bias + c0 + j);
+                            acc[j] = __float_as_uint(__fdividef(__uint_as_float(acc[j]), 1.0f + __expf(-z)));
+                        }
+                    }
+                    if (ok) {
+                        float *o = a.out + (b * COUT + c0) * hw + (int64_t)gy * w + gx;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            float v = __uint_as_float(acc[j]);
+                            if (!GATE && a.bias) v += __ldg(a.bias + c0 + j);
+                            o[(int64_t)j * hw] = v;
+                        }
                     }
                 }
             }
         }
+        // the next tile's first MMA (issued after the chunk-0 barrier) overwrites the accumulators:
+        // order this warp's TMEM reads before that barrier
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        WM_TICK(5);
     }
+    if (a.dbg && tid == 0) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) a.dbg[blockIdx.x * 6 + k] = tacc[k];
+    }
+#undef WM_TICK
+
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) {
@@ -364,11 +426,16 @@ int launch(const Args &a, int64_t B, cudaStream_t s)
     constexpr size_t smem = sizeof(float4) * (2 * (CIN / 4) * kNPos + kStages * (2 * (CIN / 4) * COUT / (CIN >= 64 ? 2 : 1))) + 64;
     WM_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc5_kernel<CIN, COUT, GATE>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((a.w + kTW - 1) / kTW, (a.h + kR - 1) / kR, (unsigned)B);
-    conv3x3_tc5_kernel<CIN, COUT, GATE><<<grid, kThreads, smem, s>>>(a);
+    const int tiles_x = (a.w + kTW - 1) / kTW, tiles_y = (a.h + kR - 1) / kR;
+    const int64_t total = (int64_t)tiles_x * tiles_y * B;
+    WM_REQUIRE(total < (int64_t)1 << 31, "wm_conv3x3_fwd: too many tiles");
+    const int grid = (int)(total < sm_count() ? total : sm_count());   // persistent: one CTA per SM
+    conv3x3_tc5_kernel<CIN, COUT, GATE><<<grid, kThreads, smem, s>>>(a, tiles_x, tiles_y, (int)total);
     WM_LAUNCH_OK("conv3x3 tcgen05");
     return WM_OK;
 }
+
+void set_debug(long long *p) { g_dbg = p; }
 
 size_t packed_bytes(int64_t Cin, int64_t Cout, int with_gate)
 {
@@ -392,6 +459,7 @@ int forward(const float *in_a, int64_t a_bstride, int64_t Ca, const float *in_b,
 {
     WM_REQUIRE((h + kR - 1) / kR <= 65535, "wm_conv3x3_fwd: image too tall");
     Args a;
+    a.dbg = g_dbg;
     a.in_a = in_a; a.a_bstride = a_bstride; a.Ca = (int)Ca; a.in_b = in_b; a.b_bstride = b_bstride;
     a.chan_map = chan_map; a.packed = static_cast<const float4 *>(packed); a.bias = bias;
     a.gate_bias = gate_bias; a.out = out; a.h = (int)h; a.w = (int)w;
