@@ -82,7 +82,9 @@ def measured_hbm_peak():
 # ----------------------------------------------------------------------------------------------
 def cpu_forward_sample(params, h, w, reps=1, seed=1234):
     from oracle import model as om
+    from oracle import scan as oscan
     torch.set_num_threads(os.cpu_count() or 1)
+    oscan.set_threads(os.cpu_count() or 1)        # torchrun exports OMP_NUM_THREADS=1
     x, _ = om.synth_lowlight(1, h, w, seed)
     best = float("inf")
     for _ in range(reps):
@@ -134,7 +136,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -263,8 +265,26 @@ class OpTimer:
         return rows
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The one JSON line goes to the real stdout; everything else (NCCL banners, warnings) was
+    redirected to stderr at start-up."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    # Keep stdout clean for the driver: libraries (e.g. NCCL's version banner) print to fd 1.
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
         return
@@ -402,7 +422,7 @@ def main():
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(params, H, W)
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 

@@ -45,6 +45,14 @@ def _load():
     return _lib
 
 
+def set_threads(n: int) -> int:
+    """Set the OpenMP thread count of the C scan (torchrun exports OMP_NUM_THREADS=1)."""
+    lib = _load()
+    lib.wm_oracle_set_threads.restype = ctypes.c_int
+    lib.wm_oracle_set_threads.argtypes = [ctypes.c_int]
+    return int(lib.wm_oracle_set_threads(int(n)))
+
+
 def selective_scan_loop(u, delta, A, Bm, Cm, D=None, delta_bias=None):
     """Sequential recurrence in the dtype of ``u`` (fp32 or fp64).
 

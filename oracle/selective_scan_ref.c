@@ -30,7 +30,23 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
 #define MAX_STATE 64
+
+/* torchrun exports OMP_NUM_THREADS=1; the CPU baseline sets its thread count explicitly. */
+int wm_oracle_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
 
 static inline float softplus_f(float x) { return x > 20.0f ? x : log1pf(expf(x)); }
 static inline double softplus_d(double x) { return x > 20.0 ? x : log1p(exp(x)); }
