@@ -15,13 +15,36 @@ namespace pw {
 constexpr int kTH = 8, kTW = 32;               // interior tile
 constexpr int kHH = kTH + 2, kHW = kTW + 2;    // halo tile 10 x 34
 constexpr int kHalo = kHH * kHW;               // 340 positions
-constexpr int kXP = 344;                       // padded position stride
+constexpr int kXP = 360;                       // padded position stride (== 8 mod 32: conflict-free
+                                               // mma A-fragment loads from xs[channel][position])
 constexpr int kPix = kTH * kTW;                // 256 interior pixels
 constexpr int kThreads = 256;
 
 __device__ __forceinline__ float gelu_erf(float v)
 {
     return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));  // torch exact GELU
+}
+
+// ---- tensor-core helpers for the 1x1 phase (3xTF32, fp32-accurate; see conv3x3.cu) ----------
+__device__ __forceinline__ uint32_t to_tf32(float v)
+{
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ void split_tf32(float a, uint32_t &hi, uint32_t &lo)
+{
+    hi = __float_as_uint(a) & 0xffffe000u;
+    lo = __float_as_uint(a - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0,
+                                         uint32_t b1)
+{
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
+        "{%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
 // LayerNorm2d over `C` channels for one position held in smem column `pos` (stride kXP).
@@ -64,32 +87,32 @@ __device__ __forceinline__ void load_halo32(const float *__restrict__ x, float *
 // y = dw3x3( pw1x1( ln?(x) ) ),  Cin = 32, Cout = 32*G
 // ---------------------------------------------------------------------------------------------
 template <int COUT>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 pw_dw_kernel(const float *__restrict__ x, const float *__restrict__ ln_w,
              const float *__restrict__ ln_b, float eps, const float *__restrict__ pw_w,
              const float *__restrict__ pw_b, const float *__restrict__ dw_w,
              const float *__restrict__ dw_b, int act, float *__restrict__ y, int h, int w)
 {
+    // 1x1 on the tensor cores: per 32-output group, D[pos][co] = X[pos][ci] W[co][ci] as
+    // 22 m-tiles (340 halo positions) x 4 n-tiles x 4 k-steps of mma.sync m16n8k8 TF32 with the
+    // 3xTF32 split (fp32-accurate).  The depthwise 3x3 then runs on the FMA pipe from shared memory.
     constexpr int CIN = 32;
+    constexpr int kMT = (kHalo + 15) / 16;      // 22 m-tiles
     extern __shared__ __align__(16) float smem[];
     float *xs = smem;                       // [32][kXP]
     float *ps = xs + CIN * kXP;             // [32][kXP]  one output group after the 1x1
-    float *wt = ps + 32 * kXP;              // [32][COUT] transposed 1x1 weights
-    float *pb = wt + CIN * COUT;            // [COUT]
+    float4 *wf = reinterpret_cast<float4 *>(ps + 32 * kXP);   // [4 ks][4 nt][32 lanes] B fragments hi|lo
+    float *pb = reinterpret_cast<float *>(wf + 4 * 4 * 32);   // [COUT]
     float *dww = pb + COUT;                 // [COUT][9]
     float *dwb = dww + COUT * 9;            // [COUT]
     float *lnw = dwb + COUT;                // [32]
     float *lnb = lnw + CIN;                 // [32]
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx0 = blockIdx.x * kTW, ty0 = blockIdx.y * kTH;
     const int64_t b = blockIdx.z;
     const int64_t hw = (int64_t)h * w;
 
-    for (int i = tid; i < CIN * COUT; i += kThreads) {
-        const int co = i / CIN, ci = i - co * CIN;
-        wt[ci * COUT + co] = __ldg(pw_w + i);
-    }
     for (int i = tid; i < COUT; i += kThreads) {
         pb[i] = pw_b ? __ldg(pw_b + i) : 0.0f;
         dwb[i] = __ldg(dw_b + i);
@@ -97,6 +120,10 @@ pw_dw_kernel(const float *__restrict__ x, const float *__restrict__ ln_w,
     for (int i = tid; i < COUT * 9; i += kThreads) dww[i] = __ldg(dw_w + i);
     if (ln_w != nullptr && tid < CIN) { lnw[tid] = __ldg(ln_w + tid); lnb[tid] = __ldg(ln_b + tid); }
     load_halo32(x, xs, b, CIN, h, w, ty0, tx0);
+    for (int i = tid; i < CIN * (kXP - kHalo); i += kThreads) {   // rows read by the last m-tile
+        const int c = i / (kXP - kHalo), r = i - c * (kXP - kHalo);
+        xs[c * kXP + kHalo + r] = 0.0f;
+    }
     __syncthreads();
 
     if (ln_w != nullptr) {
@@ -104,42 +131,66 @@ pw_dw_kernel(const float *__restrict__ x, const float *__restrict__ ln_w,
         __syncthreads();
     }
 
-    // validity of my (up to) two halo positions: the dw conv zero-pads the 1x1 OUTPUT
-    bool valid[2];
-    int mypos[2];
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        const int pos = tid + r * kThreads;
-        mypos[r] = pos < kHalo ? pos : kHalo - 1;
-        const int py = mypos[r] / kHW, px = mypos[r] - py * kHW;
-        const int gy = ty0 - 1 + py, gx = tx0 - 1 + px;
-        valid[r] = pos < kHalo && gy >= 0 && gy < h && gx >= 0 && gx < w;
-    }
-
+    const int gq = lane >> 2, t4 = lane & 3;
     for (int g = 0; g < COUT / 32; ++g) {
-        // ---- 1x1: 32 outputs of this group at my positions --------------------------------
-        const int nrounds = (tid + kThreads < kHalo) ? 2 : 1;
-        for (int r = 0; r < nrounds; ++r) {
-            float acc[32];
+        // ---- B fragments of this group's 32 x 32 weights, split into tf32 hi / lo ------------
+        for (int i = tid; i < 4 * 4 * 32; i += kThreads) {
+            const int ln_ = i & 31, nt = (i >> 5) & 3, ks = i >> 7;
+            const int co = g * 32 + nt * 8 + (ln_ >> 2), ci = ks * 8 + (ln_ & 3);
+            const float w0 = __ldg(pw_w + co * CIN + ci), w1 = __ldg(pw_w + co * CIN + ci + 4);
+            const uint32_t h0 = to_tf32(w0), h1 = to_tf32(w1);
+            wf[i] = make_float4(__uint_as_float(h0), __uint_as_float(h1),
+                                __uint_as_float(to_tf32(w0 - __uint_as_float(h0))),
+                                __uint_as_float(to_tf32(w1 - __uint_as_float(h1))));
+        }
+        __syncthreads();   // also: every warp is done with the previous group's ps
+
+        // ---- 1x1: warp w takes m-tiles w, w+8, w+16 ----------------------------------------
+#pragma unroll 1
+        for (int mt = warp; mt < kMT; mt += kThreads / 32) {
+            float acc[4][4];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc[j] = 0.0f;
-            const float *xc = xs + mypos[r];
-#pragma unroll 4
-            for (int ci = 0; ci < CIN; ++ci) {
-                const float xv = xc[ci * kXP];
-                const float4 *wr = reinterpret_cast<const float4 *>(wt + ci * COUT + g * 32);
+            for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 wv = wr[j];
-                    acc[4 * j + 0] = fmaf(xv, wv.x, acc[4 * j + 0]);
-                    acc[4 * j + 1] = fmaf(xv, wv.y, acc[4 * j + 1]);
-                    acc[4 * j + 2] = fmaf(xv, wv.z, acc[4 * j + 2]);
-                    acc[4 * j + 3] = fmaf(xv, wv.w, acc[4 * j + 3]);
+                for (int i = 0; i < 4; ++i) acc[nt][i] = 0.0f;
+            const float *abase = xs + t4 * kXP + mt * 16 + gq;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const float *ap = abase + ks * 8 * kXP;
+                const float av[4] = {ap[0], ap[8], ap[4 * kXP], ap[4 * kXP + 8]};
+                uint32_t ahi[4], alo[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) split_tf32(av[i], ahi[i], alo[i]);
+                float4 bw[4];
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) bw[nt] = wf[(ks * 4 + nt) * 32 + lane];
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt)
+                    mma_tf32(acc[nt], alo, __float_as_uint(bw[nt].x), __float_as_uint(bw[nt].y));
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt)
+                    mma_tf32(acc[nt], ahi, __float_as_uint(bw[nt].z), __float_as_uint(bw[nt].w));
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt)
+                    mma_tf32(acc[nt], ahi, __float_as_uint(bw[nt].x), __float_as_uint(bw[nt].y));
+            }
+            // fragments -> ps[co][pos]; the dw conv zero-pads the 1x1 OUTPUT (bias included)
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int pos = mt * 16 + gq + half * 8;
+                if (pos < kHalo) {
+                    const int py = pos / kHW, px = pos - py * kHW;
+                    const int gy = ty0 - 1 + py, gx = tx0 - 1 + px;
+                    const bool valid = gy >= 0 && gy < h && gx >= 0 && gx < w;
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const int cl = nt * 8 + 2 * t4 + j;
+                            ps[cl * kXP + pos] = valid ? acc[nt][half * 2 + j] + pb[g * 32 + cl] : 0.0f;
+                        }
                 }
             }
-            float *pc = ps + mypos[r];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) pc[j * kXP] = valid[r] ? acc[j] + pb[g * 32 + j] : 0.0f;
         }
         __syncthreads();
 
@@ -173,7 +224,7 @@ pw_dw_kernel(const float *__restrict__ x, const float *__restrict__ ln_w,
                 for (int dx = 0; dx < 3; ++dx) { r0[dx] = r1[dx]; r1[dx] = r2[dx]; }
             }
         }
-        __syncthreads();
+        // (the barrier at the top of the next group protects ps and wf)
     }
 }
 
@@ -288,7 +339,7 @@ static int launch_pw_dw(const float *x, const float *ln_w, const float *ln_b, fl
                         const float *dw_b, int act, float *y, int64_t B, int64_t h, int64_t w,
                         cudaStream_t s)
 {
-    const size_t smem = sizeof(float) * (32 * kXP * 2 + 32 * COUT + COUT + COUT * 9 + COUT + 64);
+    const size_t smem = sizeof(float) * (32 * kXP * 2 + 4 * 4 * 32 * 4 + COUT + COUT * 9 + COUT + 64);
     WM_CUDA_OK(opt_in_smem(pw_dw_kernel<COUT>, smem));
     dim3 grid((unsigned)((w + kTW - 1) / kTW), (unsigned)((h + kTH - 1) / kTH), (unsigned)B);
     pw_dw_kernel<COUT><<<grid, kThreads, smem, s>>>(x, ln_w, ln_b, eps, pw_w, pw_b, dw_w, dw_b, act,
