@@ -27,7 +27,8 @@ __device__ __forceinline__ float gelu_erf(float v)
 {
     return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
 }
-__device__ __forceinline__ float silu(float v) { return v / (1.0f + expf(-v)); }
+// SiLU / sigmoid with the MUFU-based fast exp and divide (relative error ~2e-7 on O(1) values)
+__device__ __forceinline__ float silu(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
 struct Args {
     const float *x;          // (B, CIN or 2*CIN, hw)
@@ -119,9 +120,99 @@ pixel_kernel(const Args a)
             for (int j = 0; j < 8; ++j) {
                 float v = acc[j];
                 if (POST == kPostSilu) v = silu(v);
-                if (POST == kPostSigmoidMul) v = a.mul_out[o + j * hw] * (1.0f / (1.0f + expf(-v)));
+                if (POST == kPostSigmoidMul) v = __fdividef(a.mul_out[o + j * hw], 1.0f + __expf(-v));
                 if (a.res) v = fmaf(a.res[o + j * hw], rs[g * 8 + j], v);
                 a.y[o + j * hw] = v;
+            }
+        }
+    }
+}
+
+// SS2D tail (wm_lfss_out_fwd) with TWO threads per pixel: each lane of a pair owns 32 of the 64
+// scan channels (sum of the four direction planes, LayerNorm statistics exchanged with one
+// shuffle, * silu(z)), accumulates its half of the 64->32 out_proj for all 32 outputs, and the
+// pair is reduced with shuffles.  Half the registers per thread of the one-thread form (no
+// spills, 2x the resident warps) -- this kernel is bound by global-load latency.
+__global__ void __launch_bounds__(kThreads, 3)
+lfss_out_pair_kernel(const Args a)
+{
+    constexpr int CIN = 64, HALF = 32, COUT = 32;
+    __shared__ __align__(16) float wt[CIN * COUT];  // [ci][co]
+    __shared__ float rs[COUT], lw[CIN], lb[CIN];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < CIN * COUT; i += kThreads) {
+        const int co = i / CIN, ci = i - co * CIN;
+        wt[ci * COUT + co] = __ldg(a.w + i);
+    }
+    for (int i = tid; i < COUT; i += kThreads) rs[i] = a.res_scale ? __ldg(a.res_scale + i) : 1.0f;
+    for (int i = tid; i < CIN; i += kThreads) { lw[i] = __ldg(a.ln_w + i); lb[i] = __ldg(a.ln_b + i); }
+    __syncthreads();
+
+    const int64_t hw = a.hw;
+    const int64_t b = blockIdx.y;
+    const int side = tid & 1;                    // which 32 channels this lane owns
+    const int c0 = side * HALF;
+    const float *x0 = a.x + (b * CIN + c0) * hw;
+    const float *xa = a.xa ? a.xa + (b * CIN + c0) * hw : nullptr;
+    const float *xb = a.xb_ ? a.xb_ + (b * CIN + c0) * hw : nullptr;
+    const float *xc = a.xc ? a.xc + (b * CIN + c0) * hw : nullptr;
+    const float *mz = a.mul + (b * CIN + c0) * hw;
+    const int64_t npairs = (int64_t)gridDim.x * (kThreads / 2);
+    // the loop bound is warp-uniform (full-mask shuffles below); lanes past the end compute on a
+    // clamped pixel and skip the store
+    for (int64_t pw0 = (int64_t)blockIdx.x * (kThreads / 2) + ((tid >> 5) << 4); pw0 < hw; pw0 += npairs) {
+        const int64_t pr = pw0 + ((tid & 31) >> 1);
+        const bool live = pr < hw;
+        const int64_t p = live ? pr : hw - 1;
+        float xv[HALF];
+#pragma unroll
+        for (int i = 0; i < HALF; ++i) {
+            float v = __ldg(x0 + i * hw + p);
+            if (xa) v += __ldg(xa + i * hw + p);
+            if (xb) v += __ldg(xb + i * hw + p);
+            if (xc) v += __ldg(xc + i * hw + p);
+            xv[i] = v;
+        }
+        float mu = 0.0f;
+#pragma unroll
+        for (int i = 0; i < HALF; ++i) mu += xv[i];
+        mu += __shfl_xor_sync(0xffffffffu, mu, 1);
+        mu *= (1.0f / CIN);
+        float var = 0.0f;
+#pragma unroll
+        for (int i = 0; i < HALF; ++i) { const float dlt = xv[i] - mu; var = fmaf(dlt, dlt, var); }
+        var += __shfl_xor_sync(0xffffffffu, var, 1);
+        var *= (1.0f / CIN);
+        const float rstd = 1.0f / sqrtf(var + a.eps);
+#pragma unroll
+        for (int i = 0; i < HALF; ++i)
+            xv[i] = fmaf((xv[i] - mu) * rstd, lw[c0 + i], lb[c0 + i]) * __ldg(mz + i * hw + p);
+#pragma unroll 1
+        for (int g = 0; g < COUT / 8; ++g) {
+            float acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+#pragma unroll
+            for (int i = 0; i < HALF; ++i) {
+                const float4 w0 = *reinterpret_cast<const float4 *>(wt + (c0 + i) * COUT + g * 8);
+                const float4 w1 = *reinterpret_cast<const float4 *>(wt + (c0 + i) * COUT + g * 8 + 4);
+                acc[0] = fmaf(xv[i], w0.x, acc[0]); acc[1] = fmaf(xv[i], w0.y, acc[1]);
+                acc[2] = fmaf(xv[i], w0.z, acc[2]); acc[3] = fmaf(xv[i], w0.w, acc[3]);
+                acc[4] = fmaf(xv[i], w1.x, acc[4]); acc[5] = fmaf(xv[i], w1.y, acc[5]);
+                acc[6] = fmaf(xv[i], w1.z, acc[6]); acc[7] = fmaf(xv[i], w1.w, acc[7]);
+            }
+            // pair reduction; lane `side` then writes outputs g*8 + side*4 .. +3
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 1);
+            const int64_t o = (b * COUT + g * 8 + side * 4) * hw + p;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int co = g * 8 + side * 4 + j;
+                float v = side ? acc[4 + j] : acc[j];
+                if (live) {
+                    v = fmaf(a.res[o + j * hw], rs[co], v);
+                    a.y[o + j * hw] = v;
+                }
             }
         }
     }
@@ -256,5 +347,12 @@ extern "C" int wm_lfss_out_fwd(const float *y, const float *ya, const float *yb,
     Args a = {};
     a.x = y; a.xa = ya; a.xb_ = yb; a.xc = yc; a.ln_w = on_w; a.ln_b = on_b; a.eps = eps; a.mul = zs; a.w = w_out;
     a.res = x; a.res_scale = skip_scale; a.y = out; a.hw = h * w;
-    return launch<64, 32, kPreLNMul, kPostNone>(a, B, (cudaStream_t)stream, "lfss out");
+    {
+        const int64_t want = (a.hw + kThreads / 2 - 1) / (kThreads / 2);
+        const int64_t cap = (int64_t)sm_count() * 16;
+        dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)B);
+        lfss_out_pair_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);
+        WM_LAUNCH_OK("lfss out");
+    }
+    return WM_OK;
 }

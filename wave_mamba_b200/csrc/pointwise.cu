@@ -218,7 +218,7 @@ pw_dw_kernel(const float *__restrict__ x, const float *__restrict__ ln_w,
                 o = fmaf(k[0], r0[0], o); o = fmaf(k[1], r0[1], o); o = fmaf(k[2], r0[2], o);
                 o = fmaf(k[3], r1[0], o); o = fmaf(k[4], r1[1], o); o = fmaf(k[5], r1[2], o);
                 o = fmaf(k[6], r2[0], o); o = fmaf(k[7], r2[1], o); o = fmaf(k[8], r2[2], o);
-                if (act == 1) o = o / (1.0f + expf(-o));  // SiLU (SS2D.act, reference :487)
+                if (act == 1) o = __fdividef(o, 1.0f + __expf(-o));  // SiLU (SS2D.act, reference :487)
                 if (gx < w && ty0 + row < h) yo[(int64_t)row * w] = o;
 #pragma unroll
                 for (int dx = 0; dx < 3; ++dx) { r0[dx] = r1[dx]; r1[dx] = r2[dx]; }
