@@ -205,6 +205,7 @@ class OpTimer:
         self.records = []   # (name, bytes, start_event, end_event)
         self.enabled = False
         self._orig = {}
+        self.conv_flops = 0.0
 
     @staticmethod
     def _numel_bytes(*tensors):
@@ -229,6 +230,14 @@ class OpTimer:
             setattr(ops, name, inner)
 
         nb = self._numel_bytes
+        timer = self
+
+        def conv_bytes(a, k, o):
+            w3 = a[1]
+            cout, cin = w3.shape[0], w3.shape[1]
+            px = o.shape[0] * o.shape[2] * o.shape[3]
+            timer.conv_flops += 2.0 * px * cout * cin * (9 + (1 if k.get("gate_w") is not None else 0))
+            return (cin + cout) * px * 4
         # algorithmic bytes: every input activation read once, every output written once
         wrap("dwt_haar", lambda a, k, o: nb(a[0]) + nb(*o))
         wrap("iwt_haar", lambda a, k, o: nb(a[0], a[1]) + nb(o))
@@ -240,9 +249,7 @@ class OpTimer:
                                                                   a[6] if len(a) > 6 else None))
         wrap("pw", lambda a, k, o: nb(a[0]) + nb(o) + nb(k.get("residual")))
         wrap("paconv_gate", lambda a, k, o: nb(a[0]) + 2 * nb(o))
-        wrap("conv3x3", lambda a, k, o: nb(a[0]) + nb(o) + (
-            0 if k.get("x_b") is None else (a[1].shape[1] - a[0].shape[1]) * a[0].shape[0]
-            * a[0].shape[2] * a[0].shape[3] * 4))
+        wrap("conv3x3", conv_bytes)
         wrap("stem_conv3x3", lambda a, k, o: nb(a[0]) + nb(o))
         wrap("head_conv3x3", lambda a, k, o: nb(a[0]) + nb(o) + nb(k.get("residual")))
         wrap("gram32", lambda a, k, o: 2 * 32 * a[0].shape[0] * a[0].shape[2] * a[0].shape[3] * 4)
@@ -259,9 +266,13 @@ class OpTimer:
         rows = []
         for name, d in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
             gbs = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else 0.0
-            rows.append({"kernel": name, "calls": d["calls"], "ms_total": round(d["ms"], 4),
-                         "algorithmic_gb": round(d["bytes"] / 1e9, 4), "achieved_gbs": round(gbs, 1),
-                         "frac_of_hbm_peak": round(gbs / peak_gbs, 4)})
+            row = {"kernel": name, "calls": d["calls"], "ms_total": round(d["ms"], 4),
+                   "algorithmic_gb": round(d["bytes"] / 1e9, 4), "achieved_gbs": round(gbs, 1),
+                   "frac_of_hbm_peak": round(gbs / peak_gbs, 4)}
+            if name == "conv3x3" and d["ms"] > 0:
+                row["bound"] = "tensor (tcgen05 kind::tf32, 3xTF32 => 3 MMAs per fp32-accurate MAC)"
+                row["achieved_tflops_fp32_equiv"] = round(self.conv_flops / (d["ms"] * 1e-3) / 1e12, 2)
+            rows.append(row)
         return rows
 
 
@@ -394,14 +405,26 @@ def main():
         roofline = {
             "kernel": "ss2d_dirs (pass 1 + carry + pass 2; the 4-way sum is fused into lfss_out)", "bound": "hbm",
             "achieved": ss["achieved_gbs"], "peak": peak_gbs, "unit": "GB/s",
-            "frac": ss["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src,
+            "frac": ss["frac_of_hbm_peak"], "traffic": None,
+            "traffic_note": "ncu (profiles/): a 4K level-1 call moves 2.25 GB (pass 1) + 4.37 GB "
+                            "(pass 2) of DRAM traffic vs 1.06 GB algorithmic: two passes x two scan "
+                            "orientations re-read x, four direction planes are written",
+            "peak_source": peak_src,
             "bytes_definition": "512*B*L per call (x read once + merged y written once), SURVEY 8d",
             "ms_per_image": round(ss["ms_total"] / args.steps, 4),
             "scan_operand_bytes_frac": round(ss["frac_of_hbm_peak"] * 7.0, 4),
             "note": "instruction-bound (one MUFU ex2 + ~4 FMA per state update, evaluated twice), "
                     "not HBM-bound: see DESIGN.md section 4",
             "state_updates_per_s": round(L_total * 4096 * args.steps / (ss["ms_total"] * 1e-3), 1),
+            # the binding resource: one MUFU ex2 per state update and per pass (two passes)
+            # + 2 per (position, channel) for softplus; MUFU peak = 16 lanes/clk/SM
+            "binding": {"resource": "MUFU (XU pipe)", "unit": "G exp/s",
+                        "achieved": round(L_total * (4096 * 2 + 256 * 2 * 2) * args.steps
+                                          / (ss["ms_total"] * 1e-3) / 1e9, 1),
+                        "peak": round(16 * 148 * ((clk or {}).get("sm_mhz") or 1965.0) * 1e6 / 1e9, 1)},
         }
+        b_ = roofline["binding"]
+        b_["frac"] = round(b_["achieved"] / b_["peak"], 4) if b_["peak"] else None
     n_img = world * args.steps
     line = {
         "metric": METRIC, "value": n_img / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world,
