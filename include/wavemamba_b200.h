@@ -66,6 +66,9 @@ int wm_iwt_haar_fwd(const float *low, int64_t low_bstride, const float *high,
  * workspace: >= wm_ss2d_core_workspace_bytes(B,h,w) bytes, 256-byte aligned.
  * Fixed model constants: d_inner 64, d_state 16, dt_rank 2, 4 directions. */
 size_t wm_ss2d_core_workspace_bytes(int64_t B, int64_t h, int64_t w);
+/* Developer aid: non-NULL device buffer of 4096*6 int64 -> every pass kernel CTA writes its phase
+ * cycle sums [wait-x, projection, delta, scan, store, tiles] at index blockIdx.x % 4096. */
+int wm_ss2d_debug_timing(void *device_buffer);
 /* Same computation without the final 4-way sum: on return the first 4*B*64*h*w floats of
  * `workspace` hold the four direction outputs as planes[k][b][d][i][j] (pixel order, k = 0..3 in
  * the reference's direction order); the consumer sums them as ((p0 + p2) + p1) + p3, which is the
