@@ -20,7 +20,14 @@ for one_cta in (0, 1):
     lib.wm_ss2d_debug_timing(None)
     d = dbg.view(4096, 6).double()
     d = d[d[:, 5] > 0]
+    col = (w + 3) // 4
+    row = (d.shape[0] - 2 * col) // 2
+    lo = 0
+    for name, n in (("k0 row fwd", row), ("k1 col fwd", col), ("k2 row bwd", row), ("k3 col bwd", col)):
+        part = d[lo:lo + n]; lo += n
+        pt = (part[:, :5].sum(0) / part[:, 5].sum()).tolist()
+        print(f"   {name}: {[int(v) for v in pt]} sum {int(sum(pt))}")
     per_tile = (d[:, :5].sum(0) / d[:, 5].sum()).tolist()
     print(f"pass 2, {h}x{w}, {2 - one_cta} CTA/SM: cycles per tile per CTA:",
-          dict(zip(["wait_x", "dt_low", "proj+delta", "scan", "store"], [int(v) for v in per_tile])),
+          dict(zip(["wait_x", "projection", "delta", "scan", "store"], [int(v) for v in per_tile])),
           "sum", int(sum(per_tile)), f"| dirs call {e0.elapsed_time(e1):.3f} ms")

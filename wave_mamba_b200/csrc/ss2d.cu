@@ -51,22 +51,21 @@ constexpr int kTP = 16;      // steps per tile
 constexpr int kPos = kSeq * kTP;  // 64 positions per tile
 constexpr int kXS = 72;      // xs row stride  [channel][position]  (== 8 mod 32: mma A loads)
 constexpr int kPJ = 36;      // pj row stride  [position][B16|C16|dt2|pad2]
-constexpr int kDS = 65;      // dd row stride  [channel][position] float2 (odd: scan reads)
+constexpr int kDD = 132;     // dd row stride  [position][channel] float2 (dt, u)  (== 4 mod 32)
 constexpr int kYS = 65;      // ys row stride  [channel][position]
-constexpr int kThreads = 512;
+constexpr int kThreads = 256;
 constexpr int kChains = kD * kN;     // 1024 (d,n) chains per direction
-constexpr int kNTiles = 4;           // mma n-tiles: B0-7, B8-15, C0-7, C8-15 (dt rows: FP32 FMAs)
+constexpr int kNTiles = 5;           // mma n-tiles: B0-7, B8-15, C0-7, C8-15, dt(2)+pad
 
 // shared memory carve-up (floats)
 constexpr int kOffXs = 0;
 constexpr int kOffPj = kOffXs + kD * kXS;               // 4608
 constexpr int kOffDd = kOffPj + kPos * kPJ;             // +2304
-constexpr int kOffYs = kOffDd + kD * kDS * 2;           // +8320
+constexpr int kOffYs = kOffDd + kPos * kDD;             // +8448
 constexpr int kOffWf = kOffYs + kD * kYS;               // +4160
 constexpr int kOffCst = kOffWf + 8 * kNTiles * 32 * 4;  // +5120
-constexpr int kOffDlw = kOffCst + 4 * kD;               // +256
-constexpr int kSmemFloats = kOffDlw + 2 * kD;           // +128
-constexpr size_t kSmemBytes = sizeof(float) * kSmemFloats;   // 95,488 B -> 2 CTAs per SM
+constexpr int kSmemFloats = kOffCst + 3 * kD;           // +192
+constexpr size_t kSmemBytes = sizeof(float) * kSmemFloats;   // 99,328 B -> 2 CTAs per SM
 
 struct Geom {
     int B, h, w;
@@ -250,13 +249,13 @@ __device__ __forceinline__ void vec_chunk(const Geom &g, const TileGeom &tg, int
     }
 }
 
-// Per-thread addressing of the two 16-byte chunks it moves per full tile (x in, y out).
+// Per-thread addressing of the four 16-byte chunks it moves per full tile (x in, y out).
 struct ChunkMap {
     int64_t goff;      // element offset inside a channel plane for tile 0 (channel d0)
     int64_t gstep;     // added per tile
     uint32_t xs_dst;   // shared address of xs[d0][p0]
     int ys_idx;        // index of ys[d0][p0]
-    int d0;            // first channel (second chunk: d0 + 32)
+    int d0;            // first channel (chunk j: d0 + 16 j)
 };
 
 __device__ __forceinline__ ChunkMap make_chunk_map(const Geom &g, const TileGeom &tg, float *xs)
@@ -290,15 +289,16 @@ __device__ __forceinline__ void load_tile(const Geom &g, const TileGeom &tg, con
 {
     if (tile_is_vec(g, tg, ti)) {
         const float *src = xb + (int64_t)cm.d0 * g.L + cm.goff + (int64_t)ti * cm.gstep;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(cm.xs_dst), "l"(src) : "memory");
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(cm.xs_dst + 32 * kXS * 4),
-                     "l"(src + 32 * g.L)
-                     : "memory");
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(cm.xs_dst + j * 16 * kXS * 4),
+                         "l"(src + (int64_t)j * 16 * g.L)
+                         : "memory");
     } else {
         // ragged tile: scalar loads, zero fill
         const int tid = threadIdx.x;
 #pragma unroll 1
-        for (int r = 0; r < 8; ++r) {
+        for (int r = 0; r < kD * kPos / kThreads; ++r) {
             const int idx = tid + r * kThreads;      // 0..4095 = (d, s, e)
             const int d = idx >> 6, s = (idx >> 4) & 3, e = idx & 15;
             const int t = ti * kTP + e;
@@ -315,13 +315,15 @@ __device__ __forceinline__ void store_tile(const Geom &g, const TileGeom &tg, co
 {
     if (tile_is_vec(g, tg, ti)) {
         float *dst = ob + (int64_t)cm.d0 * g.L + cm.goff + (int64_t)ti * cm.gstep;
-        const float *a = ys + cm.ys_idx, *b = a + 32 * kYS;
-        *reinterpret_cast<float4 *>(dst) = make_float4(a[0], a[1], a[2], a[3]);
-        *reinterpret_cast<float4 *>(dst + 32 * g.L) = make_float4(b[0], b[1], b[2], b[3]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float *a = ys + cm.ys_idx + j * 16 * kYS;
+            *reinterpret_cast<float4 *>(dst + (int64_t)j * 16 * g.L) = make_float4(a[0], a[1], a[2], a[3]);
+        }
     } else {
         const int tid = threadIdx.x;
 #pragma unroll 1
-        for (int r = 0; r < 8; ++r) {
+        for (int r = 0; r < kD * kPos / kThreads; ++r) {
             const int idx = tid + r * kThreads;
             const int d = idx >> 6, s = (idx >> 4) & 3, e = idx & 15;
             const int t = ti * kTP + e;
@@ -331,53 +333,77 @@ __device__ __forceinline__ void store_tile(const Geom &g, const TileGeom &tg, co
     }
 }
 
-// One recurrence step.  DP = smem position stride per step (+1 row fwd, -1 row bwd, +4 column).
+// Inputs of one recurrence step of a scan thread = (strand, channel pair, state half): 2 channels
+// x 8 states, so the B/C rows of the position are fetched once per 16 state updates.  They are
+// loaded one step ahead (the compiler cannot hoist them itself: the y store may alias).
 template <bool FINAL>
-__device__ __forceinline__ void scan_step(const float2 *ddp, const float *pjp, float *ysp,
-                                          f32x2 (&hst)[4], const f32x2 (&A2)[4], float &sdt,
-                                          bool writer)
+struct StepIn {
+    float4 dv;        // (dt0, u0, dt1, u1)
+    float4 b0, b1;    // B[half*8 .. +7]
+    float4 c0, c1;    // C[half*8 .. +7]   (pass 2)
+    __device__ __forceinline__ void load(const float *ddp, const float *pjp)
+    {
+        dv = *reinterpret_cast<const float4 *>(ddp);
+        b0 = *reinterpret_cast<const float4 *>(pjp);
+        b1 = *reinterpret_cast<const float4 *>(pjp + 4);
+        if (FINAL) {
+            c0 = *reinterpret_cast<const float4 *>(pjp + 16);
+            c1 = *reinterpret_cast<const float4 *>(pjp + 20);
+        }
+    }
+};
+
+template <bool FINAL>
+__device__ __forceinline__ void scan_step(const StepIn<FINAL> &in, float *ysp, f32x2 (&hst)[2][4],
+                                          const f32x2 (&A2)[2][4], float (&sdt)[2], float my_skip,
+                                          bool half)
 {
-    const float2 dv = *ddp;                       // (dt, dt*u)
-    const float4 b0 = *reinterpret_cast<const float4 *>(pjp);
-    const float4 b1 = *reinterpret_cast<const float4 *>(pjp + 4);
-    const f32x2 dt2 = pack2(dv.x, dv.x), du2 = pack2(dv.y, dv.y);
-    const f32x2 bb[4] = {pack2(b0.x, b0.y), pack2(b0.z, b0.w), pack2(b1.x, b1.y), pack2(b1.z, b1.w)};
-    if (!FINAL) sdt += dv.x;
+    const f32x2 bb[4] = {pack2(in.b0.x, in.b0.y), pack2(in.b0.z, in.b0.w), pack2(in.b1.x, in.b1.y),
+                         pack2(in.b1.z, in.b1.w)};
     f32x2 cc[4];
     if (FINAL) {
-        const float4 c0 = *reinterpret_cast<const float4 *>(pjp + 16);
-        const float4 c1 = *reinterpret_cast<const float4 *>(pjp + 20);
-        cc[0] = pack2(c0.x, c0.y); cc[1] = pack2(c0.z, c0.w);
-        cc[2] = pack2(c1.x, c1.y); cc[3] = pack2(c1.z, c1.w);
+        cc[0] = pack2(in.c0.x, in.c0.y); cc[1] = pack2(in.c0.z, in.c0.w);
+        cc[2] = pack2(in.c1.x, in.c1.y); cc[3] = pack2(in.c1.z, in.c1.w);
     }
-    f32x2 acc = pack2(0.0f, 0.0f);
+    const float dtv[2] = {in.dv.x, in.dv.z}, uv[2] = {in.dv.y, in.dv.w};
+    float yv[2];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const f32x2 a = ex2_2(fmul2(dt2, A2[j]));
-        hst[j] = ffma2(a, hst[j], fmul2(du2, bb[j]));
-        if (FINAL) acc = ffma2(hst[j], cc[j], acc);
+    for (int c = 0; c < 2; ++c) {
+        const float du = dtv[c] * uv[c];
+        const f32x2 dt2 = pack2(dtv[c], dtv[c]), du2 = pack2(du, du);
+        if (!FINAL) sdt[c] += dtv[c];
+        f32x2 acc = pack2(0.0f, 0.0f);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const f32x2 a = ex2_2(fmul2(dt2, A2[c][j]));
+            hst[c][j] = ffma2(a, hst[c][j], fmul2(du2, bb[j]));
+            if (FINAL) acc = ffma2(hst[c][j], cc[j], acc);
+        }
+        if (FINAL) {
+            float lo, hi;
+            unpack2(acc, lo, hi);
+            yv[c] = lo + hi;
+        }
     }
+    // half 0 finishes channel d0, half 1 channel d1: swap the other channel's partial sum with the
+    // partner lane, add the D skip term (reference :469)
     if (FINAL) {
-        float lo, hi;
-        unpack2(acc, lo, hi);
-        float y = lo + hi;
-        y += __shfl_xor_sync(0xffffffffu, y, 1);
-        if (writer) *ysp += y;                    // ys held D*u
+        const float other = __shfl_xor_sync(0xffffffffu, half ? yv[0] : yv[1], 1);
+        *ysp = fmaf(my_skip, half ? uv[1] : uv[0], (half ? yv[1] : yv[0]) + other);
     }
 }
 
 // The whole tile loop of one CTA, specialised on the pass and on the scan's smem stride.
-template <bool FINAL, int DP>
+template <bool FINAL, int DP, bool TIMED>
 __device__ __forceinline__ void run_cta(const Params &prm, const Geom &g, const TileGeom &tg,
                                         float *smem, int b)
 {
     float *xs = smem + kOffXs;
     float *pj = smem + kOffPj;
-    float2 *dd = reinterpret_cast<float2 *>(smem + kOffDd);
+    float *dd = smem + kOffDd;
     float *ys = smem + kOffYs;
     float4 *wf = reinterpret_cast<float4 *>(smem + kOffWf);
-    float *cst = smem + kOffCst;   // [dtw0 | dtw1 | dtb | Dskip] x 64
-    float *dlw = smem + kOffDlw;   // dt rows of W_k, [r 2][kq 4][i 16]
+    float *cst = smem + kOffCst;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -389,70 +415,90 @@ __device__ __forceinline__ void run_cta(const Params &prm, const Geom &g, const 
     load_tile(g, tg, cm, 0, xb, xs);   // in flight while the weights are prepared
 
     // ---- mma B fragments of W_k, pre-split into tf32 hi/lo -----------------------------------
-    // n-tile nt, column n (0..7) -> row 2 + 8 nt + n of x_proj_weight[k] (34,64) = [dt(2)|B(16)|C(16)]
+    // n-tile nt, column n (0..7) -> row of x_proj_weight[k] (34,64) = [dt(2) | B(16) | C(16)]
     for (int i = tid; i < 8 * kNTiles * 32; i += kThreads) {
         const int ln_ = i & 31, nt = (i >> 5) % kNTiles, ks = i / (32 * kNTiles);
         const int gq = ln_ >> 2, t4 = ln_ & 3;
-        const float *wr = prm.x_proj_w + ((int64_t)k * kProj + 2 + nt * 8 + gq) * kD + ks * 8;
-        const float w0 = __ldg(wr + t4), w1 = __ldg(wr + t4 + 4);
+        int row;  // source row for output column n = gq of n-tile nt
+        if (nt < 4) row = 2 + nt * 8 + gq;            // B0..15 -> rows 2..17, C0..15 -> rows 18..33
+        else row = gq < 2 ? gq : -1;                  // dt rows 0,1; rest zero padding
+        float w0 = 0.0f, w1 = 0.0f;
+        if (row >= 0) {
+            const float *wr = prm.x_proj_w + ((int64_t)k * kProj + row) * kD + ks * 8;
+            w0 = __ldg(wr + t4);
+            w1 = __ldg(wr + t4 + 4);
+        }
         const uint32_t h0 = to_tf32(w0), h1 = to_tf32(w1);
         const uint32_t l0 = to_tf32(w0 - __uint_as_float(h0)), l1 = to_tf32(w1 - __uint_as_float(h1));
         wf[i] = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(l0),
                             __uint_as_float(l1));
     }
-    // dt rows for the FP32 dt-low phase: dlw[r][kq][i] = W_k[r][4 i + kq]
-    if (tid < 2 * kD) {
-        const int r = tid >> 6, kq = (tid >> 4) & 3, i = tid & 15;
-        dlw[tid] = __ldg(prm.x_proj_w + ((int64_t)k * kProj + r) * kD + 4 * i + kq);
-    }
+
+    // ---- delta-phase constants [dt_proj col 0 | col 1 | bias] x 64 channels -------------------
     if (tid < kD) {
         const int chn = k * kD + tid;
         cst[tid] = __ldg(prm.dt_w + chn * 2 + 0);
         cst[kD + tid] = __ldg(prm.dt_w + chn * 2 + 1);
         cst[2 * kD + tid] = __ldg(prm.dt_b + chn);
-        cst[3 * kD + tid] = __ldg(prm.Ds + chn);
     }
 
-    // ---- scan-thread identity: (strand, channel, state half) -------------------------------
-    const int s = tid >> 7, d = (tid & 127) >> 1, half = tid & 1;
-    f32x2 A2[4];  // A * log2(e), A = -exp(A_log)   (reference :462)
+    // ---- scan-thread identity: (strand, channel pair, state half) ----------------------------
+    const int s = tid >> 6, cp = (tid & 63) >> 1;
+    const bool half = (tid & 1) != 0;
+    const int hoff = half ? 8 : 0;
+    f32x2 A2[2][4];  // A * log2(e), A = -exp(A_log)   (reference :462)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float *ap = prm.A_logs + (int64_t)(k * kD + d) * kN + half * 8 + 2 * j;
-        A2[j] = pack2(-expf(__ldg(ap)) * 1.4426950408889634f,
-                      -expf(__ldg(ap + 1)) * 1.4426950408889634f);
-    }
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float *ap = prm.A_logs + (int64_t)(k * kD + 2 * cp + c) * kN + hoff + 2 * j;
+            A2[c][j] = pack2(-expf(__ldg(ap)) * 1.4426950408889634f,
+                             -expf(__ldg(ap + 1)) * 1.4426950408889634f);
+        }
+    const float my_skip = FINAL ? __ldg(prm.Ds + k * kD + 2 * cp + (half ? 1 : 0)) : 0.0f;
     const int my_len = strand_len(g, tg, s);
     const int my_chunk = tg.chunk0 + s;
     const int64_t agg_off =
-        (((int64_t)b * kK + k) * g.max_chunks + my_chunk) * kChains + (int64_t)d * kN + half * 8;
+        (((int64_t)b * kK + k) * g.max_chunks + my_chunk) * kChains + (int64_t)(2 * cp) * kN + hoff;
 
-    f32x2 hst[4];
+    f32x2 hst[2][4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) hst[j] = pack2(0.0f, 0.0f);
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) hst[c][j] = pack2(0.0f, 0.0f);
     if (FINAL && my_len > 0 && my_chunk > 0) {
-        const float4 *hp = reinterpret_cast<const float4 *>(prm.aggH + agg_off);
-        const float4 f0 = hp[0], f1 = hp[1];
-        hst[0] = pack2(f0.x, f0.y); hst[1] = pack2(f0.z, f0.w);
-        hst[2] = pack2(f1.x, f1.y); hst[3] = pack2(f1.z, f1.w);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const float4 *hp = reinterpret_cast<const float4 *>(prm.aggH + agg_off + c * kN);
+            const float4 f0 = hp[0], f1 = hp[1];
+            hst[c][0] = pack2(f0.x, f0.y); hst[c][1] = pack2(f0.z, f0.w);
+            hst[c][2] = pack2(f1.x, f1.y); hst[c][3] = pack2(f1.z, f1.w);
+        }
     }
-    double sum_dt = 0.0;
+    double sum_dt[2] = {0.0, 0.0};
 
     // smem position of step 0 of my strand; step e sits at p0 + e*DP
     const int p0 = tile_pos(tg, s, 0);
-    const float2 *dd0 = dd + d * kDS + p0;
-    const float *pj0 = pj + p0 * kPJ + half * 8;
-    float *ys0 = ys + d * kYS + p0;
-    const bool writer = half == 0;
+    const float *dd0 = dd + p0 * kDD + 4 * cp;
+    const float *pj0 = pj + p0 * kPJ + hoff;
+    float *ys0 = ys + (2 * cp + (half ? 1 : 0)) * kYS + p0;
 
     float *oplane = FINAL ? prm.planes + (((int64_t)k * g.B + b) * kD) * g.L : nullptr;
 
-    // projection role of this warp: m-tile (16 positions) x one n-tile (pass 1 needs B only)
-    const int mt = warp & 3, nt = warp >> 2;      // nt: B0-7 | B8-15 | C0-7 | C8-15
-    const bool has_mma = FINAL || nt < 2;
+    // projection role of this warp: m-tile (16 positions) and up to three n-tiles.
+    //   pass 2: warps 0-3 -> B0-7, B8-15, dt;  warps 4-7 -> C0-7, C8-15
+    //   pass 1: warps 0-3 -> B0-7, B8-15;      warps 4-7 -> dt
+    // every SM sub-partition hosts one warp of each kind, so the tensor pipes stay balanced
+    const int mt = warp & 3, nh = warp >> 2;
+    int nt_list[3], nt_count;
+    if (FINAL) {
+        nt_list[0] = nh ? 2 : 0; nt_list[1] = nh ? 3 : 1; nt_list[2] = 4; nt_count = nh ? 2 : 3;
+    } else {
+        nt_list[0] = nh ? 4 : 0; nt_list[1] = 1; nt_list[2] = 1; nt_count = nh ? 1 : 2;
+    }
 
     long long tacc[5] = {0, 0, 0, 0, 0}, tprev = 0;
-    const bool timed = prm.dbg != nullptr && tid == 0;
+    const bool timed = TIMED && tid == 0;
 #define WM_TICK(k) \
     if (timed) { const long long tn = clock64(); tacc[k] += tn - tprev; tprev = tn; }
     if (timed) tprev = clock64();
@@ -463,70 +509,78 @@ __device__ __forceinline__ void run_cta(const Params &prm, const Geom &g, const 
         __syncthreads();                       // xs(ti) landed; previous tile fully consumed
         WM_TICK(0);
 
-        // ---- dt-low: 2 x 64 dot products per position in plain FP32 (reference :453) -------
-        // thread = (dt row r = tid/256, k-slice kq: channels kq, 4+kq, .., position p); a quad of
-        // lanes 8 apart holds the four k-slices of one position (xs reads are conflict-free)
+        // ---- projection on tensor cores (reference :453) ---------------------------------
         {
-            const int r = tid >> 8, kq = (tid >> 3) & 3, p = ((tid & 255) >> 5) * 8 + (tid & 7);
-            const float *xp = xs + kq * kXS + p;
-            const float4 *wq = reinterpret_cast<const float4 *>(dlw + (r * 4 + kq) * 16);
-            float a0 = 0.0f, a1 = 0.0f;
+            float acc[3][4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float4 w4 = wq[q];
-                a0 = fmaf(w4.x, xp[(4 * q + 0) * 4 * kXS], a0);
-                a1 = fmaf(w4.y, xp[(4 * q + 1) * 4 * kXS], a1);
-                a0 = fmaf(w4.z, xp[(4 * q + 2) * 4 * kXS], a0);
-                a1 = fmaf(w4.w, xp[(4 * q + 3) * 4 * kXS], a1);
+            for (int t = 0; t < 3; ++t)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[t][i] = 0.0f;
+            const int gq = lane >> 2, t4 = lane & 3;
+            const float *abase = xs + t4 * kXS + mt * 16 + gq;
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+                const float *ap = abase + ks * 8 * kXS;
+                const float av[4] = {ap[0], ap[8], ap[4 * kXS], ap[4 * kXS + 8]};
+                uint32_t ahi[4], alo[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) split_tf32(av[i], ahi[i], alo[i]);
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    if (t < nt_count) {
+                        const float4 bw = wf[(ks * kNTiles + nt_list[t]) * 32 + lane];
+                        mma_tf32(acc[t], alo, __float_as_uint(bw.x), __float_as_uint(bw.y));
+                        mma_tf32(acc[t], ahi, __float_as_uint(bw.z), __float_as_uint(bw.w));
+                        mma_tf32(acc[t], ahi, __float_as_uint(bw.x), __float_as_uint(bw.y));
+                    }
+                }
             }
-            a0 += a1;
-            a0 += __shfl_xor_sync(0xffffffffu, a0, 8);
-            a0 += __shfl_xor_sync(0xffffffffu, a0, 16);
-            if (kq == 0) pj[p * kPJ + 32 + r] = a0;
+            float *pr = pj + (mt * 16 + gq) * kPJ;
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                if (t < nt_count) {
+                    const int nt = nt_list[t];
+                    if (nt < 4) {
+                        *reinterpret_cast<float2 *>(pr + nt * 8 + 2 * t4) = make_float2(acc[t][0], acc[t][1]);
+                        *reinterpret_cast<float2 *>(pr + 8 * kPJ + nt * 8 + 2 * t4) =
+                            make_float2(acc[t][2], acc[t][3]);
+                    } else if (t4 == 0) {
+                        *reinterpret_cast<float2 *>(pr + 32) = make_float2(acc[t][0], acc[t][1]);
+                        *reinterpret_cast<float2 *>(pr + 8 * kPJ + 32) = make_float2(acc[t][2], acc[t][3]);
+                    }
+                }
+            }
         }
         __syncthreads();
         WM_TICK(1);
 
-        // ---- B/C projection on tensor cores (reference :453-454), interleaved with the delta
-        //      phase: dt = softplus(dt_proj . dt_low + bias)  (reference :455, scan_fn) ---------
-        // mma: warp = (m-tile, n-tile).  delta: warp w owns channels 4w..4w+3, lane = position
-        // within a 32-position round; item ks of the k-loop is (round ks/4, channel ks%4).
+        // ---- delta phase: dt = softplus(dt_proj . dt_low + bias)  (reference :455, scan_fn) --
+        // warp w owns channels 8w..8w+7; lane = position within a 32-position round
         {
-            float c0[4] = {0.f, 0.f, 0.f, 0.f};
-            const int gq = lane >> 2, t4 = lane & 3;
-            const float *abase = xs + t4 * kXS + mt * 16 + gq;
-            const float4 *wfp = wf + nt * 32 + lane;
-            const float *xw = xs + warp * 4 * kXS + lane;
-            float2 *dw = dd + warp * 4 * kDS + lane;
-            float *yw = ys + warp * 4 * kYS + lane;
-            const float *cw = cst + warp * 4;
-            float2 dlow = make_float2(0.f, 0.f);
+            float dw0[8], dw1[8], dbias[8];
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
-                if (has_mma) {
-                    const float *ap = abase + ks * 8 * kXS;
-                    const float av[4] = {ap[0], ap[8], ap[4 * kXS], ap[4 * kXS + 8]};
-                    uint32_t ahi[4], alo[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) split_tf32(av[i], ahi[i], alo[i]);
-                    const float4 bw = wfp[ks * kNTiles * 32];
-                    mma_tf32(c0, alo, __float_as_uint(bw.x), __float_as_uint(bw.y));
-                    mma_tf32(c0, ahi, __float_as_uint(bw.z), __float_as_uint(bw.w));
-                    mma_tf32(c0, ahi, __float_as_uint(bw.x), __float_as_uint(bw.y));
-                }
-                const int rnd = ks >> 2, i = ks & 3;
-                if (i == 0)
-                    dlow = *reinterpret_cast<const float2 *>(pj + (rnd * 32 + lane) * kPJ + 32);
-                const float u = xw[i * kXS + rnd * 32];
-                const float raw = fmaf(cw[kD + i], dlow.y, cw[i] * dlow.x) + cw[2 * kD + i];
-                const float dt = softplus_fast(raw);
-                dw[i * kDS + rnd * 32] = make_float2(dt, dt * u);
-                if (FINAL) yw[i * kYS + rnd * 32] = cw[3 * kD + i] * u;
+            for (int q = 0; q < 2; ++q) {
+                const float4 a = *reinterpret_cast<const float4 *>(cst + warp * 8 + 4 * q);
+                const float4 bq = *reinterpret_cast<const float4 *>(cst + kD + warp * 8 + 4 * q);
+                const float4 cq = *reinterpret_cast<const float4 *>(cst + 2 * kD + warp * 8 + 4 * q);
+                dw0[4 * q] = a.x; dw0[4 * q + 1] = a.y; dw0[4 * q + 2] = a.z; dw0[4 * q + 3] = a.w;
+                dw1[4 * q] = bq.x; dw1[4 * q + 1] = bq.y; dw1[4 * q + 2] = bq.z; dw1[4 * q + 3] = bq.w;
+                dbias[4 * q] = cq.x; dbias[4 * q + 1] = cq.y; dbias[4 * q + 2] = cq.z; dbias[4 * q + 3] = cq.w;
             }
-            if (has_mma) {
-                float *pr = pj + (mt * 16 + gq) * kPJ + nt * 8 + 2 * t4;
-                *reinterpret_cast<float2 *>(pr) = make_float2(c0[0], c0[1]);
-                *reinterpret_cast<float2 *>(pr + 8 * kPJ) = make_float2(c0[2], c0[3]);
+#pragma unroll
+            for (int rnd = 0; rnd < 2; ++rnd) {
+                const int p = rnd * 32 + lane;
+                const float2 dlow = *reinterpret_cast<const float2 *>(pj + p * kPJ + 32);
+                const float *xw = xs + warp * 8 * kXS + p;
+                float4 *dq = reinterpret_cast<float4 *>(dd + p * kDD + warp * 16);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float u0 = xw[(2 * q) * kXS], u1 = xw[(2 * q + 1) * kXS];
+                    const float r0 = fmaf(dw1[2 * q], dlow.y, dw0[2 * q] * dlow.x) + dbias[2 * q];
+                    const float r1 =
+                        fmaf(dw1[2 * q + 1], dlow.y, dw0[2 * q + 1] * dlow.x) + dbias[2 * q + 1];
+                    dq[q] = make_float4(softplus_fast(r0), u0, softplus_fast(r1), u1);
+                }
             }
         }
         __syncthreads();                       // xs is dead from here on
@@ -537,17 +591,25 @@ __device__ __forceinline__ void run_cta(const Params &prm, const Geom &g, const 
         // ---- recurrence over the 16 steps of this tile        (reference :465-471) --------
         {
             const int nvalid = my_len - ti * kTP;          // warp-uniform
-            float sdt = 0.0f;
+            float sdt[2] = {0.0f, 0.0f};
             if (nvalid >= kTP) {
+                StepIn<FINAL> cur, nxt;
+                cur.load(dd0, pj0);
 #pragma unroll
-                for (int e = 0; e < kTP; ++e)
-                    scan_step<FINAL>(dd0 + e * DP, pj0 + e * DP * kPJ, ys0 + e * DP, hst, A2, sdt, writer);
+                for (int e = 0; e < kTP; ++e) {
+                    if (e + 1 < kTP) nxt.load(dd0 + (e + 1) * DP * kDD, pj0 + (e + 1) * DP * kPJ);
+                    scan_step<FINAL>(cur, ys0 + e * DP, hst, A2, sdt, my_skip, half);
+                    cur = nxt;
+                }
             } else {
 #pragma unroll 1
-                for (int e = 0; e < nvalid; ++e)
-                    scan_step<FINAL>(dd0 + e * DP, pj0 + e * DP * kPJ, ys0 + e * DP, hst, A2, sdt, writer);
+                for (int e = 0; e < nvalid; ++e) {
+                    StepIn<FINAL> cur;
+                    cur.load(dd0 + e * DP * kDD, pj0 + e * DP * kPJ);
+                    scan_step<FINAL>(cur, ys0 + e * DP, hst, A2, sdt, my_skip, half);
+                }
             }
-            if (!FINAL) sum_dt += (double)sdt;
+            if (!FINAL) { sum_dt[0] += (double)sdt[0]; sum_dt[1] += (double)sdt[1]; }
         }
         if (FINAL) {
             __syncthreads();
@@ -565,26 +627,29 @@ __device__ __forceinline__ void run_cta(const Params &prm, const Geom &g, const 
     }
 
     if (!FINAL && my_len > 0) {
-        float4 *pp4 = reinterpret_cast<float4 *>(prm.aggP + agg_off);
-        float4 *hp4 = reinterpret_cast<float4 *>(prm.aggH + agg_off);
-        float pv[8], hv[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float a_lo, a_hi;
-            unpack2(A2[j], a_lo, a_hi);
-            pv[2 * j] = ex2_approx((float)((double)a_lo * sum_dt));
-            pv[2 * j + 1] = ex2_approx((float)((double)a_hi * sum_dt));
-            unpack2(hst[j], hv[2 * j], hv[2 * j + 1]);
+        for (int c = 0; c < 2; ++c) {
+            float4 *pp4 = reinterpret_cast<float4 *>(prm.aggP + agg_off + c * kN);
+            float4 *hp4 = reinterpret_cast<float4 *>(prm.aggH + agg_off + c * kN);
+            float pv[8], hv[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float a_lo, a_hi;
+                unpack2(A2[c][j], a_lo, a_hi);
+                pv[2 * j] = ex2_approx((float)((double)a_lo * sum_dt[c]));
+                pv[2 * j + 1] = ex2_approx((float)((double)a_hi * sum_dt[c]));
+                unpack2(hst[c][j], hv[2 * j], hv[2 * j + 1]);
+            }
+            pp4[0] = make_float4(pv[0], pv[1], pv[2], pv[3]);
+            pp4[1] = make_float4(pv[4], pv[5], pv[6], pv[7]);
+            hp4[0] = make_float4(hv[0], hv[1], hv[2], hv[3]);
+            hp4[1] = make_float4(hv[4], hv[5], hv[6], hv[7]);
         }
-        pp4[0] = make_float4(pv[0], pv[1], pv[2], pv[3]);
-        pp4[1] = make_float4(pv[4], pv[5], pv[6], pv[7]);
-        hp4[0] = make_float4(hv[0], hv[1], hv[2], hv[3]);
-        hp4[1] = make_float4(hv[4], hv[5], hv[6], hv[7]);
     }
 }
 
 // FINAL=false: pass 1 (aggregates).  FINAL=true: pass 2 (outputs).
-template <bool FINAL>
+template <bool FINAL, bool TIMED>
 __global__ void __launch_bounds__(kThreads, 2)
 ss2d_pass_kernel(const Params prm, const Geom g, const Launch ln)
 {
@@ -600,9 +665,9 @@ ss2d_pass_kernel(const Params prm, const Geom g, const Launch ln)
     tg.chunk0 = (blockIdx.x - begin) * kSeq;
     tg.maxlen = tg.col ? g.h : g.row_T;
     const int b = blockIdx.y;
-    if (tg.col) run_cta<FINAL, kSeq>(prm, g, tg, smem, b);
-    else if (tg.fwd) run_cta<FINAL, 1>(prm, g, tg, smem, b);
-    else run_cta<FINAL, -1>(prm, g, tg, smem, b);
+    if (tg.col) run_cta<FINAL, kSeq, TIMED>(prm, g, tg, smem, b);
+    else if (tg.fwd) run_cta<FINAL, 1, TIMED>(prm, g, tg, smem, b);
+    else run_cta<FINAL, -1, TIMED>(prm, g, tg, smem, b);
 }
 
 // h_in[c] = P[c-1]*h_in[c-1] + H[c-1], h_in[0] = 0; written over aggH in place.
@@ -745,19 +810,19 @@ int run_dirs(const float *x, const float *x_proj_weight, const float *dt_projs_w
     prm.dbg = g_dbg;
     const size_t smem_bytes = kSmemBytes + (size_t)g_dbg_pad;
 
-    WM_CUDA_OK(cudaFuncSetAttribute(ss2d_pass_kernel<false>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    WM_CUDA_OK(cudaFuncSetAttribute(ss2d_pass_kernel<true>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    auto pass1 = g_dbg ? ss2d_pass_kernel<false, true> : ss2d_pass_kernel<false, false>;
+    auto pass2 = g_dbg ? ss2d_pass_kernel<true, true> : ss2d_pass_kernel<true, false>;
+    WM_CUDA_OK(cudaFuncSetAttribute(pass1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    WM_CUDA_OK(cudaFuncSetAttribute(pass2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     // interleave row and column CTAs of the same cost so waves stay balanced
     const Launch ln = make_launch(g, {0, 1, 2, 3});
     dim3 grid(ln.cta_begin[4], (unsigned)B);
-    ss2d_pass_kernel<false><<<grid, kThreads, smem_bytes, s>>>(prm, g, ln);
+    pass1<<<grid, kThreads, smem_bytes, s>>>(prm, g, ln);
     WM_LAUNCH_OK("ss2d pass 1");
     dim3 cgrid(kChains / 256, kK, (unsigned)B);
     ss2d_carry_kernel<<<cgrid, 256, 0, s>>>(prm.aggP, prm.aggH, g);
     WM_LAUNCH_OK("ss2d carry");
-    ss2d_pass_kernel<true><<<grid, kThreads, smem_bytes, s>>>(prm, g, ln);
+    pass2<<<grid, kThreads, smem_bytes, s>>>(prm, g, ln);
     WM_LAUNCH_OK("ss2d pass 2");
     return WM_OK;
 }
