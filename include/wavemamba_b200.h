@@ -69,6 +69,9 @@ size_t wm_ss2d_core_workspace_bytes(int64_t B, int64_t h, int64_t w);
 /* Developer aid: non-NULL device buffer of 4096*6 int64 -> every pass kernel CTA writes its phase
  * cycle sums [wait-x, projection, delta, scan, store, tiles] at index blockIdx.x % 4096. */
 int wm_ss2d_debug_timing(void *device_buffer);
+/* Developer aid: the chunk plan chosen for (B,h,w): out6 = {row chunk steps, row CTAs per
+ * direction, column segment steps, segments per column, column CTAs per direction, columns first}. */
+int wm_ss2d_debug_geometry(int64_t B, int64_t h, int64_t w, int *out6);
 /* Same computation without the final 4-way sum: on return the first 4*B*64*h*w floats of
  * `workspace` hold the four direction outputs as planes[k][b][d][i][j] (pixel order, k = 0..3 in
  * the reference's direction order); the consumer sums them as ((p0 + p2) + p1) + p3, which is the

@@ -23,6 +23,7 @@ SIGNATURES = {
     "wm_iwt_haar_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p] + [c_int64] * 4 + [c_void_p]),
     "wm_ss2d_core_workspace_bytes": (c_size_t, [c_int64] * 3),
     "wm_ss2d_debug_timing": (c_int, [c_void_p]),
+    "wm_ss2d_debug_geometry": (c_int, [c_int64] * 3 + [c_void_p]),
     "wm_ss2d_dirs_fwd": (c_int, [c_void_p] * 7 + [c_size_t] + [c_int64] * 3 + [c_void_p]),
     "wm_ss2d_core_fwd": (c_int, [c_void_p] * 8 + [c_size_t] + [c_int64] * 3 + [c_void_p]),
     "wm_layernorm2d_fwd": (c_int, [c_void_p] * 3 + [c_float, c_void_p] + [c_int64] * 4 + [c_void_p]),

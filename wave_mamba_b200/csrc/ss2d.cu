@@ -35,7 +35,12 @@
 //
 // Roofline: not HBM-bound.  Each state update costs one MUFU ex2 (16/clk/SM) and every exp is
 // evaluated twice (pass 1 and pass 2); see DESIGN.md section 4.
+#include <stdlib.h>
+
 #include <initializer_list>
+#include <mutex>
+#include <utility>
+#include <vector>
 
 #include "common.cuh"
 
@@ -73,8 +78,11 @@ struct Geom {
     int row_T;       // steps per row chunk (multiple of kTP)
     int row_chunks;  // ceil(L / row_T)
     int row_ctas;    // ceil(row_chunks / kSeq)
-    int col_ctas;    // ceil(w / kSeq)
-    int max_chunks;  // max(row_chunks, w): chunk stride of the aggregate arrays
+    int col_seg;     // steps per column chunk (multiple of kTP): a column is cut into ncolseg chunks
+    int ncolseg;     // ceil(h / col_seg)
+    int col_ctas;    // ceil(w / kSeq) * ncolseg
+    int max_chunks;  // max(row_chunks, w * ncolseg): chunk stride of the aggregate arrays
+    int cols_first;  // launch order: column-direction CTAs before row-direction CTAs
     int vec_rows;    // 1 when row tiles may use 16-byte global accesses (L % 4 == 0)
     int vec_cols;    // 1 when column tiles may (w % 4 == 0)
 };
@@ -185,15 +193,16 @@ struct TileGeom {
     int k;          // direction
     bool col;       // column-major direction
     bool fwd;       // forward direction (0 or 1)
-    int chunk0;     // sequence-order chunk index of strand 0
-    int maxlen;     // steps per full chunk (row_T or h)
+    int chunk0;     // rows: sequence-order chunk index of strand 0; columns: image column of strand 0
+    int seg, t0;    // columns: segment index inside the column and its first step (rows: 0)
+    int maxlen;     // steps of the longest strand of this CTA
 };
 
 // number of valid steps of strand s
 __device__ __forceinline__ int strand_len(const Geom &g, const TileGeom &tg, int s)
 {
     const int c = tg.chunk0 + s;
-    if (tg.col) return c < g.w ? g.h : 0;
+    if (tg.col) return c < g.w ? min(g.col_seg, g.h - tg.t0) : 0;
     const int64_t rem = g.L - (int64_t)c * g.row_T;
     return rem <= 0 ? 0 : (rem < g.row_T ? (int)rem : g.row_T);
 }
@@ -207,7 +216,7 @@ __device__ __forceinline__ int64_t strand_elem(const Geom &g, const TileGeom &tg
         return tg.fwd ? l : g.L - 1 - l;
     }
     const int j = tg.fwd ? c : g.w - 1 - c;
-    const int i = tg.fwd ? t : g.h - 1 - t;
+    const int i = tg.fwd ? tg.t0 + t : g.h - 1 - tg.t0 - t;
     return (int64_t)i * g.w + j;
 }
 
@@ -224,7 +233,7 @@ __device__ __forceinline__ bool tile_is_vec(const Geom &g, const TileGeom &tg, i
 {
     const int t_end = ti * kTP + kTP;
     if (tg.col)
-        return g.vec_cols && tg.chunk0 + kSeq <= g.w && t_end <= g.h;
+        return g.vec_cols && tg.chunk0 + kSeq <= g.w && t_end <= min(g.col_seg, g.h - tg.t0);
     return g.vec_rows && (int64_t)(tg.chunk0 + kSeq - 1) * g.row_T + t_end <= g.L;
 }
 
@@ -242,7 +251,7 @@ __device__ __forceinline__ void vec_chunk(const Geom &g, const TileGeom &tg, int
         p0 = s * kTP + 4 * v;
     } else {
         const int e = cidx;
-        const int i = tg.fwd ? ti * kTP + e : g.h - 1 - (ti * kTP + e);
+        const int i = tg.fwd ? tg.t0 + ti * kTP + e : g.h - 1 - (tg.t0 + ti * kTP + e);
         const int jlow = tg.fwd ? tg.chunk0 : g.w - kSeq - tg.chunk0;
         goff = (int64_t)i * g.w + jlow;
         p0 = e * kSeq;
@@ -273,7 +282,7 @@ __device__ __forceinline__ ChunkMap make_chunk_map(const Geom &g, const TileGeom
         p0 = s * kTP + 4 * v;
     } else {
         const int e = cidx;
-        const int i = tg.fwd ? e : g.h - 1 - e;
+        const int i = tg.fwd ? tg.t0 + e : g.h - 1 - tg.t0 - e;
         const int jlow = tg.fwd ? tg.chunk0 : g.w - kSeq - tg.chunk0;
         cm.goff = (int64_t)i * g.w + jlow;
         cm.gstep = tg.fwd ? (int64_t)kTP * g.w : -(int64_t)kTP * g.w;
@@ -457,7 +466,7 @@ __device__ __forceinline__ void run_cta(const Params &prm, const Geom &g, const 
         }
     const float my_skip = FINAL ? __ldg(prm.Ds + k * kD + 2 * cp + (half ? 1 : 0)) : 0.0f;
     const int my_len = strand_len(g, tg, s);
-    const int my_chunk = tg.chunk0 + s;
+    const int my_chunk = tg.col ? (tg.chunk0 + s) * g.ncolseg + tg.seg : tg.chunk0 + s;
     const int64_t agg_off =
         (((int64_t)b * kK + k) * g.max_chunks + my_chunk) * kChains + (int64_t)(2 * cp) * kN + hoff;
 
@@ -662,8 +671,18 @@ ss2d_pass_kernel(const Params prm, const Geom g, const Launch ln)
     tg.k = k;
     tg.col = (k & 1) != 0;
     tg.fwd = k < 2;
-    tg.chunk0 = (blockIdx.x - begin) * kSeq;
-    tg.maxlen = tg.col ? g.h : g.row_T;
+    const int idx = blockIdx.x - begin;
+    if (tg.col) {
+        tg.seg = idx % g.ncolseg;
+        tg.chunk0 = (idx / g.ncolseg) * kSeq;
+        tg.t0 = tg.seg * g.col_seg;
+        tg.maxlen = min(g.col_seg, g.h - tg.t0);
+    } else {
+        tg.seg = 0;
+        tg.t0 = 0;
+        tg.chunk0 = idx * kSeq;
+        tg.maxlen = g.row_T;
+    }
     const int b = blockIdx.y;
     if (tg.col) run_cta<FINAL, kSeq, TIMED>(prm, g, tg, smem, b);
     else if (tg.fwd) run_cta<FINAL, 1, TIMED>(prm, g, tg, smem, b);
@@ -671,31 +690,67 @@ ss2d_pass_kernel(const Params prm, const Geom g, const Launch ln)
 }
 
 // h_in[c] = P[c-1]*h_in[c-1] + H[c-1], h_in[0] = 0; written over aggH in place.
-__global__ void __launch_bounds__(256)
+// A block owns 32 chains (lanes: one 128-byte line per chunk) and cuts the chunk sequence into
+// kCarryWarps contiguous segments, one per warp: sweep 1 composes each segment's affine map
+// (A, B) = (prod P, local end state), the segment carries are chained through shared memory, sweep 2
+// rewrites H with the true initial states.  Fixed evaluation order: deterministic.
+constexpr int kCarryWarps = 16;
+constexpr int kCarryBatch = 8;
+__global__ void __launch_bounds__(32 * kCarryWarps)
 ss2d_carry_kernel(const float *__restrict__ aggP, float *__restrict__ aggH, Geom g)
 {
-    const int chain = blockIdx.x * 256 + threadIdx.x;  // 0..1023
+    __shared__ float compA[kCarryWarps][32], compB[kCarryWarps][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int chain = blockIdx.x * 32 + lane;            // 0..1023
     const int k = blockIdx.y, b = blockIdx.z;
-    const int nchunks = (k & 1) ? g.w : g.row_chunks;
+    const int nchunks = (k & 1) ? g.w * g.ncolseg : g.row_chunks;
     const int64_t off = (((int64_t)b * kK + k) * g.max_chunks) * kChains + chain;
     const float *P = aggP + off;
     float *H = aggH + off;
-    float carry = 0.0f;
-    int c = 0;
-    for (; c + 8 <= nchunks; c += 8) {
-        float p[8], hv[8];
+    const int per = (nchunks + kCarryWarps - 1) / kCarryWarps;
+    const int c0 = min(warp * per, nchunks), c1 = min(c0 + per, nchunks);
+
+    float accA = 1.0f, accB = 0.0f;
+    int c = c0;
+    for (; c + kCarryBatch <= c1; c += kCarryBatch) {
+        float p[kCarryBatch], hv[kCarryBatch];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < kCarryBatch; ++i) {
             p[i] = P[(int64_t)(c + i) * kChains];
             hv[i] = H[(int64_t)(c + i) * kChains];
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < kCarryBatch; ++i) {
+            accB = fmaf(p[i], accB, hv[i]);
+            accA *= p[i];
+        }
+    }
+    for (; c < c1; ++c) {
+        const float p = P[(int64_t)c * kChains], hv = H[(int64_t)c * kChains];
+        accB = fmaf(p, accB, hv);
+        accA *= p;
+    }
+    compA[warp][lane] = accA;
+    compB[warp][lane] = accB;
+    __syncthreads();
+    float carry = 0.0f;
+    for (int v = 0; v < warp; ++v) carry = fmaf(compA[v][lane], carry, compB[v][lane]);
+
+    c = c0;
+    for (; c + kCarryBatch <= c1; c += kCarryBatch) {
+        float p[kCarryBatch], hv[kCarryBatch];
+#pragma unroll
+        for (int i = 0; i < kCarryBatch; ++i) {
+            p[i] = P[(int64_t)(c + i) * kChains];
+            hv[i] = H[(int64_t)(c + i) * kChains];
+        }
+#pragma unroll
+        for (int i = 0; i < kCarryBatch; ++i) {
             H[(int64_t)(c + i) * kChains] = carry;
             carry = fmaf(p[i], carry, hv[i]);
         }
     }
-    for (; c < nchunks; ++c) {
+    for (; c < c1; ++c) {
         const float p = P[(int64_t)c * kChains], hv = H[(int64_t)c * kChains];
         H[(int64_t)c * kChains] = carry;
         carry = fmaf(p, carry, hv);
@@ -726,23 +781,114 @@ ss2d_combine_kernel(float *__restrict__ y, const float *__restrict__ planes, int
 
 inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
+// Makespan (in tile units) of a greedy launch-order schedule of the CTA list on `slots` CTA slots.
+// CTA cost = tiles + kCtaOverhead.  All CTAs of one orientation cost the same, so the schedule is
+// simulated on (count, cost) runs with a small array of slot finish times.
+constexpr double kCtaOverhead = 0.75;
+double schedule_makespan(int slots, const int *counts, const double *costs, int nruns)
+{
+    // slots are interchangeable: keep finish times sorted ascending in a multiset-like vector
+    static thread_local std::vector<double> fin;
+    fin.assign(slots, 0.0);
+    // fin is kept as a min-heap
+    auto sift_down = [&](int i) {
+        const int n = slots;
+        for (;;) {
+            int l = 2 * i + 1, r = l + 1, m = i;
+            if (l < n && fin[l] < fin[m]) m = l;
+            if (r < n && fin[r] < fin[m]) m = r;
+            if (m == i) break;
+            std::swap(fin[i], fin[m]);
+            i = m;
+        }
+    };
+    double makespan = 0.0;
+    for (int r = 0; r < nruns; ++r)
+        for (int c = 0; c < counts[r]; ++c) {
+            fin[0] += costs[r];
+            if (fin[0] > makespan) makespan = fin[0];
+            sift_down(0);
+        }
+    return makespan;
+}
+
+// Chunking: both orientations are cut so that the CTAs of one launch fill the machine's CTA slots
+// (2 per SM) with as little tail as possible; the choice is cached per (B, h, w).
 Geom make_geom(int64_t B, int64_t h, int64_t w)
 {
+    struct Key { int64_t B, h, w; };
+    static std::mutex mu;
+    static std::vector<std::pair<Key, Geom>> cache;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        for (const auto &e : cache)
+            if (e.first.B == B && e.first.h == h && e.first.w == w) return e.second;
+    }
     Geom g;
     g.B = (int)B; g.h = (int)h; g.w = (int)w;
     g.L = h * w;
-    g.col_ctas = (int)((w + kSeq - 1) / kSeq);
-    // Row chunks: about as many as there are columns so both orientations give similar CTA
-    // counts and similar chunk lengths, and never shorter than 4 tiles.
-    int64_t T = (g.L + w - 1) / w;       // = h
-    if (T < 4 * kTP) T = 4 * kTP;
-    T = align_up(T, kTP);
-    g.row_T = (int)T;
-    g.row_chunks = (int)((g.L + T - 1) / T);
-    g.row_ctas = (g.row_chunks + kSeq - 1) / kSeq;
-    g.max_chunks = g.row_chunks > g.w ? g.row_chunks : g.w;
     g.vec_rows = (g.L % 4 == 0) ? 1 : 0;
     g.vec_cols = (w % 4 == 0) ? 1 : 0;
+    const int slots = 2 * sm_count();
+    const int64_t col_groups = (w + kSeq - 1) / kSeq;
+    double best = 1e300;
+    int best_seg = 0, best_T = 0, best_first = 0;
+    const char *plan_env = getenv("WM_SS2D_PLAN");
+    const bool legacy = plan_env != nullptr && plan_env[0] == 'l';
+    if (legacy) {   // one chunk per column, row chunks of about the same length
+        best_seg = (int)align_up(h, kTP);
+        int64_t T = h < 4 * kTP ? 4 * kTP : h;
+        best_T = (int)align_up(T, kTP);
+    }
+    for (int nseg = 1; nseg <= 8 && !legacy; ++nseg) {
+        int64_t seg = align_up((h + nseg - 1) / nseg, kTP);
+        if (nseg > 1 && seg < 4 * kTP) break;          // never shorter than 4 tiles
+        const int ncolseg = (int)((h + seg - 1) / seg);
+        if (ncolseg != nseg && nseg > 1) continue;
+        const int64_t last = h - (int64_t)(ncolseg - 1) * seg;
+        // row chunk lengths: from 4 tiles up to a little more than the column segment
+        for (int64_t T = 4 * kTP; T <= seg + 8 * kTP; T += kTP) {
+            const int64_t row_chunks = (g.L + T - 1) / T;
+            const int64_t row_ctas = (row_chunks + kSeq - 1) / kSeq;
+            if (row_chunks > 16384 || w * ncolseg > 16384) continue;   // aggregate arrays stay small
+            // per direction: full column segments, the shorter last segment, row CTAs
+            const int n_full = (int)(col_groups * (ncolseg - 1)), n_last = (int)col_groups;
+            const double c_full = (double)(seg / kTP) + kCtaOverhead;
+            const double c_last = (double)((last + kTP - 1) / kTP) + kCtaOverhead;
+            const double c_row = (double)(T / kTP) + kCtaOverhead;
+            for (int first = 0; first < 2; ++first) {
+                // launch order of the four directions (x B images, consecutive in blockIdx.y)
+                int counts[12];
+                double costs[12];
+                int n = 0;
+                auto add_cols = [&]() {
+                    // segments of a column group are interleaved (idx % ncolseg); model them as
+                    // one run of the average cost split into its two cost classes
+                    counts[n] = n_full * (int)B; costs[n++] = c_full;
+                    counts[n] = n_last * (int)B; costs[n++] = c_last;
+                };
+                auto add_rows = [&]() { counts[n] = (int)(row_ctas * B); costs[n++] = c_row; };
+                if (first) { add_cols(); add_cols(); add_rows(); add_rows(); }
+                else { add_rows(); add_cols(); add_rows(); add_cols(); }
+                const double m = schedule_makespan(slots, counts, costs, n);
+                if (m < best - 1e-9) { best = m; best_seg = (int)seg; best_T = (int)T; best_first = first; }
+            }
+        }
+    }
+    g.col_seg = best_seg;
+    g.ncolseg = (int)((h + g.col_seg - 1) / g.col_seg);
+    g.col_ctas = (int)(col_groups * g.ncolseg);
+    g.row_T = best_T;
+    g.row_chunks = (int)((g.L + g.row_T - 1) / g.row_T);
+    g.row_ctas = (g.row_chunks + kSeq - 1) / kSeq;
+    const int col_chunks = g.w * g.ncolseg;
+    g.max_chunks = g.row_chunks > col_chunks ? g.row_chunks : col_chunks;
+    g.cols_first = best_first;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (cache.size() > 64) cache.clear();
+        cache.emplace_back(Key{B, h, w}, g);
+    }
     return g;
 }
 
@@ -815,12 +961,12 @@ int run_dirs(const float *x, const float *x_proj_weight, const float *dt_projs_w
     WM_CUDA_OK(cudaFuncSetAttribute(pass1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     WM_CUDA_OK(cudaFuncSetAttribute(pass2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     // interleave row and column CTAs of the same cost so waves stay balanced
-    const Launch ln = make_launch(g, {0, 1, 2, 3});
+    const Launch ln = g.cols_first ? make_launch(g, {1, 3, 0, 2}) : make_launch(g, {0, 1, 2, 3});
     dim3 grid(ln.cta_begin[4], (unsigned)B);
     pass1<<<grid, kThreads, smem_bytes, s>>>(prm, g, ln);
     WM_LAUNCH_OK("ss2d pass 1");
-    dim3 cgrid(kChains / 256, kK, (unsigned)B);
-    ss2d_carry_kernel<<<cgrid, 256, 0, s>>>(prm.aggP, prm.aggH, g);
+    dim3 cgrid(kChains / 32, kK, (unsigned)B);
+    ss2d_carry_kernel<<<cgrid, 32 * kCarryWarps, 0, s>>>(prm.aggP, prm.aggH, g);
     WM_LAUNCH_OK("ss2d carry");
     pass2<<<grid, kThreads, smem_bytes, s>>>(prm, g, ln);
     WM_LAUNCH_OK("ss2d pass 2");
@@ -837,6 +983,16 @@ extern "C" int wm_ss2d_debug_timing(void *device_buffer)
     const uintptr_t v = reinterpret_cast<uintptr_t>(device_buffer);
     wm::ss2d::g_dbg_pad = (v & 1) ? 60 * 1024 : 0;
     wm::ss2d::g_dbg = reinterpret_cast<long long *>(v & ~(uintptr_t)1);
+    return WM_OK;
+}
+
+extern "C" int wm_ss2d_debug_geometry(int64_t B, int64_t h, int64_t w, int *out6)
+{
+    // developer aid: {row_T, row_ctas, col_seg, ncolseg, col_ctas, cols_first} of the chunk plan
+    if (B <= 0 || h <= 0 || w <= 0 || out6 == nullptr) return WM_EINVAL;
+    const wm::ss2d::Geom g = wm::ss2d::make_geom(B, h, w);
+    out6[0] = g.row_T; out6[1] = g.row_ctas; out6[2] = g.col_seg; out6[3] = g.ncolseg;
+    out6[4] = g.col_ctas; out6[5] = g.cols_first;
     return WM_OK;
 }
 
