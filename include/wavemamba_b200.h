@@ -31,7 +31,7 @@ extern "C" {
 #define WM_ECUDA (-2)     /* a CUDA runtime call or kernel launch failed               */
 #define WM_ENODEVICE (-3) /* no sm_100-class CUDA device is current                     */
 
-#define WM_ABI_VERSION 7
+#define WM_ABI_VERSION 8
 
 typedef void *wm_stream_t;
 
@@ -187,6 +187,26 @@ int wm_head_conv3x3_fwd(const float *x, const float *w3x3, const float *bias, co
  * (PAConv.k2 + sigmoid + mul, :694-697).  In-place on k3out allowed (y == k3out). */
 int wm_paconv_gate_fwd(const float *x, const float *k2_w, const float *k2_b, const float *k3out,
                        float *y, int64_t B, int64_t C, int64_t h, int64_t w, wm_stream_t stream);
+
+/* ---- SKFF band fusion -- SKFF.forward, wavemamba_arch.py:939-959 (called :981) -------------
+ * f0,f1,f2: the HL, LH, HH bands, each (B,32,h,w) contiguous.  out (B,32,h,w) =
+ * (f0*a0 + f1*a1) + f2*a2 with a = softmax over the three bands of fcs_k(PReLU(conv_du(mean_hw(
+ * (f0+f1)+f2)))).  w_du (4,32) = conv_du.0.weight, prelu_weight (1) = conv_du.1.weight,
+ * w_fck (32,4) = fcs.k.weight (all bias-free, as in the reference).
+ * workspace: >= wm_skff_workspace_bytes(B,h,w) bytes, 8-byte aligned (per-CTA pool partials). */
+size_t wm_skff_workspace_bytes(int64_t B, int64_t h, int64_t w);
+int wm_skff_fwd(const float *f0, const float *f1, const float *f2, const float *w_du,
+                const float *prelu_weight, const float *w_fc0, const float *w_fc1,
+                const float *w_fc2, float *out, void *workspace, size_t workspace_bytes, int64_t B,
+                int64_t C, int64_t h, int64_t w, wm_stream_t stream);
+
+/* ---- side inputs -- UNet.ps_down{1,2,3} = PixelUnshuffle(r) + Conv2d(3 r^2, 32, 1),
+ *      wavemamba_arch.py:1014-1025, called :1043-1045 ----------------------------------------
+ * x: (B,3,H,W), H and W multiples of r (2, 4 or 8), 16-byte aligned, W % 4 == 0.
+ * weight (32, 3 r^2) with the unshuffled channel order ci*r*r + dy*r + dx, bias (32) or NULL.
+ * y: (B,32,H/r,W/r).  The unshuffled tensor is never materialised. */
+int wm_ps_down_fwd(const float *x, const float *weight, const float *bias, float *y, int64_t B,
+                   int64_t H, int64_t W, int r, wm_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -420,3 +420,44 @@ def test_stem_and_head_conv(ops, dev):
     want = F.conv2d(f, w2, b2, padding=1) + x
     got = ops.head_conv3x3(f.to(dev), w2.to(dev), b2.to(dev), residual=x.to(dev)).cpu()
     torch.testing.assert_close(got, want, rtol=2e-5, atol=2e-5)
+
+
+# ------------------------------------------------------------------------------- SKFF / ps_down
+def test_skff_golden(ops, dev):
+    """SKFF (ref:939-959) against the reference's own output; 2e-6 abs (pool in fp64 partials)."""
+    from conftest import load_params
+    g = load_golden("skff")
+    sd = om.strip_prefix(load_params(str(g["ckpt"])))
+    pre = str(g["block"]) + "."
+    p = {k[len(pre):]: v.to(dev) for k, v in sd.items() if k.startswith(pre)}
+    got = ops.skff(g["a"].to(dev), g["b"].to(dev), g["c"].to(dev), p["conv_du.0.weight"],
+                   p["conv_du.1.weight"], p["fcs.0.weight"], p["fcs.1.weight"], p["fcs.2.weight"])
+    torch.testing.assert_close(got.cpu(), g["y"], rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("shape", [(1, 32, 8, 8), (2, 32, 25, 37), (1, 32, 135, 240), (3, 32, 1, 1)])
+def test_skff_vs_oracle(ops, dev, shape):
+    g = torch.Generator().manual_seed(5)
+    feats = [torch.randn(*shape, generator=g) for _ in range(3)]
+    p = {"conv_du.0.weight": 0.3 * torch.randn(4, 32, 1, 1, generator=g),
+         "conv_du.1.weight": torch.tensor([0.25]),
+         "fcs.0.weight": torch.randn(32, 4, 1, 1, generator=g),
+         "fcs.1.weight": torch.randn(32, 4, 1, 1, generator=g),
+         "fcs.2.weight": torch.randn(32, 4, 1, 1, generator=g)}
+    want = om.skff(p, feats)
+    got = ops.skff(*[f.to(dev) for f in feats], p["conv_du.0.weight"].to(dev), p["conv_du.1.weight"].to(dev),
+                   p["fcs.0.weight"].to(dev), p["fcs.1.weight"].to(dev), p["fcs.2.weight"].to(dev))
+    torch.testing.assert_close(got.cpu(), want, rtol=1e-5, atol=5e-6)
+
+
+@pytest.mark.parametrize("r", [2, 4, 8])
+@pytest.mark.parametrize("shape", [(1, 3, 16, 24), (2, 3, 64, 40), (1, 3, 200, 304)])
+def test_ps_down_vs_oracle(ops, dev, r, shape):
+    """PixelUnshuffle(r) + 1x1 conv (ref:1014-1025): 2e-5 abs (different summation order)."""
+    g = torch.Generator().manual_seed(r)
+    x = torch.rand(*shape, generator=g)
+    w = torch.randn(32, 3 * r * r, 1, 1, generator=g) * 0.2
+    b = torch.randn(32, generator=g)
+    want = F.conv2d(F.pixel_unshuffle(x, r), w, b)
+    got = ops.ps_down(x.to(dev), w.to(dev), b.to(dev), r)
+    torch.testing.assert_close(got.cpu(), want, rtol=1e-5, atol=2e-5)

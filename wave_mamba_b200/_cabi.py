@@ -12,7 +12,7 @@ from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libwavemamba_b200.so")
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 # name -> (restype, argtypes); mirrors include/wavemamba_b200.h one to one
 SIGNATURES = {
@@ -45,6 +45,9 @@ SIGNATURES = {
     "wm_stem_conv3x3_fwd": (c_int, [c_void_p] * 4 + [c_int64] * 3 + [c_void_p]),
     "wm_head_conv3x3_fwd": (c_int, [c_void_p] * 5 + [c_int64] * 3 + [c_void_p]),
     "wm_paconv_gate_fwd": (c_int, [c_void_p] * 5 + [c_int64] * 4 + [c_void_p]),
+    "wm_skff_workspace_bytes": (c_size_t, [c_int64] * 3),
+    "wm_skff_fwd": (c_int, [c_void_p] * 10 + [c_size_t] + [c_int64] * 4 + [c_void_p]),
+    "wm_ps_down_fwd": (c_int, [c_void_p] * 4 + [c_int64] * 3 + [c_int, c_void_p]),
 }
 
 
@@ -59,16 +62,17 @@ def load() -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("WM_B200_LIB", LIB_PATH)   # developer override: an A/B build variant
+    if not os.path.exists(path):
         raise WaveMambaNativeError(
-            f"{LIB_PATH} is missing. Build it with `python -m wave_mamba_b200.build` "
+            f"{path} is missing. Build it with `python -m wave_mamba_b200.build` "
             "(needs nvcc). wave_mamba_b200 has no CPU or PyTorch fallback.")
-    lib = ctypes.CDLL(LIB_PATH)
+    lib = ctypes.CDLL(path)
     for name, (restype, argtypes) in SIGNATURES.items():
         try:
             fn = getattr(lib, name)
         except AttributeError as exc:
-            raise WaveMambaNativeError(f"{LIB_PATH} does not export {name}; rebuild it") from exc
+            raise WaveMambaNativeError(f"{path} does not export {name}; rebuild it") from exc
         fn.restype = restype
         fn.argtypes = argtypes
     if lib.wm_abi_version() != ABI_VERSION:

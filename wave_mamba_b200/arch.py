@@ -293,7 +293,7 @@ class HFEBlock(nn.Module):
 
 
 class SKFF(nn.Module):
-    """reference :923-959; library ops for now (fusion with the DWT epilogue is 8f-4)."""
+    """reference :923-959 as two streaming kernels (wm_skff_fwd)."""
 
     def __init__(self, in_channels: int, height: int = 3, reduction: int = 8):
         super().__init__()
@@ -302,10 +302,8 @@ class SKFF(nn.Module):
         self.fcs = nn.ModuleList([nn.Conv2d(d, in_channels, 1, bias=False) for _ in range(height)])
 
     def forward(self, feats: List[torch.Tensor]):
-        pooled = (feats[0] + feats[1] + feats[2]).mean(dim=(2, 3), keepdim=True)
-        z = self.conv_du(pooled)
-        att = torch.stack([fc(z) for fc in self.fcs], dim=1).softmax(dim=1)
-        return feats[0] * att[:, 0] + feats[1] * att[:, 1] + feats[2] * att[:, 2]
+        return ops.skff(feats[0], feats[1], feats[2], self.conv_du[0].weight, self.conv_du[1].weight,
+                        self.fcs[0].weight, self.fcs[1].weight, self.fcs[2].weight)
 
 
 # --------------------------------------------------------------------------------------
@@ -379,7 +377,9 @@ class UNet(nn.Module):
             raise ValueError(f"input must be (B,C,H,W) with H and W multiples of 8, got {tuple(x.shape)}")
         with torch.no_grad():
             x = x.contiguous()
-            side = [getattr(self, f"ps_down{l}")(x) for l in (1, 2, 3)]
+            side = [ops.ps_down(x, getattr(self, f"ps_down{l}")[1].weight,
+                                getattr(self, f"ps_down{l}")[1].bias, r)
+                    for l, r in ((1, 2), (2, 4), (3, 8))]                       # :1043-1045
             t = ops.stem_conv3x3(x, self.conv_01.weight, self.conv_01.bias)
             low, h1 = self.down_group1(t, side[0])
             low, h2 = self.down_group2(low, side[1])

@@ -13,7 +13,9 @@
 //
 // 3xTF32: the tensor core reads the top 19 bits of an fp32 word, so the "hi" operand is the raw
 // activation and only lo = a - trunc(a) needs a second copy; weights are split (rna) at prepack.
-//   acc += a_lo*b_hi ; acc += a_hi*b_lo ; acc += a_hi*b_hi     (fp32 accumulate in TMEM)
+//   [acc | acc2] += a_hi*[b_hi | b_lo]  (one MMA, N = 2*COUT) ; acc += a_lo*b_hi  (N = COUT)
+//   fp32 accumulate in TMEM, acc + acc2 in the epilogue.  The SS-mode MMA is bound by reading the
+//   activation operand from shared memory, so the merged N halves the a_hi reads.
 //
 // Persistent: one CTA per SM (217 KB of shared memory, TMEM allocated once) loops over tiles.
 // Per tile: finish the cp.async halo staging -> MMA pipeline over a 3-deep cp.async weight ring
@@ -117,7 +119,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
 template <int COUT, bool GATE>
 constexpr int tmem_cols()
 {
-    constexpr int need = 2 * COUT * (GATE ? 2 : 1);
+    // per M tile: COUT columns for a_hi*b_hi + a_lo*b_hi and COUT columns for a_hi*b_lo
+    constexpr int need = 2 * 2 * COUT * (GATE ? 2 : 1);
     return need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
 }
 
@@ -154,8 +157,11 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
         float4 *dst = wbuf + (c % kStages) * kCF4;
         constexpr int kHalf = 2 * KSC * COUT;               // float4 of hi (or lo) per chunk
         for (int i = tid; i < kCF4; i += kThreads) {
+            // shared layout [kc][hi co 0..COUT-1 | lo co 0..COUT-1]: one B operand of N = 2*COUT rows
+            // (a_hi x [b_hi | b_lo] in a single MMA) whose first COUT rows are the b_hi operand
             const int hl = i / kHalf, r = i - hl * kHalf;
-            const uint32_t d = smem_u32(dst + i);
+            const int kcl = r / COUT, co = r - kcl * COUT;
+            const uint32_t d = smem_u32(dst + (kcl * 2 + hl) * COUT + co);
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + hl * kWF4 + r)
                          : "memory");
         }
@@ -227,14 +233,18 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
-    // instruction descriptor: D=f32, A=B=tf32, both K-major, N = COUT, M = 128
+    // instruction descriptors: D=f32, A=B=tf32, both K-major, M = 128; N = COUT (b_hi only) or
+    // N = 2*COUT ([b_hi | b_lo]: the activation operand is read from shared memory once for both)
     constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(COUT >> 3) << 17) |
                                ((uint32_t)(128 >> 4) << 24);
+    constexpr uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * COUT) >> 3) << 17) |
+                                ((uint32_t)(128 >> 4) << 24);
+    static_assert(2 * COUT <= 256 && (2 * COUT) % 16 == 0, "merged N must be a legal UMMA N");
     // descriptors differ only in the 14-bit start-address field (bytes >> 4): build the bases once
     // and add offsets per MMA (all of this CTA's shared memory is below 256 KB, no carry out)
     const uint64_t a_hi0 = make_desc(smem_u32(xhi), kNPos * 16u, 128u);
     const uint64_t a_lo0 = make_desc(smem_u32(xlo), kNPos * 16u, 128u);
-    const uint64_t b_00 = make_desc(smem_u32(wbuf), COUT * 16u, 128u);
+    const uint64_t b_00 = make_desc(smem_u32(wbuf), 2 * COUT * 16u, 128u);
     uint32_t phase_bits = 0u;                               // bit i: parity to wait for on mbar[i]
     long long tacc[6] = {0, 0, 0, 0, 0, 0}, tprev = clock64();
 #define WM_TICK(k) do { if (a.dbg) { const long long _t = clock64(); tacc[k] += _t - tprev; tprev = _t; } } while (0)
@@ -284,22 +294,20 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
                 // offsets in 16-byte units (= float4 = one (kc, position) or (kc, co) element)
                 const uint32_t shift = (uint32_t)(dy * kHW + dx);
                 const uint64_t b_hi0 = b_00 + (uint32_t)(c % kStages) * kCF4;
-                const uint64_t b_lo0 = b_hi0 + (uint32_t)(2 * KSC * COUT);
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt) {
-                    const uint32_t dcol = tmem_base + (uint32_t)((gate_tap ? 2 * COUT : 0) + mt * COUT);
+                    const uint32_t dcol = tmem_base + (uint32_t)((gate_tap ? 4 * COUT : 0) + mt * 2 * COUT);
                     const uint32_t arow = shift + (uint32_t)mt * 128u;
 #pragma unroll
                     for (int kl = 0; kl < KSC; ++kl) {
                         const int ks = part * KSC + kl;
                         const uint32_t aoff = (uint32_t)(2 * ks) * kNPos + arow;
-                        const uint32_t boff = (uint32_t)(2 * kl) * COUT;
+                        const uint32_t boff = (uint32_t)(2 * kl) * 2 * COUT;
                         const uint64_t a_hi = a_hi0 + aoff, a_lo = a_lo0 + aoff;
-                        const uint64_t b_hi = b_hi0 + boff, b_lo = b_lo0 + boff;
+                        const uint64_t b_hl = b_hi0 + boff;     // rows [0,COUT) = hi, [COUT,2COUT) = lo
                         const uint32_t first = (ks == 0 && (tap == 0 || gate_tap)) ? 0u : 1u;
-                        mma_tf32_ss(dcol, a_lo, b_hi, idesc, first);
-                        mma_tf32_ss(dcol, a_hi, b_lo, idesc, 1u);
-                        mma_tf32_ss(dcol, a_hi, b_hi, idesc, 1u);
+                        mma_tf32_ss(dcol, a_hi, b_hl, idesc2, first);   // cols [0,COUT) += a_hi b_hi, [COUT,2COUT) += a_hi b_lo
+                        mma_tf32_ss(dcol, a_lo, b_hl, idesc, 1u);       // cols [0,COUT) += a_lo b_hi
                     }
                 }
                 asm volatile(
@@ -349,13 +357,22 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
                 for (int g = whalf; g < NG; g += 2) {
                     const int c0 = g * 32;
                     uint32_t acc[32];
-                    tmem_ld32(lane_addr + (uint32_t)(mt * COUT + c0), acc);
+                    {
+                        uint32_t part[32];
+                        tmem_ld32(lane_addr + (uint32_t)(mt * 2 * COUT + c0), acc);
+                        tmem_ld32(lane_addr + (uint32_t)(mt * 2 * COUT + COUT + c0), part);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(part[j]));
+                    }
                     if (GATE) {
-                        uint32_t gt[32];
-                        tmem_ld32(lane_addr + (uint32_t)(2 * COUT + mt * COUT + c0), gt);
+                        uint32_t gt[32], part[32];
+                        tmem_ld32(lane_addr + (uint32_t)(4 * COUT + mt * 2 * COUT + c0), gt);
+                        tmem_ld32(lane_addr + (uint32_t)(4 * COUT + mt * 2 * COUT + COUT + c0), part);
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            const float z = __uint_as_float(gt[j]) + __ldg(a.gate_bias + c0 + j);
+                            const float z = (__uint_as_float(gt[j]) + __uint_as_float(part[j])) +
+                                            __ldg(a.gate_bias + c0 + j);
                             acc[j] = __float_as_uint(__fdividef(__uint_as_float(acc[j]), 1.0f + __expf(-z)));
                         }
                     }

@@ -1,0 +1,263 @@
+// SKFF band fusion and the pixel-unshuffle side inputs for sm_100a -- HBM-bound streaming kernels.
+//
+// SKFF (reference wavemamba_arch.py:923-959), three bands HL / LH / HH of one DWT level:
+//   U = (f0 + f1) + f2 ; S = mean_hw(U) ; Z = PReLU(W_du S) ; a_k = softmax_k(W_k Z) ;
+//   V = (f0 a_0 + f1 a_1) + f2 a_2
+// as two passes over the bands instead of the reference's cat + sum + pool + 3 mul + 2 add:
+//   skff_pool_kernel   reads the three bands once, per-CTA partial sums of U (fp32 per thread,
+//                      fp64 across threads; fixed order => deterministic)
+//   skff_apply_kernel  every CTA re-derives the 3 x 32 attention weights of its image from the
+//                      partial sums (32->4->96 MACs, negligible), then streams V
+// Algorithmic bytes: pool 3 planes read, apply 3 read + 1 written (per B*C*h*w*4).
+//
+// ps_down (reference :1014-1025, :1043-1045): PixelUnshuffle(r) followed by a 1x1 conv
+// (3 r^2 -> 32, bias).  One kernel reads the r x r x 3 patch of an output pixel straight from the
+// image and writes the 32 outputs: the unshuffled copy is never materialised.
+#include "common.cuh"
+
+namespace wm {
+namespace skff {
+
+constexpr int kThreads = 256;
+constexpr int kC = 32;      // channels per band
+constexpr int kMid = 4;     // max(32 / 8, 4)
+
+// partial[(b*C + c) * nblk + blk] = sum over this CTA's slice of plane (b,c) of (f0 + f1) + f2
+__global__ void __launch_bounds__(kThreads)
+skff_pool_kernel(const float *__restrict__ f0, const float *__restrict__ f1,
+                 const float *__restrict__ f2, double *__restrict__ partial, int64_t hw, int vec)
+{
+    const int nblk = gridDim.x;
+    const int64_t plane = blockIdx.y;
+    const float *p0 = f0 + plane * hw, *p1 = f1 + plane * hw, *p2 = f2 + plane * hw;
+    float acc = 0.0f;
+    if (vec) {
+        const int64_t n4 = hw >> 2;
+        float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n4; i += (int64_t)nblk * kThreads) {
+            const float4 a = ld_stream4(p0 + 4 * i), b = ld_stream4(p1 + 4 * i), c = ld_stream4(p2 + 4 * i);
+            a4.x += (a.x + b.x) + c.x; a4.y += (a.y + b.y) + c.y;
+            a4.z += (a.z + b.z) + c.z; a4.w += (a.w + b.w) + c.w;
+        }
+        acc = (a4.x + a4.y) + (a4.z + a4.w);
+    } else {
+        for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < hw; i += (int64_t)nblk * kThreads)
+            acc += (p0[i] + p1[i]) + p2[i];
+    }
+    double d = (double)acc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    __shared__ double ws[kThreads / 32];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = d;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int i = 0; i < kThreads / 32; ++i) t += ws[i];
+        partial[plane * nblk + blockIdx.x] = t;
+    }
+}
+
+// grid (nblk_apply, C, B): CTA = a slice of plane (b, c)
+__global__ void __launch_bounds__(kThreads)
+skff_apply_kernel(const float *__restrict__ f0, const float *__restrict__ f1,
+                  const float *__restrict__ f2, const double *__restrict__ partial, int nblk_pool,
+                  const float *__restrict__ w_du, const float *__restrict__ prelu,
+                  const float *__restrict__ w_fc0, const float *__restrict__ w_fc1,
+                  const float *__restrict__ w_fc2, float *__restrict__ out, int64_t hw, int vec)
+{
+    __shared__ float s_mean[kC];
+    __shared__ float s_z[kMid];
+    __shared__ float s_att[3];
+    const int c = blockIdx.y, b = blockIdx.z;
+    if (threadIdx.x < kC) {
+        const double *pp = partial + ((int64_t)b * kC + threadIdx.x) * nblk_pool;
+        double t = 0.0;
+        for (int i = 0; i < nblk_pool; ++i) t += pp[i];
+        s_mean[threadIdx.x] = (float)(t / (double)hw);        // AdaptiveAvgPool2d(1)  (:948)
+    }
+    __syncthreads();
+    if (threadIdx.x < kMid) {                                  // conv_du: 1x1 32->4, PReLU  (:949)
+        float z = 0.0f;
+        for (int i = 0; i < kC; ++i) z = fmaf(__ldg(w_du + threadIdx.x * kC + i), s_mean[i], z);
+        const float slope = __ldg(prelu);
+        s_z[threadIdx.x] = z >= 0.0f ? z : slope * z;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {                                    // fcs + softmax over the bands (:951-955)
+        float a[3];
+        const float *wf[3] = {w_fc0, w_fc1, w_fc2};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            float v = 0.0f;
+#pragma unroll
+            for (int j = 0; j < kMid; ++j) v = fmaf(__ldg(wf[k] + c * kMid + j), s_z[j], v);
+            a[k] = v;
+        }
+        const float m = fmaxf(a[0], fmaxf(a[1], a[2]));
+        const float e0 = expf(a[0] - m), e1 = expf(a[1] - m), e2 = expf(a[2] - m);
+        const float inv = 1.0f / ((e0 + e1) + e2);
+        s_att[0] = e0 * inv; s_att[1] = e1 * inv; s_att[2] = e2 * inv;
+    }
+    __syncthreads();
+    const float a0 = s_att[0], a1 = s_att[1], a2 = s_att[2];
+    const int64_t plane = (int64_t)b * kC + c;
+    const float *p0 = f0 + plane * hw, *p1 = f1 + plane * hw, *p2 = f2 + plane * hw;
+    float *po = out + plane * hw;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    // V = (f0 a0 + f1 a1) + f2 a2 with separate multiplies and adds, as torch.sum(x * a, dim=1)  (:957)
+    if (vec) {
+        const int64_t n4 = hw >> 2;
+        for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n4; i += stride) {
+            const float4 x = ld_stream4(p0 + 4 * i), y = ld_stream4(p1 + 4 * i), z = ld_stream4(p2 + 4 * i);
+            float4 r;
+            r.x = __fadd_rn(__fadd_rn(__fmul_rn(x.x, a0), __fmul_rn(y.x, a1)), __fmul_rn(z.x, a2));
+            r.y = __fadd_rn(__fadd_rn(__fmul_rn(x.y, a0), __fmul_rn(y.y, a1)), __fmul_rn(z.y, a2));
+            r.z = __fadd_rn(__fadd_rn(__fmul_rn(x.z, a0), __fmul_rn(y.z, a1)), __fmul_rn(z.z, a2));
+            r.w = __fadd_rn(__fadd_rn(__fmul_rn(x.w, a0), __fmul_rn(y.w, a1)), __fmul_rn(z.w, a2));
+            *reinterpret_cast<float4 *>(po + 4 * i) = r;
+        }
+    } else {
+        for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < hw; i += stride)
+            po[i] = __fadd_rn(__fadd_rn(__fmul_rn(p0[i], a0), __fmul_rn(p1[i], a1)), __fmul_rn(p2[i], a2));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// PixelUnshuffle(R) + 1x1 conv 3R^2 -> 32 (+bias): thread = output pixel x 8 output channels
+// ---------------------------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(kThreads)
+ps_down_kernel(const float *__restrict__ x, const float *__restrict__ wgt,
+               const float *__restrict__ bias, float *__restrict__ y, int H, int W)
+{
+    // unshuffled channel index = ci * R*R + dy * R + dx   (torch.nn.PixelUnshuffle)
+    constexpr int CIN = 3 * R * R;
+    constexpr int COG = 8;                        // output channels per thread
+    extern __shared__ float ws[];                 // [CIN][32] transposed weights, then [32] bias
+    for (int i = threadIdx.x; i < 32 * CIN; i += kThreads) {
+        const int co = i / CIN, k = i - co * CIN;
+        ws[k * 32 + co] = __ldg(wgt + i);
+    }
+    if (threadIdx.x < 32) ws[CIN * 32 + threadIdx.x] = bias ? __ldg(bias + threadIdx.x) : 0.0f;
+    __syncthreads();
+    const int h = H / R, w = W / R;
+    const int64_t hw = (int64_t)h * w, HW = (int64_t)H * W;
+    const int b = blockIdx.z;
+    const int cog = blockIdx.y;                   // 0..3: output channels 8*cog ..
+    const int64_t pix = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (pix >= hw) return;
+    const int oy = (int)(pix / w), ox = (int)(pix - (int64_t)oy * w);
+    float acc[COG];
+#pragma unroll
+    for (int j = 0; j < COG; ++j) acc[j] = ws[CIN * 32 + cog * COG + j];
+    const float *xb = x + (int64_t)b * 3 * HW + (int64_t)(oy * R) * W + ox * R;
+#pragma unroll 1
+    for (int ci = 0; ci < 3; ++ci) {
+#pragma unroll
+        for (int dy = 0; dy < R; ++dy) {
+            const float *row = xb + ci * HW + (int64_t)dy * W;
+            float v[R];
+            if (R >= 4) {
+#pragma unroll
+                for (int q = 0; q < R / 4; ++q) {
+                    const float4 t = __ldg(reinterpret_cast<const float4 *>(row) + q);
+                    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+                }
+            } else {
+                const float2 t = __ldg(reinterpret_cast<const float2 *>(row));
+                v[0] = t.x; v[1] = t.y;
+            }
+#pragma unroll
+            for (int dx = 0; dx < R; ++dx) {
+                const float *wr = ws + ((ci * R + dy) * R + dx) * 32 + cog * COG;
+                const float4 w0 = *reinterpret_cast<const float4 *>(wr);
+                const float4 w1 = *reinterpret_cast<const float4 *>(wr + 4);
+                acc[0] = fmaf(v[dx], w0.x, acc[0]); acc[1] = fmaf(v[dx], w0.y, acc[1]);
+                acc[2] = fmaf(v[dx], w0.z, acc[2]); acc[3] = fmaf(v[dx], w0.w, acc[3]);
+                acc[4] = fmaf(v[dx], w1.x, acc[4]); acc[5] = fmaf(v[dx], w1.y, acc[5]);
+                acc[6] = fmaf(v[dx], w1.z, acc[6]); acc[7] = fmaf(v[dx], w1.w, acc[7]);
+            }
+        }
+    }
+    float *yo = y + ((int64_t)b * 32 + cog * COG) * hw + pix;
+#pragma unroll
+    for (int j = 0; j < COG; ++j) yo[(int64_t)j * hw] = acc[j];
+}
+
+template <int R>
+int launch_ps_down(const float *x, const float *wgt, const float *bias, float *y, int64_t B,
+                   int64_t H, int64_t W, cudaStream_t s)
+{
+    constexpr int CIN = 3 * R * R;
+    const size_t smem = sizeof(float) * (CIN * 32 + 32);
+    WM_CUDA_OK(cudaFuncSetAttribute(ps_down_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t hw = (H / R) * (W / R);
+    dim3 grid((unsigned)((hw + kThreads - 1) / kThreads), 4, (unsigned)B);
+    ps_down_kernel<R><<<grid, kThreads, smem, s>>>(x, wgt, bias, y, (int)H, (int)W);
+    WM_LAUNCH_OK("ps_down");
+    return WM_OK;
+}
+
+inline int pool_blocks(int64_t hw)
+{
+    // enough CTAs per plane to fill the machine at B*C = 32 planes, never more than the data needs
+    int64_t want = (hw / 4 + kThreads * 4 - 1) / (kThreads * 4);
+    if (want < 1) want = 1;
+    if (want > 64) want = 64;
+    return (int)want;
+}
+
+}  // namespace skff
+}  // namespace wm
+
+extern "C" size_t wm_skff_workspace_bytes(int64_t B, int64_t h, int64_t w)
+{
+    if (B <= 0 || h <= 0 || w <= 0) return 0;
+    return (size_t)B * wm::skff::kC * wm::skff::pool_blocks(h * w) * sizeof(double);
+}
+
+extern "C" int wm_skff_fwd(const float *f0, const float *f1, const float *f2, const float *w_du,
+                           const float *prelu_weight, const float *w_fc0, const float *w_fc1,
+                           const float *w_fc2, float *out, void *workspace, size_t workspace_bytes,
+                           int64_t B, int64_t C, int64_t h, int64_t w, wm_stream_t stream)
+{
+    using namespace wm;
+    using namespace wm::skff;
+    WM_REQUIRE(B >= 0 && h >= 0 && w >= 0 && B <= 65535, "wm_skff_fwd: bad sizes");
+    WM_REQUIRE(C == kC, "wm_skff_fwd: C=%lld unsupported (32)", (long long)C);
+    if (B == 0 || h == 0 || w == 0) return WM_OK;
+    WM_REQUIRE(f0 && f1 && f2 && w_du && prelu_weight && w_fc0 && w_fc1 && w_fc2 && out,
+               "wm_skff_fwd: null pointer");
+    const int64_t hw = h * w;
+    const int nblk = pool_blocks(hw);
+    WM_REQUIRE(workspace && workspace_bytes >= (size_t)B * kC * nblk * sizeof(double),
+               "wm_skff_fwd: workspace too small");
+    WM_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 7u) == 0, "wm_skff_fwd: workspace must be 8-byte aligned");
+    const int vec = (hw % 4 == 0 && aligned16(f0) && aligned16(f1) && aligned16(f2) && aligned16(out)) ? 1 : 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    double *partial = static_cast<double *>(workspace);
+    skff_pool_kernel<<<dim3(nblk, (unsigned)(B * kC)), kThreads, 0, s>>>(f0, f1, f2, partial, hw, vec);
+    WM_LAUNCH_OK("skff pool");
+    skff_apply_kernel<<<dim3(nblk, kC, (unsigned)B), kThreads, 0, s>>>(f0, f1, f2, partial, nblk, w_du,
+                                                                        prelu_weight, w_fc0, w_fc1,
+                                                                        w_fc2, out, hw, vec);
+    WM_LAUNCH_OK("skff apply");
+    return WM_OK;
+}
+
+extern "C" int wm_ps_down_fwd(const float *x, const float *weight, const float *bias, float *y,
+                              int64_t B, int64_t H, int64_t W, int r, wm_stream_t stream)
+{
+    using namespace wm;
+    WM_REQUIRE(B >= 0 && H >= 0 && W >= 0 && B <= 65535, "wm_ps_down_fwd: bad sizes");
+    WM_REQUIRE(r == 2 || r == 4 || r == 8, "wm_ps_down_fwd: r=%d unsupported (2, 4, 8)", r);
+    WM_REQUIRE(H % r == 0 && W % r == 0, "wm_ps_down_fwd: H and W must be multiples of r");
+    if (B == 0 || H == 0 || W == 0) return WM_OK;
+    WM_REQUIRE(x && weight && y, "wm_ps_down_fwd: null pointer");
+    WM_REQUIRE(aligned16(x) && W % 4 == 0, "wm_ps_down_fwd: x must be 16-byte aligned with W %% 4 == 0");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (r == 2) return skff::launch_ps_down<2>(x, weight, bias, y, B, H, W, s);
+    if (r == 4) return skff::launch_ps_down<4>(x, weight, bias, y, B, H, W, s);
+    return skff::launch_ps_down<8>(x, weight, bias, y, B, H, W, s);
+}

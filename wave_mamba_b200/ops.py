@@ -470,6 +470,55 @@ def head_conv3x3(x, weight, bias=None, residual=None) -> torch.Tensor:
     return y
 
 
+def skff(f0, f1, f2, w_du, prelu_weight, w_fc0, w_fc1, w_fc2) -> torch.Tensor:
+    """SKFF over the three high-frequency bands (reference :939-959): two streaming kernels."""
+    _chk(f0, "f0")
+    B, C, h, w = f0.shape
+    _chk(f1, "f1", (B, C, h, w))
+    _chk(f2, "f2", (B, C, h, w))
+    d = w_du.shape[0]
+    if C != 32 or d != 4:
+        raise ValueError(f"skff: C={C}, d={d} unsupported (32, 4)")
+    w_du = _chk(w_du.reshape(d, C), "w_du")
+    fcs = [_chk(t.reshape(C, d), "w_fc") for t in (w_fc0, w_fc1, w_fc2)]
+    _chk(prelu_weight, "prelu_weight", (1,))
+    out = torch.empty_like(f0)
+    lib = _cabi.load()
+    nbytes = lib.wm_skff_workspace_bytes(B, h, w)
+    ws = torch.empty(max(nbytes // 8, 1), dtype=torch.float64, device=f0.device)
+    with torch.cuda.device(f0.device):
+        rc = lib.wm_skff_fwd(f0.data_ptr(), f1.data_ptr(), f2.data_ptr(), w_du.data_ptr(),
+                             prelu_weight.data_ptr(), fcs[0].data_ptr(), fcs[1].data_ptr(),
+                             fcs[2].data_ptr(), out.data_ptr(), ws.data_ptr(), nbytes, B, C, h, w,
+                             _stream(f0))
+    _cabi.check(rc, "wm_skff_fwd")
+    if B and h and w:
+        _count(2)
+    return out
+
+
+def ps_down(x, weight, bias, r: int) -> torch.Tensor:
+    """PixelUnshuffle(r) + 1x1 conv 3 r^2 -> 32 (reference :1014-1025) without the unshuffled copy."""
+    _chk(x, "x")
+    B, C, H, W = x.shape
+    if C != 3:
+        raise ValueError(f"ps_down: expected 3 input channels, got {C}")
+    weight = _chk(weight.reshape(32, 3 * r * r), "weight")
+    if bias is not None:
+        _chk(bias, "bias", (32,))
+    if H % r or W % r:
+        raise ValueError(f"ps_down: H, W must be multiples of r={r}, got {(H, W)}")
+    y = torch.empty(B, 32, H // r, W // r, dtype=x.dtype, device=x.device)
+    lib = _cabi.load()
+    with torch.cuda.device(x.device):
+        rc = lib.wm_ps_down_fwd(x.data_ptr(), weight.data_ptr(), _ptr(bias), y.data_ptr(), B, H, W, r,
+                                _stream(x))
+    _cabi.check(rc, "wm_ps_down_fwd")
+    if B and H and W:
+        _count(1)
+    return y
+
+
 def set_conv_impl(name: str) -> None:
     """Select the dense-3x3 implementation: "mma" (mma.sync, legacy tensor path) or "tcgen05"
     (5th-gen tensor cores, TMEM accumulators).  Process-wide."""
