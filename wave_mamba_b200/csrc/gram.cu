@@ -5,8 +5,9 @@
 //     default mm mode; the argmin over j (:624) only needs G = X P^T and the two norm vectors.
 //   * CMTAttention: normalize(q) @ normalize(k)^T (:787-790) = (q k^T) / (|q| |k|^T).
 // cuBLAS handles this shape (M=N=32, K = hw up to 2 M) with split-K SGEMMs at ~10 % of the HBM
-// roofline; here every CTA streams a pixel range, keeps a 2x2 register block per thread, sums
-// 128-pixel tiles in fp32 and carries tile sums in fp64; per-CTA partials are reduced in a fixed
+// roofline; here every CTA streams a pixel range through shared memory, multiplies it on the tensor
+// cores (mma.sync TF32 with the 3xTF32 split on both operands => fp32-accurate products), folds the
+// fp32 accumulators into fp64 every 128 pixels per warp; per-CTA partials are reduced in a fixed
 // order by a second tiny kernel => deterministic, and closer to the fp64 truth than SGEMM.
 // Algorithmic bytes: 2 * 32 * hw * 4 per batch item.
 #include "common.cuh"
@@ -27,15 +28,41 @@ __device__ __forceinline__ float sq4(const float4 v, float acc)
     return acc;
 }
 
-__global__ void __launch_bounds__(kThreads)
+// 3xTF32 helpers (fp32-accurate products on the tensor cores; see conv3x3.cu)
+__device__ __forceinline__ void split_tf32(float a, uint32_t &hi, uint32_t &lo)
+{
+    hi = __float_as_uint(a) & 0xffffe000u;
+    lo = __float_as_uint(a - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2])
+{
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
+        "{%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+constexpr int kFlushTiles = 8;       // fp32 accumulators are folded into fp64 every 8 tiles
+constexpr size_t kSmemBytes = sizeof(double) * 8 * kC * kC;   // 64 KB: cross-warp reduction buffer
+static_assert(kSmemBytes >= sizeof(float) * 2 * kC * kRS, "staging tiles must fit the reduction buffer");
+
+// G = X Y^T on the tensor cores.  A CTA streams its pixel range in 128-pixel tiles: registers ->
+// shared [row][pixel] (the next tile's loads are already in flight while this one is consumed);
+// warp w multiplies the two 8-pixel k-steps {w, w+8} of the tile with mma.sync m16n8k8 TF32 and the
+// 3xTF32 split on both operands (2 x 4 fragment tiles = the whole 32x32 output, fp32 accumulate),
+// folds its accumulators into fp64 every 8 tiles (= 128 pixels per warp, as the tile sums of the
+// fp32 version), and the eight warps are summed in a fixed order at the end.
+__global__ void __launch_bounds__(kThreads, 1)
 gram_partial_kernel(const float *__restrict__ x, int64_t x_bstride, const float *__restrict__ y,
                     int64_t y_bstride, double *__restrict__ partial, int64_t hw, int chunk,
                     int nchunks, int vec)
 {
-    __shared__ __align__(16) float xs[kC * kRS];
-    __shared__ __align__(16) float ysm[kC * kRS];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *xs = reinterpret_cast<float *>(smem_raw);          // [32][kRS]
+    float *ysm = xs + kC * kRS;                               // [32][kRS]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int ti = tid >> 4, tj = tid & 15;     // rows {ti, ti+16} of X, rows {tj, tj+16} of Y
+    const int g = lane >> 2, t4 = lane & 3;
     const int64_t b = blockIdx.y;
     const float *xb = x + b * x_bstride;
     const float *yb = y + b * y_bstride;
@@ -43,19 +70,26 @@ gram_partial_kernel(const float *__restrict__ x, int64_t x_bstride, const float 
     int64_t p_end = p_begin + chunk;
     if (p_end > hw) p_end = hw;
 
-    double g00 = 0, g01 = 0, g10 = 0, g11 = 0;
+    float acc[2][4][4];
+    double g64[2][4][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { acc[mt][nt][i] = 0.0f; g64[mt][nt][i] = 0.0; }
     // staging role: warp w loads rows w, w+8, w+16, w+24 (lane = quad); it also owns their norms
     double nx[4] = {0, 0, 0, 0}, ny[4] = {0, 0, 0, 0};
+    float4 ra[4], rc[4];
 
-    for (int64_t p0 = p_begin; p0 < p_end; p0 += kTile) {
+    auto fetch = [&](int64_t p0) {
         const bool full = vec && p0 + kTile <= p_end;
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             const int row = warp + 8 * r;
-            float4 a, c;
             if (full) {
-                a = ld_stream4(xb + (int64_t)row * hw + p0 + 4 * lane);
-                c = ld_stream4(yb + (int64_t)row * hw + p0 + 4 * lane);
+                ra[r] = ld_stream4(xb + (int64_t)row * hw + p0 + 4 * lane);
+                rc[r] = ld_stream4(yb + (int64_t)row * hw + p0 + 4 * lane);
             } else {
                 float av[4], cv[4];
 #pragma unroll
@@ -65,40 +99,88 @@ gram_partial_kernel(const float *__restrict__ x, int64_t x_bstride, const float 
                     av[e] = ok ? __ldg(xb + (int64_t)row * hw + p) : 0.0f;
                     cv[e] = ok ? __ldg(yb + (int64_t)row * hw + p) : 0.0f;
                 }
-                a = make_float4(av[0], av[1], av[2], av[3]);
-                c = make_float4(cv[0], cv[1], cv[2], cv[3]);
+                ra[r] = make_float4(av[0], av[1], av[2], av[3]);
+                rc[r] = make_float4(cv[0], cv[1], cv[2], cv[3]);
             }
-            *reinterpret_cast<float4 *>(xs + row * kRS + 4 * lane) = a;
-            *reinterpret_cast<float4 *>(ysm + row * kRS + 4 * lane) = c;
-            nx[r] += (double)sq4(a, 0.0f);
-            ny[r] += (double)sq4(c, 0.0f);
+        }
+    };
+
+    if (p_begin < p_end) fetch(p_begin);
+    int since_flush = 0;
+    for (int64_t p0 = p_begin; p0 < p_end; p0 += kTile) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int row = warp + 8 * r;
+            *reinterpret_cast<float4 *>(xs + row * kRS + 4 * lane) = ra[r];
+            *reinterpret_cast<float4 *>(ysm + row * kRS + 4 * lane) = rc[r];
+            nx[r] += (double)sq4(ra[r], 0.0f);
+            ny[r] += (double)sq4(rc[r], 0.0f);
         }
         __syncthreads();
-        float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;
-        const float4 *xr0 = reinterpret_cast<const float4 *>(xs + ti * kRS);
-        const float4 *xr1 = reinterpret_cast<const float4 *>(xs + (ti + 16) * kRS);
-        const float4 *yr0 = reinterpret_cast<const float4 *>(ysm + tj * kRS);
-        const float4 *yr1 = reinterpret_cast<const float4 *>(ysm + (tj + 16) * kRS);
-#pragma unroll 4
-        for (int q = 0; q < kTile / 4; ++q) {
-            const float4 u0 = xr0[q], u1 = xr1[q], v0 = yr0[q], v1 = yr1[q];
-            a00 = fmaf(u0.x, v0.x, a00); a00 = fmaf(u0.y, v0.y, a00);
-            a00 = fmaf(u0.z, v0.z, a00); a00 = fmaf(u0.w, v0.w, a00);
-            a01 = fmaf(u0.x, v1.x, a01); a01 = fmaf(u0.y, v1.y, a01);
-            a01 = fmaf(u0.z, v1.z, a01); a01 = fmaf(u0.w, v1.w, a01);
-            a10 = fmaf(u1.x, v0.x, a10); a10 = fmaf(u1.y, v0.y, a10);
-            a10 = fmaf(u1.z, v0.z, a10); a10 = fmaf(u1.w, v0.w, a10);
-            a11 = fmaf(u1.x, v1.x, a11); a11 = fmaf(u1.y, v1.y, a11);
-            a11 = fmaf(u1.z, v1.z, a11); a11 = fmaf(u1.w, v1.w, a11);
+        if (p0 + kTile < p_end) fetch(p0 + kTile);          // in flight while this tile is multiplied
+#pragma unroll
+        for (int ksi = 0; ksi < 2; ++ksi) {
+            const int pk = (warp + 8 * ksi) * 8;               // first pixel of the k-step
+            uint32_t ahi[2][4], alo[2][4], bhi[4][2], blo[4][2];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                const float *ap = xs + (g + 16 * mt) * kRS + pk + t4;
+                split_tf32(ap[0], ahi[mt][0], alo[mt][0]);
+                split_tf32(ap[8 * kRS], ahi[mt][1], alo[mt][1]);
+                split_tf32(ap[4], ahi[mt][2], alo[mt][2]);
+                split_tf32(ap[8 * kRS + 4], ahi[mt][3], alo[mt][3]);
+            }
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const float *bp = ysm + (g + 8 * nt) * kRS + pk + t4;
+                split_tf32(bp[0], bhi[nt][0], blo[nt][0]);
+                split_tf32(bp[4], bhi[nt][1], blo[nt][1]);
+            }
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    mma_tf32(acc[mt][nt], alo[mt], bhi[nt]);
+                    mma_tf32(acc[mt][nt], ahi[mt], blo[nt]);
+                    mma_tf32(acc[mt][nt], ahi[mt], bhi[nt]);
+                }
         }
-        g00 += (double)a00; g01 += (double)a01; g10 += (double)a10; g11 += (double)a11;
+        if (++since_flush == kFlushTiles || p0 + kTile >= p_end) {
+            since_flush = 0;
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        g64[mt][nt][i] += (double)acc[mt][nt][i];
+                        acc[mt][nt][i] = 0.0f;
+                    }
+        }
         __syncthreads();
     }
+
+    // ---- fixed-order sum over the eight warps ------------------------------------------------
+    double *red = reinterpret_cast<double *>(smem_raw);       // [8 warps][32*32]; staging tiles are dead
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int row = g + 16 * mt + ((i & 2) ? 8 : 0), col = 8 * nt + 2 * t4 + (i & 1);
+                red[warp * kC * kC + row * kC + col] = g64[mt][nt][i];
+            }
+    __syncthreads();
     double *out = partial + ((int64_t)b * nchunks + blockIdx.x) * kOut;
-    out[ti * kC + tj] = g00;
-    out[ti * kC + tj + 16] = g01;
-    out[(ti + 16) * kC + tj] = g10;
-    out[(ti + 16) * kC + tj + 16] = g11;
+#pragma unroll
+    for (int j = 0; j < kC * kC / kThreads; ++j) {
+        const int o = tid + j * kThreads;
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) t += red[w * kC * kC + o];
+        out[o] = t;
+    }
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         double sx = nx[r], sy = ny[r];
@@ -128,8 +210,8 @@ gram_reduce_kernel(const double *__restrict__ partial, float *__restrict__ out, 
 
 inline void plan(int64_t hw, int &chunk, int &nchunks)
 {
-    // about two CTAs per SM, chunk a multiple of the tile
-    const int64_t target = (int64_t)sm_count() * 2;
+    // one CTA per SM (64 KB of shared memory, ~180 registers), chunk a multiple of the tile
+    const int64_t target = (int64_t)sm_count();
     int64_t c = (hw + target - 1) / target;
     c = (c + kTile - 1) / kTile * kTile;
     if (c < kTile) c = kTile;
@@ -172,7 +254,9 @@ extern "C" int wm_gram32_fwd(const float *x, int64_t x_bstride, const float *y, 
     const int vec = (hw % 4 == 0 && aligned16(x) && aligned16(y) && x_bstride % 4 == 0 &&
                      y_bstride % 4 == 0) ? 1 : 0;
     dim3 grid(nchunks, (unsigned)B);
-    gram_partial_kernel<<<grid, kThreads, 0, s>>>(x, x_bstride, y, y_bstride,
+    WM_CUDA_OK(cudaFuncSetAttribute(gram_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)kSmemBytes));
+    gram_partial_kernel<<<grid, kThreads, kSmemBytes, s>>>(x, x_bstride, y, y_bstride,
                                                   static_cast<double *>(workspace), hw, chunk,
                                                   nchunks, vec);
     WM_LAUNCH_OK("gram partial");
