@@ -46,7 +46,7 @@ struct Args {
 };
 
 template <int CIN, int COUT, int PRE, int POST>
-__global__ void __launch_bounds__(kThreads, CIN <= 32 ? 3 : 2)
+__global__ void __launch_bounds__(kThreads, (CIN <= 32 && PRE != kPreGate) ? 3 : 2)
 pixel_kernel(const Args a)
 {
     __shared__ __align__(16) float wt[CIN * COUT];  // [ci][co]
@@ -73,17 +73,26 @@ pixel_kernel(const Args a)
     const float *xc = a.xc ? a.xc + b * XCH * hw : nullptr;
     for (int64_t p = (int64_t)blockIdx.x * kThreads + tid; p < hw;
          p += (int64_t)gridDim.x * kThreads) {
+        // every input load of the pixel is issued before anything consumes one (the kernel is
+        // bound by load latency); the residuals of an output group are fetched before its FMAs
         float xv[CIN];
+        float x2[PRE == kPreGate ? CIN : 1];
 #pragma unroll
         for (int ci = 0; ci < CIN; ++ci) {
-            if (PRE == kPreGate) {
-                xv[ci] = gelu_erf(__ldg(xb + ci * hw + p)) * __ldg(xb + (CIN + ci) * hw + p);
-            } else {
-                xv[ci] = __ldg(xb + ci * hw + p);
+            xv[ci] = __ldg(xb + ci * hw + p);
+            if (PRE == kPreGate) x2[ci] = __ldg(xb + (CIN + ci) * hw + p);
+        }
+        if (PRE != kPreGate) {
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci) {
                 if (xa) xv[ci] += __ldg(xa + ci * hw + p);
                 if (xb2) xv[ci] += __ldg(xb2 + ci * hw + p);
                 if (xc) xv[ci] += __ldg(xc + ci * hw + p);
             }
+        }
+        if (PRE == kPreGate) {
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci) xv[ci] = gelu_erf(xv[ci]) * x2[ci];
         }
         if (PRE == kPreLN || PRE == kPreLNMul) {
             float mu = 0.0f;
@@ -103,7 +112,11 @@ pixel_kernel(const Args a)
         }
 #pragma unroll 1
         for (int g = 0; g < COUT / 8; ++g) {
-            float acc[8];
+            float acc[8], rv[8];
+            if (a.res) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) rv[j] = __ldg(a.res + (b * COUT + g * 8 + j) * hw + p);
+            }
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[j] = pb[g * 8 + j];
 #pragma unroll
@@ -121,7 +134,7 @@ pixel_kernel(const Args a)
                 float v = acc[j];
                 if (POST == kPostSilu) v = silu(v);
                 if (POST == kPostSigmoidMul) v = __fdividef(a.mul_out[o + j * hw], 1.0f + __expf(-v));
-                if (a.res) v = fmaf(a.res[o + j * hw], rs[g * 8 + j], v);
+                if (a.res) v = fmaf(rv[j], rs[g * 8 + j], v);
                 a.y[o + j * hw] = v;
             }
         }
@@ -189,7 +202,10 @@ lfss_out_pair_kernel(const Args a)
             xv[i] = fmaf((xv[i] - mu) * rstd, lw[c0 + i], lb[c0 + i]) * __ldg(mz + i * hw + p);
 #pragma unroll 1
         for (int g = 0; g < COUT / 8; ++g) {
-            float acc[8];
+            float acc[8], rv[4];
+            const int64_t o = (b * COUT + g * 8 + side * 4) * hw + p;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rv[j] = __ldg(a.res + o + j * hw);   // in flight under the FMAs
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
 #pragma unroll
@@ -204,13 +220,12 @@ lfss_out_pair_kernel(const Args a)
             // pair reduction; lane `side` then writes outputs g*8 + side*4 .. +3
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 1);
-            const int64_t o = (b * COUT + g * 8 + side * 4) * hw + p;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int co = g * 8 + side * 4 + j;
                 float v = side ? acc[4 + j] : acc[j];
                 if (live) {
-                    v = fmaf(a.res[o + j * hw], rs[co], v);
+                    v = fmaf(rv[j], rs[co], v);
                     a.y[o + j * hw] = v;
                 }
             }

@@ -68,20 +68,40 @@ __device__ __forceinline__ void ln_column(float *col, const float *lnw, const fl
 }
 
 // Load the 32-channel halo tile of image b at (ty0-1, tx0-1) into xs[c][pos]; zeros outside.
+// 4-byte cp.async with zero fill: no register staging, every load of the tile in flight at once
+// (the scalar-load form was bound by global latency).  Warp w takes halo rows w, w+8, ... of the
+// C*10 (channel, row) pairs; lanes run along the row (34 floats: lanes 0,1 also take the tail).
+// The caller waits with halo_wait() before its first __syncthreads.
 __device__ __forceinline__ void load_halo32(const float *__restrict__ x, float *xs, int64_t b,
                                             int C, int h, int w, int ty0, int tx0)
 {
     const int64_t hw = (int64_t)h * w;
-    for (int idx = threadIdx.x; idx < C * kHalo; idx += kThreads) {
-        const int c = idx / kHalo, pos = idx - c * kHalo;
-        const int py = pos / kHW, px = pos - py * kHW;
-        const int gy = ty0 - 1 + py, gx = tx0 - 1 + px;
-        float v = 0.0f;
-        if (gy >= 0 && gy < h && gx >= 0 && gx < w)
-            v = __ldg(x + ((int64_t)b * C + c) * hw + (int64_t)gy * w + gx);
-        xs[c * kXP + pos] = v;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t xs_base = (uint32_t)__cvta_generic_to_shared(xs);
+    const float *xb = x + (int64_t)b * C * hw;
+    const int gx0 = tx0 - 1 + lane, gx1 = tx0 + 31 + lane;
+    const bool okx0 = gx0 >= 0 && gx0 < w;
+    const bool okx1 = lane < 2 && gx1 < w;
+    for (int r = warp; r < C * kHH; r += kThreads / 32) {
+        const int c = r / kHH, py = r - c * kHH;
+        const int gy = ty0 - 1 + py;
+        const bool oky = gy >= 0 && gy < h;
+        const float *row = xb + (int64_t)c * hw + (int64_t)(oky ? gy : 0) * w;
+        const uint32_t dst = xs_base + (uint32_t)(c * kXP + py * kHW + lane) * 4u;
+        const bool ok0 = oky && okx0;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(ok0 ? row + gx0 : xb),
+                     "r"(ok0 ? 4u : 0u)
+                     : "memory");
+        if (lane < 2) {
+            const bool ok1 = oky && okx1;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + 32u * 4u),
+                         "l"(ok1 ? row + gx1 : xb), "r"(ok1 ? 4u : 0u)
+                         : "memory");
+        }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
 }
+__device__ __forceinline__ void halo_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------
 // y = dw3x3( pw1x1( ln?(x) ) ),  Cin = 32, Cout = 32*G
@@ -124,6 +144,7 @@ pw_dw_kernel(const float *__restrict__ x, const float *__restrict__ ln_w,
         const int c = i / (kXP - kHalo), r = i - c * (kXP - kHalo);
         xs[c * kXP + kHalo + r] = 0.0f;
     }
+    halo_wait();
     __syncthreads();
 
     if (ln_w != nullptr) {
@@ -258,6 +279,7 @@ dw_act_pw_kernel(const float *__restrict__ x, const float *__restrict__ dw_w,
     if (tid < C) { pb[tid] = __ldg(pw_b + tid); dwb[tid] = __ldg(dw_b + tid); }
     for (int i = tid; i < C * 9; i += kThreads) dww[i] = __ldg(dw_w + i);
     load_halo32(x, xs, b, C, h, w, ty0, tx0);
+    halo_wait();
     __syncthreads();
 
     const int col = tid & 31;
@@ -417,6 +439,7 @@ stem_conv3x3_kernel(const float *__restrict__ x, const float *__restrict__ wgt,
     }
     if (tid < COUT) bs[tid] = bias ? __ldg(bias + tid) : 0.0f;
     load_halo32(x, xs, b, CIN, h, w, ty0, tx0);
+    halo_wait();
     __syncthreads();
     const int col = tid & 31, row = tid >> 5;
     float acc[COUT];
@@ -462,6 +485,7 @@ head_conv3x3_kernel(const float *__restrict__ x, const float *__restrict__ wgt,
     for (int i = tid; i < CIN * 9; i += kThreads)
         wt[i] = make_float4(__ldg(wgt + i), __ldg(wgt + CIN * 9 + i), __ldg(wgt + 2 * CIN * 9 + i), 0.0f);
     load_halo32(x, xs, b, CIN, h, w, ty0, tx0);
+    halo_wait();
     __syncthreads();
     const int col = tid & 31, row = tid >> 5;
     float a0 = bias ? __ldg(bias + 0) : 0.0f, a1 = bias ? __ldg(bias + 1) : 0.0f,
