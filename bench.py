@@ -256,6 +256,8 @@ class OpTimer:
         wrap("lfss_z", lambda a, k, o: nb(a[0]) + nb(o))
         wrap("lfss_out", lambda a, k, o: nb(a[0], a[1], a[6]) + nb(o) + nb(*k.get("extra", ())))
         wrap("ss2d_dirs", lambda a, k, o: 2 * nb(a[0]))           # 512*B*L
+        wrap("skff", lambda a, k, o: 2 * nb(a[0], a[1], a[2]) + nb(o))   # pool reads 3, apply reads 3 + writes 1
+        wrap("ps_down", lambda a, k, o: nb(a[0]) + nb(o))
 
     def summary(self, peak_gbs):
         agg = {}

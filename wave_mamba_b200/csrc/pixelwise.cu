@@ -202,10 +202,7 @@ lfss_out_pair_kernel(const Args a)
             xv[i] = fmaf((xv[i] - mu) * rstd, lw[c0 + i], lb[c0 + i]) * __ldg(mz + i * hw + p);
 #pragma unroll 1
         for (int g = 0; g < COUT / 8; ++g) {
-            float acc[8], rv[4];
-            const int64_t o = (b * COUT + g * 8 + side * 4) * hw + p;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) rv[j] = __ldg(a.res + o + j * hw);   // in flight under the FMAs
+            float acc[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
 #pragma unroll
@@ -220,12 +217,13 @@ lfss_out_pair_kernel(const Args a)
             // pair reduction; lane `side` then writes outputs g*8 + side*4 .. +3
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 1);
+            const int64_t o = (b * COUT + g * 8 + side * 4) * hw + p;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int co = g * 8 + side * 4 + j;
                 float v = side ? acc[4 + j] : acc[j];
                 if (live) {
-                    v = fmaf(rv[j], rs[co], v);
+                    v = fmaf(a.res[o + j * hw], rs[co], v);
                     a.y[o + j * hw] = v;
                 }
             }
