@@ -407,10 +407,14 @@ def main():
         roofline = {
             "kernel": "ss2d_dirs (pass 1 + carry + pass 2; the 4-way sum is fused into lfss_out)", "bound": "hbm",
             "achieved": ss["achieved_gbs"], "peak": peak_gbs, "unit": "GB/s",
-            "frac": ss["frac_of_hbm_peak"], "traffic": None,
-            "traffic_note": "ncu (profiles/): a 4K level-1 call moves 2.25 GB (pass 1) + 4.37 GB "
-                            "(pass 2) of DRAM traffic vs 1.06 GB algorithmic: two passes x two scan "
-                            "orientations re-read x, four direction planes are written",
+            "frac": ss["frac_of_hbm_peak"],
+            # ncu --set full, profiles/r1_ncu_ss2d_v4_level1.txt: dram__bytes_read.sum + dram__bytes_write.sum
+            # of pass 1 (2.148 + 0.084 GB) and pass 2 (2.264 + 2.118 GB) of ONE 4K level-1 call
+            # (1 x 64 x 1080 x 1920), whose algorithmic bytes are 1.062 GB
+            "traffic": 6.614e9, "traffic_unit": "bytes per level-1 call (algorithmic: 1.062e9)",
+            "traffic_note": "two passes x two scan orientations re-read x (4 x 0.53 GB each pass) and "
+                            "pass 2 writes four direction planes (2.12 GB) that lfss_out sums; it "
+                            "overlaps the instruction-bound compute",
             "peak_source": peak_src,
             "bytes_definition": "512*B*L per call (x read once + merged y written once), SURVEY 8d",
             "ms_per_image": round(ss["ms_total"] / args.steps, 4),

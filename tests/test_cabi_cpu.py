@@ -144,3 +144,26 @@ print(net.load_state_dict(sd, strict=True))
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "All keys matched" in out.stdout
+
+
+def test_ss2d_chunk_plan_is_consistent(lib_path):
+    """The SS2D chunk planner (host logic, no GPU): chunk lengths are whole tiles, the chunks cover
+    every position of both scan orientations, and the workspace holds the planes + aggregates."""
+    from wave_mamba_b200 import _cabi
+    lib = _cabi.load()
+    for B, h, w in [(1, 1080, 1920), (1, 540, 960), (1, 270, 480), (4, 200, 300), (4, 50, 75),
+                    (8, 256, 256), (2, 135, 240), (1, 9, 13), (1, 1, 1), (3, 17, 64)]:
+        out = (ctypes.c_int * 6)()
+        assert lib.wm_ss2d_debug_geometry(B, h, w, out) == 0
+        row_T, row_ctas, col_seg, ncolseg, col_ctas, cols_first = list(out)
+        L = h * w
+        assert row_T % 16 == 0 and row_T >= 64
+        assert col_seg % 16 == 0 and col_seg * ncolseg >= h and col_seg * (ncolseg - 1) < h
+        row_chunks = -(-L // row_T)
+        assert row_ctas == -(-row_chunks // 4)
+        assert col_ctas == -(-w // 4) * ncolseg
+        assert cols_first in (0, 1)
+        max_chunks = max(row_chunks, w * ncolseg)
+        need = 4 * B * 64 * L * 4 + 2 * B * 4 * max_chunks * 1024 * 4
+        assert lib.wm_ss2d_core_workspace_bytes(B, h, w) >= need
+    assert lib.wm_ss2d_debug_geometry(0, 8, 8, (ctypes.c_int * 6)()) != 0
