@@ -31,7 +31,7 @@ extern "C" {
 #define WM_ECUDA (-2)     /* a CUDA runtime call or kernel launch failed               */
 #define WM_ENODEVICE (-3) /* no sm_100-class CUDA device is current                     */
 
-#define WM_ABI_VERSION 8
+#define WM_ABI_VERSION 9
 
 typedef void *wm_stream_t;
 
@@ -207,6 +207,18 @@ int wm_skff_fwd(const float *f0, const float *f1, const float *f2, const float *
  * y: (B,32,H/r,W/r).  The unshuffled tensor is never materialised. */
 int wm_ps_down_fwd(const float *x, const float *weight, const float *bias, float *y, int64_t B,
                    int64_t H, int64_t W, int r, wm_stream_t stream);
+
+/* ---- image I/O edges of the inference loop -- img2tensor + "/255." + check_image_size
+ *      (basicsr/utils/img_util.py:9-33, inference_wavemamba.py:28-36,102-106) and the crop +
+ *      tensor2img on the way out (inference_wavemamba.py:112-113, img_util.py:36-98) -----------
+ * img: (B,H,W,3) uint8, BGR (a cv2 image), 4-byte aligned.  out: (B,3,Hp,Wp) float32 RGB in [0,1],
+ * reflect-padded at the bottom / right (Hp-H < H, Wp-W < W), 16-byte aligned.  Bit-exact. */
+int wm_img_u8_to_f32_fwd(const uint8_t *img, float *out, int64_t B, int64_t H, int64_t W, int64_t Hp,
+                         int64_t Wp, wm_stream_t stream);
+/* x: (B,3,Hs,Ws) float32 RGB.  img: (B,h,w,3) uint8 BGR = round_half_even(clamp(x[:, :, :h, :w], 0, 1)
+ * * 255).  Bit-exact with tensor2img. */
+int wm_img_f32_to_u8_fwd(const float *x, uint8_t *img, int64_t B, int64_t h, int64_t w, int64_t Hs,
+                         int64_t Ws, wm_stream_t stream);
 
 #ifdef __cplusplus
 }

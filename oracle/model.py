@@ -344,3 +344,24 @@ def psnr_y(img: "np.ndarray", ref: "np.ndarray", crop_border: int = 1) -> float:
     if mse == 0:
         return float("inf")
     return float(20.0 * math.log10(255.0 / math.sqrt(mse)))
+
+
+# --------------------------------------------------------------------------------------
+# image I/O edges of the inference loop (reference inference_wavemamba.py:101-113)
+# --------------------------------------------------------------------------------------
+def img_u8_to_f32(img_bgr_u8: torch.Tensor, window: int = 128) -> torch.Tensor:
+    """(B,H,W,3) uint8 BGR -> (B,3,Hp,Wp) float32 RGB: ``img2tensor`` (basicsr/utils/img_util.py:9-33:
+    BGR->RGB, HWC->CHW, float), ``/ 255.`` (inference_wavemamba.py:102) and ``check_image_size``
+    (inference_wavemamba.py:28-36: reflect pad bottom/right to a multiple of ``window``)."""
+    x = img_bgr_u8.flip(-1).permute(0, 3, 1, 2).float() / 255.
+    h, w = x.shape[2:]
+    pad_h = (window - h % window) % window
+    pad_w = (window - w % window) % window
+    return F.pad(x, (0, pad_w, 0, pad_h), "reflect")
+
+
+def img_f32_to_u8(x: torch.Tensor, h: int, w: int) -> torch.Tensor:
+    """(B,3,Hs,Ws) float32 RGB -> (B,h,w,3) uint8 BGR: the crop at inference_wavemamba.py:112 and
+    ``tensor2img`` (img_util.py:36-98: clamp to [0,1], HWC, RGB->BGR, ``(x * 255.0).round()``, uint8)."""
+    t = x[:, :, :h, :w].float().clamp(0, 1).permute(0, 2, 3, 1).flip(-1)
+    return torch.from_numpy((t.numpy() * 255.0).round().astype("uint8"))

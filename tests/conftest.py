@@ -19,7 +19,7 @@ def pytest_configure(config):
 
 def load_golden(name):
     with np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False) as z:
-        return {k: (torch.from_numpy(z[k]) if z[k].dtype.kind == "f" or z[k].dtype.kind == "i"
+        return {k: (torch.from_numpy(z[k]) if z[k].dtype.kind in "fiu"
                     else str(z[k])) for k in z.files}
 
 

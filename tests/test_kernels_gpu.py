@@ -461,3 +461,53 @@ def test_ps_down_vs_oracle(ops, dev, r, shape):
     want = F.conv2d(F.pixel_unshuffle(x, r), w, b)
     got = ops.ps_down(x.to(dev), w.to(dev), b.to(dev), r)
     torch.testing.assert_close(got.cpu(), want, rtol=1e-5, atol=2e-5)
+
+
+# ------------------------------------------------------------------------------- image I/O edges
+@pytest.mark.parametrize("shape,window", [((1, 16, 24), 8), ((2, 50, 37), 8), ((1, 200, 300), 128),
+                                          ((1, 135, 241), 128), ((1, 256, 256), 128)])
+def test_img_u8_to_f32_bit_exact(ops, dev, shape, window):
+    """img2tensor + /255. + reflect pad (inference_wavemamba.py:28-36,101-106): bit-exact."""
+    g = torch.Generator().manual_seed(3)
+    B, H, W = shape
+    img = torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8)
+    want = om.img_u8_to_f32(img, window)
+    got = ops.img_u8_to_f32(img.to(dev), window)
+    assert got.shape == want.shape
+    assert torch.equal(got.cpu(), want)
+
+
+@pytest.mark.parametrize("shape,crop", [((1, 16, 24), (16, 24)), ((2, 56, 40), (50, 37)),
+                                        ((1, 256, 384), (200, 300)), ((1, 128, 256), (128, 256))])
+def test_img_f32_to_u8_bit_exact(ops, dev, shape, crop):
+    """crop + tensor2img (img_util.py:36-98): clamp, *255, round half to even, BGR: bit-exact."""
+    g = torch.Generator().manual_seed(4)
+    B, Hs, Ws = shape
+    x = torch.rand(B, 3, Hs, Ws, generator=g) * 1.4 - 0.2          # exercises both clamps
+    x.view(-1)[:256] = (torch.arange(256, dtype=torch.float32) + 0.5) / 255.0   # exact .5 ties
+    want = om.img_f32_to_u8(x, *crop)
+    got = ops.img_f32_to_u8(x.to(dev), *crop)
+    assert torch.equal(got.cpu(), want)
+
+
+def test_enhance_bgr_u8_matches_float_path(dev):
+    """The uint8 entry point = the reference loop body: same uint8 image as converting on the host."""
+    import wave_mamba_b200 as wm
+    from conftest import load_params
+    net = wm.WaveMamba(in_chn=3, wf=32, n_l_blocks=[1, 2, 4], n_h_blocks=[1, 1, 2], ffn_scale=2.0)
+    net.load_state_dict(load_params("LOLv1"), strict=True)
+    net = net.to(dev).eval()
+    g = torch.Generator().manual_seed(9)
+    img = (torch.rand(100, 150, 3, generator=g) * 60).to(torch.uint8)
+    got = wm.enhance_bgr_u8(net, img, window=128).cpu()
+    with torch.no_grad():
+        y = net.restoration_network(om.img_u8_to_f32(img[None], 128).to(dev)).cpu()
+    want = om.img_f32_to_u8(y, 100, 150)[0]
+    assert got.shape == (100, 150, 3) and torch.equal(got, want)
+
+
+def test_img_io_edges_golden(ops, dev):
+    """The device conversions against the reference's own img2tensor / check_image_size / tensor2img."""
+    g = load_golden("imgio")
+    assert torch.equal(ops.img_u8_to_f32(g["img"][None].to(dev), 128).cpu(), g["x"])
+    assert torch.equal(ops.img_f32_to_u8(g["y"].to(dev), 100, 150).cpu()[0], g["out_img"])

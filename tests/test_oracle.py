@@ -125,3 +125,11 @@ def test_float64_arbiter_model_agrees_with_fp32(params_cache):
     p64 = om.cast_params(params_cache(g["ckpt"]), torch.float64)
     y64 = om.unet_forward(p64, g["x"].double())
     assert (y64 - g["y"].double()).abs().max() < 5e-5
+
+
+def test_img_io_edges_match_reference():
+    """oracle img_u8_to_f32 / img_f32_to_u8 vs the reference's img2tensor + /255. + check_image_size
+    and crop + tensor2img (golden from tools/make_golden_imgio.py): bit-exact."""
+    g = load_golden("imgio")
+    assert torch.equal(om.img_u8_to_f32(g["img"][None], 128), g["x"])
+    assert torch.equal(om.img_f32_to_u8(g["y"], 100, 150)[0], g["out_img"])

@@ -12,7 +12,7 @@ from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libwavemamba_b200.so")
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 # name -> (restype, argtypes); mirrors include/wavemamba_b200.h one to one
 SIGNATURES = {
@@ -48,6 +48,8 @@ SIGNATURES = {
     "wm_skff_workspace_bytes": (c_size_t, [c_int64] * 3),
     "wm_skff_fwd": (c_int, [c_void_p] * 10 + [c_size_t] + [c_int64] * 4 + [c_void_p]),
     "wm_ps_down_fwd": (c_int, [c_void_p] * 4 + [c_int64] * 3 + [c_int, c_void_p]),
+    "wm_img_u8_to_f32_fwd": (c_int, [c_void_p] * 2 + [c_int64] * 5 + [c_void_p]),
+    "wm_img_f32_to_u8_fwd": (c_int, [c_void_p] * 2 + [c_int64] * 5 + [c_void_p]),
 }
 
 

@@ -519,6 +519,56 @@ def ps_down(x, weight, bias, r: int) -> torch.Tensor:
     return y
 
 
+def _chk_u8(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or t.dtype != torch.uint8:
+        raise TypeError(f"{name}: expected a uint8 torch.Tensor")
+    if not t.is_cuda:
+        raise _cabi.WaveMambaNativeError(f"{name} is on {t.device}; wave_mamba_b200 runs on CUDA only")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: expected a contiguous tensor")
+    return t
+
+
+def img_u8_to_f32(img: torch.Tensor, window: int = 128) -> torch.Tensor:
+    """(B,H,W,3) uint8 BGR -> (B,3,Hp,Wp) float32 RGB in [0,1], reflect-padded up to multiples of
+    `window`: img2tensor + /255. + check_image_size of inference_wavemamba.py, bit-exact."""
+    _chk_u8(img, "img")
+    if img.dim() != 4 or img.shape[3] != 3:
+        raise ValueError(f"img: expected (B,H,W,3), got {tuple(img.shape)}")
+    B, H, W, _ = img.shape
+    Hp, Wp = -(-H // window) * window, -(-W // window) * window
+    if B and H and W and (Hp - H >= H or Wp - W >= W):
+        raise ValueError("reflect padding must be smaller than the image")
+    out = torch.empty(B, 3, Hp, Wp, dtype=torch.float32, device=img.device)
+    lib = _cabi.load()
+    with torch.cuda.device(img.device):
+        rc = lib.wm_img_u8_to_f32_fwd(img.data_ptr(), out.data_ptr(), B, H, W, Hp, Wp, _stream(img))
+    _cabi.check(rc, "wm_img_u8_to_f32_fwd")
+    if B and H and W:
+        _count(1)
+    return out
+
+
+def img_f32_to_u8(x: torch.Tensor, h: Optional[int] = None, w: Optional[int] = None) -> torch.Tensor:
+    """(B,3,Hs,Ws) float32 RGB -> (B,h,w,3) uint8 BGR: crop + tensor2img, bit-exact."""
+    _chk(x, "x")
+    if x.dim() != 4 or x.shape[1] != 3:
+        raise ValueError(f"x: expected (B,3,H,W), got {tuple(x.shape)}")
+    B, _, Hs, Ws = x.shape
+    h = Hs if h is None else h
+    w = Ws if w is None else w
+    if h > Hs or w > Ws:
+        raise ValueError("crop larger than the source")
+    img = torch.empty(B, h, w, 3, dtype=torch.uint8, device=x.device)
+    lib = _cabi.load()
+    with torch.cuda.device(x.device):
+        rc = lib.wm_img_f32_to_u8_fwd(x.data_ptr(), img.data_ptr(), B, h, w, Hs, Ws, _stream(x))
+    _cabi.check(rc, "wm_img_f32_to_u8_fwd")
+    if B and h and w:
+        _count(1)
+    return img
+
+
 def set_conv_impl(name: str) -> None:
     """Select the dense-3x3 implementation: "mma" (mma.sync, legacy tensor path) or "tcgen05"
     (5th-gen tensor cores, TMEM accumulators).  Process-wide."""
