@@ -31,7 +31,7 @@ extern "C" {
 #define WM_ECUDA (-2)     /* a CUDA runtime call or kernel launch failed               */
 #define WM_ENODEVICE (-3) /* no sm_100-class CUDA device is current                     */
 
-#define WM_ABI_VERSION 9
+#define WM_ABI_VERSION 10
 
 typedef void *wm_stream_t;
 
@@ -174,6 +174,15 @@ int wm_conv3x3_fwd(const float *in_a, int64_t a_bstride, int64_t Ca, const float
                    int64_t b_bstride, const int *chan_map, const void *packed, const float *bias,
                    const float *gate_bias, float *out, int64_t B, int64_t Cin, int64_t Cout,
                    int64_t h, int64_t w, wm_stream_t stream);
+/* Same, with channel-quad tensor layouts (B, C/4, h, w, 4) for the input (in_c4, needs Ca == Cin)
+ * and/or the output (out_c4): the intermediate between PAConv.k3 and k4 is only ever read by the
+ * next conv, and 16-byte (4-channel) elements are what its shared-memory operand layout wants.
+ * tcgen05 implementation only. */
+int wm_conv3x3_ex_fwd(const float *in_a, int64_t a_bstride, int64_t Ca, const float *in_b,
+                   int64_t b_bstride, const int *chan_map, const void *packed, const float *bias,
+                   const float *gate_bias, float *out, int64_t B, int64_t Cin, int64_t Cout,
+                   int64_t h, int64_t w, int in_c4, int out_c4,
+                     wm_stream_t stream);
 
 /* Stem / head 3x3 convs with 3 channels on one side (direct FFMA, fp32):
  *   stem: UNet.conv_01 (:1026,1048)  x (B,3,h,w)  -> y (B,32,h,w) = conv3x3(x) + bias

@@ -511,3 +511,29 @@ def test_img_io_edges_golden(ops, dev):
     g = load_golden("imgio")
     assert torch.equal(ops.img_u8_to_f32(g["img"][None].to(dev), 128).cpu(), g["x"])
     assert torch.equal(ops.img_f32_to_u8(g["y"].to(dev), 100, 150).cpu()[0], g["out_img"])
+
+
+@pytest.mark.parametrize("shape", [(2, 21, 50), (1, 7, 32), (1, 40, 96)])
+def test_conv3x3_channel_quad_layout(ops, dev, shape):
+    """PAConv k3 (+k2 gate, gathered second input) -> k4 through the (B, C/4, h, w, 4) intermediate:
+    identical to the NCHW path bit for bit (same arithmetic, different addressing) and within 2e-5
+    of the fp64 reference (reference :694-698)."""
+    ops.set_conv_impl("tcgen05")
+    g = torch.Generator().manual_seed(35)
+    B, h, w = shape
+    x, per = _rand(B, 32, h, w, g=g), _rand(B, 32, h, w, g=g)
+    idx = torch.stack([torch.randperm(32, generator=g) for _ in range(B)]).to(torch.int32)
+    k3, k4 = _rand(64, 64, 3, 3, g=g, s=0.1), _rand(32, 64, 3, 3, g=g, s=0.1)
+    k2w, k2b = _rand(64, 64, 1, 1, g=g, s=0.2), _rand(64, g=g, s=0.1)
+    a = dict(x_b=per.to(dev), chan_map=idx.to(dev), gate_w=k2w.to(dev), gate_b=k2b.to(dev))
+    t_nchw = ops.conv3x3(x.to(dev), k3.to(dev), **a)
+    t_c4 = ops.conv3x3(x.to(dev), k3.to(dev), out_c4=True, **a)
+    assert t_c4.shape == (B, 16, h, w, 4)
+    assert torch.equal(t_c4.permute(0, 1, 4, 2, 3).reshape(B, 64, h, w), t_nchw)
+    y_nchw = ops.conv3x3(t_nchw, k4.to(dev))
+    y_c4 = ops.conv3x3(t_c4, k4.to(dev), in_c4=True)
+    assert torch.equal(y_c4, y_nchw)
+    cat = torch.cat([x, torch.stack([per[b][idx[b].long()] for b in range(B)])], dim=1).double()
+    t = F.conv2d(cat, k3.double(), None, padding=1) * torch.sigmoid(F.conv2d(cat, k2w.double(), k2b.double()))
+    want = F.conv2d(t, k4.double(), None, padding=1)
+    assert (y_c4.cpu().double() - want).abs().max().item() <= 2e-5 * max(1.0, want.abs().max().item())

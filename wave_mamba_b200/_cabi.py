@@ -12,7 +12,7 @@ from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libwavemamba_b200.so")
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 # name -> (restype, argtypes); mirrors include/wavemamba_b200.h one to one
 SIGNATURES = {
@@ -42,6 +42,8 @@ SIGNATURES = {
     "wm_conv3x3_prepack": (c_int, [c_void_p] * 3 + [c_int64] * 2 + [c_void_p]),
     "wm_conv3x3_fwd": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64] + [c_void_p] * 5 +
                        [c_int64] * 5 + [c_void_p]),
+    "wm_conv3x3_ex_fwd": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64] + [c_void_p] * 5 +
+                          [c_int64] * 5 + [c_int, c_int, c_void_p]),
     "wm_stem_conv3x3_fwd": (c_int, [c_void_p] * 4 + [c_int64] * 3 + [c_void_p]),
     "wm_head_conv3x3_fwd": (c_int, [c_void_p] * 5 + [c_int64] * 3 + [c_void_p]),
     "wm_paconv_gate_fwd": (c_int, [c_void_p] * 5 + [c_int64] * 4 + [c_void_p]),

@@ -199,9 +199,11 @@ class PAConv(nn.Module):
 
     def forward(self, x, x_b=None, chan_map=None):
         """x (+ x_b gathered by chan_map) are the 2*dim input channels (the reference's cat)."""
+        # t is only read by k4: keep it in the channel-quad layout both tcgen05 kernels prefer
+        c4 = ops.get_conv_impl() == "tcgen05"
         t = ops.conv3x3(x, self.k3.weight, x_b=x_b, chan_map=chan_map, gate_w=self.k2.weight,
-                        gate_b=self.k2.bias)                                   # :694-697
-        return ops.conv3x3(t, self.k4.weight)                                  # :698
+                        gate_b=self.k2.bias, out_c4=c4)                        # :694-697
+        return ops.conv3x3(t, self.k4.weight, in_c4=c4)                        # :698
 
 
 def nearest_channel_index(x: torch.Tensor, perception: torch.Tensor) -> torch.Tensor:

@@ -280,7 +280,8 @@ int prepack(const float *w3x3, const float *w1x1, void *packed, int64_t Cin, int
             cudaStream_t s);
 int forward(const float *in_a, int64_t a_bstride, int64_t Ca, const float *in_b, int64_t b_bstride,
             const int *chan_map, const void *packed, const float *bias, const float *gate_bias,
-            float *out, int64_t B, int64_t Cin, int64_t Cout, int64_t h, int64_t w, cudaStream_t s);
+            float *out, int64_t B, int64_t Cin, int64_t Cout, int64_t h, int64_t w, int in_c4, int out_c4,
+            cudaStream_t s);
 }  // namespace tc5
 namespace conv {
 static int g_impl = 1;   // 0: mma.sync m16n8k8 (legacy tensor path), 1: tcgen05 + TMEM (default)
@@ -338,10 +339,11 @@ extern "C" int wm_conv3x3_prepack(const float *w3x3, const float *w1x1, void *pa
                         Cin, Cout, (cudaStream_t)stream);
 }
 
-extern "C" int wm_conv3x3_fwd(const float *in_a, int64_t a_bstride, int64_t Ca, const float *in_b,
-                              int64_t b_bstride, const int *chan_map, const void *packed,
-                              const float *bias, const float *gate_bias, float *out, int64_t B,
-                              int64_t Cin, int64_t Cout, int64_t h, int64_t w, wm_stream_t stream)
+extern "C" int wm_conv3x3_ex_fwd(const float *in_a, int64_t a_bstride, int64_t Ca, const float *in_b,
+                                 int64_t b_bstride, const int *chan_map, const void *packed,
+                                 const float *bias, const float *gate_bias, float *out, int64_t B,
+                                 int64_t Cin, int64_t Cout, int64_t h, int64_t w, int in_c4, int out_c4,
+                                 wm_stream_t stream)
 {
     using namespace wm;
     using namespace wm::conv;
@@ -356,8 +358,9 @@ extern "C" int wm_conv3x3_fwd(const float *in_a, int64_t a_bstride, int64_t Ca, 
     if (g_impl == 1) {
         const void *tc = static_cast<const char *>(packed) + mma_part_bytes(Cin, Cout, gate_bias != nullptr);
         return tc5::forward(in_a, a_bstride, Ca, in_b, b_bstride, chan_map, tc, bias, gate_bias, out,
-                            B, Cin, Cout, h, w, (cudaStream_t)stream);
+                            B, Cin, Cout, h, w, in_c4, out_c4, (cudaStream_t)stream);
     }
+    WM_REQUIRE(!in_c4 && !out_c4, "wm_conv3x3_ex_fwd: channel-quad layouts need the tcgen05 implementation");
     Args a;
     a.in_a = in_a; a.a_bstride = a_bstride; a.Ca = (int)Ca; a.in_b = in_b; a.b_bstride = b_bstride;
     a.chan_map = chan_map; a.packed = static_cast<const float4 *>(packed); a.bias = bias;
@@ -373,4 +376,13 @@ extern "C" int wm_conv3x3_fwd(const float *in_a, int64_t a_bstride, int64_t Ca, 
     if (Cin == 32 && Cout == 32) return launch<32, 32, false>(a, B, s);
     WM_REQUIRE(false, "wm_conv3x3_fwd: Cin=%lld Cout=%lld unsupported", (long long)Cin, (long long)Cout);
     return WM_EINVAL;
+}
+
+extern "C" int wm_conv3x3_fwd(const float *in_a, int64_t a_bstride, int64_t Ca, const float *in_b,
+                              int64_t b_bstride, const int *chan_map, const void *packed,
+                              const float *bias, const float *gate_bias, float *out, int64_t B,
+                              int64_t Cin, int64_t Cout, int64_t h, int64_t w, wm_stream_t stream)
+{
+    return wm_conv3x3_ex_fwd(in_a, a_bstride, Ca, in_b, b_bstride, chan_map, packed, bias, gate_bias, out,
+                             B, Cin, Cout, h, w, 0, 0, stream);
 }

@@ -54,6 +54,9 @@ struct Args {
     const float *gate_bias;
     float *out;
     int h, w;
+    // channel-quad layouts (B, C/4, h, w, 4): a 16-byte cp.async / store moves the 4 channels of one
+    // K chunk at once.  in_c4 needs Ca == CIN (no second input); used between PAConv.k3 and k4.
+    int in_c4, out_c4;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -179,6 +182,34 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
         const int gx0 = tx0 - 1 + lane, gx1 = tx0 + 31 + lane;
         const bool okx0 = gx0 >= 0 && gx0 < w;
         const bool okx1 = lane < 2 && gx1 < w;
+        if (a.in_c4) {
+            // (kc, position) elements are 16 contiguous bytes on both sides: one cp.async each
+            const float4 *src4 = reinterpret_cast<const float4 *>(a.in_a + b * a.a_bstride);
+#pragma unroll 1
+            for (int kc = warp; kc < KC; kc += kThreads / 32) {
+                const float4 *plane4 = src4 + (int64_t)kc * hw;
+                const uint32_t dst_k = xhi_base + (uint32_t)(kc * kNPos) * 16u;
+#pragma unroll
+                for (int py = 0; py < kR + 2; ++py) {
+                    const int gy = ty0 - 1 + py;
+                    const bool oky = gy >= 0 && gy < h;
+                    const float4 *row = plane4 + (int64_t)(oky ? gy : 0) * w;
+                    const uint32_t dst = dst_k + (uint32_t)(py * kHW + lane) * 16u;
+                    const bool ok0 = oky && okx0;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst),
+                                 "l"(ok0 ? row + gx0 : plane4), "r"(ok0 ? 16u : 0u)
+                                 : "memory");
+                    if (lane < 2) {
+                        const bool ok1 = oky && okx1;
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + 32u * 16u),
+                                     "l"(ok1 ? row + gx1 : plane4), "r"(ok1 ? 16u : 0u)
+                                     : "memory");
+                    }
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            return;
+        }
 #pragma unroll 1
         for (int c = warp; c < CIN; c += kThreads / 32) {
             const float *plane;
@@ -376,7 +407,20 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
                             acc[j] = __float_as_uint(__fdividef(__uint_as_float(acc[j]), 1.0f + __expf(-z)));
                         }
                     }
-                    if (ok) {
+                    if (ok && a.out_c4) {
+                        float4 *o4 = reinterpret_cast<float4 *>(a.out) +
+                                     (b * (COUT / 4) + c0 / 4) * hw + (int64_t)gy * w + gx;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            float v[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                v[j] = __uint_as_float(acc[4 * q + j]);
+                                if (!GATE && a.bias) v[j] += __ldg(a.bias + c0 + 4 * q + j);
+                            }
+                            o4[(int64_t)q * hw] = make_float4(v[0], v[1], v[2], v[3]);
+                        }
+                    } else if (ok) {
                         float *o = a.out + (b * COUT + c0) * hw + (int64_t)gy * w + gx;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
@@ -472,10 +516,15 @@ int prepack(const float *w3x3, const float *w1x1, void *packed, int64_t Cin, int
 
 int forward(const float *in_a, int64_t a_bstride, int64_t Ca, const float *in_b, int64_t b_bstride,
             const int *chan_map, const void *packed, const float *bias, const float *gate_bias,
-            float *out, int64_t B, int64_t Cin, int64_t Cout, int64_t h, int64_t w, cudaStream_t s)
+            float *out, int64_t B, int64_t Cin, int64_t Cout, int64_t h, int64_t w, int in_c4, int out_c4,
+            cudaStream_t s)
 {
     WM_REQUIRE((h + kR - 1) / kR <= 65535, "wm_conv3x3_fwd: image too tall");
+    WM_REQUIRE(!in_c4 || (Ca == Cin && aligned16(in_a) && a_bstride % 4 == 0),
+               "wm_conv3x3_ex_fwd: the channel-quad input layout needs a single 16-byte aligned input");
+    WM_REQUIRE(!out_c4 || aligned16(out), "wm_conv3x3_ex_fwd: channel-quad output must be 16-byte aligned");
     Args a;
+    a.in_c4 = in_c4; a.out_c4 = out_c4;
     a.dbg = g_dbg;
     a.in_a = in_a; a.a_bstride = a_bstride; a.Ca = (int)Ca; a.in_b = in_b; a.b_bstride = b_bstride;
     a.chan_map = chan_map; a.packed = static_cast<const float4 *>(packed); a.bias = bias;

@@ -130,6 +130,12 @@ __device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c)
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
     return d;
 }
+__device__ __forceinline__ f32x2 fadd2(f32x2 a, f32x2 b)
+{
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
 __device__ __forceinline__ f32x2 ex2_2(f32x2 v)
 {
     float lo, hi;
@@ -186,6 +192,34 @@ __device__ __forceinline__ float softplus_fast(float v)
     p = fmaf(p, t, 1.0f);
     const float sp = fmaf(2.0f * s, p, fmaxf(v, 0.0f));
     return v > 20.0f ? v : sp;
+}
+
+// Two softplus values at once on the packed FP32 pipe (same arithmetic per element as
+// softplus_fast: identical results, ~2/3 of the instructions).
+__device__ __forceinline__ void softplus_fast2(float v0, float v1, float &o0, float &o1)
+{
+    const float e0 = ex2_approx(-fabsf(v0) * 1.4426950408889634f);
+    const float e1 = ex2_approx(-fabsf(v1) * 1.4426950408889634f);
+    const f32x2 e = pack2(e0, e1);
+    float d0, d1;
+    unpack2(fadd2(e, pack2(2.0f, 2.0f)), d0, d1);
+    // s = e / (2 + e) as e * rcp(2 + e), exactly what __fdividef does for these magnitudes
+    float r0, r1;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d0));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d1));
+    const f32x2 sv = fmul2(e, pack2(r0, r1));
+    const f32x2 t = fmul2(sv, sv);
+    f32x2 p = ffma2(t, pack2(0.07692307692f, 0.07692307692f), pack2(0.09090909091f, 0.09090909091f));
+    p = ffma2(p, t, pack2(0.11111111111f, 0.11111111111f));
+    p = ffma2(p, t, pack2(0.14285714286f, 0.14285714286f));
+    p = ffma2(p, t, pack2(0.2f, 0.2f));
+    p = ffma2(p, t, pack2(0.33333333333f, 0.33333333333f));
+    p = ffma2(p, t, pack2(1.0f, 1.0f));
+    const f32x2 sp = ffma2(fadd2(sv, sv), p, pack2(fmaxf(v0, 0.0f), fmaxf(v1, 0.0f)));
+    float s0, s1;
+    unpack2(sp, s0, s1);
+    o0 = v0 > 20.0f ? v0 : s0;
+    o1 = v1 > 20.0f ? v1 : s1;
 }
 
 struct TileGeom {
@@ -588,7 +622,9 @@ __device__ __forceinline__ void run_cta(const Params &prm, const Geom &g, const 
                     const float r0 = fmaf(dw1[2 * q], dlow.y, dw0[2 * q] * dlow.x) + dbias[2 * q];
                     const float r1 =
                         fmaf(dw1[2 * q + 1], dlow.y, dw0[2 * q + 1] * dlow.x) + dbias[2 * q + 1];
-                    dq[q] = make_float4(softplus_fast(r0), u0, softplus_fast(r1), u1);
+                    float sp0, sp1;
+                    softplus_fast2(r0, r1, sp0, sp1);
+                    dq[q] = make_float4(sp0, u0, sp1, u1);
                 }
             }
         }

@@ -379,14 +379,24 @@ def conv3x3_pack(w3x3: torch.Tensor, w1x1: Optional[torch.Tensor] = None) -> tor
     return packed
 
 
-def conv3x3(x_a, w3x3, bias=None, x_b=None, chan_map=None, gate_w=None, gate_b=None) -> torch.Tensor:
+def conv3x3(x_a, w3x3, bias=None, x_b=None, chan_map=None, gate_w=None, gate_b=None,
+            in_c4: bool = False, out_c4: bool = False) -> torch.Tensor:
     """Dense 3x3 conv, stride 1, zero pad 1 (3xTF32 tensor-core implicit GEMM, fp32-accurate).
+
+    ``in_c4`` / ``out_c4``: x_a / the result use the channel-quad layout (B, C/4, h, w, 4) (tcgen05
+    implementation only; an intermediate that only the next conv reads, e.g. PAConv k3 -> k4).
 
     Input channels = x_a's channels followed by x_b's (optionally gathered per batch item through
     ``chan_map`` (B, Cb) int32) -- the reference's torch.cat is not materialised.
     ``gate_w``/``gate_b``: PAConv stage A, returns conv3x3(x) * sigmoid(conv1x1(x; gate_w) + gate_b)."""
-    _chk_planes(x_a, "x_a")
-    B, Ca, h, w = x_a.shape
+    if in_c4:
+        _chk(x_a, "x_a")
+        if x_a.dim() != 5 or x_a.shape[4] != 4 or x_b is not None:
+            raise ValueError("in_c4: x_a must be (B, C/4, h, w, 4) and the only input")
+        B, Ca, h, w = x_a.shape[0], x_a.shape[1] * 4, x_a.shape[2], x_a.shape[3]
+    else:
+        _chk_planes(x_a, "x_a")
+        B, Ca, h, w = x_a.shape
     Cout, Cin = w3x3.shape[0], w3x3.shape[1]
     Cb = Cin - Ca
     if Cb < 0 or (Cb > 0 and x_b is None):
@@ -408,14 +418,16 @@ def conv3x3(x_a, w3x3, bias=None, x_b=None, chan_map=None, gate_w=None, gate_b=N
     if gate_b is not None:
         _chk(gate_b, "gate_b", (Cout,))
     packed = conv3x3_pack(w3x3, gate_w)
-    out = torch.empty(B, Cout, h, w, device=x_a.device, dtype=torch.float32)
+    out = torch.empty((B, Cout // 4, h, w, 4) if out_c4 else (B, Cout, h, w), device=x_a.device,
+                      dtype=torch.float32)
     lib = _cabi.load()
     with torch.cuda.device(x_a.device):
-        rc = lib.wm_conv3x3_fwd(x_a.data_ptr(), x_a.stride(0) if B > 1 else Ca * h * w, Ca,
-                                _ptr(x_b), 0 if x_b is None else (x_b.stride(0) if B > 1 else 0),
-                                _ptr(chan_map), packed.data_ptr(), _ptr(bias), _ptr(gate_b),
-                                out.data_ptr(), B, Cin, Cout, h, w, _stream(x_a))
-    _cabi.check(rc, "wm_conv3x3_fwd")
+        rc = lib.wm_conv3x3_ex_fwd(x_a.data_ptr(), x_a.stride(0) if B > 1 else Ca * h * w, Ca,
+                                   _ptr(x_b), 0 if x_b is None else (x_b.stride(0) if B > 1 else 0),
+                                   _ptr(chan_map), packed.data_ptr(), _ptr(bias), _ptr(gate_b),
+                                   out.data_ptr(), B, Cin, Cout, h, w, int(in_c4), int(out_c4),
+                                   _stream(x_a))
+    _cabi.check(rc, "wm_conv3x3_ex_fwd")
     _count(1)
     return out
 
