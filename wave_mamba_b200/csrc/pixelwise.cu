@@ -146,7 +146,10 @@ pixel_kernel(const Args a)
 // shuffle, * silu(z)), accumulates its half of the 64->32 out_proj for all 32 outputs, and the
 // pair is reduced with shuffles.  Half the registers per thread of the one-thread form (no
 // spills, 2x the resident warps) -- this kernel is bound by global-load latency.
-__global__ void __launch_bounds__(kThreads, 3)
+#ifndef WM_LFSS_OUT_MINB
+#define WM_LFSS_OUT_MINB 3
+#endif
+__global__ void __launch_bounds__(kThreads, WM_LFSS_OUT_MINB)
 lfss_out_pair_kernel(const Args a)
 {
     constexpr int CIN = 64, HALF = 32, COUT = 32;

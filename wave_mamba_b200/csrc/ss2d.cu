@@ -418,7 +418,11 @@ __device__ __forceinline__ void scan_step(const StepIn<FINAL> &in, float *ysp, f
         f32x2 acc = pack2(0.0f, 0.0f);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
+#ifdef WM_DBG_NOMUFU   // timing experiment only (wrong results): the recurrence without its exps
+            const f32x2 a = fmul2(dt2, A2[c][j]);
+#else
             const f32x2 a = ex2_2(fmul2(dt2, A2[c][j]));
+#endif
             hst[c][j] = ffma2(a, hst[c][j], fmul2(du2, bb[j]));
             if (FINAL) acc = ffma2(hst[c][j], cc[j], acc);
         }
@@ -642,7 +646,11 @@ __device__ __forceinline__ void run_cta(const Params &prm, const Geom &g, const 
                 cur.load(dd0, pj0);
 #pragma unroll
                 for (int e = 0; e < kTP; ++e) {
+#ifndef WM_DBG_NOLDS    // (-DWM_DBG_NOLDS: timing experiment only, step inputs loaded once per tile)
                     if (e + 1 < kTP) nxt.load(dd0 + (e + 1) * DP * kDD, pj0 + (e + 1) * DP * kPJ);
+#else
+                    nxt = cur;
+#endif
                     scan_step<FINAL>(cur, ys0 + e * DP, hst, A2, sdt, my_skip, half);
                     cur = nxt;
                 }
