@@ -141,6 +141,92 @@ pixel_kernel(const Args a)
     }
 }
 
+// Two adjacent pixels per thread (8-byte loads and stores; hw even).  The 1x1 weights reach the
+// FMAs as broadcast LDS.128 whose cost is the 512 bytes per warp they return to the register file,
+// not the 16 unique bytes: with two pixels per thread every weight load feeds 16 FMAs instead of 8,
+// which halves the LSU return traffic that bounds the one-pixel form at COUT >= 32 outputs.
+template <int CIN, int COUT, int PRE, int POST>
+__global__ void __launch_bounds__(kThreads, 2)
+pixel2_kernel(const Args a)
+{
+    static_assert(PRE == kPreNone || PRE == kPreLN, "two-pixel form: plain or LayerNorm prologue");
+    __shared__ __align__(16) float wt[CIN * COUT];  // [ci][co]
+    __shared__ float pb[COUT], rs[COUT], lw[CIN], lb[CIN];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < CIN * COUT; i += kThreads) {
+        const int co = i / CIN, ci = i - co * CIN;
+        wt[ci * COUT + co] = __ldg(a.w + i);
+    }
+    for (int i = tid; i < COUT; i += kThreads) {
+        pb[i] = a.b ? __ldg(a.b + i) : 0.0f;
+        rs[i] = a.res_scale ? __ldg(a.res_scale + i) : 1.0f;
+    }
+    if (PRE == kPreLN)
+        for (int i = tid; i < CIN; i += kThreads) { lw[i] = __ldg(a.ln_w + i); lb[i] = __ldg(a.ln_b + i); }
+    __syncthreads();
+
+    const int64_t hw = a.hw, npair = hw >> 1;
+    const int64_t b = blockIdx.y;
+    const float *xb = a.x + b * CIN * hw;
+    for (int64_t q = (int64_t)blockIdx.x * kThreads + tid; q < npair; q += (int64_t)gridDim.x * kThreads) {
+        const int64_t p = 2 * q;
+        float xv[2][CIN];
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) {
+            const float2 v = __ldg(reinterpret_cast<const float2 *>(xb + ci * hw + p));
+            xv[0][ci] = v.x; xv[1][ci] = v.y;
+        }
+        if (PRE == kPreLN) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                float mu = 0.0f;
+#pragma unroll
+                for (int ci = 0; ci < CIN; ++ci) mu += xv[k][ci];
+                mu *= (1.0f / CIN);
+                float var = 0.0f;
+#pragma unroll
+                for (int ci = 0; ci < CIN; ++ci) { const float dlt = xv[k][ci] - mu; var = fmaf(dlt, dlt, var); }
+                var *= (1.0f / CIN);
+                const float rstd = 1.0f / sqrtf(var + a.eps);
+#pragma unroll
+                for (int ci = 0; ci < CIN; ++ci) xv[k][ci] = fmaf((xv[k][ci] - mu) * rstd, lw[ci], lb[ci]);
+            }
+        }
+#pragma unroll 1
+        for (int g = 0; g < COUT / 8; ++g) {
+            float acc[2][8];
+            float2 rv[8];
+            if (a.res) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    rv[j] = __ldg(reinterpret_cast<const float2 *>(a.res + (b * COUT + g * 8 + j) * hw + p));
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { acc[0][j] = pb[g * 8 + j]; acc[1][j] = pb[g * 8 + j]; }
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci) {
+                const float4 w0 = *reinterpret_cast<const float4 *>(wt + ci * COUT + g * 8);
+                const float4 w1 = *reinterpret_cast<const float4 *>(wt + ci * COUT + g * 8 + 4);
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    acc[k][0] = fmaf(xv[k][ci], w0.x, acc[k][0]); acc[k][1] = fmaf(xv[k][ci], w0.y, acc[k][1]);
+                    acc[k][2] = fmaf(xv[k][ci], w0.z, acc[k][2]); acc[k][3] = fmaf(xv[k][ci], w0.w, acc[k][3]);
+                    acc[k][4] = fmaf(xv[k][ci], w1.x, acc[k][4]); acc[k][5] = fmaf(xv[k][ci], w1.y, acc[k][5]);
+                    acc[k][6] = fmaf(xv[k][ci], w1.z, acc[k][6]); acc[k][7] = fmaf(xv[k][ci], w1.w, acc[k][7]);
+                }
+            }
+            const int64_t o = (b * COUT + g * 8) * hw + p;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float v0 = acc[0][j], v1 = acc[1][j];
+                if (POST == kPostSilu) { v0 = silu(v0); v1 = silu(v1); }
+                if (a.res) { v0 = fmaf(rv[j].x, rs[g * 8 + j], v0); v1 = fmaf(rv[j].y, rs[g * 8 + j], v1); }
+                *reinterpret_cast<float2 *>(a.y + o + j * hw) = make_float2(v0, v1);
+            }
+        }
+    }
+}
+
 // SS2D tail (wm_lfss_out_fwd) with TWO threads per pixel: each lane of a pair owns 32 of the 64
 // scan channels (sum of the four direction planes, LayerNorm statistics exchanged with one
 // shuffle, * silu(z)), accumulates its half of the 64->32 out_proj for all 32 outputs, and the
@@ -272,11 +358,29 @@ inline bool dims_ok(int64_t B, int64_t h, int64_t w)
     return B >= 0 && B <= 65535 && h >= 0 && w >= 0 && h < (1 << 24) && w < (1 << 24);
 }
 
+inline bool aligned8(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; }
+
+// the two-pixel form when the layout allows 8-byte accesses, else the one-pixel form
+template <int CIN, int COUT, int PRE, int POST>
+int launch2(const Args &a, int64_t B, cudaStream_t s, const char *what);
+
 template <int CIN, int COUT, int PRE, int POST>
 int launch(const Args &a, int64_t B, cudaStream_t s, const char *what)
 {
     dim3 grid(flat_grid(a.hw), (unsigned)B);
     pixel_kernel<CIN, COUT, PRE, POST><<<grid, kThreads, 0, s>>>(a);
+    WM_LAUNCH_OK(what);
+    return WM_OK;
+}
+
+template <int CIN, int COUT, int PRE, int POST>
+int launch2(const Args &a, int64_t B, cudaStream_t s, const char *what)
+{
+    const bool ok = a.hw % 2 == 0 && aligned8(a.x) && aligned8(a.y) && (!a.res || aligned8(a.res)) &&
+                    !a.xa && !a.xb_ && !a.xc;
+    if (!ok) return launch<CIN, COUT, PRE, POST>(a, B, s, what);
+    dim3 grid(flat_grid(a.hw / 2), (unsigned)B);
+    pixel2_kernel<CIN, COUT, PRE, POST><<<grid, kThreads, 0, s>>>(a);
     WM_LAUNCH_OK(what);
     return WM_OK;
 }
@@ -317,7 +421,7 @@ extern "C" int wm_pw_fwd(const float *x, const float *pw_w, const float *pw_b, i
     a.x = x; a.w = pw_w; a.b = pw_b; a.res = residual; a.res_scale = res_scale; a.y = y;
     a.hw = h * w;
     cudaStream_t s = (cudaStream_t)stream;
-    if (gate_mode == 0 && Cin == 32 && Cout == 32) return launch<32, 32, kPreNone, kPostNone>(a, B, s, "pw 32->32");
+    if (gate_mode == 0 && Cin == 32 && Cout == 32) return launch2<32, 32, kPreNone, kPostNone>(a, B, s, "pw 32->32");
     if (gate_mode == 0 && Cin == 32 && Cout == 64) return launch<32, 64, kPreNone, kPostNone>(a, B, s, "pw 32->64");
     if (gate_mode == 0 && Cin == 64 && Cout == 32) return launch<64, 32, kPreNone, kPostNone>(a, B, s, "pw 64->32");
     if (gate_mode == 1 && Cin == 32 && Cout == 32) return launch<32, 32, kPreGate, kPostNone>(a, B, s, "pw gate 32->32");
@@ -348,7 +452,7 @@ extern "C" int wm_lfss_z_fwd(const float *x, const float *ln_w, const float *ln_
     WM_REQUIRE(x && ln_w && ln_b && w_z && zs, "wm_lfss_z_fwd: null pointer");
     Args a = {};
     a.x = x; a.ln_w = ln_w; a.ln_b = ln_b; a.eps = eps; a.w = w_z; a.y = zs; a.hw = h * w;
-    return launch<32, 64, kPreLN, kPostSilu>(a, B, (cudaStream_t)stream, "lfss z");
+    return launch2<32, 64, kPreLN, kPostSilu>(a, B, (cudaStream_t)stream, "lfss z");
 }
 
 extern "C" int wm_lfss_out_fwd(const float *y, const float *ya, const float *yb, const float *yc,
