@@ -13,6 +13,8 @@
 // channels, GELU gate, elementwise multiply -- runs there); outputs are produced 8 at a time
 // with the weight row broadcast from shared memory as two 128-bit loads per input channel.
 // Global accesses are coalesced along the pixel index for every channel plane.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace wm {
@@ -320,6 +322,104 @@ lfss_out_pair_kernel(const Args a)
     }
 }
 
+// Two-pixel variant of lfss_out_pair_kernel (hw even, 8-byte aligned tensors): each lane of a pair
+// owns 32 channels of TWO adjacent pixels, so every broadcast weight load feeds 16 FMAs.  Half of the
+// one-pixel kernel's time was the LSU return traffic of those weight loads.
+__global__ void __launch_bounds__(kThreads, 2)
+lfss_out_pair2_kernel(const Args a)
+{
+    constexpr int CIN = 64, HALF = 32, COUT = 32;
+    __shared__ __align__(16) float wt[CIN * COUT];  // [ci][co]
+    __shared__ float rs[COUT], lw[CIN], lb[CIN];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < CIN * COUT; i += kThreads) {
+        const int co = i / CIN, ci = i - co * CIN;
+        wt[ci * COUT + co] = __ldg(a.w + i);
+    }
+    for (int i = tid; i < COUT; i += kThreads) rs[i] = a.res_scale ? __ldg(a.res_scale + i) : 1.0f;
+    for (int i = tid; i < CIN; i += kThreads) { lw[i] = __ldg(a.ln_w + i); lb[i] = __ldg(a.ln_b + i); }
+    __syncthreads();
+
+    const int64_t hw = a.hw, nq = hw >> 1;          // pixel pairs
+    const int64_t b = blockIdx.y;
+    const int side = tid & 1;
+    const int c0 = side * HALF;
+    const float *x0 = a.x + (b * CIN + c0) * hw;
+    const float *xa = a.xa ? a.xa + (b * CIN + c0) * hw : nullptr;
+    const float *xb = a.xb_ ? a.xb_ + (b * CIN + c0) * hw : nullptr;
+    const float *xc = a.xc ? a.xc + (b * CIN + c0) * hw : nullptr;
+    const float *mz = a.mul + (b * CIN + c0) * hw;
+    const int64_t stride = (int64_t)gridDim.x * (kThreads / 2);
+    for (int64_t q0 = (int64_t)blockIdx.x * (kThreads / 2) + ((tid >> 5) << 4); q0 < nq; q0 += stride) {
+        const int64_t qr = q0 + ((tid & 31) >> 1);
+        const bool live = qr < nq;
+        const int64_t p = 2 * (live ? qr : nq - 1);
+        float xv[2][HALF];
+#pragma unroll
+        for (int i = 0; i < HALF; ++i) {
+            float2 v = __ldg(reinterpret_cast<const float2 *>(x0 + i * hw + p));
+            if (xa) { const float2 t = __ldg(reinterpret_cast<const float2 *>(xa + i * hw + p)); v.x += t.x; v.y += t.y; }
+            if (xb) { const float2 t = __ldg(reinterpret_cast<const float2 *>(xb + i * hw + p)); v.x += t.x; v.y += t.y; }
+            if (xc) { const float2 t = __ldg(reinterpret_cast<const float2 *>(xc + i * hw + p)); v.x += t.x; v.y += t.y; }
+            xv[0][i] = v.x; xv[1][i] = v.y;
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            float mu = 0.0f;
+#pragma unroll
+            for (int i = 0; i < HALF; ++i) mu += xv[k][i];
+            mu += __shfl_xor_sync(0xffffffffu, mu, 1);
+            mu *= (1.0f / CIN);
+            float var = 0.0f;
+#pragma unroll
+            for (int i = 0; i < HALF; ++i) { const float dlt = xv[k][i] - mu; var = fmaf(dlt, dlt, var); }
+            var += __shfl_xor_sync(0xffffffffu, var, 1);
+            var *= (1.0f / CIN);
+            const float rstd = 1.0f / sqrtf(var + a.eps);
+#pragma unroll
+            for (int i = 0; i < HALF; ++i) xv[k][i] = fmaf((xv[k][i] - mu) * rstd, lw[c0 + i], lb[c0 + i]);
+        }
+#pragma unroll
+        for (int i = 0; i < HALF; ++i) {
+            const float2 z = __ldg(reinterpret_cast<const float2 *>(mz + i * hw + p));
+            xv[0][i] *= z.x; xv[1][i] *= z.y;
+        }
+#pragma unroll 1
+        for (int g = 0; g < COUT / 8; ++g) {
+            float acc[2][8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { acc[0][j] = 0.0f; acc[1][j] = 0.0f; }
+#pragma unroll
+            for (int i = 0; i < HALF; ++i) {
+                const float4 w0 = *reinterpret_cast<const float4 *>(wt + (c0 + i) * COUT + g * 8);
+                const float4 w1 = *reinterpret_cast<const float4 *>(wt + (c0 + i) * COUT + g * 8 + 4);
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    acc[k][0] = fmaf(xv[k][i], w0.x, acc[k][0]); acc[k][1] = fmaf(xv[k][i], w0.y, acc[k][1]);
+                    acc[k][2] = fmaf(xv[k][i], w0.z, acc[k][2]); acc[k][3] = fmaf(xv[k][i], w0.w, acc[k][3]);
+                    acc[k][4] = fmaf(xv[k][i], w1.x, acc[k][4]); acc[k][5] = fmaf(xv[k][i], w1.y, acc[k][5]);
+                    acc[k][6] = fmaf(xv[k][i], w1.z, acc[k][6]); acc[k][7] = fmaf(xv[k][i], w1.w, acc[k][7]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[k][j] += __shfl_xor_sync(0xffffffffu, acc[k][j], 1);
+            const int64_t o = (b * COUT + g * 8 + side * 4) * hw + p;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int co = g * 8 + side * 4 + j;
+                if (live) {
+                    const float2 r = __ldg(reinterpret_cast<const float2 *>(a.res + o + j * hw));
+                    const float v0 = fmaf(r.x, rs[co], side ? acc[0][4 + j] : acc[0][j]);
+                    const float v1 = fmaf(r.y, rs[co], side ? acc[1][4 + j] : acc[1][j]);
+                    *reinterpret_cast<float2 *>(a.y + o + j * hw) = make_float2(v0, v1);
+                }
+            }
+        }
+    }
+}
+
 template <int C>
 __global__ void __launch_bounds__(kThreads)
 layernorm2d_kernel(const float *__restrict__ x, const float *__restrict__ ln_w,
@@ -467,7 +567,16 @@ extern "C" int wm_lfss_out_fwd(const float *y, const float *ya, const float *yb,
     Args a = {};
     a.x = y; a.xa = ya; a.xb_ = yb; a.xc = yc; a.ln_w = on_w; a.ln_b = on_b; a.eps = eps; a.mul = zs; a.w = w_out;
     a.res = x; a.res_scale = skip_scale; a.y = out; a.hw = h * w;
-    {
+    const bool two = a.hw % 2 == 0 && aligned8(y) && (!ya || aligned8(ya)) && (!yb || aligned8(yb)) &&
+                     (!yc || aligned8(yc)) && aligned8(zs) && aligned8(x) && aligned8(out) &&
+                     getenv("WM_LFSS_OUT_ONE") == nullptr;
+    if (two) {
+        const int64_t want = (a.hw / 2 + kThreads / 2 - 1) / (kThreads / 2);
+        const int64_t cap = (int64_t)sm_count() * 16;
+        dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)B);
+        lfss_out_pair2_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);
+        WM_LAUNCH_OK("lfss out (two pixels)");
+    } else {
         const int64_t want = (a.hw + kThreads / 2 - 1) / (kThreads / 2);
         const int64_t cap = (int64_t)sm_count() * 16;
         dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)B);
