@@ -169,14 +169,17 @@ pixel2_kernel(const Args a)
 
     const int64_t hw = a.hw, npair = hw >> 1;
     const int64_t b = blockIdx.y;
-    const float *xb = a.x + b * CIN * hw;
+    constexpr int XCH = PRE == kPreGate ? 2 * CIN : CIN;
+    const float *xb = a.x + b * XCH * hw;
     for (int64_t q = (int64_t)blockIdx.x * kThreads + tid; q < npair; q += (int64_t)gridDim.x * kThreads) {
         const int64_t p = 2 * q;
         float xv[2][CIN];
+        {
 #pragma unroll
-        for (int ci = 0; ci < CIN; ++ci) {
-            const float2 v = __ldg(reinterpret_cast<const float2 *>(xb + ci * hw + p));
-            xv[0][ci] = v.x; xv[1][ci] = v.y;
+            for (int ci = 0; ci < CIN; ++ci) {
+                const float2 v = __ldg(reinterpret_cast<const float2 *>(xb + ci * hw + p));
+                xv[0][ci] = v.x; xv[1][ci] = v.y;
+            }
         }
         if (PRE == kPreLN) {
 #pragma unroll

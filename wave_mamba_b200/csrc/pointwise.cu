@@ -477,34 +477,45 @@ head_conv3x3_kernel(const float *__restrict__ x, const float *__restrict__ wgt,
     constexpr int CIN = 32, COUT = 3;
     extern __shared__ __align__(16) float smem[];
     float *xs = smem;                                   // [32][kXP]
-    float4 *wt = reinterpret_cast<float4 *>(xs + CIN * kXP);   // [ci*9+tap] -> (w0, w1, w2, 0)
+    // A CTA takes TWO horizontally adjacent 8x32 tiles; a thread computes the same (row, col) of both,
+    // so every broadcast weight load (LDS.128: 512 bytes returned per warp) feeds 6 FMAs instead of 3.
+    float *xs2 = xs + CIN * kXP;                                // second tile's halo
+    float4 *wt = reinterpret_cast<float4 *>(xs2 + CIN * kXP);  // [ci*9+tap] -> (w0, w1, w2, 0)
     const int tid = threadIdx.x;
-    const int tx0 = blockIdx.x * kTW, ty0 = blockIdx.y * kTH;
+    const int tx0 = blockIdx.x * (2 * kTW), ty0 = blockIdx.y * kTH;
     const int64_t b = blockIdx.z;
     const int64_t hw = (int64_t)h * w;
     for (int i = tid; i < CIN * 9; i += kThreads)
         wt[i] = make_float4(__ldg(wgt + i), __ldg(wgt + CIN * 9 + i), __ldg(wgt + 2 * CIN * 9 + i), 0.0f);
     load_halo32(x, xs, b, CIN, h, w, ty0, tx0);
+    load_halo32(x, xs2, b, CIN, h, w, ty0, tx0 + kTW);           // all zeros when past the right edge
     halo_wait();
     __syncthreads();
     const int col = tid & 31, row = tid >> 5;
-    float a0 = bias ? __ldg(bias + 0) : 0.0f, a1 = bias ? __ldg(bias + 1) : 0.0f,
-          a2 = bias ? __ldg(bias + 2) : 0.0f;
+    const float b0 = bias ? __ldg(bias + 0) : 0.0f, b1 = bias ? __ldg(bias + 1) : 0.0f,
+                b2 = bias ? __ldg(bias + 2) : 0.0f;
+    float a0[2] = {b0, b0}, a1[2] = {b1, b1}, a2[2] = {b2, b2};
 #pragma unroll 4
     for (int ci = 0; ci < CIN; ++ci) {
         const float *xc = xs + ci * kXP + row * kHW + col;
+        const float *xd = xs2 + ci * kXP + row * kHW + col;
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
-            const float xv = xc[(t / 3) * kHW + t % 3];
             const float4 wv = wt[ci * 9 + t];
-            a0 = fmaf(xv, wv.x, a0); a1 = fmaf(xv, wv.y, a1); a2 = fmaf(xv, wv.z, a2);
+            const float u = xc[(t / 3) * kHW + t % 3], v = xd[(t / 3) * kHW + t % 3];
+            a0[0] = fmaf(u, wv.x, a0[0]); a1[0] = fmaf(u, wv.y, a1[0]); a2[0] = fmaf(u, wv.z, a2[0]);
+            a0[1] = fmaf(v, wv.x, a0[1]); a1[1] = fmaf(v, wv.y, a1[1]); a2[1] = fmaf(v, wv.z, a2[1]);
         }
     }
-    const int gy = ty0 + row, gx = tx0 + col;
-    if (gy < h && gx < w) {
-        const int64_t o = b * COUT * hw + (int64_t)gy * w + gx;
-        if (residual) { a0 += __ldg(residual + o); a1 += __ldg(residual + o + hw); a2 += __ldg(residual + o + 2 * hw); }
-        y[o] = a0; y[o + hw] = a1; y[o + 2 * hw] = a2;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int gy = ty0 + row, gx = tx0 + k * kTW + col;
+        if (gy < h && gx < w) {
+            const int64_t o = b * COUT * hw + (int64_t)gy * w + gx;
+            float r0 = a0[k], r1 = a1[k], r2 = a2[k];
+            if (residual) { r0 += __ldg(residual + o); r1 += __ldg(residual + o + hw); r2 += __ldg(residual + o + 2 * hw); }
+            y[o] = r0; y[o + hw] = r1; y[o + 2 * hw] = r2;
+        }
     }
 }
 
@@ -530,9 +541,9 @@ extern "C" int wm_head_conv3x3_fwd(const float *x, const float *w3x3, const floa
     WM_REQUIRE(dims_ok(B, h, w) && (h + kTH - 1) / kTH <= 65535, "wm_head_conv3x3_fwd: bad sizes");
     if (B == 0 || h == 0 || w == 0) return WM_OK;
     WM_REQUIRE(x && w3x3 && y, "wm_head_conv3x3_fwd: null pointer");
-    const size_t smem = sizeof(float) * 32 * kXP + sizeof(float4) * 32 * 9;
+    const size_t smem = sizeof(float) * 2 * 32 * kXP + sizeof(float4) * 32 * 9;
     WM_CUDA_OK(opt_in_smem(head_conv3x3_kernel, smem));
-    dim3 grid((unsigned)((w + kTW - 1) / kTW), (unsigned)((h + kTH - 1) / kTH), (unsigned)B);
+    dim3 grid((unsigned)((w + 2 * kTW - 1) / (2 * kTW)), (unsigned)((h + kTH - 1) / kTH), (unsigned)B);
     head_conv3x3_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(x, w3x3, bias, residual, y,
                                                                         (int)h, (int)w);
     WM_LAUNCH_OK("head conv3x3");
