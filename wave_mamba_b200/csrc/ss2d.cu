@@ -9,32 +9,35 @@
 //   contiguous in the sequence AND cheap to address in the NCHW map:
 //     k=0/2 (row-major, forward/backward): chunk = row_T consecutive positions of the
 //            flattened map (element stride +-1);
-//     k=1/3 (column-major, forward/backward): chunk = one image column (element stride +-w).
-//   One CTA (512 threads, 2 CTAs/SM) owns 4 neighbouring chunks ("strands") of one direction
-//   and all 64 channels x 16 states of them.  thread = (strand s, channel d, state half):
-//   8 states in registers, walked sequentially, 16 steps per tile.  For column directions the
-//   four strands are four adjacent columns, so a tile row is one 16-byte segment per channel.
+//     k=1/3 (column-major, forward/backward): chunk = a segment of one image column (element
+//            stride +-w); segments per column, row-chunk length and launch order come from the
+//            chunk planner (make_geom), which fills the 2 x SMs CTA slots with the least tail.
+//   One CTA (256 threads, 128 registers, 2 CTAs/SM) owns 4 neighbouring chunks ("strands") of one
+//   direction and all 64 channels x 16 states of them.  thread = (strand s, channel pair, state
+//   half): 2 channels x 8 states in registers (B/C rows of a position are fetched once per 16 state
+//   updates), walked sequentially, 16 steps per tile.  For column directions the four strands are
+//   four adjacent columns, so a tile row is one 16-byte segment per channel.
 //
-// Per tile (64 positions x 64 channels), five phases separated by __syncthreads:
+// Per tile (64 positions x 64 channels), phases separated by __syncthreads:
 //   load     cp.async 16-byte chunks -> xs[d][p]      (issued one tile ahead, overlaps the scan)
-//   dt-low   pj[p][32..33] = W_k[0:2] (2x64) . x[:,p]   plain FP32 FMAs, 8 lanes per position
-//   project+delta  (one phase, interleaved per warp so the tensor-pipe latency hides behind the
-//            delta arithmetic)
-//            pj[p][B16|C16] = W_k[2:34] (32x64) . x[:,p]  on the tensor cores: mma.sync m16n8k8
-//            TF32 with the 3xTF32 split (a_lo*b_hi + a_hi*b_lo + a_hi*b_hi), fp32 accumulate;
-//            dd[d][p] = (dt, dt*u), dt = softplus(dt_proj . dt_low + bias); ys[d][p] = D*u
-//   scan     h = exp2(dt*A2)*h + dt*u*B ; y += C.h    packed FFMA2/FMUL2, MUFU ex2.approx
+//   project  pj[p][B16|C16|dt2] = W_k (34x64) . x[:,p]  on the tensor cores: mma.sync m16n8k8
+//            TF32 with the 3xTF32 split (a_lo*b_hi + a_hi*b_lo + a_hi*b_hi), fp32 accumulate
+//   delta    dd[p][d] = (dt, u), dt = softplus(dt_proj . dt_low + bias), two at a time on the
+//            packed FP32 pipe
+//   scan     h = exp2(dt*A2)*h + dt*u*B ; y = C.h + D*u   packed FFMA2/FMUL2, MUFU ex2.approx,
+//            step inputs prefetched one step ahead into registers
 //   store    ys[d][p] -> 16-byte coalesced stores into this direction's output plane (pass 2)
 //
 // Chunks are made independent with a three-phase carry scheme (the recurrence is linear):
 //   pass 1  every chunk from h=0: aggregate (P = prod a = exp2(A2*sum dt), H = local end state)
-//   carry   per (b,k,d,n): h_in[c] = P[c-1]*h_in[c-1] + H[c-1]          (tiny, sequential in c)
+//   carry   per (b,k,d,n): h_in[c] = P[c-1]*h_in[c-1] + H[c-1]   (segmented: 16 warps per 32 chains)
 //   pass 2  every chunk again from its true h_in, emitting y into one plane per direction.
 // The four planes are summed in the reference's order ((y0+y2)+y1)+y3 by the consumer
 // (wm_lfss_out_fwd) or by the combine kernel of wm_ss2d_core_fwd.  No atomics: deterministic.
 //
-// Roofline: not HBM-bound.  Each state update costs one MUFU ex2 (16/clk/SM) and every exp is
-// evaluated twice (pass 1 and pass 2); see DESIGN.md section 4.
+// Roofline: not HBM-bound.  Every exp is evaluated twice (pass 1 and pass 2) and the scan loop is
+// bound by the LSU return path into the register file (80 bytes per thread and step, B/C being
+// broadcast data): measured in DESIGN.md section 4.2.
 #include <stdlib.h>
 
 #include <initializer_list>
