@@ -130,3 +130,21 @@ def test_cudnn_tf32_for_library_convs_is_measured_not_assumed(dev, params_cache)
               f"differing uint8 values {int((om.to_uint8_bgr(y[0]) != om.to_uint8_bgr(want[0])).sum())}")
     assert deltas[False] <= 1e-3, deltas
     assert deltas[True] <= 5e-2, deltas
+
+
+def test_lol_400x600_batch4_matches_oracle(dev, params_cache):
+    """BASELINE configs[1] exactly: LOLv1 weights, 400x600, batch 4, fp32, against the CPU oracle:
+    raw max-abs error <= 2e-4 and |dPSNR| <= 1e-3 dB per image."""
+    params = params_cache("LOLv1")
+    x, gt = om.synth_lowlight(4, 400, 600, seed=0)
+    want = om.unet_forward(params, x)
+    net = _net(params, dev)
+    with torch.no_grad():
+        y = net.restoration_network(x.to(dev)).cpu()
+    err = (y - want).abs().max().item()
+    print(f"400x600 x4: max abs err vs oracle {err:.3e}")
+    assert err <= 2e-4
+    for i in range(4):
+        g8 = om.to_uint8_bgr(gt[i])
+        d = abs(om.psnr_y(om.to_uint8_bgr(y[i]), g8) - om.psnr_y(om.to_uint8_bgr(want[i]), g8))
+        assert d <= 1e-3, d

@@ -46,8 +46,38 @@ def _require_inference(module: nn.Module, t: torch.Tensor) -> None:
 # --------------------------------------------------------------------------------------
 # wavelets                                                      reference :133-148
 # --------------------------------------------------------------------------------------
+class _DWTFn(torch.autograd.Function):
+    """The reference's Haar pair is orthonormal (4 taps of +-1/2), so the adjoint of the analysis is
+    the synthesis and vice versa: both backward passes reuse the forward kernels."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return ops.dwt_haar(x.contiguous())
+
+    @staticmethod
+    def backward(ctx, g_ll, g_hl, g_lh, g_hh):
+        high = torch.cat([g_hl, g_lh, g_hh], dim=1)
+        return ops.iwt_haar(g_ll.contiguous(), high)
+
+
+class _IWTFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, low, high):
+        ctx.channels = low.shape[1]
+        return ops.iwt_haar(low.contiguous(), high.contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        g_ll, g_hl, g_lh, g_hh = ops.dwt_haar(g.contiguous())
+        return g_ll, torch.cat([g_hl, g_lh, g_hh], dim=1)
+
+
 class DWT(nn.Module):
+    """Differentiable on its own (the whole network's training step still needs the SS2D backward)."""
+
     def forward(self, x):
+        if torch.is_grad_enabled() and x.requires_grad:
+            return _DWTFn.apply(x)
         return ops.dwt_haar(x.contiguous())
 
 
@@ -56,7 +86,12 @@ class IWT(nn.Module):
 
     def forward(self, x, high=None):
         if high is None:
+            if torch.is_grad_enabled() and x.requires_grad:
+                c = x.shape[1] // 4
+                return _IWTFn.apply(x[:, :c], x[:, c:])
             return ops.iwt_haar_cat(x.contiguous())
+        if torch.is_grad_enabled() and (x.requires_grad or high.requires_grad):
+            return _IWTFn.apply(x, high)
         return ops.iwt_haar(x.contiguous(), high.contiguous())
 
 
