@@ -332,12 +332,15 @@ __global__ void __launch_bounds__(kThreads, 2)
 lfss_out_pair2_kernel(const Args a)
 {
     constexpr int CIN = 64, HALF = 32, COUT = 32;
-    __shared__ __align__(16) float wt[CIN * COUT];  // [ci][co]
+    // [ci][co]; the second lane's 32 rows start 16 floats later so that the two row addresses of a
+    // warp-wide LDS.128 fall into different banks (the unpadded layout had 2-way conflicts)
+    constexpr int kSide = HALF * COUT + 16;
+    __shared__ __align__(16) float wt[2 * kSide];
     __shared__ float rs[COUT], lw[CIN], lb[CIN];
     const int tid = threadIdx.x;
     for (int i = tid; i < CIN * COUT; i += kThreads) {
         const int co = i / CIN, ci = i - co * CIN;
-        wt[ci * COUT + co] = __ldg(a.w + i);
+        wt[(ci / HALF) * kSide + (ci % HALF) * COUT + co] = __ldg(a.w + i);
     }
     for (int i = tid; i < COUT; i += kThreads) rs[i] = a.res_scale ? __ldg(a.res_scale + i) : 1.0f;
     for (int i = tid; i < CIN; i += kThreads) { lw[i] = __ldg(a.ln_w + i); lb[i] = __ldg(a.ln_b + i); }
@@ -394,8 +397,8 @@ lfss_out_pair2_kernel(const Args a)
             for (int j = 0; j < 8; ++j) { acc[0][j] = 0.0f; acc[1][j] = 0.0f; }
 #pragma unroll
             for (int i = 0; i < HALF; ++i) {
-                const float4 w0 = *reinterpret_cast<const float4 *>(wt + (c0 + i) * COUT + g * 8);
-                const float4 w1 = *reinterpret_cast<const float4 *>(wt + (c0 + i) * COUT + g * 8 + 4);
+                const float4 w0 = *reinterpret_cast<const float4 *>(wt + side * kSide + i * COUT + g * 8);
+                const float4 w1 = *reinterpret_cast<const float4 *>(wt + side * kSide + i * COUT + g * 8 + 4);
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
                     acc[k][0] = fmaf(xv[k][i], w0.x, acc[k][0]); acc[k][1] = fmaf(xv[k][i], w0.y, acc[k][1]);
