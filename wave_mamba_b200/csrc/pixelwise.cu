@@ -32,6 +32,25 @@ __device__ __forceinline__ float gelu_erf(float v)
 // SiLU / sigmoid with the MUFU-based fast exp and divide (relative error ~2e-7 on O(1) values)
 __device__ __forceinline__ float silu(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
+// packed fp32x2 helpers (Blackwell FFMA2): element-wise IEEE fma on a register pair
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
 struct Args {
     const float *x;          // (B, CIN or 2*CIN, hw)
     const float *xa, *xb_, *xc;  // optional addends, summed in this order: ((x + xa) + xb_) + xc
@@ -199,7 +218,9 @@ pixel2_kernel(const Args a)
         }
 #pragma unroll 1
         for (int g = 0; g < COUT / 8; ++g) {
-            float acc[2][8];
+            // packed FP32 (FFMA2): one instruction = two of the eight outputs of a pixel; the weight
+            // float4s are register pairs already, the activation is duplicated once per (pixel, ci)
+            f32x2 acc2[2][4];
             float2 rv[8];
             if (a.res) {
 #pragma unroll
@@ -207,19 +228,27 @@ pixel2_kernel(const Args a)
                     rv[j] = __ldg(reinterpret_cast<const float2 *>(a.res + (b * COUT + g * 8 + j) * hw + p));
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { acc[0][j] = pb[g * 8 + j]; acc[1][j] = pb[g * 8 + j]; }
+            for (int j = 0; j < 4; ++j) {
+                acc2[0][j] = pack2(pb[g * 8 + 2 * j], pb[g * 8 + 2 * j + 1]);
+                acc2[1][j] = acc2[0][j];
+            }
 #pragma unroll
             for (int ci = 0; ci < CIN; ++ci) {
                 const float4 w0 = *reinterpret_cast<const float4 *>(wt + ci * COUT + g * 8);
                 const float4 w1 = *reinterpret_cast<const float4 *>(wt + ci * COUT + g * 8 + 4);
+                const f32x2 wp[4] = {pack2(w0.x, w0.y), pack2(w0.z, w0.w), pack2(w1.x, w1.y), pack2(w1.z, w1.w)};
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
-                    acc[k][0] = fmaf(xv[k][ci], w0.x, acc[k][0]); acc[k][1] = fmaf(xv[k][ci], w0.y, acc[k][1]);
-                    acc[k][2] = fmaf(xv[k][ci], w0.z, acc[k][2]); acc[k][3] = fmaf(xv[k][ci], w0.w, acc[k][3]);
-                    acc[k][4] = fmaf(xv[k][ci], w1.x, acc[k][4]); acc[k][5] = fmaf(xv[k][ci], w1.y, acc[k][5]);
-                    acc[k][6] = fmaf(xv[k][ci], w1.z, acc[k][6]); acc[k][7] = fmaf(xv[k][ci], w1.w, acc[k][7]);
+                    const f32x2 xx = pack2(xv[k][ci], xv[k][ci]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc2[k][j] = ffma2(xx, wp[j], acc2[k][j]);
                 }
             }
+            float acc[2][8];
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) unpack2(acc2[k][j], acc[k][2 * j], acc[k][2 * j + 1]);
             const int64_t o = (b * COUT + g * 8) * hw + p;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
