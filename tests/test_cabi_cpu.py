@@ -167,3 +167,18 @@ def test_ss2d_chunk_plan_is_consistent(lib_path):
         need = 4 * B * 64 * L * 4 + 2 * B * 4 * max_chunks * 1024 * 4
         assert lib.wm_ss2d_core_workspace_bytes(B, h, w) >= need
     assert lib.wm_ss2d_debug_geometry(0, 8, 8, (ctypes.c_int * 6)()) != 0
+
+
+def test_uint8_entry_point_validates_and_refuses_cpu(lib_path):
+    """wave_mamba_b200.enhance_bgr_u8: shape/dtype errors are Python errors, a CPU module is refused
+    loudly (no fallback)."""
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import wave_mamba_b200 as wm
+    net = wm.WaveMamba(in_chn=3, wf=32, n_l_blocks=[1, 2, 4], n_h_blocks=[1, 1, 2], ffn_scale=2.0).eval()
+    with pytest.raises(ValueError):
+        wm.enhance_bgr_u8(net, torch.zeros(16, 16, 3))                      # not uint8
+    with pytest.raises(ValueError):
+        wm.enhance_bgr_u8(net, torch.zeros(16, 16, 4, dtype=torch.uint8))   # not 3 channels
+    with pytest.raises((wm.WaveMambaNativeError, RuntimeError)):
+        wm.enhance_bgr_u8(net, torch.zeros(16, 16, 3, dtype=torch.uint8), device=torch.device("cpu"))
