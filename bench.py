@@ -10,8 +10,10 @@ torchrun, one rank per GPU; images are independent, so ranks share nothing on th
 
 One JSON line on stdout (rank 0):
   value        images/s, inputs resident in HBM, CUDA-event timed, max over ranks
-  e2e          same, but every step copies its input from pinned host memory and reads the full
-               output image back (what inference_wavemamba.py does per image)
+  e2e          same through the public API wave_mamba_b200.enhance_bgr_u8 (the body of
+               inference_wavemamba.py's loop): every step copies its uint8 BGR image from pinned host
+               memory, converts / pads on the device, runs the forward, converts back and copies the
+               uint8 result to pinned host memory; `float32_edges` = the same with 12-byte pixels
   roofline     the dominant hand-written kernel group (SS2D core): algorithmic bytes / measured
                duration vs the measured HBM peak (MEASURED_PEAKS.json), plus per-kernel rows
   cpu_baseline the CPU oracle (port of the reference forward) timed on this box's host cores on a
