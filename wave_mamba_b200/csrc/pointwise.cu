@@ -82,21 +82,36 @@ __device__ __forceinline__ void load_halo32(const float *__restrict__ x, float *
     const int gx0 = tx0 - 1 + lane, gx1 = tx0 + 31 + lane;
     const bool okx0 = gx0 >= 0 && gx0 < w;
     const bool okx1 = lane < 2 && gx1 < w;
-    for (int r = warp; r < C * kHH; r += kThreads / 32) {
-        const int c = r / kHH, py = r - c * kHH;
+    // row offsets and validity are the same for every channel: computed once (the per-element
+    // index arithmetic of the first version was a quarter of pw_dw's instructions)
+    int64_t roff[kHH];
+    uint32_t okrows = 0u;
+#pragma unroll
+    for (int py = 0; py < kHH; ++py) {
         const int gy = ty0 - 1 + py;
         const bool oky = gy >= 0 && gy < h;
-        const float *row = xb + (int64_t)c * hw + (int64_t)(oky ? gy : 0) * w;
-        const uint32_t dst = xs_base + (uint32_t)(c * kXP + py * kHW + lane) * 4u;
-        const bool ok0 = oky && okx0;
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(ok0 ? row + gx0 : xb),
-                     "r"(ok0 ? 4u : 0u)
-                     : "memory");
-        if (lane < 2) {
-            const bool ok1 = oky && okx1;
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + 32u * 4u),
-                         "l"(ok1 ? row + gx1 : xb), "r"(ok1 ? 4u : 0u)
+        roff[py] = oky ? (int64_t)gy * w : 0;
+        okrows |= oky ? (1u << py) : 0u;
+    }
+#pragma unroll 1
+    for (int c = warp; c < C; c += kThreads / 32) {
+        const float *plane = xb + (int64_t)c * hw;
+        const uint32_t dst_c = xs_base + (uint32_t)(c * kXP + lane) * 4u;
+#pragma unroll
+        for (int py = 0; py < kHH; ++py) {
+            const bool oky = (okrows >> py) & 1u;
+            const float *row = plane + roff[py];
+            const uint32_t dst = dst_c + (uint32_t)(py * kHW) * 4u;
+            const bool ok0 = oky && okx0;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(ok0 ? row + gx0 : xb),
+                         "r"(ok0 ? 4u : 0u)
                          : "memory");
+            if (lane < 2) {
+                const bool ok1 = oky && okx1;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + 32u * 4u),
+                             "l"(ok1 ? row + gx1 : xb), "r"(ok1 ? 4u : 0u)
+                             : "memory");
+            }
         }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
