@@ -134,6 +134,27 @@ def test_ss2d_core_other_checkpoints(ops, dev, params_cache, ckpt, block):
     assert (got.double() - want64).abs().max().item() <= 2e-5 * max(1.0, want64.abs().max().item())
 
 
+@pytest.mark.parametrize("shape", [(1, 64, 100, 37), (1, 64, 300, 8), (1, 64, 257, 9), (2, 64, 160, 20)])
+def test_ss2d_core_with_segmented_columns(ops, dev, params_cache, shape):
+    """Shapes for which the chunk planner cuts a column into 2..5 segments (the 4K level-2 map,
+    540x960, runs with 2): the carry must chain the segments of a column before moving to the next
+    column.  Same tolerance as test_ss2d_core_vs_oracle."""
+    import ctypes
+    from wave_mamba_b200 import _cabi
+    geo = (ctypes.c_int * 6)()
+    assert _cabi.load().wm_ss2d_debug_geometry(shape[0], shape[2], shape[3], geo) == 0
+    assert geo[3] >= 2, f"planner no longer segments the columns of {shape}: pick another shape"
+    g = torch.Generator().manual_seed(2)
+    x = F.silu(0.5 * torch.randn(*shape, generator=g))
+    prm = _ss_params(params_cache)
+    want64 = _arbiter(x, prm)
+    got = ops.ss2d_core(x.to(dev), *[t.to(dev) for t in prm]).cpu()
+    scale = max(1.0, want64.abs().max().item())
+    err = (got.double() - want64).abs().max().item()
+    print(f"{shape}: {geo[3]} column segments, gpu-vs-f64 {err:.2e} (scale {scale:.2f})")
+    assert err <= 2e-5 * scale
+
+
 def test_ss2d_core_is_deterministic(ops, dev, params_cache):
     x = F.silu(torch.randn(2, 64, 48, 72, device=dev))
     prm = [t.to(dev) for t in _ss_params(params_cache)]
