@@ -133,3 +133,25 @@ def test_img_io_edges_match_reference():
     g = load_golden("imgio")
     assert torch.equal(om.img_u8_to_f32(g["img"][None], 128), g["x"])
     assert torch.equal(om.img_f32_to_u8(g["y"], 100, 150)[0], g["out_img"])
+
+
+def test_ss2d_core_backward_oracle_gradcheck(params_cache):
+    """The backward oracle for the next round: autograd through the pure-torch
+    sequential scan (oracle.scan.selective_scan_loop, fp64) is what a CUDA SS2D backward will be
+    compared against.  Pinned here with central finite differences on a tiny map: gradients with
+    respect to the input map, the decay parameters, the skip weights and the dt bias."""
+    from oracle import scan as oscan
+    p = om.sub(om.strip_prefix(params_cache("UHDLOL4K")), "down_group1.l_blk.0.self_attention")
+    prm = [p[k].double() for k in ("x_proj_weight", "dt_projs_weight", "dt_projs_bias", "A_logs", "Ds")]
+    g = torch.Generator().manual_seed(13)
+    x = torch.nn.functional.silu(0.5 * torch.randn(1, 64, 2, 3, generator=g)).double().requires_grad_(True)
+    xp, dw = prm[0], prm[1]
+    db = prm[2].clone().requires_grad_(True)
+    al = prm[3].clone().requires_grad_(True)
+    ds = prm[4].clone().requires_grad_(True)
+
+    def fn(x_, db_, al_, ds_):
+        return om.ss2d_core(x_, xp, dw, db_, al_, ds_, scan_fn=oscan.selective_scan_loop)
+
+    assert torch.autograd.gradcheck(fn, (x, db, al, ds), eps=1e-6, atol=1e-6, rtol=1e-4, nondet_tol=0.0,
+                                    fast_mode=True)
