@@ -31,7 +31,7 @@ extern "C" {
 #define WM_ECUDA (-2)     /* a CUDA runtime call or kernel launch failed               */
 #define WM_ENODEVICE (-3) /* no sm_100-class CUDA device is current                     */
 
-#define WM_ABI_VERSION 10
+#define WM_ABI_VERSION 11
 
 typedef void *wm_stream_t;
 
@@ -115,10 +115,14 @@ int wm_dw_act_pw_fwd(const float *x, const float *dw_w, const float *dw_b, const
  * CMTAttention.project_out (:797) fused with the HFEBlock residual add (:849);
  * ffn.conv3 after the gate fused with `x*skip_scale2 +` (:526).  gate_mode 0: plain; 1: input is
  * (B,2*Cin,h,w) and the 1x1 sees gelu(x[:, :Cin]) * x[:, Cin:]  (ffn gate, :227-228).
- * res_scale: optional (Cout) per-channel multiplier of the residual. */
-int wm_pw_fwd(const float *x, const float *pw_w, const float *pw_b, int gate_mode,
-              const float *residual, const float *res_scale, float *y, int64_t B, int64_t Cin,
-              int64_t Cout, int64_t h, int64_t w, wm_stream_t stream);
+ * res_scale: optional (Cout) per-channel multiplier of the residual.
+ * x_bstride: batch stride of x in floats (0 = dense; lets x be a channel slice of a wider tensor);
+ * w_bstride: batch stride of pw_w in floats (0 = one weight matrix; non-zero = per-image weights,
+ * used for the CxC attention folded into project_out, :791-797). */
+int wm_pw_fwd(const float *x, int64_t x_bstride, const float *pw_w, int64_t w_bstride,
+              const float *pw_b, int gate_mode, const float *residual, const float *res_scale,
+              float *y, int64_t B, int64_t Cin, int64_t Cout, int64_t h, int64_t w,
+              wm_stream_t stream);
 
 /* SS2D z branch: zs = silu( in_proj.weight[64:128] . LayerNorm_c(x) ), x (B,32,h,w) -> (B,64,h,w)
  * (ln_1 :524, in_proj + chunk :483-484, F.silu(z) :493).  w_z points at row 64 of in_proj.weight. */
@@ -160,13 +164,8 @@ int wm_gram32_fwd(const float *x, int64_t x_bstride, const float *y, int64_t y_b
  *                      `packed` must have been built with the 1x1 weights.
  * fp32 accuracy (a_lo*b_hi + a_hi*b_lo + a_hi*b_hi, fp32 accumulate). */
 size_t wm_conv3x3_packed_bytes(int64_t Cin, int64_t Cout, int with_gate);
-/* Two implementations share the entry points and the packed buffer (it holds both weight orders):
- * 0 = mma.sync m16n8k8 TF32 (legacy tensor path), 1 = tcgen05.mma kind::tf32 with TMEM
- * accumulators.  Process-wide switch; returns WM_EINVAL for other values. */
-int wm_conv3x3_set_impl(int impl);
-int wm_conv3x3_get_impl(void);
-/* Developer aid: non-NULL device buffer of 6*SMs int64 -> the tcgen05 kernel writes per-CTA phase
- * cycle counts (wait-X, lo-split, MMA loop, drain, next-stage issue, epilogue); NULL disables. */
+/* Developer aid: non-NULL device buffer of 6*SMs int64 -> the kernel's MMA thread writes per-CTA
+ * cycle counts (total, wait-weights, wait-X, wait-accumulators, issue, tiles); NULL disables. */
 int wm_conv3x3_debug_timing(void *device_buffer);
 int wm_conv3x3_prepack(const float *w3x3, const float *w1x1, void *packed, int64_t Cin, int64_t Cout,
                        wm_stream_t stream);

@@ -114,17 +114,10 @@ def test_product_never_imports_the_oracle():
 def test_plugin_overlays_the_reference_registry(tmp_path):
     """Overlay plugin/basicsr/archs/wavemamba_arch.py on a (symlinked) reference checkout and
     build the network through the reference's own build_network / ARCH_REGISTRY."""
-    ref = "/root/reference"
+    sys.path.insert(0, ROOT)
+    from tools.ref_overlay import make_overlay
     over = tmp_path / "overlay"
-    (over / "basicsr" / "archs").mkdir(parents=True)
-    for entry in os.listdir(f"{ref}/basicsr"):
-        if entry not in ("archs", "__pycache__"):
-            os.symlink(f"{ref}/basicsr/{entry}", over / "basicsr" / entry)
-    for entry in os.listdir(f"{ref}/basicsr/archs"):
-        if entry not in ("wavemamba_arch.py", "__pycache__"):
-            os.symlink(f"{ref}/basicsr/archs/{entry}", over / "basicsr" / "archs" / entry)
-    os.symlink(os.path.join(ROOT, "plugin", "basicsr", "archs", "wavemamba_arch.py"),
-               over / "basicsr" / "archs" / "wavemamba_arch.py")
+    make_overlay("/root/reference", str(over))
     code = f"""
 import sys
 sys.path.insert(0, {str(ROOT)!r})

@@ -155,6 +155,58 @@ def test_ss2d_core_with_segmented_columns(ops, dev, params_cache, shape):
     assert err <= 2e-5 * scale
 
 
+def _arbiter_streamed(x, prm):
+    """The fp64 arbiter of ``_arbiter`` evaluated one direction at a time (same arithmetic; peak
+    host memory ~5 GB instead of ~20 GB at the 4K level-1 size).  Index maps: SURVEY appendix A."""
+    xp, dw, db, al, ds = [t.double() for t in prm]
+    B, D, h, w = x.shape
+    L = h * w
+    A = -torch.exp(al)
+    row = x.reshape(B, D, L)
+    col = x.transpose(2, 3).reshape(B, D, L)
+    y = torch.zeros(B, D, L, dtype=torch.float64)
+    for k in range(4):
+        seq = col if k % 2 else row
+        seq = (seq.flip(-1) if k >= 2 else seq).double().contiguous()
+        proj = torch.einsum("cd,bdl->bcl", xp[k], seq)
+        dt_low, Bm, Cm = torch.split(proj, [2, 16, 16], dim=1)
+        delta = torch.einsum("dr,brl->bdl", dw[k], dt_low)
+        out = oscan.selective_scan_c(seq, delta, A[k * D:(k + 1) * D], Bm[:, None].contiguous(),
+                                     Cm[:, None].contiguous(), ds[k * D:(k + 1) * D], db[k])
+        del proj, dt_low, Bm, Cm, delta, seq
+        if k >= 2:
+            out = out.flip(-1)
+        if k % 2:
+            out = out.reshape(B, D, w, h).transpose(2, 3).reshape(B, D, L)
+        y += out
+    return y.reshape(B, D, h, w)
+
+
+def test_streamed_arbiter_is_the_arbiter(params_cache):
+    g = torch.Generator().manual_seed(11)
+    x = F.silu(0.5 * torch.randn(2, 64, 9, 14, generator=g))
+    prm = _ss_params(params_cache)
+    a, b = _arbiter(x, prm), _arbiter_streamed(x, prm)
+    assert (a - b).abs().max().item() <= 1e-12 * max(1.0, a.abs().max().item())
+
+
+@pytest.mark.parametrize("shape", [(1, 64, 540, 960), (1, 64, 1080, 1920)])
+def test_ss2d_core_vs_arbiter_at_4k_level_sizes(ops, dev, params_cache, shape):
+    """The SS2D core at the sizes bench.py runs (BASELINE configs[2]: 4K level-2 and level-1 maps,
+    L = 518 400 / 2 073 600, the production chunk plans) against the fp64 arbiter; same tolerance
+    as the small shapes: |gpu - f64| <= 2e-5 * max(1, max|y|)."""
+    g = torch.Generator().manual_seed(0)
+    x = F.silu(0.5 * torch.randn(*shape, generator=g))
+    prm = _ss_params(params_cache)
+    got = ops.ss2d_core(x.to(dev), *[t.to(dev) for t in prm]).cpu()
+    want64 = _arbiter_streamed(x, prm)
+    scale = max(1.0, want64.abs().max().item())
+    diff = (got.double() - want64).abs()
+    err = diff.max().item()
+    print(f"{shape}: gpu-vs-f64 max {err:.2e} rms {diff.pow(2).mean().sqrt().item():.2e} (scale {scale:.2f})")
+    assert err <= 2e-5 * scale
+
+
 def test_ss2d_core_is_deterministic(ops, dev, params_cache):
     x = F.silu(torch.randn(2, 64, 48, 72, device=dev))
     prm = [t.to(dev) for t in _ss_params(params_cache)]
@@ -237,6 +289,22 @@ def test_pw_plain_gate_and_residual(ops, dev):
     a, b2 = x.chunk(2, dim=1)
     want = F.conv2d(F.gelu(a) * b2, w_, b_)
     torch.testing.assert_close(ops.pw(d(x), d(w_), d(b_), gate=True).cpu(), want, rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("hw", [(11, 29), (12, 30)])
+def test_pw_per_image_weights_on_a_channel_slice(ops, dev, hw):
+    """CMTAttention tail (reference :791-797, :849): v is the last third of the qkv tensor (batch
+    stride 96*h*w) and every image has its own 32x32 matrix (project_out folded with the attention);
+    one launch.  Odd and even pixel counts take the one- and the two-pixel kernels."""
+    g = torch.Generator().manual_seed(12)
+    B, (h, w) = 3, hw
+    qkv = _rand(B, 96, h, w, g=g).to(dev)
+    wts = _rand(B, 32, 32, g=g, s=0.2).to(dev)
+    bias, res = _rand(32, g=g, s=0.1).to(dev), _rand(B, 32, h, w, g=g).to(dev)
+    v = qkv[:, 64:]
+    want = torch.einsum("boc,bchw->bohw", wts.double(), v.double()) + bias.double().view(1, -1, 1, 1) + res.double()
+    got = ops.pw(v, wts, bias, residual=res)
+    assert (got.double() - want).abs().max().item() <= 2e-5 * max(1.0, want.abs().max().item())
 
 
 def test_paconv_gate_and_layernorm2d(ops, dev):
@@ -373,18 +441,9 @@ def test_gram32_argmin_matches_cdist_oracle(ops, dev):
 
 
 # ------------------------------------------------------------------------------- dense 3x3 conv
-@pytest.fixture(params=["mma", "tcgen05"])
-def conv_impl(request, ops):
-    """Both implementations behind wm_conv3x3_fwd: mma.sync and tcgen05/TMEM."""
-    prev = ops.get_conv_impl()
-    ops.set_conv_impl(request.param)
-    yield request.param
-    ops.set_conv_impl(prev)
-
-
 @pytest.mark.parametrize("cin,cout", [(64, 32), (64, 64), (32, 96), (32, 32)])
 @pytest.mark.parametrize("hw", [(13, 37), (8, 32), (40, 70)])
-def test_conv3x3_plain(ops, dev, conv_impl, cin, cout, hw):
+def test_conv3x3_plain(ops, dev, cin, cout, hw):
     """3xTF32 tensor-core conv vs float64 F.conv2d: fp32-level accuracy (not TF32-level)."""
     g = torch.Generator().manual_seed(31)
     h, w = hw
@@ -399,7 +458,7 @@ def test_conv3x3_plain(ops, dev, conv_impl, cin, cout, hw):
     assert err <= 2e-5 * max(1.0, want.abs().max().item())
 
 
-def test_conv3x3_two_inputs_with_channel_gather(ops, dev, conv_impl):
+def test_conv3x3_two_inputs_with_channel_gather(ops, dev):
     g = torch.Generator().manual_seed(32)
     B, h, w = 2, 19, 45
     xa = _rand(B, 32, h, w, g=g)
@@ -417,7 +476,7 @@ def test_conv3x3_two_inputs_with_channel_gather(ops, dev, conv_impl):
     assert (got - want).abs().max().item() <= 2e-5 * max(1.0, want.abs().max().item())
 
 
-def test_conv3x3_paconv_gate(ops, dev, conv_impl):
+def test_conv3x3_paconv_gate(ops, dev):
     """PAConv stage A: k3(x) * sigmoid(k2(x) + b) in one kernel (reference :694-697)."""
     g = torch.Generator().manual_seed(33)
     x = _rand(2, 64, 21, 50, g=g)
@@ -427,6 +486,49 @@ def test_conv3x3_paconv_gate(ops, dev, conv_impl):
         F.conv2d(x.double(), k2w.double(), k2b.double()))
     got = ops.conv3x3(x.to(dev), k3.to(dev), gate_w=k2w.to(dev), gate_b=k2b.to(dev)).cpu().double()
     assert (got - want).abs().max().item() <= 2e-5 * max(1.0, want.abs().max().item())
+
+
+@pytest.mark.parametrize("cin,cout,gate", [(64, 64, True), (64, 32, False), (64, 64, False),
+                                           (32, 96, False), (32, 32, False)])
+def test_conv3x3_many_tiles_per_cta(ops, dev, cin, cout, gate):
+    """A map large enough that every persistent CTA walks several tiles (638 tiles on 148 SMs): the
+    weight ring, the two X slabs and the TMEM accumulator buffers all wrap their mbarrier phases more
+    than once.  Reference: fp64 convolution on the GPU; ragged right/bottom tiles included."""
+    g = torch.Generator().manual_seed(36)
+    B, h, w = 2, 200, 330
+    x = _rand(B, cin, h, w, g=g).to(dev)
+    wt = _rand(cout, cin, 3, 3, g=g, s=0.1).to(dev)
+    if gate:
+        k2w, k2b = _rand(cout, cin, 1, 1, g=g, s=0.2).to(dev), _rand(cout, g=g, s=0.1).to(dev)
+        want = F.conv2d(x.double(), wt.double(), None, padding=1) * torch.sigmoid(
+            F.conv2d(x.double(), k2w.double(), k2b.double()))
+        got = ops.conv3x3(x, wt, gate_w=k2w, gate_b=k2b)
+    else:
+        bias = _rand(cout, g=g, s=0.1).to(dev)
+        want = F.conv2d(x.double(), wt.double(), bias.double(), padding=1)
+        got = ops.conv3x3(x, wt, bias)
+    err = (got.double() - want).abs().max().item()
+    assert err <= 2e-5 * max(1.0, want.abs().max().item()), err
+    assert torch.equal(got, ops.conv3x3(x, wt, gate_w=k2w, gate_b=k2b) if gate else ops.conv3x3(x, wt, bias))
+
+
+def test_conv_pack_cache_sees_data_writes(ops, dev):
+    """The pre-pack cache must not serve stale weights after a write through ``.data`` (which does
+    not bump ``_version``) once ``clear_pack_cache`` is called, nor after an in-place ``copy_``."""
+    g = torch.Generator().manual_seed(37)
+    x = _rand(1, 32, 16, 40, g=g).to(dev)
+    w = torch.nn.Parameter(_rand(32, 32, 3, 3, g=g, s=0.1).to(dev))
+    w2 = _rand(32, 32, 3, 3, g=g, s=0.1).to(dev)
+    y1 = ops.conv3x3(x, w)
+    with torch.no_grad():
+        w.copy_(w2)                                   # bumps _version
+    y2 = ops.conv3x3(x, w)
+    torch.testing.assert_close(y2, F.conv2d(x, w2, None, padding=1), rtol=2e-5, atol=2e-5)
+    w.data.mul_(2.0)                                  # behind autograd's back
+    ops.clear_pack_cache()
+    y3 = ops.conv3x3(x, w)
+    torch.testing.assert_close(y3, 2.0 * y2, rtol=2e-5, atol=2e-5)
+    assert not torch.equal(y1, y2)
 
 
 def test_stem_and_head_conv(ops, dev):
@@ -539,7 +641,6 @@ def test_conv3x3_channel_quad_layout(ops, dev, shape):
     """PAConv k3 (+k2 gate, gathered second input) -> k4 through the (B, C/4, h, w, 4) intermediate:
     identical to the NCHW path bit for bit (same arithmetic, different addressing) and within 2e-5
     of the fp64 reference (reference :694-698)."""
-    ops.set_conv_impl("tcgen05")
     g = torch.Generator().manual_seed(35)
     B, h, w = shape
     x, per = _rand(B, 32, h, w, g=g), _rand(B, 32, h, w, g=g)

@@ -49,6 +49,14 @@ def _worker(rank, world, port, batch_size, result_queue):
         ok = True
         if rank == 0:
             ok = torch.allclose(out, ref(batch))
+        # uint8 batch (the configs[3] edge format), ragged shards, a shape-preserving map
+        u8 = (torch.arange(batch_size * 6 * 5 * 3) % 251).to(torch.uint8).view(batch_size, 6, 5, 3) \
+            if rank == 0 else None
+        out8 = parallel.sharded_forward(lambda t: 255 - t, u8, torch.device("cpu"), src=0)
+        if rank == 0:
+            ok = ok and out8.dtype == torch.uint8 and torch.equal(out8, 255 - u8)
+        else:
+            ok = ok and out8 is None
         result_queue.put((rank, bool(same), bool(ok)))
     finally:
         dist.destroy_process_group()

@@ -19,14 +19,12 @@ ap.add_argument("--tf32", type=int, default=0)
 ap.add_argument("--height", type=int, default=2160)
 ap.add_argument("--width", type=int, default=3840)
 ap.add_argument("--rows", type=int, default=45)
-ap.add_argument("--conv-impl", default="tcgen05", choices=["mma", "tcgen05"])
 args = ap.parse_args()
 
 torch.backends.cudnn.benchmark = True
 torch.backends.cudnn.allow_tf32 = bool(args.tf32)
 torch.backends.cuda.matmul.allow_tf32 = False
 dev = torch.device("cuda:0")
-wm.ops.set_conv_impl(args.conv_impl)
 params = torch.load(os.path.join(ROOT, "ckpt", "WaveMamba_UHDLL.pth"), map_location="cpu")["params"]
 net = wm.WaveMamba(in_chn=3, wf=32, n_l_blocks=[1, 2, 4], n_h_blocks=[1, 1, 2], ffn_scale=2.0)
 net.load_state_dict(params, strict=True)

@@ -1,8 +1,9 @@
 """Import the UNMODIFIED reference (``/root/reference``) inside the build container.
 
-Build-container tooling only (tools/make_golden.py and the tests that are skipped when
-/root/reference is absent).  Nothing here travels into the product path, and nothing
-here is read on the GPU box.
+Test tooling only: tools/make_golden.py (build container), the tests that are skipped when
+the reference tree is absent, and tests/test_reference_scripts_gpu.py, which runs the reference's
+own drivers from the staged copy baseline/_ref (tools/stage_reference.py).  Nothing here is part
+of the product path.
 
 The reference needs four packages that are not installed here:
 ``timm`` (DropPath/to_2tuple/trunc_normal_), ``lmdb``, ``pyiqa`` and ``mamba_ssm``.  Tiny
@@ -96,6 +97,32 @@ def install(reference_root: str = REFERENCE_ROOT):
     sys.modules.setdefault("mamba_ssm", mamba)
     sys.modules.setdefault("mamba_ssm.ops", mamba_ops)
     sys.modules.setdefault("mamba_ssm.ops.selective_scan_interface", mamba_if)
+
+    # inference_wavemamba.py:16-18 builds an LPIPS metric at import time (torchmetrics is absent and
+    # its AlexNet weights would need the network); the stand-in reports 0
+    tm = types.ModuleType("torchmetrics")
+    tm_image = types.ModuleType("torchmetrics.image")
+    tm_lpip = types.ModuleType("torchmetrics.image.lpip")
+
+    class _ZeroLPIPS:
+        def __init__(self, *a, **k):
+            pass
+
+        def __call__(self, a, b):
+            return torch.zeros(())
+
+    tm_lpip.LearnedPerceptualImagePatchSimilarity = _ZeroLPIPS
+    tm.image = tm_image
+    tm_image.lpip = tm_lpip
+    sys.modules.setdefault("torchmetrics", tm)
+    sys.modules.setdefault("torchmetrics.image", tm_image)
+    sys.modules.setdefault("torchmetrics.image.lpip", tm_lpip)
+
+    # comput_psnr_ssim.py:5 imports skimage.metrics but only mentions it in comments
+    sk = types.ModuleType("skimage")
+    sk.metrics = types.ModuleType("skimage.metrics")
+    sys.modules.setdefault("skimage", sk)
+    sys.modules.setdefault("skimage.metrics", sk.metrics)
 
     sys.modules.setdefault("lmdb", types.ModuleType("lmdb"))
     sys.modules.setdefault("pyiqa", _Anything("pyiqa"))

@@ -12,7 +12,7 @@ from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libwavemamba_b200.so")
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 # name -> (restype, argtypes); mirrors include/wavemamba_b200.h one to one
 SIGNATURES = {
@@ -29,15 +29,13 @@ SIGNATURES = {
     "wm_layernorm2d_fwd": (c_int, [c_void_p] * 3 + [c_float, c_void_p] + [c_int64] * 4 + [c_void_p]),
     "wm_pw_dw_fwd": (c_int, [c_void_p] * 3 + [c_float] + [c_void_p] * 4 + [c_int, c_void_p] + [c_int64] * 5 + [c_void_p]),
     "wm_dw_act_pw_fwd": (c_int, [c_void_p] * 5 + [c_int] + [c_void_p] * 2 + [c_int64] * 4 + [c_void_p]),
-    "wm_pw_fwd": (c_int, [c_void_p] * 3 + [c_int] + [c_void_p] * 3 + [c_int64] * 5 + [c_void_p]),
+    "wm_pw_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int] + [c_void_p] * 3 + [c_int64] * 5 + [c_void_p]),
     "wm_lfss_z_fwd": (c_int, [c_void_p] * 3 + [c_float] + [c_void_p] * 2 + [c_int64] * 3 + [c_void_p]),
     "wm_lfss_out_fwd": (c_int, [c_void_p] * 7 + [c_float] + [c_void_p] * 4 + [c_int64] * 3 + [c_void_p]),
     "wm_gram32_workspace_bytes": (c_size_t, [c_int64] * 2),
     "wm_gram32_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_size_t,
                               c_int64, c_int64, c_void_p]),
     "wm_conv3x3_packed_bytes": (c_size_t, [c_int64, c_int64, c_int]),
-    "wm_conv3x3_set_impl": (c_int, [c_int]),
-    "wm_conv3x3_get_impl": (c_int, []),
     "wm_conv3x3_debug_timing": (c_int, [c_void_p]),
     "wm_conv3x3_prepack": (c_int, [c_void_p] * 3 + [c_int64] * 2 + [c_void_p]),
     "wm_conv3x3_fwd": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64] + [c_void_p] * 5 +

@@ -1,7 +1,7 @@
 // Dense 3x3 convolution on the 5th-generation tensor cores: tcgen05.mma kind::tf32 with the
-// accumulators in TMEM, fp32-accurate through the 3xTF32 split.  Same contract as conv3x3.cu
-// (NCHW in/out, two-source input with channel gather, PAConv gate fused); selected by
-// wm_conv3x3_set_impl(1).
+// accumulators in TMEM, fp32-accurate through the 3xTF32 split.  NCHW in/out, two-source input with
+// a per-image channel gather (the reference's torch.cat + Matching gather, wavemamba_arch.py:716,
+// :975), PAConv's 1x1 sigmoid gate fused as a 10th tap (:694-697).
 //
 // Implicit GEMM without im2col.  Shared memory holds the halo tile in the K-major *no-swizzle*
 // UMMA canonical layout  X[kc = ci/4][position][ci%4]  (16 bytes per (kc, position)); with
@@ -14,14 +14,23 @@
 // 3xTF32: the tensor core reads the top 19 bits of an fp32 word, so the "hi" operand is the raw
 // activation and only lo = a - trunc(a) needs a second copy; weights are split (rna) at prepack.
 //   [acc | acc2] += a_hi*[b_hi | b_lo]  (one MMA, N = 2*COUT) ; acc += a_lo*b_hi  (N = COUT)
-//   fp32 accumulate in TMEM, acc + acc2 in the epilogue.  The SS-mode MMA is bound by reading the
-//   activation operand from shared memory, so the merged N halves the a_hi reads.
+//   fp32 accumulate in TMEM, acc + acc2 in the epilogue.
 //
-// Persistent: one CTA per SM (217 KB of shared memory, TMEM allocated once) loops over tiles.
-// Per tile: finish the cp.async halo staging -> MMA pipeline over a 3-deep cp.async weight ring
-// (one thread issues tcgen05.mma, tcgen05.commit -> mbarrier frees ring slots) -> start the NEXT
-// tile's halo loads -> all 8 warps drain TMEM with tcgen05.ld.32x32b and run the epilogue while
-// those loads are in flight.
+// Warp-specialised, persistent (one CTA per SM, 14 warps), everything synchronised with mbarriers --
+// no CTA-wide barrier inside the tile loop:
+//   warps 0-3   X producers: a work unit is (tile, 32-channel K half); its halo slab is loaded
+//               global -> registers (all 76 loads of a thread in flight) -> shared as hi AND lo
+//               (the 3xTF32 split is fused into the staging), two slabs ring-buffered, so the next
+//               unit is staged while the tensor core works on the current one
+//   warp 12     weight producer: one TMA bulk copy (cp.async.bulk + mbarrier complete_tx) per
+//               (tap, K half) chunk into a 3/4-deep ring; the prepacked layout is the shared layout
+//   warp 13     MMA issuer: one thread, tcgen05.mma; tcgen05.commit frees ring stages / X slabs and
+//               publishes the accumulators
+//   warps 4-11  epilogue: tcgen05.ld -> bias or k3*sigmoid(k2+b) -> NCHW / channel-quad stores; the
+//               accumulators are double-buffered in TMEM when 2 x columns <= 512 (all variants but
+//               the gated 64->64 and the 32->96 one), so the epilogue overlaps the next tile's MMAs
+#include <atomic>
+
 #include "common.cuh"
 
 namespace wm {
@@ -29,17 +38,22 @@ namespace tc5 {
 
 constexpr int kR = 7, kTW = 32;             // tile: 7 rows x 32 columns
 constexpr int kHW = kTW + 2;                // halo row length 34
-constexpr int kHaloPos = (kR + 2) * kHW;    // 306 real halo positions
-constexpr int kNPos = kHaloPos;             // rows m > 235 of the M window are dropped: their reads
-                                            // may run past a K-chunk block into the next one (still
-                                            // inside this CTA's shared memory), harmless garbage
+constexpr int kHaloRows = kR + 2;           // 9
+constexpr int kNPos = kHaloRows * kHW;      // 306 halo positions; rows m > 235 of the M window are
+                                            // dropped: their reads run past a K-chunk block into the
+                                            // next one (still inside this CTA's shared memory)
 constexpr int kQ0 = kHW + 1;                // halo position of output (0,0) of the tile
-constexpr int kThreads = 256;
-constexpr int kStages = 4;                  // weight-chunk ring depth (prefetch distance 3)
+constexpr int kKcSlab = 8;                  // 16-byte K chunks per slab (32 channels)
+constexpr int kSlabF4 = kKcSlab * kNPos;    // float4 per slab and per part (hi or lo)
+constexpr int kProdWarps = 4, kEpiWarps = 8;
+constexpr int kProdThreads = 32 * kProdWarps;
+constexpr int kWarpW = kProdWarps + kEpiWarps;       // weight producer warp
+constexpr int kWarpMma = kWarpW + 1;                  // MMA issuer warp
+constexpr int kThreads = 32 * (kWarpMma + 1);         // 448
 
-// optional per-CTA phase timing (cycles), enabled with wm_conv3x3_debug_timing(ptr != NULL):
-// [0] wait for staged X  [1] xlo  [2] chunk loop  [3] drain  [4] issue next stage  [5] epilogue
-static long long *g_dbg = nullptr;
+// optional per-CTA timing of the MMA thread (cycles), enabled with wm_conv3x3_debug_timing(ptr):
+// [0] total  [1] wait weights  [2] wait X  [3] wait accumulator buffer  [4] issue  [5] tiles
+static std::atomic<long long *> g_dbg{nullptr};
 
 struct Args {
     long long *dbg;
@@ -49,13 +63,13 @@ struct Args {
     const float *in_b;
     int64_t b_bstride;
     const int *chan_map;
-    const float4 *packed;    // [ntaps][2 (hi,lo)][CIN/4][COUT] float4 (4 consecutive ci)
+    const float4 *packed;    // [tap][part][kc 0..7][hi|lo][COUT] float4 (4 consecutive ci)
     const float *bias;
     const float *gate_bias;
     float *out;
     int h, w;
-    // channel-quad layouts (B, C/4, h, w, 4): a 16-byte cp.async / store moves the 4 channels of one
-    // K chunk at once.  in_c4 needs Ca == CIN (no second input); used between PAConv.k3 and k4.
+    // channel-quad layouts (B, C/4, h, w, 4): one 16-byte access moves the 4 channels of a K chunk.
+    // in_c4 needs Ca == CIN (no second input); used between PAConv.k3 and k4.
     int in_c4, out_c4;
 };
 
@@ -87,21 +101,49 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t tmem_d, uint64_t adesc, uin
         : "memory");
 }
 
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+// Blocks until the phase with parity `parity` has completed.  try_wait suspends the thread in
+// hardware for a bounded time; the retry loop is bounded too (a protocol bug traps instead of
+// hanging the GPU).
 __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity)
 {
     uint32_t ok = 0;
 #pragma unroll 1
-    for (int spin = 0; spin < (1 << 22); ++spin) {   // non-blocking probe, bounded (~0.3 s)
+    for (int spin = 0; spin < (1 << 20); ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}\n"
             : "=r"(ok)
             : "r"(mbar), "r"(parity)
             : "memory");
         if (ok) return;
     }
-    __trap();   // never hang the GPU on a protocol bug
+    __trap();
+}
+// tcgen05.commit: the mbarrier gets one arrival when every MMA issued so far by this thread is done
+__device__ __forceinline__ void mma_commit(uint32_t mbar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t mbar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(mbar)
+        : "memory");
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
@@ -119,345 +161,364 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
     asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
 
-template <int COUT, bool GATE>
-constexpr int tmem_cols()
+__device__ __forceinline__ float tf32_lo(float v)
 {
-    // per M tile: COUT columns for a_hi*b_hi + a_lo*b_hi and COUT columns for a_hi*b_lo
-    constexpr int need = 2 * 2 * COUT * (GATE ? 2 : 1);
-    return need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
+    return v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
 }
+
+template <int CIN, int COUT, bool GATE>
+struct Cfg {
+    static constexpr int NCH = CIN / 32;                       // K halves (slabs) per tile
+    static constexpr int NTAPS = GATE ? 10 : 9;
+    static constexpr int kChunkF4 = kKcSlab * 2 * COUT;        // float4 per weight chunk
+    static constexpr int kChunkBytes = kChunkF4 * 16;
+    static constexpr int kStages = COUT >= 96 ? 3 : 4;         // weight ring depth
+    static constexpr int kColsBuf = 4 * COUT * (GATE ? 2 : 1); // TMEM columns of one accumulator set
+    static constexpr int NACC = 2 * kColsBuf <= 512 ? 2 : 1;
+    static constexpr int kColsNeed = NACC * kColsBuf;
+    static constexpr int kCols = kColsNeed <= 32 ? 32 : kColsNeed <= 64 ? 64 : kColsNeed <= 128 ? 128
+                                 : kColsNeed <= 256 ? 256 : 512;
+    static constexpr int kNumBars = 2 * kStages + 4 + 2 * NACC;
+    static constexpr size_t kSmem = sizeof(float4) * (size_t)(4 * kSlabF4 + kStages * kChunkF4) +
+                                    8 * kNumBars + 16;
+    static_assert(CIN == 32 || CIN == 64, "CIN must be 32 or 64");
+    static_assert(2 * COUT <= 256 && (2 * COUT) % 16 == 0, "merged N must be a legal UMMA N");
+    static_assert(kColsNeed <= 512, "accumulators do not fit TMEM");
+    static_assert(kSmem <= 232448, "shared memory budget");
+};
 
 template <int CIN, int COUT, bool GATE>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
 {
-    constexpr int KC = CIN / 4;                 // 16-byte K chunks
-    constexpr int KS = CIN / 8;                 // MMA k-steps (K = 8 for tf32)
-    constexpr int NTAPS = GATE ? 10 : 9;
-    constexpr int kWF4 = KC * COUT;             // float4 per weight part (hi or lo) per tap
-    constexpr int NCH = CIN >= 64 ? 2 : 1;      // weight chunks per tap (K split so the ring fits)
-    constexpr int KSC = KS / NCH;               // k-steps per chunk
-    constexpr int kCF4 = 2 * kWF4 / NCH;        // float4 per chunk: [hi | lo][2*KSC kc][COUT]
-    constexpr int kCols = tmem_cols<COUT, GATE>();
-    constexpr int NCHUNK = NTAPS * NCH;
-    static_assert(NCHUNK >= 4, "pipeline prologue assumes at least four chunks");
+    using C = Cfg<CIN, COUT, GATE>;
+    constexpr int NCH = C::NCH, NTAPS = C::NTAPS, kStages = C::kStages, NACC = C::NACC;
     extern __shared__ __align__(128) float smem[];
-    float4 *xhi = reinterpret_cast<float4 *>(smem);          // [KC][kNPos]
-    float4 *xlo = xhi + KC * kNPos;                          // [KC][kNPos]
-    float4 *wbuf = xlo + KC * kNPos;                         // [kStages][kCF4]
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(wbuf + kStages * kCF4);   // [kStages]: chunk's MMAs done
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mbar + kStages);
+    float4 *xhi = reinterpret_cast<float4 *>(smem);                 // [2 slots][8 kc][kNPos]
+    float4 *xlo = xhi + 2 * kSlabF4;                                // [2 slots][8 kc][kNPos]
+    float4 *wbuf = xlo + 2 * kSlabF4;                               // [kStages][kChunkF4]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(wbuf + kStages * C::kChunkF4);
+    const uint32_t bar0 = smem_u32(bars);
+    // barrier map (8 bytes each)
+    auto wfull = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+    auto wempty = [&](int i) { return bar0 + 8u * (uint32_t)(kStages + i); };
+    auto xfull = [&](int i) { return bar0 + 8u * (uint32_t)(2 * kStages + i); };
+    auto xempty = [&](int i) { return bar0 + 8u * (uint32_t)(2 * kStages + 2 + i); };
+    auto accfull = [&](int i) { return bar0 + 8u * (uint32_t)(2 * kStages + 4 + i); };
+    auto accempty = [&](int i) { return bar0 + 8u * (uint32_t)(2 * kStages + 4 + NACC + i); };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + C::kNumBars);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int h = a.h, w = a.w;
     const int64_t hw = (int64_t)h * w;
 
-    // chunk c of the packed weights: tap = c / NCH, K part = c % NCH.  Packed per tap as
-    // [hi|lo][kc][co]; a chunk takes kc in [part*2*KSC, (part+1)*2*KSC) of both hi and lo.
-    auto issue_chunk = [&](int c) {
-        const int tap = c / NCH, part = c - tap * NCH;
-        const float4 *src = a.packed + (int64_t)tap * 2 * kWF4 + part * (2 * KSC * COUT);
-        float4 *dst = wbuf + (c % kStages) * kCF4;
-        constexpr int kHalf = 2 * KSC * COUT;               // float4 of hi (or lo) per chunk
-        for (int i = tid; i < kCF4; i += kThreads) {
-            // shared layout [kc][hi co 0..COUT-1 | lo co 0..COUT-1]: one B operand of N = 2*COUT rows
-            // (a_hi x [b_hi | b_lo] in a single MMA) whose first COUT rows are the b_hi operand
-            const int hl = i / kHalf, r = i - hl * kHalf;
-            const int kcl = r / COUT, co = r - kcl * COUT;
-            const uint32_t d = smem_u32(dst + (kcl * 2 + hl) * COUT + co);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + hl * kWF4 + r)
-                         : "memory");
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-
-    // Halo tile of `tile` -> xhi via 4-byte cp.async (zero fill outside the image): no register
-    // staging, every load of the tile in flight at once.  Warp w takes channels w, w+8, ...; lanes
-    // run along a halo row (34 floats: lanes 0,1 also take the tail).  One commit group.
-    auto issue_stage = [&](int tile) {
-        const int txi = tile % tiles_x, tyi = (tile / tiles_x) % tiles_y;
-        const int64_t b = tile / (tiles_x * tiles_y);
-        const int tx0 = txi * kTW, ty0 = tyi * kR;
-        const uint32_t xhi_base = smem_u32(xhi);
-        const int gx0 = tx0 - 1 + lane, gx1 = tx0 + 31 + lane;
-        const bool okx0 = gx0 >= 0 && gx0 < w;
-        const bool okx1 = lane < 2 && gx1 < w;
-        if (a.in_c4) {
-            // (kc, position) elements are 16 contiguous bytes on both sides: one cp.async each
-            const float4 *src4 = reinterpret_cast<const float4 *>(a.in_a + b * a.a_bstride);
-#pragma unroll 1
-            for (int kc = warp; kc < KC; kc += kThreads / 32) {
-                const float4 *plane4 = src4 + (int64_t)kc * hw;
-                const uint32_t dst_k = xhi_base + (uint32_t)(kc * kNPos) * 16u;
-#pragma unroll
-                for (int py = 0; py < kR + 2; ++py) {
-                    const int gy = ty0 - 1 + py;
-                    const bool oky = gy >= 0 && gy < h;
-                    const float4 *row = plane4 + (int64_t)(oky ? gy : 0) * w;
-                    const uint32_t dst = dst_k + (uint32_t)(py * kHW + lane) * 16u;
-                    const bool ok0 = oky && okx0;
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst),
-                                 "l"(ok0 ? row + gx0 : plane4), "r"(ok0 ? 16u : 0u)
-                                 : "memory");
-                    if (lane < 2) {
-                        const bool ok1 = oky && okx1;
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + 32u * 16u),
-                                     "l"(ok1 ? row + gx1 : plane4), "r"(ok1 ? 16u : 0u)
-                                     : "memory");
-                    }
-                }
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            return;
-        }
-#pragma unroll 1
-        for (int c = warp; c < CIN; c += kThreads / 32) {
-            const float *plane;
-            if (c < a.Ca) {
-                plane = a.in_a + b * a.a_bstride + (int64_t)c * hw;
-            } else {
-                const int cb = a.chan_map ? __ldg(a.chan_map + b * (CIN - a.Ca) + (c - a.Ca)) : c - a.Ca;
-                plane = a.in_b + b * a.b_bstride + (int64_t)cb * hw;
-            }
-            // element (c, pos) lives at float index ((c/4)*kNPos + pos)*4 + c%4
-            const uint32_t dst_c = xhi_base + (uint32_t)(((c >> 2) * kNPos) * 4 + (c & 3)) * 4u;
-#pragma unroll
-            for (int py = 0; py < kR + 2; ++py) {
-                const int gy = ty0 - 1 + py;
-                const bool oky = gy >= 0 && gy < h;
-                const float *row = plane + (int64_t)(oky ? gy : 0) * w;
-                const uint32_t dst = dst_c + (uint32_t)(py * kHW + lane) * 16u;
-                const bool ok0 = oky && okx0;
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst),
-                             "l"(ok0 ? row + gx0 : plane), "r"(ok0 ? 4u : 0u)
-                             : "memory");
-                if (lane < 2) {
-                    const bool ok1 = oky && okx1;
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + 32u * 16u),
-                                 "l"(ok1 ? row + gx1 : plane), "r"(ok1 ? 4u : 0u)
-                                 : "memory");
-                }
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-
-    // ---- one-time setup: TMEM allocation (warp 0), mbarrier init (one thread) ---------------
-    if (warp == 0) {
+    // ---- one-time setup: barriers (one thread), TMEM allocation (the MMA warp) ---------------
+    if (tid == 0) {
+        for (int i = 0; i < kStages; ++i) { mbar_init(wfull(i), 1); mbar_init(wempty(i), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(xfull(i), kProdThreads); mbar_init(xempty(i), 1); }
+        for (int i = 0; i < NACC; ++i) { mbar_init(accfull(i), 1); mbar_init(accempty(i), kEpiWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kWarpMma) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                          smem_u32(tmem_slot)),
-                     "r"((uint32_t)kCols)
+                     "r"((uint32_t)C::kCols)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (tid == 32) {
-#pragma unroll
-        for (int i = 0; i < kStages; ++i)
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar + i)) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    int tile = blockIdx.x;
-    if (tile < total_tiles) issue_stage(tile);
-
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
-    // instruction descriptors: D=f32, A=B=tf32, both K-major, M = 128; N = COUT (b_hi only) or
-    // N = 2*COUT ([b_hi | b_lo]: the activation operand is read from shared memory once for both)
-    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(COUT >> 3) << 17) |
-                               ((uint32_t)(128 >> 4) << 24);
-    constexpr uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * COUT) >> 3) << 17) |
-                                ((uint32_t)(128 >> 4) << 24);
-    static_assert(2 * COUT <= 256 && (2 * COUT) % 16 == 0, "merged N must be a legal UMMA N");
-    // descriptors differ only in the 14-bit start-address field (bytes >> 4): build the bases once
-    // and add offsets per MMA (all of this CTA's shared memory is below 256 KB, no carry out)
-    const uint64_t a_hi0 = make_desc(smem_u32(xhi), kNPos * 16u, 128u);
-    const uint64_t a_lo0 = make_desc(smem_u32(xlo), kNPos * 16u, 128u);
-    const uint64_t b_00 = make_desc(smem_u32(wbuf), 2 * COUT * 16u, 128u);
-    uint32_t phase_bits = 0u;                               // bit i: parity to wait for on mbar[i]
-    long long tacc[6] = {0, 0, 0, 0, 0, 0}, tprev = clock64();
-#define WM_TICK(k) do { if (a.dbg) { const long long _t = clock64(); tacc[k] += _t - tprev; tprev = _t; } } while (0)
-
-    // Persistent loop over this CTA's tiles.  Per tile: [finish staging X] -> [MMA pipeline over
-    // weight chunks] -> [start staging the NEXT tile's X, asynchronously] -> [epilogue from TMEM].
+    if (warp < kProdWarps) {
+        // =============================== X producers ========================================
+        // warp pw stages K chunks 2pw, 2pw+1 of the slab: 18 halo rows, lanes along the row
+        // (columns 0..31); the two tail columns of all 72 rows are spread over the 128 threads.
+        const int pw = warp;
+        uint32_t unit = 0;
 #pragma unroll 1
-    for (; tile < total_tiles; tile += gridDim.x) {
-        const int txi = tile % tiles_x, tyi = (tile / tiles_x) % tiles_y;
-        const int64_t b = tile / (tiles_x * tiles_y);
-        const int tx0 = txi * kTW, ty0 = tyi * kR;
-
-        issue_chunk(0);                          // first three weight chunks of this tile
-        issue_chunk(1);
-        issue_chunk(2);
-        if (a.dbg) tprev = clock64();
-        asm volatile("cp.async.wait_group 3;" ::: "memory");   // X(tile) landed (older than all three)
-        __syncthreads();
-        WM_TICK(0);
-        for (int i = tid; i < KC * kNPos; i += kThreads) {      // xlo = a - trunc_tf32(a)
-            const float4 v = xhi[i];
-            float4 lo;
-            lo.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-            lo.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-            lo.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-            lo.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-            xlo[i] = lo;
-        }
-        WM_TICK(1);
-
-        // 4-deep weight ring: the MMAs of chunk c run while chunks c+1..c+3 are copied; slot
-        // (c+3)%4 is free once the MMAs of chunk c-1 (committed to mbar[(c-1)%4]) completed.
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int txi = tile % tiles_x, tyi = (tile / tiles_x) % tiles_y;
+            const int64_t b = tile / (tiles_x * tiles_y);
+            const int tx0 = txi * kTW, ty0 = tyi * kR;
+            const int gx = tx0 - 1 + lane;
+            const bool okx = gx >= 0 && gx < w;
 #pragma unroll 1
-        for (int c = 0; c < NCHUNK; ++c) {
-            // groups issued so far: chunks 0 .. min(c+2, NCHUNK-1); chunk c must have landed
-            if (c + 2 < NCHUNK) asm volatile("cp.async.wait_group 2;" ::: "memory");
-            else if (c + 1 < NCHUNK) asm volatile("cp.async.wait_group 1;" ::: "memory");
-            else asm volatile("cp.async.wait_group 0;" ::: "memory");
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncthreads();                                // chunk c weights (and X) visible
-            if (tid == 0) {
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const int tap = c / NCH, part = c - tap * NCH;
-                const bool gate_tap = GATE && tap == 9;
-                const int dy = gate_tap ? 1 : tap / 3, dx = gate_tap ? 1 : tap - (tap / 3) * 3;
-                // offsets in 16-byte units (= float4 = one (kc, position) or (kc, co) element)
-                const uint32_t shift = (uint32_t)(dy * kHW + dx);
-                const uint64_t b_hi0 = b_00 + (uint32_t)(c % kStages) * kCF4;
+            for (int part = 0; part < NCH; ++part, ++unit) {
+                const int slot = unit & 1;
+                float4 v[18];
+                float4 vt[2];
+                // tail items: item i -> row (kc = i / 18, py = (i % 18) / 2), column 32 + (i & 1)
+                int t_kc[2], t_py[2], t_px[2];
 #pragma unroll
-                for (int mt = 0; mt < 2; ++mt) {
-                    const uint32_t dcol = tmem_base + (uint32_t)((gate_tap ? 4 * COUT : 0) + mt * 2 * COUT);
-                    const uint32_t arow = shift + (uint32_t)mt * 128u;
-#pragma unroll
-                    for (int kl = 0; kl < KSC; ++kl) {
-                        const int ks = part * KSC + kl;
-                        const uint32_t aoff = (uint32_t)(2 * ks) * kNPos + arow;
-                        const uint32_t boff = (uint32_t)(2 * kl) * 2 * COUT;
-                        const uint64_t a_hi = a_hi0 + aoff, a_lo = a_lo0 + aoff;
-                        const uint64_t b_hl = b_hi0 + boff;     // rows [0,COUT) = hi, [COUT,2COUT) = lo
-                        const uint32_t first = (ks == 0 && (tap == 0 || gate_tap)) ? 0u : 1u;
-                        mma_tf32_ss(dcol, a_hi, b_hl, idesc2, first);   // cols [0,COUT) += a_hi b_hi, [COUT,2COUT) += a_hi b_lo
-                        mma_tf32_ss(dcol, a_lo, b_hl, idesc, 1u);       // cols [0,COUT) += a_lo b_hi
-                    }
+                for (int q = 0; q < 2; ++q) {
+                    const int i = tid + q * kProdThreads;
+                    t_kc[q] = i / 18; t_py[q] = (i % 18) >> 1; t_px[q] = 32 + (i & 1);
                 }
-                asm volatile(
-                    "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                        smem_u32(mbar + (c % kStages)))
-                    : "memory");
-            }
-            if (c + 3 < NCHUNK) {
-                if (c >= 1) {                               // slot (c+3)%4 was read by chunk c-1
-                    const int i = (c - 1) % kStages;
-                    mbar_wait(smem_u32(mbar + i), (phase_bits >> i) & 1u);
-                    phase_bits ^= 1u << i;
-                }
-                issue_chunk(c + 3);
-            }
-        }
-        WM_TICK(2);
-        // drain: chunks NCHUNK-4 .. NCHUNK-1 (in-loop waits covered 0 .. NCHUNK-5)
-#pragma unroll 1
-        for (int c = NCHUNK - 4; c < NCHUNK; ++c) {
-            const int i = c % kStages;
-            mbar_wait(smem_u32(mbar + i), (phase_bits >> i) & 1u);
-            phase_bits ^= 1u << i;
-        }
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        WM_TICK(3);
-
-        // every MMA of this tile has completed: X is free -> start fetching the next tile's halo
-        // now; the loads fly while the accumulators are drained below
-        if (tile + (int)gridDim.x < total_tiles) issue_stage(tile + gridDim.x);
-        WM_TICK(4);
-
-        // ---- epilogue: TMEM -> registers -> NCHW -------------------------------------------
-        {
-            // warp w drains TMEM lane quarter w % 4; warps w and w+4 split the 32-channel groups
-            const int quarter = warp & 3, whalf = warp >> 2;
-            constexpr int NG = COUT / 32;                   // 32-channel groups per accumulator
-#pragma unroll 1
-            for (int mt = 0; mt < 2; ++mt) {
-                const int m = mt * 128 + quarter * 32 + lane;
-                const int q = kQ0 + m;
-                const int py = q / kHW, px = q - py * kHW;
-                const int gy = ty0 + py - 1, gx = tx0 + px - 1;
-                const bool ok = px >= 1 && px <= kTW && py <= kR && gy < h && gx < w;
-                const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-#pragma unroll 1
-                for (int g = whalf; g < NG; g += 2) {
-                    const int c0 = g * 32;
-                    uint32_t acc[32];
-                    {
-                        uint32_t part[32];
-                        tmem_ld32(lane_addr + (uint32_t)(mt * 2 * COUT + c0), acc);
-                        tmem_ld32(lane_addr + (uint32_t)(mt * 2 * COUT + COUT + c0), part);
+                if (a.in_c4) {
+                    const float4 *src4 = reinterpret_cast<const float4 *>(a.in_a + b * a.a_bstride);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(part[j]));
+                    for (int r = 0; r < 18; ++r) {
+                        const int kcl = 2 * pw + r / 9, py = r % 9;
+                        const int gy = ty0 - 1 + py;
+                        const bool ok = okx && gy >= 0 && gy < h;
+                        v[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (ok) v[r] = __ldg(src4 + (int64_t)(part * kKcSlab + kcl) * hw + (int64_t)gy * w + gx);
                     }
-                    if (GATE) {
-                        uint32_t gt[32], part[32];
-                        tmem_ld32(lane_addr + (uint32_t)(4 * COUT + mt * 2 * COUT + c0), gt);
-                        tmem_ld32(lane_addr + (uint32_t)(4 * COUT + mt * 2 * COUT + COUT + c0), part);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float z = (__uint_as_float(gt[j]) + __uint_as_float(part[j])) +
-                                            __ldg(a.gate_bias + c0 + j);
-                            acc[j] = __float_as_uint(__fdividef(__uint_as_float(acc[j]), 1.0f + __expf(-z)));
+                    for (int q = 0; q < 2; ++q) {
+                        vt[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (tid + q * kProdThreads < 144) {
+                            const int gy = ty0 - 1 + t_py[q], gxt = tx0 - 1 + t_px[q];
+                            if (gy >= 0 && gy < h && gxt < w)
+                                vt[q] = __ldg(src4 + (int64_t)(part * kKcSlab + t_kc[q]) * hw + (int64_t)gy * w + gxt);
                         }
                     }
-                    if (ok && a.out_c4) {
-                        float4 *o4 = reinterpret_cast<float4 *>(a.out) +
-                                     (b * (COUT / 4) + c0 / 4) * hw + (int64_t)gy * w + gx;
+                } else {
+                    // plane of input channel c: first Ca channels from in_a, the rest from in_b
+                    // (optionally gathered through the per-image channel map)
+                    auto plane_of = [&](int c) -> const float * {
+                        if (c < a.Ca) return a.in_a + b * a.a_bstride + (int64_t)c * hw;
+                        const int cb = a.chan_map ? __ldg(a.chan_map + b * (CIN - a.Ca) + (c - a.Ca)) : c - a.Ca;
+                        return a.in_b + b * a.b_bstride + (int64_t)cb * hw;
+                    };
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            float v[4];
+                    for (int kk = 0; kk < 2; ++kk) {
+                        const int c0 = part * 32 + (2 * pw + kk) * 4;
+                        const float *p0 = plane_of(c0), *p1 = plane_of(c0 + 1), *p2 = plane_of(c0 + 2),
+                                    *p3 = plane_of(c0 + 3);
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                v[j] = __uint_as_float(acc[4 * q + j]);
-                                if (!GATE && a.bias) v[j] += __ldg(a.bias + c0 + 4 * q + j);
+                        for (int py = 0; py < 9; ++py) {
+                            const int gy = ty0 - 1 + py;
+                            const bool ok = okx && gy >= 0 && gy < h;
+                            const int64_t off = (int64_t)gy * w + gx;
+                            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (ok) { t.x = __ldg(p0 + off); t.y = __ldg(p1 + off); t.z = __ldg(p2 + off); t.w = __ldg(p3 + off); }
+                            v[kk * 9 + py] = t;
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        vt[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (tid + q * kProdThreads < 144) {
+                            const int gy = ty0 - 1 + t_py[q], gxt = tx0 - 1 + t_px[q];
+                            if (gy >= 0 && gy < h && gxt < w) {
+                                const int c0 = part * 32 + t_kc[q] * 4;
+                                const int64_t off = (int64_t)gy * w + gxt;
+                                vt[q].x = __ldg(plane_of(c0) + off); vt[q].y = __ldg(plane_of(c0 + 1) + off);
+                                vt[q].z = __ldg(plane_of(c0 + 2) + off); vt[q].w = __ldg(plane_of(c0 + 3) + off);
                             }
-                            o4[(int64_t)q * hw] = make_float4(v[0], v[1], v[2], v[3]);
                         }
-                    } else if (ok) {
-                        float *o = a.out + (b * COUT + c0) * hw + (int64_t)gy * w + gx;
+                    }
+                }
+                // the loads above are in flight while we wait for the slab to be released
+                mbar_wait(xempty(slot), ((unit >> 1) & 1u) ^ 1u);
+                float4 *dhi = xhi + slot * kSlabF4, *dlo = xlo + slot * kSlabF4;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            float v = __uint_as_float(acc[j]);
-                            if (!GATE && a.bias) v += __ldg(a.bias + c0 + j);
-                            o[(int64_t)j * hw] = v;
-                        }
+                for (int r = 0; r < 18; ++r) {
+                    const int idx = (2 * pw + r / 9) * kNPos + (r % 9) * kHW + lane;
+                    dhi[idx] = v[r];
+                    dlo[idx] = make_float4(tf32_lo(v[r].x), tf32_lo(v[r].y), tf32_lo(v[r].z), tf32_lo(v[r].w));
+                }
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    if (tid + q * kProdThreads < 144) {
+                        const int idx = t_kc[q] * kNPos + t_py[q] * kHW + t_px[q];
+                        dhi[idx] = vt[q];
+                        dlo[idx] = make_float4(tf32_lo(vt[q].x), tf32_lo(vt[q].y), tf32_lo(vt[q].z), tf32_lo(vt[q].w));
+                    }
+                }
+                // generic-proxy stores -> visible to the tensor core's async-proxy reads
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(xfull(slot));
+            }
+        }
+    } else if (warp == kWarpW) {
+        // =============================== weight producer ====================================
+        if (lane == 0) {
+            uint32_t cnt = 0;
+#pragma unroll 1
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+#pragma unroll 1
+                for (int part = 0; part < NCH; ++part) {
+#pragma unroll 1
+                    for (int tap = 0; tap < NTAPS; ++tap, ++cnt) {
+                        const int st = cnt % kStages;
+                        mbar_wait(wempty(st), ((cnt / kStages) & 1u) ^ 1u);
+                        mbar_expect_tx(wfull(st), (uint32_t)C::kChunkBytes);
+                        bulk_g2s(smem_u32(wbuf + st * C::kChunkF4),
+                                 a.packed + (int64_t)(tap * NCH + part) * C::kChunkF4,
+                                 (uint32_t)C::kChunkBytes, wfull(st));
                     }
                 }
             }
         }
-        // the next tile's first MMA (issued after the chunk-0 barrier) overwrites the accumulators:
-        // order this warp's TMEM reads before that barrier
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        WM_TICK(5);
-    }
-    if (a.dbg && tid == 0) {
+    } else if (warp == kWarpMma) {
+        // =============================== MMA issuer =========================================
+        if (lane == 0) {
+            // instruction descriptors: D=f32, A=B=tf32, both K-major, M = 128; N = COUT (b_hi only)
+            // or N = 2*COUT ([b_hi | b_lo]: the activation operand is read once for both)
+            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(COUT >> 3) << 17) |
+                                       ((uint32_t)(128 >> 4) << 24);
+            constexpr uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) |
+                                        ((uint32_t)((2 * COUT) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            // descriptors differ only in the 14-bit start-address field (bytes >> 4)
+            const uint64_t a_hi0 = make_desc(smem_u32(xhi), kNPos * 16u, 128u);
+            const uint64_t a_lo0 = make_desc(smem_u32(xlo), kNPos * 16u, 128u);
+            const uint64_t b_00 = make_desc(smem_u32(wbuf), 2 * COUT * 16u, 128u);
+            uint32_t cnt = 0, unit = 0, tcount = 0;
+            long long tacc[5] = {0, 0, 0, 0, 0}, t0 = 0, tp = 0;
+            const bool timed = a.dbg != nullptr;
+            if (timed) { t0 = clock64(); tp = t0; }
+#define WM_TICK(k) do { if (timed) { const long long _t = clock64(); tacc[k] += _t - tp; tp = _t; } } while (0)
+#pragma unroll 1
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+                const int buf = tcount % NACC;
+                mbar_wait(accempty(buf), ((tcount / NACC) & 1u) ^ 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                WM_TICK(3);
+                const uint32_t dbase = tmem_base + (uint32_t)(buf * C::kColsBuf);
+#pragma unroll 1
+                for (int part = 0; part < NCH; ++part, ++unit) {
+                    const int slot = unit & 1;
+                    mbar_wait(xfull(slot), (unit >> 1) & 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    WM_TICK(2);
+#pragma unroll 1
+                    for (int tap = 0; tap < NTAPS; ++tap, ++cnt) {
+                        const int st = cnt % kStages;
+                        mbar_wait(wfull(st), (cnt / kStages) & 1u);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        WM_TICK(1);
+                        const bool gate_tap = GATE && tap == 9;
+                        const int dy = gate_tap ? 1 : tap / 3, dx = gate_tap ? 1 : tap - (tap / 3) * 3;
+                        // offsets in 16-byte units (= one (kc, position) or (kc, co) element)
+                        const uint32_t shift = (uint32_t)(slot * kSlabF4 + dy * kHW + dx);
+                        const uint64_t b_hi0 = b_00 + (uint32_t)(st * C::kChunkF4);
 #pragma unroll
-        for (int k = 0; k < 6; ++k) a.dbg[blockIdx.x * 6 + k] = tacc[k];
-    }
+                        for (int mt = 0; mt < 2; ++mt) {
+                            const uint32_t dcol = dbase + (uint32_t)((gate_tap ? 4 * COUT : 0) + mt * 2 * COUT);
+                            const uint32_t arow = shift + (uint32_t)mt * 128u;
+#pragma unroll
+                            for (int kl = 0; kl < 4; ++kl) {
+                                const uint32_t aoff = (uint32_t)(2 * kl) * kNPos + arow;
+                                const uint32_t boff = (uint32_t)(2 * kl) * 2 * COUT;
+                                const uint32_t first = (part == 0 && kl == 0 && (tap == 0 || gate_tap)) ? 0u : 1u;
+                                // cols [0,COUT) += a_hi b_hi, [COUT,2COUT) += a_hi b_lo ; cols [0,COUT) += a_lo b_hi
+                                mma_tf32_ss(dcol, a_hi0 + aoff, b_hi0 + boff, idesc2, first);
+                                mma_tf32_ss(dcol, a_lo0 + aoff, b_hi0 + boff, idesc, 1u);
+                            }
+                        }
+                        mma_commit(wempty(st));
+                        WM_TICK(4);
+                    }
+                    mma_commit(xempty(slot));
+                }
+                mma_commit(accfull(buf));
+            }
 #undef WM_TICK
+            if (timed) {
+                a.dbg[blockIdx.x * 6 + 0] = clock64() - t0;
+                for (int k = 1; k < 5; ++k) a.dbg[blockIdx.x * 6 + k] = tacc[k];
+                a.dbg[blockIdx.x * 6 + 5] = tcount;
+            }
+        }
+    } else {
+        // =============================== epilogue ===========================================
+        // warp e: TMEM lane quarter (warp % 4 -- the hardware restriction), M tile e / 4
+        const int e = warp - kProdWarps;
+        const int quarter = warp & 3, mt = e >> 2;
+        constexpr int NG = COUT / 32;                   // 32-channel groups per accumulator
+        uint32_t tcount = 0;
+#pragma unroll 1
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+            const int txi = tile % tiles_x, tyi = (tile / tiles_x) % tiles_y;
+            const int64_t b = tile / (tiles_x * tiles_y);
+            const int tx0 = txi * kTW, ty0 = tyi * kR;
+            const int buf = tcount % NACC;
+            const int m = mt * 128 + quarter * 32 + lane;
+            const int q = kQ0 + m;
+            const int py = q / kHW, px = q - py * kHW;
+            const int gy = ty0 + py - 1, gx = tx0 + px - 1;
+            const bool ok = px >= 1 && px <= kTW && py <= kR && gy < h && gx < w;
+            mbar_wait(accfull(buf), (tcount / NACC) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
+                                       (uint32_t)(buf * C::kColsBuf + mt * 2 * COUT);
+#pragma unroll 1
+            for (int g = 0; g < NG; ++g) {
+                const int c0 = g * 32;
+                uint32_t acc[32];
+                {
+                    uint32_t part[32];
+                    tmem_ld32(lane_addr + (uint32_t)c0, acc);
+                    tmem_ld32(lane_addr + (uint32_t)(COUT + c0), part);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(part[j]));
+                }
+                if (GATE) {
+                    uint32_t gt[32], part[32];
+                    tmem_ld32(lane_addr + (uint32_t)(4 * COUT + c0), gt);
+                    tmem_ld32(lane_addr + (uint32_t)(4 * COUT + COUT + c0), part);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float z = (__uint_as_float(gt[j]) + __uint_as_float(part[j])) +
+                                        __ldg(a.gate_bias + c0 + j);
+                        acc[j] = __float_as_uint(__fdividef(__uint_as_float(acc[j]), 1.0f + __expf(-z)));
+                    }
+                }
+                if (g == NG - 1) {
+                    // every TMEM read of this warp is done: hand the accumulators back before the
+                    // global stores
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(accempty(buf));
+                }
+                if (ok && a.out_c4) {
+                    float4 *o4 = reinterpret_cast<float4 *>(a.out) +
+                                 (b * (COUT / 4) + c0 / 4) * hw + (int64_t)gy * w + gx;
+#pragma unroll
+                    for (int qq = 0; qq < 8; ++qq) {
+                        float v[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            v[j] = __uint_as_float(acc[4 * qq + j]);
+                            if (!GATE && a.bias) v[j] += __ldg(a.bias + c0 + 4 * qq + j);
+                        }
+                        o4[(int64_t)qq * hw] = make_float4(v[0], v[1], v[2], v[3]);
+                    }
+                } else if (ok) {
+                    float *o = a.out + (b * COUT + c0) * hw + (int64_t)gy * w + gx;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float v = __uint_as_float(acc[j]);
+                        if (!GATE && a.bias) v += __ldg(a.bias + c0 + j);
+                        o[(int64_t)j * hw] = v;
+                    }
+                }
+            }
+        }
+    }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) {
+    if (warp == kWarpMma) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                     "r"((uint32_t)kCols)
+                     "r"((uint32_t)C::kCols)
                      : "memory");
     }
 }
 
-// w3: (COUT, CIN, 3, 3); w1: (COUT, CIN) or null -> packed[tap][hi|lo][ci/4][co] float4
+// w3: (COUT, CIN, 3, 3); w1: (COUT, CIN) or null -> packed[tap][part][kc 0..7][hi|lo][co] float4:
+// one contiguous chunk per (tap, K half) in exactly the shared-memory operand layout, so the
+// weight producer moves a chunk with a single bulk copy.
 __global__ void __launch_bounds__(256)
 prepack_tc5_kernel(const float *__restrict__ w3, const float *__restrict__ w1,
                    float4 *__restrict__ out, int CIN, int COUT, int ntaps)
 {
-    const int KC = CIN / 4;
+    const int KC = CIN / 4, NCH = CIN / 32;
     const int total = ntaps * KC * COUT;
     for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
         const int co = i % COUT;
@@ -475,60 +536,88 @@ prepack_tc5_kernel(const float *__restrict__ w3, const float *__restrict__ w1,
             hi[j] = __uint_as_float(hbits);
             lo[j] = __uint_as_float(lbits);
         }
-        float4 *dst = out + (int64_t)tap * 2 * KC * COUT;
-        dst[kc * COUT + co] = make_float4(hi[0], hi[1], hi[2], hi[3]);
-        dst[KC * COUT + kc * COUT + co] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        const int part = kc / kKcSlab, kcl = kc % kKcSlab;
+        float4 *dst = out + ((int64_t)(tap * NCH + part) * kKcSlab + kcl) * 2 * COUT;
+        dst[co] = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        dst[COUT + co] = make_float4(lo[0], lo[1], lo[2], lo[3]);
     }
 }
 
 template <int CIN, int COUT, bool GATE>
 int launch(const Args &a, int64_t B, cudaStream_t s)
 {
-    constexpr size_t smem = sizeof(float4) * (2 * (CIN / 4) * kNPos + kStages * (2 * (CIN / 4) * COUT / (CIN >= 64 ? 2 : 1))) + 64;
+    using C = Cfg<CIN, COUT, GATE>;
     WM_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc5_kernel<CIN, COUT, GATE>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));
     const int tiles_x = (a.w + kTW - 1) / kTW, tiles_y = (a.h + kR - 1) / kR;
     const int64_t total = (int64_t)tiles_x * tiles_y * B;
     WM_REQUIRE(total < (int64_t)1 << 31, "wm_conv3x3_fwd: too many tiles");
     const int grid = (int)(total < sm_count() ? total : sm_count());   // persistent: one CTA per SM
-    conv3x3_tc5_kernel<CIN, COUT, GATE><<<grid, kThreads, smem, s>>>(a, tiles_x, tiles_y, (int)total);
+    conv3x3_tc5_kernel<CIN, COUT, GATE><<<grid, kThreads, C::kSmem, s>>>(a, tiles_x, tiles_y, (int)total);
     WM_LAUNCH_OK("conv3x3 tcgen05");
     return WM_OK;
 }
 
-void set_debug(long long *p) { g_dbg = p; }
+}  // namespace tc5
+}  // namespace wm
 
-size_t packed_bytes(int64_t Cin, int64_t Cout, int with_gate)
-{
-    return (size_t)(with_gate ? 10 : 9) * 2 * (Cin / 4) * Cout * sizeof(float4);
-}
+using namespace wm;
 
-int prepack(const float *w3x3, const float *w1x1, void *packed, int64_t Cin, int64_t Cout,
-            cudaStream_t s)
+/* Developer aid (not part of the reference-facing surface): when `device_buffer` is non-NULL the
+ * kernel's MMA thread adds cycle counts into it (6 int64 per CTA, 148 CTAs max). */
+extern "C" int wm_conv3x3_debug_timing(void *device_buffer)
 {
-    const int ntaps = w1x1 ? 10 : 9;
-    const int total = ntaps * (int)(Cin / 4) * (int)Cout;
-    prepack_tc5_kernel<<<(total + 255) / 256, 256, 0, s>>>(w3x3, w1x1, static_cast<float4 *>(packed),
-                                                            (int)Cin, (int)Cout, ntaps);
-    WM_LAUNCH_OK("conv3x3 tcgen05 prepack");
+    tc5::g_dbg.store(static_cast<long long *>(device_buffer));
     return WM_OK;
 }
 
-int forward(const float *in_a, int64_t a_bstride, int64_t Ca, const float *in_b, int64_t b_bstride,
-            const int *chan_map, const void *packed, const float *bias, const float *gate_bias,
-            float *out, int64_t B, int64_t Cin, int64_t Cout, int64_t h, int64_t w, int in_c4, int out_c4,
-            cudaStream_t s)
+extern "C" size_t wm_conv3x3_packed_bytes(int64_t Cin, int64_t Cout, int with_gate)
 {
+    if (Cin <= 0 || Cout <= 0 || Cin % 32 || Cout % 8) return 0;
+    return (size_t)(with_gate ? 10 : 9) * 2 * (Cin / 4) * Cout * sizeof(float4);
+}
+
+extern "C" int wm_conv3x3_prepack(const float *w3x3, const float *w1x1, void *packed, int64_t Cin,
+                                  int64_t Cout, wm_stream_t stream)
+{
+    WM_REQUIRE(w3x3 && packed, "wm_conv3x3_prepack: null pointer");
+    WM_REQUIRE(Cin > 0 && Cout > 0 && Cin % 32 == 0 && Cout % 8 == 0 && Cin <= 512 && Cout <= 512,
+               "wm_conv3x3_prepack: Cin=%lld must be a multiple of 32, Cout=%lld of 8", (long long)Cin,
+               (long long)Cout);
+    WM_REQUIRE(aligned16(packed), "wm_conv3x3_prepack: packed must be 16-byte aligned");
+    const int ntaps = w1x1 ? 10 : 9;
+    const int total = ntaps * (int)(Cin / 4) * (int)Cout;
+    tc5::prepack_tc5_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        w3x3, w1x1, static_cast<float4 *>(packed), (int)Cin, (int)Cout, ntaps);
+    WM_LAUNCH_OK("conv3x3 prepack");
+    return WM_OK;
+}
+
+extern "C" int wm_conv3x3_ex_fwd(const float *in_a, int64_t a_bstride, int64_t Ca, const float *in_b,
+                                 int64_t b_bstride, const int *chan_map, const void *packed,
+                                 const float *bias, const float *gate_bias, float *out, int64_t B,
+                                 int64_t Cin, int64_t Cout, int64_t h, int64_t w, int in_c4, int out_c4,
+                                 wm_stream_t stream)
+{
+    using namespace wm::tc5;
+    WM_REQUIRE(B >= 0 && B <= 65535 && h >= 0 && w >= 0 && h < (1 << 24) && w < (1 << 24),
+               "wm_conv3x3_fwd: bad sizes");
+    if (B == 0 || h == 0 || w == 0) return WM_OK;
+    WM_REQUIRE(in_a && packed && out, "wm_conv3x3_fwd: null pointer");
+    WM_REQUIRE(Ca > 0 && Ca <= Cin && (Ca == Cin || in_b != nullptr),
+               "wm_conv3x3_fwd: Ca=%lld of Cin=%lld needs a second input", (long long)Ca, (long long)Cin);
     WM_REQUIRE((h + kR - 1) / kR <= 65535, "wm_conv3x3_fwd: image too tall");
+    WM_REQUIRE(aligned16(packed), "wm_conv3x3_fwd: packed weights must be 16-byte aligned");
     WM_REQUIRE(!in_c4 || (Ca == Cin && aligned16(in_a) && a_bstride % 4 == 0),
                "wm_conv3x3_ex_fwd: the channel-quad input layout needs a single 16-byte aligned input");
     WM_REQUIRE(!out_c4 || aligned16(out), "wm_conv3x3_ex_fwd: channel-quad output must be 16-byte aligned");
     Args a;
     a.in_c4 = in_c4; a.out_c4 = out_c4;
-    a.dbg = g_dbg;
+    a.dbg = g_dbg.load();
     a.in_a = in_a; a.a_bstride = a_bstride; a.Ca = (int)Ca; a.in_b = in_b; a.b_bstride = b_bstride;
     a.chan_map = chan_map; a.packed = static_cast<const float4 *>(packed); a.bias = bias;
     a.gate_bias = gate_bias; a.out = out; a.h = (int)h; a.w = (int)w;
+    cudaStream_t s = (cudaStream_t)stream;
     if (gate_bias) {
         WM_REQUIRE(Cin == 64 && Cout == 64, "wm_conv3x3_fwd: gated mode supports 64->64 only");
         return launch<64, 64, true>(a, B, s);
@@ -541,5 +630,11 @@ int forward(const float *in_a, int64_t a_bstride, int64_t Ca, const float *in_b,
     return WM_EINVAL;
 }
 
-}  // namespace tc5
-}  // namespace wm
+extern "C" int wm_conv3x3_fwd(const float *in_a, int64_t a_bstride, int64_t Ca, const float *in_b,
+                              int64_t b_bstride, const int *chan_map, const void *packed,
+                              const float *bias, const float *gate_bias, float *out, int64_t B,
+                              int64_t Cin, int64_t Cout, int64_t h, int64_t w, wm_stream_t stream)
+{
+    return wm_conv3x3_ex_fwd(in_a, a_bstride, Ca, in_b, b_bstride, chan_map, packed, bias, gate_bias, out,
+                             B, Cin, Cout, h, w, 0, 0, stream);
+}

@@ -53,6 +53,8 @@ __device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c)
 
 struct Args {
     const float *x;          // (B, CIN or 2*CIN, hw)
+    int64_t x_bstride;       // batch stride of x in floats (0: dense, XCH * hw)
+    int64_t w_bstride;       // batch stride of w in floats (0: one weight matrix for every image)
     const float *xa, *xb_, *xc;  // optional addends, summed in this order: ((x + xa) + xb_) + xc
     const float *ln_w, *ln_b;
     float eps;
@@ -73,9 +75,10 @@ pixel_kernel(const Args a)
     __shared__ __align__(16) float wt[CIN * COUT];  // [ci][co]
     __shared__ float pb[COUT], rs[COUT], lw[CIN], lb[CIN];
     const int tid = threadIdx.x;
+    const float *wsrc = a.w + (int64_t)blockIdx.y * a.w_bstride;
     for (int i = tid; i < CIN * COUT; i += kThreads) {
         const int co = i / CIN, ci = i - co * CIN;
-        wt[ci * COUT + co] = __ldg(a.w + i);
+        wt[ci * COUT + co] = __ldg(wsrc + i);
     }
     for (int i = tid; i < COUT; i += kThreads) {
         pb[i] = a.b ? __ldg(a.b + i) : 0.0f;
@@ -88,7 +91,7 @@ pixel_kernel(const Args a)
     const int64_t hw = a.hw;
     const int64_t b = blockIdx.y;
     constexpr int XCH = PRE == kPreGate ? 2 * CIN : CIN;
-    const float *xb = a.x + b * XCH * hw;
+    const float *xb = a.x + b * (a.x_bstride ? a.x_bstride : XCH * hw);
     const float *xa = a.xa ? a.xa + b * XCH * hw : nullptr;
     const float *xb2 = a.xb_ ? a.xb_ + b * XCH * hw : nullptr;
     const float *xc = a.xc ? a.xc + b * XCH * hw : nullptr;
@@ -174,9 +177,10 @@ pixel2_kernel(const Args a)
     __shared__ __align__(16) float wt[CIN * COUT];  // [ci][co]
     __shared__ float pb[COUT], rs[COUT], lw[CIN], lb[CIN];
     const int tid = threadIdx.x;
+    const float *wsrc = a.w + (int64_t)blockIdx.y * a.w_bstride;
     for (int i = tid; i < CIN * COUT; i += kThreads) {
         const int co = i / CIN, ci = i - co * CIN;
-        wt[ci * COUT + co] = __ldg(a.w + i);
+        wt[ci * COUT + co] = __ldg(wsrc + i);
     }
     for (int i = tid; i < COUT; i += kThreads) {
         pb[i] = a.b ? __ldg(a.b + i) : 0.0f;
@@ -189,7 +193,7 @@ pixel2_kernel(const Args a)
     const int64_t hw = a.hw, npair = hw >> 1;
     const int64_t b = blockIdx.y;
     constexpr int XCH = PRE == kPreGate ? 2 * CIN : CIN;
-    const float *xb = a.x + b * XCH * hw;
+    const float *xb = a.x + b * (a.x_bstride ? a.x_bstride : XCH * hw);
     for (int64_t q = (int64_t)blockIdx.x * kThreads + tid; q < npair; q += (int64_t)gridDim.x * kThreads) {
         const int64_t p = 2 * q;
         float xv[2][CIN];
@@ -543,10 +547,12 @@ extern "C" int wm_layernorm2d_fwd(const float *x, const float *ln_w, const float
     return WM_OK;
 }
 
-extern "C" int wm_pw_fwd(const float *x, const float *pw_w, const float *pw_b, int gate_mode,
-                         const float *residual, const float *res_scale, float *y, int64_t B,
-                         int64_t Cin, int64_t Cout, int64_t h, int64_t w, wm_stream_t stream)
+extern "C" int wm_pw_fwd(const float *x, int64_t x_bstride, const float *pw_w, int64_t w_bstride,
+                         const float *pw_b, int gate_mode, const float *residual,
+                         const float *res_scale, float *y, int64_t B, int64_t Cin, int64_t Cout,
+                         int64_t h, int64_t w, wm_stream_t stream)
 {
+    WM_REQUIRE(x_bstride >= 0 && w_bstride >= 0, "wm_pw_fwd: negative stride");
     WM_REQUIRE(dims_ok(B, h, w), "wm_pw_fwd: bad sizes");
     WM_REQUIRE(gate_mode == 0 || gate_mode == 1, "wm_pw_fwd: gate_mode must be 0 or 1");
     WM_REQUIRE(!(res_scale && !residual), "wm_pw_fwd: res_scale without residual");
@@ -555,6 +561,8 @@ extern "C" int wm_pw_fwd(const float *x, const float *pw_w, const float *pw_b, i
     Args a = {};
     a.x = x; a.w = pw_w; a.b = pw_b; a.res = residual; a.res_scale = res_scale; a.y = y;
     a.hw = h * w;
+    a.x_bstride = x_bstride; a.w_bstride = w_bstride;
+    WM_REQUIRE(x_bstride % 2 == 0 || a.hw % 2 != 0 || B == 1, "wm_pw_fwd: odd batch stride");
     cudaStream_t s = (cudaStream_t)stream;
     if (gate_mode == 0 && Cin == 32 && Cout == 32) return launch2<32, 32, kPreNone, kPostNone>(a, B, s, "pw 32->32");
     if (gate_mode == 0 && Cin == 32 && Cout == 64) return launch<32, 64, kPreNone, kPostNone>(a, B, s, "pw 32->64");

@@ -40,6 +40,7 @@
 // broadcast data): measured in DESIGN.md section 4.2.
 #include <stdlib.h>
 
+#include <atomic>
 #include <initializer_list>
 #include <mutex>
 #include <utility>
@@ -863,30 +864,35 @@ double schedule_makespan(int slots, const int *counts, const double *costs, int 
 // (2 per SM) with as little tail as possible; the choice is cached per (B, h, w).
 Geom make_geom(int64_t B, int64_t h, int64_t w)
 {
-    struct Key { int64_t B, h, w; };
+    // the plan depends on the machine's CTA slots and on the developer switch: both are in the key
+    struct Key { int64_t B, h, w; int slots, legacy; };
     static std::mutex mu;
     static std::vector<std::pair<Key, Geom>> cache;
+    const int slots = 2 * sm_count();
+    const char *plan_env = getenv("WM_SS2D_PLAN");
+    bool legacy = plan_env != nullptr && plan_env[0] == 'l';
     {
         std::lock_guard<std::mutex> lock(mu);
         for (const auto &e : cache)
-            if (e.first.B == B && e.first.h == h && e.first.w == w) return e.second;
+            if (e.first.B == B && e.first.h == h && e.first.w == w && e.first.slots == slots &&
+                e.first.legacy == (int)legacy)
+                return e.second;
     }
+    const Key key{B, h, w, slots, (int)legacy};
     Geom g;
     g.B = (int)B; g.h = (int)h; g.w = (int)w;
     g.L = h * w;
     g.vec_rows = (g.L % 4 == 0) ? 1 : 0;
     g.vec_cols = (w % 4 == 0) ? 1 : 0;
-    const int slots = 2 * sm_count();
     const int64_t col_groups = (w + kSeq - 1) / kSeq;
     double best = 1e300;
     int best_seg = 0, best_T = 0, best_first = 0;
-    const char *plan_env = getenv("WM_SS2D_PLAN");
-    const bool legacy = plan_env != nullptr && plan_env[0] == 'l';
-    if (legacy) {   // one chunk per column, row chunks of about the same length
+    auto legacy_plan = [&]() {   // one chunk per column, row chunks of about the same length
         best_seg = (int)align_up(h, kTP);
         int64_t T = h < 4 * kTP ? 4 * kTP : h;
         best_T = (int)align_up(T, kTP);
-    }
+    };
+    if (legacy) legacy_plan();
     for (int nseg = 1; nseg <= 8 && !legacy; ++nseg) {
         int64_t seg = align_up((h + nseg - 1) / nseg, kTP);
         if (nseg > 1 && seg < 4 * kTP) break;          // never shorter than 4 tiles
@@ -922,6 +928,8 @@ Geom make_geom(int64_t B, int64_t h, int64_t w)
             }
         }
     }
+    // very wide / very large maps: every candidate may have been skipped by the aggregate-size cap
+    if (best_seg <= 0 || best_T <= 0) legacy_plan();
     g.col_seg = best_seg;
     g.ncolseg = (int)((h + g.col_seg - 1) / g.col_seg);
     g.col_ctas = (int)(col_groups * g.ncolseg);
@@ -934,7 +942,7 @@ Geom make_geom(int64_t B, int64_t h, int64_t w)
     {
         std::lock_guard<std::mutex> lock(mu);
         if (cache.size() > 64) cache.clear();
-        cache.emplace_back(Key{B, h, w}, g);
+        cache.emplace_back(key, g);
     }
     return g;
 }
@@ -971,8 +979,9 @@ Launch make_launch(const Geom &g, std::initializer_list<int> dirs)
     return ln;
 }
 
-long long *g_dbg = nullptr;   // wm_ss2d_debug_timing
-int g_dbg_pad = 0;            // extra dynamic smem (forces one CTA per SM when > 0)
+// developer switches (wm_ss2d_debug_timing): atomics, read once per call
+std::atomic<long long *> g_dbg{nullptr};
+std::atomic<int> g_dbg_pad{0};   // extra dynamic smem (forces one CTA per SM when > 0)
 
 // Runs pass 1, carry, pass 2; leaves the four direction planes at workspace[0 : 4*B*64*L].
 int run_dirs(const float *x, const float *x_proj_weight, const float *dt_projs_weight,
@@ -1000,11 +1009,11 @@ int run_dirs(const float *x, const float *x_proj_weight, const float *dt_projs_w
     prm.planes = reinterpret_cast<float *>(wsb + ws.planes_off);
     prm.aggP = reinterpret_cast<float *>(wsb + ws.aggP_off);
     prm.aggH = reinterpret_cast<float *>(wsb + ws.aggH_off);
-    prm.dbg = g_dbg;
-    const size_t smem_bytes = kSmemBytes + (size_t)g_dbg_pad;
+    prm.dbg = g_dbg.load();
+    const size_t smem_bytes = kSmemBytes + (size_t)g_dbg_pad.load();
 
-    auto pass1 = g_dbg ? ss2d_pass_kernel<false, true> : ss2d_pass_kernel<false, false>;
-    auto pass2 = g_dbg ? ss2d_pass_kernel<true, true> : ss2d_pass_kernel<true, false>;
+    auto pass1 = prm.dbg ? ss2d_pass_kernel<false, true> : ss2d_pass_kernel<false, false>;
+    auto pass2 = prm.dbg ? ss2d_pass_kernel<true, true> : ss2d_pass_kernel<true, false>;
     WM_CUDA_OK(cudaFuncSetAttribute(pass1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     WM_CUDA_OK(cudaFuncSetAttribute(pass2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     // interleave row and column CTAs of the same cost so waves stay balanced
@@ -1028,8 +1037,8 @@ extern "C" int wm_ss2d_debug_timing(void *device_buffer)
     // low bit of a NULL-buffer call is not used; a buffer address with bit 0 set requests the
     // one-CTA-per-SM variant (smem padded) for occupancy experiments
     const uintptr_t v = reinterpret_cast<uintptr_t>(device_buffer);
-    wm::ss2d::g_dbg_pad = (v & 1) ? 60 * 1024 : 0;
-    wm::ss2d::g_dbg = reinterpret_cast<long long *>(v & ~(uintptr_t)1);
+    wm::ss2d::g_dbg_pad.store((v & 1) ? 60 * 1024 : 0);
+    wm::ss2d::g_dbg.store(reinterpret_cast<long long *>(v & ~(uintptr_t)1));
     return WM_OK;
 }
 

@@ -17,11 +17,16 @@ from . import ops
 
 @torch.no_grad()
 def enhance_bgr_u8(net, img: torch.Tensor, window: int = 128, out: Optional[torch.Tensor] = None,
-                   device: Optional[torch.device] = None) -> torch.Tensor:
+                   device: Optional[torch.device] = None, sync: bool = False) -> torch.Tensor:
     """img: (H,W,3) or (B,H,W,3) uint8 BGR, on the host (ideally pinned) or already on the GPU.
     Returns the enhanced uint8 BGR image(s) with the input's leading shape: on the GPU, or copied
-    asynchronously into ``out`` (a host uint8 tensor of the same shape, ideally pinned) when given.
-    ``net`` is a ``WaveMamba`` (its ``restoration_network`` is used, as the reference does)."""
+    into ``out`` (a host uint8 tensor of the same shape, ideally pinned) when given.
+    ``net`` is a ``WaveMamba`` (its ``restoration_network`` is used, as the reference does).
+
+    Stream contract: everything is enqueued on the current CUDA stream.  With a pinned ``img`` /
+    ``out`` the two PCIe copies are asynchronous: do not overwrite ``img`` or read ``out`` before the
+    stream has been synchronised -- pass ``sync=True`` for the reference loop's blocking behaviour
+    (``tensor2img`` returns finished data)."""
     if img.dtype != torch.uint8 or img.dim() not in (3, 4) or img.shape[-1] != 3:
         raise ValueError(f"expected a (H,W,3) or (B,H,W,3) uint8 image, got {tuple(img.shape)} {img.dtype}")
     squeeze = img.dim() == 3
@@ -41,5 +46,7 @@ def enhance_bgr_u8(net, img: torch.Tensor, window: int = 128, out: Optional[torc
         res = res[0]
     if out is not None:
         out.copy_(res, non_blocking=True)
-        return out
+        res = out
+    if sync:
+        torch.cuda.current_stream(img.device).synchronize()
     return res

@@ -110,9 +110,9 @@ def ss2d_core(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds) -> t
     _chk(Ds, "Ds", (256,))
     lib = _cabi.load()
     y = torch.empty_like(x)
-    nbytes = lib.wm_ss2d_core_workspace_bytes(B, h, w)
-    ws = torch.empty(max(nbytes, 256), device=x.device, dtype=torch.uint8)
     with torch.cuda.device(x.device):
+        nbytes = lib.wm_ss2d_core_workspace_bytes(B, h, w)
+        ws = torch.empty(max(nbytes, 256), device=x.device, dtype=torch.uint8)
         rc = lib.wm_ss2d_core_fwd(x.data_ptr(), x_proj_weight.data_ptr(), dt_projs_weight.data_ptr(),
                                   dt_projs_bias.data_ptr(), A_logs.data_ptr(), Ds.data_ptr(),
                                   y.data_ptr(), ws.data_ptr(), nbytes, B, h, w, _stream(x))
@@ -134,9 +134,9 @@ def ss2d_dirs(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds) -> t
     _chk(A_logs, "A_logs", (256, 16))
     _chk(Ds, "Ds", (256,))
     lib = _cabi.load()
-    nbytes = lib.wm_ss2d_core_workspace_bytes(B, h, w)
-    ws = torch.empty(max(nbytes, 256) // 4, device=x.device, dtype=torch.float32)
     with torch.cuda.device(x.device):
+        nbytes = lib.wm_ss2d_core_workspace_bytes(B, h, w)
+        ws = torch.empty(max(nbytes, 256) // 4, device=x.device, dtype=torch.float32)
         rc = lib.wm_ss2d_dirs_fwd(x.data_ptr(), x_proj_weight.data_ptr(), dt_projs_weight.data_ptr(),
                                   dt_projs_bias.data_ptr(), A_logs.data_ptr(), Ds.data_ptr(),
                                   ws.data_ptr(), nbytes, B, h, w, _stream(x))
@@ -214,13 +214,19 @@ def dw_act_pw(x, dw_w, dw_b, pw_w, pw_b, act: str = "gelu", residual=None) -> to
 
 def pw(x, pw_w, pw_b=None, gate: bool = False, residual=None, res_scale=None, out=None) -> torch.Tensor:
     """y = residual?*res_scale? + pw1x1(x) (+bias).  gate=True: x is (B,2*Cin,h,w) and the conv
-    sees gelu(x[:, :Cin]) * x[:, Cin:]  (reference ffn :227-228)."""
-    _chk(x, "x")
+    sees gelu(x[:, :Cin]) * x[:, Cin:]  (reference ffn :227-228).
+    x may be a channel slice of a wider tensor (planes contiguous); pw_w may be (Cout,Cin[,1,1]) or
+    per-image (B,Cout,Cin)."""
+    _chk_planes(x, "x")
     B, Cx, h, w = x.shape
-    Cout, Cin = pw_w.shape[0], pw_w.shape[1]
+    per_image = pw_w.dim() == 3
+    Cout, Cin = (pw_w.shape[1], pw_w.shape[2]) if per_image else (pw_w.shape[0], pw_w.shape[1])
     if Cx != (2 * Cin if gate else Cin):
         raise ValueError(f"x has {Cx} channels, weight expects {2 * Cin if gate else Cin}")
-    _chk(pw_w, "pw_w", (Cout, Cin) if pw_w.dim() == 2 else (Cout, Cin, 1, 1))
+    if per_image:
+        _chk(pw_w, "pw_w", (B, Cout, Cin))
+    else:
+        _chk(pw_w, "pw_w", (Cout, Cin) if pw_w.dim() == 2 else (Cout, Cin, 1, 1))
     if pw_b is not None:
         _chk(pw_b, "pw_b", (Cout,))
     if residual is not None:
@@ -233,7 +239,8 @@ def pw(x, pw_w, pw_b=None, gate: bool = False, residual=None, res_scale=None, ou
         y = _chk(out, "out", (B, Cout, h, w))
     lib = _cabi.load()
     with torch.cuda.device(x.device):
-        rc = lib.wm_pw_fwd(x.data_ptr(), pw_w.data_ptr(), _ptr(pw_b), 1 if gate else 0,
+        rc = lib.wm_pw_fwd(x.data_ptr(), x.stride(0) if B > 1 else 0, pw_w.data_ptr(),
+                           Cout * Cin if per_image else 0, _ptr(pw_b), 1 if gate else 0,
                            _ptr(residual), _ptr(res_scale), y.data_ptr(), B, Cin, Cout, h, w,
                            _stream(x))
     _cabi.check(rc, "wm_pw_fwd")
@@ -330,11 +337,11 @@ def gram32(x: torch.Tensor, y: torch.Tensor):
     hw = h * w
     lib = _cabi.load()
     out = torch.empty(B, 32 * 32 + 64, device=x.device, dtype=torch.float32)
-    nbytes = lib.wm_gram32_workspace_bytes(B, hw)
-    ws = torch.empty(max(nbytes, 8) // 8, device=x.device, dtype=torch.float64)
     xb = x.stride(0) if B > 1 else 32 * hw
     yb = y.stride(0) if B > 1 else 32 * hw
     with torch.cuda.device(x.device):
+        nbytes = lib.wm_gram32_workspace_bytes(B, hw)
+        ws = torch.empty(max(nbytes, 8) // 8, device=x.device, dtype=torch.float64)
         rc = lib.wm_gram32_fwd(x.data_ptr(), xb, y.data_ptr(), yb, out.data_ptr(), ws.data_ptr(),
                                nbytes, B, hw, _stream(x))
     _cabi.check(rc, "wm_gram32_fwd")
@@ -342,22 +349,35 @@ def gram32(x: torch.Tensor, y: torch.Tensor):
     return out[:, :1024].view(B, 32, 32), out[:, 1024:1056], out[:, 1056:1088]
 
 
-_packed_cache = {}   # id(weight tensor) -> (weakref to it, versions, gate-weight ref, packed)
+_packed_cache = {}   # id(weight) -> (weakref, (data_ptr, device, version) of w3x3 and w1x1, packed)
+
+
+def _w_state(t: Optional[torch.Tensor]):
+    """What a cached pack is valid for.  ``_version`` alone misses writes through ``.data`` /
+    ``module.to()``, which keep the Parameter object: the storage address and device are compared
+    too, and code that rewrites weights behind autograd's back (``p.data.copy_``) must call
+    ``clear_pack_cache()`` (parallel.broadcast_parameters does)."""
+    return None if t is None else (t.data_ptr(), t.device, t._version)
+
+
+def clear_pack_cache() -> None:
+    """Drop every cached pre-packed conv weight (call after modifying weights through ``.data``)."""
+    _packed_cache.clear()
 
 
 def conv3x3_pack(w3x3: torch.Tensor, w1x1: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Pre-pack (Cout,Cin,3,3) weights (+ optional (Cout,Cin[,1,1]) 1x1 gate weights) into mma
-    fragment order with the tf32 hi/lo split.  Cached per weight tensor object (weakly) and
-    invalidated when either tensor is modified in place (``_version``)."""
+    """Pre-pack (Cout,Cin,3,3) weights (+ optional (Cout,Cin[,1,1]) 1x1 gate weights) into the
+    tcgen05 operand order with the tf32 hi/lo split.  Cached per weight tensor object (weakly);
+    a hit is validated against the storage address, device and ``_version`` of both tensors."""
     _chk(w3x3, "w3x3")
     Cout, Cin = w3x3.shape[0], w3x3.shape[1]
     key = id(w3x3)
+    state = (_w_state(w3x3), _w_state(w1x1))
     hit = _packed_cache.get(key)
     if hit is not None:
-        ref3, ver3, ref1, ver1, packed = hit
+        ref3, ref1, st, packed = hit
         same_gate = (ref1 is None and w1x1 is None) or (ref1 is not None and ref1() is w1x1)
-        if ref3() is w3x3 and ver3 == w3x3._version and same_gate and \
-                (w1x1 is None or ver1 == w1x1._version):
+        if ref3() is w3x3 and same_gate and st == state and packed.device == w3x3.device:
             return packed
     if w1x1 is not None:
         _chk(w1x1, "w1x1")
@@ -366,7 +386,7 @@ def conv3x3_pack(w3x3: torch.Tensor, w1x1: Optional[torch.Tensor] = None) -> tor
     lib = _cabi.load()
     nbytes = lib.wm_conv3x3_packed_bytes(Cin, Cout, 1 if w1x1 is not None else 0)
     if nbytes == 0:
-        raise ValueError(f"conv3x3: Cin={Cin} Cout={Cout} must be multiples of 8")
+        raise ValueError(f"conv3x3: Cin={Cin} must be a multiple of 32 and Cout={Cout} of 8")
     packed = torch.empty(nbytes // 4, device=w3x3.device, dtype=torch.float32)
     with torch.cuda.device(w3x3.device):
         rc = lib.wm_conv3x3_prepack(w3x3.data_ptr(), _ptr(w1x1), packed.data_ptr(), Cin, Cout,
@@ -374,8 +394,7 @@ def conv3x3_pack(w3x3: torch.Tensor, w1x1: Optional[torch.Tensor] = None) -> tor
     _cabi.check(rc, "wm_conv3x3_prepack")
     _count(1)
     _packed_cache[key] = (weakref.ref(w3x3, lambda _r, k=key: _packed_cache.pop(k, None)),
-                          w3x3._version, None if w1x1 is None else weakref.ref(w1x1),
-                          None if w1x1 is None else w1x1._version, packed)
+                          None if w1x1 is None else weakref.ref(w1x1), state, packed)
     return packed
 
 
@@ -496,9 +515,9 @@ def skff(f0, f1, f2, w_du, prelu_weight, w_fc0, w_fc1, w_fc2) -> torch.Tensor:
     _chk(prelu_weight, "prelu_weight", (1,))
     out = torch.empty_like(f0)
     lib = _cabi.load()
-    nbytes = lib.wm_skff_workspace_bytes(B, h, w)
-    ws = torch.empty(max(nbytes // 8, 1), dtype=torch.float64, device=f0.device)
     with torch.cuda.device(f0.device):
+        nbytes = lib.wm_skff_workspace_bytes(B, h, w)
+        ws = torch.empty(max(nbytes // 8, 1), dtype=torch.float64, device=f0.device)
         rc = lib.wm_skff_fwd(f0.data_ptr(), f1.data_ptr(), f2.data_ptr(), w_du.data_ptr(),
                              prelu_weight.data_ptr(), fcs[0].data_ptr(), fcs[1].data_ptr(),
                              fcs[2].data_ptr(), out.data_ptr(), ws.data_ptr(), nbytes, B, C, h, w,
@@ -579,13 +598,3 @@ def img_f32_to_u8(x: torch.Tensor, h: Optional[int] = None, w: Optional[int] = N
     if B and h and w:
         _count(1)
     return img
-
-
-def set_conv_impl(name: str) -> None:
-    """Select the dense-3x3 implementation: "mma" (mma.sync, legacy tensor path) or "tcgen05"
-    (5th-gen tensor cores, TMEM accumulators).  Process-wide."""
-    _cabi.check(_cabi.load().wm_conv3x3_set_impl({"mma": 0, "tcgen05": 1}[name]), "wm_conv3x3_set_impl")
-
-
-def get_conv_impl() -> str:
-    return ("mma", "tcgen05")[_cabi.load().wm_conv3x3_get_impl()]

@@ -26,65 +26,123 @@ def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
 
 def broadcast_parameters(module: torch.nn.Module, src: int = 0) -> None:
     """One flat broadcast of every parameter and buffer (6.05 MB for Wave-Mamba)."""
-    tensors = [p.data for p in module.parameters()] + [b.data for b in module.buffers()]
+    tensors = list(module.parameters()) + list(module.buffers())
     if not tensors or not dist.is_initialized() or dist.get_world_size() == 1:
         return
-    flat = torch.cat([t.reshape(-1).float() for t in tensors])
-    dist.broadcast(flat, src=src)
-    off = 0
-    for t in tensors:
-        n = t.numel()
-        t.copy_(flat[off:off + n].view_as(t))
-        off += n
+    with torch.no_grad():
+        flat = torch.cat([t.reshape(-1).float() for t in tensors])
+        dist.broadcast(flat, src=src)
+        off = 0
+        for t in tensors:
+            n = t.numel()
+            t.copy_(flat[off:off + n].view_as(t))      # in-place, bumps ``_version``
+            off += n
+    from . import ops
+    ops.clear_pack_cache()                             # pre-packed conv weights are stale now
+
+
+_DTYPES = [torch.float32, torch.uint8, torch.float16, torch.bfloat16, torch.float64, torch.int32]
+
+
+def _exchange(ops_list):
+    """Post a group of point-to-point transfers (one NCCL group: they run concurrently over NVLink)."""
+    if not ops_list:
+        return []
+    return dist.batch_isend_irecv(ops_list)
 
 
 @torch.no_grad()
 def sharded_forward(forward, batch: Optional[torch.Tensor], device: torch.device, src: int = 0,
-                    gather: bool = True) -> Optional[torch.Tensor]:
+                    gather: bool = True, stats: Optional[dict] = None) -> Optional[torch.Tensor]:
     """Run ``forward`` on this rank's slice of a batch that lives on rank ``src``.
 
-    batch: (B,3,H,W) on rank ``src`` (None elsewhere).  Returns the (B,3,H,W) result on rank
-    ``src`` when ``gather`` (None elsewhere), else this rank's slice.  Edge traffic only:
-    one scatter of the inputs and one gather of the outputs.
+    batch: (B, ...) tensor on rank ``src`` (host or device; None elsewhere), any dtype in _DTYPES;
+    ``forward`` maps a (b, ...) slice to a tensor of the same shape and dtype.  Returns the (B, ...)
+    result on ``src``'s device when ``gather`` (None elsewhere), else this rank's slice.
+
+    Edge traffic only: the inputs are scattered and the outputs gathered with grouped
+    point-to-point transfers (``batch_isend_irecv``: one NCCL group each way, ragged shards allowed);
+    the root starts on its own shard while its sends are in flight.  ``stats`` (rank ``src``, CUDA):
+    appends (start, end) event pairs under "scatter" / "gather".
     """
     world, rank = dist.get_world_size(), dist.get_rank()
-    meta = [None]
+    meta = torch.zeros(10, dtype=torch.int64, device=device)
     if rank == src:
-        meta = [tuple(batch.shape)]
-    dist.broadcast_object_list(meta, src=src)
-    B, C, H, W = meta[0]
+        shape = list(batch.shape)
+        if len(shape) > 8:
+            raise ValueError("sharded_forward: at most 8 dimensions")
+        meta[0] = len(shape)
+        meta[1] = _DTYPES.index(batch.dtype)
+        meta[2:2 + len(shape)] = torch.tensor(shape, dtype=torch.int64)
+    dist.broadcast(meta, src=src)
+    meta = meta.tolist()
+    shape, dtype = meta[2:2 + meta[0]], _DTYPES[meta[1]]
+    B, rest = shape[0], shape[1:]
     begin, end = shard_range(B, rank, world)
-    mine = torch.empty(end - begin, C, H, W, device=device)
+    timed = stats is not None and rank == src and device.type == "cuda"
+
+    def mark():
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        return ev
+
+    # ---- scatter ----------------------------------------------------------------------------
+    t0 = mark() if timed else None
     if rank == src:
-        chunks = []
+        whole = batch.to(device, non_blocking=True).contiguous()
+        sends = []
         for r in range(world):
             b0, b1 = shard_range(B, r, world)
-            chunks.append(batch[b0:b1].to(device).contiguous())
+            if r != src and b1 > b0:
+                sends.append(dist.P2POp(dist.isend, whole[b0:b1], r))
+        reqs = _exchange(sends)
+        mine = whole[begin:end]
     else:
-        chunks = None
-    # scatter needs equal-size chunks in some backends; use point-to-point for ragged shards
-    if rank == src:
-        for r in range(world):
-            if r == src:
-                mine.copy_(chunks[r])
-            elif chunks[r].numel():
-                dist.send(chunks[r], dst=r)
-    elif mine.numel():
-        dist.recv(mine, src=src)
-    out = forward(mine) if mine.shape[0] else mine
+        mine = torch.empty([end - begin] + rest, dtype=dtype, device=device)
+        reqs = _exchange([dist.P2POp(dist.irecv, mine, src)] if end > begin else [])
+        for q in reqs:
+            q.wait()
+        reqs = []
+    if timed:
+        stats.setdefault("scatter", []).append((t0, mark()))
+    out = forward(mine) if end > begin else mine
+    for q in reqs:      # the root's sends overlapped its own forward
+        q.wait()
     if not gather:
         return out
+    # ---- gather -----------------------------------------------------------------------------
+    t1 = mark() if timed else None
+    result = None
     if rank == src:
-        result = torch.empty(B, C, H, W, device=device)
+        result = torch.empty(shape, dtype=out.dtype, device=device)
+        recvs = []
         for r in range(world):
             b0, b1 = shard_range(B, r, world)
-            if r == src:
-                result[b0:b1] = out
-            elif b1 > b0:
-                buf = torch.empty(b1 - b0, C, H, W, device=device)
-                dist.recv(buf, src=r)
-                result[b0:b1] = buf
-        return result
-    if out.numel():
-        dist.send(out.contiguous(), dst=src)
-    return None
+            if r != src and b1 > b0:
+                recvs.append(dist.P2POp(dist.irecv, result[b0:b1], r))
+        reqs = _exchange(recvs)
+        result[begin:end] = out
+    else:
+        reqs = _exchange([dist.P2POp(dist.isend, out.contiguous(), src)] if end > begin else [])
+    for q in reqs:
+        q.wait()
+    if timed:
+        stats.setdefault("gather", []).append((t1, mark()))
+    return result
+
+
+@torch.no_grad()
+def sharded_enhance_u8(net, batch: Optional[torch.Tensor], device: torch.device, window: int = 128,
+                       out: Optional[torch.Tensor] = None, src: int = 0,
+                       stats: Optional[dict] = None) -> Optional[torch.Tensor]:
+    """BASELINE configs[3]: a batch of uint8 BGR images (B,H,W,3) held by rank ``src`` (host, ideally
+    pinned) is enhanced by all ranks: H2D on ``src`` -> NCCL scatter -> ``enhance_bgr_u8`` on every
+    rank's shard -> NCCL gather -> (optionally) D2H into ``out`` on ``src``.  uint8 crosses PCIe and
+    NVLink (3 bytes per pixel each way).  Returns the result on ``src`` (``out`` if given)."""
+    from .imageio import enhance_bgr_u8
+    res = sharded_forward(lambda t: enhance_bgr_u8(net, t, window=window), batch, device, src=src,
+                          gather=True, stats=stats)
+    if res is not None and out is not None:
+        out.copy_(res, non_blocking=True)
+        return out
+    return res
