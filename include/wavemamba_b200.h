@@ -220,9 +220,12 @@ int wm_ps_down_fwd(const float *x, const float *weight, const float *bias, float
  *      (basicsr/utils/img_util.py:9-33, inference_wavemamba.py:28-36,102-106) and the crop +
  *      tensor2img on the way out (inference_wavemamba.py:112-113, img_util.py:36-98) -----------
  * img: (B,H,W,3) uint8, BGR (a cv2 image), 4-byte aligned.  out: (B,3,Hp,Wp) float32 RGB in [0,1],
- * reflect-padded at the bottom / right (Hp-H < H, Wp-W < W), 16-byte aligned.  Bit-exact. */
+ * reflect-padded at the bottom / right (Hp-H < H, Wp-W < W), 16-byte aligned.  Bit-exact:
+ * reciprocal == 0: byte / 255.0f (IEEE division -- what the reference's line computes on a CPU tensor);
+ * reciprocal != 0: byte * (1.0f / 255.0f) -- what the same line computes on a CUDA tensor (torch's
+ * tensor / python-scalar kernel multiplies by the reciprocal), i.e. the reference script's GPU run. */
 int wm_img_u8_to_f32_fwd(const uint8_t *img, float *out, int64_t B, int64_t H, int64_t W, int64_t Hp,
-                         int64_t Wp, wm_stream_t stream);
+                         int64_t Wp, int reciprocal, wm_stream_t stream);
 /* x: (B,3,Hs,Ws) float32 RGB.  img: (B,h,w,3) uint8 BGR = round_half_even(clamp(x[:, :, :h, :w], 0, 1)
  * * 255).  Bit-exact with tensor2img. */
 int wm_img_f32_to_u8_fwd(const float *x, uint8_t *img, int64_t B, int64_t h, int64_t w, int64_t Hs,

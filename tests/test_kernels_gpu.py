@@ -242,7 +242,7 @@ def _rand(*shape, g, s=1.0):
 
 @pytest.mark.parametrize("cout", [32, 64, 96])
 @pytest.mark.parametrize("use_ln", [False, True])
-@pytest.mark.parametrize("hw", [(13, 37), (8, 32), (24, 70)])
+@pytest.mark.parametrize("hw", [(13, 37), (8, 32), (24, 70), (40, 96)])
 def test_pw_dw(ops, dev, cout, use_ln, hw):
     g = torch.Generator().manual_seed(7)
     h, w = hw
@@ -255,6 +255,31 @@ def test_pw_dw(ops, dev, cout, use_ln, hw):
     d = lambda v: None if v is None else v.to(dev)
     got = ops.pw_dw(d(x), d(pw_w), d(pw_b), d(dw_w), d(dw_b), d(ln_w), d(ln_b), 1e-6).cpu()
     torch.testing.assert_close(got, want, rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("cout,act", [(32, "none"), (64, "silu"), (64, "none"), (96, "none")])
+def test_pw_dw_many_tiles_per_cta(ops, dev, cout, act):
+    """The TMA + tcgen05 pipeline on a map where every persistent CTA walks several tiles (ragged
+    bottom rows, batch 2: 650 tiles on 148 SMs), against the fp64 composition on the GPU; and the
+    legacy cp.async / mma.sync kernel (w % 4 != 0) on the same kind of map."""
+    g = torch.Generator().manual_seed(8)
+    for h, w in ((203, 400), (61, 150)):
+        x = _rand(2, 32, h, w, g=g).to(dev)
+        pw_w, pw_b = _rand(cout, 32, 1, 1, g=g, s=0.2).to(dev), _rand(cout, g=g, s=0.1).to(dev)
+        dw_w, dw_b = _rand(cout, 1, 3, 3, g=g, s=0.3).to(dev), _rand(cout, g=g, s=0.1).to(dev)
+        ln_w, ln_b = (1 + _rand(32, g=g, s=0.1)).to(dev), _rand(32, g=g, s=0.1).to(dev)
+        xd = x.double()
+        mu = xd.mean(1, keepdim=True)
+        t = (xd - mu) / ((xd - mu).pow(2).mean(1, keepdim=True) + 1e-6).sqrt()
+        t = t * ln_w.double().view(1, -1, 1, 1) + ln_b.double().view(1, -1, 1, 1)
+        want = F.conv2d(F.conv2d(t, pw_w.double(), pw_b.double()), dw_w.double(), dw_b.double(), padding=1,
+                        groups=cout)
+        if act == "silu":
+            want = F.silu(want)
+        got = ops.pw_dw(x, pw_w, pw_b, dw_w, dw_b, ln_w, ln_b, 1e-6, act=act)
+        err = (got.double() - want).abs().max().item()
+        assert err <= 2e-5 * max(1.0, want.abs().max().item()), (h, w, err)
+        assert torch.equal(got, ops.pw_dw(x, pw_w, pw_b, dw_w, dw_b, ln_w, ln_b, 1e-6, act=act))
 
 
 @pytest.mark.parametrize("hw", [(13, 37), (16, 64)])
@@ -598,6 +623,10 @@ def test_img_u8_to_f32_bit_exact(ops, dev, shape, window):
     got = ops.img_u8_to_f32(img.to(dev), window)
     assert got.shape == want.shape
     assert torch.equal(got.cpu(), want)
+    # the same reference line evaluated on a CUDA tensor (torch multiplies by the reciprocal there)
+    x = img.to(dev).flip(-1).permute(0, 3, 1, 2).float() / 255.
+    want_cuda = F.pad(x, (0, want.shape[3] - W, 0, want.shape[2] - H), "reflect")
+    assert torch.equal(ops.img_u8_to_f32(img.to(dev), window, cuda_division=True), want_cuda)
 
 
 @pytest.mark.parametrize("shape,crop", [((1, 16, 24), (16, 24)), ((2, 56, 40), (50, 37)),

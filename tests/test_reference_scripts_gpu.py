@@ -67,9 +67,15 @@ def test_inference_script_runs_unmodified_on_the_plugin(tmp_path, dev, params_ca
         img = cv2.imread(str(low / name), cv2.IMREAD_UNCHANGED)
         gt_img = cv2.imread(str(high / name), cv2.IMREAD_UNCHANGED)
         written = cv2.imread(str(outd / name), cv2.IMREAD_UNCHANGED)
-        ours = wm.enhance_bgr_u8(net, torch.from_numpy(img), window=128).cpu().numpy()
+        # the script evaluates `img2tensor(img).to(device) / 255.` on a CUDA tensor, which torch
+        # computes as a multiplication by the rounded reciprocal: cuda_division=True is that run
+        ours = wm.enhance_bgr_u8(net, torch.from_numpy(img), window=128, cuda_division=True).cpu().numpy()
         assert written.shape == ours.shape == (H, W, 3)
         assert np.array_equal(written, ours), f"{name}: {(written != ours).sum()} bytes differ"
+        ieee = wm.enhance_bgr_u8(net, torch.from_numpy(img), window=128).cpu().numpy()
+        print(f"{name}: IEEE-division input path differs from the script's GPU run in "
+              f"{(ieee != written).sum()} of {written.size} bytes")
+        assert (ieee != written).sum() <= 1e-4 * written.size
         # the oracle on the same file
         xo = om.img_u8_to_f32(torch.from_numpy(img)[None], 128)
         yo = om.img_f32_to_u8(om.unet_forward(params, xo), H, W)[0].numpy()

@@ -48,7 +48,7 @@ SIGNATURES = {
     "wm_skff_workspace_bytes": (c_size_t, [c_int64] * 3),
     "wm_skff_fwd": (c_int, [c_void_p] * 10 + [c_size_t] + [c_int64] * 4 + [c_void_p]),
     "wm_ps_down_fwd": (c_int, [c_void_p] * 4 + [c_int64] * 3 + [c_int, c_void_p]),
-    "wm_img_u8_to_f32_fwd": (c_int, [c_void_p] * 2 + [c_int64] * 5 + [c_void_p]),
+    "wm_img_u8_to_f32_fwd": (c_int, [c_void_p] * 2 + [c_int64] * 5 + [c_int, c_void_p]),
     "wm_img_f32_to_u8_fwd": (c_int, [c_void_p] * 2 + [c_int64] * 5 + [c_void_p]),
 }
 

@@ -31,7 +31,7 @@
 //               the gated 64->64 and the 32->96 one), so the epilogue overlaps the next tile's MMAs
 #include <atomic>
 
-#include "common.cuh"
+#include "tc5_common.cuh"
 
 namespace wm {
 namespace tc5 {
@@ -72,99 +72,6 @@ struct Args {
     // in_c4 needs Ca == CIN (no second input); used between PAConv.k3 and k4.
     int in_c4, out_c4;
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// K-major, no swizzle: 8-row groups SBO bytes apart, the two 16-byte K chunks LBO bytes apart.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
-{
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3fff);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
-    d |= (uint64_t)1 << 46;   // descriptor version for sm_100
-    return d;                 // base_offset 0, lbo_mode 0, layout_type 0 (no swizzle)
-}
-
-__device__ __forceinline__ void mma_tf32_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
-                                            uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
-        "}\n"
-        :
-        : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u),
-          "r"(0u)
-        : "memory");
-}
-
-__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t mbar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
-}
-// Blocks until the phase with parity `parity` has completed.  try_wait suspends the thread in
-// hardware for a bounded time; the retry loop is bounded too (a protocol bug traps instead of
-// hanging the GPU).
-__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity)
-{
-    uint32_t ok = 0;
-#pragma unroll 1
-    for (int spin = 0; spin < (1 << 20); ++spin) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}\n"
-            : "=r"(ok)
-            : "r"(mbar), "r"(parity)
-            : "memory");
-        if (ok) return;
-    }
-    __trap();
-}
-// tcgen05.commit: the mbarrier gets one arrival when every MMA issued so far by this thread is done
-__device__ __forceinline__ void mma_commit(uint32_t mbar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t mbar)
-{
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-        "l"(src), "r"(bytes), "r"(mbar)
-        : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
-          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
-          "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
-          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-}
-
-__device__ __forceinline__ float tf32_lo(float v)
-{
-    return v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-}
 
 template <int CIN, int COUT, bool GATE>
 struct Cfg {
@@ -338,12 +245,14 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
         // =============================== weight producer ====================================
         if (lane == 0) {
             uint32_t cnt = 0;
+            const int rot = blockIdx.x % NTAPS;   // see the MMA issuer
 #pragma unroll 1
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
 #pragma unroll 1
                 for (int part = 0; part < NCH; ++part) {
 #pragma unroll 1
-                    for (int tap = 0; tap < NTAPS; ++tap, ++cnt) {
+                    for (int ti = 0; ti < NTAPS; ++ti, ++cnt) {
+                        const int tap = ti + rot < NTAPS ? ti + rot : ti + rot - NTAPS;
                         const int st = cnt % kStages;
                         mbar_wait(wempty(st), ((cnt / kStages) & 1u) ^ 1u);
                         mbar_expect_tx(wfull(st), (uint32_t)C::kChunkBytes);
@@ -368,6 +277,9 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
             const uint64_t a_lo0 = make_desc(smem_u32(xlo), kNPos * 16u, 128u);
             const uint64_t b_00 = make_desc(smem_u32(wbuf), 2 * COUT * 16u, 128u);
             uint32_t cnt = 0, unit = 0, tcount = 0;
+            // CTAs walk the taps in rotated orders so that the 148 SMs do not all pull the same
+            // 16 KB weight chunk from the same L2 lines at the same moment
+            const int rot = blockIdx.x % NTAPS;
             long long tacc[5] = {0, 0, 0, 0, 0}, t0 = 0, tp = 0;
             const bool timed = a.dbg != nullptr;
             if (timed) { t0 = clock64(); tp = t0; }
@@ -386,7 +298,8 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     WM_TICK(2);
 #pragma unroll 1
-                    for (int tap = 0; tap < NTAPS; ++tap, ++cnt) {
+                    for (int ti = 0; ti < NTAPS; ++ti, ++cnt) {
+                        const int tap = ti + rot < NTAPS ? ti + rot : ti + rot - NTAPS;
                         const int st = cnt % kStages;
                         mbar_wait(wfull(st), (cnt / kStages) & 1u);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -404,7 +317,10 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
                             for (int kl = 0; kl < 4; ++kl) {
                                 const uint32_t aoff = (uint32_t)(2 * kl) * kNPos + arow;
                                 const uint32_t boff = (uint32_t)(2 * kl) * 2 * COUT;
-                                const uint32_t first = (part == 0 && kl == 0 && (tap == 0 || gate_tap)) ? 0u : 1u;
+                                // the first MMA into an accumulator region overwrites it: the main
+                                // region at the first 3x3 tap of K half 0, the gate region at the gate tap
+                                const bool first_main = ti == 0 || (GATE && ti == 1 && rot == 9);
+                                const uint32_t first = (part == 0 && kl == 0 && (gate_tap || first_main)) ? 0u : 1u;
                                 // cols [0,COUT) += a_hi b_hi, [COUT,2COUT) += a_hi b_lo ; cols [0,COUT) += a_lo b_hi
                                 mma_tf32_ss(dcol, a_hi0 + aoff, b_hi0 + boff, idesc2, first);
                                 mma_tf32_ss(dcol, a_lo0 + aoff, b_hi0 + boff, idesc, 1u);
@@ -452,8 +368,9 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
                 uint32_t acc[32];
                 {
                     uint32_t part[32];
-                    tmem_ld32(lane_addr + (uint32_t)c0, acc);
+                    tmem_ld32(lane_addr + (uint32_t)c0, acc);              // both loads in flight
                     tmem_ld32(lane_addr + (uint32_t)(COUT + c0), part);
+                    tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(part[j]));
@@ -462,6 +379,7 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
                     uint32_t gt[32], part[32];
                     tmem_ld32(lane_addr + (uint32_t)(4 * COUT + c0), gt);
                     tmem_ld32(lane_addr + (uint32_t)(4 * COUT + COUT + c0), part);
+                    tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const float z = (__uint_as_float(gt[j]) + __uint_as_float(part[j])) +

@@ -19,8 +19,13 @@ constexpr int kThreads = 256;
 __device__ __forceinline__ int reflect(int i, int n) { return i < n ? i : 2 * (n - 1) - i; }
 
 __global__ void __launch_bounds__(kThreads)
-u8_to_f32_kernel(const uint8_t *__restrict__ img, float *__restrict__ out, int H, int W, int Hp, int Wp)
+u8_to_f32_kernel(const uint8_t *__restrict__ img, float *__restrict__ out, int H, int W, int Hp, int Wp,
+                 int recip)
 {
+    // "/ 255." is an IEEE division on the CPU; torch's CUDA kernel for tensor / python-scalar
+    // multiplies by the rounded reciprocal instead (1 ulp apart for some bytes).  Both are offered.
+    const float inv255 = __fdiv_rn(1.0f, 255.0f);
+    auto scale = [&](uint8_t v) { return recip ? __fmul_rn((float)v, inv255) : __fdiv_rn((float)v, 255.0f); };
     const int b = blockIdx.z, y = blockIdx.y;
     const int x0 = (blockIdx.x * kThreads + threadIdx.x) * 4;
     if (x0 >= Wp) return;
@@ -36,9 +41,9 @@ u8_to_f32_kernel(const uint8_t *__restrict__ img, float *__restrict__ out, int H
                                 (uint8_t)(w2), (uint8_t)(w2 >> 8), (uint8_t)(w2 >> 16), (uint8_t)(w2 >> 24)};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            bl[i] = __fdiv_rn((float)by[3 * i + 0], 255.0f);
-            g[i] = __fdiv_rn((float)by[3 * i + 1], 255.0f);
-            r[i] = __fdiv_rn((float)by[3 * i + 2], 255.0f);
+            bl[i] = scale(by[3 * i + 0]);
+            g[i] = scale(by[3 * i + 1]);
+            r[i] = scale(by[3 * i + 2]);
         }
     } else {
 #pragma unroll
@@ -46,9 +51,9 @@ u8_to_f32_kernel(const uint8_t *__restrict__ img, float *__restrict__ out, int H
             const int x = x0 + i;
             const int sx = reflect(x < Wp ? x : Wp - 1, W);
             const uint8_t *p = row + (int64_t)sx * 3;
-            bl[i] = __fdiv_rn((float)__ldg(p + 0), 255.0f);
-            g[i] = __fdiv_rn((float)__ldg(p + 1), 255.0f);
-            r[i] = __fdiv_rn((float)__ldg(p + 2), 255.0f);
+            bl[i] = scale(__ldg(p + 0));
+            g[i] = scale(__ldg(p + 1));
+            r[i] = scale(__ldg(p + 2));
         }
     }
     const int64_t plane = (int64_t)Hp * Wp;
@@ -100,7 +105,7 @@ f32_to_u8_kernel(const float *__restrict__ x, uint8_t *__restrict__ img, int h, 
 }  // namespace wm
 
 extern "C" int wm_img_u8_to_f32_fwd(const uint8_t *img, float *out, int64_t B, int64_t H, int64_t W,
-                                    int64_t Hp, int64_t Wp, wm_stream_t stream)
+                                    int64_t Hp, int64_t Wp, int reciprocal, wm_stream_t stream)
 {
     using namespace wm;
     WM_REQUIRE(B >= 0 && H >= 0 && W >= 0 && B <= 65535 && Hp <= 65535, "wm_img_u8_to_f32_fwd: bad sizes");
@@ -112,7 +117,8 @@ extern "C" int wm_img_u8_to_f32_fwd(const uint8_t *img, float *out, int64_t B, i
                "wm_img_u8_to_f32_fwd: img must be 4-byte and out 16-byte aligned");
     dim3 grid((unsigned)((Wp + 4 * imgio::kThreads - 1) / (4 * imgio::kThreads)), (unsigned)Hp, (unsigned)B);
     imgio::u8_to_f32_kernel<<<grid, imgio::kThreads, 0, (cudaStream_t)stream>>>(img, out, (int)H, (int)W,
-                                                                                  (int)Hp, (int)Wp);
+                                                                                  (int)Hp, (int)Wp,
+                                                                                  reciprocal ? 1 : 0);
     WM_LAUNCH_OK("img u8->f32");
     return WM_OK;
 }

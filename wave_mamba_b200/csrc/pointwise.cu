@@ -7,9 +7,16 @@
 // Spatial kernels work on 8x32-pixel tiles with a one-pixel halo held in shared memory
 // [channel][position]; lanes always run along the image row, so global accesses are
 // coalesced 128-byte rows and shared-memory accesses are conflict-free.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace wm {
+namespace pwdw {   // pw_dw_tc5.cu: returns 1 when the TMA preconditions do not hold
+int forward(const float *x, const float *ln_w, const float *ln_b, float eps, const float *pw_w,
+            const float *pw_b, const float *dw_w, const float *dw_b, int act, float *y, int64_t B,
+            int64_t Cout, int64_t h, int64_t w, cudaStream_t s);
+}
 namespace pw {
 
 constexpr int kTH = 8, kTW = 32;               // interior tile
@@ -400,6 +407,13 @@ extern "C" int wm_pw_dw_fwd(const float *x, const float *ln_w, const float *ln_b
     WM_REQUIRE((h + kTH - 1) / kTH <= 65535, "wm_pw_dw_fwd: image too tall");
     if (B == 0 || h == 0 || w == 0) return WM_OK;
     cudaStream_t s = (cudaStream_t)stream;
+    // TMA + tcgen05 pipeline (pw_dw_tc5.cu) whenever its preconditions hold; WM_PW_DW_LEGACY=1 is a
+    // developer switch for A/B timing of the cp.async + mma.sync kernel below
+    static const bool legacy = getenv("WM_PW_DW_LEGACY") != nullptr;
+    if (!legacy) {
+        const int rc = wm::pwdw::forward(x, ln_w, ln_b, eps, pw_w, pw_b, dw_w, dw_b, act, y, B, Cout, h, w, s);
+        if (rc != 1) return rc;
+    }
     if (Cout == 32) return launch_pw_dw<32>(x, ln_w, ln_b, eps, pw_w, pw_b, dw_w, dw_b, act, y, B, h, w, s);
     if (Cout == 64) return launch_pw_dw<64>(x, ln_w, ln_b, eps, pw_w, pw_b, dw_w, dw_b, act, y, B, h, w, s);
     return launch_pw_dw<96>(x, ln_w, ln_b, eps, pw_w, pw_b, dw_w, dw_b, act, y, B, h, w, s);

@@ -1,0 +1,439 @@
+// y = act( dw3x3( pw1x1( LayerNorm_c?(x) ) ) ),  Cin = 32, Cout in {32, 64, 96}: the fused
+// pointwise + depthwise groups of HFEBlock / LFSSBlock (reference wavemamba_arch.py:483-487
+// in_proj+conv2d+SiLU, :226 ffn conv1+conv2, :729-732 project_in, :762-764 qkv+qkv_dwconv), as a
+// persistent, warp-specialised sm_100a pipeline (one CTA per SM):
+//
+//   TMA        one cp.async.bulk.tensor (4-D box 36 x 10 x 32ch, zero fill outside the image) per
+//              8x32-pixel tile brings the halo tile into shared memory; the next tile's box is in
+//              flight while the current tile is computed
+//   warps 0-3  LayerNorm over channels per halo position, written straight into the UMMA K-major
+//              operand layout [ci/4][position][ci%4] as tf32 hi and lo = a - hi (3xTF32 split)
+//   warp 12    one thread issues tcgen05.mma kind::tf32 (M=128 positions, N=64 = [w_hi | w_lo] of a
+//              32-channel output group, K=32 in 4 steps) into TMEM, double-buffered per group
+//   warps 4-11 TMEM -> registers -> +bias, zero outside the image (the depthwise conv pads the 1x1
+//              OUTPUT) -> shared [channel][position]; then the depthwise 3x3 + SiLU from shared
+//              memory, two adjacent pixels per thread (8-byte shared loads and global stores)
+//
+// Falls back to the cp.async / mma.sync kernel of pointwise.cu when the TMA preconditions do not
+// hold (w % 4 != 0 or unaligned pointers).
+#include <cuda.h>
+
+#include "tc5_common.cuh"
+
+namespace wm {
+namespace pwdw {
+
+using namespace wm::tc5;
+
+constexpr int kTH = 8, kTW = 32;
+constexpr int kBoxW = 36, kBoxH = kTH + 2;     // TMA box: columns tx0-1 .. tx0+34, rows ty0-1 .. ty0+8
+constexpr int kPos = kBoxW * kBoxH;            // 360 halo positions
+constexpr int kMPos = 384;                     // three M=128 MMAs
+constexpr int kCin = 32;
+constexpr int kWarpsA = 4, kWarpsB = 8;
+constexpr int kThreadsA = 32 * kWarpsA, kThreadsB = 32 * kWarpsB;
+constexpr int kWarpMma = kWarpsA + kWarpsB;
+constexpr int kThreads = 32 * (kWarpMma + 1);  // 416
+constexpr int kAccCols = 3 * 64;               // one accumulator set: 3 M tiles x [32 hi-sum | 32 lo]
+constexpr uint32_t kBoxBytes = kPos * kCin * 4;
+
+template <int COUT>
+struct Smem {
+    static constexpr int G = COUT / 32;
+    static constexpr size_t xraw = 0;                                  // [32][360] floats (TMA box)
+    static constexpr size_t xhi = xraw + (size_t)kCin * kPos * 4;      // [8][384] float4
+    static constexpr size_t xlo = xhi + (size_t)8 * kMPos * 16;
+    static constexpr size_t ps = xlo + (size_t)8 * kMPos * 16;         // [32][360] floats
+    static constexpr size_t wsm = ps + (size_t)32 * kPos * 4;          // [G][8][64] float4
+    static constexpr size_t cst = wsm + (size_t)G * 8 * 64 * 16;       // pwb[COUT] dww[COUT*9] dwb[COUT] lnw[32] lnb[32]
+    static constexpr size_t bars = cst + (size_t)(COUT * 11 + 64) * 4; // 8 mbarriers + tmem slot
+    static constexpr size_t total = bars + 8 * 8 + 16;
+    static_assert(xhi % 128 == 0 && wsm % 16 == 0 && bars % 8 == 0, "alignment");
+    static_assert(total <= 232448, "shared memory budget");
+};
+
+struct Args {
+    const float *ln_w, *ln_b;
+    float eps;
+    const float *pw_w, *pw_b, *dw_w, *dw_b;
+    float *y;
+    int h, w, tiles_x, tiles_y, total_tiles;
+};
+
+__device__ __forceinline__ void tma_load_box(uint32_t dst, const CUtensorMap *tmap, int c0, int c1, int c2,
+                                             int c3, uint32_t mbar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(mbar)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+          "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+
+__device__ __forceinline__ void named_bar(int id, int count)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+template <int COUT, bool LN, bool SILU>
+__global__ void __launch_bounds__(kThreads, 1)
+pw_dw_tc5_kernel(const __grid_constant__ CUtensorMap tmap, const Args a)
+{
+    using S = Smem<COUT>;
+    constexpr int G = S::G;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *xraw = reinterpret_cast<float *>(smem_raw + S::xraw);
+    float4 *xhi = reinterpret_cast<float4 *>(smem_raw + S::xhi);
+    float4 *xlo = reinterpret_cast<float4 *>(smem_raw + S::xlo);
+    float *ps = reinterpret_cast<float *>(smem_raw + S::ps);
+    float4 *wsm = reinterpret_cast<float4 *>(smem_raw + S::wsm);
+    float *pwb = reinterpret_cast<float *>(smem_raw + S::cst);
+    float *dww = pwb + COUT;
+    float *dwb = dww + COUT * 9;
+    float *lnw = dwb + COUT;
+    float *lnb = lnw + 32;
+    const uint32_t bar0 = smem_u32(smem_raw + S::bars);
+    const uint32_t xraw_full = bar0, xk_full = bar0 + 8, xk_empty = bar0 + 16;
+    auto acc_full = [&](int i) { return bar0 + 24u + 8u * (uint32_t)i; };
+    auto acc_empty = [&](int i) { return bar0 + 40u + 8u * (uint32_t)i; };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem_raw + S::bars + 64);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int h = a.h, w = a.w;
+    const int64_t hw = (int64_t)h * w;
+
+    // ---- one-time setup ---------------------------------------------------------------------
+    if (tid == 0) {
+        mbar_init(xraw_full, 1);
+        mbar_init(xk_full, kThreadsA);
+        mbar_init(xk_empty, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), kWarpsB); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kWarpMma) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_u32(tmem_slot)),
+                     "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // 1x1 weights -> UMMA K-major B operand [group][kc][hi co 0..31 | lo co 0..31], split at rna
+    for (int i = tid; i < COUT * 8; i += kThreads) {
+        const int co = i >> 3, kc = i & 7;
+        float hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float v = __ldg(a.pw_w + co * kCin + kc * 4 + j);
+            uint32_t hb, lb;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+            const float rest = v - __uint_as_float(hb);
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(rest));
+            hi[j] = __uint_as_float(hb);
+            lo[j] = __uint_as_float(lb);
+        }
+        float4 *dst = wsm + ((co >> 5) * 8 + kc) * 64 + (co & 31);
+        dst[0] = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        dst[32] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    }
+    for (int i = tid; i < COUT; i += kThreads) {
+        pwb[i] = a.pw_b ? __ldg(a.pw_b + i) : 0.0f;
+        dwb[i] = __ldg(a.dw_b + i);
+    }
+    for (int i = tid; i < COUT * 9; i += kThreads) dww[i] = __ldg(a.dw_w + i);
+    if (LN && tid < 32) { lnw[tid] = __ldg(a.ln_w + tid); lnb[tid] = __ldg(a.ln_b + tid); }
+    // rows 360..383 of the operand (read by the third M tile, results never used): defined values
+    for (int i = tid; i < 8 * (kMPos - kPos); i += kThreads) {
+        const int kc = i / (kMPos - kPos), r = i - kc * (kMPos - kPos);
+        xhi[kc * kMPos + kPos + r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        xlo[kc * kMPos + kPos + r] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto tile_coords = [&](int tile, int &tx0, int &ty0, int &b) {
+        const int txi = tile % a.tiles_x, tyi = (tile / a.tiles_x) % a.tiles_y;
+        b = tile / (a.tiles_x * a.tiles_y);
+        tx0 = txi * kTW;
+        ty0 = tyi * kTH;
+    };
+
+    if (warp < kWarpsA) {
+        // =========================== LayerNorm + operand layout ==============================
+        auto issue_tma = [&](int tile) {
+            int tx0, ty0, b;
+            tile_coords(tile, tx0, ty0, b);
+            mbar_expect_tx(xraw_full, kBoxBytes);
+            tma_load_box(smem_u32(xraw), &tmap, tx0 - 1, ty0 - 1, 0, b, xraw_full);
+        };
+        if (tid == 0 && (int)blockIdx.x < a.total_tiles) issue_tma(blockIdx.x);
+        uint32_t it = 0;
+#pragma unroll 1
+        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
+            mbar_wait(xraw_full, it & 1u);
+            mbar_wait(xk_empty, (it & 1u) ^ 1u);       // the previous tile's MMAs have read xhi/xlo
+#pragma unroll 1
+            for (int pos = tid; pos < kPos; pos += kThreadsA) {
+                float v[kCin];
+#pragma unroll
+                for (int c = 0; c < kCin; ++c) v[c] = xraw[c * kPos + pos];
+                if (LN) {
+                    float mu = 0.0f;
+#pragma unroll
+                    for (int c = 0; c < kCin; ++c) mu += v[c];
+                    mu *= (1.0f / kCin);
+                    float var = 0.0f;
+#pragma unroll
+                    for (int c = 0; c < kCin; ++c) { const float d = v[c] - mu; var = fmaf(d, d, var); }
+                    var *= (1.0f / kCin);
+                    const float rstd = 1.0f / sqrtf(var + a.eps);
+#pragma unroll
+                    for (int c = 0; c < kCin; ++c) v[c] = fmaf((v[c] - mu) * rstd, lnw[c], lnb[c]);
+                }
+#pragma unroll
+                for (int kc = 0; kc < 8; ++kc) {
+                    const float4 t = make_float4(v[4 * kc], v[4 * kc + 1], v[4 * kc + 2], v[4 * kc + 3]);
+                    xhi[kc * kMPos + pos] = t;
+                    xlo[kc * kMPos + pos] = make_float4(tf32_lo(t.x), tf32_lo(t.y), tf32_lo(t.z), tf32_lo(t.w));
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(xk_full);
+            named_bar(1, kThreadsA);                   // every thread is done reading xraw
+            if (tid == 0 && tile + (int)gridDim.x < a.total_tiles) issue_tma(tile + gridDim.x);
+        }
+    } else if (warp == kWarpMma) {
+        // =========================== MMA issuer ==============================================
+        if (lane == 0) {
+            constexpr uint32_t idesc64 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) |
+                                         ((uint32_t)(128 >> 4) << 24);
+            constexpr uint32_t idesc32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(32 >> 3) << 17) |
+                                         ((uint32_t)(128 >> 4) << 24);
+            const uint64_t a_hi0 = make_desc(smem_u32(xhi), kMPos * 16u, 128u);
+            const uint64_t a_lo0 = make_desc(smem_u32(xlo), kMPos * 16u, 128u);
+            const uint64_t b_0 = make_desc(smem_u32(wsm), 64 * 16u, 128u);
+            uint32_t it = 0, gcount = 0;
+#pragma unroll 1
+            for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
+                mbar_wait(xk_full, it & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+                for (int g = 0; g < G; ++g, ++gcount) {
+                    const int buf = gcount & 1;
+                    mbar_wait(acc_empty(buf), ((gcount >> 1) & 1u) ^ 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                    for (int mt = 0; mt < 3; ++mt) {
+                        const uint32_t d = tmem_base + (uint32_t)(buf * kAccCols + mt * 64);
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint32_t aoff = (uint32_t)(2 * ks * kMPos + mt * 128);
+                            const uint32_t boff = (uint32_t)((g * 8 + 2 * ks) * 64);
+                            // cols [0,32) += a_hi w_hi, [32,64) += a_hi w_lo ; cols [0,32) += a_lo w_hi
+                            mma_tf32_ss(d, a_hi0 + aoff, b_0 + boff, idesc64, ks > 0 ? 1u : 0u);
+                            mma_tf32_ss(d, a_lo0 + aoff, b_0 + boff, idesc32, 1u);
+                        }
+                    }
+                    mma_commit(acc_full(buf));
+                }
+                mma_commit(xk_empty);
+            }
+        }
+    } else {
+        // =========================== epilogue + depthwise 3x3 ================================
+        const int e = warp - kWarpsA;                  // 0..7
+        const int quarter = warp & 3, chalf = e >> 2;  // TMEM lane quarter, 16-channel half of the group
+        const int tb = tid - kThreadsA;                // 0..255
+        uint32_t gcount = 0;
+#pragma unroll 1
+        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+            int tx0, ty0, b;
+            tile_coords(tile, tx0, ty0, b);
+#pragma unroll 1
+            for (int g = 0; g < G; ++g, ++gcount) {
+                const int buf = gcount & 1;
+                mbar_wait(acc_full(buf), (gcount >> 1) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+                for (int mt = 0; mt < 3; ++mt) {
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
+                                           (uint32_t)(buf * kAccCols + mt * 64 + chalf * 16);
+                    uint32_t acc[16], part[16];
+                    tmem_ld16(taddr, acc);
+                    tmem_ld16(taddr + 32u, part);
+                    tmem_ld_wait();
+                    const int pos = mt * 128 + quarter * 32 + lane;
+                    if (pos < kPos) {
+                        const int row = pos / kBoxW, col = pos - row * kBoxW;
+                        const int gy = ty0 - 1 + row, gx = tx0 - 1 + col;
+                        const bool valid = gy >= 0 && gy < h && gx >= 0 && gx < w;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float v = (__uint_as_float(acc[j]) + __uint_as_float(part[j])) +
+                                            pwb[g * 32 + chalf * 16 + j];
+                            ps[(chalf * 16 + j) * kPos + pos] = valid ? v : 0.0f;
+                        }
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty(buf));
+                named_bar(2, kThreadsB);               // ps of this group is complete
+
+                // depthwise 3x3 (+ SiLU): item = (channel, column pair), 8 rows, sliding window
+#pragma unroll 1
+                for (int i = 0; i < 2; ++i) {
+                    const int item = tb + i * kThreadsB;
+                    const int cl = item >> 4, j2 = (item & 15) * 2;
+                    const int co = g * 32 + cl;
+                    float k[9];
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) k[t] = dww[co * 9 + t];
+                    const float bias = dwb[co];
+                    const float *pc = ps + cl * kPos + j2;
+                    float r0[4], r1[4], r2[4];
+                    {
+                        const float2 p0 = *reinterpret_cast<const float2 *>(pc), p1 = *reinterpret_cast<const float2 *>(pc + 2);
+                        const float2 q0 = *reinterpret_cast<const float2 *>(pc + kBoxW), q1 = *reinterpret_cast<const float2 *>(pc + kBoxW + 2);
+                        r0[0] = p0.x; r0[1] = p0.y; r0[2] = p1.x; r0[3] = p1.y;
+                        r1[0] = q0.x; r1[1] = q0.y; r1[2] = q1.x; r1[3] = q1.y;
+                    }
+                    const int gx = tx0 + j2;
+                    float *yo = a.y + ((int64_t)b * COUT + co) * hw + (int64_t)ty0 * w + gx;
+#pragma unroll
+                    for (int row = 0; row < kTH; ++row) {
+                        const float2 s0 = *reinterpret_cast<const float2 *>(pc + (row + 2) * kBoxW);
+                        const float2 s1 = *reinterpret_cast<const float2 *>(pc + (row + 2) * kBoxW + 2);
+                        r2[0] = s0.x; r2[1] = s0.y; r2[2] = s1.x; r2[3] = s1.y;
+                        float o0 = bias, o1 = bias;
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx) {
+                            o0 = fmaf(k[dx], r0[dx], o0);     o1 = fmaf(k[dx], r0[dx + 1], o1);
+                        }
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx) {
+                            o0 = fmaf(k[3 + dx], r1[dx], o0); o1 = fmaf(k[3 + dx], r1[dx + 1], o1);
+                        }
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx) {
+                            o0 = fmaf(k[6 + dx], r2[dx], o0); o1 = fmaf(k[6 + dx], r2[dx + 1], o1);
+                        }
+                        if (SILU) {   // SS2D.act (reference :487)
+                            o0 = __fdividef(o0, 1.0f + __expf(-o0));
+                            o1 = __fdividef(o1, 1.0f + __expf(-o1));
+                        }
+                        // w % 4 == 0 and gx even: the pair is inside the image or outside together
+                        if (gx < w && ty0 + row < h)
+                            *reinterpret_cast<float2 *>(yo + (int64_t)row * w) = make_float2(o0, o1);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) { r0[q] = r1[q]; r1[q] = r2[q]; }
+                    }
+                }
+                named_bar(2, kThreadsB);               // ps may be overwritten by the next group
+            }
+        }
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == kWarpMma) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u)
+                     : "memory");
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// NCHW fp32 tensor (B, 32, h, w) as a 4-D tensor map with a 36 x 10 x 32 x 1 box
+static bool make_tmap(CUtensorMap *tm, const float *x, int64_t B, int64_t h, int64_t w)
+{
+    EncodeTiledFn enc = encode_fn();
+    if (enc == nullptr) return false;
+    const cuuint64_t dims[4] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)kCin, (cuuint64_t)B};
+    const cuuint64_t strides[3] = {(cuuint64_t)w * 4, (cuuint64_t)h * w * 4, (cuuint64_t)kCin * h * w * 4};
+    const cuuint32_t box[4] = {kBoxW, kBoxH, kCin, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult rc = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(x), dims, strides, box,
+                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return rc == CUDA_SUCCESS;
+}
+
+template <int COUT, bool LN, bool SILU>
+static int launch(const CUtensorMap &tm, const Args &a, cudaStream_t s)
+{
+    using S = Smem<COUT>;
+    WM_CUDA_OK(cudaFuncSetAttribute(pw_dw_tc5_kernel<COUT, LN, SILU>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::total));
+    const int grid = a.total_tiles < sm_count() ? a.total_tiles : sm_count();
+    pw_dw_tc5_kernel<COUT, LN, SILU><<<grid, kThreads, S::total, s>>>(tm, a);
+    WM_LAUNCH_OK("pw_dw (tcgen05)");
+    return WM_OK;
+}
+
+// Returns WM_OK when the tcgen05 path ran, 1 when its preconditions do not hold (the caller then uses
+// the cp.async / mma.sync kernel), or an error code.
+int forward(const float *x, const float *ln_w, const float *ln_b, float eps, const float *pw_w,
+            const float *pw_b, const float *dw_w, const float *dw_b, int act, float *y, int64_t B,
+            int64_t Cout, int64_t h, int64_t w, cudaStream_t s)
+{
+    if (w % 4 != 0 || !aligned16(x) || !aligned16(y) || w < kTW || h < kTH) return 1;
+    CUtensorMap tm;
+    if (!make_tmap(&tm, x, B, h, w)) return 1;
+    Args a;
+    a.ln_w = ln_w; a.ln_b = ln_b; a.eps = eps; a.pw_w = pw_w; a.pw_b = pw_b; a.dw_w = dw_w; a.dw_b = dw_b;
+    a.y = y; a.h = (int)h; a.w = (int)w;
+    a.tiles_x = (int)((w + kTW - 1) / kTW);
+    a.tiles_y = (int)((h + kTH - 1) / kTH);
+    const int64_t total = (int64_t)a.tiles_x * a.tiles_y * B;
+    if (total >= ((int64_t)1 << 31)) return 1;
+    a.total_tiles = (int)total;
+    const bool ln = ln_w != nullptr, silu = act == 1;
+#define WM_PWDW_CASE(C)                                                                  \
+    if (Cout == C) {                                                                     \
+        if (ln && silu) return launch<C, true, true>(tm, a, s);                          \
+        if (ln) return launch<C, true, false>(tm, a, s);                                 \
+        if (silu) return launch<C, false, true>(tm, a, s);                               \
+        return launch<C, false, false>(tm, a, s);                                        \
+    }
+    WM_PWDW_CASE(32)
+    WM_PWDW_CASE(64)
+    WM_PWDW_CASE(96)
+#undef WM_PWDW_CASE
+    return 1;
+}
+
+}  // namespace pwdw
+}  // namespace wm

@@ -17,11 +17,16 @@ from . import ops
 
 @torch.no_grad()
 def enhance_bgr_u8(net, img: torch.Tensor, window: int = 128, out: Optional[torch.Tensor] = None,
-                   device: Optional[torch.device] = None, sync: bool = False) -> torch.Tensor:
+                   device: Optional[torch.device] = None, sync: bool = False,
+                   cuda_division: bool = False) -> torch.Tensor:
     """img: (H,W,3) or (B,H,W,3) uint8 BGR, on the host (ideally pinned) or already on the GPU.
     Returns the enhanced uint8 BGR image(s) with the input's leading shape: on the GPU, or copied
     into ``out`` (a host uint8 tensor of the same shape, ideally pinned) when given.
     ``net`` is a ``WaveMamba`` (its ``restoration_network`` is used, as the reference does).
+
+    ``cuda_division=True`` reproduces the reference script's GPU run bit for bit (its ``/ 255.`` on a
+    CUDA tensor is a multiplication by the rounded reciprocal); the default is the IEEE division the
+    CPU reference and the oracle compute.
 
     Stream contract: everything is enqueued on the current CUDA stream.  With a pinned ``img`` /
     ``out`` the two PCIe copies are asynchronous: do not overwrite ``img`` or read ``out`` before the
@@ -39,7 +44,7 @@ def enhance_bgr_u8(net, img: torch.Tensor, window: int = 128, out: Optional[torc
     img = img.contiguous()
     _, H, W, _ = img.shape
     fwd = getattr(net, "restoration_network", net)
-    x = ops.img_u8_to_f32(img, window)                 # img2tensor, /255., check_image_size
+    x = ops.img_u8_to_f32(img, window, cuda_division)                 # img2tensor, /255., check_image_size
     y = fwd(x)
     res = ops.img_f32_to_u8(y, H, W)                   # [:, :, :h, :w] + tensor2img
     if squeeze:

@@ -560,9 +560,12 @@ def _chk_u8(t: torch.Tensor, name: str) -> torch.Tensor:
     return t
 
 
-def img_u8_to_f32(img: torch.Tensor, window: int = 128) -> torch.Tensor:
+def img_u8_to_f32(img: torch.Tensor, window: int = 128, cuda_division: bool = False) -> torch.Tensor:
     """(B,H,W,3) uint8 BGR -> (B,3,Hp,Wp) float32 RGB in [0,1], reflect-padded up to multiples of
-    `window`: img2tensor + /255. + check_image_size of inference_wavemamba.py, bit-exact."""
+    `window`: img2tensor + /255. + check_image_size of inference_wavemamba.py, bit-exact.
+    ``cuda_division=False``: IEEE ``byte / 255`` (the line evaluated on a CPU tensor, and the oracle);
+    ``True``: ``byte * (1/255)``, what torch computes for the same line on a CUDA tensor -- the
+    reference script's own GPU run (a few bytes per million differ by one ulp)."""
     _chk_u8(img, "img")
     if img.dim() != 4 or img.shape[3] != 3:
         raise ValueError(f"img: expected (B,H,W,3), got {tuple(img.shape)}")
@@ -573,7 +576,8 @@ def img_u8_to_f32(img: torch.Tensor, window: int = 128) -> torch.Tensor:
     out = torch.empty(B, 3, Hp, Wp, dtype=torch.float32, device=img.device)
     lib = _cabi.load()
     with torch.cuda.device(img.device):
-        rc = lib.wm_img_u8_to_f32_fwd(img.data_ptr(), out.data_ptr(), B, H, W, Hp, Wp, _stream(img))
+        rc = lib.wm_img_u8_to_f32_fwd(img.data_ptr(), out.data_ptr(), B, H, W, Hp, Wp,
+                                      1 if cuda_division else 0, _stream(img))
     _cabi.check(rc, "wm_img_u8_to_f32_fwd")
     if B and H and W:
         _count(1)
