@@ -85,6 +85,19 @@ int wm_ss2d_core_fwd(const float *x, const float *x_proj_weight, const float *dt
                      void *workspace, size_t workspace_bytes, int64_t B, int64_t h, int64_t w,
                      wm_stream_t stream);
 
+/* Backward of wm_ss2d_core_fwd (training: the gradient the reference gets from autograd through
+ * selective_scan_fn, the einsum projections and the cross-scan / cross-merge, :446-478,490).
+ * grad_y (B,64,h,w) -> grad_x (B,64,h,w) and the parameter gradients (same shapes as the
+ * parameters; overwritten, not accumulated).  Deterministic (fixed-order reductions).
+ * workspace: wm_ss2d_core_bwd_workspace_bytes(B,h,w) bytes, 256-byte aligned. */
+size_t wm_ss2d_core_bwd_workspace_bytes(int64_t B, int64_t h, int64_t w);
+int wm_ss2d_core_bwd(const float *x, const float *x_proj_weight, const float *dt_projs_weight,
+                     const float *dt_projs_bias, const float *A_logs, const float *Ds,
+                     const float *grad_y, float *grad_x, float *grad_x_proj_weight,
+                     float *grad_dt_projs_weight, float *grad_dt_projs_bias, float *grad_A_logs,
+                     float *grad_Ds, void *workspace, size_t workspace_bytes, int64_t B, int64_t h,
+                     int64_t w, wm_stream_t stream);
+
 /* ---- fused pointwise (1x1) / depthwise (3x3) convolution groups ----------------------------
  * HFEBlock / CMTAttention / FeedForward / PAConv / LFSSBlock.ffn pieces,
  * wavemamba_arch.py:214-231,687,694-697,729-742,756-764,775,797,826-851.
@@ -167,6 +180,10 @@ size_t wm_conv3x3_packed_bytes(int64_t Cin, int64_t Cout, int with_gate);
 /* Developer aid: non-NULL device buffer of 6*SMs int64 -> the kernel's MMA thread writes per-CTA
  * cycle counts (total, wait-weights, wait-X, wait-accumulators, issue, tiles); NULL disables. */
 int wm_conv3x3_debug_timing(void *device_buffer);
+/* Developer aid: synchronises the device, returns and clears the word in which the mbarrier pipelines
+ * (dense 3x3 conv, pw_dw) record a wait that timed out: 0 = none, else
+ * 0x80000000 | role << 24 | barrier << 16 | iteration of the first one. */
+int wm_debug_pipeline_error(unsigned int *out);
 int wm_conv3x3_prepack(const float *w3x3, const float *w1x1, void *packed, int64_t Cin, int64_t Cout,
                        wm_stream_t stream);
 int wm_conv3x3_fwd(const float *in_a, int64_t a_bstride, int64_t Ca, const float *in_b,

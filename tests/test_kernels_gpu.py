@@ -207,6 +207,32 @@ def test_ss2d_core_vs_arbiter_at_4k_level_sizes(ops, dev, params_cache, shape):
     assert err <= 2e-5 * scale
 
 
+@pytest.mark.parametrize("shape", [(1, 64, 6, 10), (2, 64, 9, 5), (1, 64, 24, 40), (1, 64, 70, 9)])
+def test_ss2d_core_backward_vs_oracle_autograd(ops, dev, params_cache, shape):
+    """wm_ss2d_core_bwd against autograd through the fp64 oracle (pure-torch sequential scan,
+    pinned by the finite-difference gradcheck in tests/test_oracle.py): gradients with respect to the
+    input map and all five parameter tensors, for a random upstream gradient.  Tolerance: 2e-4 of
+    the largest entry of each gradient (fp32 recurrences in both time directions, sums over L)."""
+    g = torch.Generator().manual_seed(21)
+    x = F.silu(0.5 * torch.randn(*shape, generator=g))
+    gy = torch.randn(*shape, generator=g)
+    prm = _ss_params(params_cache)
+    leaves = [x.double().requires_grad_(True)] + [t.double().clone().requires_grad_(True) for t in prm]
+    y = om.ss2d_core(*leaves, scan_fn=oscan.selective_scan_loop)
+    want = torch.autograd.grad(y, leaves, gy.double())
+    got = ops.ss2d_core_bwd(x.to(dev), *[t.to(dev) for t in prm], gy.to(dev))
+    names = ("x", "x_proj_weight", "dt_projs_weight", "dt_projs_bias", "A_logs", "Ds")
+    worst = 0.0
+    for n, a, b in zip(names, got, want):
+        scale = max(b.abs().max().item(), 1e-30)
+        err = (a.cpu().double() - b).abs().max().item() / scale
+        print(f"{shape} d{n}: rel err {err:.2e} (max |grad| {scale:.3e})")
+        worst = max(worst, err)
+    assert worst <= 2e-4
+    again = ops.ss2d_core_bwd(x.to(dev), *[t.to(dev) for t in prm], gy.to(dev))
+    assert all(torch.equal(a, b) for a, b in zip(got, again))
+
+
 def test_ss2d_core_is_deterministic(ops, dev, params_cache):
     x = F.silu(torch.randn(2, 64, 48, 72, device=dev))
     prm = [t.to(dev) for t in _ss_params(params_cache)]

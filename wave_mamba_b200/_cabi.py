@@ -26,6 +26,8 @@ SIGNATURES = {
     "wm_ss2d_debug_geometry": (c_int, [c_int64] * 3 + [c_void_p]),
     "wm_ss2d_dirs_fwd": (c_int, [c_void_p] * 7 + [c_size_t] + [c_int64] * 3 + [c_void_p]),
     "wm_ss2d_core_fwd": (c_int, [c_void_p] * 8 + [c_size_t] + [c_int64] * 3 + [c_void_p]),
+    "wm_ss2d_core_bwd_workspace_bytes": (c_size_t, [c_int64] * 3),
+    "wm_ss2d_core_bwd": (c_int, [c_void_p] * 14 + [c_size_t] + [c_int64] * 3 + [c_void_p]),
     "wm_layernorm2d_fwd": (c_int, [c_void_p] * 3 + [c_float, c_void_p] + [c_int64] * 4 + [c_void_p]),
     "wm_pw_dw_fwd": (c_int, [c_void_p] * 3 + [c_float] + [c_void_p] * 4 + [c_int, c_void_p] + [c_int64] * 5 + [c_void_p]),
     "wm_dw_act_pw_fwd": (c_int, [c_void_p] * 5 + [c_int] + [c_void_p] * 2 + [c_int64] * 4 + [c_void_p]),
@@ -37,6 +39,7 @@ SIGNATURES = {
                               c_int64, c_int64, c_void_p]),
     "wm_conv3x3_packed_bytes": (c_size_t, [c_int64, c_int64, c_int]),
     "wm_conv3x3_debug_timing": (c_int, [c_void_p]),
+    "wm_debug_pipeline_error": (c_int, [c_void_p]),
     "wm_conv3x3_prepack": (c_int, [c_void_p] * 3 + [c_int64] * 2 + [c_void_p]),
     "wm_conv3x3_fwd": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64] + [c_void_p] * 5 +
                        [c_int64] * 5 + [c_void_p]),

@@ -31,7 +31,41 @@ int sm_count()
     return cached_sms;
 }
 
+// One 32-bit word per device in which the mbarrier pipelines (conv3x3_tc5.cu, pw_dw_tc5.cu) record a
+// wait that timed out; zero-initialised, allocated on first use, never freed.
+unsigned int *pipeline_err_word()
+{
+    static thread_local int cached_dev = -1;
+    static thread_local unsigned int *cached = nullptr;
+    static unsigned int *per_dev[64] = {nullptr};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (dev == cached_dev) return cached;
+    if (per_dev[dev] == nullptr) {
+        unsigned int *p = nullptr;
+        if (cudaMalloc(&p, 16) != cudaSuccess || cudaMemset(p, 0, 16) != cudaSuccess) return nullptr;
+        per_dev[dev] = p;
+    }
+    cached_dev = dev;
+    cached = per_dev[dev];
+    return cached;
+}
+
 }  // namespace wm
+
+/* Developer aid: synchronises the device and returns (and clears) the pipeline error word:
+ * 0 = every mbarrier wait of the tcgen05 kernels completed; otherwise
+ * 0x80000000 | role << 24 | barrier << 16 | iteration of the first wait that timed out. */
+extern "C" int wm_debug_pipeline_error(unsigned int *out)
+{
+    if (out == nullptr) return WM_EINVAL;
+    unsigned int *w = wm::pipeline_err_word();
+    if (w == nullptr) { wm::set_error("wm_debug_pipeline_error: no device"); return WM_ENODEVICE; }
+    WM_CUDA_OK(cudaDeviceSynchronize());
+    WM_CUDA_OK(cudaMemcpy(out, w, 4, cudaMemcpyDeviceToHost));
+    WM_CUDA_OK(cudaMemset(w, 0, 4));
+    return WM_OK;
+}
 
 extern "C" int wm_abi_version(void) { return WM_ABI_VERSION; }
 

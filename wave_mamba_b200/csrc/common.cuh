@@ -43,6 +43,8 @@ inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 // Number of SMs of the current device (cached per process; B200 = 148).
 int sm_count();
+// Device word in which the mbarrier pipelines record a timed-out wait (abi.cu).
+unsigned int *pipeline_err_word();
 
 // ---- device-side load/store helpers -------------------------------------------------
 // Streaming 128-bit load: read-only path, do not allocate in L1 (data is touched once).

@@ -71,6 +71,7 @@ struct Args {
     // channel-quad layouts (B, C/4, h, w, 4): one 16-byte access moves the 4 channels of a K chunk.
     // in_c4 needs Ca == CIN (no second input); used between PAConv.k3 and k4.
     int in_c4, out_c4;
+    unsigned int *err;       // pipeline error word (mbar_wait_flag)
 };
 
 template <int CIN, int COUT, bool GATE>
@@ -220,7 +221,7 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
                     }
                 }
                 // the loads above are in flight while we wait for the slab to be released
-                mbar_wait(xempty(slot), ((unit >> 1) & 1u) ^ 1u);
+                mbar_wait_flag(xempty(slot), ((unit >> 1) & 1u) ^ 1u, a.err, (1u << 24) | (1u << 16) | (unit & 0xffffu));
                 float4 *dhi = xhi + slot * kSlabF4, *dlo = xlo + slot * kSlabF4;
 #pragma unroll
                 for (int r = 0; r < 18; ++r) {
@@ -254,7 +255,7 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
                     for (int ti = 0; ti < NTAPS; ++ti, ++cnt) {
                         const int tap = ti + rot < NTAPS ? ti + rot : ti + rot - NTAPS;
                         const int st = cnt % kStages;
-                        mbar_wait(wempty(st), ((cnt / kStages) & 1u) ^ 1u);
+                        mbar_wait_flag(wempty(st), ((cnt / kStages) & 1u) ^ 1u, a.err, (4u << 24) | (2u << 16) | (cnt & 0xffffu));
                         mbar_expect_tx(wfull(st), (uint32_t)C::kChunkBytes);
                         bulk_g2s(smem_u32(wbuf + st * C::kChunkF4),
                                  a.packed + (int64_t)(tap * NCH + part) * C::kChunkF4,
@@ -287,21 +288,21 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
 #pragma unroll 1
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
                 const int buf = tcount % NACC;
-                mbar_wait(accempty(buf), ((tcount / NACC) & 1u) ^ 1u);
+                mbar_wait_flag(accempty(buf), ((tcount / NACC) & 1u) ^ 1u, a.err, (2u << 24) | (4u << 16) | (tcount & 0xffffu));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 WM_TICK(3);
                 const uint32_t dbase = tmem_base + (uint32_t)(buf * C::kColsBuf);
 #pragma unroll 1
                 for (int part = 0; part < NCH; ++part, ++unit) {
                     const int slot = unit & 1;
-                    mbar_wait(xfull(slot), (unit >> 1) & 1u);
+                    mbar_wait_flag(xfull(slot), (unit >> 1) & 1u, a.err, (2u << 24) | (1u << 16) | (unit & 0xffffu));
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     WM_TICK(2);
 #pragma unroll 1
                     for (int ti = 0; ti < NTAPS; ++ti, ++cnt) {
                         const int tap = ti + rot < NTAPS ? ti + rot : ti + rot - NTAPS;
                         const int st = cnt % kStages;
-                        mbar_wait(wfull(st), (cnt / kStages) & 1u);
+                        mbar_wait_flag(wfull(st), (cnt / kStages) & 1u, a.err, (2u << 24) | (2u << 16) | (cnt & 0xffffu));
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         WM_TICK(1);
                         const bool gate_tap = GATE && tap == 9;
@@ -358,7 +359,7 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
             const int py = q / kHW, px = q - py * kHW;
             const int gy = ty0 + py - 1, gx = tx0 + px - 1;
             const bool ok = px >= 1 && px <= kTW && py <= kR && gy < h && gx < w;
-            mbar_wait(accfull(buf), (tcount / NACC) & 1u);
+            mbar_wait_flag(accfull(buf), (tcount / NACC) & 1u, a.err, (3u << 24) | (3u << 16) | (tcount & 0xffffu));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
                                        (uint32_t)(buf * C::kColsBuf + mt * 2 * COUT);
@@ -532,6 +533,8 @@ extern "C" int wm_conv3x3_ex_fwd(const float *in_a, int64_t a_bstride, int64_t C
     Args a;
     a.in_c4 = in_c4; a.out_c4 = out_c4;
     a.dbg = g_dbg.load();
+    a.err = pipeline_err_word();
+    WM_REQUIRE(a.err != nullptr, "wm_conv3x3_fwd: no CUDA device");
     a.in_a = in_a; a.a_bstride = a_bstride; a.Ca = (int)Ca; a.in_b = in_b; a.b_bstride = b_bstride;
     a.chan_map = chan_map; a.packed = static_cast<const float4 *>(packed); a.bias = bias;
     a.gate_bias = gate_bias; a.out = out; a.h = (int)h; a.w = (int)w;

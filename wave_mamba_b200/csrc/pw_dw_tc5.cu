@@ -58,6 +58,7 @@ struct Args {
     const float *pw_w, *pw_b, *dw_w, *dw_b;
     float *y;
     int h, w, tiles_x, tiles_y, total_tiles;
+    unsigned int *err;     // pipeline error word (mbar_wait_flag)
 };
 
 __device__ __forceinline__ void tma_load_box(uint32_t dst, const CUtensorMap *tmap, int c0, int c1, int c2,
@@ -183,8 +184,8 @@ pw_dw_tc5_kernel(const __grid_constant__ CUtensorMap tmap, const Args a)
         uint32_t it = 0;
 #pragma unroll 1
         for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
-            mbar_wait(xraw_full, it & 1u);
-            mbar_wait(xk_empty, (it & 1u) ^ 1u);       // the previous tile's MMAs have read xhi/xlo
+            mbar_wait_flag(xraw_full, it & 1u, a.err, (1u << 24) | (0u << 16) | (it & 0xffffu));
+            mbar_wait_flag(xk_empty, (it & 1u) ^ 1u, a.err, (1u << 24) | (2u << 16) | (it & 0xffffu));       // the previous tile's MMAs have read xhi/xlo
 #pragma unroll 1
             for (int pos = tid; pos < kPos; pos += kThreadsA) {
                 float v[kCin];
@@ -228,12 +229,12 @@ pw_dw_tc5_kernel(const __grid_constant__ CUtensorMap tmap, const Args a)
             uint32_t it = 0, gcount = 0;
 #pragma unroll 1
             for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
-                mbar_wait(xk_full, it & 1u);
+                mbar_wait_flag(xk_full, it & 1u, a.err, (2u << 24) | (1u << 16) | (it & 0xffffu));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
                 for (int g = 0; g < G; ++g, ++gcount) {
                     const int buf = gcount & 1;
-                    mbar_wait(acc_empty(buf), ((gcount >> 1) & 1u) ^ 1u);
+                    mbar_wait_flag(acc_empty(buf), ((gcount >> 1) & 1u) ^ 1u, a.err, (2u << 24) | (4u << 16) | (gcount & 0xffffu));
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
                     for (int mt = 0; mt < 3; ++mt) {
@@ -265,7 +266,7 @@ pw_dw_tc5_kernel(const __grid_constant__ CUtensorMap tmap, const Args a)
 #pragma unroll 1
             for (int g = 0; g < G; ++g, ++gcount) {
                 const int buf = gcount & 1;
-                mbar_wait(acc_full(buf), (gcount >> 1) & 1u);
+                mbar_wait_flag(acc_full(buf), (gcount >> 1) & 1u, a.err, (3u << 24) | (3u << 16) | (gcount & 0xffffu));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
                 for (int mt = 0; mt < 3; ++mt) {
@@ -420,6 +421,8 @@ int forward(const float *x, const float *ln_w, const float *ln_b, float eps, con
     const int64_t total = (int64_t)a.tiles_x * a.tiles_y * B;
     if (total >= ((int64_t)1 << 31)) return 1;
     a.total_tiles = (int)total;
+    a.err = pipeline_err_word();
+    if (a.err == nullptr) return 1;
     const bool ln = ln_w != nullptr, silu = act == 1;
 #define WM_PWDW_CASE(C)                                                                  \
     if (Cout == C) {                                                                     \

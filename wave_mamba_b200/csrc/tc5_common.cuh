@@ -65,6 +65,28 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity)
     }
     __trap();
 }
+// Debuggable variant for pipeline bring-up: instead of trapping, a wait that times out records
+// `code` (role << 24 | barrier << 16 | iteration) in the global word `err` (first failure wins) and
+// returns, so the kernel terminates and the host can report WHICH wait never completed
+// (wm_debug_pipeline_error).  Once the word is set every later wait gives up after 1024 probes.
+__device__ __forceinline__ void mbar_wait_flag(uint32_t mbar, uint32_t parity, unsigned int *err,
+                                               unsigned int code)
+{
+    uint32_t ok = 0;
+#pragma unroll 1
+    for (int spin = 0; spin < (1 << 20); ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(ok)
+            : "r"(mbar), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if ((spin & 1023) == 1023 && *reinterpret_cast<volatile unsigned int *>(err) != 0u) return;
+    }
+    atomicCAS(err, 0u, code | 0x80000000u);
+}
 // tcgen05.commit: the mbarrier gets one arrival when every MMA issued so far by this thread is done
 __device__ __forceinline__ void mma_commit(uint32_t mbar)
 {

@@ -121,6 +121,44 @@ def ss2d_core(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds) -> t
     return y
 
 
+def ss2d_core_bwd(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, grad_y):
+    """Backward of ``ss2d_core`` (training; the reference gets it from autograd through
+    selective_scan_fn and the einsums, :446-478,490).  Returns (grad_x, grad_x_proj_weight,
+    grad_dt_projs_weight, grad_dt_projs_bias, grad_A_logs, grad_Ds)."""
+    _chk(x, "x")
+    B, D, h, w = x.shape
+    if D != 64:
+        raise ValueError(f"ss2d_core_bwd supports d_inner=64; got {D}")
+    _chk(grad_y, "grad_y", (B, D, h, w))
+    _chk(x_proj_weight, "x_proj_weight", (4, 34, 64))
+    _chk(dt_projs_weight, "dt_projs_weight", (4, 64, 2))
+    _chk(dt_projs_bias, "dt_projs_bias", (4, 64))
+    _chk(A_logs, "A_logs", (256, 16))
+    _chk(Ds, "Ds", (256,))
+    lib = _cabi.load()
+    gx = torch.empty_like(x)
+    grads = [torch.empty_like(t) for t in (x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds)]
+    with torch.cuda.device(x.device):
+        nbytes = lib.wm_ss2d_core_bwd_workspace_bytes(B, h, w)
+        ws = torch.empty(max(nbytes, 256), device=x.device, dtype=torch.uint8)
+        rc = lib.wm_ss2d_core_bwd(x.data_ptr(), x_proj_weight.data_ptr(), dt_projs_weight.data_ptr(),
+                                  dt_projs_bias.data_ptr(), A_logs.data_ptr(), Ds.data_ptr(),
+                                  grad_y.data_ptr(), gx.data_ptr(), *[t.data_ptr() for t in grads],
+                                  ws.data_ptr(), nbytes, B, h, w, _stream(x))
+    _cabi.check(rc, "wm_ss2d_core_bwd")
+    _count(16)
+    return (gx, *grads)
+
+
+def pipeline_error() -> int:
+    """Developer aid: 0 when every mbarrier wait of the tcgen05 pipelines completed since the last
+    call, else the code of the first wait that timed out (synchronises the device)."""
+    import ctypes
+    out = ctypes.c_uint(0)
+    _cabi.check(_cabi.load().wm_debug_pipeline_error(ctypes.byref(out)), "wm_debug_pipeline_error")
+    return int(out.value)
+
+
 def ss2d_dirs(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds) -> torch.Tensor:
     """Un-merged SS2D core: returns the four direction outputs as a (4,B,64,h,w) view of the
     workspace (pixel order).  The reference sum y1+y2+y3+y4 is ((p[0]+p[2])+p[1])+p[3]."""
