@@ -233,6 +233,23 @@ int wm_skff_fwd(const float *f0, const float *f1, const float *f2, const float *
 int wm_ps_down_fwd(const float *x, const float *weight, const float *bias, float *y, int64_t B,
                    int64_t H, int64_t W, int r, wm_stream_t stream);
 
+/* ---- training-only kernels (reference training step femasr_model.py:157-185) ---------
+ * The backward pass is built from forward kernels with transposed weights, Gram matrices for the
+ * weight gradients (wm_gram32_fwd), the Haar adjoints, wm_ss2d_core_bwd, and these three. */
+/* Depthwise 3x3, zero pad 1, any C; wgt (C,9); bias may be NULL.  flip != 0: taps rotated by 180
+ * degrees (the data gradient of the same convolution). */
+int wm_dw3x3_fwd(const float *x, const float *wgt, const float *bias, float *y, int64_t B, int64_t C,
+                 int64_t h, int64_t w, int flip, wm_stream_t stream);
+/* Scratch for wm_dw3x3_wgrad / wm_layernorm2d_bwd (16-byte aligned). */
+size_t wm_train_workspace_bytes(int64_t B, int64_t C, int64_t h, int64_t w);
+/* dwgt[c][t] = sum dy[b,c,p] x[b,c,p+t], dbias[c] = sum dy (dbias may be NULL). Deterministic. */
+int wm_dw3x3_wgrad(const float *dy, const float *x, float *dwgt, float *dbias, void *workspace,
+                   size_t workspace_bytes, int64_t B, int64_t C, int64_t h, int64_t w, wm_stream_t stream);
+/* Backward of wm_layernorm2d_fwd (C = 32 or 64): dx, dln_w, dln_b.  Deterministic. */
+int wm_layernorm2d_bwd(const float *x, const float *ln_w, const float *dy, float eps, float *dx,
+                       float *dln_w, float *dln_b, void *workspace, size_t workspace_bytes, int64_t B,
+                       int64_t C, int64_t h, int64_t w, wm_stream_t stream);
+
 /* ---- image I/O edges of the inference loop -- img2tensor + "/255." + check_image_size
  *      (basicsr/utils/img_util.py:9-33, inference_wavemamba.py:28-36,102-106) and the crop +
  *      tensor2img on the way out (inference_wavemamba.py:112-113, img_util.py:36-98) -----------

@@ -51,6 +51,10 @@ SIGNATURES = {
     "wm_skff_workspace_bytes": (c_size_t, [c_int64] * 3),
     "wm_skff_fwd": (c_int, [c_void_p] * 10 + [c_size_t] + [c_int64] * 4 + [c_void_p]),
     "wm_ps_down_fwd": (c_int, [c_void_p] * 4 + [c_int64] * 3 + [c_int, c_void_p]),
+    "wm_dw3x3_fwd": (c_int, [c_void_p] * 4 + [c_int64] * 4 + [c_int, c_void_p]),
+    "wm_train_workspace_bytes": (c_size_t, [c_int64] * 4),
+    "wm_dw3x3_wgrad": (c_int, [c_void_p] * 5 + [c_size_t] + [c_int64] * 4 + [c_void_p]),
+    "wm_layernorm2d_bwd": (c_int, [c_void_p] * 3 + [c_float] + [c_void_p] * 4 + [c_size_t] + [c_int64] * 4 + [c_void_p]),
     "wm_img_u8_to_f32_fwd": (c_int, [c_void_p] * 2 + [c_int64] * 5 + [c_int, c_void_p]),
     "wm_img_f32_to_u8_fwd": (c_int, [c_void_p] * 2 + [c_int64] * 5 + [c_void_p]),
 }

@@ -89,7 +89,7 @@ struct Cfg {
     static constexpr int kNumBars = 2 * kStages + 4 + 2 * NACC;
     static constexpr size_t kSmem = sizeof(float4) * (size_t)(4 * kSlabF4 + kStages * kChunkF4) +
                                     8 * kNumBars + 16;
-    static_assert(CIN == 32 || CIN == 64, "CIN must be 32 or 64");
+    static_assert(CIN == 32 || CIN == 64 || CIN == 96, "CIN must be 32, 64 or 96");
     static_assert(2 * COUT <= 256 && (2 * COUT) % 16 == 0, "merged N must be a legal UMMA N");
     static_assert(kColsNeed <= 512, "accumulators do not fit TMEM");
     static_assert(kSmem <= 232448, "shared memory budget");
@@ -547,6 +547,9 @@ extern "C" int wm_conv3x3_ex_fwd(const float *in_a, int64_t a_bstride, int64_t C
     if (Cin == 64 && Cout == 64) return launch<64, 64, false>(a, B, s);
     if (Cin == 32 && Cout == 96) return launch<32, 96, false>(a, B, s);
     if (Cin == 32 && Cout == 32) return launch<32, 32, false>(a, B, s);
+    // data gradients of the 64->32 and 32->96 convolutions (training path)
+    if (Cin == 32 && Cout == 64) return launch<32, 64, false>(a, B, s);
+    if (Cin == 96 && Cout == 32) return launch<96, 32, false>(a, B, s);
     WM_REQUIRE(false, "wm_conv3x3_fwd: Cin=%lld Cout=%lld unsupported", (long long)Cin, (long long)Cout);
     return WM_EINVAL;
 }

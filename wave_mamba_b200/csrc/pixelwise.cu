@@ -568,6 +568,9 @@ extern "C" int wm_pw_fwd(const float *x, int64_t x_bstride, const float *pw_w, i
     if (gate_mode == 0 && Cin == 32 && Cout == 64) return launch<32, 64, kPreNone, kPostNone>(a, B, s, "pw 32->64");
     if (gate_mode == 0 && Cin == 64 && Cout == 32) return launch<64, 32, kPreNone, kPostNone>(a, B, s, "pw 64->32");
     if (gate_mode == 1 && Cin == 32 && Cout == 32) return launch<32, 32, kPreGate, kPostNone>(a, B, s, "pw gate 32->32");
+    // training-path shapes: qkv 32->96 (:762), PAConv k2 64->64 (:687) and their transposes
+    if (gate_mode == 0 && Cin == 32 && Cout == 96) return launch<32, 96, kPreNone, kPostNone>(a, B, s, "pw 32->96");
+    if (gate_mode == 0 && Cin == 64 && Cout == 64) return launch<64, 64, kPreNone, kPostNone>(a, B, s, "pw 64->64");
     WM_REQUIRE(false, "wm_pw_fwd: Cin=%lld Cout=%lld gate_mode=%d unsupported", (long long)Cin,
                (long long)Cout, gate_mode);
     return WM_EINVAL;

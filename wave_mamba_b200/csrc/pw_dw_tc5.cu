@@ -174,11 +174,12 @@ pw_dw_tc5_kernel(const __grid_constant__ CUtensorMap tmap, const Args a)
 
     if (warp < kWarpsA) {
         // =========================== LayerNorm + operand layout ==============================
+        const CUtensorMap *tmap_ptr = &tmap;      // generic address of the __grid_constant__ parameter
         auto issue_tma = [&](int tile) {
             int tx0, ty0, b;
             tile_coords(tile, tx0, ty0, b);
             mbar_expect_tx(xraw_full, kBoxBytes);
-            tma_load_box(smem_u32(xraw), &tmap, tx0 - 1, ty0 - 1, 0, b, xraw_full);
+            tma_load_box(smem_u32(xraw), tmap_ptr, tx0 - 1, ty0 - 1, 0, b, xraw_full);
         };
         if (tid == 0 && (int)blockIdx.x < a.total_tiles) issue_tma(blockIdx.x);
         uint32_t it = 0;

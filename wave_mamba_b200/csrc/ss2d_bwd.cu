@@ -138,13 +138,33 @@ __device__ __forceinline__ void run_bwd_cta(const BwdParams &prm, const Geom &g,
     const float *hck = MODE == 1 ? prm.hbuf + (((int64_t)b * nch + my_chunk) * dir_chunk_len(g, k)) * kChains + chain0
                                  : nullptr;
 
-    float q[2][8], dA[2][8];
-    float dDacc = 0.0f;
+    float q[2][8];
+    double dA[2][8];     // sums over every step of the chunk: fp64 (long sums with cancellation)
+    double dDacc = 0.0;
     double sum_dt[2] = {0.0, 0.0};
 #pragma unroll
     for (int c = 0; c < 2; ++c)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { q[c][j] = 0.0f; dA[c][j] = 0.0f; }
+        for (int j = 0; j < 8; ++j) { q[c][j] = 0.0f; dA[c][j] = 0.0; }
+    // state after step t of my chunk (checkpoint row t); t = -1: the chunk's true initial state
+    const float *h_init = prm.aggH + (((int64_t)b * kK + k) * g.max_chunks + my_chunk) * kChains + chain0;
+    auto load_state = [&](int t, float (&dst)[2][8]) {
+        if (t < 0 && my_chunk == 0) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dst[c][j] = 0.0f;
+            return;
+        }
+        const float *hp = t < 0 ? h_init : hck + (int64_t)t * kChains;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const float4 f0 = *reinterpret_cast<const float4 *>(hp + c * kN);
+            const float4 f1 = *reinterpret_cast<const float4 *>(hp + c * kN + 4);
+            dst[c][0] = f0.x; dst[c][1] = f0.y; dst[c][2] = f0.z; dst[c][3] = f0.w;
+            dst[c][4] = f1.x; dst[c][5] = f1.y; dst[c][6] = f1.z; dst[c][7] = f1.w;
+        }
+    };
     if (MODE == 1 && my_len > 0) {
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
@@ -161,10 +181,10 @@ __device__ __forceinline__ void run_bwd_cta(const BwdParams &prm, const Geom &g,
 
     // dense-phase identity: (position, group of 16 channels / outputs)
     const int dp = tid & 63, grp = tid >> 6;
-    float accw[9];       // d x_proj_weight rows grp, grp+4, ... for input channel dp
+    double accw[9];      // d x_proj_weight rows grp, grp+4, ... for input channel dp (fp32 per tile, fp64 across)
 #pragma unroll
-    for (int i = 0; i < 9; ++i) accw[i] = 0.0f;
-    float acc_misc = 0.0f;   // grp 0: d dt_w[:,0], grp 1: d dt_w[:,1], grp 2: d dt_bias   (channel dp)
+    for (int i = 0; i < 9; ++i) accw[i] = 0.0;
+    double acc_misc = 0.0;   // grp 0: d dt_w[:,0], grp 1: d dt_w[:,1], grp 2: d dt_bias   (channel dp)
 
 #pragma unroll 1
     for (int ti = ntiles - 1; ti >= 0; --ti) {
@@ -204,16 +224,10 @@ __device__ __forceinline__ void run_bwd_cta(const BwdParams &prm, const Geom &g,
         // ---- reverse recurrence over the valid steps of this tile --------------------------------
         {
             const int nvalid = min(my_len - ti * kTP, kTP);       // warp-uniform
-            float hn[2][8];
+            float hcur[2][8], hprev[2][8];     // states after steps t and t-1 of the step being processed
             if (MODE == 1 && nvalid > 0) {
-                const float *hp = hck + (int64_t)(ti * kTP + nvalid - 1) * kChains;
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const float4 f0 = *reinterpret_cast<const float4 *>(hp + c * kN);
-                    const float4 f1 = *reinterpret_cast<const float4 *>(hp + c * kN + 4);
-                    hn[c][0] = f0.x; hn[c][1] = f0.y; hn[c][2] = f0.z; hn[c][3] = f0.w;
-                    hn[c][4] = f1.x; hn[c][5] = f1.y; hn[c][6] = f1.z; hn[c][7] = f1.w;
-                }
+                load_state(ti * kTP + nvalid - 1, hcur);
+                load_state(ti * kTP + nvalid - 2, hprev);
             }
 #pragma unroll 1
             for (int e = nvalid - 1; e >= 0; --e) {
@@ -247,21 +261,8 @@ __device__ __forceinline__ void run_bwd_cta(const BwdParams &prm, const Geom &g,
                     Bv[0] = b0.x; Bv[1] = b0.y; Bv[2] = b0.z; Bv[3] = b0.w;
                     Bv[4] = b1.x; Bv[5] = b1.y; Bv[6] = b1.z; Bv[7] = b1.w;
                 }
-                float h[2][8];
-#pragma unroll
-                for (int c = 0; c < 2; ++c)
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) h[c][j] = hn[c][j];
-                if (e > 0) {                    // prefetch the state of the next (earlier) step
-                    const float *hp = hck + (int64_t)(ti * kTP + e - 1) * kChains;
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        const float4 f0 = *reinterpret_cast<const float4 *>(hp + c * kN);
-                        const float4 f1 = *reinterpret_cast<const float4 *>(hp + c * kN + 4);
-                        hn[c][0] = f0.x; hn[c][1] = f0.y; hn[c][2] = f0.z; hn[c][3] = f0.w;
-                        hn[c][4] = f1.x; hn[c][5] = f1.y; hn[c][6] = f1.z; hn[c][7] = f1.w;
-                    }
-                }
+                float hpp[2][8];                // prefetch: the state two steps back (next step's hprev)
+                if (e > 0) load_state(ti * kTP + e - 2, hpp);
                 float v[16];                    // dB[0..7] | dC[0..7] partial sums over my 2 channels
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = 0.0f;
@@ -274,13 +275,13 @@ __device__ __forceinline__ void run_bwd_cta(const BwdParams &prm, const Geom &g,
                     for (int j = 0; j < 8; ++j) {
                         const float a = ex2_approx(dtv[c] * A2[c][j]);
                         const float gq = fmaf(Cv[j], gyv[c], q[c][j]);                 // g_l
-                        const float hm = fmaf(-dtu, Bv[j], h[c][j]);                   // a_l h_{l-1}
+                        const float hm = a * hprev[c][j];                              // a_l h_{l-1}
                         const float An = A2[c][j] * 0.6931471805599453f;               // A
                         s_dt = fmaf(gq, fmaf(An, hm, uv[c] * Bv[j]), s_dt);
                         s_du = fmaf(gq, Bv[j], s_du);
-                        dA[c][j] = fmaf(gq * dtv[c], hm, dA[c][j]);
+                        dA[c][j] += (double)(gq * dtv[c]) * (double)hm;
                         v[j] = fmaf(gq, dtu, v[j]);
-                        v[8 + j] = fmaf(gyv[c], h[c][j], v[8 + j]);
+                        v[8 + j] = fmaf(gyv[c], hcur[c][j], v[8 + j]);
                         q[c][j] = a * gq;
                     }
                     sdt[c] = s_dt;
@@ -297,7 +298,7 @@ __device__ __forceinline__ void run_bwd_cta(const BwdParams &prm, const Geom &g,
                     ddt[p * kDT + d] = c ? sdt[1] : sdt[0];
                     const float gyc = c ? gyv[1] : gyv[0], uc = c ? uv[1] : uv[0];
                     dus[p * kDT + d] = fmaf(cst[3 * kD + d], gyc, c ? sdu[1] : sdu[0]);
-                    dDacc = fmaf(gyc, uc, dDacc);
+                    dDacc += (double)gyc * (double)uc;
                 }
                 // dB / dC: reduce-scatter over the 16 channel-pair lanes of this warp with my state half
                 // (lane bits 1..4): 8 + 4 + 2 + 1 shuffles, every lane ends with one finished value
@@ -335,6 +336,10 @@ __device__ __forceinline__ void run_bwd_cta(const BwdParams &prm, const Geom &g,
                 // idx < 8: dB[hoff + idx], else dC[hoff + idx - 8]; the strand's other warp adds the
                 // other 16 channel pairs (two addends on a zeroed cell: order-independent)
                 atomicAdd(dpj + p * kPJ + (idx < 8 ? hoff + idx : 16 + hoff + (idx - 8)), w1);
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { hcur[c][j] = hprev[c][j]; hprev[c][j] = hpp[c][j]; }
             }
         }
         if (MODE == 0) continue;
@@ -381,6 +386,9 @@ __device__ __forceinline__ void run_bwd_cta(const BwdParams &prm, const Geom &g,
         }
         {
             // thread = (input channel dp, output rows grp, grp+4, ...): sums over the 64 positions
+            float tw[9], tm = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) tw[i] = 0.0f;
 #pragma unroll 1
             for (int p = 0; p < kPos; ++p) {
                 const float xv = xs[dp * kXS + p];
@@ -388,13 +396,16 @@ __device__ __forceinline__ void run_bwd_cta(const BwdParams &prm, const Geom &g,
 #pragma unroll
                 for (int i = 0; i < 9; ++i) {
                     const int o = grp + 4 * i;
-                    if (o < kProj) accw[i] = fmaf(dr[pj_col(o)], xv, accw[i]);
+                    if (o < kProj) tw[i] = fmaf(dr[pj_col(o)], xv, tw[i]);
                 }
                 const float dpre = ddt[p * kDT + dp];
-                if (grp == 0) acc_misc = fmaf(dpre, pj[p * kPJ + 32], acc_misc);
-                else if (grp == 1) acc_misc = fmaf(dpre, pj[p * kPJ + 33], acc_misc);
-                else if (grp == 2) acc_misc += dpre;
+                if (grp == 0) tm = fmaf(dpre, pj[p * kPJ + 32], tm);
+                else if (grp == 1) tm = fmaf(dpre, pj[p * kPJ + 33], tm);
+                else if (grp == 2) tm += dpre;
             }
+#pragma unroll
+            for (int i = 0; i < 9; ++i) accw[i] += (double)tw[i];
+            acc_misc += (double)tm;
         }
         __syncthreads();
         store_tile_acc(g, tg, cmg, ti, prm.dx + (int64_t)b * kD * g.L, gs, prm.accumulate != 0);
@@ -427,9 +438,9 @@ __device__ __forceinline__ void run_bwd_cta(const BwdParams &prm, const Geom &g,
 #pragma unroll
             for (int j = 0; j < 8; ++j)
                 stage[s * (kChains + kD) + (2 * cp + c) * kN + hoff + j] =
-                    dA[c][j] * (A2[c][j] * 0.6931471805599453f);               // d A_log = dA * A
+                    (float)(dA[c][j] * (double)(A2[c][j] * 0.6931471805599453f));   // d A_log = dA * A
         // lane `half` accumulated dD of channel 2cp+half
-        stage[s * (kChains + kD) + kChains + 2 * cp + half] = dDacc;
+        stage[s * (kChains + kD) + kChains + 2 * cp + half] = (float)dDacc;
     }
     __syncthreads();
     float *part = prm.part + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * kPart;
@@ -440,11 +451,11 @@ __device__ __forceinline__ void run_bwd_cta(const BwdParams &prm, const Geom &g,
 #pragma unroll
     for (int i = 0; i < 9; ++i) {
         const int o = grp + 4 * i;
-        if (o < kProj) part[kP_Wx + o * kD + dp] = accw[i];
+        if (o < kProj) part[kP_Wx + o * kD + dp] = (float)accw[i];
     }
-    if (grp == 0) part[kP_Wdt + dp * 2 + 0] = acc_misc;
-    else if (grp == 1) part[kP_Wdt + dp * 2 + 1] = acc_misc;
-    else if (grp == 2) part[kP_Bias + dp] = acc_misc;
+    if (grp == 0) part[kP_Wdt + dp * 2 + 0] = (float)acc_misc;
+    else if (grp == 1) part[kP_Wdt + dp * 2 + 1] = (float)acc_misc;
+    else if (grp == 2) part[kP_Bias + dp] = (float)acc_misc;
 }
 
 template <int MODE>
