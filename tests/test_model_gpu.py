@@ -81,9 +81,9 @@ def test_registry_class_api(dev, params_cache):
     assert padded.shape[2] % 8 == 0 and padded.shape[3] % 8 == 0
     with pytest.raises(ValueError):
         net.restoration_network(torch.rand(1, 3, 60, 64, device=dev))
-    net.train()
-    with pytest.raises(NotImplementedError):
-        net(xd)
+    net.train()                      # grad mode + trainable parameters: the differentiable path
+    d = net(xd)
+    assert d.requires_grad and (d - a).abs().max().item() <= 2e-5
 
 
 class _Sink(dict):

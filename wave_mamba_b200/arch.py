@@ -8,12 +8,17 @@ Drop-in contract (reference basicsr/archs/wavemamba_arch.p
     checkpoints load with ``strict=True``.
 
 Module classes below are parameter containers whose names reproduce that key schema; their
-forwards call ``wave_mamba_b200.ops`` (hand-written CUDA through the C ABI) for the hot path
--- Haar DWT/IWT, the SS2D core, the HFEBlock / ffn pointwise + depthwise groups -- and library
-ops (cuDNN / cuBLAS through torch) for what SURVEY.md section 8f schedules as "next": the
-dense 3x3 convolutions, channel matching, the CxC attention and SKFF.
+forwards call ``wave_mamba_b200.ops`` (hand-written CUDA through the C ABI) for everything that
+touches a feature map: Haar DWT/IWT, the SS2D core, the pointwise + depthwise groups, the dense
+3x3 convolutions (tcgen05), channel matching / CxC attention (Gram kernel), SKFF, the stem / head
+convolutions.  Only 32x32-element bookkeeping (argmin, softmax, folding the attention into the
+1x1 weights) is left to torch.
 
-Inference only in this round: running with autograd enabled raises (no backward kernels yet).
+Two paths share the parameters:
+  * inference (``torch.no_grad()`` / ``.eval()`` without grad): the fused kernels;
+  * training (grad enabled): an unfused composition of ``wave_mamba_b200.autograd`` Functions --
+    every convolution, LayerNorm, the wavelets and the SS2D core run this repo's CUDA kernels in
+    both directions; pointwise glue is torch elementwise autograd.
 There is no CPU path: tensors that are not on a CUDA device raise.
 """
 from __future__ import annotations
@@ -25,6 +30,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import autograd as ag
 from . import ops
 from ._cabi import WaveMambaNativeError
 
@@ -32,15 +38,17 @@ __all__ = ["WaveMamba", "UNet", "DownFRG", "upFRG", "LFSSBlock", "SS2D", "HFEBlo
            "DWT", "IWT"]
 
 
-def _require_inference(module: nn.Module, t: torch.Tensor) -> None:
+def _require_cuda(t: torch.Tensor) -> None:
     if not t.is_cuda:
         raise WaveMambaNativeError(
             f"input is on {t.device}: the B200 Wave-Mamba path has no CPU fallback; move the "
             "module and its input to a CUDA device")
-    if torch.is_grad_enabled() and (module.training or t.requires_grad):
-        raise NotImplementedError(
-            "wave_mamba_b200 implements the forward (inference) path only; backward kernels for "
-            "DWT/IWT/SS2D are scheduled next (SURVEY.md 8f-3). Use .eval() / torch.no_grad().")
+
+
+def _wants_grad(module: nn.Module, t: torch.Tensor) -> bool:
+    """The differentiable (training) path is taken whenever autograd could record something: grad mode
+    on and either the input or any parameter of the network requires a gradient."""
+    return torch.is_grad_enabled() and (t.requires_grad or any(p.requires_grad for p in module.parameters()))
 
 
 # --------------------------------------------------------------------------------------
@@ -108,6 +116,13 @@ class _FFN(nn.Module):
         self.conv2 = nn.Conv2d(mid, mid, 3, padding=1, groups=mid)
         self.conv3 = nn.Conv2d(mid // 2, num_feat, 1)
 
+    def forward_train(self, x):
+        """reference ffn.forward (:225-230), differentiable."""
+        t = ag.PW.apply(x, self.conv1.weight, self.conv1.bias)
+        t = ag.DW.apply(t, self.conv2.weight, self.conv2.bias)
+        x1, x2 = t.chunk(2, dim=1)
+        return ag.PW.apply(F.gelu(x1) * x2, self.conv3.weight, self.conv3.bias)
+
     def forward(self, x, ln_w=None, ln_b=None, eps=1e-5, residual=None, res_scale=None):
         """ln?(x) -> conv1 -> conv2 -> gate -> conv3 (+ residual*res_scale), two kernels."""
         t = ops.pw_dw(x, self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias,
@@ -169,6 +184,17 @@ class SS2D(nn.Module):
         return ops.lfss_out(p[0], zs, self.out_norm.weight, self.out_norm.bias, self.out_norm.eps,
                             self.out_proj.weight, x, skip_scale, extra=(p[2], p[1], p[3]))
 
+    def forward_train(self, xn: torch.Tensor) -> torch.Tensor:
+        """SS2D.forward (:480-497) on an already normalised NCHW map, differentiable: in_proj -> dwconv ->
+        SiLU -> core -> out_norm -> * silu(z) -> out_proj."""
+        D = self.d_inner
+        xz = ag.PW.apply(xn, self.in_proj.weight[:D], None), ag.PW.apply(xn, self.in_proj.weight[D:], None)
+        xc = F.silu(ag.DW.apply(xz[0], self.conv2d.weight, self.conv2d.bias))
+        y = ag.SS2DCore.apply(xc, self.x_proj_weight, self.dt_projs_weight, self.dt_projs_bias,
+                              self.A_logs, self.Ds)
+        y = ag.LN2d.apply(y, self.out_norm.weight, self.out_norm.bias, self.out_norm.eps)
+        return ag.PW.apply(y * F.silu(xz[1]), self.out_proj.weight, None)
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """Reference calling convention: x (B,h,w,C) channels-last -> (B,h,w,C) (:480-497)."""
         # The fused kernels take the LayerNorm with them, so this un-normalised entry point runs
@@ -195,8 +221,19 @@ class LFSSBlock(nn.Module):
         self.ln_2 = nn.LayerNorm(hidden_dim)
         self.skip_scale2 = nn.Parameter(torch.ones(hidden_dim))
 
+    def forward_train(self, x: torch.Tensor) -> torch.Tensor:
+        """LFSSBlock.forward (:520-528) on NCHW, differentiable."""
+        s1 = self.skip_scale.view(1, -1, 1, 1)
+        s2 = self.skip_scale2.view(1, -1, 1, 1)
+        x = x * s1 + self.self_attention.forward_train(
+            ag.LN2d.apply(x, self.ln_1.weight, self.ln_1.bias, self.ln_1.eps))
+        return x * s2 + self.conv_blk.forward_train(
+            ag.LN2d.apply(x, self.ln_2.weight, self.ln_2.bias, self.ln_2.eps))
+
     def forward_nchw(self, x: torch.Tensor) -> torch.Tensor:
         """(B,C,h,w) -> (B,C,h,w); five kernels + the scan, all NCHW."""
+        if _wants_grad(self, x):
+            return self.forward_train(x)
         x = self.self_attention.forward_nchw(x, self.ln_1.weight, self.ln_1.bias, self.ln_1.eps,
                                              self.skip_scale)                       # :524-525
         return self.conv_blk(x, self.ln_2.weight, self.ln_2.bias, self.ln_2.eps,
@@ -220,6 +257,8 @@ class LayerNorm2d(nn.Module):
         self.eps = eps
 
     def forward(self, x):
+        if _wants_grad(self, x):
+            return ag.LN2d.apply(x, self.weight, self.bias, self.eps)
         return ops.layernorm2d(x.contiguous(), self.weight, self.bias, self.eps)
 
 
@@ -231,6 +270,12 @@ class PAConv(nn.Module):
         self.k2 = nn.Conv2d(nf, nf, 1)
         self.k3 = nn.Conv2d(nf, nf, 3, padding=1, bias=False)
         self.k4 = nn.Conv2d(nf, nf // 2, 3, padding=1, bias=False)
+
+    def forward_train(self, x):
+        """PAConv.forward (:692-699) on the concatenated input, differentiable."""
+        y = torch.sigmoid(ag.PW.apply(x, self.k2.weight, self.k2.bias))
+        out = ag.Conv3.apply(x, self.k3.weight, None) * y
+        return ag.Conv3.apply(out, self.k4.weight, None)
 
     def forward(self, x, x_b=None, chan_map=None):
         """x (+ x_b gathered by chan_map) are the 2*dim input channels (the reference's cat)."""
@@ -256,8 +301,14 @@ class Matching_transformation(nn.Module):
         self.last_index = None  # kept for parity tests (argmin indices)
 
     def forward(self, x, perception):
-        idx = nearest_channel_index(x, perception)
+        with torch.no_grad():
+            idx = nearest_channel_index(x.detach().contiguous(), perception.detach().contiguous())
         self.last_index = idx
+        if _wants_grad(self, x) or perception.requires_grad:
+            # the gather and the cat are data movement: torch autograd scatters the gradient back
+            B, C, h, w = perception.shape
+            cand = torch.gather(perception, 1, idx[:, :, None, None].expand(-1, -1, h, w))
+            return self.paconv.forward_train(torch.cat([x, cand], dim=1))
         # cat([x, perception[idx]]) (:716) is expressed as a channel gather inside the conv
         return self.paconv(x, perception, idx.to(torch.int32).contiguous())
 
@@ -270,7 +321,19 @@ class FeedForward(nn.Module):
         self.project_out = nn.Sequential(nn.Conv2d(dim, dim, 3, padding=1, groups=dim), nn.GELU(),
                                          nn.Conv2d(dim, dim, 1))
 
+    def forward_train(self, x, perception, norm: LayerNorm2d, residual):
+        """x + FeedForward(norm2(x), per) (:745-751, :851), differentiable."""
+        pi0, pi1 = self.project_in[0], self.project_in[1]
+        t = ag.PW.apply(norm(x), pi0.weight, pi0.bias)
+        t = ag.DW.apply(t, pi1.weight, pi1.bias)
+        t = self.matching_transformation(t, perception)
+        po0, po2 = self.project_out[0], self.project_out[2]
+        t = F.gelu(ag.DW.apply(t, po0.weight, po0.bias))
+        return residual + ag.PW.apply(t, po2.weight, po2.bias)
+
     def forward(self, x, perception, norm: LayerNorm2d, residual):
+        if _wants_grad(self, x) or perception.requires_grad:
+            return self.forward_train(x, perception, norm, residual)
         pi0, pi1 = self.project_in[0], self.project_in[1]
         t = ops.pw_dw(x, pi0.weight, pi0.bias, pi1.weight, pi1.bias, norm.weight, norm.bias, norm.eps)
         t = self.matching_transformation(t, perception)
@@ -289,7 +352,25 @@ class CMTAttention(nn.Module):
         self.project_out = nn.Conv2d(dim, dim, 1)
         self.matching_transformation = Matching_transformation(dim)
 
+    def forward_train(self, x, perception, norm: LayerNorm2d, residual):
+        """x + CMTAttention(norm1(x), per) (:772-798, :849), differentiable.  Same algebra as the
+        inference path: one Gram matrix + norms instead of the normalised copies, the attention folded
+        into the project_out weights."""
+        B, C, h, w = x.shape
+        qkv = ag.DW.apply(ag.PW.apply(norm(x), self.qkv.weight, self.qkv.bias),
+                          self.qkv_dwconv.weight, self.qkv_dwconv.bias)
+        q, k, v = qkv.chunk(3, dim=1)
+        q = self.matching_transformation(q, perception)
+        gram, nq2, nk2 = ag.Gram32.apply(q, k)
+        nq = nq2.sqrt().clamp_min(1e-12)
+        nk = nk2.sqrt().clamp_min(1e-12)
+        attn = (gram / (nq[:, :, None] * nk[:, None, :]) * self.temperature).softmax(dim=-1)
+        mixed = (self.project_out.weight.view(1, C, C, 1) * attn.unsqueeze(1)).sum(2)
+        return ag.PWPerImage.apply(v, mixed, self.project_out.bias, residual)
+
     def forward(self, x, perception, norm: LayerNorm2d, residual):
+        if _wants_grad(self, x) or perception.requires_grad:
+            return self.forward_train(x, perception, norm, residual)
         B, C, h, w = x.shape
         qkv = ops.pw_dw(x, self.qkv.weight, self.qkv.bias, self.qkv_dwconv.weight,
                         self.qkv_dwconv.bias, norm.weight, norm.bias, norm.eps)
@@ -335,7 +416,21 @@ class SKFF(nn.Module):
         self.conv_du = nn.Sequential(nn.Conv2d(in_channels, d, 1, bias=False), nn.PReLU())
         self.fcs = nn.ModuleList([nn.Conv2d(d, in_channels, 1, bias=False) for _ in range(height)])
 
+    def forward_train(self, feats: List[torch.Tensor]):
+        """SKFF.forward (:939-959), differentiable: three-band sum, global average pool, 32->4->3x32
+        squeeze-excite on (B,32) vectors, softmax over the bands, weighted sum -- all elementwise /
+        reductions (no convolution touches a feature map), left to torch autograd."""
+        B, C = feats[0].shape[:2]
+        stacked = torch.stack(feats, dim=1)
+        pooled = stacked.sum(1).mean(dim=(2, 3))                                    # (B, C)
+        z = F.prelu(pooled @ self.conv_du[0].weight.view(-1, C).t(), self.conv_du[1].weight)
+        att = torch.stack([z @ fc.weight.view(C, -1).t() for fc in self.fcs], dim=1)  # (B, 3, C)
+        att = att.softmax(dim=1)
+        return (stacked * att[:, :, :, None, None]).sum(1)
+
     def forward(self, feats: List[torch.Tensor]):
+        if _wants_grad(self, feats[0]):
+            return self.forward_train(feats)
         return ops.skff(feats[0], feats[1], feats[2], self.conv_du[0].weight, self.conv_du[1].weight,
                         self.fcs[0].weight, self.fcs[1].weight, self.fcs[2].weight)
 
@@ -361,6 +456,14 @@ class DownFRG(nn.Module):
         self.h_blk = nn.Sequential(*[HFEBlock(dim) for _ in range(n_h_blocks)])
 
     def forward(self, x, x_d):
+        if _wants_grad(self, x):
+            ll, hl, lh, hh = _DWTFn.apply(x)
+            low = ag.Conv3.apply(torch.cat([ll, x_d], dim=1), self.l_conv.weight, self.l_conv.bias)
+            low = _run_low(self.l_blk, low)
+            high = self.h_fusion([hl, lh, hh])
+            for blk in self.h_blk:
+                high = blk(high, low)
+            return low, high
         ll, hl, lh, hh = self.dwt(x)
         low = ops.conv3x3(ll, self.l_conv.weight, self.l_conv.bias, x_b=x_d.contiguous())  # cat-free :975
         low = _run_low(self.l_blk, low)
@@ -382,6 +485,9 @@ class upFRG(nn.Module):
         x_l = _run_low(self.l_blk, x_l)
         for blk in self.h_blk:
             x_h = blk(x_h, x_l)
+        if _wants_grad(self, x_h):
+            x_h = ag.Conv3.apply(x_h, self.h_out_conv.weight, self.h_out_conv.bias)
+            return _IWTFn.apply(x_l, x_h)
         x_h = ops.conv3x3(x_h, self.h_out_conv.weight, self.h_out_conv.bias)       # :1005
         return self.iwt(x_l, x_h)  # IWT of cat([x_l, x_h]) without the cat (:1006)
 
@@ -403,12 +509,30 @@ class UNet(nn.Module):
             setattr(self, f"up_group{i + 1}", upFRG(wf, n_l_blocks[i], n_h_blocks[i], ffn_scale))
         self.last = nn.Conv2d(wf, in_chn, 3, 1, 1, bias=True)
 
+    def forward_train(self, x):
+        """UNet.forward (:1041-1063) with autograd: the same graph through wave_mamba_b200.autograd."""
+        x = x.contiguous()
+        side = []
+        for lvl, r in ((1, 2), (2, 4), (3, 8)):
+            conv = getattr(self, f"ps_down{lvl}")[1]
+            side.append(ag.PSDown.apply(x, conv.weight, conv.bias, r))
+        t = ag.StemConv.apply(x, self.conv_01.weight, self.conv_01.bias)
+        low, h1 = self.down_group1(t, side[0])
+        low, h2 = self.down_group2(low, side[1])
+        low, h3 = self.down_group3(low, side[2])
+        low = self.up_group3(low, h3)
+        low = self.up_group2(low, h2)
+        low = self.up_group1(low, h1)
+        return ag.HeadConv.apply(low, self.last.weight, self.last.bias, x)
+
     def forward(self, x):
-        _require_inference(self, x)
+        _require_cuda(x)
         if x.dtype != torch.float32:
             raise TypeError(f"expected a float32 image tensor, got {x.dtype}")
         if x.dim() != 4 or x.shape[2] % 8 or x.shape[3] % 8:
             raise ValueError(f"input must be (B,C,H,W) with H and W multiples of 8, got {tuple(x.shape)}")
+        if _wants_grad(self, x):
+            return self.forward_train(x)
         with torch.no_grad():
             x = x.contiguous()
             side = [ops.ps_down(x, getattr(self, f"ps_down{l}")[1].weight,

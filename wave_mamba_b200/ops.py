@@ -640,3 +640,64 @@ def img_f32_to_u8(x: torch.Tensor, h: Optional[int] = None, w: Optional[int] = N
     if B and h and w:
         _count(1)
     return img
+
+
+# --------------------------------------------------------------------------------------------
+# training-only kernels (csrc/train.cu)
+# --------------------------------------------------------------------------------------------
+def dw3x3(x, weight, bias=None, flip: bool = False) -> torch.Tensor:
+    """Depthwise 3x3, zero pad 1: x (B,C,h,w), weight (C,1,3,3) or (C,9).  ``flip`` rotates the taps by
+    180 degrees (the data gradient of the same convolution)."""
+    _chk(x, "x")
+    B, C, h, w = x.shape
+    weight = _chk(weight.reshape(C, 9), "weight")
+    if bias is not None:
+        _chk(bias, "bias", (C,))
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        rc = _cabi.load().wm_dw3x3_fwd(x.data_ptr(), weight.data_ptr(), _ptr(bias), y.data_ptr(), B, C, h, w,
+                                       1 if flip else 0, _stream(x))
+    _cabi.check(rc, "wm_dw3x3_fwd")
+    _count(1)
+    return y
+
+
+def _train_ws(x: torch.Tensor, C: int):
+    B, _, h, w = x.shape
+    nbytes = _cabi.load().wm_train_workspace_bytes(B, C, h, w)
+    return torch.empty(max(nbytes, 16) // 8 + 1, device=x.device, dtype=torch.float64), nbytes
+
+
+def dw3x3_wgrad(grad_y, x):
+    """Tap and bias gradients of ``dw3x3``: returns (dweight (C,1,3,3), dbias (C))."""
+    _chk(grad_y, "grad_y")
+    _chk(x, "x", tuple(grad_y.shape))
+    B, C, h, w = x.shape
+    dw = torch.empty(C, 1, 3, 3, device=x.device, dtype=torch.float32)
+    db = torch.empty(C, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        ws, nbytes = _train_ws(x, C)
+        rc = _cabi.load().wm_dw3x3_wgrad(grad_y.data_ptr(), x.data_ptr(), dw.data_ptr(), db.data_ptr(),
+                                         ws.data_ptr(), nbytes, B, C, h, w, _stream(x))
+    _cabi.check(rc, "wm_dw3x3_wgrad")
+    _count(2)
+    return dw, db
+
+
+def layernorm2d_bwd(x, weight, grad_y, eps: float):
+    """Backward of ``layernorm2d``: returns (dx, dweight, dbias)."""
+    _chk(x, "x")
+    _chk(grad_y, "grad_y", tuple(x.shape))
+    B, C, h, w = x.shape
+    _chk(weight, "weight", (C,))
+    dx = torch.empty_like(x)
+    dw = torch.empty(C, device=x.device, dtype=torch.float32)
+    db = torch.empty(C, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        ws, nbytes = _train_ws(x, C)
+        rc = _cabi.load().wm_layernorm2d_bwd(x.data_ptr(), weight.data_ptr(), grad_y.data_ptr(), eps,
+                                             dx.data_ptr(), dw.data_ptr(), db.data_ptr(), ws.data_ptr(),
+                                             nbytes, B, C, h, w, _stream(x))
+    _cabi.check(rc, "wm_layernorm2d_bwd")
+    _count(3)
+    return dx, dw, db
