@@ -101,13 +101,17 @@ int main(int argc, char **argv)
     struct Case { const char *name; int W, H, C, B, bw, bh, bc, c0, c1, use_global; };
     const Case cases[] = {
         {"A box 32x8x4 at (0,0), param map", 128, 64, 32, 2, 32, 8, 4, 0, 0, 0},
-        {"B box 32x8x4 at (0,0), global map", 128, 64, 32, 2, 32, 8, 4, 0, 0, 1},
         {"C box 36x10x4 at (-1,-1), param map", 128, 64, 32, 2, 36, 10, 4, -1, -1, 0},
-        {"D box 36x10x32 at (-1,-1), param map", 128, 64, 32, 2, 36, 10, 32, -1, -1, 0},
-        {"E box 36x10x32 at (31,7), global map", 128, 64, 32, 2, 36, 10, 32, 31, 7, 1},
-        {"F box 36x10x16 at (-1,-1), param map", 128, 64, 32, 2, 36, 10, 16, -1, -1, 0},
         {"G box 32x10x32 at (0,-1), param map", 128, 64, 32, 2, 32, 10, 32, 0, -1, 0},
-        {"H box 36x10x32 at (-1,-1), W=32 H=8", 32, 8, 32, 2, 36, 10, 32, -1, -1, 0},
+        {"I box 32x10x32 at (-1,-1)", 128, 64, 32, 2, 32, 10, 32, -1, -1, 0},
+        {"J box 4x10x32 at (31,-1)", 128, 64, 32, 2, 4, 10, 32, 31, -1, 0},
+        {"K box 8x10x32 at (31,-1)", 128, 64, 32, 2, 8, 10, 32, 31, -1, 0},
+        {"L box 40x10x32 at (-4,-1)", 128, 64, 32, 2, 40, 10, 32, -4, -1, 0},
+        {"M box 48x10x32 at (-1,-1)", 128, 64, 32, 2, 48, 10, 32, -1, -1, 0},
+        {"N box 64x10x32 at (-1,-1)", 128, 64, 32, 2, 64, 10, 32, -1, -1, 0},
+        {"O box 36x10x8 at (0,0)", 128, 64, 32, 2, 36, 10, 8, 0, 0, 0},
+        {"P box 36x2x2 at (0,0)", 128, 64, 32, 2, 36, 2, 2, 0, 0, 0},
+        {"Q box 64x10x32 at (-1,-1), W=1920 H=1080", 1920, 1080, 32, 1, 64, 10, 32, -1, -1, 0},
     };
     const int ncases = (int)(sizeof(cases) / sizeof(cases[0]));
     if (argc > 1) {

@@ -409,7 +409,7 @@ extern "C" int wm_pw_dw_fwd(const float *x, const float *ln_w, const float *ln_b
     cudaStream_t s = (cudaStream_t)stream;
     // TMA + tcgen05 pipeline (pw_dw_tc5.cu) whenever its preconditions hold; WM_PW_DW_LEGACY=1 is a
     // developer switch for A/B timing of the cp.async + mma.sync kernel below
-    static const bool legacy = getenv("WM_PW_DW_TC5") == nullptr;   // TEMPORARY: opt-in while the TMA box is debugged
+    static const bool legacy = getenv("WM_PW_DW_LEGACY") != nullptr;
     if (!legacy) {
         const int rc = wm::pwdw::forward(x, ln_w, ln_b, eps, pw_w, pw_b, dw_w, dw_b, act, y, B, Cout, h, w, s);
         if (rc != 1) return rc;

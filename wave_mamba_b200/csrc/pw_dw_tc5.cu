@@ -3,9 +3,11 @@
 // in_proj+conv2d+SiLU, :226 ffn conv1+conv2, :729-732 project_in, :762-764 qkv+qkv_dwconv), as a
 // persistent, warp-specialised sm_100a pipeline (one CTA per SM):
 //
-//   TMA        one cp.async.bulk.tensor (4-D box 36 x 10 x 32ch, zero fill outside the image) per
+//   TMA        one cp.async.bulk.tensor (4-D box 40 x 10 x 32ch, zero fill outside the image) per
 //              8x32-pixel tile brings the halo tile into shared memory; the next tile's box is in
-//              flight while the current tile is computed
+//              flight while the current tile is computed.  (The box starts 4 columns left of the
+//              tile: the innermost start coordinate must be a multiple of 16 bytes -- measured with
+//              tools/probes/tma_probe.cu, a box at x0-1 raises an illegal-instruction fault.)
 //   warps 0-3  LayerNorm over channels per halo position, written straight into the UMMA K-major
 //              operand layout [ci/4][position][ci%4] as tf32 hi and lo = a - hi (3xTF32 split)
 //   warp 12    one thread issues tcgen05.mma kind::tf32 (M=128 positions, N=64 = [w_hi | w_lo] of a
@@ -26,8 +28,11 @@ namespace pwdw {
 using namespace wm::tc5;
 
 constexpr int kTH = 8, kTW = 32;
-constexpr int kBoxW = 36, kBoxH = kTH + 2;     // TMA box: columns tx0-1 .. tx0+34, rows ty0-1 .. ty0+8
-constexpr int kPos = kBoxW * kBoxH;            // 360 halo positions
+constexpr int kBoxW = 40, kBoxH = kTH + 2;     // TMA box: columns tx0-4 .. tx0+35, rows ty0-1 .. ty0+8
+constexpr int kBoxLeft = 4;                    // box column of image column tx0
+constexpr int kRaw = kBoxW * kBoxH;            // 400 floats per channel in the TMA buffer
+constexpr int kHW = kTW + 2;                   // halo row length 34 (columns tx0-1 .. tx0+32)
+constexpr int kPos = kHW * kBoxH;              // 340 halo positions
 constexpr int kMPos = 384;                     // three M=128 MMAs
 constexpr int kCin = 32;
 constexpr int kWarpsA = 4, kWarpsB = 8;
@@ -35,15 +40,15 @@ constexpr int kThreadsA = 32 * kWarpsA, kThreadsB = 32 * kWarpsB;
 constexpr int kWarpMma = kWarpsA + kWarpsB;
 constexpr int kThreads = 32 * (kWarpMma + 1);  // 416
 constexpr int kAccCols = 3 * 64;               // one accumulator set: 3 M tiles x [32 hi-sum | 32 lo]
-constexpr uint32_t kBoxBytes = kPos * kCin * 4;
+constexpr uint32_t kBoxBytes = kRaw * kCin * 4;
 
 template <int COUT>
 struct Smem {
     static constexpr int G = COUT / 32;
-    static constexpr size_t xraw = 0;                                  // [32][360] floats (TMA box)
-    static constexpr size_t xhi = xraw + (size_t)kCin * kPos * 4;      // [8][384] float4
+    static constexpr size_t xraw = 0;                                  // [32][10][40] floats (TMA box)
+    static constexpr size_t xhi = xraw + (size_t)kCin * kRaw * 4;      // [8][384] float4
     static constexpr size_t xlo = xhi + (size_t)8 * kMPos * 16;
-    static constexpr size_t ps = xlo + (size_t)8 * kMPos * 16;         // [32][360] floats
+    static constexpr size_t ps = xlo + (size_t)8 * kMPos * 16;         // [32][340] floats
     static constexpr size_t wsm = ps + (size_t)32 * kPos * 4;          // [G][8][64] float4
     static constexpr size_t cst = wsm + (size_t)G * 8 * 64 * 16;       // pwb[COUT] dww[COUT*9] dwb[COUT] lnw[32] lnb[32]
     static constexpr size_t bars = cst + (size_t)(COUT * 11 + 64) * 4; // 8 mbarriers + tmem slot
@@ -153,7 +158,7 @@ pw_dw_tc5_kernel(const __grid_constant__ CUtensorMap tmap, const Args a)
     }
     for (int i = tid; i < COUT * 9; i += kThreads) dww[i] = __ldg(a.dw_w + i);
     if (LN && tid < 32) { lnw[tid] = __ldg(a.ln_w + tid); lnb[tid] = __ldg(a.ln_b + tid); }
-    // rows 360..383 of the operand (read by the third M tile, results never used): defined values
+    // rows 340..383 of the operand (read by the third M tile, results never used): defined values
     for (int i = tid; i < 8 * (kMPos - kPos); i += kThreads) {
         const int kc = i / (kMPos - kPos), r = i - kc * (kMPos - kPos);
         xhi[kc * kMPos + kPos + r] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -179,7 +184,7 @@ pw_dw_tc5_kernel(const __grid_constant__ CUtensorMap tmap, const Args a)
             int tx0, ty0, b;
             tile_coords(tile, tx0, ty0, b);
             mbar_expect_tx(xraw_full, kBoxBytes);
-            tma_load_box(smem_u32(xraw), tmap_ptr, tx0 - 1, ty0 - 1, 0, b, xraw_full);
+            tma_load_box(smem_u32(xraw), tmap_ptr, tx0 - kBoxLeft, ty0 - 1, 0, b, xraw_full);
         };
         if (tid == 0 && (int)blockIdx.x < a.total_tiles) issue_tma(blockIdx.x);
         uint32_t it = 0;
@@ -190,8 +195,10 @@ pw_dw_tc5_kernel(const __grid_constant__ CUtensorMap tmap, const Args a)
 #pragma unroll 1
             for (int pos = tid; pos < kPos; pos += kThreadsA) {
                 float v[kCin];
+                const int prow = pos / kHW;
+                const int raw = prow * kBoxW + (pos - prow * kHW) + (kBoxLeft - 1);   // box column 3 = tx0-1
 #pragma unroll
-                for (int c = 0; c < kCin; ++c) v[c] = xraw[c * kPos + pos];
+                for (int c = 0; c < kCin; ++c) v[c] = xraw[c * kRaw + raw];
                 if (LN) {
                     float mu = 0.0f;
 #pragma unroll
@@ -279,7 +286,7 @@ pw_dw_tc5_kernel(const __grid_constant__ CUtensorMap tmap, const Args a)
                     tmem_ld_wait();
                     const int pos = mt * 128 + quarter * 32 + lane;
                     if (pos < kPos) {
-                        const int row = pos / kBoxW, col = pos - row * kBoxW;
+                        const int row = pos / kHW, col = pos - row * kHW;
                         const int gy = ty0 - 1 + row, gx = tx0 - 1 + col;
                         const bool valid = gy >= 0 && gy < h && gx >= 0 && gx < w;
 #pragma unroll
@@ -309,7 +316,7 @@ pw_dw_tc5_kernel(const __grid_constant__ CUtensorMap tmap, const Args a)
                     float r0[4], r1[4], r2[4];
                     {
                         const float2 p0 = *reinterpret_cast<const float2 *>(pc), p1 = *reinterpret_cast<const float2 *>(pc + 2);
-                        const float2 q0 = *reinterpret_cast<const float2 *>(pc + kBoxW), q1 = *reinterpret_cast<const float2 *>(pc + kBoxW + 2);
+                        const float2 q0 = *reinterpret_cast<const float2 *>(pc + kHW), q1 = *reinterpret_cast<const float2 *>(pc + kHW + 2);
                         r0[0] = p0.x; r0[1] = p0.y; r0[2] = p1.x; r0[3] = p1.y;
                         r1[0] = q0.x; r1[1] = q0.y; r1[2] = q1.x; r1[3] = q1.y;
                     }
@@ -317,8 +324,8 @@ pw_dw_tc5_kernel(const __grid_constant__ CUtensorMap tmap, const Args a)
                     float *yo = a.y + ((int64_t)b * COUT + co) * hw + (int64_t)ty0 * w + gx;
 #pragma unroll
                     for (int row = 0; row < kTH; ++row) {
-                        const float2 s0 = *reinterpret_cast<const float2 *>(pc + (row + 2) * kBoxW);
-                        const float2 s1 = *reinterpret_cast<const float2 *>(pc + (row + 2) * kBoxW + 2);
+                        const float2 s0 = *reinterpret_cast<const float2 *>(pc + (row + 2) * kHW);
+                        const float2 s1 = *reinterpret_cast<const float2 *>(pc + (row + 2) * kHW + 2);
                         r2[0] = s0.x; r2[1] = s0.y; r2[2] = s1.x; r2[3] = s1.y;
                         float o0 = bias, o1 = bias;
 #pragma unroll
@@ -378,7 +385,7 @@ static EncodeTiledFn encode_fn()
     return fn;
 }
 
-// NCHW fp32 tensor (B, 32, h, w) as a 4-D tensor map with a 36 x 10 x 32 x 1 box
+// NCHW fp32 tensor (B, 32, h, w) as a 4-D tensor map with a 40 x 10 x 32 x 1 box
 static bool make_tmap(CUtensorMap *tm, const float *x, int64_t B, int64_t h, int64_t w)
 {
     EncodeTiledFn enc = encode_fn();
