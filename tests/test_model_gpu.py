@@ -72,18 +72,23 @@ def test_registry_class_api(dev, params_cache):
     net = _net(params_cache("UHDLL"), dev)
     x, _ = om.synth_lowlight(1, 64, 64, seed=3)
     xd = x.to(dev)
-    a = net(xd)
-    b = net.test(xd)
-    c = net.restoration_network(xd)
+    b = net.test(xd)                                   # no_grad inside, as the reference's test()
+    with torch.no_grad():
+        a = net(xd)
+        c = net.restoration_network(xd)
     assert torch.equal(a, b) and torch.equal(a, c)
-    assert not a.requires_grad
+    assert not b.requires_grad
     padded = net.check_image_size(torch.rand(1, 3, 61, 70, device=dev))
     assert padded.shape[2] % 8 == 0 and padded.shape[3] % 8 == 0
     with pytest.raises(ValueError):
         net.restoration_network(torch.rand(1, 3, 60, 64, device=dev))
-    net.train()                      # grad mode + trainable parameters: the differentiable path
+    # grad mode + trainable parameters (eval() or train(), as in PyTorch): the differentiable path
     d = net(xd)
     assert d.requires_grad and (d - a).abs().max().item() <= 2e-5
+    for p in net.parameters():
+        p.requires_grad_(False)
+    e = net(xd)                                        # nothing to differentiate: the fused path
+    assert not e.requires_grad and torch.equal(e, a)
 
 
 class _Sink(dict):

@@ -246,7 +246,7 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
         // =============================== weight producer ====================================
         if (lane == 0) {
             uint32_t cnt = 0;
-            const int rot = blockIdx.x % NTAPS;   // see the MMA issuer
+            const int rot = 0;   // a per-CTA rotation of the tap order was measured: no gain
 #pragma unroll 1
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
 #pragma unroll 1
@@ -278,9 +278,7 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
             const uint64_t a_lo0 = make_desc(smem_u32(xlo), kNPos * 16u, 128u);
             const uint64_t b_00 = make_desc(smem_u32(wbuf), 2 * COUT * 16u, 128u);
             uint32_t cnt = 0, unit = 0, tcount = 0;
-            // CTAs walk the taps in rotated orders so that the 148 SMs do not all pull the same
-            // 16 KB weight chunk from the same L2 lines at the same moment
-            const int rot = blockIdx.x % NTAPS;
+            const int rot = 0;   // tap-order rotation per CTA (against L2 hot spots): measured, no gain
             long long tacc[5] = {0, 0, 0, 0, 0}, t0 = 0, tp = 0;
             const bool timed = a.dbg != nullptr;
             if (timed) { t0 = clock64(); tp = t0; }

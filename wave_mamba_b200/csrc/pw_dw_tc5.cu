@@ -13,8 +13,8 @@
 //   warp 12    one thread issues tcgen05.mma kind::tf32 (M=128 positions, N=64 = [w_hi | w_lo] of a
 //              32-channel output group, K=32 in 4 steps) into TMEM, double-buffered per group
 //   warps 4-11 TMEM -> registers -> +bias, zero outside the image (the depthwise conv pads the 1x1
-//              OUTPUT) -> shared [channel][position]; then the depthwise 3x3 + SiLU from shared
-//              memory, two adjacent pixels per thread (8-byte shared loads and global stores)
+//              OUTPUT) -> shared [channel][row][36]; then the depthwise 3x3 + SiLU from shared
+//              memory, four adjacent pixels per thread on the packed FP32 pipe (FFMA2), 16-byte stores
 //
 // Falls back to the cp.async / mma.sync kernel of pointwise.cu when the TMA preconditions do not
 // hold (w % 4 != 0 or unaligned pointers).
@@ -33,6 +33,8 @@ constexpr int kBoxLeft = 4;                    // box column of image column tx0
 constexpr int kRaw = kBoxW * kBoxH;            // 400 floats per channel in the TMA buffer
 constexpr int kHW = kTW + 2;                   // halo row length 34 (columns tx0-1 .. tx0+32)
 constexpr int kPos = kHW * kBoxH;              // 340 halo positions
+constexpr int kPSW = 36;                       // row stride of the 1x1 output tile (16-byte rows)
+constexpr int kPS = kPSW * kBoxH;              // 360 floats per channel
 constexpr int kMPos = 384;                     // three M=128 MMAs
 constexpr int kCin = 32;
 constexpr int kWarpsA = 4, kWarpsB = 8;
@@ -48,8 +50,8 @@ struct Smem {
     static constexpr size_t xraw = 0;                                  // [32][10][40] floats (TMA box)
     static constexpr size_t xhi = xraw + (size_t)kCin * kRaw * 4;      // [8][384] float4
     static constexpr size_t xlo = xhi + (size_t)8 * kMPos * 16;
-    static constexpr size_t ps = xlo + (size_t)8 * kMPos * 16;         // [32][340] floats
-    static constexpr size_t wsm = ps + (size_t)32 * kPos * 4;          // [G][8][64] float4
+    static constexpr size_t ps = xlo + (size_t)8 * kMPos * 16;         // [32][10][36] floats
+    static constexpr size_t wsm = ps + (size_t)32 * kPS * 4;           // [G][8][64] float4
     static constexpr size_t cst = wsm + (size_t)G * 8 * 64 * 16;       // pwb[COUT] dww[COUT*9] dwb[COUT] lnw[32] lnb[32]
     static constexpr size_t bars = cst + (size_t)(COUT * 11 + 64) * 4; // 8 mbarriers + tmem slot
     static constexpr size_t total = bars + 8 * 8 + 16;
@@ -85,6 +87,24 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16])
           "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
           "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
+}
+
+typedef unsigned long long f32x2;      // packed fp32 pair (Blackwell FFMA2)
+__device__ __forceinline__ f32x2 pack2(float lo, float hi)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
 }
 
 __device__ __forceinline__ void named_bar(int id, int count)
@@ -293,7 +313,7 @@ pw_dw_tc5_kernel(const __grid_constant__ CUtensorMap tmap, const Args a)
                         for (int j = 0; j < 16; ++j) {
                             const float v = (__uint_as_float(acc[j]) + __uint_as_float(part[j])) +
                                             pwb[g * 32 + chalf * 16 + j];
-                            ps[(chalf * 16 + j) * kPos + pos] = valid ? v : 0.0f;
+                            ps[(chalf * 16 + j) * kPS + row * kPSW + col] = valid ? v : 0.0f;
                         }
                     }
                 }
@@ -302,53 +322,50 @@ pw_dw_tc5_kernel(const __grid_constant__ CUtensorMap tmap, const Args a)
                 if (lane == 0) mbar_arrive(acc_empty(buf));
                 named_bar(2, kThreadsB);               // ps of this group is complete
 
-                // depthwise 3x3 (+ SiLU): item = (channel, column pair), 8 rows, sliding window
-#pragma unroll 1
-                for (int i = 0; i < 2; ++i) {
-                    const int item = tb + i * kThreadsB;
-                    const int cl = item >> 4, j2 = (item & 15) * 2;
+                // depthwise 3x3 (+ SiLU): thread = (channel, 4 adjacent columns), 8 rows, sliding window of
+                // three input rows held as packed pairs (FFMA2: two outputs per instruction).  Per input
+                // row one LDS.128 + one LDS.64 bring the 6 values (v0..v5) four outputs need.
+                {
+                    const int cl = tb >> 3, j4 = (tb & 7) * 4;
                     const int co = g * 32 + cl;
-                    float k[9];
+                    f32x2 k2[9];
 #pragma unroll
-                    for (int t = 0; t < 9; ++t) k[t] = dww[co * 9 + t];
+                    for (int t = 0; t < 9; ++t) { const float kv = dww[co * 9 + t]; k2[t] = pack2(kv, kv); }
                     const float bias = dwb[co];
-                    const float *pc = ps + cl * kPos + j2;
-                    float r0[4], r1[4], r2[4];
-                    {
-                        const float2 p0 = *reinterpret_cast<const float2 *>(pc), p1 = *reinterpret_cast<const float2 *>(pc + 2);
-                        const float2 q0 = *reinterpret_cast<const float2 *>(pc + kHW), q1 = *reinterpret_cast<const float2 *>(pc + kHW + 2);
-                        r0[0] = p0.x; r0[1] = p0.y; r0[2] = p1.x; r0[3] = p1.y;
-                        r1[0] = q0.x; r1[1] = q0.y; r1[2] = q1.x; r1[3] = q1.y;
-                    }
-                    const int gx = tx0 + j2;
+                    const float *pc = ps + cl * kPS + j4;
+                    // packed pairs of one input row: P0=(v0,v1) P1=(v2,v3) P2=(v4,v5) Q0=(v1,v2) Q1=(v3,v4)
+                    f32x2 P[3][3], Q[3][2];
+                    auto load_row = [&](int r, int slot) {
+                        const float4 a4 = *reinterpret_cast<const float4 *>(pc + r * kPSW);
+                        const float2 b2 = *reinterpret_cast<const float2 *>(pc + r * kPSW + 4);
+                        P[slot][0] = pack2(a4.x, a4.y); P[slot][1] = pack2(a4.z, a4.w); P[slot][2] = pack2(b2.x, b2.y);
+                        Q[slot][0] = pack2(a4.y, a4.z); Q[slot][1] = pack2(a4.w, b2.x);
+                    };
+                    load_row(0, 0);
+                    load_row(1, 1);
+                    const int gx = tx0 + j4;
                     float *yo = a.y + ((int64_t)b * COUT + co) * hw + (int64_t)ty0 * w + gx;
 #pragma unroll
                     for (int row = 0; row < kTH; ++row) {
-                        const float2 s0 = *reinterpret_cast<const float2 *>(pc + (row + 2) * kHW);
-                        const float2 s1 = *reinterpret_cast<const float2 *>(pc + (row + 2) * kHW + 2);
-                        r2[0] = s0.x; r2[1] = s0.y; r2[2] = s1.x; r2[3] = s1.y;
-                        float o0 = bias, o1 = bias;
+                        load_row(row + 2, (row + 2) % 3);
+                        f32x2 oa = pack2(bias, bias), ob = oa;
 #pragma unroll
-                        for (int dx = 0; dx < 3; ++dx) {
-                            o0 = fmaf(k[dx], r0[dx], o0);     o1 = fmaf(k[dx], r0[dx + 1], o1);
+                        for (int dy = 0; dy < 3; ++dy) {
+                            const int sl = (row + dy) % 3;
+                            oa = ffma2(k2[3 * dy + 0], P[sl][0], oa); ob = ffma2(k2[3 * dy + 0], P[sl][1], ob);
+                            oa = ffma2(k2[3 * dy + 1], Q[sl][0], oa); ob = ffma2(k2[3 * dy + 1], Q[sl][1], ob);
+                            oa = ffma2(k2[3 * dy + 2], P[sl][1], oa); ob = ffma2(k2[3 * dy + 2], P[sl][2], ob);
                         }
-#pragma unroll
-                        for (int dx = 0; dx < 3; ++dx) {
-                            o0 = fmaf(k[3 + dx], r1[dx], o0); o1 = fmaf(k[3 + dx], r1[dx + 1], o1);
-                        }
-#pragma unroll
-                        for (int dx = 0; dx < 3; ++dx) {
-                            o0 = fmaf(k[6 + dx], r2[dx], o0); o1 = fmaf(k[6 + dx], r2[dx + 1], o1);
-                        }
+                        float o0, o1, o2, o3;
+                        unpack2(oa, o0, o1);
+                        unpack2(ob, o2, o3);
                         if (SILU) {   // SS2D.act (reference :487)
-                            o0 = __fdividef(o0, 1.0f + __expf(-o0));
-                            o1 = __fdividef(o1, 1.0f + __expf(-o1));
+                            o0 = __fdividef(o0, 1.0f + __expf(-o0)); o1 = __fdividef(o1, 1.0f + __expf(-o1));
+                            o2 = __fdividef(o2, 1.0f + __expf(-o2)); o3 = __fdividef(o3, 1.0f + __expf(-o3));
                         }
-                        // w % 4 == 0 and gx even: the pair is inside the image or outside together
+                        // w % 4 == 0 and gx % 4 == 0: the four columns are inside the image or outside together
                         if (gx < w && ty0 + row < h)
-                            *reinterpret_cast<float2 *>(yo + (int64_t)row * w) = make_float2(o0, o1);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) { r0[q] = r1[q]; r1[q] = r2[q]; }
+                            *reinterpret_cast<float4 *>(yo + (int64_t)row * w) = make_float4(o0, o1, o2, o3);
                     }
                 }
                 named_bar(2, kThreadsB);               // ps may be overwritten by the next group
