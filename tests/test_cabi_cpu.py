@@ -153,8 +153,8 @@ def test_ss2d_chunk_plan_is_consistent(lib_path):
         assert row_T % 16 == 0 and row_T >= 64
         assert col_seg % 16 == 0 and col_seg * ncolseg >= h and col_seg * (ncolseg - 1) < h
         row_chunks = -(-L // row_T)
-        assert row_ctas == -(-row_chunks // 4)
-        assert col_ctas == -(-w // 4) * ncolseg
+        assert row_ctas == -(-row_chunks // 8)          # the forward walks 8 strands per CTA
+        assert col_ctas == -(-w // 8) * ncolseg
         assert cols_first in (0, 1)
         max_chunks = max(row_chunks, w * ncolseg)
         need = 4 * B * 64 * L * 4 + 2 * B * 4 * max_chunks * 1024 * 4

@@ -40,6 +40,7 @@ SIGNATURES = {
     "wm_conv3x3_packed_bytes": (c_size_t, [c_int64, c_int64, c_int]),
     "wm_conv3x3_debug_timing": (c_int, [c_void_p]),
     "wm_debug_pipeline_error": (c_int, [c_void_p]),
+    "wm_pw_dw_debug_timing": (c_int, [c_void_p]),
     "wm_conv3x3_prepack": (c_int, [c_void_p] * 3 + [c_int64] * 2 + [c_void_p]),
     "wm_conv3x3_fwd": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64] + [c_void_p] * 5 +
                        [c_int64] * 5 + [c_void_p]),

@@ -20,6 +20,8 @@
 // hold (w % 4 != 0 or unaligned pointers).
 #include <cuda.h>
 
+#include <atomic>
+
 #include "tc5_common.cuh"
 
 namespace wm {
@@ -66,7 +68,13 @@ struct Args {
     float *y;
     int h, w, tiles_x, tiles_y, total_tiles;
     unsigned int *err;     // pipeline error word (mbar_wait_flag)
+    long long *dbg;        // optional per-CTA cycle counters (wm_pw_dw_debug_timing), 12 per CTA:
+                           // LN warps: [0] wait TMA [1] wait operand free [2] LN pass
+                           // MMA: [3] wait operand [4] wait accumulators [5] issue
+                           // epilogue warps: [6] wait MMA [7] TMEM -> ps [8] depthwise [9] tiles [10] total
 };
+
+static std::atomic<long long *> g_dbg{nullptr};
 
 __device__ __forceinline__ void tma_load_box(uint32_t dst, const CUtensorMap *tmap, int c0, int c1, int c2,
                                              int c3, uint32_t mbar)
@@ -208,10 +216,15 @@ pw_dw_tc5_kernel(const __grid_constant__ CUtensorMap tmap, const Args a)
         };
         if (tid == 0 && (int)blockIdx.x < a.total_tiles) issue_tma(blockIdx.x);
         uint32_t it = 0;
+        const bool timed = a.dbg != nullptr && tid == 0;
+        long long ta[3] = {0, 0, 0}, tp = timed ? clock64() : 0;
+#define WM_TICKA(k) do { if (timed) { const long long _t = clock64(); ta[k] += _t - tp; tp = _t; } } while (0)
 #pragma unroll 1
         for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
             mbar_wait_flag(xraw_full, it & 1u, a.err, (1u << 24) | (0u << 16) | (it & 0xffffu));
-            mbar_wait_flag(xk_empty, (it & 1u) ^ 1u, a.err, (1u << 24) | (2u << 16) | (it & 0xffffu));       // the previous tile's MMAs have read xhi/xlo
+            WM_TICKA(0);
+            mbar_wait_flag(xk_empty, (it & 1u) ^ 1u, a.err, (1u << 24) | (2u << 16) | (it & 0xffffu));
+            WM_TICKA(1);       // the previous tile's MMAs have read xhi/xlo
 #pragma unroll 1
             for (int pos = tid; pos < kPos; pos += kThreadsA) {
                 float v[kCin];
@@ -243,7 +256,10 @@ pw_dw_tc5_kernel(const __grid_constant__ CUtensorMap tmap, const Args a)
             mbar_arrive(xk_full);
             named_bar(1, kThreadsA);                   // every thread is done reading xraw
             if (tid == 0 && tile + (int)gridDim.x < a.total_tiles) issue_tma(tile + gridDim.x);
+            WM_TICKA(2);
         }
+        if (timed) for (int i = 0; i < 3; ++i) a.dbg[blockIdx.x * 12 + i] = ta[i];
+#undef WM_TICKA
     } else if (warp == kWarpMma) {
         // =========================== MMA issuer ==============================================
         if (lane == 0) {
@@ -255,15 +271,20 @@ pw_dw_tc5_kernel(const __grid_constant__ CUtensorMap tmap, const Args a)
             const uint64_t a_lo0 = make_desc(smem_u32(xlo), kMPos * 16u, 128u);
             const uint64_t b_0 = make_desc(smem_u32(wsm), 64 * 16u, 128u);
             uint32_t it = 0, gcount = 0;
+            const bool timed = a.dbg != nullptr;
+            long long tm[3] = {0, 0, 0}, tp = timed ? clock64() : 0;
+#define WM_TICKM(k) do { if (timed) { const long long _t = clock64(); tm[k] += _t - tp; tp = _t; } } while (0)
 #pragma unroll 1
             for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
                 mbar_wait_flag(xk_full, it & 1u, a.err, (2u << 24) | (1u << 16) | (it & 0xffffu));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                WM_TICKM(0);
 #pragma unroll 1
                 for (int g = 0; g < G; ++g, ++gcount) {
                     const int buf = gcount & 1;
                     mbar_wait_flag(acc_empty(buf), ((gcount >> 1) & 1u) ^ 1u, a.err, (2u << 24) | (4u << 16) | (gcount & 0xffffu));
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    WM_TICKM(1);
 #pragma unroll
                     for (int mt = 0; mt < 3; ++mt) {
                         const uint32_t d = tmem_base + (uint32_t)(buf * kAccCols + mt * 64);
@@ -277,9 +298,12 @@ pw_dw_tc5_kernel(const __grid_constant__ CUtensorMap tmap, const Args a)
                         }
                     }
                     mma_commit(acc_full(buf));
+                    WM_TICKM(2);
                 }
                 mma_commit(xk_empty);
             }
+            if (timed) for (int i = 0; i < 3; ++i) a.dbg[blockIdx.x * 12 + 3 + i] = tm[i];
+#undef WM_TICKM
         }
     } else {
         // =========================== epilogue + depthwise 3x3 ================================
@@ -287,8 +311,12 @@ pw_dw_tc5_kernel(const __grid_constant__ CUtensorMap tmap, const Args a)
         const int quarter = warp & 3, chalf = e >> 2;  // TMEM lane quarter, 16-channel half of the group
         const int tb = tid - kThreadsA;                // 0..255
         uint32_t gcount = 0;
+        const bool timed = a.dbg != nullptr && tb == 0;
+        long long tbb[3] = {0, 0, 0}, t0 = timed ? clock64() : 0, tp = t0;
+        int ntile = 0;
+#define WM_TICKB(k) do { if (timed) { const long long _t = clock64(); tbb[k] += _t - tp; tp = _t; } } while (0)
 #pragma unroll 1
-        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++ntile) {
             int tx0, ty0, b;
             tile_coords(tile, tx0, ty0, b);
 #pragma unroll 1
@@ -296,6 +324,7 @@ pw_dw_tc5_kernel(const __grid_constant__ CUtensorMap tmap, const Args a)
                 const int buf = gcount & 1;
                 mbar_wait_flag(acc_full(buf), (gcount >> 1) & 1u, a.err, (3u << 24) | (3u << 16) | (gcount & 0xffffu));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                WM_TICKB(0);
 #pragma unroll 1
                 for (int mt = 0; mt < 3; ++mt) {
                     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
@@ -321,6 +350,7 @@ pw_dw_tc5_kernel(const __grid_constant__ CUtensorMap tmap, const Args a)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(acc_empty(buf));
                 named_bar(2, kThreadsB);               // ps of this group is complete
+                WM_TICKB(1);
 
                 // depthwise 3x3 (+ SiLU): thread = (channel, 4 adjacent columns), 8 rows, sliding window of
                 // three input rows held as packed pairs (FFMA2: two outputs per instruction).  Per input
@@ -369,8 +399,15 @@ pw_dw_tc5_kernel(const __grid_constant__ CUtensorMap tmap, const Args a)
                     }
                 }
                 named_bar(2, kThreadsB);               // ps may be overwritten by the next group
+                WM_TICKB(2);
             }
         }
+        if (timed) {
+            for (int i = 0; i < 3; ++i) a.dbg[blockIdx.x * 12 + 6 + i] = tbb[i];
+            a.dbg[blockIdx.x * 12 + 9] = ntile;
+            a.dbg[blockIdx.x * 12 + 10] = clock64() - t0;
+        }
+#undef WM_TICKB
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -448,6 +485,7 @@ int forward(const float *x, const float *ln_w, const float *ln_b, float eps, con
     a.total_tiles = (int)total;
     a.err = pipeline_err_word();
     if (a.err == nullptr) return 1;
+    a.dbg = g_dbg.load();
     const bool ln = ln_w != nullptr, silu = act == 1;
 #define WM_PWDW_CASE(C)                                                                  \
     if (Cout == C) {                                                                     \
@@ -465,3 +503,11 @@ int forward(const float *x, const float *ln_w, const float *ln_b, float eps, con
 
 }  // namespace pwdw
 }  // namespace wm
+
+/* Developer aid: non-NULL device buffer of 12*SMs int64 -> per-CTA cycle counters of the pw_dw pipeline
+ * (see Args::dbg); NULL disables. */
+extern "C" int wm_pw_dw_debug_timing(void *device_buffer)
+{
+    wm::pwdw::g_dbg.store(static_cast<long long *>(device_buffer));
+    return WM_OK;
+}

@@ -46,22 +46,27 @@
 #include <utility>
 #include <vector>
 
+#define WM_SS2D_SEQ 8
+#define WM_SS2D_TP 8
 #include "ss2d_common.cuh"
 
 namespace wm {
 namespace ss2d {
 
-// Inputs of one recurrence step of a scan thread = (strand, channel pair, state half): 2 channels
-// x 8 states, so the B/C rows of the position are fetched once per 16 state updates.  They are
-// loaded one step ahead (the compiler cannot hoist them itself: the y store may alias).
+constexpr int kCh = 4;       // channels per scan thread
+// Inputs of one recurrence step of a scan thread = (strand, channel quad, state half): 4 channels x 8
+// states, so the B/C rows of the position are fetched once per 32 state updates (96 bytes per step:
+// 3 bytes per update; the 2 x 8 blocking of round 1 moved 5 and was bound by the LSU return path).
+// They are loaded one step ahead (the compiler cannot hoist them itself: the y store may alias).
 template <bool FINAL>
 struct StepIn {
-    float4 dv;        // (dt0, u0, dt1, u1)
+    float4 dv0, dv1;  // (dt0, u0, dt1, u1), (dt2, u2, dt3, u3)
     float4 b0, b1;    // B[half*8 .. +7]
     float4 c0, c1;    // C[half*8 .. +7]   (pass 2)
     __device__ __forceinline__ void load(const float *ddp, const float *pjp)
     {
-        dv = *reinterpret_cast<const float4 *>(ddp);
+        dv0 = *reinterpret_cast<const float4 *>(ddp);
+        dv1 = *reinterpret_cast<const float4 *>(ddp + 4);
         b0 = *reinterpret_cast<const float4 *>(pjp);
         b1 = *reinterpret_cast<const float4 *>(pjp + 4);
         if (FINAL) {
@@ -71,10 +76,11 @@ struct StepIn {
     }
 };
 
+// ysp: &ys[first of my two output channels][position]; the second channel is kYS floats further
 template <bool FINAL>
-__device__ __forceinline__ void scan_step(const StepIn<FINAL> &in, float *ysp, f32x2 (&hst)[2][4],
-                                          const f32x2 (&A2)[2][4], float (&sdt)[2], float my_skip,
-                                          bool half)
+__device__ __forceinline__ void scan_step(const StepIn<FINAL> &in, float *ysp, f32x2 (&hst)[kCh][4],
+                                          const f32x2 (&A2)[kCh][4], float (&sdt)[kCh],
+                                          const float (&my_skip)[2], bool half)
 {
     const f32x2 bb[4] = {pack2(in.b0.x, in.b0.y), pack2(in.b0.z, in.b0.w), pack2(in.b1.x, in.b1.y),
                          pack2(in.b1.z, in.b1.w)};
@@ -83,10 +89,11 @@ __device__ __forceinline__ void scan_step(const StepIn<FINAL> &in, float *ysp, f
         cc[0] = pack2(in.c0.x, in.c0.y); cc[1] = pack2(in.c0.z, in.c0.w);
         cc[2] = pack2(in.c1.x, in.c1.y); cc[3] = pack2(in.c1.z, in.c1.w);
     }
-    const float dtv[2] = {in.dv.x, in.dv.z}, uv[2] = {in.dv.y, in.dv.w};
-    float yv[2];
+    const float dtv[kCh] = {in.dv0.x, in.dv0.z, in.dv1.x, in.dv1.z};
+    const float uv[kCh] = {in.dv0.y, in.dv0.w, in.dv1.y, in.dv1.w};
+    float yv[kCh];
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    for (int c = 0; c < kCh; ++c) {
         const float du = dtv[c] * uv[c];
         const f32x2 dt2 = pack2(dtv[c], dtv[c]), du2 = pack2(du, du);
         if (!FINAL) sdt[c] += dtv[c];
@@ -107,19 +114,21 @@ __device__ __forceinline__ void scan_step(const StepIn<FINAL> &in, float *ysp, f
             yv[c] = lo + hi;
         }
     }
-    // half 0 finishes channel d0, half 1 channel d1: swap the other channel's partial sum with the
-    // partner lane, add the D skip term (reference :469)
+    // half 0 finishes channels 0,1 of the quad, half 1 channels 2,3: swap the other two partial sums
+    // with the partner lane, add the D skip term (reference :469)
     if (FINAL) {
-        const float other = __shfl_xor_sync(0xffffffffu, half ? yv[0] : yv[1], 1);
-        *ysp = fmaf(my_skip, half ? uv[1] : uv[0], (half ? yv[1] : yv[0]) + other);
+        const float o0 = __shfl_xor_sync(0xffffffffu, half ? yv[0] : yv[2], 1);
+        const float o1 = __shfl_xor_sync(0xffffffffu, half ? yv[1] : yv[3], 1);
+        ysp[0] = fmaf(my_skip[0], half ? uv[2] : uv[0], (half ? yv[2] : yv[0]) + o0);
+        ysp[kYS] = fmaf(my_skip[1], half ? uv[3] : uv[1], (half ? yv[3] : yv[1]) + o1);
     }
 }
 
-// state of a scan thread (2 channels x 8 states) -> 2 x 32 contiguous bytes of a checkpoint row
-__device__ __forceinline__ void store_state(float *dst, const f32x2 (&hst)[2][4])
+// state of a scan thread (4 channels x 8 states) -> 4 x 32 contiguous bytes of a checkpoint row
+__device__ __forceinline__ void store_state(float *dst, const f32x2 (&hst)[kCh][4])
 {
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    for (int c = 0; c < kCh; ++c) {
         float v[8];
 #pragma unroll
         for (int j = 0; j < 4; ++j) unpack2(hst[c][j], v[2 * j], v[2 * j + 1]);
@@ -180,52 +189,55 @@ __device__ __forceinline__ void run_cta(const Params &prm, const Geom &g, const 
         cst[2 * kD + tid] = __ldg(prm.dt_b + chn);
     }
 
-    // ---- scan-thread identity: (strand, channel pair, state half) ----------------------------
-    const int s = tid >> 6, cp = (tid & 63) >> 1;
+    // ---- scan-thread identity: (strand = warp, channel quad, state half) ----------------------
+    const int s = tid >> 5, cq = (tid & 31) >> 1;
     const bool half = (tid & 1) != 0;
     const int hoff = half ? 8 : 0;
-    f32x2 A2[2][4];  // A * log2(e), A = -exp(A_log)   (reference :462)
+    f32x2 A2[kCh][4];  // A * log2(e), A = -exp(A_log)   (reference :462)
 #pragma unroll
-    for (int c = 0; c < 2; ++c)
+    for (int c = 0; c < kCh; ++c)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float *ap = prm.A_logs + (int64_t)(k * kD + 2 * cp + c) * kN + hoff + 2 * j;
+            const float *ap = prm.A_logs + (int64_t)(k * kD + kCh * cq + c) * kN + hoff + 2 * j;
             A2[c][j] = pack2(-expf(__ldg(ap)) * 1.4426950408889634f,
                              -expf(__ldg(ap + 1)) * 1.4426950408889634f);
         }
-    const float my_skip = FINAL ? __ldg(prm.Ds + k * kD + 2 * cp + (half ? 1 : 0)) : 0.0f;
+    // this lane finishes channels 4cq + 2*half and + 1 of the quad
+    const int my_d = kCh * cq + (half ? 2 : 0);
+    const float my_skip[2] = {FINAL ? __ldg(prm.Ds + k * kD + my_d) : 0.0f,
+                              FINAL ? __ldg(prm.Ds + k * kD + my_d + 1) : 0.0f};
     const int my_len = strand_len(g, tg, s);
     const int my_chunk = tg.col ? (tg.chunk0 + s) * g.ncolseg + tg.seg : tg.chunk0 + s;
     const int64_t agg_off =
-        (((int64_t)b * kK + k) * g.max_chunks + my_chunk) * kChains + (int64_t)(2 * cp) * kN + hoff;
+        (((int64_t)b * kK + k) * g.max_chunks + my_chunk) * kChains + (int64_t)(kCh * cq) * kN + hoff;
 
-    f32x2 hst[2][4];
+    f32x2 hst[kCh][4];
 #pragma unroll
-    for (int c = 0; c < 2; ++c)
+    for (int c = 0; c < kCh; ++c)
 #pragma unroll
         for (int j = 0; j < 4; ++j) hst[c][j] = pack2(0.0f, 0.0f);
     if ((FINAL || CKPT) && my_len > 0 && my_chunk > 0) {
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        for (int c = 0; c < kCh; ++c) {
             const float4 *hp = reinterpret_cast<const float4 *>(prm.aggH + agg_off + c * kN);
             const float4 f0 = hp[0], f1 = hp[1];
             hst[c][0] = pack2(f0.x, f0.y); hst[c][1] = pack2(f0.z, f0.w);
             hst[c][2] = pack2(f1.x, f1.y); hst[c][3] = pack2(f1.z, f1.w);
         }
     }
-    double sum_dt[2] = {0.0, 0.0};
+    double sum_dt[kCh] = {0.0, 0.0, 0.0, 0.0};
 
     // smem position of step 0 of my strand; step e sits at p0 + e*DP
     const int p0 = tile_pos(tg, s, 0);
-    const float *dd0 = dd + p0 * kDD + 4 * cp;
+    const float *dd0 = dd + p0 * kDD + 2 * kCh * cq;
     const float *pj0 = pj + p0 * kPJ + hoff;
-    float *ys0 = ys + (2 * cp + (half ? 1 : 0)) * kYS + p0;
+    float *ys0 = ys + my_d * kYS + p0;
 
     float *oplane = FINAL ? prm.planes + (((int64_t)k * g.B + b) * kD) * g.L : nullptr;
     float *hck = nullptr;   // checkpoint rows of my chunk: step t at hck + t * kChains
     if (CKPT)
         hck = prm.hbuf + (((int64_t)b * dir_chunks(g, k) + my_chunk) * dir_chunk_len(g, k)) * kChains +
-              (int64_t)(2 * cp) * kN + hoff;
+              (int64_t)(kCh * cq) * kN + hoff;
 
     // projection role of this warp: m-tile (16 positions) and up to three n-tiles.
     //   pass 2: warps 0-3 -> B0-7, B8-15, dt;  warps 4-7 -> C0-7, C8-15
@@ -334,8 +346,8 @@ __device__ __forceinline__ void run_cta(const Params &prm, const Geom &g, const 
 
         // ---- recurrence over the 16 steps of this tile        (reference :465-471) --------
         {
-            const int nvalid = my_len - ti * kTP;          // warp-uniform
-            float sdt[2] = {0.0f, 0.0f};
+            const int nvalid = my_len - ti * kTP;          // warp-uniform (a warp is one strand)
+            float sdt[kCh] = {0.0f, 0.0f, 0.0f, 0.0f};
             if (nvalid >= kTP) {
                 StepIn<FINAL> cur, nxt;
                 cur.load(dd0, pj0);
@@ -359,7 +371,10 @@ __device__ __forceinline__ void run_cta(const Params &prm, const Geom &g, const 
                     if (CKPT) store_state(hck + (int64_t)(ti * kTP + e) * kChains, hst);
                 }
             }
-            if (!FINAL && !CKPT) { sum_dt[0] += (double)sdt[0]; sum_dt[1] += (double)sdt[1]; }
+            if (!FINAL && !CKPT) {
+#pragma unroll
+                for (int c = 0; c < kCh; ++c) sum_dt[c] += (double)sdt[c];
+            }
         }
         if (FINAL) {
             __syncthreads();
@@ -378,7 +393,7 @@ __device__ __forceinline__ void run_cta(const Params &prm, const Geom &g, const 
 
     if (!FINAL && !CKPT && my_len > 0) {
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        for (int c = 0; c < kCh; ++c) {
             float4 *pp4 = reinterpret_cast<float4 *>(prm.aggP + agg_off + c * kN);
             float4 *hp4 = reinterpret_cast<float4 *>(prm.aggH + agg_off + c * kN);
             float pv[8], hv[8];
@@ -581,19 +596,19 @@ Geom make_geom(int64_t B, int64_t h, int64_t w)
     double best = 1e300;
     int best_seg = 0, best_T = 0, best_first = 0;
     auto legacy_plan = [&]() {   // one chunk per column, row chunks of about the same length
-        best_seg = (int)align_up(h, kTP);
-        int64_t T = h < 4 * kTP ? 4 * kTP : h;
-        best_T = (int)align_up(T, kTP);
+        best_seg = (int)align_up(h, kAlign);
+        int64_t T = h < 4 * kAlign ? 4 * kAlign : h;
+        best_T = (int)align_up(T, kAlign);
     };
     if (legacy) legacy_plan();
     for (int nseg = 1; nseg <= 8 && !legacy; ++nseg) {
-        int64_t seg = align_up((h + nseg - 1) / nseg, kTP);
-        if (nseg > 1 && seg < 4 * kTP) break;          // never shorter than 4 tiles
+        int64_t seg = align_up((h + nseg - 1) / nseg, kAlign);
+        if (nseg > 1 && seg < 4 * kAlign) break;       // never shorter than 64 steps
         const int ncolseg = (int)((h + seg - 1) / seg);
         if (ncolseg != nseg && nseg > 1) continue;
         const int64_t last = h - (int64_t)(ncolseg - 1) * seg;
         // row chunk lengths: from 4 tiles up to a little more than the column segment
-        for (int64_t T = 4 * kTP; T <= seg + 8 * kTP; T += kTP) {
+        for (int64_t T = 4 * kAlign; T <= seg + 8 * kAlign; T += kAlign) {
             const int64_t row_chunks = (g.L + T - 1) / T;
             const int64_t row_ctas = (row_chunks + kSeq - 1) / kSeq;
             if (row_chunks > 16384 || w * ncolseg > 16384) continue;   // aggregate arrays stay small

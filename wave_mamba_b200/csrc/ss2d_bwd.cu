@@ -22,6 +22,8 @@
 //                                        sums of the weight gradients
 //                  reduce             -> fixed-order sum of the partials (fp64): deterministic
 // Correctness first: one CTA per SM, scalar fp32 arithmetic, about 4x the forward's time.
+#define WM_SS2D_SEQ 4
+#define WM_SS2D_TP 16
 #include "ss2d_common.cuh"
 
 namespace wm {
@@ -82,7 +84,7 @@ __device__ __forceinline__ void store_tile_acc(const Geom &g, const TileGeom &tg
 #pragma unroll 1
         for (int r = 0; r < kD * kPos / kThreads; ++r) {
             const int idx = tid + r * kThreads;
-            const int d = idx >> 6, s = (idx >> 4) & 3, e = idx & 15;
+            const int d = idx >> 6, s = (idx & 63) / kTP, e = (idx & 63) % kTP;
             const int t = ti * kTP + e;
             if (t < strand_len(g, tg, s)) {
                 float *o = ob + (int64_t)d * g.L + strand_elem(g, tg, s, t);
@@ -507,6 +509,25 @@ ss2d_bwd_reduce_kernel(const float *__restrict__ part, int nparts, int k, float 
     else d_ds[(int64_t)k * kD + (i - kP_D)] = v;
 }
 
+// CTA ranges of the backward's own tile layout (kSeq = 4 strands per CTA) over the shared chunk plan
+static Launch make_launch_bwd(const Geom &g, std::initializer_list<int> dirs)
+{
+    Launch ln;
+    ln.ndirs = 0;
+    int acc = 0;
+    const int row_ctas = (g.row_chunks + kSeq - 1) / kSeq;
+    const int col_ctas = ((g.w + kSeq - 1) / kSeq) * g.ncolseg;
+    for (int k : dirs) {
+        ln.dir[ln.ndirs] = k;
+        ln.cta_begin[ln.ndirs] = acc;
+        acc += (k & 1) ? col_ctas : row_ctas;
+        ++ln.ndirs;
+    }
+    for (int i = ln.ndirs; i < 4; ++i) { ln.dir[i] = 0; ln.cta_begin[i] = acc; }
+    ln.cta_begin[4] = acc;
+    return ln;
+}
+
 struct BwdWorkspace {
     int64_t agg, hbuf_off, part_off, total;
 };
@@ -520,7 +541,7 @@ static BwdWorkspace plan_bwd(const Geom &g)
     for (int k = 0; k < 2; ++k) {
         const int64_t r = (int64_t)dir_chunks(g, k) * dir_chunk_len(g, k);
         rows = r > rows ? r : rows;
-        const int64_t c = (k & 1) ? g.col_ctas : g.row_ctas;
+        const int64_t c = (k & 1) ? (int64_t)((g.w + kSeq - 1) / kSeq) * g.ncolseg : (g.row_chunks + kSeq - 1) / kSeq;
         ctas = c > ctas ? c : ctas;
     }
     ws.hbuf_off = 4 * ws.agg;
@@ -585,8 +606,9 @@ extern "C" int wm_ss2d_core_bwd(const float *x, const float *x_proj_weight, cons
     rc = launch_carry(aggP, aggH, g, s);                    // aggH <- true initial states
     if (rc != WM_OK) return rc;
     {
-        dim3 grid(all.cta_begin[4], (unsigned)B);
-        ss2d_bwd_kernel<0><<<grid, kThreads, kBwdSmem, s>>>(bp, g, all);   // chunk aggregates of q (mirrored)
+        const Launch ball = make_launch_bwd(g, {0, 1, 2, 3});
+        dim3 grid(ball.cta_begin[4], (unsigned)B);
+        ss2d_bwd_kernel<0><<<grid, kThreads, kBwdSmem, s>>>(bp, g, ball);   // chunk aggregates of q (mirrored)
         WM_LAUNCH_OK("ss2d backward pass 1");
     }
     rc = launch_carry(aggP2, aggQ, g, s);                   // aggQ <- true incoming q
@@ -596,10 +618,11 @@ extern "C" int wm_ss2d_core_bwd(const float *x, const float *x_proj_weight, cons
         rc = launch_pass(2, fp, g, one, s);                 // states after every step of direction k
         if (rc != WM_OK) return rc;
         bp.accumulate = k > 0 ? 1 : 0;
-        dim3 grid(one.cta_begin[4], (unsigned)B);
-        ss2d_bwd_kernel<1><<<grid, kThreads, kBwdSmem, s>>>(bp, g, one);
+        const Launch bone = make_launch_bwd(g, {k});
+        dim3 grid(bone.cta_begin[4], (unsigned)B);
+        ss2d_bwd_kernel<1><<<grid, kThreads, kBwdSmem, s>>>(bp, g, bone);
         WM_LAUNCH_OK("ss2d backward main pass");
-        ss2d_bwd_reduce_kernel<<<(kPart + 255) / 256, 256, 0, s>>>(part, (int)(one.cta_begin[4] * B), k,
+        ss2d_bwd_reduce_kernel<<<(kPart + 255) / 256, 256, 0, s>>>(part, (int)(bone.cta_begin[4] * B), k,
                                                                    grad_x_proj_weight, grad_dt_projs_weight,
                                                                    grad_dt_projs_bias, grad_A_logs, grad_Ds);
         WM_LAUNCH_OK("ss2d backward reduce");

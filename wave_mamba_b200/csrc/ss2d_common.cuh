@@ -13,9 +13,19 @@ constexpr int kD = 64;       // d_inner
 constexpr int kN = 16;       // d_state
 constexpr int kK = 4;        // directions
 constexpr int kProj = 34;    // dt_rank(2) + 2*d_state
-constexpr int kSeq = 4;      // strands per CTA
-constexpr int kTP = 16;      // steps per tile
-constexpr int kPos = kSeq * kTP;  // 64 positions per tile
+// Tile layout of the including translation unit: a CTA owns kSeq neighbouring chunks ("strands") and
+// walks them kTP steps per tile (always 64 positions per tile).  The forward (ss2d.cu) uses 8 x 8 --
+// a scan thread then owns 4 channels x 8 states, which cuts the shared-memory bytes per state update
+// from 5 to 3 --, the backward (ss2d_bwd.cu) 4 x 16.  The chunk plan (Geom) does not depend on it.
+#ifndef WM_SS2D_SEQ
+#error "define WM_SS2D_SEQ / WM_SS2D_TP before including ss2d_common.cuh"
+#endif
+constexpr int kSeq = WM_SS2D_SEQ;   // strands per CTA
+constexpr int kTP = WM_SS2D_TP;     // steps per tile
+constexpr int kPos = kSeq * kTP;    // 64 positions per tile
+static_assert(kPos == 64 && kSeq % 4 == 0 && kTP % 4 == 0, "tile layout");
+constexpr int kAlign = 16;          // chunk lengths are multiples of 16 steps in every layout
+constexpr int kFwdSeq = 8;          // the forward's strands per CTA (Geom::row_ctas / col_ctas)
 constexpr int kXS = 72;      // xs row stride  [channel][position]  (== 8 mod 32: mma A loads)
 constexpr int kPJ = 36;      // pj row stride  [position][B16|C16|dt2|pad2]
 constexpr int kDD = 132;     // dd row stride  [position][channel] float2 (dt, u)  (== 4 mod 32)
@@ -245,27 +255,6 @@ __device__ __forceinline__ bool tile_is_vec(const Geom &g, const TileGeom &tg, i
     return g.vec_rows && (int64_t)(tg.chunk0 + kSeq - 1) * g.row_T + t_end <= g.L;
 }
 
-// Global offset (inside a channel plane) of the 16-byte chunk `cidx` (0..15) of a vec tile and
-// the smem position of its first element.  Rows: chunk = (s, v) -> 4 consecutive steps.
-// Columns: chunk = e -> the 4 strands of one image row.
-__device__ __forceinline__ void vec_chunk(const Geom &g, const TileGeom &tg, int ti, int cidx,
-                                          int64_t &goff, int &p0)
-{
-    if (!tg.col) {
-        const int s = cidx >> 2, v = cidx & 3;
-        const int64_t l0 = (int64_t)(tg.chunk0 + s) * g.row_T + ti * kTP;  // first step of the tile
-        // memory-ascending chunk v of the 16 elements of this strand's tile
-        goff = tg.fwd ? l0 + 4 * v : g.L - 1 - l0 - (kTP - 1) + 4 * v;
-        p0 = s * kTP + 4 * v;
-    } else {
-        const int e = cidx;
-        const int i = tg.fwd ? tg.t0 + ti * kTP + e : g.h - 1 - (tg.t0 + ti * kTP + e);
-        const int jlow = tg.fwd ? tg.chunk0 : g.w - kSeq - tg.chunk0;
-        goff = (int64_t)i * g.w + jlow;
-        p0 = e * kSeq;
-    }
-}
-
 // Per-thread addressing of the four 16-byte chunks it moves per full tile (x in, y out).
 struct ChunkMap {
     int64_t goff;      // element offset inside a channel plane for tile 0 (channel d0)
@@ -283,18 +272,22 @@ __device__ __forceinline__ ChunkMap make_chunk_map(const Geom &g, const TileGeom
     cm.d0 = tid >> 4;
     int p0;
     if (!tg.col) {
-        const int s = cidx >> 2, v = cidx & 3;
+        // rows: a strand's kTP steps are kTP/4 chunks of 16 bytes
+        constexpr int kCps = kTP / 4;
+        const int s = cidx / kCps, v = cidx % kCps;
         const int64_t l0 = (int64_t)(tg.chunk0 + s) * g.row_T;
         cm.goff = tg.fwd ? l0 + 4 * v : g.L - 1 - l0 - (kTP - 1) + 4 * v;
         cm.gstep = tg.fwd ? kTP : -kTP;
         p0 = s * kTP + 4 * v;
     } else {
-        const int e = cidx;
+        // columns: one image row of the kSeq adjacent columns is kSeq/4 chunks of 16 bytes
+        constexpr int kCpr = kSeq / 4;
+        const int e = cidx / kCpr, hv = cidx % kCpr;
         const int i = tg.fwd ? tg.t0 + e : g.h - 1 - tg.t0 - e;
         const int jlow = tg.fwd ? tg.chunk0 : g.w - kSeq - tg.chunk0;
-        cm.goff = (int64_t)i * g.w + jlow;
+        cm.goff = (int64_t)i * g.w + jlow + 4 * hv;
         cm.gstep = tg.fwd ? (int64_t)kTP * g.w : -(int64_t)kTP * g.w;
-        p0 = e * kSeq;
+        p0 = e * kSeq + 4 * hv;
     }
     cm.xs_dst = (uint32_t)__cvta_generic_to_shared(xs + cm.d0 * kXS + p0);
     cm.ys_idx = cm.d0 * kYS + p0;
@@ -317,7 +310,7 @@ __device__ __forceinline__ void load_tile(const Geom &g, const TileGeom &tg, con
 #pragma unroll 1
         for (int r = 0; r < kD * kPos / kThreads; ++r) {
             const int idx = tid + r * kThreads;      // 0..4095 = (d, s, e)
-            const int d = idx >> 6, s = (idx >> 4) & 3, e = idx & 15;
+            const int d = idx >> 6, s = (idx & 63) / kTP, e = (idx & 63) % kTP;
             const int t = ti * kTP + e;
             float v = 0.0f;
             if (t < strand_len(g, tg, s)) v = __ldg(xb + (int64_t)d * g.L + strand_elem(g, tg, s, t));
@@ -342,7 +335,7 @@ __device__ __forceinline__ void store_tile(const Geom &g, const TileGeom &tg, co
 #pragma unroll 1
         for (int r = 0; r < kD * kPos / kThreads; ++r) {
             const int idx = tid + r * kThreads;
-            const int d = idx >> 6, s = (idx >> 4) & 3, e = idx & 15;
+            const int d = idx >> 6, s = (idx & 63) / kTP, e = (idx & 63) % kTP;
             const int t = ti * kTP + e;
             if (t < strand_len(g, tg, s))
                 ob[(int64_t)d * g.L + strand_elem(g, tg, s, t)] = ys[d * kYS + tile_pos(tg, s, e)];
