@@ -10,9 +10,9 @@
 //              tools/probes/tma_probe.cu, a box at x0-1 raises an illegal-instruction fault.)
 //   warps 0-3  LayerNorm over channels per halo position, written straight into the UMMA K-major
 //              operand layout [ci/4][position][ci%4] as tf32 hi and lo = a - hi (3xTF32 split)
-//   warp 12    one thread issues tcgen05.mma kind::tf32 (M=128 positions, N=64 = [w_hi | w_lo] of a
+//   warp 20    one thread issues tcgen05.mma kind::tf32 (M=128 positions, N=64 = [w_hi | w_lo] of a
 //              32-channel output group, K=32 in 4 steps) into TMEM, double-buffered per group
-//   warps 4-11 TMEM -> registers -> +bias, zero outside the image (the depthwise conv pads the 1x1
+//   warps 4-19 TMEM -> registers -> +bias, zero outside the image (the depthwise conv pads the 1x1
 //              OUTPUT) -> shared [channel][row][36]; then the depthwise 3x3 + SiLU from shared
 //              memory, four adjacent pixels per thread on the packed FP32 pipe (FFMA2), 16-byte stores
 //
@@ -39,10 +39,10 @@ constexpr int kPSW = 36;                       // row stride of the 1x1 output t
 constexpr int kPS = kPSW * kBoxH;              // 360 floats per channel
 constexpr int kMPos = 384;                     // three M=128 MMAs
 constexpr int kCin = 32;
-constexpr int kWarpsA = 4, kWarpsB = 8;
+constexpr int kWarpsA = 4, kWarpsB = 16;
 constexpr int kThreadsA = 32 * kWarpsA, kThreadsB = 32 * kWarpsB;
 constexpr int kWarpMma = kWarpsA + kWarpsB;
-constexpr int kThreads = 32 * (kWarpMma + 1);  // 416
+constexpr int kThreads = 32 * (kWarpMma + 1);  // 672
 constexpr int kAccCols = 3 * 64;               // one accumulator set: 3 M tiles x [32 hi-sum | 32 lo]
 constexpr uint32_t kBoxBytes = kRaw * kCin * 4;
 
@@ -307,9 +307,12 @@ pw_dw_tc5_kernel(const __grid_constant__ CUtensorMap tmap, const Args a)
         }
     } else {
         // =========================== epilogue + depthwise 3x3 ================================
-        const int e = warp - kWarpsA;                  // 0..7
-        const int quarter = warp & 3, chalf = e >> 2;  // TMEM lane quarter, 16-channel half of the group
-        const int tb = tid - kThreadsA;                // 0..255
+        // 16 warps (the two phases are latency-bound: more warps hide the TMEM / MUFU / shared latencies)
+        const int e = warp - kWarpsA;                  // 0..15
+        // TMEM lane quarter (= warp % 4, the hardware rule), 16-channel half of the group, M-tile set:
+        // set 0 drains M tiles 0 and 1, set 1 M tile 2 (positions 256..339)
+        const int quarter = warp & 3, chalf = (e >> 2) & 1, mset = e >> 3;
+        const int tb = tid - kThreadsA;                // 0..511
         uint32_t gcount = 0;
         const bool timed = a.dbg != nullptr && tb == 0;
         long long tbb[3] = {0, 0, 0}, t0 = timed ? clock64() : 0, tp = t0;
@@ -326,7 +329,7 @@ pw_dw_tc5_kernel(const __grid_constant__ CUtensorMap tmap, const Args a)
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 WM_TICKB(0);
 #pragma unroll 1
-                for (int mt = 0; mt < 3; ++mt) {
+                for (int mt = mset ? 2 : 0; mt < (mset ? 3 : 2); ++mt) {
                     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
                                            (uint32_t)(buf * kAccCols + mt * 64 + chalf * 16);
                     uint32_t acc[16], part[16];
@@ -352,17 +355,18 @@ pw_dw_tc5_kernel(const __grid_constant__ CUtensorMap tmap, const Args a)
                 named_bar(2, kThreadsB);               // ps of this group is complete
                 WM_TICKB(1);
 
-                // depthwise 3x3 (+ SiLU): thread = (channel, 4 adjacent columns), 8 rows, sliding window of
-                // three input rows held as packed pairs (FFMA2: two outputs per instruction).  Per input
-                // row one LDS.128 + one LDS.64 bring the 6 values (v0..v5) four outputs need.
+                // depthwise 3x3 (+ SiLU): thread = (channel, 4 adjacent columns, 4 of the 8 rows), sliding
+                // window of three input rows held as packed pairs (FFMA2: two outputs per instruction).
+                // Per input row one LDS.128 + one LDS.64 bring the 6 values (v0..v5) four outputs need.
                 {
-                    const int cl = tb >> 3, j4 = (tb & 7) * 4;
+                    const int rhalf = tb >> 8;                       // rows 0-3 or 4-7 of the tile
+                    const int cl = (tb & 255) >> 3, j4 = (tb & 7) * 4;
                     const int co = g * 32 + cl;
                     f32x2 k2[9];
 #pragma unroll
                     for (int t = 0; t < 9; ++t) { const float kv = dww[co * 9 + t]; k2[t] = pack2(kv, kv); }
                     const float bias = dwb[co];
-                    const float *pc = ps + cl * kPS + j4;
+                    const float *pc = ps + cl * kPS + rhalf * 4 * kPSW + j4;
                     // packed pairs of one input row: P0=(v0,v1) P1=(v2,v3) P2=(v4,v5) Q0=(v1,v2) Q1=(v3,v4)
                     f32x2 P[3][3], Q[3][2];
                     auto load_row = [&](int r, int slot) {
@@ -373,10 +377,10 @@ pw_dw_tc5_kernel(const __grid_constant__ CUtensorMap tmap, const Args a)
                     };
                     load_row(0, 0);
                     load_row(1, 1);
-                    const int gx = tx0 + j4;
-                    float *yo = a.y + ((int64_t)b * COUT + co) * hw + (int64_t)ty0 * w + gx;
+                    const int gx = tx0 + j4, gy0 = ty0 + rhalf * 4;
+                    float *yo = a.y + ((int64_t)b * COUT + co) * hw + (int64_t)gy0 * w + gx;
 #pragma unroll
-                    for (int row = 0; row < kTH; ++row) {
+                    for (int row = 0; row < 4; ++row) {
                         load_row(row + 2, (row + 2) % 3);
                         f32x2 oa = pack2(bias, bias), ob = oa;
 #pragma unroll
@@ -394,7 +398,7 @@ pw_dw_tc5_kernel(const __grid_constant__ CUtensorMap tmap, const Args a)
                             o2 = __fdividef(o2, 1.0f + __expf(-o2)); o3 = __fdividef(o3, 1.0f + __expf(-o3));
                         }
                         // w % 4 == 0 and gx % 4 == 0: the four columns are inside the image or outside together
-                        if (gx < w && ty0 + row < h)
+                        if (gx < w && gy0 + row < h)
                             *reinterpret_cast<float4 *>(yo + (int64_t)row * w) = make_float4(o0, o1, o2, o3);
                     }
                 }
