@@ -29,6 +29,8 @@
 //   warps 4-11  epilogue: tcgen05.ld -> bias or k3*sigmoid(k2+b) -> NCHW / channel-quad stores; the
 //               accumulators are double-buffered in TMEM when 2 x columns <= 512 (all variants but
 //               the gated 64->64 and the 32->96 one), so the epilogue overlaps the next tile's MMAs
+#include <stdlib.h>
+
 #include <atomic>
 
 #include "tc5_common.cuh"
@@ -72,6 +74,7 @@ struct Args {
     // in_c4 needs Ca == CIN (no second input); used between PAConv.k3 and k4.
     int in_c4, out_c4;
     unsigned int *err;       // pipeline error word (mbar_wait_flag)
+    int wsplit;              // bulk copies per weight chunk (1, 2, 4 or 8)
 };
 
 template <int CIN, int COUT, bool GATE>
@@ -257,9 +260,12 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
                         const int st = cnt % kStages;
                         mbar_wait_flag(wempty(st), ((cnt / kStages) & 1u) ^ 1u, a.err, (4u << 24) | (2u << 16) | (cnt & 0xffffu));
                         mbar_expect_tx(wfull(st), (uint32_t)C::kChunkBytes);
-                        bulk_g2s(smem_u32(wbuf + st * C::kChunkF4),
-                                 a.packed + (int64_t)(tap * NCH + part) * C::kChunkF4,
-                                 (uint32_t)C::kChunkBytes, wfull(st));
+                        // the chunk as `wsplit` bulk copies in flight at once (all complete on wfull)
+                        const float4 *src = a.packed + (int64_t)(tap * NCH + part) * C::kChunkF4;
+                        const uint32_t dst = smem_u32(wbuf + st * C::kChunkF4);
+                        const uint32_t piece = (uint32_t)C::kChunkBytes / (uint32_t)a.wsplit;
+                        for (int q = 0; q < a.wsplit; ++q)
+                            bulk_g2s(dst + q * piece, reinterpret_cast<const char *>(src) + q * piece, piece, wfull(st));
                     }
                 }
             }
@@ -533,6 +539,12 @@ extern "C" int wm_conv3x3_ex_fwd(const float *in_a, int64_t a_bstride, int64_t C
     a.dbg = g_dbg.load();
     a.err = pipeline_err_word();
     WM_REQUIRE(a.err != nullptr, "wm_conv3x3_fwd: no CUDA device");
+    static const int wsplit = []() {   // developer switch WM_CONV_WSPLIT (power of two <= 8)
+        const char *e = getenv("WM_CONV_WSPLIT");
+        const int v = e ? atoi(e) : 1;
+        return (v == 1 || v == 2 || v == 4 || v == 8) ? v : 1;
+    }();
+    a.wsplit = wsplit;
     a.in_a = in_a; a.a_bstride = a_bstride; a.Ca = (int)Ca; a.in_b = in_b; a.b_bstride = b_bstride;
     a.chan_map = chan_map; a.packed = static_cast<const float4 *>(packed); a.bias = bias;
     a.gate_bias = gate_bias; a.out = out; a.h = (int)h; a.w = (int)w;

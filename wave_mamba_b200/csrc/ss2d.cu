@@ -440,23 +440,6 @@ ss2d_pass_kernel(const Params prm, const Geom g, const Launch ln)
         tg.maxlen = g.row_T;
     }
     const int b = blockIdx.y;
-    // Two CTAs share an SM.  Launched together they run in lockstep -- both in the MUFU-bound scan phase,
-    // then both in the projection / delta / store phases with the MUFU idle (measured: XU 53 % although
-    // the overlapped scan phases saturate it).  The second CTA to arrive on an SM therefore starts half
-    // a tile period late, so that one CTA's scan overlaps the other's tensor/FMA phases.
-    if (prm.phase_ctr != nullptr) {
-        __shared__ int late;
-        if (threadIdx.x == 0) {
-            unsigned smid;
-            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            late = atomicAdd(prm.phase_ctr + (smid & 255u), 1) == 1 ? 1 : 0;
-        }
-        __syncthreads();
-        if (late) {
-            const long long t0 = clock64();
-            while (clock64() - t0 < prm.phase_delay) __nanosleep(256);
-        }
-    }
     if (tg.col) run_cta<FINAL, kSeq, TIMED, CKPT>(prm, g, tg, smem, b);
     else if (tg.fwd) run_cta<FINAL, 1, TIMED, CKPT>(prm, g, tg, smem, b);
     else run_cta<FINAL, -1, TIMED, CKPT>(prm, g, tg, smem, b);
@@ -673,9 +656,8 @@ Geom make_geom(int64_t B, int64_t h, int64_t w)
 }
 
 struct Workspace {
-    int64_t planes_off, aggP_off, aggH_off, ctr_off, total;
+    int64_t planes_off, aggP_off, aggH_off, total;
 };
-constexpr int64_t kCtrBytes = 2 * 256 * sizeof(int);   // per-SM arrival counters of pass 1 and pass 2
 
 Workspace plan_workspace(const Geom &g)
 {
@@ -685,8 +667,7 @@ Workspace plan_workspace(const Geom &g)
     ws.planes_off = 0;
     ws.aggP_off = planes_bytes;
     ws.aggH_off = planes_bytes + agg_bytes;
-    ws.ctr_off = planes_bytes + 2 * agg_bytes;
-    ws.total = ws.ctr_off + align_up(kCtrBytes, 256);
+    ws.total = planes_bytes + 2 * agg_bytes;
     return ws;
 }
 
@@ -767,15 +748,6 @@ int run_dirs(const float *x, const float *x_proj_weight, const float *dt_projs_w
     prm.aggH = reinterpret_cast<float *>(wsb + ws.aggH_off);
     prm.dbg = g_dbg.load();
     prm.hbuf = nullptr;
-    // de-phasing of the two CTAs per SM (WM_SS2D_PHASE=<cycles>, 0 disables; developer switch)
-    static const int phase_cycles = []() {
-        const char *e = getenv("WM_SS2D_PHASE");
-        return e ? atoi(e) : 7000;
-    }();
-    int *ctr = reinterpret_cast<int *>(wsb + ws.ctr_off);
-    prm.phase_delay = phase_cycles;
-    prm.phase_ctr = phase_cycles > 0 ? ctr : nullptr;
-    if (prm.phase_ctr) WM_CUDA_OK(cudaMemsetAsync(ctr, 0, kCtrBytes, s));
     const size_t smem_bytes = kSmemBytes + (size_t)g_dbg_pad.load();
 
     auto pass1 = prm.dbg ? ss2d_pass_kernel<false, true> : ss2d_pass_kernel<false, false>;
@@ -790,7 +762,6 @@ int run_dirs(const float *x, const float *x_proj_weight, const float *dt_projs_w
     dim3 cgrid(kChains / 32, kK, (unsigned)B);
     ss2d_carry_kernel<<<cgrid, 32 * kCarryWarps, 0, s>>>(prm.aggP, prm.aggH, g);
     WM_LAUNCH_OK("ss2d carry");
-    if (prm.phase_ctr) prm.phase_ctr += 256;
     pass2<<<grid, kThreads, smem_bytes, s>>>(prm, g, ln);
     WM_LAUNCH_OK("ss2d pass 2");
     return WM_OK;

@@ -76,8 +76,6 @@ struct Params {
     float *aggP;               // (B,4,max_chunks,1024)
     float *aggH;               // (B,4,max_chunks,1024)  pass 1: local end state; after carry: h_in
     long long *dbg;            // developer aid (wm_ss2d_debug_timing): per-CTA phase cycle sums
-    int *phase_ctr;            // per-SM arrival counters of this launch (null: no de-phasing), see ss2d.cu
-    int phase_delay;           // cycles the second CTA of an SM waits before its first tile
     float *hbuf;               // checkpoint pass (backward): state after every step of ONE direction,
                                // [b][chunk][step][1024 chains]
 };
