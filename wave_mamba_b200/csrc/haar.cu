@@ -79,31 +79,36 @@ __device__ __forceinline__ void haar_synthesis(float p, float q, float r, float 
     oo = ((p + q) + r) + s;
 }
 
+// blockIdx.y = plane (b, c); the x dimension strides over the (row, 4-pixel group) items of the plane
+// with 32-bit index arithmetic (the flat 64-bit div/mod chain of the first version cost more
+// instructions than the data movement: 118 M vs the DWT's 70 M at the 4K level-1 size).
 __global__ void __launch_bounds__(kThreads)
 iwt_vec_kernel(const float *__restrict__ low, int64_t low_bstride, const float *__restrict__ high,
-               int64_t high_bstride, float *__restrict__ y, int64_t B, int C, int h, int w4)
+               int64_t high_bstride, float *__restrict__ y, int C, int h, int w4)
 {
-    const int64_t w = 4 * (int64_t)w4, hw = (int64_t)h * w;
-    const int64_t items = B * C * h * w4;
-    const int64_t stride = (int64_t)gridDim.x * kThreads;
-    for (int64_t it = (int64_t)blockIdx.x * kThreads + threadIdx.x; it < items; it += stride) {
-        int64_t t = it;
-        const int q = (int)(t % w4); t /= w4;
-        const int i = (int)(t % h);  t /= h;
-        const int c = (int)(t % C);
-        const int64_t b = t / C;
-        const int64_t in_off = (int64_t)i * w + 4 * q;
-        const float4 vp = ld_stream4(low + b * low_bstride + c * hw + in_off);
-        const float *hb = high + b * high_bstride + in_off;
-        const float4 vq = ld_stream4(hb + (int64_t)c * hw);
-        const float4 vr = ld_stream4(hb + (int64_t)(C + c) * hw);
-        const float4 vs = ld_stream4(hb + (int64_t)(2 * C + c) * hw);
+    const int w = 4 * w4;
+    const int64_t hw = (int64_t)h * w;
+    const int plane = blockIdx.y;
+    const int b = plane / C, c = plane - b * C;
+    const float *lp = low + (int64_t)b * low_bstride + (int64_t)c * hw;
+    const float *hq = high + (int64_t)b * high_bstride + (int64_t)c * hw;
+    const float *hr = hq + (int64_t)C * hw, *hs = hq + 2 * (int64_t)C * hw;
+    float *yp = y + (int64_t)plane * 4 * hw;
+    const int items = h * w4;
+    const int stride = gridDim.x * kThreads;
+    for (int it = blockIdx.x * kThreads + threadIdx.x; it < items; it += stride) {
+        const int i = it / w4, q = it - i * w4;
+        const int in_off = i * w + 4 * q;
+        const float4 vp = ld_stream4(lp + in_off);
+        const float4 vq = ld_stream4(hq + in_off);
+        const float4 vr = ld_stream4(hr + in_off);
+        const float4 vs = ld_stream4(hs + in_off);
         float4 e0, e1, o0, o1;  // even output row (8 floats) / odd output row
         haar_synthesis(vp.x * 0.5f, vq.x * 0.5f, vr.x * 0.5f, vs.x * 0.5f, e0.x, o0.x, e0.y, o0.y);
         haar_synthesis(vp.y * 0.5f, vq.y * 0.5f, vr.y * 0.5f, vs.y * 0.5f, e0.z, o0.z, e0.w, o0.w);
         haar_synthesis(vp.z * 0.5f, vq.z * 0.5f, vr.z * 0.5f, vs.z * 0.5f, e1.x, o1.x, e1.y, o1.y);
         haar_synthesis(vp.w * 0.5f, vq.w * 0.5f, vr.w * 0.5f, vs.w * 0.5f, e1.z, o1.z, e1.w, o1.w);
-        float *out = y + ((b * C + c) * (2 * (int64_t)h) + 2 * i) * (2 * w) + 8 * q;
+        float *out = yp + (int64_t)(2 * i) * (2 * w) + 8 * q;
         st_stream4(out, e0);
         st_stream4(out + 4, e1);
         st_stream4(out + 2 * w, o0);
@@ -190,10 +195,17 @@ extern "C" int wm_iwt_haar_fwd(const float *low, int64_t low_bstride, const floa
     cudaStream_t s = (cudaStream_t)stream;
     const bool vec = (w % 4 == 0) && aligned16(low) && aligned16(high) && aligned16(y) &&
                      (low_bstride % 4 == 0) && (high_bstride % 4 == 0);
-    if (vec) {
+    if (vec && B * C <= 65535 && h * (w / 4) < ((int64_t)1 << 30)) {
         const int w4 = (int)(w / 4);
-        iwt_vec_kernel<<<stream_grid(B * C * h * w4), kThreads, 0, s>>>(
-            low, low_bstride, high, high_bstride, y, B, (int)C, (int)h, w4);
+        const int64_t planes = B * C;
+        const int64_t per_plane = (h * w4 + kThreads - 1) / kThreads;
+        int64_t gx = ((int64_t)sm_count() * 8 + planes - 1) / planes;      // ~8 CTAs per SM in total
+        gx = gx < per_plane ? gx : per_plane;
+        dim3 grid((unsigned)(gx > 0 ? gx : 1), (unsigned)planes);
+        iwt_vec_kernel<<<grid, kThreads, 0, s>>>(low, low_bstride, high, high_bstride, y, (int)C, (int)h, w4);
+    } else if (vec) {
+        iwt_scalar_kernel<<<stream_grid(B * C * h * w), kThreads, 0, s>>>(
+            low, low_bstride, high, high_bstride, y, B, (int)C, (int)h, (int)w);
     } else {
         iwt_scalar_kernel<<<stream_grid(B * C * h * w), kThreads, 0, s>>>(
             low, low_bstride, high, high_bstride, y, B, (int)C, (int)h, (int)w);
