@@ -8,7 +8,10 @@ baseline/_ref is a verbatim copy of the reference tree staged by tools/stage_ref
     inference_wavemamba.py:71-131: build, load, pad to x128, restoration_network, crop, tensor2img,
     PSNR/SSIM, imwrite) on two synthetic PNG pairs; the written images must equal
     wave_mamba_b200.enhance_bgr_u8 byte for byte and the printed PSNRs the oracle's within 1e-3 dB;
-  * build_model(FeMaSRModel) -> feed_data -> test()   (basicsr/models/femasr_model.py:27,187-199).
+  * build_model(FeMaSRModel) -> feed_data -> test()   (basicsr/models/femasr_model.py:27,187-199);
+  * build_model(FeMaSRModel, is_train=True) -> feed_data -> optimize_parameters()  (the body of
+    basicsr/train.py's loop, femasr_model.py:157-185) with the optimiser / scheduler / loss options
+    of options/train_wavemamba_lol.yml.
 
 Stand-ins only for packages that are not installed in this image (timm, lmdb, pyiqa, torchmetrics, skimage).
 """
@@ -115,3 +118,46 @@ print('validation path ok', tuple(model.output.shape))
     err = (y - want).abs().max().item()
     print(f"FeMaSRModel.test(): max abs err vs oracle {err:.3e}")
     assert err <= 2e-4
+
+
+@needs_ref
+def test_femasr_model_training_step_on_the_plugin(tmp_path, dev):
+    """The reference's own training step driving the plugin: init_training_settings (losses, AdamW,
+    CosineAnnealingRestartCyclicLR as options/train_wavemamba_lol.yml:73-97), feed_data,
+    optimize_parameters twice (zero_grad -> net_g(lq) -> L1 (+FFT loss) -> backward -> step),
+    update_learning_rate; the loss is finite and the weights move."""
+    code = f"""
+import sys, torch
+sys.path.insert(0, {ROOT!r})
+from tools import ref_overlay, ref_shims
+from tools.synth import synth_lowlight
+ref_overlay.make_overlay({REF!r}, {str(tmp_path / 'overlay')!r})
+ref_shims.install({str(tmp_path / 'overlay')!r})
+from basicsr.models import build_model
+train = dict(optim_g=dict(type='AdamW', lr=1e-4, weight_decay=1e-3, betas=[0.9, 0.99]),
+             scheduler=dict(type='CosineAnnealingRestartCyclicLR', periods=[100, 100000], restart_weights=[1, 1],
+                            eta_mins=[0.0001, 0.0000001]),
+             total_iter=101000, warmup_iter=-1,
+             pixel_opt=dict(type='L1Loss', loss_weight=1.0, reduction='mean'),
+             fft_opt=dict(type='FFTLoss', loss_weight=0.1, reduction='mean'))
+opt = dict(model_type='FeMaSRModel', num_gpu=1, is_train=True, dist=False, val=dict(), train=train,
+           network_g=dict(type='WaveMamba', in_chn=3, wf=32, n_l_blocks=[1, 2, 4], n_h_blocks=[1, 1, 2], ffn_scale=2.0),
+           path=dict(pretrain_network_g={CKPT!r}, strict_load=True))
+model = build_model(opt)
+assert type(model.net_g).__mro__[1].__module__ == 'wave_mamba_b200.arch'
+before = [p.detach().clone() for p in model.net_g.parameters()]
+x, gt = synth_lowlight(2, 64, 64, 11)
+losses = []
+for it in range(2):
+    model.update_learning_rate(it + 1, warmup_iter=-1)
+    model.feed_data(dict(lq=x, gt=gt))
+    model.optimize_parameters(it + 1)
+    losses.append({{k: float(v) for k, v in model.log_dict.items()}})
+moved = sum(int(not torch.equal(a, b)) for a, b in zip(before, model.net_g.parameters()))
+print('losses', losses, 'moved', moved, 'of', len(before))
+assert all(v == v and abs(v) < 1e6 for d in losses for v in d.values())
+assert moved == len(before)
+"""
+    run = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900)
+    assert run.returncode == 0, run.stdout[-1500:] + run.stderr[-3000:]
+    print(run.stdout.strip().splitlines()[-1])

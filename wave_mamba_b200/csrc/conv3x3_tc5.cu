@@ -83,7 +83,11 @@ struct Cfg {
     static constexpr int NTAPS = GATE ? 10 : 9;
     static constexpr int kChunkF4 = kKcSlab * 2 * COUT;        // float4 per weight chunk
     static constexpr int kChunkBytes = kChunkF4 * 16;
-    static constexpr int kStages = COUT >= 96 ? 3 : 4;         // weight ring depth
+    // weight ring depth: a stage is refilled only after its MMAs completed, and the refill (commit ->
+    // mbarrier -> producer -> bulk copy -> mbarrier) takes ~3 k cycles, about 3.5 chunks of MMA work:
+    // 4 stages leave the MMA thread waiting ~360 cycles per chunk (measured), 8 stages hide it --
+    // affordable where a chunk is 8 KB (COUT = 32); the 64- and 96-output variants fill shared memory
+    static constexpr int kStages = COUT >= 96 ? 3 : COUT <= 32 ? 8 : 4;
     static constexpr int kColsBuf = 4 * COUT * (GATE ? 2 : 1); // TMEM columns of one accumulator set
     static constexpr int NACC = 2 * kColsBuf <= 512 ? 2 : 1;
     static constexpr int kColsNeed = NACC * kColsBuf;
