@@ -245,7 +245,10 @@ __device__ __forceinline__ void run_cta(const Params &prm, const Geom &g, const 
     // every SM sub-partition hosts one warp of each kind, so the tensor pipes stay balanced
     const int mt = warp & 3, nh = warp >> 2;
     int nt_list[3], nt_count;
-    if (FINAL) {
+    // pass 1 of the replay scheme also projects C: its [pj | dd] tiles are what pass 2 consumes
+    const bool dump = !FINAL && !CKPT && prm.tiles != nullptr;
+    const int64_t slot0 = ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * prm.tile_stride;
+    if (FINAL || dump) {
         nt_list[0] = nh ? 2 : 0; nt_list[1] = nh ? 3 : 1; nt_list[2] = 4; nt_count = nh ? 2 : 3;
     } else {
         nt_list[0] = nh ? 4 : 0; nt_list[1] = 1; nt_list[2] = 1; nt_count = nh ? 1 : 2;
@@ -343,6 +346,12 @@ __device__ __forceinline__ void run_cta(const Params &prm, const Geom &g, const 
         WM_TICK(2);
 
         if (ti + 1 < ntiles) load_tile(g, tg, cm, ti + 1, xb, xs);
+        if (dump) {   // pj and dd are adjacent in shared memory: one 43 KB block per tile, streamed out
+            float *dst = prm.tiles + (slot0 + ti) * (int64_t)kTileFloats;
+            const float *src = smem + kOffPj;
+            for (int i = tid; i < kTileFloats / 4; i += kThreads)
+                st_stream4(dst + 4 * i, *reinterpret_cast<const float4 *>(src + 4 * i));
+        }
 
         // ---- recurrence over the 16 steps of this tile        (reference :465-471) --------
         {
@@ -411,6 +420,153 @@ __device__ __forceinline__ void run_cta(const Params &prm, const Geom &g, const 
             hp4[1] = make_float4(hv[4], hv[5], hv[6], hv[7]);
         }
     }
+}
+
+// Pass 2 of the replay scheme: the projected tiles [pj | dd] written by pass 1 are read back
+// (double-buffered 16-byte cp.async, the next tile in flight during the scan) instead of recomputing the
+// projection, the softplus and the (dt, u) interleave -- about a third of a recomputing pass 2.  The HBM
+// traffic this adds (43 KB per 64 positions, written once and read once) rides on bandwidth the
+// MUFU-bound scan leaves idle.
+constexpr int kR_Buf = 0;                               // two [pj | dd] buffers
+constexpr int kR_Ys = 2 * kTileFloats;
+constexpr int kR_Floats = kR_Ys + kD * kYS;
+constexpr size_t kReplaySmem = sizeof(float) * kR_Floats;   // 102,656 B -> 2 CTAs per SM
+
+template <int DP, bool TIMED>
+__device__ __forceinline__ void run_cta_replay(const Params &prm, const Geom &g, const TileGeom &tg,
+                                               float *smem, int b)
+{
+    float *ys = smem + kR_Ys;
+    const int tid = threadIdx.x;
+    const int k = tg.k;
+    const int ntiles = (tg.maxlen + kTP - 1) / kTP;
+    const ChunkMap cm = make_chunk_map(g, tg, smem);   // store addressing only
+
+    const int s = tid >> 5, cq = (tid & 31) >> 1;
+    const bool half = (tid & 1) != 0;
+    const int hoff = half ? 8 : 0;
+    f32x2 A2[kCh][4];
+#pragma unroll
+    for (int c = 0; c < kCh; ++c)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float *ap = prm.A_logs + (int64_t)(k * kD + kCh * cq + c) * kN + hoff + 2 * j;
+            A2[c][j] = pack2(-expf(__ldg(ap)) * 1.4426950408889634f,
+                             -expf(__ldg(ap + 1)) * 1.4426950408889634f);
+        }
+    const int my_d = kCh * cq + (half ? 2 : 0);
+    const float my_skip[2] = {__ldg(prm.Ds + k * kD + my_d), __ldg(prm.Ds + k * kD + my_d + 1)};
+    const int my_len = strand_len(g, tg, s);
+    const int my_chunk = tg.col ? (tg.chunk0 + s) * g.ncolseg + tg.seg : tg.chunk0 + s;
+    const int64_t agg_off =
+        (((int64_t)b * kK + k) * g.max_chunks + my_chunk) * kChains + (int64_t)(kCh * cq) * kN + hoff;
+    f32x2 hst[kCh][4];
+#pragma unroll
+    for (int c = 0; c < kCh; ++c)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) hst[c][j] = pack2(0.0f, 0.0f);
+    if (my_len > 0 && my_chunk > 0) {
+#pragma unroll
+        for (int c = 0; c < kCh; ++c) {
+            const float4 *hp = reinterpret_cast<const float4 *>(prm.aggH + agg_off + c * kN);
+            const float4 f0 = hp[0], f1 = hp[1];
+            hst[c][0] = pack2(f0.x, f0.y); hst[c][1] = pack2(f0.z, f0.w);
+            hst[c][2] = pack2(f1.x, f1.y); hst[c][3] = pack2(f1.z, f1.w);
+        }
+    }
+    const int p0 = tile_pos(tg, s, 0);
+    float *ys0 = ys + my_d * kYS + p0;
+    float *oplane = prm.planes + (((int64_t)k * g.B + b) * kD) * g.L;
+    const int64_t slot0 = ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * prm.tile_stride;
+    const uint32_t buf_s = (uint32_t)__cvta_generic_to_shared(smem + kR_Buf);
+
+    auto fetch = [&](int ti) {
+        const float *src = prm.tiles + (slot0 + ti) * (int64_t)kTileFloats;
+        const uint32_t dst = buf_s + (uint32_t)(ti & 1) * kTileFloats * 4u;
+        for (int i = tid; i < kTileFloats / 4; i += kThreads)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * i), "l"(src + 4 * i) : "memory");
+        cp_async_commit();
+    };
+    long long tacc[5] = {0, 0, 0, 0, 0}, tprev = 0;
+    const bool timed = TIMED && tid == 0;
+#define WM_TICK(k) \
+    if (timed) { const long long tn = clock64(); tacc[k] += tn - tprev; tprev = tn; }
+    if (timed) tprev = clock64();
+
+    fetch(0);
+#pragma unroll 1
+    for (int ti = 0; ti < ntiles; ++ti) {
+        cp_async_wait_all();
+        __syncthreads();                 // tile ti landed; the other buffer and ys are free again
+        WM_TICK(0);
+        if (ti + 1 < ntiles) fetch(ti + 1);
+        const float *pj = smem + kR_Buf + (ti & 1) * kTileFloats;
+        const float *dd = pj + kPos * kPJ;
+        const float *dd0 = dd + p0 * kDD + 2 * kCh * cq;
+        const float *pj0 = pj + p0 * kPJ + hoff;
+        {
+            const int nvalid = my_len - ti * kTP;          // warp-uniform (a warp is one strand)
+            float sdt[kCh];
+            if (nvalid >= kTP) {
+                StepIn<true> cur, nxt;
+                cur.load(dd0, pj0);
+#pragma unroll
+                for (int e = 0; e < kTP; ++e) {
+                    if (e + 1 < kTP) nxt.load(dd0 + (e + 1) * DP * kDD, pj0 + (e + 1) * DP * kPJ);
+                    scan_step<true>(cur, ys0 + e * DP, hst, A2, sdt, my_skip, half);
+                    cur = nxt;
+                }
+            } else {
+#pragma unroll 1
+                for (int e = 0; e < nvalid; ++e) {
+                    StepIn<true> cur;
+                    cur.load(dd0 + e * DP * kDD, pj0 + e * DP * kPJ);
+                    scan_step<true>(cur, ys0 + e * DP, hst, A2, sdt, my_skip, half);
+                }
+            }
+        }
+        __syncthreads();
+        WM_TICK(3);
+        store_tile(g, tg, cm, ti, oplane, ys);
+        WM_TICK(4);
+    }
+#undef WM_TICK
+    if (timed) {
+        long long *o = prm.dbg + (blockIdx.x & 4095) * 6;
+        for (int i = 0; i < 5; ++i) o[i] = tacc[i];
+        o[5] = ntiles;
+    }
+}
+
+template <bool TIMED>
+__global__ void __launch_bounds__(kThreads, 2)
+ss2d_replay_kernel(const Params prm, const Geom g, const Launch ln)
+{
+    extern __shared__ __align__(16) float smem[];
+    int k = ln.dir[0], begin = 0;
+    if (ln.ndirs > 1 && (int)blockIdx.x >= ln.cta_begin[1]) { k = ln.dir[1]; begin = ln.cta_begin[1]; }
+    if (ln.ndirs > 2 && (int)blockIdx.x >= ln.cta_begin[2]) { k = ln.dir[2]; begin = ln.cta_begin[2]; }
+    if (ln.ndirs > 3 && (int)blockIdx.x >= ln.cta_begin[3]) { k = ln.dir[3]; begin = ln.cta_begin[3]; }
+    TileGeom tg;
+    tg.k = k;
+    tg.col = (k & 1) != 0;
+    tg.fwd = k < 2;
+    const int idx = blockIdx.x - begin;
+    if (tg.col) {
+        tg.seg = idx % g.ncolseg;
+        tg.chunk0 = (idx / g.ncolseg) * kSeq;
+        tg.t0 = tg.seg * g.col_seg;
+        tg.maxlen = min(g.col_seg, g.h - tg.t0);
+    } else {
+        tg.seg = 0;
+        tg.t0 = 0;
+        tg.chunk0 = idx * kSeq;
+        tg.maxlen = g.row_T;
+    }
+    const int b = blockIdx.y;
+    if (tg.col) run_cta_replay<kSeq, TIMED>(prm, g, tg, smem, b);
+    else if (tg.fwd) run_cta_replay<1, TIMED>(prm, g, tg, smem, b);
+    else run_cta_replay<-1, TIMED>(prm, g, tg, smem, b);
 }
 
 // FINAL=false: pass 1 (aggregates).  FINAL=true: pass 2 (outputs).  CKPT: checkpoint pass.
@@ -656,8 +812,19 @@ Geom make_geom(int64_t B, int64_t h, int64_t w)
 }
 
 struct Workspace {
-    int64_t planes_off, aggP_off, aggH_off, total;
+    int64_t planes_off, aggP_off, aggH_off, tiles_off, total;
+    int tile_stride;
 };
+
+// Replay scheme on unless WM_SS2D_REPLAY=0 (developer switch: the recomputing pass 2)
+static bool replay_enabled()
+{
+    static const bool on = []() {
+        const char *e = getenv("WM_SS2D_REPLAY");
+        return !(e != nullptr && e[0] == '0');
+    }();
+    return on;
+}
 
 Workspace plan_workspace(const Geom &g)
 {
@@ -667,7 +834,12 @@ Workspace plan_workspace(const Geom &g)
     ws.planes_off = 0;
     ws.aggP_off = planes_bytes;
     ws.aggH_off = planes_bytes + agg_bytes;
-    ws.total = planes_bytes + 2 * agg_bytes;
+    ws.tiles_off = planes_bytes + 2 * agg_bytes;
+    const int longest = g.row_T > g.col_seg ? g.row_T : g.col_seg;
+    ws.tile_stride = (longest + kTP - 1) / kTP;
+    const int64_t ctas = 2 * ((int64_t)g.row_ctas + g.col_ctas) * g.B;
+    const int64_t tiles_bytes = replay_enabled() ? align_up(ctas * ws.tile_stride * kTileFloats * 4, 256) : 0;
+    ws.total = ws.tiles_off + tiles_bytes;
     return ws;
 }
 
@@ -748,6 +920,8 @@ int run_dirs(const float *x, const float *x_proj_weight, const float *dt_projs_w
     prm.aggH = reinterpret_cast<float *>(wsb + ws.aggH_off);
     prm.dbg = g_dbg.load();
     prm.hbuf = nullptr;
+    prm.tiles = replay_enabled() ? reinterpret_cast<float *>(wsb + ws.tiles_off) : nullptr;
+    prm.tile_stride = ws.tile_stride;
     const size_t smem_bytes = kSmemBytes + (size_t)g_dbg_pad.load();
 
     auto pass1 = prm.dbg ? ss2d_pass_kernel<false, true> : ss2d_pass_kernel<false, false>;
@@ -762,7 +936,13 @@ int run_dirs(const float *x, const float *x_proj_weight, const float *dt_projs_w
     dim3 cgrid(kChains / 32, kK, (unsigned)B);
     ss2d_carry_kernel<<<cgrid, 32 * kCarryWarps, 0, s>>>(prm.aggP, prm.aggH, g);
     WM_LAUNCH_OK("ss2d carry");
-    pass2<<<grid, kThreads, smem_bytes, s>>>(prm, g, ln);
+    if (prm.tiles != nullptr) {
+        auto replay = prm.dbg ? ss2d_replay_kernel<true> : ss2d_replay_kernel<false>;
+        WM_CUDA_OK(cudaFuncSetAttribute(replay, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kReplaySmem));
+        replay<<<grid, kThreads, kReplaySmem, s>>>(prm, g, ln);
+    } else {
+        pass2<<<grid, kThreads, smem_bytes, s>>>(prm, g, ln);
+    }
     WM_LAUNCH_OK("ss2d pass 2");
     return WM_OK;
 }

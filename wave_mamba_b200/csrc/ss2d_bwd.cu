@@ -592,6 +592,7 @@ extern "C" int wm_ss2d_core_bwd(const float *x, const float *x_proj_weight, cons
     fp.x = x; fp.x_proj_w = x_proj_weight; fp.dt_w = dt_projs_weight; fp.dt_b = dt_projs_bias;
     fp.A_logs = A_logs; fp.Ds = Ds; fp.planes = nullptr; fp.aggP = aggP; fp.aggH = aggH; fp.dbg = nullptr;
     fp.hbuf = hbuf;
+    fp.tiles = nullptr; fp.tile_stride = 0;
     BwdParams bp;
     bp.x = x; bp.gy = grad_y; bp.x_proj_w = x_proj_weight; bp.dt_w = dt_projs_weight; bp.dt_b = dt_projs_bias;
     bp.A_logs = A_logs; bp.Ds = Ds; bp.aggH = aggH; bp.aggP2 = aggP2; bp.aggQ = aggQ; bp.hbuf = hbuf;

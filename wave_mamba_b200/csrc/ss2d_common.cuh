@@ -42,6 +42,7 @@ constexpr int kOffYs = kOffDd + kPos * kDD;             // +8448
 constexpr int kOffWf = kOffYs + kD * kYS;               // +4160
 constexpr int kOffCst = kOffWf + 8 * kNTiles * 32 * 4;  // +5120
 constexpr int kSmemFloats = kOffCst + 3 * kD;           // +192
+constexpr int kTileFloats = kPos * kPJ + kPos * kDD;    // one projected tile [pj | dd]: 10752 floats
 constexpr size_t kSmemBytes = sizeof(float) * kSmemFloats;   // 99,328 B -> 2 CTAs per SM
 
 struct Geom {
@@ -76,6 +77,9 @@ struct Params {
     float *aggP;               // (B,4,max_chunks,1024)
     float *aggH;               // (B,4,max_chunks,1024)  pass 1: local end state; after carry: h_in
     long long *dbg;            // developer aid (wm_ss2d_debug_timing): per-CTA phase cycle sums
+    float *tiles;              // replay scratch (null: pass 2 recomputes): pass 1 dumps the projected
+                               // tile [pj | dd] of every (CTA, tile), pass 2 reads it back
+    int tile_stride;           // tile slots per CTA
     float *hbuf;               // checkpoint pass (backward): state after every step of ONE direction,
                                // [b][chunk][step][1024 chains]
 };
