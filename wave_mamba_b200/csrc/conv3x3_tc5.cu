@@ -16,7 +16,7 @@
 //   [acc | acc2] += a_hi*[b_hi | b_lo]  (one MMA, N = 2*COUT) ; acc += a_lo*b_hi  (N = COUT)
 //   fp32 accumulate in TMEM, acc + acc2 in the epilogue.
 //
-// Warp-specialised, persistent (one CTA per SM, 14 warps), everything synchronised with mbarriers --
+// Warp-specialised, persistent (one CTA per SM, 15 warps), everything synchronised with mbarriers --
 // no CTA-wide barrier inside the tile loop:
 //   warps 0-3   X producers: a work unit is (tile, 32-channel K half); its halo slab is loaded
 //               global -> registers (all 76 loads of a thread in flight) -> shared as hi AND lo
@@ -24,8 +24,8 @@
 //               unit is staged while the tensor core works on the current one
 //   warp 12     weight producer: one TMA bulk copy (cp.async.bulk + mbarrier complete_tx) per
 //               (tap, K half) chunk into a 3/4-deep ring; the prepacked layout is the shared layout
-//   warp 13     MMA issuer: one thread, tcgen05.mma; tcgen05.commit frees ring stages / X slabs and
-//               publishes the accumulators
+//   warps 13,14 MMA issuers: one thread each (M tile 0 / M tile 1), tcgen05.mma; tcgen05.commit frees
+//               ring stages / X slabs and publishes the accumulators
 //   warps 4-11  epilogue: tcgen05.ld -> bias or k3*sigmoid(k2+b) -> NCHW / channel-quad stores; the
 //               accumulators are double-buffered in TMEM when 2 x columns <= 512 (all variants but
 //               the gated 64->64 and the 32->96 one), so the epilogue overlaps the next tile's MMAs
@@ -50,8 +50,9 @@ constexpr int kSlabF4 = kKcSlab * kNPos;    // float4 per slab and per part (hi 
 constexpr int kProdWarps = 4, kEpiWarps = 8;
 constexpr int kProdThreads = 32 * kProdWarps;
 constexpr int kWarpW = kProdWarps + kEpiWarps;       // weight producer warp
-constexpr int kWarpMma = kWarpW + 1;                  // MMA issuer warp
-constexpr int kThreads = 32 * (kWarpMma + 1);         // 448
+constexpr int kWarpMma = kWarpW + 1;                  // MMA issuer warps: kWarpMma (M tile 0), +1 (M tile 1)
+constexpr int kMmaWarps = 2;
+constexpr int kThreads = 32 * (kWarpMma + kMmaWarps); // 480
 
 // optional per-CTA timing of the MMA thread (cycles), enabled with wm_conv3x3_debug_timing(ptr):
 // [0] total  [1] wait weights  [2] wait X  [3] wait accumulator buffer  [4] issue  [5] tiles
@@ -129,9 +130,9 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
 
     // ---- one-time setup: barriers (one thread), TMEM allocation (the MMA warp) ---------------
     if (tid == 0) {
-        for (int i = 0; i < kStages; ++i) { mbar_init(wfull(i), 1); mbar_init(wempty(i), 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(xfull(i), kProdThreads); mbar_init(xempty(i), 1); }
-        for (int i = 0; i < NACC; ++i) { mbar_init(accfull(i), 1); mbar_init(accempty(i), kEpiWarps); }
+        for (int i = 0; i < kStages; ++i) { mbar_init(wfull(i), 1); mbar_init(wempty(i), kMmaWarps); }
+        for (int i = 0; i < 2; ++i) { mbar_init(xfull(i), kProdThreads); mbar_init(xempty(i), kMmaWarps); }
+        for (int i = 0; i < NACC; ++i) { mbar_init(accfull(i), kMmaWarps); mbar_init(accempty(i), kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kWarpMma) {
@@ -274,8 +275,14 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
                 }
             }
         }
-    } else if (warp == kWarpMma) {
-        // =============================== MMA issuer =========================================
+    } else if (warp >= kWarpMma) {
+        // =============================== MMA issuers ========================================
+        // One thread needs ~54 cycles to issue a tcgen05.mma (measured: 16 MMAs per chunk in ~860 cycles)
+        // -- about what the tensor core needs to EXECUTE one (48-64 cycles), so a single issuer that also
+        // pays ~370 cycles of barrier latency per chunk starves the pipe.  Two issuer warps split the
+        // two M tiles (disjoint TMEM columns, no ordering between them); every barrier they release
+        // counts both.
+        const int my_mt = warp - kWarpMma;
         if (lane == 0) {
             // instruction descriptors: D=f32, A=B=tf32, both K-major, M = 128; N = COUT (b_hi only)
             // or N = 2*COUT ([b_hi | b_lo]: the activation operand is read once for both)
@@ -290,7 +297,7 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
             uint32_t cnt = 0, unit = 0, tcount = 0;
             const int rot = 0;   // tap-order rotation per CTA (against L2 hot spots): measured, no gain
             long long tacc[5] = {0, 0, 0, 0, 0}, t0 = 0, tp = 0;
-            const bool timed = a.dbg != nullptr;
+            const bool timed = a.dbg != nullptr && my_mt == 0;
             if (timed) { t0 = clock64(); tp = t0; }
 #define WM_TICK(k) do { if (timed) { const long long _t = clock64(); tacc[k] += _t - tp; tp = _t; } } while (0)
 #pragma unroll 1
@@ -318,8 +325,8 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
                         // offsets in 16-byte units (= one (kc, position) or (kc, co) element)
                         const uint32_t shift = (uint32_t)(slot * kSlabF4 + dy * kHW + dx);
                         const uint64_t b_hi0 = b_00 + (uint32_t)(st * C::kChunkF4);
-#pragma unroll
-                        for (int mt = 0; mt < 2; ++mt) {
+                        {
+                            const int mt = my_mt;
                             const uint32_t dcol = dbase + (uint32_t)((gate_tap ? 4 * COUT : 0) + mt * 2 * COUT);
                             const uint32_t arow = shift + (uint32_t)mt * 128u;
 #pragma unroll
