@@ -75,7 +75,6 @@ struct Args {
     // in_c4 needs Ca == CIN (no second input); used between PAConv.k3 and k4.
     int in_c4, out_c4;
     unsigned int *err;       // pipeline error word (mbar_wait_flag)
-    int wsplit;              // bulk copies per weight chunk (1, 2, 4 or 8)
 };
 
 template <int CIN, int COUT, bool GATE>
@@ -84,10 +83,9 @@ struct Cfg {
     static constexpr int NTAPS = GATE ? 10 : 9;
     static constexpr int kChunkF4 = kKcSlab * 2 * COUT;        // float4 per weight chunk
     static constexpr int kChunkBytes = kChunkF4 * 16;
-    // weight ring depth: a stage is refilled only after its MMAs completed, and the refill (commit ->
-    // mbarrier -> producer -> bulk copy -> mbarrier) takes ~3 k cycles, about 3.5 chunks of MMA work:
-    // 4 stages leave the MMA thread waiting ~360 cycles per chunk (measured), 8 stages hide it --
-    // affordable where a chunk is 8 KB (COUT = 32); the 64- and 96-output variants fill shared memory
+    // weight ring depth (what fits next to the X slabs).  The issuing threads run ahead of the tensor
+    // core until they meet a stage that is still being refilled, so their timers always show a wait on
+    // the weights (~350 cycles per chunk at any depth): it is slack, not a stall of the tensor pipe.
     static constexpr int kStages = COUT >= 96 ? 3 : COUT <= 32 ? 8 : 4;
     static constexpr int kColsBuf = 4 * COUT * (GATE ? 2 : 1); // TMEM columns of one accumulator set
     static constexpr int NACC = 2 * kColsBuf <= 512 ? 2 : 1;
@@ -265,12 +263,9 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
                         const int st = cnt % kStages;
                         mbar_wait_flag(wempty(st), ((cnt / kStages) & 1u) ^ 1u, a.err, (4u << 24) | (2u << 16) | (cnt & 0xffffu));
                         mbar_expect_tx(wfull(st), (uint32_t)C::kChunkBytes);
-                        // the chunk as `wsplit` bulk copies in flight at once (all complete on wfull)
-                        const float4 *src = a.packed + (int64_t)(tap * NCH + part) * C::kChunkF4;
-                        const uint32_t dst = smem_u32(wbuf + st * C::kChunkF4);
-                        const uint32_t piece = (uint32_t)C::kChunkBytes / (uint32_t)a.wsplit;
-                        for (int q = 0; q < a.wsplit; ++q)
-                            bulk_g2s(dst + q * piece, reinterpret_cast<const char *>(src) + q * piece, piece, wfull(st));
+                        bulk_g2s(smem_u32(wbuf + st * C::kChunkF4),
+                                 a.packed + (int64_t)(tap * NCH + part) * C::kChunkF4,
+                                 (uint32_t)C::kChunkBytes, wfull(st));
                     }
                 }
             }
@@ -550,12 +545,7 @@ extern "C" int wm_conv3x3_ex_fwd(const float *in_a, int64_t a_bstride, int64_t C
     a.dbg = g_dbg.load();
     a.err = pipeline_err_word();
     WM_REQUIRE(a.err != nullptr, "wm_conv3x3_fwd: no CUDA device");
-    static const int wsplit = []() {   // developer switch WM_CONV_WSPLIT (power of two <= 8)
-        const char *e = getenv("WM_CONV_WSPLIT");
-        const int v = e ? atoi(e) : 1;
-        return (v == 1 || v == 2 || v == 4 || v == 8) ? v : 1;
-    }();
-    a.wsplit = wsplit;
+
     a.in_a = in_a; a.a_bstride = a_bstride; a.Ca = (int)Ca; a.in_b = in_b; a.b_bstride = b_bstride;
     a.chan_map = chan_map; a.packed = static_cast<const float4 *>(packed); a.bias = bias;
     a.gate_bias = gate_bias; a.out = out; a.h = (int)h; a.w = (int)w;
