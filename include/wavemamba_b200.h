@@ -184,7 +184,7 @@ int wm_conv3x3_debug_timing(void *device_buffer);
  * (dense 3x3 conv, pw_dw) record a wait that timed out: 0 = none, else
  * 0x80000000 | role << 24 | barrier << 16 | iteration of the first one. */
 int wm_debug_pipeline_error(unsigned int *out);
-/* Developer aid: non-NULL device buffer of 12*SMs int64 -> per-CTA cycle counters of the pw_dw
+/* Developer aid: non-NULL device buffer of 16*SMs int64 -> per-CTA cycle counters of the pw_dw
  * pipeline (waits and phases of its three warp roles); NULL disables. */
 int wm_pw_dw_debug_timing(void *device_buffer);
 int wm_conv3x3_prepack(const float *w3x3, const float *w1x1, void *packed, int64_t Cin, int64_t Cout,

@@ -26,16 +26,18 @@ for cout, act in ((64, "silu"), (64, "none"), (96, "none"), (32, "none")):
     gb = (32 + cout) * 1080 * 1920 * 4 / 1e9
     if not os.environ.get("WM_PW_DW_LEGACY"):
         from wave_mamba_b200 import _cabi
-        dbg = torch.zeros(148 * 12, dtype=torch.int64, device=dev)
+        dbg = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
         _cabi.load().wm_pw_dw_debug_timing(dbg.data_ptr())
         ops.pw_dw(x, pw_w, None, dw_w, dw_b, ln_w, ln_b, 1e-6, act=act)
         torch.cuda.synchronize()
         _cabi.load().wm_pw_dw_debug_timing(None)
-        d = dbg.view(148, 12).double()
+        d = dbg.view(148, 16).double()
         tiles = d[:, 9].clamp(min=1)
         names = ["A:wait_tma", "A:wait_xk_free", "A:ln_pass", "M:wait_xk", "M:wait_acc", "M:issue",
                  "B:wait_mma", "B:tmem_to_ps", "B:depthwise"]
         print("   cycles per tile:", {n: int((d[:, i] / tiles).mean().item()) for i, n in enumerate(names)},
-              "total", int((d[:, 10] / tiles).mean().item()))
+              "total", int((d[:, 10] / tiles).mean().item()),
+              "| epilogue warp 0:", {n: int((d[:, 11 + i] / tiles).mean().item()) for i, n in
+                                      enumerate(["tmem_ld", "ps_store", "bar1", "depthwise", "bar2"])})
     print(f"pw_dw 32->{cout} {act} legacy={os.environ.get('WM_PW_DW_LEGACY', '0')}: {ms:.3f} ms, "
           f"{gb / ms * 1e3:.0f} GB/s algorithmic ({gb / ms * 1e3 / 6553 * 100:.1f}% of the measured HBM peak)")
