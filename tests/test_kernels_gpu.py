@@ -308,9 +308,11 @@ def test_pw_dw_many_tiles_per_cta(ops, dev, cout, act):
         assert torch.equal(got, ops.pw_dw(x, pw_w, pw_b, dw_w, dw_b, ln_w, ln_b, 1e-6, act=act))
 
 
-@pytest.mark.parametrize("hw", [(13, 37), (16, 64)])
+@pytest.mark.parametrize("hw", [(13, 37), (16, 64), (156, 160)])
 @pytest.mark.parametrize("with_res", [False, True])
 def test_dw_act_pw(ops, dev, hw, with_res):
+    """(13, 37): the cp.async kernel (w % 4 != 0); (16, 64): the TMA pipeline, one tile per CTA;
+    (156, 160): 200 tiles = several per persistent CTA, with a partial bottom row of tiles."""
     g = torch.Generator().manual_seed(8)
     h, w = hw
     x = _rand(2, 32, h, w, g=g)
@@ -582,14 +584,18 @@ def test_conv_pack_cache_sees_data_writes(ops, dev):
     assert not torch.equal(y1, y2)
 
 
-def test_stem_and_head_conv(ops, dev):
+@pytest.mark.parametrize("hw", [(21, 45), (24, 136), (9, 70), (8, 64)])
+def test_stem_and_head_conv(ops, dev, hw):
+    """Odd widths take the scalar stores, even widths the stem's 8-byte pairs, multiples of 4 the head's
+    16-byte rows; 136 and 70 leave a partial 64-column tile."""
     g = torch.Generator().manual_seed(41)
-    x = torch.rand(2, 3, 21, 45, generator=g)
+    h, w = hw
+    x = torch.rand(2, 3, h, w, generator=g)
     w1, b1 = _rand(32, 3, 3, 3, g=g, s=0.2), _rand(32, g=g, s=0.1)
     want = F.conv2d(x, w1, b1, padding=1)
     torch.testing.assert_close(ops.stem_conv3x3(x.to(dev), w1.to(dev), b1.to(dev)).cpu(), want,
                                rtol=2e-5, atol=2e-5)
-    f = _rand(2, 32, 21, 45, g=g)
+    f = _rand(2, 32, h, w, g=g)
     w2, b2 = _rand(3, 32, 3, 3, g=g, s=0.1), _rand(3, g=g, s=0.1)
     want = F.conv2d(f, w2, b2, padding=1) + x
     got = ops.head_conv3x3(f.to(dev), w2.to(dev), b2.to(dev), residual=x.to(dev)).cpu()

@@ -24,13 +24,7 @@ constexpr int kHH = kTH + 2, kHW = kTW + 2;    // halo tile 10 x 34
 constexpr int kHalo = kHH * kHW;               // 340 positions
 constexpr int kXP = 360;                       // padded position stride (== 8 mod 32: conflict-free
                                                // mma A-fragment loads from xs[channel][position])
-constexpr int kPix = kTH * kTW;                // 256 interior pixels
 constexpr int kThreads = 256;
-
-__device__ __forceinline__ float gelu_erf(float v)
-{
-    return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));  // torch exact GELU
-}
 
 // ---- tensor-core helpers for the 1x1 phase (3xTF32, fp32-accurate; see conv3x3.cu) ----------
 __device__ __forceinline__ uint32_t to_tf32(float v)
@@ -271,95 +265,6 @@ pw_dw_kernel(const float *__restrict__ x, const float *__restrict__ ln_w,
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// y = residual? + pw1x1( act( dw3x3(x) ) ),  C = 32
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads)
-dw_act_pw_kernel(const float *__restrict__ x, const float *__restrict__ dw_w,
-                 const float *__restrict__ dw_b, const float *__restrict__ pw_w,
-                 const float *__restrict__ pw_b, int act, const float *__restrict__ residual,
-                 float *__restrict__ y, int h, int w)
-{
-    constexpr int C = 32;
-    extern __shared__ __align__(16) float smem[];
-    float *xs = smem;                  // [32][kXP] halo tile
-    float *ds = xs + C * kXP;          // [32][256] after dw + act
-    float *wt = ds + C * kPix;         // [32][32] transposed 1x1 weights
-    float *pb = wt + C * C;            // [32]
-    float *dww = pb + C;               // [32][9]
-    float *dwb = dww + C * 9;          // [32]
-
-    const int tid = threadIdx.x;
-    const int tx0 = blockIdx.x * kTW, ty0 = blockIdx.y * kTH;
-    const int64_t b = blockIdx.z;
-    const int64_t hw = (int64_t)h * w;
-
-    for (int i = tid; i < C * C; i += kThreads) {
-        const int co = i / C, ci = i - co * C;
-        wt[ci * C + co] = __ldg(pw_w + i);
-    }
-    if (tid < C) { pb[tid] = __ldg(pw_b + tid); dwb[tid] = __ldg(dw_b + tid); }
-    for (int i = tid; i < C * 9; i += kThreads) dww[i] = __ldg(dw_w + i);
-    load_halo32(x, xs, b, C, h, w, ty0, tx0);
-    halo_wait();
-    __syncthreads();
-
-    const int col = tid & 31;
-#pragma unroll 1
-    for (int i = 0; i < 4; ++i) {
-        const int c = (tid >> 5) + 8 * i;
-        float k[9];
-#pragma unroll
-        for (int t = 0; t < 9; ++t) k[t] = dww[c * 9 + t];
-        const float bias = dwb[c];
-        const float *pc = xs + c * kXP + col;
-        float r0[3], r1[3], r2[3];
-#pragma unroll
-        for (int dx = 0; dx < 3; ++dx) { r0[dx] = pc[dx]; r1[dx] = pc[kHW + dx]; }
-#pragma unroll
-        for (int row = 0; row < kTH; ++row) {
-#pragma unroll
-            for (int dx = 0; dx < 3; ++dx) r2[dx] = pc[(row + 2) * kHW + dx];
-            float o = bias;
-            o = fmaf(k[0], r0[0], o); o = fmaf(k[1], r0[1], o); o = fmaf(k[2], r0[2], o);
-            o = fmaf(k[3], r1[0], o); o = fmaf(k[4], r1[1], o); o = fmaf(k[5], r1[2], o);
-            o = fmaf(k[6], r2[0], o); o = fmaf(k[7], r2[1], o); o = fmaf(k[8], r2[2], o);
-            ds[c * kPix + row * kTW + col] = act == 1 ? gelu_erf(o) : o;
-#pragma unroll
-            for (int dx = 0; dx < 3; ++dx) { r0[dx] = r1[dx]; r1[dx] = r2[dx]; }
-        }
-    }
-    __syncthreads();
-
-    // 1x1: thread = interior pixel
-    float acc[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] = pb[j];
-#pragma unroll 4
-    for (int ci = 0; ci < C; ++ci) {
-        const float xv = ds[ci * kPix + tid];
-        const float4 *wr = reinterpret_cast<const float4 *>(wt + ci * C);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float4 wv = wr[j];
-            acc[4 * j + 0] = fmaf(xv, wv.x, acc[4 * j + 0]);
-            acc[4 * j + 1] = fmaf(xv, wv.y, acc[4 * j + 1]);
-            acc[4 * j + 2] = fmaf(xv, wv.z, acc[4 * j + 2]);
-            acc[4 * j + 3] = fmaf(xv, wv.w, acc[4 * j + 3]);
-        }
-    }
-    const int gy = ty0 + (tid >> 5), gx = tx0 + col;
-    if (gy < h && gx < w) {
-        const int64_t o = (int64_t)b * C * hw + (int64_t)gy * w + gx;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            float v = acc[j];
-            if (residual != nullptr) v += __ldg(residual + o + j * hw);
-            y[o + j * hw] = v;
-        }
-    }
-}
-
 inline bool dims_ok(int64_t B, int64_t h, int64_t w)
 {
     return B >= 0 && B <= 65535 && h >= 0 && w >= 0 && h < (1 << 24) && w < (1 << 24);
@@ -417,164 +322,4 @@ extern "C" int wm_pw_dw_fwd(const float *x, const float *ln_w, const float *ln_b
     if (Cout == 32) return launch_pw_dw<32>(x, ln_w, ln_b, eps, pw_w, pw_b, dw_w, dw_b, act, y, B, h, w, s);
     if (Cout == 64) return launch_pw_dw<64>(x, ln_w, ln_b, eps, pw_w, pw_b, dw_w, dw_b, act, y, B, h, w, s);
     return launch_pw_dw<96>(x, ln_w, ln_b, eps, pw_w, pw_b, dw_w, dw_b, act, y, B, h, w, s);
-}
-
-extern "C" int wm_dw_act_pw_fwd(const float *x, const float *dw_w, const float *dw_b,
-                                const float *pw_w, const float *pw_b, int act,
-                                const float *residual, float *y, int64_t B, int64_t C, int64_t h,
-                                int64_t w, wm_stream_t stream)
-{
-    WM_REQUIRE(x && dw_w && dw_b && pw_w && pw_b && y, "wm_dw_act_pw_fwd: null pointer");
-    WM_REQUIRE(dims_ok(B, h, w), "wm_dw_act_pw_fwd: bad sizes");
-    WM_REQUIRE(C == 32, "wm_dw_act_pw_fwd: C=%lld unsupported (32)", (long long)C);
-    WM_REQUIRE(act == 0 || act == 1, "wm_dw_act_pw_fwd: act must be 0 or 1");
-    WM_REQUIRE((h + kTH - 1) / kTH <= 65535, "wm_dw_act_pw_fwd: image too tall");
-    if (B == 0 || h == 0 || w == 0) return WM_OK;
-    cudaStream_t s = (cudaStream_t)stream;
-    const size_t smem = sizeof(float) * (32 * kXP + 32 * kPix + 32 * 32 + 32 + 32 * 9 + 32);
-    WM_CUDA_OK(opt_in_smem(dw_act_pw_kernel, smem));
-    dim3 grid((unsigned)((w + kTW - 1) / kTW), (unsigned)((h + kTH - 1) / kTH), (unsigned)B);
-    dw_act_pw_kernel<<<grid, kThreads, smem, s>>>(x, dw_w, dw_b, pw_w, pw_b, act, residual, y,
-                                                  (int)h, (int)w);
-    WM_LAUNCH_OK("dw_act_pw");
-    return WM_OK;
-}
-
-
-// =============================================================================================
-// Stem / head 3x3 convolutions with a tiny channel count on one side (UNet.conv_01 3->32,
-// reference :1026,1048; UNet.last 32->3 + the global residual, :1039,1061).  Direct FFMA over an
-// 8x32 tile with halo in shared memory; thread = output pixel; weights broadcast from smem.
-// =============================================================================================
-namespace wm {
-namespace pw {
-
-// out[co] = bias[co] + sum_{ci,tap} w[co][ci][tap] * in[ci][tap]   (CIN = 3, COUT = 32)
-__global__ void __launch_bounds__(kThreads)
-stem_conv3x3_kernel(const float *__restrict__ x, const float *__restrict__ wgt,
-                    const float *__restrict__ bias, float *__restrict__ y, int h, int w)
-{
-    constexpr int CIN = 3, COUT = 32;
-    __shared__ __align__(16) float xs[CIN * kXP];
-    __shared__ __align__(16) float wt[CIN * 9 * COUT];   // [ci*9+tap][co]
-    __shared__ float bs[COUT];
-    const int tid = threadIdx.x;
-    const int tx0 = blockIdx.x * kTW, ty0 = blockIdx.y * kTH;
-    const int64_t b = blockIdx.z;
-    const int64_t hw = (int64_t)h * w;
-    for (int i = tid; i < COUT * CIN * 9; i += kThreads) {
-        const int co = i / (CIN * 9), r = i - co * (CIN * 9);
-        wt[r * COUT + co] = __ldg(wgt + i);
-    }
-    if (tid < COUT) bs[tid] = bias ? __ldg(bias + tid) : 0.0f;
-    load_halo32(x, xs, b, CIN, h, w, ty0, tx0);
-    halo_wait();
-    __syncthreads();
-    const int col = tid & 31, row = tid >> 5;
-    float acc[COUT];
-#pragma unroll
-    for (int j = 0; j < COUT; ++j) acc[j] = bs[j];
-#pragma unroll
-    for (int ci = 0; ci < CIN; ++ci)
-#pragma unroll
-        for (int t = 0; t < 9; ++t) {
-            const float xv = xs[ci * kXP + (row + t / 3) * kHW + col + t % 3];
-            const float4 *wr = reinterpret_cast<const float4 *>(wt + (ci * 9 + t) * COUT);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float4 wv = wr[j];
-                acc[4 * j + 0] = fmaf(xv, wv.x, acc[4 * j + 0]);
-                acc[4 * j + 1] = fmaf(xv, wv.y, acc[4 * j + 1]);
-                acc[4 * j + 2] = fmaf(xv, wv.z, acc[4 * j + 2]);
-                acc[4 * j + 3] = fmaf(xv, wv.w, acc[4 * j + 3]);
-            }
-        }
-    const int gy = ty0 + row, gx = tx0 + col;
-    if (gy < h && gx < w) {
-        float *o = y + b * COUT * hw + (int64_t)gy * w + gx;
-#pragma unroll
-        for (int j = 0; j < COUT; ++j) o[j * hw] = acc[j];
-    }
-}
-
-// out[co] = residual[co] + bias[co] + sum_{ci,tap} w[co][ci][tap] * in[ci][tap]  (CIN = 32, COUT = 3)
-__global__ void __launch_bounds__(kThreads)
-head_conv3x3_kernel(const float *__restrict__ x, const float *__restrict__ wgt,
-                    const float *__restrict__ bias, const float *__restrict__ residual,
-                    float *__restrict__ y, int h, int w)
-{
-    constexpr int CIN = 32, COUT = 3;
-    extern __shared__ __align__(16) float smem[];
-    float *xs = smem;                                   // [32][kXP]
-    // A CTA takes TWO horizontally adjacent 8x32 tiles; a thread computes the same (row, col) of both,
-    // so every broadcast weight load (LDS.128: 512 bytes returned per warp) feeds 6 FMAs instead of 3.
-    float *xs2 = xs + CIN * kXP;                                // second tile's halo
-    float4 *wt = reinterpret_cast<float4 *>(xs2 + CIN * kXP);  // [ci*9+tap] -> (w0, w1, w2, 0)
-    const int tid = threadIdx.x;
-    const int tx0 = blockIdx.x * (2 * kTW), ty0 = blockIdx.y * kTH;
-    const int64_t b = blockIdx.z;
-    const int64_t hw = (int64_t)h * w;
-    for (int i = tid; i < CIN * 9; i += kThreads)
-        wt[i] = make_float4(__ldg(wgt + i), __ldg(wgt + CIN * 9 + i), __ldg(wgt + 2 * CIN * 9 + i), 0.0f);
-    load_halo32(x, xs, b, CIN, h, w, ty0, tx0);
-    load_halo32(x, xs2, b, CIN, h, w, ty0, tx0 + kTW);           // all zeros when past the right edge
-    halo_wait();
-    __syncthreads();
-    const int col = tid & 31, row = tid >> 5;
-    const float b0 = bias ? __ldg(bias + 0) : 0.0f, b1 = bias ? __ldg(bias + 1) : 0.0f,
-                b2 = bias ? __ldg(bias + 2) : 0.0f;
-    float a0[2] = {b0, b0}, a1[2] = {b1, b1}, a2[2] = {b2, b2};
-#pragma unroll 4
-    for (int ci = 0; ci < CIN; ++ci) {
-        const float *xc = xs + ci * kXP + row * kHW + col;
-        const float *xd = xs2 + ci * kXP + row * kHW + col;
-#pragma unroll
-        for (int t = 0; t < 9; ++t) {
-            const float4 wv = wt[ci * 9 + t];
-            const float u = xc[(t / 3) * kHW + t % 3], v = xd[(t / 3) * kHW + t % 3];
-            a0[0] = fmaf(u, wv.x, a0[0]); a1[0] = fmaf(u, wv.y, a1[0]); a2[0] = fmaf(u, wv.z, a2[0]);
-            a0[1] = fmaf(v, wv.x, a0[1]); a1[1] = fmaf(v, wv.y, a1[1]); a2[1] = fmaf(v, wv.z, a2[1]);
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        const int gy = ty0 + row, gx = tx0 + k * kTW + col;
-        if (gy < h && gx < w) {
-            const int64_t o = b * COUT * hw + (int64_t)gy * w + gx;
-            float r0 = a0[k], r1 = a1[k], r2 = a2[k];
-            if (residual) { r0 += __ldg(residual + o); r1 += __ldg(residual + o + hw); r2 += __ldg(residual + o + 2 * hw); }
-            y[o] = r0; y[o + hw] = r1; y[o + 2 * hw] = r2;
-        }
-    }
-}
-
-}  // namespace pw
-}  // namespace wm
-
-extern "C" int wm_stem_conv3x3_fwd(const float *x, const float *w3x3, const float *bias, float *y,
-                                   int64_t B, int64_t h, int64_t w, wm_stream_t stream)
-{
-    WM_REQUIRE(dims_ok(B, h, w) && (h + kTH - 1) / kTH <= 65535, "wm_stem_conv3x3_fwd: bad sizes");
-    if (B == 0 || h == 0 || w == 0) return WM_OK;
-    WM_REQUIRE(x && w3x3 && y, "wm_stem_conv3x3_fwd: null pointer");
-    dim3 grid((unsigned)((w + kTW - 1) / kTW), (unsigned)((h + kTH - 1) / kTH), (unsigned)B);
-    stem_conv3x3_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, w3x3, bias, y, (int)h, (int)w);
-    WM_LAUNCH_OK("stem conv3x3");
-    return WM_OK;
-}
-
-extern "C" int wm_head_conv3x3_fwd(const float *x, const float *w3x3, const float *bias,
-                                   const float *residual, float *y, int64_t B, int64_t h, int64_t w,
-                                   wm_stream_t stream)
-{
-    WM_REQUIRE(dims_ok(B, h, w) && (h + kTH - 1) / kTH <= 65535, "wm_head_conv3x3_fwd: bad sizes");
-    if (B == 0 || h == 0 || w == 0) return WM_OK;
-    WM_REQUIRE(x && w3x3 && y, "wm_head_conv3x3_fwd: null pointer");
-    const size_t smem = sizeof(float) * 2 * 32 * kXP + sizeof(float4) * 32 * 9;
-    WM_CUDA_OK(opt_in_smem(head_conv3x3_kernel, smem));
-    dim3 grid((unsigned)((w + 2 * kTW - 1) / (2 * kTW)), (unsigned)((h + kTH - 1) / kTH), (unsigned)B);
-    head_conv3x3_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(x, w3x3, bias, residual, y,
-                                                                        (int)h, (int)w);
-    WM_LAUNCH_OK("head conv3x3");
-    return WM_OK;
 }

@@ -31,11 +31,9 @@
 //
 // Falls back to the cp.async / mma.sync kernel of pointwise.cu when the TMA preconditions do not
 // hold (w % 4 != 0 or unaligned pointers).
-#include <cuda.h>
-
 #include <atomic>
 
-#include "tc5_common.cuh"
+#include "tma.cuh"
 
 namespace wm {
 namespace pwdw {
@@ -99,16 +97,6 @@ struct Args {
 };
 
 static std::atomic<long long *> g_dbg{nullptr};
-
-__device__ __forceinline__ void tma_load_box(uint32_t dst, const CUtensorMap *tmap, int c0, int c1, int c2,
-                                             int c3, uint32_t mbar)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
-        "[%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
-        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(mbar)
-        : "memory");
-}
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16])
 {
@@ -308,7 +296,7 @@ pw_dw_tc5_kernel(const __grid_constant__ CUtensorMap tmap, const Args a)
                         mbar_wait_flag(xraw_empty(g), (it - 1u) & 1u, a.err, (4u << 24) | ((uint32_t)g << 16) | (it & 0xffffu));
                     mbar_expect_tx(xraw_full(g), (uint32_t)(row_group_end(g) - row_group_begin(g)) * kRowBytes);
                     for (int r = row_group_begin(g); r < row_group_end(g); ++r)
-                        tma_load_box(smem_u32(xraw + r * kRawRow), tmap_ptr, tx0 - kBoxLeft, ty0 - 1 + r, 0, b, xraw_full(g));
+                        tma::load_box(smem_u32(xraw + r * kRawRow), tmap_ptr, tx0 - kBoxLeft, ty0 - 1 + r, 0, b, xraw_full(g));
                 }
             }
         }
@@ -550,41 +538,6 @@ pw_dw_tc5_kernel(const __grid_constant__ CUtensorMap tmap, const Args a)
 }
 
 // ---- host side ------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
-                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                  CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn()
-{
-    static EncodeTiledFn fn = []() -> EncodeTiledFn {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-            q != cudaDriverEntryPointSuccess) {
-            cudaGetLastError();
-            return nullptr;
-        }
-        return reinterpret_cast<EncodeTiledFn>(p);
-    }();
-    return fn;
-}
-
-// NCHW fp32 tensor (B, 32, h, w) as a 4-D tensor map with a 40 x 1 x 32 x 1 box (one halo row)
-static bool make_tmap(CUtensorMap *tm, const float *x, int64_t B, int64_t h, int64_t w)
-{
-    EncodeTiledFn enc = encode_fn();
-    if (enc == nullptr) return false;
-    const cuuint64_t dims[4] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)kCin, (cuuint64_t)B};
-    const cuuint64_t strides[3] = {(cuuint64_t)w * 4, (cuuint64_t)h * w * 4, (cuuint64_t)kCin * h * w * 4};
-    const cuuint32_t box[4] = {kBoxW, 1, kCin, 1};
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
-    const CUresult rc = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(x), dims, strides, box,
-                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return rc == CUDA_SUCCESS;
-}
-
 template <int COUT, bool LN, bool SILU>
 static int launch(const CUtensorMap &tm, const Args &a, cudaStream_t s)
 {
@@ -605,7 +558,7 @@ int forward(const float *x, const float *ln_w, const float *ln_b, float eps, con
 {
     if (w % 4 != 0 || !aligned16(x) || !aligned16(y) || w < kTW || h < kTH) return 1;
     CUtensorMap tm;
-    if (!make_tmap(&tm, x, B, h, w)) return 1;
+    if (!tma::make_tmap_nchw(&tm, x, B, kCin, h, w, kBoxW, 1, kCin)) return 1;   // one halo row per box
     Args a;
     a.ln_w = ln_w; a.ln_b = ln_b; a.eps = eps; a.pw_w = pw_w; a.pw_b = pw_b; a.dw_w = dw_w; a.dw_b = dw_b;
     a.y = y; a.h = (int)h; a.w = (int)w;
