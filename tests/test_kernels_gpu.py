@@ -584,10 +584,11 @@ def test_conv_pack_cache_sees_data_writes(ops, dev):
     assert not torch.equal(y1, y2)
 
 
-@pytest.mark.parametrize("hw", [(21, 45), (24, 136), (9, 70), (8, 64)])
+@pytest.mark.parametrize("hw", [(21, 45), (24, 136), (9, 70), (8, 64), (200, 1280)])
 def test_stem_and_head_conv(ops, dev, hw):
-    """Odd widths take the scalar stores, even widths the stem's 8-byte pairs, multiples of 4 the head's
-    16-byte rows; 136 and 70 leave a partial 64-column tile."""
+    """Odd widths take the scalar stores; w % 4 == 0 takes the stem's 16-byte rows and the head's TMA
+    pipeline (tiles of 32 x 64 starting one column left of a multiple of 64); 136 and 70 leave partial
+    tiles; 200 x 1280 x 2 images = 294 tiles, two per persistent CTA."""
     g = torch.Generator().manual_seed(41)
     h, w = hw
     x = torch.rand(2, 3, h, w, generator=g)

@@ -550,6 +550,147 @@ head_conv3x3_kernel(const float *__restrict__ x, const float *__restrict__ wgt,
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Head as a persistent, TMA-fed pipeline (one CTA of 256 threads per SM).  The form above is bound by
+// the return path of its shared-memory loads (6 cycles of it per tap and 64 pixels); here a thread owns
+// 2 rows x 4 adjacent pixels, so per input channel 4 rows x (LDS.64 + LDS.128) of pixels and 7 LDS.128
+// of weights feed 108 FFMA2 (pixel pairs x (w, w) pairs): ~60 cycles of return path per channel and 256
+// pixels instead of ~216.  A tile is 32 rows x 64 columns, streamed in four 8-channel stages (box 68 x 34
+// x 8 = 74 KB, two stages in flight, requested two stages ahead), accumulators carried across the stages.
+// Tiles start ONE column left of a multiple of 64 (pixel columns 64t-1 .. 64t+62): the six input columns
+// a thread needs then start at an even box column (box origin 64t-4, the 16-byte rule of the TMA start
+// coordinate) and come in as one LDS.64 + one aligned LDS.128.  Needs w % 4 == 0, 16-byte aligned x.
+// ---------------------------------------------------------------------------------------------
+constexpr int kHtRows = 32, kHtBoxW = 68, kHtBoxH = kHtRows + 2, kHtCh = 8;
+constexpr int kHtThreads = 256;
+constexpr uint32_t kHtStageBytes = kHtBoxW * kHtBoxH * kHtCh * 4;        // 73,984
+constexpr size_t kHtSmem = 2 * kHtStageBytes + sizeof(float) * 32 * 28 + 2 * 8;
+static_assert(kHtStageBytes % 128 == 0, "TMA destinations must stay 128-byte aligned");
+
+__global__ void __launch_bounds__(kHtThreads, 1)
+head_conv3x3_tma_kernel(const __grid_constant__ CUtensorMap xmap, const float *__restrict__ wgt,
+                        const float *__restrict__ bias, const float *__restrict__ residual,
+                        float *__restrict__ y, int h, int w, int tiles_x, int tiles_y, int total_tiles)
+{
+    using namespace wm::tc5;
+    constexpr int CIN = 32, COUT = 3, NST = CIN / kHtCh;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *xs = reinterpret_cast<float *>(smem_raw);                         // [2][8][34][68]
+    float *wt = reinterpret_cast<float *>(smem_raw + 2 * kHtStageBytes);     // [ci][tap*3 + co], 28 per ci
+    const uint32_t bar0 = smem_u32(wt + CIN * 28);
+    const int tid = threadIdx.x;
+    const int64_t hw = (int64_t)h * w;
+    const int my_tiles = ((int)blockIdx.x < total_tiles) ? (total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int my_units = my_tiles * NST;
+
+    auto issue = [&](int u) {
+        const int tile = blockIdx.x + (u / NST) * gridDim.x, st = u % NST;
+        const int txi = tile % tiles_x, tyi = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+        const uint32_t bar = bar0 + 8u * (uint32_t)(u & 1);
+        mbar_expect_tx(bar, kHtStageBytes);
+        tma::load_box(smem_u32(xs) + (uint32_t)(u & 1) * kHtStageBytes, &xmap, txi * 64 - 4, tyi * kHtRows - 1,
+                      st * kHtCh, b, bar);
+    };
+    if (tid == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8u, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (my_units > 0) issue(0);
+        if (my_units > 1) issue(1);
+    }
+    for (int i = tid; i < CIN * 28; i += kHtThreads) {
+        const int ci = i / 28, r = i - ci * 28;          // r = tap * 3 + co
+        wt[i] = r < 27 ? __ldg(wgt + ((r % 3) * CIN + ci) * 9 + r / 3) : 0.0f;
+    }
+    __syncthreads();
+
+    const int rp = tid >> 4, k = tid & 15;               // row pair, column group: pixels 4k-1 .. 4k+2 of the tile
+    const float b0 = bias ? __ldg(bias + 0) : 0.0f, b1 = bias ? __ldg(bias + 1) : 0.0f,
+                b2 = bias ? __ldg(bias + 2) : 0.0f;
+    f32x2 acc[2][2][3];                                   // [row][pixel pair][co]
+    int u = 0;
+#pragma unroll 1
+    for (int j = 0; j < my_tiles; ++j) {
+#pragma unroll
+        for (int o = 0; o < 2; ++o)
+#pragma unroll
+            for (int pp = 0; pp < 2; ++pp) {
+                acc[o][pp][0] = pack2(b0, b0); acc[o][pp][1] = pack2(b1, b1); acc[o][pp][2] = pack2(b2, b2);
+            }
+#pragma unroll 1
+        for (int st = 0; st < NST; ++st, ++u) {
+            mbar_wait(bar0 + 8u * (uint32_t)(u & 1), (uint32_t)(u >> 1) & 1u);
+            const float *xb = xs + (u & 1) * (kHtStageBytes / 4) + (2 * rp) * kHtBoxW + 4 * k + 2;
+#pragma unroll 2
+            for (int c = 0; c < kHtCh; ++c) {
+                float wv[28];
+                {
+                    const float4 *wp = reinterpret_cast<const float4 *>(wt + (st * kHtCh + c) * 28);
+#pragma unroll
+                    for (int i = 0; i < 7; ++i) {
+                        const float4 t = wp[i];
+                        wv[4 * i] = t.x; wv[4 * i + 1] = t.y; wv[4 * i + 2] = t.z; wv[4 * i + 3] = t.w;
+                    }
+                }
+                // four input rows, six columns each (box columns 4k+2 .. 4k+7), as packed neighbour pairs
+                f32x2 P[4][3], Q[4][2];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const float *xr = xb + c * (kHtBoxW * kHtBoxH) + r * kHtBoxW;
+                    const float2 a2 = *reinterpret_cast<const float2 *>(xr);
+                    const float4 a4 = *reinterpret_cast<const float4 *>(xr + 2);
+                    P[r][0] = pack2(a2.x, a2.y); P[r][1] = pack2(a4.x, a4.y); P[r][2] = pack2(a4.z, a4.w);
+                    Q[r][0] = pack2(a2.y, a4.x); Q[r][1] = pack2(a4.y, a4.z);
+                }
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {
+                        const int t = dy * 3 + dx;
+                        const f32x2 w0 = pack2(wv[3 * t], wv[3 * t]), w1 = pack2(wv[3 * t + 1], wv[3 * t + 1]),
+                                    w2 = pack2(wv[3 * t + 2], wv[3 * t + 2]);
+#pragma unroll
+                        for (int o = 0; o < 2; ++o) {
+                            const f32x2 A0 = dx == 0 ? P[o + dy][0] : (dx == 1 ? Q[o + dy][0] : P[o + dy][1]);
+                            const f32x2 A1 = dx == 0 ? P[o + dy][1] : (dx == 1 ? Q[o + dy][1] : P[o + dy][2]);
+                            acc[o][0][0] = ffma2(A0, w0, acc[o][0][0]); acc[o][1][0] = ffma2(A1, w0, acc[o][1][0]);
+                            acc[o][0][1] = ffma2(A0, w1, acc[o][0][1]); acc[o][1][1] = ffma2(A1, w1, acc[o][1][1]);
+                            acc[o][0][2] = ffma2(A0, w2, acc[o][0][2]); acc[o][1][2] = ffma2(A1, w2, acc[o][1][2]);
+                        }
+                    }
+            }
+            __syncthreads();                              // every thread is done with this stage buffer
+            if (tid == 0 && u + 2 < my_units) issue(u + 2);
+        }
+        const int tile = blockIdx.x + j * gridDim.x;
+        const int txi = tile % tiles_x, tyi = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+        const int gx0 = txi * 64 + 4 * k - 1;             // pixels gx0 .. gx0+3; gx0+1 is a multiple of 4
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+            const int gy = tyi * kHtRows + 2 * rp + o;
+            if (gy >= h) continue;
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) {
+                float v[4];
+                unpack2(acc[o][0][co], v[0], v[1]);
+                unpack2(acc[o][1][co], v[2], v[3]);
+                const int64_t base = ((int64_t)b * COUT + co) * hw + (int64_t)gy * w + gx0;
+                // w % 4 == 0: pixels gx0+1, gx0+2 are inside together and 8-byte aligned
+                if (gx0 >= 0 && gx0 < w) y[base] = v[0] + (residual ? __ldg(residual + base) : 0.0f);
+                if (gx0 + 1 < w) {
+                    float2 r = make_float2(v[1], v[2]);
+                    if (residual) {
+                        const float2 t = __ldg(reinterpret_cast<const float2 *>(residual + base + 1));
+                        r.x += t.x; r.y += t.y;
+                    }
+                    *reinterpret_cast<float2 *>(y + base + 1) = r;
+                }
+                if (gx0 + 3 < w) y[base + 3] = v[3] + (residual ? __ldg(residual + base + 3) : 0.0f);
+            }
+        }
+    }
+}
+
 inline bool dims_ok(int64_t B, int64_t h, int64_t w)
 {
     return B >= 0 && B <= 65535 && h >= 0 && w >= 0 && h < (1 << 24) && w < (1 << 24) &&
@@ -628,9 +769,25 @@ extern "C" int wm_head_conv3x3_fwd(const float *x, const float *w3x3, const floa
     WM_REQUIRE(dims_ok(B, h, w), "wm_head_conv3x3_fwd: bad sizes");
     if (B == 0 || h == 0 || w == 0) return WM_OK;
     WM_REQUIRE(x && w3x3 && y, "wm_head_conv3x3_fwd: null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    // persistent TMA pipeline when its preconditions hold (WM_HEAD_LEGACY=1: developer A/B switch)
+    static const bool legacy = getenv("WM_HEAD_LEGACY") != nullptr;
+    CUtensorMap xmap;
+    const int ttx = (int)((w + 1 + 63) / 64), tty = (int)((h + kHtRows - 1) / kHtRows);   // tiles start at column 64t-1
+    const int64_t total = (int64_t)ttx * tty * B;
+    if (!legacy && w % 4 == 0 && aligned16(x) && (reinterpret_cast<uintptr_t>(y) & 7u) == 0 &&
+        (residual == nullptr || (reinterpret_cast<uintptr_t>(residual) & 7u) == 0) && total < ((int64_t)1 << 31) &&
+        tma::make_tmap_nchw(&xmap, x, B, 32, h, w, kHtBoxW, kHtBoxH, kHtCh)) {
+        WM_CUDA_OK(cudaFuncSetAttribute(head_conv3x3_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHtSmem));
+        const int grid = total < sm_count() ? (int)total : sm_count();
+        head_conv3x3_tma_kernel<<<grid, kHtThreads, kHtSmem, s>>>(xmap, w3x3, bias, residual, y, (int)h, (int)w, ttx,
+                                                                  tty, (int)total);
+        WM_LAUNCH_OK("head conv3x3 (TMA)");
+        return WM_OK;
+    }
     WM_CUDA_OK(cudaFuncSetAttribute(head_conv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHdSmem));
     dim3 grid((unsigned)((w + 2 * kHdTW - 1) / (2 * kHdTW)), (unsigned)((h + kTH - 1) / kTH), (unsigned)B);
-    head_conv3x3_kernel<<<grid, kHdThreads, kHdSmem, (cudaStream_t)stream>>>(x, w3x3, bias, residual, y,
+    head_conv3x3_kernel<<<grid, kHdThreads, kHdSmem, s>>>(x, w3x3, bias, residual, y,
                                                                              (int)h, (int)w);
     WM_LAUNCH_OK("head conv3x3");
     return WM_OK;
