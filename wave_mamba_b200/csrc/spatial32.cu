@@ -244,54 +244,64 @@ dw_act_pw_kernel(const float *__restrict__ x, const float *__restrict__ dw_w, co
 }
 
 // ---------------------------------------------------------------------------------------------
-// The same op as a persistent, TMA-fed pipeline (one CTA of 512 threads per SM): the cp.async form above
-// is bound by exposed load latency (ncu: 44 % long-scoreboard stalls, no pipe above 30 %), so here the
-// halo tile AND the residual tile of the NEXT 8x32 tile are requested (two cp.async.bulk.tensor boxes,
-// one mbarrier) before the current tile is computed.  Needs w % 4 == 0 and 16-byte aligned tensors.
-//   x box   40 x 10 x 32 channels at (tx0-4, ty0-1): halo column j is box column j+3 (the innermost
-//           start coordinate of a box must be a multiple of 16 bytes), zero fill outside the image
-//   dw      thread = (channel, 4 columns, 4 of the 8 rows), packed FFMA2, GELU, -> ds[32][256]
-//   1x1     thread = (4 adjacent pixels, 4 of the 32 outputs): per input channel one LDS.128 of weights
-//           and one of pixels feed 8 FFMA2 (the return path of the shared-memory loads is the bound of
-//           this phase); residual from its shared-memory tile, 16-byte stores
+// The same op as a persistent, warp-specialised, TMA-fed pipeline (one CTA of 512 threads per SM).  The
+// cp.async form above is bound by exposed load latency (ncu: 44 % long-scoreboard stalls, no pipe above
+// 30 %) and runs its two phases -- bound by different resources -- one after the other.  Here:
+//   thread 0     requests the halo box of the tile after next as soon as the depthwise warps have consumed
+//                a buffer (cp.async.bulk.tensor 40 x 10 x 32 channels at (tx0-4, ty0-1): halo column j is
+//                box column j+3 -- the innermost start coordinate must be a multiple of 16 bytes; zero
+//                fill outside the image), two buffers, one mbarrier each
+//   warps 0-7    depthwise 3x3 + GELU: thread = (channel, 4 columns), 8 rows with a sliding window, packed
+//                FFMA2 -> ds[tile & 1][32][256]
+//   warps 8-15   1x1 of the PREVIOUS tile: thread = (4 adjacent pixels, 8 of the 32 outputs); per input
+//                channel two LDS.128 of weights and one of pixels feed 16 FFMA2 (the return path of the
+//                shared-memory loads bounds this phase); the residual quads are fetched from global
+//                memory before the FMAs; 16-byte stores
+// The two groups hand the ds buffers over with named barriers (bar.arrive / bar.sync).  Needs w % 4 == 0
+// and 16-byte aligned tensors.
 // ---------------------------------------------------------------------------------------------
 constexpr int kTmBoxW = 40, kTmCS = kHH * kTmBoxW;          // 400 floats per channel
-constexpr int kTmThreads = 512;
-constexpr uint32_t kTmXBytes = 32 * kTmCS * 4, kTmRBytes = 32 * kDwPix * 4;
-constexpr size_t kTmSmem = 2 * kTmXBytes + 2 * kTmRBytes + sizeof(float) * (32 * kDwPix + 32 * 32 + 32 + 32 * 12) + 2 * 8;
+constexpr int kTmThreads = 512, kTmGroup = 256;
+constexpr uint32_t kTmXBytes = 32 * kTmCS * 4;
+constexpr size_t kTmSmem = 2 * kTmXBytes + sizeof(float) * (2 * 32 * kDwPix + 32 * 32 + 32 + 32 * 12) + 2 * 8;
+
+__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
 template <bool GELU, bool RES>
 __global__ void __launch_bounds__(kTmThreads, 1)
-dw_act_pw_tma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap rmap,
-                     const float *__restrict__ dw_w, const float *__restrict__ dw_b,
-                     const float *__restrict__ pw_w, const float *__restrict__ pw_b, float *__restrict__ y,
+dw_act_pw_tma_kernel(const __grid_constant__ CUtensorMap xmap, const float *__restrict__ dw_w,
+                     const float *__restrict__ dw_b, const float *__restrict__ pw_w,
+                     const float *__restrict__ pw_b, const float *__restrict__ residual, float *__restrict__ y,
                      int h, int w, int tiles_x, int tiles_y, int total_tiles)
 {
     using namespace wm::tc5;
     constexpr int C = 32;
+    constexpr int kBarFull = 1, kBarEmpty = 3, kBarDw = 5;                 // named barriers: +buffer index
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *xs = reinterpret_cast<float *>(smem_raw);                       // [2][32][10][40]
-    float *rs = reinterpret_cast<float *>(smem_raw + 2 * kTmXBytes);       // [2][32][8][32]
-    float *ds = rs + 2 * C * kDwPix;                                       // [32][256] after dw + act
-    float *wt = ds + C * kDwPix;                                           // [32 ci][32 co]
+    float *ds = reinterpret_cast<float *>(smem_raw + 2 * kTmXBytes);       // [2][32][256] after dw + act
+    float *wt = ds + 2 * C * kDwPix;                                       // [32 ci][32 co]
     float *pb = wt + C * C;
     float *dwk = pb + C;                                                   // [32][12]
-    const uint32_t bar0 = smem_u32(dwk + C * 12);                          // full[2]
+    const uint32_t bar0 = smem_u32(dwk + C * 12);                          // full[2] of the halo buffers
     const int tid = threadIdx.x;
     const int64_t hw = (int64_t)h * w;
+    const int my_tiles = ((int)blockIdx.x < total_tiles) ? (total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
-    auto issue = [&](int tile, int buf) {
+    auto issue = [&](int j) {
+        const int tile = blockIdx.x + j * gridDim.x;
         const int txi = tile % tiles_x, tyi = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
-        const uint32_t bar = bar0 + 8u * (uint32_t)buf;
-        mbar_expect_tx(bar, kTmXBytes + (RES ? kTmRBytes : 0u));
-        tma::load_box(smem_u32(xs) + (uint32_t)buf * kTmXBytes, &xmap, txi * kDwTW - 4, tyi * kTH - 1, 0, b, bar);
-        if (RES) tma::load_box(smem_u32(rs) + (uint32_t)buf * kTmRBytes, &rmap, txi * kDwTW, tyi * kTH, 0, b, bar);
+        const uint32_t bar = bar0 + 8u * (uint32_t)(j & 1);
+        mbar_expect_tx(bar, kTmXBytes);
+        tma::load_box(smem_u32(xs) + (uint32_t)(j & 1) * kTmXBytes, &xmap, txi * kDwTW - 4, tyi * kTH - 1, 0, b, bar);
     };
     if (tid == 0) {
         mbar_init(bar0, 1);
         mbar_init(bar0 + 8u, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        issue(blockIdx.x, 0);
+        if (my_tiles > 0) issue(0);
+        if (my_tiles > 1) issue(1);
     }
     for (int i = tid; i < C * C; i += kTmThreads) {
         const int co = i / C, ci = i - co * C;
@@ -304,34 +314,26 @@ dw_act_pw_tma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_cons
     }
     __syncthreads();
 
-    // depthwise role: (channel, 4 columns, row half); 1x1 role: (pixel quad, output quad)
-    const int rhalf = tid >> 8, dc = (tid & 255) >> 3, j4 = (tid & 7) * 4;
-    const int q = tid & 7, pq = tid >> 3;
-    f32x2 k2[9];
-    f32x2 bias2;
-    {
-        const float4 *kp = reinterpret_cast<const float4 *>(dwk + dc * 12);
-        const float4 ka = kp[0], kb = kp[1], kc = kp[2];
-        k2[0] = pack2(ka.x, ka.x); k2[1] = pack2(ka.y, ka.y); k2[2] = pack2(ka.z, ka.z);
-        k2[3] = pack2(ka.w, ka.w); k2[4] = pack2(kb.x, kb.x); k2[5] = pack2(kb.y, kb.y);
-        k2[6] = pack2(kb.z, kb.z); k2[7] = pack2(kb.w, kb.w); k2[8] = pack2(kc.x, kc.x);
-        bias2 = pack2(kc.y, kc.y);
-    }
-    const f32x2 pb0 = reinterpret_cast<const f32x2 *>(pb)[q * 2], pb1 = reinterpret_cast<const f32x2 *>(pb)[q * 2 + 1];
-
-    uint32_t it = 0;
-#pragma unroll 1
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        // the other buffer was released by the barrier that ended the previous iteration
-        if (tid == 0 && tile + (int)gridDim.x < total_tiles) issue(tile + gridDim.x, buf ^ 1);
-        mbar_wait(bar0 + 8u * (uint32_t)buf, (it >> 1) & 1u);
-        const int txi = tile % tiles_x, tyi = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
-        const int tx0 = txi * kDwTW, ty0 = tyi * kTH;
-
+    if (tid < kTmGroup) {
+        // =========================== depthwise 3x3 (+ GELU) ====================================
+        const int dc = tid >> 3, j4 = (tid & 7) * 4;
+        f32x2 k2[9];
+        f32x2 bias2;
         {
+            const float4 *kp = reinterpret_cast<const float4 *>(dwk + dc * 12);
+            const float4 ka = kp[0], kb = kp[1], kc = kp[2];
+            k2[0] = pack2(ka.x, ka.x); k2[1] = pack2(ka.y, ka.y); k2[2] = pack2(ka.z, ka.z);
+            k2[3] = pack2(ka.w, ka.w); k2[4] = pack2(kb.x, kb.x); k2[5] = pack2(kb.y, kb.y);
+            k2[6] = pack2(kb.z, kb.z); k2[7] = pack2(kb.w, kb.w); k2[8] = pack2(kc.x, kc.x);
+            bias2 = pack2(kc.y, kc.y);
+        }
+#pragma unroll 1
+        for (int j = 0; j < my_tiles; ++j) {
+            const int buf = j & 1;
+            mbar_wait(bar0 + 8u * (uint32_t)buf, (uint32_t)(j >> 1) & 1u);
+            if (j >= 2) bar_sync(kBarEmpty + buf, kTmThreads);          // the 1x1 warps are done with ds[buf]
             // halo columns j4 .. j4+5 = box columns j4+3 .. j4+8: a scalar, an aligned LDS.128, a scalar
-            const float *pc = xs + buf * (C * kTmCS) + dc * kTmCS + (rhalf * 4) * kTmBoxW + j4 + 3;
+            const float *pc = xs + buf * (C * kTmCS) + dc * kTmCS + j4 + 3;
             f32x2 P[3][3], Q[3][2];
             auto load_row = [&](int r, int slot) {
                 const float v0 = pc[r * kTmBoxW];
@@ -342,9 +344,9 @@ dw_act_pw_tma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_cons
             };
             load_row(0, 0);
             load_row(1, 1);
-            float *dp = ds + dc * kDwPix + (rhalf * 4) * kDwTW + j4;
+            float *dp = ds + buf * (C * kDwPix) + dc * kDwPix + j4;
 #pragma unroll
-            for (int row = 0; row < 4; ++row) {
+            for (int row = 0; row < kTH; ++row) {
                 load_row(row + 2, (row + 2) % 3);
                 f32x2 oa = bias2, ob = bias2;
 #pragma unroll
@@ -360,47 +362,70 @@ dw_act_pw_tma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_cons
                 unpack2(ob, o2, o3);
                 *reinterpret_cast<float4 *>(dp + row * kDwTW) = make_float4(o0, o1, o2, o3);
             }
+            bar_arrive(kBarFull + buf, kTmThreads);                     // ds[buf] is complete
+            bar_sync(kBarDw, kTmGroup);                                 // every depthwise thread has left xs[buf]
+            if (tid == 0 && j + 2 < my_tiles) issue(j + 2);
         }
-        __syncthreads();
-
-        {
-            f32x2 acc[4][2];
+    } else {
+        // =========================== 1x1 + residual ============================================
+        const int t = tid - kTmGroup;
+        const int q = t & 3, pq = t >> 2;                 // output quarter, pixel quad 0..63
+        f32x2 pbq[4];
 #pragma unroll
-            for (int p = 0; p < 4; ++p) { acc[p][0] = pb0; acc[p][1] = pb1; }
-#pragma unroll 8
+        for (int i = 0; i < 4; ++i) pbq[i] = reinterpret_cast<const f32x2 *>(pb)[q * 4 + i];
+#pragma unroll 1
+        for (int j = 0; j < my_tiles; ++j) {
+            const int buf = j & 1;
+            const int tile = blockIdx.x + j * gridDim.x;
+            const int txi = tile % tiles_x, tyi = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+            const int gy = tyi * kTH + (pq >> 3), gx = txi * kDwTW + (pq & 7) * 4;
+            const bool inside = gy < h && gx < w;         // w % 4 == 0: the four pixels are inside or outside together
+            const int64_t o = (int64_t)b * C * hw + (int64_t)gy * w + gx + (int64_t)(q * 8) * hw;
+            float4 rv[8];
+            if (RES && inside) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) rv[i] = __ldg(reinterpret_cast<const float4 *>(residual + o + (int64_t)i * hw));
+            }
+            bar_sync(kBarFull + buf, kTmThreads);                       // ds[buf] is complete
+            f32x2 acc[4][4];
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[p][i] = pbq[i];
+            const float *dsb = ds + buf * (C * kDwPix) + pq * 4;
+#pragma unroll 4
             for (int ci = 0; ci < C; ++ci) {
-                const float4 xv = *reinterpret_cast<const float4 *>(ds + ci * kDwPix + pq * 4);
-                const ulonglong2 wv = *reinterpret_cast<const ulonglong2 *>(wt + ci * C + q * 4);
+                const float4 xv = *reinterpret_cast<const float4 *>(dsb + ci * kDwPix);
                 const f32x2 x2[4] = {pack2(xv.x, xv.x), pack2(xv.y, xv.y), pack2(xv.z, xv.z), pack2(xv.w, xv.w)};
+                const ulonglong2 *wr = reinterpret_cast<const ulonglong2 *>(wt + ci * C + q * 8);
+                const ulonglong2 wa = wr[0], wb = wr[1];
 #pragma unroll
                 for (int p = 0; p < 4; ++p) {
-                    acc[p][0] = ffma2(x2[p], wv.x, acc[p][0]);
-                    acc[p][1] = ffma2(x2[p], wv.y, acc[p][1]);
+                    acc[p][0] = ffma2(x2[p], wa.x, acc[p][0]);
+                    acc[p][1] = ffma2(x2[p], wa.y, acc[p][1]);
+                    acc[p][2] = ffma2(x2[p], wb.x, acc[p][2]);
+                    acc[p][3] = ffma2(x2[p], wb.y, acc[p][3]);
                 }
             }
-            const int gy = ty0 + (pq >> 3), gx = tx0 + (pq & 7) * 4;
-            if (gy < h && gx < w) {       // w % 4 == 0: the four pixels are inside or outside together
-                float v[4][4];            // [output][pixel]
+            if (j + 2 < my_tiles) bar_arrive(kBarEmpty + buf, kTmThreads);   // ds[buf] may be overwritten
+            if (inside) {
 #pragma unroll
-                for (int p = 0; p < 4; ++p) {
-                    unpack2(acc[p][0], v[0][p], v[1][p]);
-                    unpack2(acc[p][1], v[2][p], v[3][p]);
-                }
-                const int64_t o = (int64_t)b * C * hw + (int64_t)gy * w + gx;
-                const float *rp = rs + buf * (C * kDwPix) + pq * 4;
+                for (int i = 0; i < 4; ++i) {
+                    float v[2][4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int co = q * 4 + j;
-                    float4 r = make_float4(v[j][0], v[j][1], v[j][2], v[j][3]);
-                    if (RES) {
-                        const float4 t = *reinterpret_cast<const float4 *>(rp + co * kDwPix);
-                        r.x += t.x; r.y += t.y; r.z += t.z; r.w += t.w;
+                    for (int p = 0; p < 4; ++p) unpack2(acc[p][i], v[0][p], v[1][p]);
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        float4 r = make_float4(v[k][0], v[k][1], v[k][2], v[k][3]);
+                        if (RES) {
+                            const float4 u = rv[2 * i + k];
+                            r.x += u.x; r.y += u.y; r.z += u.z; r.w += u.w;
+                        }
+                        *reinterpret_cast<float4 *>(y + o + (int64_t)(2 * i + k) * hw) = r;
                     }
-                    *reinterpret_cast<float4 *>(y + o + (int64_t)co * hw) = r;
                 }
             }
         }
-        __syncthreads();                  // ds and this buffer may be overwritten
     }
 }
 
@@ -718,16 +743,15 @@ extern "C" int wm_dw_act_pw_fwd(const float *x, const float *dw_w, const float *
     const int64_t total = (int64_t)tiles_x * tiles_y * B;
     // persistent TMA pipeline when its preconditions hold (WM_DW_ACT_PW_LEGACY=1: developer A/B switch)
     static const bool legacy = getenv("WM_DW_ACT_PW_LEGACY") != nullptr;
-    CUtensorMap xmap, rmap;
+    CUtensorMap xmap;
     if (!legacy && w % 4 == 0 && aligned16(x) && aligned16(y) && (residual == nullptr || aligned16(residual)) &&
-        total < ((int64_t)1 << 31) && tma::make_tmap_nchw(&xmap, x, B, 32, h, w, kTmBoxW, kHH, 32) &&
-        tma::make_tmap_nchw(&rmap, residual ? residual : x, B, 32, h, w, kDwTW, kTH, 32)) {
+        total < ((int64_t)1 << 31) && tma::make_tmap_nchw(&xmap, x, B, 32, h, w, kTmBoxW, kHH, 32)) {
         const int grid = total < sm_count() ? (int)total : sm_count();
 #define WM_DWPW_TMA(G, R)                                                                                   \
     do {                                                                                                    \
         WM_CUDA_OK(cudaFuncSetAttribute(dw_act_pw_tma_kernel<G, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                         (int)kTmSmem));                                                     \
-        dw_act_pw_tma_kernel<G, R><<<grid, kTmThreads, kTmSmem, s>>>(xmap, rmap, dw_w, dw_b, pw_w, pw_b, y, (int)h, \
+        dw_act_pw_tma_kernel<G, R><<<grid, kTmThreads, kTmSmem, s>>>(xmap, dw_w, dw_b, pw_w, pw_b, residual, y, (int)h, \
                                                                      (int)w, tiles_x, tiles_y, (int)total); \
     } while (0)
         if (act == 1 && residual) WM_DWPW_TMA(true, true);
