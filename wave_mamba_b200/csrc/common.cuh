@@ -40,6 +40,7 @@ void set_error(const char *fmt, ...);
     } while (0)
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline bool aligned32(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; }
 
 // Number of SMs of the current device (cached per process; B200 = 148).
 int sm_count();
@@ -61,6 +62,24 @@ __device__ __forceinline__ void st_stream4(float *p, float4 v)
 {
     asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
                  "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+// 256-bit forms (sm_100: LDG.E.256 / STG.E.256; 32-byte aligned): half the LSU instructions of a
+// streaming kernel whose warps otherwise stall on the load/store queue (lg_throttle).
+struct float8 { float4 lo, hi; };
+__device__ __forceinline__ float8 ld_stream8(const float *p)
+{
+    float8 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v.lo.x), "=f"(v.lo.y), "=f"(v.lo.z), "=f"(v.lo.w), "=f"(v.hi.x), "=f"(v.hi.y),
+                   "=f"(v.hi.z), "=f"(v.hi.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream8(float *p, float4 a, float4 b)
+{
+    asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a.x), "f"(a.y),
+                 "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w)
                  : "memory");
 }
 __device__ __forceinline__ float ex2_approx(float x)

@@ -9,6 +9,8 @@
 // one 128-bit store per band (DWT), or the mirror image (IWT).  Loads use the read-only,
 // no-L1-allocate path; stores are evict-first.  Persistent grid-stride over
 // SMs x 8 CTAs x 256 threads keeps >= 128 KB of loads in flight per SM.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace wm {
@@ -50,6 +52,40 @@ dwt_vec_kernel(const float *__restrict__ x, float *__restrict__ ll, float *__res
         st_stream4(hl + o, ohl);
         st_stream4(lh + o, olh);
         st_stream4(hh + o, ohh);
+    }
+}
+
+// 256-bit form: a thread owns a 2 x 16 input patch (two 32-byte loads per row) and emits one 32-byte
+// store per band (W % 16 == 0, 32-byte aligned tensors); half the load/store instructions.
+__device__ __forceinline__ void haar_analysis8(const float8 &t, const float8 &b, float4 &oll, float4 &ohl,
+                                               float4 &olh, float4 &ohh)
+{
+    haar_analysis(t.lo.x * 0.5f, b.lo.x * 0.5f, t.lo.y * 0.5f, b.lo.y * 0.5f, oll.x, ohl.x, olh.x, ohh.x);
+    haar_analysis(t.lo.z * 0.5f, b.lo.z * 0.5f, t.lo.w * 0.5f, b.lo.w * 0.5f, oll.y, ohl.y, olh.y, ohh.y);
+    haar_analysis(t.hi.x * 0.5f, b.hi.x * 0.5f, t.hi.y * 0.5f, b.hi.y * 0.5f, oll.z, ohl.z, olh.z, ohh.z);
+    haar_analysis(t.hi.z * 0.5f, b.hi.z * 0.5f, t.hi.w * 0.5f, b.hi.w * 0.5f, oll.w, ohl.w, olh.w, ohh.w);
+}
+
+__global__ void __launch_bounds__(kThreads)
+dwt_vec8_kernel(const float *__restrict__ x, float *__restrict__ ll, float *__restrict__ hl,
+                float *__restrict__ lh, float *__restrict__ hh, int64_t out_rows, int w8, int64_t W)
+{
+    const int64_t items = out_rows * w8;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t it = (int64_t)blockIdx.x * kThreads + threadIdx.x; it < items; it += stride) {
+        const int64_t r = it / w8;
+        const int q = (int)(it - r * w8);
+        const float *top = x + (2 * r) * W + 16 * q;
+        const float8 t0 = ld_stream8(top), t1 = ld_stream8(top + 8);
+        const float8 b0 = ld_stream8(top + W), b1 = ld_stream8(top + W + 8);
+        float4 oll[2], ohl[2], olh[2], ohh[2];
+        haar_analysis8(t0, b0, oll[0], ohl[0], olh[0], ohh[0]);
+        haar_analysis8(t1, b1, oll[1], ohl[1], olh[1], ohh[1]);
+        const int64_t o = r * (8 * (int64_t)w8) + 8 * q;
+        st_stream8(ll + o, oll[0], oll[1]);
+        st_stream8(hl + o, ohl[0], ohl[1]);
+        st_stream8(lh + o, olh[0], olh[1]);
+        st_stream8(hh + o, ohh[0], ohh[1]);
     }
 }
 
@@ -116,6 +152,45 @@ iwt_vec_kernel(const float *__restrict__ low, int64_t low_bstride, const float *
     }
 }
 
+// The same with 256-bit accesses: a thread owns 8 coefficient columns = one 32-byte load per band and two
+// 32-byte stores per output row (w % 8 == 0, 32-byte aligned tensors).  Half the load/store
+// instructions: the 128-bit form spends 27 % of its warp time stalled on the LSU queue (ncu lg_throttle).
+__global__ void __launch_bounds__(kThreads)
+iwt_vec8_kernel(const float *__restrict__ low, int64_t low_bstride, const float *__restrict__ high,
+                int64_t high_bstride, float *__restrict__ y, int C, int h, int w8)
+{
+    const int w = 8 * w8;
+    const int64_t hw = (int64_t)h * w;
+    const int plane = blockIdx.y;
+    const int b = plane / C, c = plane - b * C;
+    const float *lp = low + (int64_t)b * low_bstride + (int64_t)c * hw;
+    const float *hq = high + (int64_t)b * high_bstride + (int64_t)c * hw;
+    const float *hr = hq + (int64_t)C * hw, *hs = hq + 2 * (int64_t)C * hw;
+    float *yp = y + (int64_t)plane * 4 * hw;
+    const int items = h * w8;
+    const int stride = gridDim.x * kThreads;
+    for (int it = blockIdx.x * kThreads + threadIdx.x; it < items; it += stride) {
+        const int i = it / w8, q = it - i * w8;
+        const int in_off = i * w + 8 * q;
+        const float8 vp = ld_stream8(lp + in_off), vq = ld_stream8(hq + in_off);
+        const float8 vr = ld_stream8(hr + in_off), vs = ld_stream8(hs + in_off);
+        float4 e[4], o[4];   // even / odd output row, 16 floats each
+        haar_synthesis(vp.lo.x * 0.5f, vq.lo.x * 0.5f, vr.lo.x * 0.5f, vs.lo.x * 0.5f, e[0].x, o[0].x, e[0].y, o[0].y);
+        haar_synthesis(vp.lo.y * 0.5f, vq.lo.y * 0.5f, vr.lo.y * 0.5f, vs.lo.y * 0.5f, e[0].z, o[0].z, e[0].w, o[0].w);
+        haar_synthesis(vp.lo.z * 0.5f, vq.lo.z * 0.5f, vr.lo.z * 0.5f, vs.lo.z * 0.5f, e[1].x, o[1].x, e[1].y, o[1].y);
+        haar_synthesis(vp.lo.w * 0.5f, vq.lo.w * 0.5f, vr.lo.w * 0.5f, vs.lo.w * 0.5f, e[1].z, o[1].z, e[1].w, o[1].w);
+        haar_synthesis(vp.hi.x * 0.5f, vq.hi.x * 0.5f, vr.hi.x * 0.5f, vs.hi.x * 0.5f, e[2].x, o[2].x, e[2].y, o[2].y);
+        haar_synthesis(vp.hi.y * 0.5f, vq.hi.y * 0.5f, vr.hi.y * 0.5f, vs.hi.y * 0.5f, e[2].z, o[2].z, e[2].w, o[2].w);
+        haar_synthesis(vp.hi.z * 0.5f, vq.hi.z * 0.5f, vr.hi.z * 0.5f, vs.hi.z * 0.5f, e[3].x, o[3].x, e[3].y, o[3].y);
+        haar_synthesis(vp.hi.w * 0.5f, vq.hi.w * 0.5f, vr.hi.w * 0.5f, vs.hi.w * 0.5f, e[3].z, o[3].z, e[3].w, o[3].w);
+        float *out = yp + (int64_t)(2 * i) * (2 * w) + 16 * q;
+        st_stream8(out, e[0], e[1]);
+        st_stream8(out + 8, e[2], e[3]);
+        st_stream8(out + 2 * w, o[0], o[1]);
+        st_stream8(out + 2 * w + 8, o[2], o[3]);
+    }
+}
+
 __global__ void __launch_bounds__(kThreads)
 iwt_scalar_kernel(const float *__restrict__ low, int64_t low_bstride,
                   const float *__restrict__ high, int64_t high_bstride, float *__restrict__ y,
@@ -169,7 +244,11 @@ extern "C" int wm_dwt_haar_fwd(const float *x, float *ll, float *hl, float *lh, 
     const int64_t h = H / 2, w = W / 2, out_rows = planes * h;
     const bool vec = (W % 8 == 0) && aligned16(x) && aligned16(ll) && aligned16(hl) &&
                      aligned16(lh) && aligned16(hh);
-    if (vec) {
+    static const bool no256 = getenv("WM_IWT_128") != nullptr;     // developer A/B switch (both transforms)
+    if (vec && !no256 && W % 16 == 0 && aligned32(x) && aligned32(ll) && aligned32(hl) && aligned32(lh) && aligned32(hh)) {
+        const int w8 = (int)(w / 8);
+        dwt_vec8_kernel<<<stream_grid(out_rows * w8), kThreads, 0, s>>>(x, ll, hl, lh, hh, out_rows, w8, W);
+    } else if (vec) {
         const int w4 = (int)(w / 4);
         dwt_vec_kernel<<<stream_grid(out_rows * w4), kThreads, 0, s>>>(x, ll, hl, lh, hh, out_rows,
                                                                         w4, W);
@@ -195,7 +274,19 @@ extern "C" int wm_iwt_haar_fwd(const float *low, int64_t low_bstride, const floa
     cudaStream_t s = (cudaStream_t)stream;
     const bool vec = (w % 4 == 0) && aligned16(low) && aligned16(high) && aligned16(y) &&
                      (low_bstride % 4 == 0) && (high_bstride % 4 == 0);
-    if (vec && B * C <= 65535 && h * (w / 4) < ((int64_t)1 << 30)) {
+    // WM_IWT_128=1: developer A/B switch for the 128-bit form
+    static const bool no256 = getenv("WM_IWT_128") != nullptr;
+    const bool vec8 = vec && !no256 && (w % 8 == 0) && aligned32(low) && aligned32(high) && aligned32(y) &&
+                      (low_bstride % 8 == 0) && (high_bstride % 8 == 0) && ((C * h * w) % 8 == 0);
+    if (vec8 && B * C <= 65535 && h * (w / 8) < ((int64_t)1 << 30)) {
+        const int w8 = (int)(w / 8);
+        const int64_t planes = B * C;
+        const int64_t per_plane = (h * w8 + kThreads - 1) / kThreads;
+        int64_t gx = ((int64_t)sm_count() * 8 + planes - 1) / planes;      // ~8 CTAs per SM in total
+        gx = gx < per_plane ? gx : per_plane;
+        dim3 grid((unsigned)(gx > 0 ? gx : 1), (unsigned)planes);
+        iwt_vec8_kernel<<<grid, kThreads, 0, s>>>(low, low_bstride, high, high_bstride, y, (int)C, (int)h, w8);
+    } else if (vec && B * C <= 65535 && h * (w / 4) < ((int64_t)1 << 30)) {
         const int w4 = (int)(w / 4);
         const int64_t planes = B * C;
         const int64_t per_plane = (h * w4 + kThreads - 1) / kThreads;

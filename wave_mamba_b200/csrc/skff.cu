@@ -31,7 +31,18 @@ skff_pool_kernel(const float *__restrict__ f0, const float *__restrict__ f1,
     const int64_t plane = blockIdx.y;
     const float *p0 = f0 + plane * hw, *p1 = f1 + plane * hw, *p2 = f2 + plane * hw;
     float acc = 0.0f;
-    if (vec) {
+    if (vec == 2) {      // 256-bit loads (hw % 8 == 0, 32-byte aligned planes): half the LSU instructions
+        const int64_t n8 = hw >> 3;
+        float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = a4;
+        for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n8; i += (int64_t)nblk * kThreads) {
+            const float8 a = ld_stream8(p0 + 8 * i), b = ld_stream8(p1 + 8 * i), c = ld_stream8(p2 + 8 * i);
+            a4.x += (a.lo.x + b.lo.x) + c.lo.x; a4.y += (a.lo.y + b.lo.y) + c.lo.y;
+            a4.z += (a.lo.z + b.lo.z) + c.lo.z; a4.w += (a.lo.w + b.lo.w) + c.lo.w;
+            b4.x += (a.hi.x + b.hi.x) + c.hi.x; b4.y += (a.hi.y + b.hi.y) + c.hi.y;
+            b4.z += (a.hi.z + b.hi.z) + c.hi.z; b4.w += (a.hi.w + b.hi.w) + c.hi.w;
+        }
+        acc = ((a4.x + a4.y) + (a4.z + a4.w)) + ((b4.x + b4.y) + (b4.z + b4.w));
+    } else if (vec) {
         const int64_t n4 = hw >> 2;
         float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n4; i += (int64_t)nblk * kThreads) {
@@ -106,7 +117,25 @@ skff_apply_kernel(const float *__restrict__ f0, const float *__restrict__ f1,
     float *po = out + plane * hw;
     const int64_t stride = (int64_t)gridDim.x * kThreads;
     // V = (f0 a0 + f1 a1) + f2 a2 with separate multiplies and adds, as torch.sum(x * a, dim=1)  (:957)
-    if (vec) {
+    auto mix = [&](const float4 &x, const float4 &y, const float4 &z) {
+        float4 r;
+        r.x = __fadd_rn(__fadd_rn(__fmul_rn(x.x, a0), __fmul_rn(y.x, a1)), __fmul_rn(z.x, a2));
+        r.y = __fadd_rn(__fadd_rn(__fmul_rn(x.y, a0), __fmul_rn(y.y, a1)), __fmul_rn(z.y, a2));
+        r.z = __fadd_rn(__fadd_rn(__fmul_rn(x.z, a0), __fmul_rn(y.z, a1)), __fmul_rn(z.z, a2));
+        r.w = __fadd_rn(__fadd_rn(__fmul_rn(x.w, a0), __fmul_rn(y.w, a1)), __fmul_rn(z.w, a2));
+        return r;
+    };
+    if (vec == 2) {
+        const int64_t n8 = hw >> 3;
+        for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n8; i += stride) {
+            const float8 x = ld_stream8(p0 + 8 * i), y = ld_stream8(p1 + 8 * i), z = ld_stream8(p2 + 8 * i);
+            const float4 rl = mix(x.lo, y.lo, z.lo), rh = mix(x.hi, y.hi, z.hi);
+            // plain (not evict-first) store: the next kernel reads this map
+            asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(po + 8 * i), "f"(rl.x), "f"(rl.y),
+                         "f"(rl.z), "f"(rl.w), "f"(rh.x), "f"(rh.y), "f"(rh.z), "f"(rh.w)
+                         : "memory");
+        }
+    } else if (vec) {
         const int64_t n4 = hw >> 2;
         for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n4; i += stride) {
             const float4 x = ld_stream4(p0 + 4 * i), y = ld_stream4(p1 + 4 * i), z = ld_stream4(p2 + 4 * i);
@@ -234,7 +263,8 @@ extern "C" int wm_skff_fwd(const float *f0, const float *f1, const float *f2, co
     WM_REQUIRE(workspace && workspace_bytes >= (size_t)B * kC * nblk * sizeof(double),
                "wm_skff_fwd: workspace too small");
     WM_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 7u) == 0, "wm_skff_fwd: workspace must be 8-byte aligned");
-    const int vec = (hw % 4 == 0 && aligned16(f0) && aligned16(f1) && aligned16(f2) && aligned16(out)) ? 1 : 0;
+    int vec = (hw % 4 == 0 && aligned16(f0) && aligned16(f1) && aligned16(f2) && aligned16(out)) ? 1 : 0;
+    if (vec && hw % 8 == 0 && aligned32(f0) && aligned32(f1) && aligned32(f2) && aligned32(out)) vec = 2;
     cudaStream_t s = (cudaStream_t)stream;
     double *partial = static_cast<double *>(workspace);
     skff_pool_kernel<<<dim3(nblk, (unsigned)(B * kC)), kThreads, 0, s>>>(f0, f1, f2, partial, hw, vec);
