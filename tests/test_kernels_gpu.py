@@ -433,6 +433,28 @@ def test_lfss_z_and_out(ops, dev):
         torch.testing.assert_close(got, want, rtol=3e-5, atol=3e-5)
 
 
+@pytest.mark.parametrize("hw", [(12, 20), (200, 160)])
+def test_lfss_out_four_planes_tma(ops, dev, hw):
+    """The production call: four direction planes summed in the order ((y0 + y2) + y1) + y3.  hw % 4 == 0
+    takes the TMA pipeline (64-pixel tiles): 240 pixels leave a partial tile, 32000 x 2 images are 1000
+    tiles = several per persistent CTA."""
+    g = torch.Generator().manual_seed(112)
+    B, (h, w) = 2, hw
+    x = _rand(B, 32, h, w, g=g)
+    zs = F.silu(_rand(B, 64, h, w, g=g))
+    ys = [_rand(B, 64, h, w, g=g) for _ in range(4)]
+    on_w, on_b = 1 + _rand(64, g=g, s=0.1), _rand(64, g=g, s=0.1)
+    w_out = _rand(32, 64, g=g, s=0.2)
+    skip = 1 + _rand(32, g=g, s=0.2)
+    ysum = ((ys[0] + ys[1]) + ys[2]) + ys[3]
+    yn = F.layer_norm(ysum.permute(0, 2, 3, 1), (64,), on_w, on_b, 1e-5)
+    want = x * skip.view(1, -1, 1, 1) + F.linear(yn * zs.permute(0, 2, 3, 1), w_out).permute(0, 3, 1, 2)
+    d = lambda v: v.to(dev)
+    got = ops.lfss_out(d(ys[0]), d(zs), d(on_w), d(on_b), 1e-5, d(w_out), d(x), d(skip),
+                       extra=(d(ys[1]), d(ys[2]), d(ys[3]))).cpu()
+    torch.testing.assert_close(got, want, rtol=3e-5, atol=3e-5)
+
+
 def test_pw_gate_with_scaled_residual(ops, dev):
     g = torch.Generator().manual_seed(13)
     x = _rand(2, 64, 11, 29, g=g)

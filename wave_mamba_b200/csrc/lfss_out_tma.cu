@@ -1,0 +1,243 @@
+// SS2D tail of an LFSSBlock as a persistent, warp-specialised, TMA-fed pipeline (one CTA of 192 threads
+// per SM):   out = x * skip_scale + out_proj( LayerNorm_64( ((y0 + y2) + y1) + y3 ) * silu(z) )
+// (reference wavemamba_arch.py:490-494, 525; the four direction planes of wm_ss2d_dirs_fwd, zs of
+// wm_lfss_z_fwd).  The op moves 384 channel planes per call and is pointwise in the pixel, so a tile is 64
+// consecutive pixels of one image: five TMA boxes (64 pixels x 64 channels of each direction plane and
+// of z, 80 KB) per tile and stage, two stages, requested two tiles ahead.  The register-staged form in
+// pixelwise.cu is bound by exposed load latency (ncu: 61 % long-scoreboard stalls at 24 % occupancy).
+//   thread 0     requests the boxes of the tile after next once the LayerNorm warps have left a stage
+//   warps 0-3    lane pair = pixel (32 channels each): direction sum, LayerNorm statistics exchanged with
+//                one shuffle, affine, * z  ->  v[tile & 1][64 channels][64 pixels]
+//   warps 4-5    out_proj of the PREVIOUS tile: thread = (4 adjacent pixels, 8 of the 32 outputs), per
+//                input channel one LDS.128 of pixels and two of weights feed 16 FFMA2; x (the residual
+//                input) comes straight from global memory, fetched before the FMAs; 16-byte stores
+// The two groups hand the v buffers over with named barriers.  Needs hw % 4 == 0, all four planes and
+// 16-byte aligned tensors; wm_lfss_out_fwd falls back to the register-staged kernels otherwise.
+#include "tma.cuh"
+
+namespace wm {
+namespace lfss {
+
+using namespace wm::tc5;
+
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+constexpr int kTP = 64;                       // pixels per tile
+constexpr int kC = 64, kCout = 32;
+constexpr int kThreadsA = 128, kThreadsB = 64, kThreads = kThreadsA + kThreadsB;
+constexpr uint32_t kBoxBytes = kC * kTP * 4;  // 16 KB
+constexpr uint32_t kStageBytes = 5 * kBoxBytes;
+constexpr size_t kSmem = 2 * kStageBytes + 2 * kBoxBytes + sizeof(float) * (kC * kCout + 2 * kC + kCout) + 2 * 8;
+
+struct Maps {
+    CUtensorMap p[4];    // direction planes in summation order
+    CUtensorMap z;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+lfss_out_tma_kernel(const __grid_constant__ Maps maps, const float *__restrict__ on_w,
+                    const float *__restrict__ on_b, float eps, const float *__restrict__ w_out,
+                    const float *__restrict__ x, const float *__restrict__ skip_scale, float *__restrict__ out,
+                    int64_t hw, int tiles_per_img, int total_tiles)
+{
+    constexpr int kBarFull = 1, kBarEmpty = 3, kBarA = 5;                  // named barriers: +buffer index
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *stage = reinterpret_cast<float *>(smem_raw);                    // [2][5][64 ch][64 px]
+    float *vbuf = reinterpret_cast<float *>(smem_raw + 2 * kStageBytes);   // [2][64 ch][64 px]
+    float *wt = vbuf + 2 * kC * kTP;                                       // [64 ci][32 co]
+    float *lw = wt + kC * kCout, *lb = lw + kC, *rs = lb + kC;
+    const uint32_t bar0 = smem_u32(rs + kCout);
+    const int tid = threadIdx.x;
+    const int my_tiles = ((int)blockIdx.x < total_tiles) ? (total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    auto issue = [&](int j) {
+        const int tile = blockIdx.x + j * gridDim.x;
+        const int b = tile / tiles_per_img, px0 = (tile - b * tiles_per_img) * kTP;
+        const uint32_t bar = bar0 + 8u * (uint32_t)(j & 1);
+        const uint32_t dst = smem_u32(stage) + (uint32_t)(j & 1) * kStageBytes;
+        mbar_expect_tx(bar, kStageBytes);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const CUtensorMap *m = &maps.p[k];
+            asm volatile(
+                "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
+                    "r"(dst + (uint32_t)k * kBoxBytes), "l"(reinterpret_cast<uint64_t>(m)), "r"(px0), "r"(b * kC), "r"(bar)
+                : "memory");
+        }
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
+                "r"(dst + 4u * kBoxBytes), "l"(reinterpret_cast<uint64_t>(&maps.z)), "r"(px0), "r"(b * kC), "r"(bar)
+            : "memory");
+    };
+    if (tid == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8u, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (my_tiles > 0) issue(0);
+        if (my_tiles > 1) issue(1);
+    }
+    for (int i = tid; i < kC * kCout; i += kThreads) {
+        const int co = i / kC, ci = i - co * kC;
+        wt[ci * kCout + co] = __ldg(w_out + i);
+    }
+    for (int i = tid; i < kC; i += kThreads) { lw[i] = __ldg(on_w + i); lb[i] = __ldg(on_b + i); }
+    if (tid < kCout) rs[tid] = __ldg(skip_scale + tid);
+    __syncthreads();
+
+    if (tid < kThreadsA) {
+        // =========================== direction sum, LayerNorm, * z ==============================
+        const int side = tid & 1, px = tid >> 1, c0 = side * 32;
+#pragma unroll 1
+        for (int j = 0; j < my_tiles; ++j) {
+            const int buf = j & 1;
+            mbar_wait(bar0 + 8u * (uint32_t)buf, (uint32_t)(j >> 1) & 1u);
+            const float *st = stage + buf * (kStageBytes / 4) + c0 * kTP + px;
+            float xv[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                // the caller's order: ((y + ya) + yb) + yc  (= ((y0 + y2) + y1) + y3 of the reference)
+                float v = st[i * kTP];
+                v += st[kC * kTP + i * kTP];
+                v += st[2 * kC * kTP + i * kTP];
+                v += st[3 * kC * kTP + i * kTP];
+                xv[i] = v;
+            }
+            float mu = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mu += xv[i];
+            mu += __shfl_xor_sync(0xffffffffu, mu, 1);
+            mu *= (1.0f / kC);
+            float var = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { const float d = xv[i] - mu; var = fmaf(d, d, var); }
+            var += __shfl_xor_sync(0xffffffffu, var, 1);
+            var *= (1.0f / kC);
+            const float rstd = 1.0f / sqrtf(var + eps);
+            if (j >= 2) bar_sync(kBarEmpty + buf, kThreads);             // the out_proj warps are done with v[buf]
+            float *vp = vbuf + buf * (kC * kTP) + c0 * kTP + px;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                vp[i * kTP] = fmaf((xv[i] - mu) * rstd, lw[c0 + i], lb[c0 + i]) * st[4 * kC * kTP + i * kTP];
+            bar_arrive(kBarFull + buf, kThreads);                        // v[buf] is complete
+            bar_sync(kBarA, kThreadsA);                                  // every thread of the group has left the stage
+            if (tid == 0 && j + 2 < my_tiles) issue(j + 2);
+        }
+    } else {
+        // =========================== out_proj + skip ===========================================
+        const int t = tid - kThreadsA;
+        const int q = t & 3, pq = t >> 2;                 // output quarter (8 outputs), pixel quad 0..15
+#pragma unroll 1
+        for (int j = 0; j < my_tiles; ++j) {
+            const int buf = j & 1;
+            const int tile = blockIdx.x + j * gridDim.x;
+            const int b = tile / tiles_per_img;
+            const int64_t p = (int64_t)(tile - b * tiles_per_img) * kTP + 4 * pq;
+            const bool inside = p < hw;                   // hw % 4 == 0: the four pixels are inside or outside together
+            const int64_t o = ((int64_t)b * kCout + q * 8) * hw + p;
+            float4 xr[8];
+            if (inside) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) xr[i] = __ldg(reinterpret_cast<const float4 *>(x + o + (int64_t)i * hw));
+            }
+            bar_sync(kBarFull + buf, kThreads);                          // v[buf] is complete
+            f32x2 acc[4][4];
+#pragma unroll
+            for (int pp = 0; pp < 4; ++pp)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[pp][i] = pack2(0.0f, 0.0f);
+            const float *vb = vbuf + buf * (kC * kTP) + 4 * pq;
+#pragma unroll 4
+            for (int ci = 0; ci < kC; ++ci) {
+                const float4 xv = *reinterpret_cast<const float4 *>(vb + ci * kTP);
+                const f32x2 x2[4] = {pack2(xv.x, xv.x), pack2(xv.y, xv.y), pack2(xv.z, xv.z), pack2(xv.w, xv.w)};
+                const ulonglong2 *wr = reinterpret_cast<const ulonglong2 *>(wt + ci * kCout + q * 8);
+                const ulonglong2 wa = wr[0], wb = wr[1];
+#pragma unroll
+                for (int pp = 0; pp < 4; ++pp) {
+                    acc[pp][0] = ffma2(x2[pp], wa.x, acc[pp][0]);
+                    acc[pp][1] = ffma2(x2[pp], wa.y, acc[pp][1]);
+                    acc[pp][2] = ffma2(x2[pp], wb.x, acc[pp][2]);
+                    acc[pp][3] = ffma2(x2[pp], wb.y, acc[pp][3]);
+                }
+            }
+            if (j + 2 < my_tiles) bar_arrive(kBarEmpty + buf, kThreads);  // v[buf] may be overwritten
+            if (inside) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float v[2][4];
+#pragma unroll
+                    for (int pp = 0; pp < 4; ++pp) unpack2(acc[pp][i], v[0][pp], v[1][pp]);
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const int co = 2 * i + k;
+                        const float sc = rs[q * 8 + co];
+                        const float4 u = xr[co];
+                        // x * skip_scale + out_proj(...)  (reference :525), one FMA per element as before
+                        const float4 r = make_float4(fmaf(u.x, sc, v[k][0]), fmaf(u.y, sc, v[k][1]),
+                                                     fmaf(u.z, sc, v[k][2]), fmaf(u.w, sc, v[k][3]));
+                        *reinterpret_cast<float4 *>(out + o + (int64_t)co * hw) = r;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// 2-D map over a (rows, hw) fp32 matrix with a 64-pixel x 64-row box
+static bool make_map2d(CUtensorMap *tm, const float *base, int64_t rows, int64_t hw)
+{
+    tma::EncodeTiledFn enc = tma::encode_fn();
+    if (enc == nullptr) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)hw, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)hw * 4};
+    const cuuint32_t box[2] = {kTP, kC};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// Returns WM_OK when the pipeline ran, 1 when its preconditions do not hold, or an error code.
+int forward(const float *y, const float *ya, const float *yb, const float *yc, const float *zs,
+            const float *on_w, const float *on_b, float eps, const float *w_out, const float *x,
+            const float *skip_scale, float *out, int64_t B, int64_t hw, cudaStream_t s)
+{
+    if (!ya || !yb || !yc || hw % 4 != 0 || hw < kTP) return 1;
+    if (!aligned16(y) || !aligned16(ya) || !aligned16(yb) || !aligned16(yc) || !aligned16(zs) || !aligned16(x) ||
+        !aligned16(out))
+        return 1;
+    const int64_t tiles_per_img = (hw + kTP - 1) / kTP, total = tiles_per_img * B;
+    if (total >= ((int64_t)1 << 31) || B * kC >= ((int64_t)1 << 31)) return 1;
+    Maps maps;
+    const float *planes[4] = {y, ya, yb, yc};
+    for (int k = 0; k < 4; ++k)
+        if (!make_map2d(&maps.p[k], planes[k], B * kC, hw)) return 1;
+    if (!make_map2d(&maps.z, zs, B * kC, hw)) return 1;
+    WM_CUDA_OK(cudaFuncSetAttribute(lfss_out_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
+    const int grid = total < sm_count() ? (int)total : sm_count();
+    lfss_out_tma_kernel<<<grid, kThreads, kSmem, s>>>(maps, on_w, on_b, eps, w_out, x, skip_scale, out, hw,
+                                                      (int)tiles_per_img, (int)total);
+    WM_LAUNCH_OK("lfss out (TMA)");
+    return WM_OK;
+}
+
+}  // namespace lfss
+}  // namespace wm

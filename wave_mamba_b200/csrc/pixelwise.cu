@@ -18,6 +18,11 @@
 #include "common.cuh"
 
 namespace wm {
+namespace lfss {   // lfss_out_tma.cu: returns 1 when the TMA preconditions do not hold
+int forward(const float *y, const float *ya, const float *yb, const float *yc, const float *zs,
+            const float *on_w, const float *on_b, float eps, const float *w_out, const float *x,
+            const float *skip_scale, float *out, int64_t B, int64_t hw, cudaStream_t s);
+}
 namespace px {
 
 constexpr int kThreads = 256;
@@ -610,6 +615,14 @@ extern "C" int wm_lfss_out_fwd(const float *y, const float *ya, const float *yb,
     if (B == 0 || h == 0 || w == 0) return WM_OK;
     WM_REQUIRE(y && zs && on_w && on_b && w_out && x && skip_scale && out,
                "wm_lfss_out_fwd: null pointer");
+    // persistent TMA pipeline (lfss_out_tma.cu) whenever its preconditions hold; WM_LFSS_OUT_LEGACY=1 is a
+    // developer switch for A/B timing of the register-staged kernels below
+    static const bool legacy = getenv("WM_LFSS_OUT_LEGACY") != nullptr;
+    if (!legacy) {
+        const int rc = wm::lfss::forward(y, ya, yb, yc, zs, on_w, on_b, eps, w_out, x, skip_scale, out, B, h * w,
+                                         (cudaStream_t)stream);
+        if (rc != 1) return rc;
+    }
     Args a = {};
     a.x = y; a.xa = ya; a.xb_ = yb; a.xc = yc; a.ln_w = on_w; a.ln_b = on_b; a.eps = eps; a.mul = zs; a.w = w_out;
     a.res = x; a.res_scale = skip_scale; a.y = out; a.hw = h * w;
