@@ -274,6 +274,7 @@ class OpTimer:
         wrap("gram32", lambda a, k, o: 2 * 32 * a[0].shape[0] * a[0].shape[2] * a[0].shape[3] * 4)
         wrap("lfss_z", lambda a, k, o: nb(a[0]) + nb(o))
         wrap("lfss_out", lambda a, k, o: nb(a[0], a[1], a[6]) + nb(o) + nb(*k.get("extra", ())))
+        wrap("lfss_tail", lambda a, k, o: nb(*a[0]) + nb(a[1]) + nb(o))   # 4 planes + x read, out written
         wrap("ss2d_dirs", lambda a, k, o: 2 * nb(a[0]))           # 512*B*L
         wrap("skff", lambda a, k, o: 2 * nb(a[0], a[1], a[2]) + nb(o))   # pool reads 3, apply reads 3 + writes 1
         wrap("ps_down", lambda a, k, o: nb(a[0]) + nb(o))

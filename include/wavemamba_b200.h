@@ -31,7 +31,7 @@ extern "C" {
 #define WM_ECUDA (-2)     /* a CUDA runtime call or kernel launch failed               */
 #define WM_ENODEVICE (-3) /* no sm_100-class CUDA device is current                     */
 
-#define WM_ABI_VERSION 11
+#define WM_ABI_VERSION 12
 
 typedef void *wm_stream_t;
 
@@ -151,6 +151,17 @@ int wm_lfss_out_fwd(const float *y, const float *ya, const float *yb, const floa
                     const float *zs, const float *on_w, const float *on_b, float eps,
                     const float *w_out, const float *x, const float *skip_scale, float *out,
                     int64_t B, int64_t h, int64_t w, wm_stream_t stream);
+
+/* The two calls above in one: the gate zs = silu(w_z . LayerNorm_32(x)) is computed inside the tail kernel
+ * (one kernel and 224 channel planes of traffic less per LFSSBlock).  All four planes are required.
+ * Shapes whose pixel count is not a multiple of 4 (or unaligned tensors) run as wm_lfss_z_fwd +
+ * wm_lfss_out_fwd through `zs_scratch` (B,64,h,w), which may be NULL otherwise (then such a shape is
+ * WM_EINVAL).  Replaces wavemamba_arch.py:483-484 (z half), :490-494, :524-525. */
+int wm_lfss_tail_fwd(const float *y, const float *ya, const float *yb, const float *yc, const float *x,
+                     const float *ln1_w, const float *ln1_b, float ln1_eps, const float *w_z,
+                     const float *on_w, const float *on_b, float on_eps, const float *w_out,
+                     const float *skip_scale, float *zs_scratch, float *out, int64_t B, int64_t h,
+                     int64_t w, wm_stream_t stream);
 
 /* ---- 32x32 Gram matrix + squared norms of two 32-channel stacks, one pass -----------------
  * out[b] = [ G (32x32, row-major, G[i][j] = sum_p X[b][i][p]*Y[b][j][p]) | |X_i|^2 (32) | |Y_j|^2 (32) ]

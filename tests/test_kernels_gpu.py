@@ -455,6 +455,30 @@ def test_lfss_out_four_planes_tma(ops, dev, hw):
     torch.testing.assert_close(got, want, rtol=3e-5, atol=3e-5)
 
 
+@pytest.mark.parametrize("hw", [(12, 20), (9, 23), (200, 160)])
+def test_lfss_tail_gate_computed_in_kernel(ops, dev, hw):
+    """wm_lfss_tail_fwd = lfss_z + lfss_out in one kernel (the production call of an LFSSBlock).  9 x 23
+    (odd pixel count) runs as the two kernels through a scratch z; the others take the TMA pipeline:
+    240 pixels leave a partial tile, 32000 x 2 images are 1000 tiles = several per persistent CTA."""
+    g = torch.Generator().manual_seed(113)
+    B, (h, w) = 2, hw
+    x = _rand(B, 32, h, w, g=g)
+    ln_w, ln_b = 1 + _rand(32, g=g, s=0.1), _rand(32, g=g, s=0.1)
+    w_in = _rand(128, 32, g=g, s=0.2)
+    ys = [_rand(B, 64, h, w, g=g) for _ in range(4)]
+    on_w, on_b = 1 + _rand(64, g=g, s=0.1), _rand(64, g=g, s=0.1)
+    w_out = _rand(32, 64, g=g, s=0.2)
+    skip = 1 + _rand(32, g=g, s=0.2)
+    zs = F.silu(F.conv2d(om.layer_norm_2d(x, ln_w, ln_b, 1e-6), w_in[64:, :, None, None]))
+    ysum = ((ys[0] + ys[1]) + ys[2]) + ys[3]
+    yn = F.layer_norm(ysum.permute(0, 2, 3, 1), (64,), on_w, on_b, 1e-5)
+    want = x * skip.view(1, -1, 1, 1) + F.linear(yn * zs.permute(0, 2, 3, 1), w_out).permute(0, 3, 1, 2)
+    d = lambda v: v.to(dev)
+    got = ops.lfss_tail([d(t) for t in ys], d(x), d(ln_w), d(ln_b), 1e-6, d(w_in), d(on_w), d(on_b), 1e-5,
+                        d(w_out), d(skip)).cpu()
+    torch.testing.assert_close(got, want, rtol=3e-5, atol=3e-5)
+
+
 def test_pw_gate_with_scaled_residual(ops, dev):
     g = torch.Generator().manual_seed(13)
     x = _rand(2, 64, 11, 29, g=g)

@@ -19,3 +19,22 @@ for h, w in ((1080, 1920), (540, 960), (270, 480)):
     ms = s.elapsed_time(e) / 10
     gb = (4 * 64 + 64 + 32 + 32) * h * w * 4 / 1e9
     print(f"lfss_out {h}x{w}: {ms:.3f} ms, {gb / ms * 1e3:.0f} GB/s algorithmic")
+    x32 = x
+    ln_w, ln_b = torch.ones(32, device=dev), torch.zeros(32, device=dev)
+    w_in = torch.randn(128, 32, device=dev) * 0.2
+    f2 = lambda: ops.lfss_tail(planes, x32, ln_w, ln_b, 1e-6, w_in, on_w, on_b, 1e-5, W, sk)
+    for _ in range(3): f2()
+    torch.cuda.synchronize()
+    s.record()
+    for _ in range(10): f2()
+    e.record(); torch.cuda.synchronize()
+    ms2 = s.elapsed_time(e) / 10
+    f3 = lambda: ops.lfss_z(x32, ln_w, ln_b, 1e-6, w_in)
+    for _ in range(3): f3()
+    torch.cuda.synchronize()
+    s.record()
+    for _ in range(10): f3()
+    e.record(); torch.cuda.synchronize()
+    ms3 = s.elapsed_time(e) / 10
+    gb2 = (4 * 64 + 32 + 32) * h * w * 4 / 1e9
+    print(f"lfss_tail {h}x{w}: {ms2:.3f} ms ({gb2 / ms2 * 1e3:.0f} GB/s algorithmic) vs lfss_z {ms3:.3f} + lfss_out {ms:.3f} = {ms3 + ms:.3f} ms")

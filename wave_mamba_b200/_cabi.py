@@ -12,7 +12,7 @@ from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libwavemamba_b200.so")
 
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 # name -> (restype, argtypes); mirrors include/wavemamba_b200.h one to one
 SIGNATURES = {
@@ -34,6 +34,8 @@ SIGNATURES = {
     "wm_pw_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int] + [c_void_p] * 3 + [c_int64] * 5 + [c_void_p]),
     "wm_lfss_z_fwd": (c_int, [c_void_p] * 3 + [c_float] + [c_void_p] * 2 + [c_int64] * 3 + [c_void_p]),
     "wm_lfss_out_fwd": (c_int, [c_void_p] * 7 + [c_float] + [c_void_p] * 4 + [c_int64] * 3 + [c_void_p]),
+    "wm_lfss_tail_fwd": (c_int, [c_void_p] * 7 + [c_float] + [c_void_p] * 3 + [c_float] + [c_void_p] * 4 +
+                         [c_int64] * 3 + [c_void_p]),
     "wm_gram32_workspace_bytes": (c_size_t, [c_int64] * 2),
     "wm_gram32_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_size_t,
                               c_int64, c_int64, c_void_p]),

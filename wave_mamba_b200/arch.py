@@ -169,20 +169,21 @@ class SS2D(nn.Module):
 
     def forward_nchw(self, x, ln_w, ln_b, ln_eps, skip_scale):
         """Fused NCHW form of ``x*skip_scale + SS2D(ln_1(x))`` (reference :524-525, :480-497):
-        three kernels around the scan, no permutes, no channels-last round trips.
+        two kernels around the scan, no permutes, no channels-last round trips.
             xc = silu(dwconv3x3(in_proj[:D] . ln(x)))          [pw_dw, LN prologue, SiLU epilogue]
-            zs = silu(in_proj[D:] . ln(x))                      [lfss_z]
             p  = the four direction planes of the scan           [ss2d_dirs]
-            out = x*skip_scale + out_proj(out_norm(sum p) * zs)  [lfss_out]"""
+            zs = silu(in_proj[D:] . ln(x))                      } [lfss_tail: one kernel,
+            out = x*skip_scale + out_proj(out_norm(sum p) * zs)  }  zs never leaves the SM]"""
         D = self.d_inner
         xc = ops.pw_dw(x, self.in_proj.weight[:D], None, self.conv2d.weight, self.conv2d.bias,
                        ln_w, ln_b, ln_eps, act="silu")
-        zs = ops.lfss_z(x, ln_w, ln_b, ln_eps, self.in_proj.weight)
         p = ops.ss2d_dirs(xc, self.x_proj_weight, self.dt_projs_weight, self.dt_projs_bias,
                           self.A_logs, self.Ds)
-        # reference sum order y1+y2+y3+y4 = ((dir0 + dir2) + dir1) + dir3, folded into lfss_out
-        return ops.lfss_out(p[0], zs, self.out_norm.weight, self.out_norm.bias, self.out_norm.eps,
-                            self.out_proj.weight, x, skip_scale, extra=(p[2], p[1], p[3]))
+        # reference sum order y1+y2+y3+y4 = ((dir0 + dir2) + dir1) + dir3, folded into the tail kernel,
+        # which also computes the gate zs from x (no z tensor)
+        return ops.lfss_tail((p[0], p[2], p[1], p[3]), x, ln_w, ln_b, ln_eps, self.in_proj.weight,
+                             self.out_norm.weight, self.out_norm.bias, self.out_norm.eps,
+                             self.out_proj.weight, skip_scale)
 
     def forward_train(self, xn: torch.Tensor) -> torch.Tensor:
         """SS2D.forward (:480-497) on an already normalised NCHW map, differentiable: in_proj -> dwconv ->

@@ -22,6 +22,10 @@ namespace lfss {   // lfss_out_tma.cu: returns 1 when the TMA preconditions do n
 int forward(const float *y, const float *ya, const float *yb, const float *yc, const float *zs,
             const float *on_w, const float *on_b, float eps, const float *w_out, const float *x,
             const float *skip_scale, float *out, int64_t B, int64_t hw, cudaStream_t s);
+int forward_tail(const float *y, const float *ya, const float *yb, const float *yc, const float *x,
+                 const float *ln1_w, const float *ln1_b, float ln1_eps, const float *w_z, const float *on_w,
+                 const float *on_b, float eps, const float *w_out, const float *skip_scale, float *out,
+                 int64_t B, int64_t hw, cudaStream_t s);
 }
 namespace px {
 
@@ -643,4 +647,28 @@ extern "C" int wm_lfss_out_fwd(const float *y, const float *ya, const float *yb,
         WM_LAUNCH_OK("lfss out");
     }
     return WM_OK;
+}
+
+extern "C" int wm_lfss_tail_fwd(const float *y, const float *ya, const float *yb, const float *yc,
+                                const float *x, const float *ln1_w, const float *ln1_b, float ln1_eps,
+                                const float *w_z, const float *on_w, const float *on_b, float on_eps,
+                                const float *w_out, const float *skip_scale, float *zs_scratch, float *out,
+                                int64_t B, int64_t h, int64_t w, wm_stream_t stream)
+{
+    WM_REQUIRE(dims_ok(B, h, w), "wm_lfss_tail_fwd: bad sizes");
+    if (B == 0 || h == 0 || w == 0) return WM_OK;
+    WM_REQUIRE(y && ya && yb && yc && x && ln1_w && ln1_b && w_z && on_w && on_b && w_out && skip_scale && out,
+               "wm_lfss_tail_fwd: null pointer");
+    // WM_LFSS_OUT_LEGACY=1 / WM_LFSS_TAIL_SPLIT=1: developer switches for A/B timing of the two-kernel form
+    static const bool split = getenv("WM_LFSS_OUT_LEGACY") != nullptr || getenv("WM_LFSS_TAIL_SPLIT") != nullptr;
+    if (!split) {
+        const int rc = wm::lfss::forward_tail(y, ya, yb, yc, x, ln1_w, ln1_b, ln1_eps, w_z, on_w, on_b, on_eps,
+                                              w_out, skip_scale, out, B, h * w, (cudaStream_t)stream);
+        if (rc != 1) return rc;
+    }
+    WM_REQUIRE(zs_scratch != nullptr,
+               "wm_lfss_tail_fwd: this shape needs the two-kernel form: pass a (B,64,h,w) scratch tensor");
+    const int rc = wm_lfss_z_fwd(x, ln1_w, ln1_b, ln1_eps, w_z, zs_scratch, B, h, w, stream);
+    if (rc != WM_OK) return rc;
+    return wm_lfss_out_fwd(y, ya, yb, yc, zs_scratch, on_w, on_b, on_eps, w_out, x, skip_scale, out, B, h, w, stream);
 }

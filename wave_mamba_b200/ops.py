@@ -350,6 +350,39 @@ def lfss_out(y, zs, on_w, on_b, eps, out_proj_weight, x, skip_scale, extra=()) -
     return out
 
 
+def lfss_tail(planes, x, ln_w, ln_b, ln_eps, in_proj_weight, on_w, on_b, on_eps, out_proj_weight,
+              skip_scale) -> torch.Tensor:
+    """out = x*skip_scale + out_proj(out_norm(((p0 + p1) + p2) + p3) * silu(in_proj.weight[64:] . ln_1(x)))
+    -- lfss_z and lfss_out in one kernel (reference :483-484, :490-494, :524-525).  ``planes``: the four
+    (B,64,h,w) direction outputs in summation order."""
+    _chk(x, "x")
+    B, C, h, w = x.shape
+    D = 2 * C
+    if len(planes) != 4:
+        raise ValueError("lfss_tail: four direction planes expected")
+    for i, t in enumerate(planes):
+        _chk(t, f"planes[{i}]", (B, D, h, w))
+    _chk(in_proj_weight, "in_proj_weight", (4 * C, C))
+    _chk(out_proj_weight, "out_proj_weight", (C, D))
+    for name, t, n in (("ln_w", ln_w, C), ("ln_b", ln_b, C), ("on_w", on_w, D), ("on_b", on_b, D),
+                       ("skip_scale", skip_scale, C)):
+        _chk(t, name, (n,))
+    out = torch.empty_like(x)
+    # the one-kernel form needs h*w % 4 == 0 and 16-byte aligned tensors; other shapes go through a scratch z
+    fused = (h * w) % 4 == 0 and h * w >= 64 and all(t.data_ptr() % 16 == 0 for t in (*planes, x, out))
+    scratch = None if fused else torch.empty(B, D, h, w, device=x.device, dtype=x.dtype)
+    lib = _cabi.load()
+    w_z = in_proj_weight.data_ptr() + 2 * C * C * 4  # rows 64..127
+    with torch.cuda.device(x.device):
+        rc = lib.wm_lfss_tail_fwd(planes[0].data_ptr(), planes[1].data_ptr(), planes[2].data_ptr(),
+                                  planes[3].data_ptr(), x.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), ln_eps,
+                                  w_z, on_w.data_ptr(), on_b.data_ptr(), on_eps, out_proj_weight.data_ptr(),
+                                  skip_scale.data_ptr(), _ptr(scratch), out.data_ptr(), B, h, w, _stream(x))
+    _cabi.check(rc, "wm_lfss_tail_fwd")
+    _count(1 if fused else 2)
+    return out
+
+
 def _chk_planes32(t: torch.Tensor, name: str):
     """(B,32,h,w) float32 CUDA tensor whose 32 planes are contiguous (batch stride free)."""
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
