@@ -344,11 +344,13 @@ def test_pw_plain_gate_and_residual(ops, dev):
     torch.testing.assert_close(ops.pw(d(x), d(w_), d(b_), gate=True).cpu(), want, rtol=2e-5, atol=2e-5)
 
 
-@pytest.mark.parametrize("hw", [(11, 29), (12, 30)])
+@pytest.mark.parametrize("hw", [(11, 29), (12, 30), (12, 32), (160, 200)])
 def test_pw_per_image_weights_on_a_channel_slice(ops, dev, hw):
     """CMTAttention tail (reference :791-797, :849): v is the last third of the qkv tensor (batch
     stride 96*h*w) and every image has its own 32x32 matrix (project_out folded with the attention);
-    one launch.  Odd and even pixel counts take the one- and the two-pixel kernels."""
+    one launch.  Odd and even pixel counts take the one- and the two-pixel kernels, multiples of 4 the
+    TMA pipeline (128-pixel tiles): 384 pixels = 3 tiles per image, 160 x 200 x 3 images = 750 tiles =
+    several per persistent CTA, which reloads the weights when it crosses into the next image."""
     g = torch.Generator().manual_seed(12)
     B, (h, w) = 3, hw
     qkv = _rand(B, 96, h, w, g=g).to(dev)
@@ -479,11 +481,15 @@ def test_lfss_tail_gate_computed_in_kernel(ops, dev, hw):
     torch.testing.assert_close(got, want, rtol=3e-5, atol=3e-5)
 
 
-def test_pw_gate_with_scaled_residual(ops, dev):
+@pytest.mark.parametrize("hw", [(11, 29), (12, 32), (10, 26), (100, 160)])
+def test_pw_gate_with_scaled_residual(ops, dev, hw):
+    """LFSSBlock.ffn tail.  11 x 29: register-staged kernel; the others (h*w % 4 == 0) the TMA pipeline:
+    384 pixels = 3 full tiles, 260 pixels leave a partial tile, 16000 x 2 = 250 tiles (two per CTA)."""
     g = torch.Generator().manual_seed(13)
-    x = _rand(2, 64, 11, 29, g=g)
+    h, w = hw
+    x = _rand(2, 64, h, w, g=g)
     w_, b_ = _rand(32, 32, 1, 1, g=g, s=0.2), _rand(32, g=g, s=0.1)
-    res, sc = _rand(2, 32, 11, 29, g=g), 1 + _rand(32, g=g, s=0.2)
+    res, sc = _rand(2, 32, h, w, g=g), 1 + _rand(32, g=g, s=0.2)
     a, b2 = x.chunk(2, dim=1)
     want = res * sc.view(1, -1, 1, 1) + F.conv2d(F.gelu(a) * b2, w_, b_)
     got = ops.pw(x.to(dev), w_.to(dev), b_.to(dev), gate=True, residual=res.to(dev),

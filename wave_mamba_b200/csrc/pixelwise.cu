@@ -27,6 +27,10 @@ int forward_tail(const float *y, const float *ya, const float *yb, const float *
                  const float *on_b, float eps, const float *w_out, const float *skip_scale, float *out,
                  int64_t B, int64_t hw, cudaStream_t s);
 }
+namespace pwt {    // pw_tma.cu: returns 1 when the TMA preconditions do not hold
+int forward_gate(const float *x, int64_t x_bstride, const float *w, const float *bias, const float *residual,
+                 const float *res_scale, float *y, int64_t B, int64_t hw, cudaStream_t s);
+}
 namespace px {
 
 constexpr int kThreads = 256;
@@ -573,6 +577,15 @@ extern "C" int wm_pw_fwd(const float *x, int64_t x_bstride, const float *pw_w, i
     a.x_bstride = x_bstride; a.w_bstride = w_bstride;
     WM_REQUIRE(x_bstride % 2 == 0 || a.hw % 2 != 0 || B == 1, "wm_pw_fwd: odd batch stride");
     cudaStream_t s = (cudaStream_t)stream;
+    if (gate_mode == 1 && Cin == 32 && Cout == 32 && w_bstride == 0) {
+        // persistent TMA pipeline (pw_tma.cu) whenever its preconditions hold; WM_PW_LEGACY=1 is a developer
+        // switch for A/B timing of the register-staged kernel below
+        static const bool legacy = getenv("WM_PW_LEGACY") != nullptr;
+        if (!legacy) {
+            const int rc = wm::pwt::forward_gate(x, x_bstride, pw_w, pw_b, residual, res_scale, y, B, h * w, s);
+            if (rc != 1) return rc;
+        }
+    }
     if (gate_mode == 0 && Cin == 32 && Cout == 32) return launch2<32, 32, kPreNone, kPostNone>(a, B, s, "pw 32->32");
     if (gate_mode == 0 && Cin == 32 && Cout == 64) return launch<32, 64, kPreNone, kPostNone>(a, B, s, "pw 32->64");
     if (gate_mode == 0 && Cin == 64 && Cout == 32) return launch<64, 32, kPreNone, kPostNone>(a, B, s, "pw 64->32");
