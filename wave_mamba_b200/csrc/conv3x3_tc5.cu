@@ -23,7 +23,8 @@
 //               (the 3xTF32 split is fused into the staging), two slabs ring-buffered, so the next
 //               unit is staged while the tensor core works on the current one
 //   warp 12     weight producer: one TMA bulk copy (cp.async.bulk + mbarrier complete_tx) per
-//               (tap, K half) chunk into a 3/4-deep ring; the prepacked layout is the shared layout
+//               (tap, K half) chunk into a 3/4-deep ring of one or two chunks per stage; the prepacked
+//               layout is the shared layout
 //   warps 13,14 MMA issuers: one thread each (M tile 0 / M tile 1), tcgen05.mma; tcgen05.commit frees
 //               ring stages / X slabs and publishes the accumulators
 //   warps 4-11  epilogue: tcgen05.ld -> bias or k3*sigmoid(k2+b) -> NCHW / channel-quad stores; the
@@ -86,14 +87,23 @@ struct Cfg {
     // weight ring depth (what fits next to the X slabs).  The issuing threads run ahead of the tensor
     // core until they meet a stage that is still being refilled, so their timers always show a wait on
     // the weights (~350 cycles per chunk at any depth): it is slack, not a stall of the tensor pipe.
-    static constexpr int kStages = COUT >= 96 ? 3 : COUT <= 32 ? 8 : 4;
+    // A ring stage holds kUnits consecutive (K half, tap) chunks behind ONE pair of barriers: every stage
+    // hand-over costs each issuing thread ~350 cycles whether or not the data is there (measured by running
+    // the pipeline without refills and without waits: 19.3 k -> 16.2 k cycles per tile for 64 -> 32), about
+    // as much as the 8 MMAs of a 32-output chunk take to issue.  Two chunks per stage where the ring has the
+    // room (the 32-output variants).
+    static constexpr int kUnits = COUT <= 32 ? 2 : 1;
+    static constexpr int kStageF4 = kUnits * kChunkF4;         // float4 per ring stage
+    static constexpr int kStages = COUT >= 96 ? 3 : 4;
+    static constexpr int kTileUnits = NCH * NTAPS;             // chunks per tile, K half major
+    static constexpr int kTileStages = (kTileUnits + kUnits - 1) / kUnits;
     static constexpr int kColsBuf = 4 * COUT * (GATE ? 2 : 1); // TMEM columns of one accumulator set
     static constexpr int NACC = 2 * kColsBuf <= 512 ? 2 : 1;
     static constexpr int kColsNeed = NACC * kColsBuf;
     static constexpr int kCols = kColsNeed <= 32 ? 32 : kColsNeed <= 64 ? 64 : kColsNeed <= 128 ? 128
                                  : kColsNeed <= 256 ? 256 : 512;
     static constexpr int kNumBars = 2 * kStages + 4 + 2 * NACC;
-    static constexpr size_t kSmem = sizeof(float4) * (size_t)(4 * kSlabF4 + kStages * kChunkF4) +
+    static constexpr size_t kSmem = sizeof(float4) * (size_t)(4 * kSlabF4 + kStages * kStageF4) +
                                     8 * kNumBars + 16;
     static_assert(CIN == 32 || CIN == 64 || CIN == 96, "CIN must be 32, 64 or 96");
     static_assert(2 * COUT <= 256 && (2 * COUT) % 16 == 0, "merged N must be a legal UMMA N");
@@ -110,8 +120,8 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
     extern __shared__ __align__(128) float smem[];
     float4 *xhi = reinterpret_cast<float4 *>(smem);                 // [2 slots][8 kc][kNPos]
     float4 *xlo = xhi + 2 * kSlabF4;                                // [2 slots][8 kc][kNPos]
-    float4 *wbuf = xlo + 2 * kSlabF4;                               // [kStages][kChunkF4]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(wbuf + kStages * C::kChunkF4);
+    float4 *wbuf = xlo + 2 * kSlabF4;                               // [kStages][kUnits][kChunkF4]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(wbuf + kStages * C::kStageF4);
     const uint32_t bar0 = smem_u32(bars);
     // barrier map (8 bytes each)
     auto wfull = [&](int i) { return bar0 + 8u * (uint32_t)i; };
@@ -252,18 +262,18 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
         // =============================== weight producer ====================================
         if (lane == 0) {
             uint32_t cnt = 0;
-            const int rot = 0;   // a per-CTA rotation of the tap order was measured: no gain
 #pragma unroll 1
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
 #pragma unroll 1
-                for (int part = 0; part < NCH; ++part) {
-#pragma unroll 1
-                    for (int ti = 0; ti < NTAPS; ++ti, ++cnt) {
-                        const int tap = ti + rot < NTAPS ? ti + rot : ti + rot - NTAPS;
-                        const int st = cnt % kStages;
-                        mbar_wait_flag(wempty(st), ((cnt / kStages) & 1u) ^ 1u, a.err, (4u << 24) | (2u << 16) | (cnt & 0xffffu));
-                        mbar_expect_tx(wfull(st), (uint32_t)C::kChunkBytes);
-                        bulk_g2s(smem_u32(wbuf + st * C::kChunkF4),
+                for (int sc = 0; sc < C::kTileStages; ++sc, ++cnt) {
+                    const int st = cnt % kStages;
+                    const int u0 = sc * C::kUnits;
+                    const int nu = C::kTileUnits - u0 < C::kUnits ? C::kTileUnits - u0 : C::kUnits;
+                    mbar_wait_flag(wempty(st), ((cnt / kStages) & 1u) ^ 1u, a.err, (4u << 24) | (2u << 16) | (cnt & 0xffffu));
+                    mbar_expect_tx(wfull(st), (uint32_t)(nu * C::kChunkBytes));
+                    for (int i = 0; i < nu; ++i) {
+                        const int part = (u0 + i) / NTAPS, tap = (u0 + i) - part * NTAPS;
+                        bulk_g2s(smem_u32(wbuf + st * C::kStageF4 + i * C::kChunkF4),
                                  a.packed + (int64_t)(tap * NCH + part) * C::kChunkF4,
                                  (uint32_t)C::kChunkBytes, wfull(st));
                     }
@@ -290,7 +300,6 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
             const uint64_t a_lo0 = make_desc(smem_u32(xlo), kNPos * 16u, 128u);
             const uint64_t b_00 = make_desc(smem_u32(wbuf), 2 * COUT * 16u, 128u);
             uint32_t cnt = 0, unit = 0, tcount = 0;
-            const int rot = 0;   // tap-order rotation per CTA (against L2 hot spots): measured, no gain
             long long tacc[5] = {0, 0, 0, 0, 0}, t0 = 0, tp = 0;
             const bool timed = a.dbg != nullptr && my_mt == 0;
             if (timed) { t0 = clock64(); tp = t0; }
@@ -309,17 +318,21 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     WM_TICK(2);
 #pragma unroll 1
-                    for (int ti = 0; ti < NTAPS; ++ti, ++cnt) {
-                        const int tap = ti + rot < NTAPS ? ti + rot : ti + rot - NTAPS;
+                    for (int ti = 0; ti < NTAPS; ++ti) {
+                        const int tap = ti;
+                        const int u = part * NTAPS + ti;               // chunk of this tile
+                        const int ui = u % C::kUnits;                  // position inside its ring stage
                         const int st = cnt % kStages;
-                        mbar_wait_flag(wfull(st), (cnt / kStages) & 1u, a.err, (2u << 24) | (2u << 16) | (cnt & 0xffffu));
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        if (ui == 0) {
+                            mbar_wait_flag(wfull(st), (cnt / kStages) & 1u, a.err, (2u << 24) | (2u << 16) | (cnt & 0xffffu));
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        }
                         WM_TICK(1);
                         const bool gate_tap = GATE && tap == 9;
                         const int dy = gate_tap ? 1 : tap / 3, dx = gate_tap ? 1 : tap - (tap / 3) * 3;
                         // offsets in 16-byte units (= one (kc, position) or (kc, co) element)
                         const uint32_t shift = (uint32_t)(slot * kSlabF4 + dy * kHW + dx);
-                        const uint64_t b_hi0 = b_00 + (uint32_t)(st * C::kChunkF4);
+                        const uint64_t b_hi0 = b_00 + (uint32_t)(st * C::kStageF4 + ui * C::kChunkF4);
                         {
                             const int mt = my_mt;
                             const uint32_t dcol = dbase + (uint32_t)((gate_tap ? 4 * COUT : 0) + mt * 2 * COUT);
@@ -330,14 +343,16 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
                                 const uint32_t boff = (uint32_t)(2 * kl) * 2 * COUT;
                                 // the first MMA into an accumulator region overwrites it: the main
                                 // region at the first 3x3 tap of K half 0, the gate region at the gate tap
-                                const bool first_main = ti == 0 || (GATE && ti == 1 && rot == 9);
-                                const uint32_t first = (part == 0 && kl == 0 && (gate_tap || first_main)) ? 0u : 1u;
+                                const uint32_t first = (part == 0 && kl == 0 && (gate_tap || ti == 0)) ? 0u : 1u;
                                 // cols [0,COUT) += a_hi b_hi, [COUT,2COUT) += a_hi b_lo ; cols [0,COUT) += a_lo b_hi
                                 mma_tf32_ss(dcol, a_hi0 + aoff, b_hi0 + boff, idesc2, first);
                                 mma_tf32_ss(dcol, a_lo0 + aoff, b_hi0 + boff, idesc, 1u);
                             }
                         }
-                        mma_commit(wempty(st));
+                        if (ui == C::kUnits - 1 || u == C::kTileUnits - 1) {
+                            mma_commit(wempty(st));
+                            ++cnt;
+                        }
                         WM_TICK(4);
                     }
                     mma_commit(xempty(slot));
