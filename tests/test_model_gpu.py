@@ -188,3 +188,40 @@ def test_lol_400x600_batch4_matches_oracle(dev, params_cache):
         g8 = om.to_uint8_bgr(gt[i])
         d = abs(om.psnr_y(om.to_uint8_bgr(y[i]), g8) - om.psnr_y(om.to_uint8_bgr(want[i]), g8))
         assert d <= 1e-3, d
+
+
+def test_cuda_graph_replay_equals_eager_400x600_batch4(dev, params_cache):
+    """BASELINE configs[1] (400x600, batch 4) through wave_mamba_b200.GraphedForward: the replayed graph
+    gives the eager result bit for bit, on a second input too (buffers and TMA descriptors are frozen at
+    capture, the data is not), and the per-step time of both is reported."""
+    import wave_mamba_b200 as wm
+    net = _net(params_cache("LOLv1"), dev)
+    x0, _ = om.synth_lowlight(4, 400, 600, seed=0)
+    x1, _ = om.synth_lowlight(4, 400, 600, seed=1)
+    x0, x1 = x0.to(dev), x1.to(dev)
+    with torch.no_grad():
+        want0 = net.restoration_network(x0).clone()
+        want1 = net.restoration_network(x1).clone()
+    g = wm.GraphedForward(net, x0.shape)
+    assert torch.equal(g(x0), want0)
+    assert torch.equal(g(x1), want1)
+    assert torch.equal(g(x0), want0)
+
+    def timed(fn, n=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(n):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        return s.elapsed_time(e) / n
+
+    with torch.no_grad():
+        t_eager = timed(lambda: net.restoration_network(x0))
+    t_graph = timed(lambda: g(x0))
+    print(f"400x600 batch 4: eager {t_eager:.2f} ms, CUDA graph {t_graph:.2f} ms per step")
+    with pytest.raises(ValueError):
+        g(x0[:2])
