@@ -53,6 +53,45 @@
 namespace wm {
 namespace ss2d {
 
+// ---- bulk async copies (TMA, 1-D): one thread moves a whole 43 KB tile ----------------------
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_s2g(float *dst, const float *src_smem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_addr(src_smem)),
+                 "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// the bulk stores issued by this thread have finished READING shared memory
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const float *src, uint32_t bytes, uint32_t mbar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity)
+{
+    uint32_t ok = 0;
+#pragma unroll 1
+    for (int spin = 0; spin < (1 << 22); ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(ok)
+            : "r"(mbar), "r"(parity)
+            : "memory");
+        if (ok) return;
+    }
+    __trap();       // a protocol bug traps instead of hanging the GPU
+}
+
 constexpr int kCh = 4;       // channels per scan thread
 // Inputs of one recurrence step of a scan thread = (strand, channel quad, state half): 4 channels x 8
 // states, so the B/C rows of the position are fetched once per 32 state updates (96 bytes per step:
@@ -263,6 +302,7 @@ __device__ __forceinline__ void run_cta(const Params &prm, const Geom &g, const 
 #pragma unroll 1
     for (int ti = 0; ti < ntiles; ++ti) {
         cp_async_wait_all();
+        if (dump && tid == 0) bulk_wait_read();    // the previous tile's store has left shared memory
         __syncthreads();                       // xs(ti) landed; previous tile fully consumed
         WM_TICK(0);
 
@@ -342,16 +382,15 @@ __device__ __forceinline__ void run_cta(const Params &prm, const Geom &g, const 
                 }
             }
         }
+        if (dump) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // pj / dd -> visible to the TMA
         __syncthreads();                       // xs is dead from here on
         WM_TICK(2);
 
         if (ti + 1 < ntiles) load_tile(g, tg, cm, ti + 1, xb, xs);
-        if (dump) {   // pj and dd are adjacent in shared memory: one 43 KB block per tile, streamed out
-            float *dst = prm.tiles + (slot0 + ti) * (int64_t)kTileFloats;
-            const float *src = smem + kOffPj;
-            for (int i = tid; i < kTileFloats / 4; i += kThreads)
-                st_stream4(dst + 4 * i, *reinterpret_cast<const float4 *>(src + 4 * i));
-        }
+        // pj and dd are adjacent in shared memory: one 43 KB block per tile, streamed out by ONE bulk
+        // async store (the 11 LDS.128 + STG.128 per thread of the first version were ~3 % of the pass)
+        if (dump && tid == 0)
+            bulk_s2g(prm.tiles + (slot0 + ti) * (int64_t)kTileFloats, smem + kOffPj, (uint32_t)(kTileFloats * 4));
 
         // ---- recurrence over the 16 steps of this tile        (reference :465-471) --------
         {
@@ -393,6 +432,7 @@ __device__ __forceinline__ void run_cta(const Params &prm, const Geom &g, const 
         }
     }
     if (!FINAL) { WM_TICK(3); }
+    if (dump && tid == 0) bulk_wait_read();        // shared memory must outlive the last store's read
 #undef WM_TICK
     if (timed) {
         long long *o = prm.dbg + (blockIdx.x & 4095) * 6;
@@ -430,7 +470,7 @@ __device__ __forceinline__ void run_cta(const Params &prm, const Geom &g, const 
 constexpr int kR_Buf = 0;                               // two [pj | dd] buffers
 constexpr int kR_Ys = 2 * kTileFloats;
 constexpr int kR_Floats = kR_Ys + kD * kYS;
-constexpr size_t kReplaySmem = sizeof(float) * kR_Floats;   // 102,656 B -> 2 CTAs per SM
+constexpr size_t kReplaySmem = sizeof(float) * kR_Floats + 16;   // + two mbarriers; 102,672 B -> 2 CTAs per SM
 
 template <int DP, bool TIMED>
 __device__ __forceinline__ void run_cta_replay(const Params &prm, const Geom &g, const TileGeom &tg,
@@ -480,13 +520,19 @@ __device__ __forceinline__ void run_cta_replay(const Params &prm, const Geom &g,
     const int64_t slot0 = ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * prm.tile_stride;
     const uint32_t buf_s = (uint32_t)__cvta_generic_to_shared(smem + kR_Buf);
 
+    // one bulk async copy (TMA, 1-D) per tile, issued by thread 0, completion on an mbarrier per buffer
+    const uint32_t bar_s = smem_addr(smem + kR_Floats);
     auto fetch = [&](int ti) {
-        const float *src = prm.tiles + (slot0 + ti) * (int64_t)kTileFloats;
-        const uint32_t dst = buf_s + (uint32_t)(ti & 1) * kTileFloats * 4u;
-        for (int i = tid; i < kTileFloats / 4; i += kThreads)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * i), "l"(src + 4 * i) : "memory");
-        cp_async_commit();
+        if (tid == 0)
+            bulk_g2s(buf_s + (uint32_t)(ti & 1) * kTileFloats * 4u, prm.tiles + (slot0 + ti) * (int64_t)kTileFloats,
+                     (uint32_t)(kTileFloats * 4), bar_s + 8u * (uint32_t)(ti & 1));
     };
+    if (tid == 0) {
+        mbar_init(bar_s, 1);
+        mbar_init(bar_s + 8u, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
     long long tacc[5] = {0, 0, 0, 0, 0}, tprev = 0;
     const bool timed = TIMED && tid == 0;
 #define WM_TICK(k) \
@@ -496,7 +542,7 @@ __device__ __forceinline__ void run_cta_replay(const Params &prm, const Geom &g,
     fetch(0);
 #pragma unroll 1
     for (int ti = 0; ti < ntiles; ++ti) {
-        cp_async_wait_all();
+        mbar_wait(bar_s + 8u * (uint32_t)(ti & 1), (uint32_t)(ti >> 1) & 1u);
         __syncthreads();                 // tile ti landed; the other buffer and ys are free again
         WM_TICK(0);
         if (ti + 1 < ntiles) fetch(ti + 1);
