@@ -485,20 +485,20 @@ def main():
             "achieved": ss["achieved_gbs"], "peak": peak_gbs, "unit": "GB/s",
             "frac": ss["frac_of_hbm_peak"],
             # ncu --set full, profiles/r2_ncu_ss2d_level1.txt: dram__bytes_read.sum + dram__bytes_write.sum
-            # of pass 1 (2.250 + 5.656 GB) and the replaying pass 2 (5.633 + 2.103 GB) of ONE 4K level-1
+            # of pass 1 (2.269 + 5.663 GB) and the replaying pass 2 (5.633 + 2.105 GB) of ONE 4K level-1
             # call (1 x 64 x 1080 x 1920), whose algorithmic bytes are 1.062 GB
-            "traffic": 15.642e9, "traffic_unit": "bytes per level-1 call (algorithmic: 1.062e9)",
+            "traffic": 15.670e9, "traffic_unit": "bytes per level-1 call (algorithmic: 1.062e9)",
             "traffic_note": "deliberate: pass 1 reads x once per direction and streams out the projected "
                             "tiles (43 KB per 64 positions), pass 2 reads them back instead of recomputing "
                             "the projection + softplus, and writes four direction planes that lfss_out sums; "
                             "bytes are spent on idle bandwidth to buy back instructions of a MUFU-bound kernel "
-                            "(round 1: 6.6 GB traffic, 26.4 ms; now 15.6 GB, 24.5 ms)",
+                            "(round 1: 6.6 GB traffic, 26.4 ms; now 15.7 GB, 22.4 ms)",
             "peak_source": peak_src,
             "bytes_definition": "512*B*L per call (x read once + merged y written once), SURVEY 8d",
             "ms_per_image": round(ss["ms_total"] / args.steps, 4),
             "scan_operand_bytes_frac": round(ss["frac_of_hbm_peak"] * 7.0, 4),
             "note": "MUFU-bound (one ex2 per state update, evaluated in both passes), not HBM-bound: the "
-                    "binding roofline is `binding` (ncu: XU 58 % in pass 1, 72 % in pass 2); see DESIGN.md 4.2",
+                    "binding roofline is `binding` (ncu: XU 67 % in pass 1, 76 % in pass 2); see DESIGN.md 4.2",
             "state_updates_per_s": round(L_total * 4096 * args.steps / (ss["ms_total"] * 1e-3), 1),
             # the binding resource: one MUFU ex2 per state update and per pass (two passes)
             # + 2 per (position, channel) for softplus; MUFU peak = 16 lanes/clk/SM
