@@ -31,7 +31,7 @@ extern "C" {
 #define WM_ECUDA (-2)     /* a CUDA runtime call or kernel launch failed               */
 #define WM_ENODEVICE (-3) /* no sm_100-class CUDA device is current                     */
 
-#define WM_ABI_VERSION 12
+#define WM_ABI_VERSION 13
 
 typedef void *wm_stream_t;
 
@@ -174,6 +174,21 @@ size_t wm_gram32_workspace_bytes(int64_t B, int64_t hw);
 int wm_gram32_fwd(const float *x, int64_t x_bstride, const float *y, int64_t y_bstride, float *out,
                   void *workspace, size_t workspace_bytes, int64_t B, int64_t hw,
                   wm_stream_t stream);
+
+/* wm_gram32_fwd with the consumer's 32x32 tail folded into the reduce kernel (one launch instead of the
+ * ~5-8 tiny torch launches that followed it in an HFEBlock).  gram_out: optional (B,1088) copy of the raw
+ * Gram output, may be NULL.  Workspace as wm_gram32_fwd.
+ *   match: idx[b][i] = argmin_j (|x_i|^2 + |p_j|^2) - 2 x_i.p_j   -- Matching :618-680 with match_factor 1
+ *          (torch.cdist's mm mode + topk(k=1, largest=False); same fp32 expression, first index on ties)
+ *   attn:  mixed[b] = W_po . softmax_j( q_i.k_j / (max(|q_i|,1e-12) max(|k_j|,1e-12)) * temperature )
+ *          -- CMTAttention :787-797: F.normalize, @, * temperature, softmax, and project_out folded into
+ *          per-image 1x1 weights for wm_pw_fwd. */
+int wm_gram32_match_fwd(const float *x, int64_t x_bstride, const float *p, int64_t p_bstride, int *idx,
+                        float *gram_out, void *workspace, size_t workspace_bytes, int64_t B, int64_t hw,
+                        wm_stream_t stream);
+int wm_gram32_attn_fwd(const float *q, int64_t q_bstride, const float *k, int64_t k_bstride,
+                       const float *temperature, const float *w_po, float *mixed, float *gram_out,
+                       void *workspace, size_t workspace_bytes, int64_t B, int64_t hw, wm_stream_t stream);
 
 /* ---- dense 3x3 convolution (stride 1, zero pad 1), implicit GEMM on tensor cores, 3xTF32 ----
  * PAConv.k3/k4 (:689-698), DownFRG.l_conv (:966,975), upFRG.h_out_conv (:993,1005).

@@ -545,6 +545,34 @@ def test_gram32_argmin_matches_cdist_oracle(ops, dev):
     assert int(want[0, 9]) == 5
 
 
+def test_match_index_and_attn_mixed_fold_the_32x32_tails(ops, dev):
+    """wm_gram32_match_fwd / wm_gram32_attn_fwd = the Gram pass + the torch ops that followed it in an
+    HFEBlock.  The argmin equals torch's on the same fp32 expression (and the cdist oracle's); the folded
+    attention weights equal the torch formula to fp32 rounding."""
+    g = torch.Generator().manual_seed(23)
+    x, p = _rand(3, 32, 40, 56, g=g), _rand(3, 32, 40, 56, g=g)
+    p[:, 5] = x[:, 9] + 1e-3 * _rand(3, 40, 56, g=g)        # a near-duplicate pair
+    xd, pd = x.to(dev), p.to(dev)
+    G, nx, ny = ops.gram32(xd, pd)
+    idx = ops.match_index(xd, pd)
+    assert idx.dtype == torch.int32 and idx.shape == (3, 32)
+    assert torch.equal(idx.long(), (nx[:, :, None] + ny[:, None, :] - 2.0 * G).topk(k=1, largest=False).indices.squeeze(-1))
+    want = torch.cdist(x.flatten(2, 3), p.flatten(2, 3)).topk(k=1, largest=False).indices.squeeze(-1)
+    assert torch.equal(idx.long().cpu(), want) and int(want[0, 9]) == 5
+    # attention tail on a channel slice (q, k are thirds of the qkv tensor in the model)
+    qkv = _rand(3, 96, 24, 40, g=g).to(dev)
+    q, k = qkv[:, :32], qkv[:, 32:64]
+    temp = torch.tensor([[[1.7]]], device=dev)
+    w_po = _rand(32, 32, 1, 1, g=g, s=0.2).to(dev)
+    Gq, nq2, nk2 = ops.gram32(q, k)
+    nq, nk = nq2.sqrt().clamp_min(1e-12), nk2.sqrt().clamp_min(1e-12)
+    attn = (Gq / (nq[:, :, None] * nk[:, None, :]) * temp).softmax(dim=-1)
+    want_mixed = (w_po.view(1, 32, 32, 1) * attn.unsqueeze(1)).sum(2)
+    got = ops.attn_mixed(q, k, temp, w_po)
+    torch.testing.assert_close(got, want_mixed, rtol=1e-5, atol=1e-6)
+    assert torch.equal(got, ops.attn_mixed(q, k, temp, w_po))      # deterministic
+
+
 # ------------------------------------------------------------------------------- dense 3x3 conv
 @pytest.mark.parametrize("cin,cout", [(64, 32), (64, 64), (32, 96), (32, 32)])
 @pytest.mark.parametrize("hw", [(13, 37), (8, 32), (40, 70)])

@@ -12,7 +12,7 @@ from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libwavemamba_b200.so")
 
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 # name -> (restype, argtypes); mirrors include/wavemamba_b200.h one to one
 SIGNATURES = {
@@ -39,6 +39,10 @@ SIGNATURES = {
     "wm_gram32_workspace_bytes": (c_size_t, [c_int64] * 2),
     "wm_gram32_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_size_t,
                               c_int64, c_int64, c_void_p]),
+    "wm_gram32_match_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_size_t,
+                                    c_int64, c_int64, c_void_p]),
+    "wm_gram32_attn_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_size_t, c_int64, c_int64, c_void_p]),
     "wm_conv3x3_packed_bytes": (c_size_t, [c_int64, c_int64, c_int]),
     "wm_conv3x3_debug_timing": (c_int, [c_void_p]),
     "wm_debug_pipeline_error": (c_int, [c_void_p]),

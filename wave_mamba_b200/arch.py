@@ -302,16 +302,20 @@ class Matching_transformation(nn.Module):
         self.last_index = None  # kept for parity tests (argmin indices)
 
     def forward(self, x, perception):
+        train = _wants_grad(self, x) or perception.requires_grad
         with torch.no_grad():
-            idx = nearest_channel_index(x.detach().contiguous(), perception.detach().contiguous())
+            if train:
+                idx = nearest_channel_index(x.detach().contiguous(), perception.detach().contiguous())
+            else:   # Gram pass + argmin in two launches, int32 indices
+                idx = ops.match_index(x.contiguous(), perception.contiguous())
         self.last_index = idx
-        if _wants_grad(self, x) or perception.requires_grad:
+        if train:
             # the gather and the cat are data movement: torch autograd scatters the gradient back
             B, C, h, w = perception.shape
             cand = torch.gather(perception, 1, idx[:, :, None, None].expand(-1, -1, h, w))
             return self.paconv.forward_train(torch.cat([x, cand], dim=1))
         # cat([x, perception[idx]]) (:716) is expressed as a channel gather inside the conv
-        return self.paconv(x, perception, idx.to(torch.int32).contiguous())
+        return self.paconv(x, perception, idx)
 
 
 class FeedForward(nn.Module):
@@ -379,16 +383,11 @@ class CMTAttention(nn.Module):
         q = self.matching_transformation(q, perception)
         # normalize(q) @ normalize(k)^T (:787-790) == (q @ k^T) / (|q| |k|^T): one Gram matrix and
         # two norm reductions instead of materialising the normalised copies (eps 1e-12 as F.normalize)
-        gram, nq2, nk2 = ops.gram32(q, k)
-        nq = nq2.sqrt().clamp_min(1e-12)
-        nk = nk2.sqrt().clamp_min(1e-12)
-        attn = (gram / (nq[:, :, None] * nk[:, None, :]) * self.temperature).softmax(dim=-1)
-        # project_out(attn @ v) == (W_po @ attn) @ v: fold the CxC attention into the 1x1 weights
-        # so `attn @ v` (:793), project_out (:797) and the residual (:849) are ONE pass over v.
-        # (32x32 per image: an explicit fp32 broadcast-sum, not a cuBLAS call, so torch's TF32
-        # switches cannot reach it); one launch with per-image weights
-        mixed = (self.project_out.weight.view(1, C, C, 1) * attn.unsqueeze(1)).sum(2)   # (B, C, C)
-        return ops.pw(v, mixed.contiguous(), self.project_out.bias, residual=residual)
+        # and the 32x32 tail is folded into the Gram reduce kernel: normalisation, * temperature, softmax,
+        # and project_out(attn @ v) == (W_po @ attn) @ v, i.e. the CxC attention folded into per-image 1x1
+        # weights, so `attn @ v` (:793), project_out (:797) and the residual (:849) are ONE pass over v
+        mixed = ops.attn_mixed(q, k, self.temperature, self.project_out.weight)        # (B, C, C)
+        return ops.pw(v, mixed, self.project_out.bias, residual=residual)
 
 
 class HFEBlock(nn.Module):

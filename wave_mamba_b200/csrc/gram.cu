@@ -208,6 +208,71 @@ gram_reduce_kernel(const double *__restrict__ partial, float *__restrict__ out, 
     out[b * kOut + i] = (float)acc;
 }
 
+// The reduce step with the consumer's 32x32 tail folded in (one CTA per image): the torch ops that
+// followed wm_gram32_fwd in an HFEBlock -- ~10 launches of a few microseconds each on a 32x32 matrix per
+// Matching / attention call, 128 of the ~400 launches of a forward -- become part of this kernel.
+//   MODE 1  Matching (reference :664, :624): idx[i] = argmin_j (|x_i|^2 + |p_j|^2) - 2 x_i.p_j, evaluated
+//           in fp32 exactly as the torch expression `nx[:, :, None] + ny[:, None, :] - 2.0 * gram`
+//           (sqrt / clamp of cdist are monotone), first index on ties
+//   MODE 2  CMTAttention (:787-797): attn = softmax_j( G_ij / (max(|q_i|, 1e-12) max(|k_j|, 1e-12)) * T ),
+//           mixed = W_po . attn  (project_out folded with the attention: the per-image 1x1 weights)
+template <int MODE>
+__global__ void __launch_bounds__(kThreads)
+gram_reduce_tail_kernel(const double *__restrict__ partial, float *__restrict__ out, int nchunks,
+                        int *__restrict__ idx_out, const float *__restrict__ temperature,
+                        const float *__restrict__ w_po, float *__restrict__ mixed_out)
+{
+    __shared__ float G[kC * kC + 2 * kC];
+    __shared__ float attn[kC * kC];
+    const int64_t b = blockIdx.x;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < kOut; i += kThreads) {
+        const double *p = partial + b * nchunks * kOut + i;
+        double acc = 0.0;
+        for (int c = 0; c < nchunks; ++c) acc += p[(int64_t)c * kOut];
+        G[i] = (float)acc;
+        if (out != nullptr) out[b * kOut + i] = (float)acc;
+    }
+    __syncthreads();
+    const float *nx = G + kC * kC, *ny = nx + kC;
+    if (MODE == 1) {
+        if (tid < kC) {
+            float best = 0.0f;
+            int bj = 0;
+            for (int j = 0; j < kC; ++j) {
+                const float d = __fsub_rn(__fadd_rn(nx[tid], ny[j]), __fmul_rn(2.0f, G[tid * kC + j]));
+                if (j == 0 || d < best) { best = d; bj = j; }
+            }
+            idx_out[b * kC + tid] = bj;
+        }
+    } else {
+        if (tid < kC) {
+            const float T = __ldg(temperature);
+            const float nq = fmaxf(sqrtf(nx[tid]), 1e-12f);
+            float v[kC], m = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < kC; ++j) {
+                const float nk = fmaxf(sqrtf(ny[j]), 1e-12f);
+                v[j] = __fmul_rn(__fdiv_rn(G[tid * kC + j], __fmul_rn(nq, nk)), T);
+                m = fmaxf(m, v[j]);
+            }
+            float sum = 0.0f;
+#pragma unroll
+            for (int j = 0; j < kC; ++j) { v[j] = expf(v[j] - m); sum += v[j]; }
+#pragma unroll
+            for (int j = 0; j < kC; ++j) attn[tid * kC + j] = __fdiv_rn(v[j], sum);
+        }
+        __syncthreads();
+        for (int i = tid; i < kC * kC; i += kThreads) {
+            const int o = i / kC, c = i - o * kC;
+            float acc = 0.0f;
+#pragma unroll
+            for (int m2 = 0; m2 < kC; ++m2) acc = fmaf(__ldg(w_po + o * kC + m2), attn[m2 * kC + c], acc);
+            mixed_out[b * kC * kC + i] = acc;
+        }
+    }
+}
+
 inline void plan(int64_t hw, int &chunk, int &nchunks)
 {
     // one CTA per SM (64 KB of shared memory, ~180 registers), chunk a multiple of the tile
@@ -230,27 +295,29 @@ extern "C" size_t wm_gram32_workspace_bytes(int64_t B, int64_t hw)
     return (size_t)B * nchunks * wm::gram::kOut * sizeof(double);
 }
 
-extern "C" int wm_gram32_fwd(const float *x, int64_t x_bstride, const float *y, int64_t y_bstride,
-                             float *out, void *workspace, size_t workspace_bytes, int64_t B,
-                             int64_t hw, wm_stream_t stream)
+static int gram_launch(const char *who, int mode, const float *x, int64_t x_bstride, const float *y,
+                       int64_t y_bstride, float *out, int *idx_out, const float *temperature,
+                       const float *w_po, float *mixed_out, void *workspace, size_t workspace_bytes, int64_t B,
+                       int64_t hw, wm_stream_t stream)
 {
     using namespace wm;
     using namespace wm::gram;
-    WM_REQUIRE(B >= 0 && hw >= 0 && B <= 65535, "wm_gram32_fwd: bad sizes");
+    WM_REQUIRE(B >= 0 && hw >= 0 && B <= 65535, "%s: bad sizes", who);
     if (B == 0) return WM_OK;
-    WM_REQUIRE(x && y && out, "wm_gram32_fwd: null pointer");
+    WM_REQUIRE(x && y, "%s: null pointer", who);
     cudaStream_t s = (cudaStream_t)stream;
+    WM_REQUIRE(hw > 0 || mode == 0, "%s: empty maps", who);
     if (hw == 0) {
         WM_CUDA_OK(cudaMemsetAsync(out, 0, (size_t)B * kOut * sizeof(float), s));
         return WM_OK;
     }
-    WM_REQUIRE(x_bstride >= kC * hw && y_bstride >= kC * hw, "wm_gram32_fwd: batch stride too small");
+    WM_REQUIRE(x_bstride >= kC * hw && y_bstride >= kC * hw, "%s: batch stride too small", who);
     int chunk, nchunks;
     plan(hw, chunk, nchunks);
     const size_t need = (size_t)B * nchunks * kOut * sizeof(double);
-    WM_REQUIRE(workspace && workspace_bytes >= need, "wm_gram32_fwd: workspace too small (%zu < %zu)",
+    WM_REQUIRE(workspace && workspace_bytes >= need, "%s: workspace too small (%zu < %zu)", who,
                workspace_bytes, need);
-    WM_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 7u) == 0, "wm_gram32_fwd: workspace alignment");
+    WM_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 7u) == 0, "%s: workspace alignment", who);
     const int vec = (hw % 4 == 0 && aligned16(x) && aligned16(y) && x_bstride % 4 == 0 &&
                      y_bstride % 4 == 0) ? 1 : 0;
     dim3 grid(nchunks, (unsigned)B);
@@ -260,8 +327,43 @@ extern "C" int wm_gram32_fwd(const float *x, int64_t x_bstride, const float *y, 
                                                   static_cast<double *>(workspace), hw, chunk,
                                                   nchunks, vec);
     WM_LAUNCH_OK("gram partial");
-    dim3 rgrid((kOut + kThreads - 1) / kThreads, (unsigned)B);
-    gram_reduce_kernel<<<rgrid, kThreads, 0, s>>>(static_cast<const double *>(workspace), out, nchunks);
+    const double *part = static_cast<const double *>(workspace);
+    if (mode == 0) {
+        dim3 rgrid((kOut + kThreads - 1) / kThreads, (unsigned)B);
+        gram_reduce_kernel<<<rgrid, kThreads, 0, s>>>(part, out, nchunks);
+    } else if (mode == 1) {
+        gram_reduce_tail_kernel<1><<<(unsigned)B, kThreads, 0, s>>>(part, out, nchunks, idx_out, nullptr, nullptr, nullptr);
+    } else {
+        gram_reduce_tail_kernel<2><<<(unsigned)B, kThreads, 0, s>>>(part, out, nchunks, nullptr, temperature, w_po, mixed_out);
+    }
     WM_LAUNCH_OK("gram reduce");
     return WM_OK;
+}
+
+extern "C" int wm_gram32_fwd(const float *x, int64_t x_bstride, const float *y, int64_t y_bstride,
+                             float *out, void *workspace, size_t workspace_bytes, int64_t B,
+                             int64_t hw, wm_stream_t stream)
+{
+    WM_REQUIRE(out != nullptr || B == 0, "wm_gram32_fwd: null pointer");
+    return gram_launch("wm_gram32_fwd", 0, x, x_bstride, y, y_bstride, out, nullptr, nullptr, nullptr, nullptr,
+                       workspace, workspace_bytes, B, hw, stream);
+}
+
+extern "C" int wm_gram32_match_fwd(const float *x, int64_t x_bstride, const float *p, int64_t p_bstride,
+                                   int *idx, float *gram_out, void *workspace, size_t workspace_bytes,
+                                   int64_t B, int64_t hw, wm_stream_t stream)
+{
+    WM_REQUIRE(idx != nullptr || B == 0, "wm_gram32_match_fwd: null pointer");
+    return gram_launch("wm_gram32_match_fwd", 1, x, x_bstride, p, p_bstride, gram_out, idx, nullptr, nullptr, nullptr,
+                       workspace, workspace_bytes, B, hw, stream);
+}
+
+extern "C" int wm_gram32_attn_fwd(const float *q, int64_t q_bstride, const float *k, int64_t k_bstride,
+                                  const float *temperature, const float *w_po, float *mixed,
+                                  float *gram_out, void *workspace, size_t workspace_bytes, int64_t B,
+                                  int64_t hw, wm_stream_t stream)
+{
+    WM_REQUIRE((temperature && w_po && mixed) || B == 0, "wm_gram32_attn_fwd: null pointer");
+    return gram_launch("wm_gram32_attn_fwd", 2, q, q_bstride, k, k_bstride, gram_out, nullptr, temperature, w_po, mixed,
+                       workspace, workspace_bytes, B, hw, stream);
 }

@@ -420,6 +420,47 @@ def gram32(x: torch.Tensor, y: torch.Tensor):
     return out[:, :1024].view(B, 32, 32), out[:, 1024:1056], out[:, 1056:1088]
 
 
+def _gram_call(fn_name, x, y, extra_args):
+    _chk_planes32(x, "x")
+    _chk_planes32(y, "y")
+    if x.shape != y.shape:
+        raise ValueError(f"x {tuple(x.shape)} and y {tuple(y.shape)} must match")
+    B, C, h, w = x.shape
+    hw = h * w
+    lib = _cabi.load()
+    xb = x.stride(0) if B > 1 else 32 * hw
+    yb = y.stride(0) if B > 1 else 32 * hw
+    with torch.cuda.device(x.device):
+        nbytes = lib.wm_gram32_workspace_bytes(B, hw)
+        ws = torch.empty(max(nbytes, 8) // 8, device=x.device, dtype=torch.float64)
+        rc = getattr(lib, fn_name)(x.data_ptr(), xb, y.data_ptr(), yb, *extra_args, None, ws.data_ptr(), nbytes,
+                                   B, hw, _stream(x))
+    _cabi.check(rc, fn_name)
+    _count(2)
+
+
+def match_index(x: torch.Tensor, perception: torch.Tensor) -> torch.Tensor:
+    """Matching (reference :618-680, match_factor 1): for every channel map of x the index of the nearest
+    channel map of ``perception`` (L2 over the whole map), (B,32) int32 -- the Gram pass and the argmin
+    of `|x_i|^2 + |p_j|^2 - 2 x_i.p_j` in two launches."""
+    idx = torch.empty(x.shape[0], 32, device=x.device, dtype=torch.int32)
+    _gram_call("wm_gram32_match_fwd", x, perception, (idx.data_ptr(),))
+    return idx
+
+
+def attn_mixed(q: torch.Tensor, k: torch.Tensor, temperature: torch.Tensor, w_po: torch.Tensor) -> torch.Tensor:
+    """CMTAttention (reference :787-797): W_po . softmax(normalize(q) normalize(k)^T * temperature), (B,32,32):
+    the per-image 1x1 weights that fold attention and project_out into one pass over v (``ops.pw``)."""
+    _chk(temperature, "temperature")
+    if temperature.numel() != 1:
+        raise ValueError("attn_mixed: single-head temperature expected")
+    w2 = w_po.reshape(32, 32)
+    _chk(w2, "w_po", (32, 32))
+    mixed = torch.empty(q.shape[0], 32, 32, device=q.device, dtype=torch.float32)
+    _gram_call("wm_gram32_attn_fwd", q, k, (temperature.data_ptr(), w2.data_ptr(), mixed.data_ptr()))
+    return mixed
+
+
 _packed_cache = {}   # id(weight) -> (weakref, (data_ptr, device, version) of w3x3 and w1x1, packed)
 
 
