@@ -13,8 +13,13 @@
 //
 // 3xTF32: the tensor core reads the top 19 bits of an fp32 word, so the "hi" operand is the raw
 // activation and only lo = a - trunc(a) needs a second copy; weights are split (rna) at prepack.
-//   [acc | acc2] += a_hi*[b_hi | b_lo]  (one MMA, N = 2*COUT) ; acc += a_lo*b_hi  (N = COUT)
+//   [acc | acc2] += a_hi*[b_hi | b_lo]  (one MMA, N = 2*COUT) ; acc += a_lo*b  (N = COUT)
 //   fp32 accumulate in TMEM, acc + acc2 in the epilogue.
+// The kernel is bound by the shared-memory reads of the MMA operands, and the correction
+// term a_lo*b is 2^-11 of the product, so it runs as a **bf16** MMA (kind::f16, K = 16 per instruction):
+// a_lo and b rounded to bf16 cost 2^-9 of that term each = 2^-20 of the product, the size of the a_lo*b_lo
+// term 3xTF32 drops anyway -- and the a_lo operand and its weights are read at half the bytes
+// (11 -> 8.5 KB per 8 input channels and M tile for 32 outputs, 14 -> 11 KB for 64).
 //
 // Warp-specialised, persistent (one CTA per SM, 15 warps), everything synchronised with mbarriers --
 // no CTA-wide barrier inside the tile loop:
@@ -82,7 +87,8 @@ template <int CIN, int COUT, bool GATE>
 struct Cfg {
     static constexpr int NCH = CIN / 32;                       // K halves (slabs) per tile
     static constexpr int NTAPS = GATE ? 10 : 9;
-    static constexpr int kChunkF4 = kKcSlab * 2 * COUT;        // float4 per weight chunk
+    static constexpr int kChunkTf32F4 = kKcSlab * 2 * COUT;    // [kc 0..7][hi | lo][COUT] float4
+    static constexpr int kChunkF4 = kChunkTf32F4 + 4 * COUT;   // + [kc8 0..3][COUT] 8 x bf16: float4 per chunk
     static constexpr int kChunkBytes = kChunkF4 * 16;
     // weight ring depth (what fits next to the X slabs).  The issuing threads run ahead of the tensor
     // core until they meet a stage that is still being refilled, so their timers always show a wait on
@@ -103,7 +109,7 @@ struct Cfg {
     static constexpr int kCols = kColsNeed <= 32 ? 32 : kColsNeed <= 64 ? 64 : kColsNeed <= 128 ? 128
                                  : kColsNeed <= 256 ? 256 : 512;
     static constexpr int kNumBars = 2 * kStages + 4 + 2 * NACC;
-    static constexpr size_t kSmem = sizeof(float4) * (size_t)(4 * kSlabF4 + kStages * kStageF4) +
+    static constexpr size_t kSmem = sizeof(float4) * (size_t)(3 * kSlabF4 + kStages * kStageF4) +
                                     8 * kNumBars + 16;
     static_assert(CIN == 32 || CIN == 64 || CIN == 96, "CIN must be 32, 64 or 96");
     static_assert(2 * COUT <= 256 && (2 * COUT) % 16 == 0, "merged N must be a legal UMMA N");
@@ -119,8 +125,8 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
     constexpr int NCH = C::NCH, NTAPS = C::NTAPS, kStages = C::kStages, NACC = C::NACC;
     extern __shared__ __align__(128) float smem[];
     float4 *xhi = reinterpret_cast<float4 *>(smem);                 // [2 slots][8 kc][kNPos]
-    float4 *xlo = xhi + 2 * kSlabF4;                                // [2 slots][8 kc][kNPos]
-    float4 *wbuf = xlo + 2 * kSlabF4;                               // [kStages][kUnits][kChunkF4]
+    uint4 *xlo = reinterpret_cast<uint4 *>(xhi + 2 * kSlabF4);      // [2 slots][4 kc8][kNPos] 8 x bf16
+    float4 *wbuf = xhi + 3 * kSlabF4;                               // [kStages][kUnits][kChunkF4]
     uint64_t *bars = reinterpret_cast<uint64_t *>(wbuf + kStages * C::kStageF4);
     const uint32_t bar0 = smem_u32(bars);
     // barrier map (8 bytes each)
@@ -173,13 +179,13 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
                 const int slot = unit & 1;
                 float4 v[18];
                 float4 vt[2];
-                // tail items: item i -> row (kc = i / 18, py = (i % 18) / 2), column 32 + (i & 1)
-                int t_kc[2], t_py[2], t_px[2];
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int i = tid + q * kProdThreads;
-                    t_kc[q] = i / 18; t_py[q] = (i % 18) >> 1; t_px[q] = 32 + (i & 1);
-                }
+                // tail items: thread i < 72 -> (K chunks 2*(i/18), 2*(i/18)+1; py = (i % 18) / 2; column
+                // 32 + (i & 1)): the 8 channels of one bf16 operand row
+                const bool has_tail = tid < 72;
+                int t_kc[2];
+                const int t_py = (tid % 18) >> 1, t_px = 32 + (tid & 1);
+                t_kc[0] = 2 * (tid / 18);
+                t_kc[1] = t_kc[0] + 1;
                 if (a.in_c4) {
                     const float4 *src4 = reinterpret_cast<const float4 *>(a.in_a + b * a.a_bstride);
 #pragma unroll
@@ -193,8 +199,8 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
                         vt[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (tid + q * kProdThreads < 144) {
-                            const int gy = ty0 - 1 + t_py[q], gxt = tx0 - 1 + t_px[q];
+                        if (has_tail) {
+                            const int gy = ty0 - 1 + t_py, gxt = tx0 - 1 + t_px;
                             if (gy >= 0 && gy < h && gxt < w)
                                 vt[q] = __ldg(src4 + (int64_t)(part * kKcSlab + t_kc[q]) * hw + (int64_t)gy * w + gxt);
                         }
@@ -225,8 +231,8 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
                         vt[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (tid + q * kProdThreads < 144) {
-                            const int gy = ty0 - 1 + t_py[q], gxt = tx0 - 1 + t_px[q];
+                        if (has_tail) {
+                            const int gy = ty0 - 1 + t_py, gxt = tx0 - 1 + t_px;
                             if (gy >= 0 && gy < h && gxt < w) {
                                 const int c0 = part * 32 + t_kc[q] * 4;
                                 const int64_t off = (int64_t)gy * w + gxt;
@@ -238,20 +244,22 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
                 }
                 // the loads above are in flight while we wait for the slab to be released
                 mbar_wait_flag(xempty(slot), ((unit >> 1) & 1u) ^ 1u, a.err, (1u << 24) | (1u << 16) | (unit & 0xffffu));
-                float4 *dhi = xhi + slot * kSlabF4, *dlo = xlo + slot * kSlabF4;
+                float4 *dhi = xhi + slot * kSlabF4;
+                uint4 *dlo = xlo + slot * (kSlabF4 / 2);
+                // lo = a - trunc_tf32(a) of 8 consecutive channels (K chunks 2pw, 2pw+1) -> one bf16 row
+                auto lo8 = [](const float4 &p, const float4 &q) {
+                    return make_uint4(pack_bf16x2(tf32_lo(p.x), tf32_lo(p.y)), pack_bf16x2(tf32_lo(p.z), tf32_lo(p.w)),
+                                      pack_bf16x2(tf32_lo(q.x), tf32_lo(q.y)), pack_bf16x2(tf32_lo(q.z), tf32_lo(q.w)));
+                };
 #pragma unroll
-                for (int r = 0; r < 18; ++r) {
-                    const int idx = (2 * pw + r / 9) * kNPos + (r % 9) * kHW + lane;
-                    dhi[idx] = v[r];
-                    dlo[idx] = make_float4(tf32_lo(v[r].x), tf32_lo(v[r].y), tf32_lo(v[r].z), tf32_lo(v[r].w));
-                }
+                for (int r = 0; r < 18; ++r) dhi[(2 * pw + r / 9) * kNPos + (r % 9) * kHW + lane] = v[r];
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    if (tid + q * kProdThreads < 144) {
-                        const int idx = t_kc[q] * kNPos + t_py[q] * kHW + t_px[q];
-                        dhi[idx] = vt[q];
-                        dlo[idx] = make_float4(tf32_lo(vt[q].x), tf32_lo(vt[q].y), tf32_lo(vt[q].z), tf32_lo(vt[q].w));
-                    }
+                for (int py = 0; py < 9; ++py) dlo[pw * kNPos + py * kHW + lane] = lo8(v[py], v[9 + py]);
+                if (has_tail) {
+                    const int pos = t_py * kHW + t_px;
+                    dhi[t_kc[0] * kNPos + pos] = vt[0];
+                    dhi[t_kc[1] * kNPos + pos] = vt[1];
+                    dlo[(t_kc[0] >> 1) * kNPos + pos] = lo8(vt[0], vt[1]);
                 }
                 // generic-proxy stores -> visible to the tensor core's async-proxy reads
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -291,14 +299,15 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
         if (lane == 0) {
             // instruction descriptors: D=f32, A=B=tf32, both K-major, M = 128; N = COUT (b_hi only)
             // or N = 2*COUT ([b_hi | b_lo]: the activation operand is read once for both)
-            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(COUT >> 3) << 17) |
-                                       ((uint32_t)(128 >> 4) << 24);
             constexpr uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) |
                                         ((uint32_t)((2 * COUT) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             // descriptors differ only in the 14-bit start-address field (bytes >> 4)
             const uint64_t a_hi0 = make_desc(smem_u32(xhi), kNPos * 16u, 128u);
+            constexpr uint32_t idesc16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(COUT >> 3) << 17) |
+                                         ((uint32_t)(128 >> 4) << 24);     // kind::f16: bf16 x bf16 -> f32
             const uint64_t a_lo0 = make_desc(smem_u32(xlo), kNPos * 16u, 128u);
             const uint64_t b_00 = make_desc(smem_u32(wbuf), 2 * COUT * 16u, 128u);
+            const uint64_t b16_00 = make_desc(smem_u32(wbuf + C::kChunkTf32F4), COUT * 16u, 128u);
             uint32_t cnt = 0, unit = 0, tcount = 0;
             long long tacc[5] = {0, 0, 0, 0, 0}, t0 = 0, tp = 0;
             const bool timed = a.dbg != nullptr && my_mt == 0;
@@ -333,6 +342,8 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
                         // offsets in 16-byte units (= one (kc, position) or (kc, co) element)
                         const uint32_t shift = (uint32_t)(slot * kSlabF4 + dy * kHW + dx);
                         const uint64_t b_hi0 = b_00 + (uint32_t)(st * C::kStageF4 + ui * C::kChunkF4);
+                        const uint64_t b16_0 = b16_00 + (uint32_t)(st * C::kStageF4 + ui * C::kChunkF4);
+                        const uint32_t shift16 = (uint32_t)(slot * (kSlabF4 / 2) + dy * kHW + dx);
                         {
                             const int mt = my_mt;
                             const uint32_t dcol = dbase + (uint32_t)((gate_tap ? 4 * COUT : 0) + mt * 2 * COUT);
@@ -344,10 +355,15 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
                                 // the first MMA into an accumulator region overwrites it: the main
                                 // region at the first 3x3 tap of K half 0, the gate region at the gate tap
                                 const uint32_t first = (part == 0 && kl == 0 && (gate_tap || ti == 0)) ? 0u : 1u;
-                                // cols [0,COUT) += a_hi b_hi, [COUT,2COUT) += a_hi b_lo ; cols [0,COUT) += a_lo b_hi
+                                // cols [0,COUT) += a_hi b_hi, [COUT,2COUT) += a_hi b_lo
                                 mma_tf32_ss(dcol, a_hi0 + aoff, b_hi0 + boff, idesc2, first);
-                                mma_tf32_ss(dcol, a_lo0 + aoff, b_hi0 + boff, idesc, 1u);
                             }
+                            // cols [0,COUT) += a_lo b in bf16, 16 input channels per instruction
+                            const uint32_t arow16 = shift16 + (uint32_t)mt * 128u;
+#pragma unroll
+                            for (int kl = 0; kl < 2; ++kl)
+                                mma_bf16_ss(dcol, a_lo0 + (uint32_t)(2 * kl) * kNPos + arow16,
+                                            b16_0 + (uint32_t)(2 * kl) * COUT, idesc16, 1u);
                         }
                         if (ui == C::kUnits - 1 || u == C::kTileUnits - 1) {
                             mma_commit(wempty(st));
@@ -455,9 +471,9 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
     }
 }
 
-// w3: (COUT, CIN, 3, 3); w1: (COUT, CIN) or null -> packed[tap][part][kc 0..7][hi|lo][co] float4:
-// one contiguous chunk per (tap, K half) in exactly the shared-memory operand layout, so the
-// weight producer moves a chunk with a single bulk copy.
+// w3: (COUT, CIN, 3, 3); w1: (COUT, CIN) or null -> packed[tap][part]{ [kc 0..7][hi|lo][co] float4,
+// [kc8 0..3][co] 8 x bf16 }: one contiguous chunk per (tap, K half) in exactly the shared-memory operand
+// layout, so the weight producer moves a chunk with a single bulk copy.
 __global__ void __launch_bounds__(256)
 prepack_tc5_kernel(const float *__restrict__ w3, const float *__restrict__ w1,
                    float4 *__restrict__ out, int CIN, int COUT, int ntaps)
@@ -481,9 +497,19 @@ prepack_tc5_kernel(const float *__restrict__ w3, const float *__restrict__ w1,
             lo[j] = __uint_as_float(lbits);
         }
         const int part = kc / kKcSlab, kcl = kc % kKcSlab;
-        float4 *dst = out + ((int64_t)(tap * NCH + part) * kKcSlab + kcl) * 2 * COUT;
+        float4 *chunk = out + (int64_t)(tap * NCH + part) * (kKcSlab * 2 + 4) * COUT;
+        float4 *dst = chunk + kcl * 2 * COUT;
         dst[co] = make_float4(hi[0], hi[1], hi[2], hi[3]);
         dst[COUT + co] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        // bf16 copy of the weights for the a_lo term: row co of K chunk pair kcl/2, this half of its 16 bytes
+        uint2 *d16 = reinterpret_cast<uint2 *>(chunk + kKcSlab * 2 * COUT + (kcl >> 1) * COUT + co) + (kcl & 1);
+        float wv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int ci = kc * 4 + j;
+            wv[j] = tap < 9 ? w3[((int64_t)co * CIN + ci) * 9 + tap] : w1[(int64_t)co * CIN + ci];
+        }
+        *d16 = make_uint2(pack_bf16x2(wv[0], wv[1]), pack_bf16x2(wv[2], wv[3]));
     }
 }
 
@@ -518,7 +544,8 @@ extern "C" int wm_conv3x3_debug_timing(void *device_buffer)
 extern "C" size_t wm_conv3x3_packed_bytes(int64_t Cin, int64_t Cout, int with_gate)
 {
     if (Cin <= 0 || Cout <= 0 || Cin % 32 || Cout % 8) return 0;
-    return (size_t)(with_gate ? 10 : 9) * 2 * (Cin / 4) * Cout * sizeof(float4);
+    // per (tap, 32-channel K half): 16 * Cout float4 of tf32 hi | lo + 4 * Cout of bf16
+    return (size_t)(with_gate ? 10 : 9) * (Cin / 32) * 20 * Cout * sizeof(float4);
 }
 
 extern "C" int wm_conv3x3_prepack(const float *w3x3, const float *w1x1, void *packed, int64_t Cin,

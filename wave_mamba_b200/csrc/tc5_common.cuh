@@ -34,6 +34,29 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t tmem_d, uint64_t adesc, uin
         : "memory");
 }
 
+// kind::f16 (here: bf16 x bf16 -> fp32), same operand forms; K = 16 per instruction
+__device__ __forceinline__ void mma_bf16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                            uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
+        "}\n"
+        :
+        : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u),
+          "r"(0u)
+        : "memory");
+}
+// two fp32 -> one register of two bf16 (round to nearest even), `lo` in the low half = lower address
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi)
+{
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
 __device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
