@@ -214,10 +214,13 @@ __device__ __forceinline__ void run_cta(const Params &prm, const Geom &g, const 
             w0 = __ldg(wr + t4);
             w1 = __ldg(wr + t4 + 4);
         }
+        // (tf32 hi pair | bf16 pair of w | bf16 pair of w - hi): the two 3xTF32 correction terms run as ONE
+        // bf16 m16n8k16 MMA whose K slots 0-7 carry a_lo * w and slots 8-15 a_hi * w_lo (slot 2t, 2t+1 <->
+        // channels t, t+4 of the k-step: the channels a thread holds for the tf32 fragment)
         const uint32_t h0 = to_tf32(w0), h1 = to_tf32(w1);
-        const uint32_t l0 = to_tf32(w0 - __uint_as_float(h0)), l1 = to_tf32(w1 - __uint_as_float(h1));
-        wf[i] = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(l0),
-                            __uint_as_float(l1));
+        wf[i] = make_float4(__uint_as_float(h0), __uint_as_float(h1),
+                            __uint_as_float(pack_bf16x2(w0, w1)),
+                            __uint_as_float(pack_bf16x2(w0 - __uint_as_float(h0), w1 - __uint_as_float(h1))));
     }
 
     // ---- delta-phase constants [dt_proj col 0 | col 1 | bias] x 64 channels -------------------
@@ -322,12 +325,15 @@ __device__ __forceinline__ void run_cta(const Params &prm, const Geom &g, const 
                 uint32_t ahi[4], alo[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) split_tf32(av[i], ahi[i], alo[i]);
+                // bf16 A fragment of the correction MMA: rows (gq, gq+8) x K slots (2t, 2t+1 | +8)
+                const uint32_t a16[4] = {pack_bf16x2(__uint_as_float(alo[0]), __uint_as_float(alo[2])),
+                                         pack_bf16x2(__uint_as_float(alo[1]), __uint_as_float(alo[3])),
+                                         pack_bf16x2(av[0], av[2]), pack_bf16x2(av[1], av[3])};
 #pragma unroll
                 for (int t = 0; t < 3; ++t) {
                     if (t < nt_count) {
                         const float4 bw = wf[(ks * kNTiles + nt_list[t]) * 32 + lane];
-                        mma_tf32(acc[t], alo, __float_as_uint(bw.x), __float_as_uint(bw.y));
-                        mma_tf32(acc[t], ahi, __float_as_uint(bw.z), __float_as_uint(bw.w));
+                        mma_bf16(acc[t], a16, __float_as_uint(bw.z), __float_as_uint(bw.w));
                         mma_tf32(acc[t], ahi, __float_as_uint(bw.x), __float_as_uint(bw.y));
                     }
                 }
