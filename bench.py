@@ -271,7 +271,10 @@ class OpTimer:
         wrap("conv3x3", conv_bytes)
         wrap("stem_conv3x3", lambda a, k, o: nb(a[0]) + nb(o))
         wrap("head_conv3x3", lambda a, k, o: nb(a[0]) + nb(o) + nb(k.get("residual")))
-        wrap("gram32", lambda a, k, o: 2 * 32 * a[0].shape[0] * a[0].shape[2] * a[0].shape[3] * 4)
+        gram_bytes = lambda a, k, o: 2 * 32 * a[0].shape[0] * a[0].shape[2] * a[0].shape[3] * 4
+        wrap("gram32", gram_bytes)
+        wrap("match_index", gram_bytes)      # Gram pass + Matching argmin
+        wrap("attn_mixed", gram_bytes)       # Gram pass + CMTAttention 32x32 tail
         wrap("lfss_z", lambda a, k, o: nb(a[0]) + nb(o))
         wrap("lfss_out", lambda a, k, o: nb(a[0], a[1], a[6]) + nb(o) + nb(*k.get("extra", ())))
         wrap("lfss_tail", lambda a, k, o: nb(*a[0]) + nb(a[1]) + nb(o))   # 4 planes + x read, out written

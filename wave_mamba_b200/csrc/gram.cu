@@ -216,8 +216,9 @@ gram_reduce_kernel(const double *__restrict__ partial, float *__restrict__ out, 
 //           (sqrt / clamp of cdist are monotone), first index on ties
 //   MODE 2  CMTAttention (:787-797): attn = softmax_j( G_ij / (max(|q_i|, 1e-12) max(|k_j|, 1e-12)) * T ),
 //           mixed = W_po . attn  (project_out folded with the attention: the per-image 1x1 weights)
+constexpr int kTailThreads = 1024;
 template <int MODE>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kTailThreads)
 gram_reduce_tail_kernel(const double *__restrict__ partial, float *__restrict__ out, int nchunks,
                         int *__restrict__ idx_out, const float *__restrict__ temperature,
                         const float *__restrict__ w_po, float *__restrict__ mixed_out)
@@ -226,10 +227,21 @@ gram_reduce_tail_kernel(const double *__restrict__ partial, float *__restrict__ 
     __shared__ float attn[kC * kC];
     const int64_t b = blockIdx.x;
     const int tid = threadIdx.x;
-    for (int i = tid; i < kOut; i += kThreads) {
+    // one CTA per image sums the 148 x 1088 partials: thread = output, consecutive lanes = consecutive
+    // outputs (coalesced 256-byte loads; a warp per output with lanes over the chunks touches one 32-byte
+    // sector per lane and took ~90 us), chunks in order => deterministic and equal to gram_reduce_kernel
+    for (int i = tid; i < kOut; i += kTailThreads) {
         const double *p = partial + b * nchunks * kOut + i;
         double acc = 0.0;
-        for (int c = 0; c < nchunks; ++c) acc += p[(int64_t)c * kOut];
+        int c = 0;
+        for (; c + 8 <= nchunks; c += 8) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = p[(int64_t)(c + u) * kOut];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc += v[u];
+        }
+        for (; c < nchunks; ++c) acc += p[(int64_t)c * kOut];
         G[i] = (float)acc;
         if (out != nullptr) out[b * kOut + i] = (float)acc;
     }
@@ -263,7 +275,7 @@ gram_reduce_tail_kernel(const double *__restrict__ partial, float *__restrict__ 
             for (int j = 0; j < kC; ++j) attn[tid * kC + j] = __fdiv_rn(v[j], sum);
         }
         __syncthreads();
-        for (int i = tid; i < kC * kC; i += kThreads) {
+        for (int i = tid; i < kC * kC; i += kTailThreads) {
             const int o = i / kC, c = i - o * kC;
             float acc = 0.0f;
 #pragma unroll
@@ -332,9 +344,9 @@ static int gram_launch(const char *who, int mode, const float *x, int64_t x_bstr
         dim3 rgrid((kOut + kThreads - 1) / kThreads, (unsigned)B);
         gram_reduce_kernel<<<rgrid, kThreads, 0, s>>>(part, out, nchunks);
     } else if (mode == 1) {
-        gram_reduce_tail_kernel<1><<<(unsigned)B, kThreads, 0, s>>>(part, out, nchunks, idx_out, nullptr, nullptr, nullptr);
+        gram_reduce_tail_kernel<1><<<(unsigned)B, kTailThreads, 0, s>>>(part, out, nchunks, idx_out, nullptr, nullptr, nullptr);
     } else {
-        gram_reduce_tail_kernel<2><<<(unsigned)B, kThreads, 0, s>>>(part, out, nchunks, nullptr, temperature, w_po, mixed_out);
+        gram_reduce_tail_kernel<2><<<(unsigned)B, kTailThreads, 0, s>>>(part, out, nchunks, nullptr, temperature, w_po, mixed_out);
     }
     WM_LAUNCH_OK("gram reduce");
     return WM_OK;
