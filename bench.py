@@ -259,6 +259,7 @@ class OpTimer:
             return (cin + cout) * px * 4
         # algorithmic bytes: every input activation read once, every output written once
         wrap("dwt_haar", lambda a, k, o: nb(a[0]) + nb(*o))
+        wrap("dwt_haar_pool", lambda a, k, o: nb(a[0]) + nb(*o[:4]))
         wrap("iwt_haar", lambda a, k, o: nb(a[0], a[1]) + nb(o))
         wrap("iwt_haar_cat", lambda a, k, o: nb(a[0]) + nb(o))
         wrap("ss2d_core", lambda a, k, o: nb(a[0]) + nb(o))      # 512*B*L  
@@ -279,7 +280,8 @@ class OpTimer:
         wrap("lfss_out", lambda a, k, o: nb(a[0], a[1], a[6]) + nb(o) + nb(*k.get("extra", ())))
         wrap("lfss_tail", lambda a, k, o: nb(*a[0]) + nb(a[1]) + nb(o))   # 4 planes + x read, out written
         wrap("ss2d_dirs", lambda a, k, o: 2 * nb(a[0]))           # 512*B*L
-        wrap("skff", lambda a, k, o: 2 * nb(a[0], a[1], a[2]) + nb(o))   # pool reads 3, apply reads 3 + writes 1
+        # pool pass reads 3 (inside the DWT epilogue when `pool` is given), apply reads 3 + writes 1
+        wrap("skff", lambda a, k, o: (1 if k.get("pool") is not None else 2) * nb(a[0], a[1], a[2]) + nb(o))
         wrap("ps_down", lambda a, k, o: nb(a[0]) + nb(o))
         wrap("img_u8_to_f32", lambda a, k, o: nb(a[0]) + nb(o))
         wrap("img_f32_to_u8", lambda a, k, o: nb(a[0]) + nb(o))

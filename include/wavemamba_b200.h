@@ -31,7 +31,7 @@ extern "C" {
 #define WM_ECUDA (-2)     /* a CUDA runtime call or kernel launch failed               */
 #define WM_ENODEVICE (-3) /* no sm_100-class CUDA device is current                     */
 
-#define WM_ABI_VERSION 13
+#define WM_ABI_VERSION 14
 
 typedef void *wm_stream_t;
 
@@ -45,6 +45,11 @@ int wm_device_check(void);
  * Bit-exact with the reference (same /2 and the same left-to-right association). */
 int wm_dwt_haar_fwd(const float *x, float *ll, float *hl, float *lh, float *hh,
                     int64_t planes, int64_t H, int64_t W, wm_stream_t stream);
+/* The same transform with SKFF's global average pool (reference :939-948) in its epilogue: per-CTA partial
+ * sums of (HL + LH) + HH per plane go to `pool_partials` (>= wm_skff_workspace_bytes(B, H/2, W/2) bytes for
+ * planes = B*32, 8-byte aligned), in the layout wm_skff_apply_fwd reads. */
+int wm_dwt_haar_pool_fwd(const float *x, float *ll, float *hl, float *lh, float *hh, void *pool_partials,
+                         size_t workspace_bytes, int64_t planes, int64_t H, int64_t W, wm_stream_t stream);
 
 /* ---- Haar IWT -- iwt_init / IWT.forward, wavemamba_arch.py:113-130,142-148 -------------
  * The reference takes torch.cat([x_l, x_h], 1) (B,4C,h,w) (wavemamba_arch.py:1006); here
@@ -253,6 +258,12 @@ int wm_skff_fwd(const float *f0, const float *f1, const float *f2, const float *
                 const float *prelu_weight, const float *w_fc0, const float *w_fc1,
                 const float *w_fc2, float *out, void *workspace, size_t workspace_bytes, int64_t B,
                 int64_t C, int64_t h, int64_t w, wm_stream_t stream);
+/* SKFF with its pool pass done elsewhere: `pool_partials` = the buffer wm_dwt_haar_pool_fwd filled for the
+ * DWT that produced f0, f1, f2 (= HL, LH, HH).  One streaming pass instead of two. */
+int wm_skff_apply_fwd(const float *f0, const float *f1, const float *f2, const float *w_du,
+                      const float *prelu_weight, const float *w_fc0, const float *w_fc1,
+                      const float *w_fc2, float *out, const void *pool_partials, size_t workspace_bytes,
+                      int64_t B, int64_t C, int64_t h, int64_t w, wm_stream_t stream);
 
 /* ---- side inputs -- UNet.ps_down{1,2,3} = PixelUnshuffle(r) + Conv2d(3 r^2, 32, 1),
  *      wavemamba_arch.py:1014-1025, called :1043-1045 ----------------------------------------

@@ -683,6 +683,24 @@ def test_stem_and_head_conv(ops, dev, hw):
     torch.testing.assert_close(got, want, rtol=2e-5, atol=2e-5)
 
 
+@pytest.mark.parametrize("shape", [(2, 32, 48, 64), (1, 32, 20, 24), (1, 32, 270, 480)])
+def test_dwt_with_skff_pool_in_its_epilogue(ops, dev, shape):
+    """wm_dwt_haar_pool_fwd: the bands are bit-exact with the plain DWT, and SKFF through the pooled buffer
+    (one streaming pass) equals SKFF through its own pool pass to fp32 rounding of the mean.  20 x 24
+    (W % 16 != 0) takes the plain DWT + the separate pool kernel inside the same entry point."""
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(*shape, generator=g).to(dev)
+    plain = ops.dwt_haar(x)
+    ll, hl, lh, hh, pool = ops.dwt_haar_pool(x)
+    for a, b in zip(plain, (ll, hl, lh, hh)):
+        assert torch.equal(a, b)
+    w_du, pr = _rand(4, 32, 1, 1, g=g, s=0.3).to(dev), torch.tensor([0.25], device=dev)
+    fcs = [_rand(32, 4, 1, 1, g=g, s=0.5).to(dev) for _ in range(3)]
+    want = ops.skff(hl, lh, hh, w_du, pr, *fcs)
+    got = ops.skff(hl, lh, hh, w_du, pr, *fcs, pool=pool)
+    torch.testing.assert_close(got, want, rtol=1e-6, atol=1e-7)
+
+
 # ------------------------------------------------------------------------------- SKFF / ps_down
 def test_skff_golden(ops, dev):
     """SKFF (ref:939-959) against the reference's own output; 2e-6 abs (pool in fp64 partials)."""

@@ -12,7 +12,7 @@ from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libwavemamba_b200.so")
 
-ABI_VERSION = 13
+ABI_VERSION = 14
 
 # name -> (restype, argtypes); mirrors include/wavemamba_b200.h one to one
 SIGNATURES = {
@@ -20,6 +20,7 @@ SIGNATURES = {
     "wm_last_error": (c_char_p, []),
     "wm_device_check": (c_int, []),
     "wm_dwt_haar_fwd": (c_int, [c_void_p] * 5 + [c_int64] * 3 + [c_void_p]),
+    "wm_dwt_haar_pool_fwd": (c_int, [c_void_p] * 6 + [c_size_t] + [c_int64] * 3 + [c_void_p]),
     "wm_iwt_haar_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p] + [c_int64] * 4 + [c_void_p]),
     "wm_ss2d_core_workspace_bytes": (c_size_t, [c_int64] * 3),
     "wm_ss2d_debug_timing": (c_int, [c_void_p]),
@@ -57,6 +58,7 @@ SIGNATURES = {
     "wm_paconv_gate_fwd": (c_int, [c_void_p] * 5 + [c_int64] * 4 + [c_void_p]),
     "wm_skff_workspace_bytes": (c_size_t, [c_int64] * 3),
     "wm_skff_fwd": (c_int, [c_void_p] * 10 + [c_size_t] + [c_int64] * 4 + [c_void_p]),
+    "wm_skff_apply_fwd": (c_int, [c_void_p] * 10 + [c_size_t] + [c_int64] * 4 + [c_void_p]),
     "wm_ps_down_fwd": (c_int, [c_void_p] * 4 + [c_int64] * 3 + [c_int, c_void_p]),
     "wm_dw3x3_fwd": (c_int, [c_void_p] * 4 + [c_int64] * 4 + [c_int, c_void_p]),
     "wm_train_workspace_bytes": (c_size_t, [c_int64] * 4),

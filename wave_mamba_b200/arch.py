@@ -428,11 +428,11 @@ class SKFF(nn.Module):
         att = att.softmax(dim=1)
         return (stacked * att[:, :, :, None, None]).sum(1)
 
-    def forward(self, feats: List[torch.Tensor]):
+    def forward(self, feats: List[torch.Tensor], pool=None):
         if _wants_grad(self, feats[0]):
             return self.forward_train(feats)
         return ops.skff(feats[0], feats[1], feats[2], self.conv_du[0].weight, self.conv_du[1].weight,
-                        self.fcs[0].weight, self.fcs[1].weight, self.fcs[2].weight)
+                        self.fcs[0].weight, self.fcs[1].weight, self.fcs[2].weight, pool=pool)
 
 
 # --------------------------------------------------------------------------------------
@@ -464,10 +464,11 @@ class DownFRG(nn.Module):
             for blk in self.h_blk:
                 high = blk(high, low)
             return low, high
-        ll, hl, lh, hh = self.dwt(x)
+        # the DWT also produces SKFF's pooled sums of its three high bands (:939-948) in its epilogue
+        ll, hl, lh, hh, pool = ops.dwt_haar_pool(x.contiguous())
         low = ops.conv3x3(ll, self.l_conv.weight, self.l_conv.bias, x_b=x_d.contiguous())  # cat-free :975
         low = _run_low(self.l_blk, low)
-        high = self.h_fusion([hl, lh, hh])
+        high = self.h_fusion([hl, lh, hh], pool=pool)
         for blk in self.h_blk:
             high = blk(high, low)
         return low, high

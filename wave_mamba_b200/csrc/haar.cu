@@ -89,6 +89,52 @@ dwt_vec8_kernel(const float *__restrict__ x, float *__restrict__ ll, float *__re
     }
 }
 
+// DWT with SKFF's global average pool in its epilogue (reference :939-948: U = (HL + LH) + HH is pooled
+// right after the transform that produced the bands): grid (nblk, planes) as skff_pool_kernel, per-CTA
+// sums in fp32 per thread and fp64 across threads, written in the layout wm_skff_apply_fwd reads.
+__global__ void __launch_bounds__(kThreads)
+dwt_vec8_pool_kernel(const float *__restrict__ x, float *__restrict__ ll, float *__restrict__ hl,
+                     float *__restrict__ lh, float *__restrict__ hh, double *__restrict__ partial, int h, int w8,
+                     int64_t W)
+{
+    const int nblk = gridDim.x;
+    const int64_t plane = blockIdx.y;
+    const int64_t hw = (int64_t)h * w8 * 8;
+    const float *xp = x + plane * 4 * hw;
+    const int items = h * w8;
+    float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+    for (int it = blockIdx.x * kThreads + threadIdx.x; it < items; it += nblk * kThreads) {
+        const int r = it / w8, q = it - r * w8;
+        const float *top = xp + (int64_t)(2 * r) * W + 16 * q;
+        const float8 t0 = ld_stream8(top), t1 = ld_stream8(top + 8);
+        const float8 b0 = ld_stream8(top + W), b1 = ld_stream8(top + W + 8);
+        float4 oll[2], ohl[2], olh[2], ohh[2];
+        haar_analysis8(t0, b0, oll[0], ohl[0], olh[0], ohh[0]);
+        haar_analysis8(t1, b1, oll[1], ohl[1], olh[1], ohh[1]);
+        const int64_t o = plane * hw + (int64_t)r * (8 * w8) + 8 * q;
+        st_stream8(ll + o, oll[0], oll[1]);
+        st_stream8(hl + o, ohl[0], ohl[1]);
+        st_stream8(lh + o, olh[0], olh[1]);
+        st_stream8(hh + o, ohh[0], ohh[1]);
+        s0.x += (ohl[0].x + olh[0].x) + ohh[0].x; s0.y += (ohl[0].y + olh[0].y) + ohh[0].y;
+        s0.z += (ohl[0].z + olh[0].z) + ohh[0].z; s0.w += (ohl[0].w + olh[0].w) + ohh[0].w;
+        s1.x += (ohl[1].x + olh[1].x) + ohh[1].x; s1.y += (ohl[1].y + olh[1].y) + ohh[1].y;
+        s1.z += (ohl[1].z + olh[1].z) + ohh[1].z; s1.w += (ohl[1].w + olh[1].w) + ohh[1].w;
+    }
+    double d = (double)(((s0.x + s0.y) + (s0.z + s0.w)) + ((s1.x + s1.y) + (s1.z + s1.w)));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    __shared__ double ws[kThreads / 32];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = d;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int i = 0; i < kThreads / 32; ++i) t += ws[i];
+        partial[plane * nblk + blockIdx.x] = t;
+    }
+}
+
 __global__ void __launch_bounds__(kThreads)
 dwt_scalar_kernel(const float *__restrict__ x, float *__restrict__ ll, float *__restrict__ hl,
                   float *__restrict__ lh, float *__restrict__ hh, int64_t out_rows, int64_t w,
@@ -229,7 +275,42 @@ inline int stream_grid(int64_t items)
 }
 
 }  // namespace
+namespace skff {   // skff.cu
+int pool_blocks(int64_t hw);
+int launch_pool(const float *f0, const float *f1, const float *f2, double *partial, int64_t planes, int64_t hw,
+                cudaStream_t s);
+}
 }  // namespace wm
+
+extern "C" int wm_dwt_haar_pool_fwd(const float *x, float *ll, float *hl, float *lh, float *hh,
+                                    void *pool_partials, size_t workspace_bytes, int64_t planes, int64_t H,
+                                    int64_t W, wm_stream_t stream)
+{
+    using namespace wm;
+    WM_REQUIRE(planes >= 0 && H >= 0 && W >= 0 && planes <= 65535, "wm_dwt_haar_pool_fwd: bad sizes");
+    WM_REQUIRE(H % 2 == 0 && W % 2 == 0, "wm_dwt_haar_pool_fwd: H=%lld W=%lld must be even", (long long)H,
+               (long long)W);
+    if (planes == 0 || H == 0 || W == 0) return WM_OK;
+    WM_REQUIRE(x && ll && hl && lh && hh && pool_partials, "wm_dwt_haar_pool_fwd: null pointer");
+    const int64_t h = H / 2, w = W / 2;
+    const int nblk = skff::pool_blocks(h * w);
+    WM_REQUIRE(workspace_bytes >= (size_t)planes * nblk * sizeof(double) &&
+                   (reinterpret_cast<uintptr_t>(pool_partials) & 7u) == 0,
+               "wm_dwt_haar_pool_fwd: pool workspace too small or misaligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    double *partial = static_cast<double *>(pool_partials);
+    static const bool no256 = getenv("WM_IWT_128") != nullptr;
+    if (!no256 && W % 16 == 0 && h * (w / 8) < ((int64_t)1 << 30) && aligned32(x) && aligned32(ll) && aligned32(hl) &&
+        aligned32(lh) && aligned32(hh)) {
+        dwt_vec8_pool_kernel<<<dim3(nblk, (unsigned)planes), kThreads, 0, s>>>(x, ll, hl, lh, hh, partial, (int)h,
+                                                                               (int)(w / 8), W);
+        WM_LAUNCH_OK("dwt + pool kernel");
+        return WM_OK;
+    }
+    const int rc = wm_dwt_haar_fwd(x, ll, hl, lh, hh, planes, H, W, stream);
+    if (rc != WM_OK) return rc;
+    return skff::launch_pool(hl, lh, hh, partial, planes, h * w, s);
+}
 
 extern "C" int wm_dwt_haar_fwd(const float *x, float *ll, float *hl, float *lh, float *hh,
                                int64_t planes, int64_t H, int64_t W, wm_stream_t stream)

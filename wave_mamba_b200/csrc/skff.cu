@@ -228,13 +228,30 @@ int launch_ps_down(const float *x, const float *wgt, const float *bias, float *y
     return WM_OK;
 }
 
-inline int pool_blocks(int64_t hw)
+int pool_blocks(int64_t hw)
 {
     // enough CTAs per plane to fill the machine at B*C = 32 planes, never more than the data needs
     int64_t want = (hw / 4 + kThreads * 4 - 1) / (kThreads * 4);
     if (want < 1) want = 1;
     if (want > 64) want = 64;
     return (int)want;
+}
+
+static int band_vec(const float *f0, const float *f1, const float *f2, const float *out, int64_t hw)
+{
+    int vec = (hw % 4 == 0 && aligned16(f0) && aligned16(f1) && aligned16(f2) && (!out || aligned16(out))) ? 1 : 0;
+    if (vec && hw % 8 == 0 && aligned32(f0) && aligned32(f1) && aligned32(f2) && (!out || aligned32(out))) vec = 2;
+    return vec;
+}
+
+// pool pass alone (used by wm_dwt_haar_pool_fwd when the fused kernel's preconditions do not hold)
+int launch_pool(const float *f0, const float *f1, const float *f2, double *partial, int64_t planes, int64_t hw,
+                cudaStream_t s)
+{
+    skff_pool_kernel<<<dim3(pool_blocks(hw), (unsigned)planes), kThreads, 0, s>>>(f0, f1, f2, partial, hw,
+                                                                                band_vec(f0, f1, f2, nullptr, hw));
+    WM_LAUNCH_OK("skff pool");
+    return WM_OK;
 }
 
 }  // namespace skff
@@ -246,10 +263,10 @@ extern "C" size_t wm_skff_workspace_bytes(int64_t B, int64_t h, int64_t w)
     return (size_t)B * wm::skff::kC * wm::skff::pool_blocks(h * w) * sizeof(double);
 }
 
-extern "C" int wm_skff_fwd(const float *f0, const float *f1, const float *f2, const float *w_du,
-                           const float *prelu_weight, const float *w_fc0, const float *w_fc1,
-                           const float *w_fc2, float *out, void *workspace, size_t workspace_bytes,
-                           int64_t B, int64_t C, int64_t h, int64_t w, wm_stream_t stream)
+static int skff_run(bool pooled, const float *f0, const float *f1, const float *f2, const float *w_du,
+                    const float *prelu_weight, const float *w_fc0, const float *w_fc1,
+                    const float *w_fc2, float *out, void *workspace, size_t workspace_bytes,
+                    int64_t B, int64_t C, int64_t h, int64_t w, wm_stream_t stream)
 {
     using namespace wm;
     using namespace wm::skff;
@@ -263,17 +280,36 @@ extern "C" int wm_skff_fwd(const float *f0, const float *f1, const float *f2, co
     WM_REQUIRE(workspace && workspace_bytes >= (size_t)B * kC * nblk * sizeof(double),
                "wm_skff_fwd: workspace too small");
     WM_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 7u) == 0, "wm_skff_fwd: workspace must be 8-byte aligned");
-    int vec = (hw % 4 == 0 && aligned16(f0) && aligned16(f1) && aligned16(f2) && aligned16(out)) ? 1 : 0;
-    if (vec && hw % 8 == 0 && aligned32(f0) && aligned32(f1) && aligned32(f2) && aligned32(out)) vec = 2;
+    const int vec = band_vec(f0, f1, f2, out, hw);
     cudaStream_t s = (cudaStream_t)stream;
     double *partial = static_cast<double *>(workspace);
-    skff_pool_kernel<<<dim3(nblk, (unsigned)(B * kC)), kThreads, 0, s>>>(f0, f1, f2, partial, hw, vec);
-    WM_LAUNCH_OK("skff pool");
+    if (!pooled) {
+        skff_pool_kernel<<<dim3(nblk, (unsigned)(B * kC)), kThreads, 0, s>>>(f0, f1, f2, partial, hw, vec);
+        WM_LAUNCH_OK("skff pool");
+    }
     skff_apply_kernel<<<dim3(nblk, kC, (unsigned)B), kThreads, 0, s>>>(f0, f1, f2, partial, nblk, w_du,
                                                                         prelu_weight, w_fc0, w_fc1,
                                                                         w_fc2, out, hw, vec);
     WM_LAUNCH_OK("skff apply");
     return WM_OK;
+}
+
+extern "C" int wm_skff_fwd(const float *f0, const float *f1, const float *f2, const float *w_du,
+                           const float *prelu_weight, const float *w_fc0, const float *w_fc1,
+                           const float *w_fc2, float *out, void *workspace, size_t workspace_bytes,
+                           int64_t B, int64_t C, int64_t h, int64_t w, wm_stream_t stream)
+{
+    return skff_run(false, f0, f1, f2, w_du, prelu_weight, w_fc0, w_fc1, w_fc2, out, workspace, workspace_bytes, B, C,
+                    h, w, stream);
+}
+
+extern "C" int wm_skff_apply_fwd(const float *f0, const float *f1, const float *f2, const float *w_du,
+                                 const float *prelu_weight, const float *w_fc0, const float *w_fc1,
+                                 const float *w_fc2, float *out, const void *pool_partials, size_t workspace_bytes,
+                                 int64_t B, int64_t C, int64_t h, int64_t w, wm_stream_t stream)
+{
+    return skff_run(true, f0, f1, f2, w_du, prelu_weight, w_fc0, w_fc1, w_fc2, out, const_cast<void *>(pool_partials),
+                    workspace_bytes, B, C, h, w, stream);
 }
 
 extern "C" int wm_ps_down_fwd(const float *x, const float *weight, const float *bias, float *y,

@@ -62,6 +62,30 @@ def dwt_haar(x: torch.Tensor):
     return tuple(outs)
 
 
+def dwt_haar_pool(x: torch.Tensor):
+    """dwt_haar plus SKFF's pool pass in the transform's epilogue (reference :939-948 pools (HL + LH) + HH
+    right after the DWT): returns (LL, HL, LH, HH, pool) where ``pool`` is the per-CTA partial-sum buffer
+    that ``skff(..., pool=pool)`` consumes instead of re-reading the three bands."""
+    _chk(x, "x")
+    if x.dim() != 4:
+        raise ValueError(f"x: expected 4 dims, got {x.dim()}")
+    B, C, H, W = x.shape
+    if H % 2 or W % 2:
+        raise ValueError(f"DWT needs even H and W, got {H}x{W}")
+    if C != 32:
+        raise ValueError(f"dwt_haar_pool: C={C} unsupported (32: the SKFF band width)")
+    outs = [torch.empty(B, C, H // 2, W // 2, device=x.device, dtype=x.dtype) for _ in range(4)]
+    lib = _cabi.load()
+    with torch.cuda.device(x.device):
+        nbytes = lib.wm_skff_workspace_bytes(B, H // 2, W // 2)
+        pool = torch.empty(max(nbytes // 8, 1), dtype=torch.float64, device=x.device)
+        rc = lib.wm_dwt_haar_pool_fwd(x.data_ptr(), *[o.data_ptr() for o in outs], pool.data_ptr(), nbytes, B * C,
+                                      H, W, _stream(x))
+    _cabi.check(rc, "wm_dwt_haar_pool_fwd")
+    _count(1)
+    return (*outs, pool)
+
+
 def iwt_haar(low: torch.Tensor, high: torch.Tensor) -> torch.Tensor:
     """low (B,C,h,w) = LL, high (B,3C,h,w) = [HL|LH|HH] -> (B,C,2h,2w).
     reference iwt_init :113-130 applied to cat([low, high], 1) (:1006), without the cat."""
@@ -613,8 +637,9 @@ def head_conv3x3(x, weight, bias=None, residual=None) -> torch.Tensor:
     return y
 
 
-def skff(f0, f1, f2, w_du, prelu_weight, w_fc0, w_fc1, w_fc2) -> torch.Tensor:
-    """SKFF over the three high-frequency bands (reference :939-959): two streaming kernels."""
+def skff(f0, f1, f2, w_du, prelu_weight, w_fc0, w_fc1, w_fc2, pool=None) -> torch.Tensor:
+    """SKFF over the three high-frequency bands (reference :939-959): two streaming kernels, or one when
+    ``pool`` (from ``dwt_haar_pool`` of the same bands) already holds the pool pass."""
     _chk(f0, "f0")
     B, C, h, w = f0.shape
     _chk(f1, "f1", (B, C, h, w))
@@ -629,14 +654,23 @@ def skff(f0, f1, f2, w_du, prelu_weight, w_fc0, w_fc1, w_fc2) -> torch.Tensor:
     lib = _cabi.load()
     with torch.cuda.device(f0.device):
         nbytes = lib.wm_skff_workspace_bytes(B, h, w)
-        ws = torch.empty(max(nbytes // 8, 1), dtype=torch.float64, device=f0.device)
-        rc = lib.wm_skff_fwd(f0.data_ptr(), f1.data_ptr(), f2.data_ptr(), w_du.data_ptr(),
-                             prelu_weight.data_ptr(), fcs[0].data_ptr(), fcs[1].data_ptr(),
-                             fcs[2].data_ptr(), out.data_ptr(), ws.data_ptr(), nbytes, B, C, h, w,
-                             _stream(f0))
-    _cabi.check(rc, "wm_skff_fwd")
+        if pool is not None:
+            if pool.dtype != torch.float64 or pool.numel() * 8 < nbytes or pool.device != f0.device:
+                raise ValueError("skff: pool is not the buffer dwt_haar_pool returned for these bands")
+            rc = lib.wm_skff_apply_fwd(f0.data_ptr(), f1.data_ptr(), f2.data_ptr(), w_du.data_ptr(),
+                                       prelu_weight.data_ptr(), fcs[0].data_ptr(), fcs[1].data_ptr(),
+                                       fcs[2].data_ptr(), out.data_ptr(), pool.data_ptr(), nbytes, B, C, h, w,
+                                       _stream(f0))
+            _cabi.check(rc, "wm_skff_apply_fwd")
+        else:
+            ws = torch.empty(max(nbytes // 8, 1), dtype=torch.float64, device=f0.device)
+            rc = lib.wm_skff_fwd(f0.data_ptr(), f1.data_ptr(), f2.data_ptr(), w_du.data_ptr(),
+                                 prelu_weight.data_ptr(), fcs[0].data_ptr(), fcs[1].data_ptr(),
+                                 fcs[2].data_ptr(), out.data_ptr(), ws.data_ptr(), nbytes, B, C, h, w,
+                                 _stream(f0))
+            _cabi.check(rc, "wm_skff_fwd")
     if B and h and w:
-        _count(2)
+        _count(1 if pool is not None else 2)
     return out
 
 
