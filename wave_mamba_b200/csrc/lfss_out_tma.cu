@@ -207,21 +207,76 @@ lfss_out_tma_kernel(const __grid_constant__ Maps maps, const float *__restrict__
 // wrote -- one kernel and 224 channel planes of traffic less per LFSSBlock (x is needed here anyway, as
 // the residual input).  Twelve warps in four roles, a 4-deep software pipeline over the tiles:
 //   thread 0     TMA: four direction-plane boxes + the x box (72 KB) per tile, two stages
-//   warps 8-11   Z: LayerNorm_32 of the x tile (one thread per pixel) -> xn; 32 -> 64 projection, thread =
-//                (4 pixels, 8 outputs), SiLU -> zbuf[64][64]
+//   warps 8-11   Z: LayerNorm_32 of the x tile (one thread per pixel) -> xn; 32 -> 64 projection on the
+//                tensor cores (a warp per 16 pixels), SiLU -> zbuf
 //   warps 0-3    A: direction sum + LayerNorm_64 (statistics need no z; lane = pixel, the two 32-channel
 //                halves of a pixel sit in different warps and exchange partial sums through shared memory),
 //                then * zbuf -> v[tile & 1]
-//   warps 4-5    B: out_proj of v + x * skip_scale, as above
+//   warps 4-7    B: out_proj of v on the tensor cores (a warp per 16 pixels) + x * skip_scale
+// The two 1x1 GEMMs run as mma.sync m16n8k8 TF32 + one bf16 m16n8k16 MMA per k-step for the two 3xTF32
+// correction terms (as the SS2D projection, ss2d.cu): with FFMA2 and weights from shared memory this kernel
+// was bound by the return path of its shared-memory loads (~5 k of 5.8 k cycles per tile against 3.5 k of
+// HBM time); the fragments need a fifth of those bytes.  v, zbuf and xn have padded row pitches
+// (72 / 68 / 72 floats) so that the fragment loads and the accumulator stores are bank-conflict free.
 // Named barriers (id: who arrives -> who waits): 1,2 vFull[buf] A->B; 3,4 vEmpty[buf] B->A; 5 zFull Z->A;
 // 6 zEmpty A->Z; 7,8 stageFree[buf] Z->A (thread 0 of A then re-issues the stage); 9 inside Z; 10 inside A.
 // ---------------------------------------------------------------------------------------------
 constexpr int kCx = 32;
-constexpr int kThreadsZ = 128, kThreadsF = kThreadsA + kThreadsB + kThreadsZ;     // 320
+constexpr int kThreadsB2 = 128, kThreadsZ = 128, kThreadsF = kThreadsA + kThreadsB2 + kThreadsZ;   // 384
+constexpr int kPV = 72, kPZ = 68, kPX = 72;        // row pitches of v, zbuf, xn
 constexpr uint32_t kXBoxBytes = kCx * kTP * 4;                                    // 8 KB
 constexpr uint32_t kStageBytesF = 4 * kBoxBytes + kXBoxBytes;                     // 72 KB
-constexpr size_t kSmemF = 2 * kStageBytesF + 2 * kBoxBytes /* v */ + kBoxBytes /* zbuf */ + kXBoxBytes /* xn */ +
-                          sizeof(float) * (kC * kCout + kCx * kC + 2 * kC + kCout + 2 * kCx + 4 * kTP) + 2 * 8;
+constexpr size_t kSmemF = 2 * kStageBytesF +
+                          sizeof(float) * (2 * kC * kPV /* v */ + kC * kPZ /* zbuf */ + kCx * kPX /* xn */ +
+                                           kC * kCout + kCx * kC + 2 * kC + kCout + 2 * kCx + 4 * kTP) + 2 * 8;
+static_assert(kSmemF <= 232448, "shared memory budget");
+
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+{
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+{
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// acc[nt] += A(16 pixels x 8K channels) . W, fp32-accurate: per k-step one TF32 MMA on the raw fp32 words (the
+// tensor core reads their top 19 bits) and one bf16 MMA whose K slots 0-7 carry a_lo x w and slots 8-15
+// a x w_lo (slot 2t, 2t+1 <-> channels t, t+4 of the k-step).  a: [channel][pixel] with row pitch PA, already
+// offset to this warp's 16 pixels; wf: float2 per (k-step, n-tile, lane) = (W[k = t][n = g], W[k = t+4][n = g]).
+template <int KSTEPS, int NT, int PA>
+__device__ __forceinline__ void gemm_frag(float (&acc)[NT][4], const float *a, const float2 *wf, int lane)
+{
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks) {
+        const float *ap = a + (8 * ks + t) * PA + g;
+        const float av[4] = {ap[0], ap[8], ap[4 * PA], ap[4 * PA + 8]};
+        uint32_t ahi[4];
+        float alo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            ahi[i] = __float_as_uint(av[i]);
+            alo[i] = av[i] - __uint_as_float(ahi[i] & 0xffffe000u);
+        }
+        const uint32_t a16[4] = {pack_bf16x2(alo[0], alo[2]), pack_bf16x2(alo[1], alo[3]),
+                                 pack_bf16x2(av[0], av[2]), pack_bf16x2(av[1], av[3])};
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const float2 w = wf[(ks * NT + nt) * 32 + lane];
+            const float l0 = w.x - __uint_as_float(__float_as_uint(w.x) & 0xffffe000u);
+            const float l1 = w.y - __uint_as_float(__float_as_uint(w.y) & 0xffffe000u);
+            mma_bf16(acc[nt], a16, pack_bf16x2(w.x, w.y), pack_bf16x2(l0, l1));
+            mma_tf32(acc[nt], ahi, __float_as_uint(w.x), __float_as_uint(w.y));
+        }
+    }
+}
 
 struct MapsF {
     CUtensorMap p[4];    // direction planes in summation order
@@ -245,14 +300,14 @@ lfss_tail_tma_kernel(const __grid_constant__ MapsF maps, const float *__restrict
                      int tiles_per_img, int total_tiles)
 {
     constexpr int kBarVFull = 1, kBarVEmpty = 3, kBarZFull = 5, kBarZEmpty = 6, kBarStage = 7, kBarZ = 9, kBarA = 10;
-    constexpr int kCntAB = kThreadsA + kThreadsB, kCntAZ = kThreadsA + kThreadsZ;
+    constexpr int kCntAB = kThreadsA + kThreadsB2, kCntAZ = kThreadsA + kThreadsZ;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *stage = reinterpret_cast<float *>(smem_raw);                     // [2]{[4][64 ch][64 px], [32 ch][64 px]}
-    float *vbuf = reinterpret_cast<float *>(smem_raw + 2 * kStageBytesF);   // [2][64][64]
-    float *zbuf = vbuf + 2 * kC * kTP;                                      // [64][64]
-    float *xn = zbuf + kC * kTP;                                            // [32][64]
-    float *wt = xn + kCx * kTP;                                             // [64 ci][32 co]  out_proj
-    float *wz = wt + kC * kCout;                                            // [32 ci][64 co]  in_proj, z half
+    float *vbuf = reinterpret_cast<float *>(smem_raw + 2 * kStageBytesF);   // [2][64 ch][kPV]
+    float *zbuf = vbuf + 2 * kC * kPV;                                      // [64 ch][kPZ]
+    float *xn = zbuf + kC * kPZ;                                            // [32 ch][kPX]
+    float *wt = xn + kCx * kPX;        // out_proj B fragments: float2 [8 k-steps][4 n-tiles][32 lanes]
+    float *wz = wt + kC * kCout;       // in_proj (z half) B fragments: float2 [4 k-steps][8 n-tiles][32 lanes]
     float *lw = wz + kCx * kC, *lb = lw + kC, *rs = lb + kC;
     float *l1w = rs + kCout, *l1b = l1w + kCx;
     float *sbuf = l1b + kCx;                                                // [mean | var][side][64 px] partial sums
@@ -277,13 +332,16 @@ lfss_tail_tma_kernel(const __grid_constant__ MapsF maps, const float *__restrict
         if (my_tiles > 0) issue(0);
         if (my_tiles > 1) issue(1);
     }
-    for (int i = tid; i < kC * kCout; i += kThreadsF) {
-        const int co = i / kC, ci = i - co * kC;
-        wt[ci * kCout + co] = __ldg(w_out + i);
+    // B fragments of m16n8k8: lane (g = lane / 4, t = lane % 4) holds W[k = 8 ks + t][n = 8 nt + g] and k + 4
+    for (int i = tid; i < 8 * 4 * 32; i += kThreadsF) {          // out_proj: k = ci (64), n = co (32); w_out (32, 64)
+        const int ln = i & 31, nt = (i >> 5) & 3, ks = i >> 7;
+        const int n = 8 * nt + (ln >> 2), k = 8 * ks + (ln & 3);
+        reinterpret_cast<float2 *>(wt)[i] = make_float2(__ldg(w_out + n * kC + k), __ldg(w_out + n * kC + k + 4));
     }
-    for (int i = tid; i < kC * kCx; i += kThreadsF) {
-        const int co = i / kCx, ci = i - co * kCx;
-        wz[ci * kC + co] = __ldg(w_z + i);              // w_z: (64, 32) = rows 64..127 of in_proj.weight
+    for (int i = tid; i < 4 * 8 * 32; i += kThreadsF) {          // in_proj z half: k = ci (32), n = co (64); w_z (64, 32)
+        const int ln = i & 31, nt = (i >> 5) & 7, ks = i >> 8;
+        const int n = 8 * nt + (ln >> 2), k = 8 * ks + (ln & 3);
+        reinterpret_cast<float2 *>(wz)[i] = make_float2(__ldg(w_z + n * kCx + k), __ldg(w_z + n * kCx + k + 4));
     }
     for (int i = tid; i < kC; i += kThreadsF) { lw[i] = __ldg(on_w + i); lb[i] = __ldg(on_b + i); }
     if (tid < kCout) rs[tid] = __ldg(skip_scale + tid);
@@ -328,76 +386,59 @@ lfss_tail_tma_kernel(const __grid_constant__ MapsF maps, const float *__restrict
             const float rstd = 1.0f / sqrtf(var + eps);
             bar_sync(kBarZFull, kCntAZ);                // zbuf holds this tile's gate
             if (j >= 2) bar_sync(kBarVEmpty + buf, kCntAB);   // B is done with v[buf]
-            float *vp = vbuf + buf * (kC * kTP) + c0 * kTP + px;
-            const float *zp = zbuf + c0 * kTP + px;
+            float *vp = vbuf + buf * (kC * kPV) + c0 * kPV + px;
+            const float *zp = zbuf + c0 * kPZ + px;
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-                vp[i * kTP] = fmaf((xv[i] - mu) * rstd, lw[c0 + i], lb[c0 + i]) * zp[i * kTP];
+                vp[i * kPV] = fmaf((xv[i] - mu) * rstd, lw[c0 + i], lb[c0 + i]) * zp[i * kPZ];
             bar_arrive(kBarVFull + buf, kCntAB);        // v[buf] is complete
             if (j + 1 < my_tiles) bar_arrive(kBarZEmpty, kCntAZ);   // zbuf may be overwritten
         }
-    } else if (tid < kThreadsA + kThreadsB) {
+    } else if (tid < kThreadsA + kThreadsB2) {
         // =========================== B: out_proj + skip ========================================
         const int t = tid - kThreadsA;
-        const int q = t & 3, pq = t >> 2;                 // output quarter (8 outputs), pixel quad 0..15
+        const int lane = t & 31, m0 = (t >> 5) * 16;      // this warp's 16 pixels
+        const int g = lane >> 2, t4 = lane & 3;
 #pragma unroll 1
         for (int j = 0; j < my_tiles; ++j) {
             const int buf = j & 1;
             const int tile = blockIdx.x + j * gridDim.x;
             const int b = tile / tiles_per_img;
-            const int64_t p = (int64_t)(tile - b * tiles_per_img) * kTP + 4 * pq;
-            const bool inside = p < hw;
-            const int64_t o = ((int64_t)b * kCout + q * 8) * hw + p;
-            float4 xr[8];
-            if (inside) {
+            const int64_t p0 = (int64_t)(tile - b * tiles_per_img) * kTP + m0 + g;   // accumulator rows g and g + 8
+            const bool in0 = p0 < hw, in1 = p0 + 8 < hw;
+            // accumulator fragment (n-tile nt, i): pixel p0 + 8 (i / 2), output 8 nt + 2 t4 + (i & 1)
+            const int64_t o = ((int64_t)b * kCout + 2 * t4) * hw + p0;
+            float xr[4][4];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) xr[i] = __ldg(reinterpret_cast<const float4 *>(x + o + (int64_t)i * hw));
-            }
-            bar_sync(kBarVFull + buf, kCntAB);
-            f32x2 acc[4][4];
-#pragma unroll
-            for (int pp = 0; pp < 4; ++pp)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) acc[pp][i] = pack2(0.0f, 0.0f);
-            const float *vb = vbuf + buf * (kC * kTP) + 4 * pq;
-#pragma unroll 4
-            for (int ci = 0; ci < kC; ++ci) {
-                const float4 xv = *reinterpret_cast<const float4 *>(vb + ci * kTP);
-                const f32x2 x2[4] = {pack2(xv.x, xv.x), pack2(xv.y, xv.y), pack2(xv.z, xv.z), pack2(xv.w, xv.w)};
-                const ulonglong2 *wr = reinterpret_cast<const ulonglong2 *>(wt + ci * kCout + q * 8);
-                const ulonglong2 wa = wr[0], wb = wr[1];
-#pragma unroll
-                for (int pp = 0; pp < 4; ++pp) {
-                    acc[pp][0] = ffma2(x2[pp], wa.x, acc[pp][0]);
-                    acc[pp][1] = ffma2(x2[pp], wa.y, acc[pp][1]);
-                    acc[pp][2] = ffma2(x2[pp], wb.x, acc[pp][2]);
-                    acc[pp][3] = ffma2(x2[pp], wb.y, acc[pp][3]);
-                }
-            }
-            if (j + 2 < my_tiles) bar_arrive(kBarVEmpty + buf, kCntAB);
-            if (inside) {
+            for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    float v[2][4];
-#pragma unroll
-                    for (int pp = 0; pp < 4; ++pp) unpack2(acc[pp][i], v[0][pp], v[1][pp]);
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        const int co = 2 * i + k;
-                        const float sc = rs[q * 8 + co];
-                        const float4 u = xr[co];
-                        const float4 r = make_float4(fmaf(u.x, sc, v[k][0]), fmaf(u.y, sc, v[k][1]),
-                                                     fmaf(u.z, sc, v[k][2]), fmaf(u.w, sc, v[k][3]));
-                        *reinterpret_cast<float4 *>(out + o + (int64_t)co * hw) = r;
-                    }
+                    const bool ok = (i & 2) ? in1 : in0;
+                    xr[nt][i] = ok ? __ldg(x + o + (int64_t)(8 * nt + (i & 1)) * hw + ((i & 2) ? 8 : 0)) : 0.0f;
                 }
-            }
+            bar_sync(kBarVFull + buf, kCntAB);
+            float acc[4][4];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[nt][i] = 0.0f;
+            gemm_frag<8, 4, kPV>(acc, vbuf + buf * (kC * kPV) + m0, reinterpret_cast<const float2 *>(wt), lane);
+            if (j + 2 < my_tiles) bar_arrive(kBarVEmpty + buf, kCntAB);
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const bool ok = (i & 2) ? in1 : in0;
+                    const int co = 8 * nt + 2 * t4 + (i & 1);
+                    if (ok)
+                        out[o + (int64_t)(8 * nt + (i & 1)) * hw + ((i & 2) ? 8 : 0)] = fmaf(xr[nt][i], rs[co], acc[nt][i]);
+                }
         }
     } else {
         // =========================== Z: LayerNorm_32(x), 32 -> 64, SiLU ==========================
-        const int t = tid - kThreadsA - kThreadsB;        // 0..127
-        const int q = t >> 4, pq = t & 15;                // 8 outputs 8q.., pixels 4pq..  (a quarter-warp = 8
-                                                          // consecutive pixel quads: conflict-free 16-byte stores)
+        const int t = tid - kThreadsA - kThreadsB2;       // 0..127
+        const int lane = t & 31, m0 = (t >> 5) * 16;      // this warp's 16 pixels in the projection
+        const int g = lane >> 2, t4 = lane & 3;
 #pragma unroll 1
         for (int j = 0; j < my_tiles; ++j) {
             const int buf = j & 1;
@@ -415,47 +456,29 @@ lfss_tail_tma_kernel(const __grid_constant__ MapsF maps, const float *__restrict
                 var *= (1.0f / kCx);
                 const float rstd = 1.0f / sqrtf(var + ln1_eps);
 #pragma unroll
-                for (int i = 0; i < kCx; ++i) xn[i * kTP + t] = fmaf((xv[i] - mu) * rstd, l1w[i], l1b[i]);
+                for (int i = 0; i < kCx; ++i) xn[i * kPX + t] = fmaf((xv[i] - mu) * rstd, l1w[i], l1b[i]);
             }
             bar_arrive(kBarStage + buf, kCntAZ);          // done with the stage (x box)
             bar_sync(kBarZ, kThreadsZ);                   // xn is complete
-            f32x2 acc[4][4];
+            float acc[8][4];
 #pragma unroll
-            for (int pp = 0; pp < 4; ++pp)
+            for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) acc[pp][i] = pack2(0.0f, 0.0f);
-#pragma unroll 4
-            for (int ci = 0; ci < kCx; ++ci) {
-                const float4 xv = *reinterpret_cast<const float4 *>(xn + ci * kTP + 4 * pq);
-                const f32x2 x2[4] = {pack2(xv.x, xv.x), pack2(xv.y, xv.y), pack2(xv.z, xv.z), pack2(xv.w, xv.w)};
-                const ulonglong2 *wr = reinterpret_cast<const ulonglong2 *>(wz + ci * kC + q * 8);
-                const ulonglong2 wa = wr[0], wb = wr[1];
-#pragma unroll
-                for (int pp = 0; pp < 4; ++pp) {
-                    acc[pp][0] = ffma2(x2[pp], wa.x, acc[pp][0]);
-                    acc[pp][1] = ffma2(x2[pp], wa.y, acc[pp][1]);
-                    acc[pp][2] = ffma2(x2[pp], wb.x, acc[pp][2]);
-                    acc[pp][3] = ffma2(x2[pp], wb.y, acc[pp][3]);
-                }
-            }
+                for (int i = 0; i < 4; ++i) acc[nt][i] = 0.0f;
+            gemm_frag<4, 8, kPX>(acc, xn + m0, reinterpret_cast<const float2 *>(wz), lane);
             bar_sync(kBarZ, kThreadsZ);                   // every thread has left xn (the next tile rewrites it)
-            float4 zr[8];                                 // SiLU before the hand-over wait: off the A <-> Z cycle
+            // SiLU before the hand-over wait: off the A <-> Z cycle
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                float v[2][4];
+            for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-                for (int pp = 0; pp < 4; ++pp) unpack2(acc[pp][i], v[0][pp], v[1][pp]);
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    float4 r;
-                    r.x = __fdividef(v[k][0], 1.0f + __expf(-v[k][0])); r.y = __fdividef(v[k][1], 1.0f + __expf(-v[k][1]));
-                    r.z = __fdividef(v[k][2], 1.0f + __expf(-v[k][2])); r.w = __fdividef(v[k][3], 1.0f + __expf(-v[k][3]));
-                    zr[2 * i + k] = r;
-                }
-            }
+                for (int i = 0; i < 4; ++i) acc[nt][i] = __fdividef(acc[nt][i], 1.0f + __expf(-acc[nt][i]));
             if (j >= 1) bar_sync(kBarZEmpty, kCntAZ);     // A is done with the previous tile's gate
+            // accumulator fragment (nt, i): pixel m0 + g + 8 (i / 2), channel 8 nt + 2 t4 + (i & 1)
 #pragma unroll
-            for (int c = 0; c < 8; ++c) *reinterpret_cast<float4 *>(zbuf + (q * 8 + c) * kTP + 4 * pq) = zr[c];
+            for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    zbuf[(8 * nt + 2 * t4 + (i & 1)) * kPZ + m0 + g + ((i & 2) ? 8 : 0)] = acc[nt][i];
             bar_arrive(kBarZFull, kCntAZ);                // zbuf holds this tile's gate
         }
     }
