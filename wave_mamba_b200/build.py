@@ -43,7 +43,7 @@ def _stale(target: str, deps) -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
     os.makedirs(OBJ, exist_ok=True)
-    shared_deps = [HEADER, os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tc5_common.cuh"), os.path.join(CSRC, "tma.cuh"),
+    shared_deps = [HEADER, os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tc5_common.cuh"), os.path.join(CSRC, "tma.cuh"), os.path.join(CSRC, "mma_frag.cuh"),
                    os.path.join(CSRC, "ss2d_common.cuh"),
                    os.path.abspath(__file__)]
     objs = []
