@@ -20,6 +20,11 @@
 // a_lo and b rounded to bf16 cost 2^-9 of that term each = 2^-20 of the product, the size of the a_lo*b_lo
 // term 3xTF32 drops anyway -- and the a_lo operand and its weights are read at half the bytes
 // (11 -> 8.5 KB per 8 input channels and M tile for 32 outputs, 14 -> 11 KB for 64).
+// The gated 64 -> 64 variant goes one step further ("KC"): BOTH correction terms share one bf16 MMA with
+// K-concatenated operands ([a_lo | a_hi] x [b | b_lo], K = 16 per 8 input channels) and the tf32 MMA is
+// the plain a_hi*b_hi with N = COUT.  That costs ~9 % more operand bytes than the merged form but halves
+// the accumulator columns: 2 x (main + gate) x 2 M tiles = 512 columns fit TMEM twice, so the gated
+// variant's epilogue -- until then exposed, a quarter of its tile time -- overlaps the next tile's MMAs.
 //
 // Warp-specialised, persistent (one CTA per SM, 15 warps), everything synchronised with mbarriers --
 // no CTA-wide barrier inside the tile loop:
@@ -87,8 +92,13 @@ template <int CIN, int COUT, bool GATE>
 struct Cfg {
     static constexpr int NCH = CIN / 32;                       // K halves (slabs) per tile
     static constexpr int NTAPS = GATE ? 10 : 9;
-    static constexpr int kChunkTf32F4 = kKcSlab * 2 * COUT;    // [kc 0..7][hi | lo][COUT] float4
-    static constexpr int kChunkF4 = kChunkTf32F4 + 4 * COUT;   // + [kc8 0..3][COUT] 8 x bf16: float4 per chunk
+    static constexpr bool KC = GATE;                           // K-concatenated bf16 corrections (see the header)
+    // weight chunk: merged [kc 0..7][hi | lo][COUT] float4 + [kc8 0..3][COUT] 8 x bf16 of w;
+    //               KC     [kc 0..7][hi][COUT] float4      + [kc8 0..3][w | w_lo][COUT] 8 x bf16
+    static constexpr int kChunkTf32F4 = KC ? kKcSlab * COUT : kKcSlab * 2 * COUT;
+    static constexpr int kChunkF4 = kChunkTf32F4 + (KC ? 8 : 4) * COUT;
+    static constexpr int kLoSlabF4 = KC ? kSlabF4 : kSlabF4 / 2;      // 16-byte units of one slot of the bf16 slab
+    static constexpr int kAccCols = KC ? COUT : 2 * COUT;             // TMEM columns per (M tile, region)
     static constexpr int kChunkBytes = kChunkF4 * 16;
     // weight ring depth (what fits next to the X slabs).  The issuing threads run ahead of the tensor
     // core until they meet a stage that is still being refilled, so their timers always show a wait on
@@ -103,13 +113,13 @@ struct Cfg {
     static constexpr int kStages = COUT >= 96 ? 3 : 4;
     static constexpr int kTileUnits = NCH * NTAPS;             // chunks per tile, K half major
     static constexpr int kTileStages = (kTileUnits + kUnits - 1) / kUnits;
-    static constexpr int kColsBuf = 4 * COUT * (GATE ? 2 : 1); // TMEM columns of one accumulator set
+    static constexpr int kColsBuf = 2 * kAccCols * (GATE ? 2 : 1);    // TMEM columns of one accumulator set
     static constexpr int NACC = 2 * kColsBuf <= 512 ? 2 : 1;
     static constexpr int kColsNeed = NACC * kColsBuf;
     static constexpr int kCols = kColsNeed <= 32 ? 32 : kColsNeed <= 64 ? 64 : kColsNeed <= 128 ? 128
                                  : kColsNeed <= 256 ? 256 : 512;
     static constexpr int kNumBars = 2 * kStages + 4 + 2 * NACC;
-    static constexpr size_t kSmem = sizeof(float4) * (size_t)(3 * kSlabF4 + kStages * kStageF4) +
+    static constexpr size_t kSmem = sizeof(float4) * (size_t)(2 * kSlabF4 + 2 * kLoSlabF4 + kStages * kStageF4) +
                                     8 * kNumBars + 16;
     static_assert(CIN == 32 || CIN == 64 || CIN == 96, "CIN must be 32, 64 or 96");
     static_assert(2 * COUT <= 256 && (2 * COUT) % 16 == 0, "merged N must be a legal UMMA N");
@@ -125,8 +135,8 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
     constexpr int NCH = C::NCH, NTAPS = C::NTAPS, kStages = C::kStages, NACC = C::NACC;
     extern __shared__ __align__(128) float smem[];
     float4 *xhi = reinterpret_cast<float4 *>(smem);                 // [2 slots][8 kc][kNPos]
-    uint4 *xlo = reinterpret_cast<uint4 *>(xhi + 2 * kSlabF4);      // [2 slots][4 kc8][kNPos] 8 x bf16
-    float4 *wbuf = xhi + 3 * kSlabF4;                               // [kStages][kUnits][kChunkF4]
+    uint4 *xlo = reinterpret_cast<uint4 *>(xhi + 2 * kSlabF4);      // [2 slots][4 kc8]([lo | hi] if KC)[kNPos] 8 x bf16
+    float4 *wbuf = xhi + 2 * kSlabF4 + 2 * C::kLoSlabF4;            // [kStages][kUnits][kChunkF4]
     uint64_t *bars = reinterpret_cast<uint64_t *>(wbuf + kStages * C::kStageF4);
     const uint32_t bar0 = smem_u32(bars);
     // barrier map (8 bytes each)
@@ -245,7 +255,12 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
                 // the loads above are in flight while we wait for the slab to be released
                 mbar_wait_flag(xempty(slot), ((unit >> 1) & 1u) ^ 1u, a.err, (1u << 24) | (1u << 16) | (unit & 0xffffu));
                 float4 *dhi = xhi + slot * kSlabF4;
-                uint4 *dlo = xlo + slot * (kSlabF4 / 2);
+                uint4 *dlo = xlo + slot * C::kLoSlabF4;
+                constexpr int kLoRows = C::KC ? 2 : 1;       // 16-byte rows per K-chunk pair: lo (and bf16 of a)
+                auto hi8 = [](const float4 &p, const float4 &q) {
+                    return make_uint4(pack_bf16x2(p.x, p.y), pack_bf16x2(p.z, p.w), pack_bf16x2(q.x, q.y),
+                                      pack_bf16x2(q.z, q.w));
+                };
                 // lo = a - trunc_tf32(a) of 8 consecutive channels (K chunks 2pw, 2pw+1) -> one bf16 row
                 auto lo8 = [](const float4 &p, const float4 &q) {
                     return make_uint4(pack_bf16x2(tf32_lo(p.x), tf32_lo(p.y)), pack_bf16x2(tf32_lo(p.z), tf32_lo(p.w)),
@@ -254,12 +269,16 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
 #pragma unroll
                 for (int r = 0; r < 18; ++r) dhi[(2 * pw + r / 9) * kNPos + (r % 9) * kHW + lane] = v[r];
 #pragma unroll
-                for (int py = 0; py < 9; ++py) dlo[pw * kNPos + py * kHW + lane] = lo8(v[py], v[9 + py]);
+                for (int py = 0; py < 9; ++py) {
+                    dlo[pw * kLoRows * kNPos + py * kHW + lane] = lo8(v[py], v[9 + py]);
+                    if (C::KC) dlo[(pw * 2 + 1) * kNPos + py * kHW + lane] = hi8(v[py], v[9 + py]);
+                }
                 if (has_tail) {
                     const int pos = t_py * kHW + t_px;
                     dhi[t_kc[0] * kNPos + pos] = vt[0];
                     dhi[t_kc[1] * kNPos + pos] = vt[1];
-                    dlo[(t_kc[0] >> 1) * kNPos + pos] = lo8(vt[0], vt[1]);
+                    dlo[(t_kc[0] >> 1) * kLoRows * kNPos + pos] = lo8(vt[0], vt[1]);
+                    if (C::KC) dlo[((t_kc[0] >> 1) * 2 + 1) * kNPos + pos] = hi8(vt[0], vt[1]);
                 }
                 // generic-proxy stores -> visible to the tensor core's async-proxy reads
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -306,7 +325,9 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
             constexpr uint32_t idesc16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(COUT >> 3) << 17) |
                                          ((uint32_t)(128 >> 4) << 24);     // kind::f16: bf16 x bf16 -> f32
             const uint64_t a_lo0 = make_desc(smem_u32(xlo), kNPos * 16u, 128u);
-            const uint64_t b_00 = make_desc(smem_u32(wbuf), 2 * COUT * 16u, 128u);
+            constexpr uint32_t idescN = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(COUT >> 3) << 17) |
+                                        ((uint32_t)(128 >> 4) << 24);      // tf32, N = COUT (KC)
+            const uint64_t b_00 = make_desc(smem_u32(wbuf), (C::KC ? 1 : 2) * COUT * 16u, 128u);
             const uint64_t b16_00 = make_desc(smem_u32(wbuf + C::kChunkTf32F4), COUT * 16u, 128u);
             uint32_t cnt = 0, unit = 0, tcount = 0;
             long long tacc[5] = {0, 0, 0, 0, 0}, t0 = 0, tp = 0;
@@ -343,25 +364,27 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
                         const uint32_t shift = (uint32_t)(slot * kSlabF4 + dy * kHW + dx);
                         const uint64_t b_hi0 = b_00 + (uint32_t)(st * C::kStageF4 + ui * C::kChunkF4);
                         const uint64_t b16_0 = b16_00 + (uint32_t)(st * C::kStageF4 + ui * C::kChunkF4);
-                        const uint32_t shift16 = (uint32_t)(slot * (kSlabF4 / 2) + dy * kHW + dx);
+                        const uint32_t shift16 = (uint32_t)(slot * C::kLoSlabF4 + dy * kHW + dx);
                         {
                             const int mt = my_mt;
-                            const uint32_t dcol = dbase + (uint32_t)((gate_tap ? 4 * COUT : 0) + mt * 2 * COUT);
+                            const uint32_t dcol = dbase + (uint32_t)((gate_tap ? 2 * C::kAccCols : 0) + mt * C::kAccCols);
                             const uint32_t arow = shift + (uint32_t)mt * 128u;
 #pragma unroll
                             for (int kl = 0; kl < 4; ++kl) {
                                 const uint32_t aoff = (uint32_t)(2 * kl) * kNPos + arow;
-                                const uint32_t boff = (uint32_t)(2 * kl) * 2 * COUT;
+                                const uint32_t boff = (uint32_t)(2 * kl) * (C::KC ? 1 : 2) * COUT;
                                 // the first MMA into an accumulator region overwrites it: the main
                                 // region at the first 3x3 tap of K half 0, the gate region at the gate tap
                                 const uint32_t first = (part == 0 && kl == 0 && (gate_tap || ti == 0)) ? 0u : 1u;
                                 // cols [0,COUT) += a_hi b_hi, [COUT,2COUT) += a_hi b_lo
-                                mma_tf32_ss(dcol, a_hi0 + aoff, b_hi0 + boff, idesc2, first);
+                                // (KC: cols [0,COUT) += a_hi b_hi only)
+                                mma_tf32_ss(dcol, a_hi0 + aoff, b_hi0 + boff, C::KC ? idescN : idesc2, first);
                             }
                             // cols [0,COUT) += a_lo b in bf16, 16 input channels per instruction
+                            // (KC: += [a_lo | a] [b | b_lo], the two corrections of 8 input channels per instruction)
                             const uint32_t arow16 = shift16 + (uint32_t)mt * 128u;
 #pragma unroll
-                            for (int kl = 0; kl < 2; ++kl)
+                            for (int kl = 0; kl < (C::KC ? 4 : 2); ++kl)
                                 mma_bf16_ss(dcol, a_lo0 + (uint32_t)(2 * kl) * kNPos + arow16,
                                             b16_0 + (uint32_t)(2 * kl) * COUT, idesc16, 1u);
                         }
@@ -403,12 +426,12 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
             mbar_wait_flag(accfull(buf), (tcount / NACC) & 1u, a.err, (3u << 24) | (3u << 16) | (tcount & 0xffffu));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
-                                       (uint32_t)(buf * C::kColsBuf + mt * 2 * COUT);
+                                       (uint32_t)(buf * C::kColsBuf + mt * C::kAccCols);
 #pragma unroll 1
             for (int g = 0; g < NG; ++g) {
                 const int c0 = g * 32;
                 uint32_t acc[32];
-                {
+                if (!C::KC) {
                     uint32_t part[32];
                     tmem_ld32(lane_addr + (uint32_t)c0, acc);              // both loads in flight
                     tmem_ld32(lane_addr + (uint32_t)(COUT + c0), part);
@@ -416,16 +439,15 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(part[j]));
-                }
-                if (GATE) {
-                    uint32_t gt[32], part[32];
-                    tmem_ld32(lane_addr + (uint32_t)(4 * COUT + c0), gt);
-                    tmem_ld32(lane_addr + (uint32_t)(4 * COUT + COUT + c0), part);
+                } else {
+                    // KC (= gated): one accumulator per region; main and gate loads in flight together
+                    uint32_t gt[32];
+                    tmem_ld32(lane_addr + (uint32_t)c0, acc);
+                    tmem_ld32(lane_addr + (uint32_t)(2 * C::kAccCols + c0), gt);
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const float z = (__uint_as_float(gt[j]) + __uint_as_float(part[j])) +
-                                        __ldg(a.gate_bias + c0 + j);
+                        const float z = __uint_as_float(gt[j]) + __ldg(a.gate_bias + c0 + j);
                         acc[j] = __float_as_uint(__fdividef(__uint_as_float(acc[j]), 1.0f + __expf(-z)));
                     }
                 }
@@ -480,11 +502,12 @@ prepack_tc5_kernel(const float *__restrict__ w3, const float *__restrict__ w1,
 {
     const int KC = CIN / 4, NCH = CIN / 32;
     const int total = ntaps * KC * COUT;
+    const bool kc_layout = w1 != nullptr;       // the gated variant's chunk layout (Cfg::KC)
     for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
         const int co = i % COUT;
         const int kc = (i / COUT) % KC;
         const int tap = i / (COUT * KC);
-        float hi[4], lo[4];
+        float hi[4], lo[4], v_lo[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int ci = kc * 4 + j;
@@ -495,21 +518,32 @@ prepack_tc5_kernel(const float *__restrict__ w3, const float *__restrict__ w1,
             asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lbits) : "f"(rest));
             hi[j] = __uint_as_float(hbits);
             lo[j] = __uint_as_float(lbits);
+            v_lo[j] = rest;
         }
         const int part = kc / kKcSlab, kcl = kc % kKcSlab;
-        float4 *chunk = out + (int64_t)(tap * NCH + part) * (kKcSlab * 2 + 4) * COUT;
-        float4 *dst = chunk + kcl * 2 * COUT;
-        dst[co] = make_float4(hi[0], hi[1], hi[2], hi[3]);
-        dst[COUT + co] = make_float4(lo[0], lo[1], lo[2], lo[3]);
-        // bf16 copy of the weights for the a_lo term: row co of K chunk pair kcl/2, this half of its 16 bytes
-        uint2 *d16 = reinterpret_cast<uint2 *>(chunk + kKcSlab * 2 * COUT + (kcl >> 1) * COUT + co) + (kcl & 1);
         float wv[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int ci = kc * 4 + j;
             wv[j] = tap < 9 ? w3[((int64_t)co * CIN + ci) * 9 + tap] : w1[(int64_t)co * CIN + ci];
         }
-        *d16 = make_uint2(pack_bf16x2(wv[0], wv[1]), pack_bf16x2(wv[2], wv[3]));
+        const uint2 w16 = make_uint2(pack_bf16x2(wv[0], wv[1]), pack_bf16x2(wv[2], wv[3]));
+        if (!kc_layout) {
+            float4 *chunk = out + (int64_t)(tap * NCH + part) * (kKcSlab * 2 + 4) * COUT;
+            float4 *dst = chunk + kcl * 2 * COUT;
+            dst[co] = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            dst[COUT + co] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            // bf16 copy of the weights for the a_lo term: row co of K chunk pair kcl/2, this half of its 16 bytes
+            reinterpret_cast<uint2 *>(chunk + kKcSlab * 2 * COUT + (kcl >> 1) * COUT + co)[kcl & 1] = w16;
+        } else {
+            // gated variant: [kc][hi][co] float4, then [kc8][w | w_lo][co] 8 x bf16
+            float4 *chunk = out + (int64_t)(tap * NCH + part) * (kKcSlab + 8) * COUT;
+            chunk[kcl * COUT + co] = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            float4 *b16 = chunk + kKcSlab * COUT + (kcl >> 1) * 2 * COUT;
+            reinterpret_cast<uint2 *>(b16 + co)[kcl & 1] = w16;
+            reinterpret_cast<uint2 *>(b16 + COUT + co)[kcl & 1] =
+                make_uint2(pack_bf16x2(v_lo[0], v_lo[1]), pack_bf16x2(v_lo[2], v_lo[3]));
+        }
     }
 }
 
@@ -544,8 +578,9 @@ extern "C" int wm_conv3x3_debug_timing(void *device_buffer)
 extern "C" size_t wm_conv3x3_packed_bytes(int64_t Cin, int64_t Cout, int with_gate)
 {
     if (Cin <= 0 || Cout <= 0 || Cin % 32 || Cout % 8) return 0;
-    // per (tap, 32-channel K half): 16 * Cout float4 of tf32 hi | lo + 4 * Cout of bf16
-    return (size_t)(with_gate ? 10 : 9) * (Cin / 32) * 20 * Cout * sizeof(float4);
+    // per (tap, 32-channel K half): 16 * Cout float4 of tf32 hi | lo + 4 * Cout of bf16 (w);
+    // gated: 8 * Cout of tf32 hi + 8 * Cout of bf16 (w | w_lo)
+    return (size_t)(with_gate ? 10 * 16 : 9 * 20) * (Cin / 32) * Cout * sizeof(float4);
 }
 
 extern "C" int wm_conv3x3_prepack(const float *w3x3, const float *w1x1, void *packed, int64_t Cin,
