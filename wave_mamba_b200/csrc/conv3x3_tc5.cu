@@ -92,7 +92,9 @@ template <int CIN, int COUT, bool GATE>
 struct Cfg {
     static constexpr int NCH = CIN / 32;                       // K halves (slabs) per tile
     static constexpr int NTAPS = GATE ? 10 : 9;
-    static constexpr bool KC = GATE;                           // K-concatenated bf16 corrections (see the header)
+    // K-concatenated bf16 corrections (see the header): the variants whose merged accumulators do not fit
+    // TMEM twice -- the gated 64 -> 64 one and 32 -> 96
+    static constexpr bool KC = GATE || COUT >= 96;
     // weight chunk: merged [kc 0..7][hi | lo][COUT] float4 + [kc8 0..3][COUT] 8 x bf16 of w;
     //               KC     [kc 0..7][hi][COUT] float4      + [kc8 0..3][w | w_lo][COUT] 8 x bf16
     static constexpr int kChunkTf32F4 = KC ? kKcSlab * COUT : kKcSlab * 2 * COUT;
@@ -439,8 +441,8 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(part[j]));
-                } else {
-                    // KC (= gated): one accumulator per region; main and gate loads in flight together
+                } else if (GATE) {
+                    // KC, gated: one accumulator per region; main and gate loads in flight together
                     uint32_t gt[32];
                     tmem_ld32(lane_addr + (uint32_t)c0, acc);
                     tmem_ld32(lane_addr + (uint32_t)(2 * C::kAccCols + c0), gt);
@@ -450,6 +452,9 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
                         const float z = __uint_as_float(gt[j]) + __ldg(a.gate_bias + c0 + j);
                         acc[j] = __float_as_uint(__fdividef(__uint_as_float(acc[j]), 1.0f + __expf(-z)));
                     }
+                } else {
+                    tmem_ld32(lane_addr + (uint32_t)c0, acc);          // KC, plain: one accumulator
+                    tmem_ld_wait();
                 }
                 if (g == NG - 1) {
                     // every TMEM read of this warp is done: hand the accumulators back before the
@@ -498,11 +503,10 @@ conv3x3_tc5_kernel(const Args a, int tiles_x, int tiles_y, int total_tiles)
 // layout, so the weight producer moves a chunk with a single bulk copy.
 __global__ void __launch_bounds__(256)
 prepack_tc5_kernel(const float *__restrict__ w3, const float *__restrict__ w1,
-                   float4 *__restrict__ out, int CIN, int COUT, int ntaps)
+                   float4 *__restrict__ out, int CIN, int COUT, int ntaps, bool kc_layout)
 {
     const int KC = CIN / 4, NCH = CIN / 32;
-    const int total = ntaps * KC * COUT;
-    const bool kc_layout = w1 != nullptr;       // the gated variant's chunk layout (Cfg::KC)
+    const int total = ntaps * KC * COUT;        // kc_layout: the chunk layout of the Cfg::KC variants
     for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
         const int co = i % COUT;
         const int kc = (i / COUT) % KC;
@@ -536,7 +540,7 @@ prepack_tc5_kernel(const float *__restrict__ w3, const float *__restrict__ w1,
             // bf16 copy of the weights for the a_lo term: row co of K chunk pair kcl/2, this half of its 16 bytes
             reinterpret_cast<uint2 *>(chunk + kKcSlab * 2 * COUT + (kcl >> 1) * COUT + co)[kcl & 1] = w16;
         } else {
-            // gated variant: [kc][hi][co] float4, then [kc8][w | w_lo][co] 8 x bf16
+            // KC variants: [kc][hi][co] float4, then [kc8][w | w_lo][co] 8 x bf16
             float4 *chunk = out + (int64_t)(tap * NCH + part) * (kKcSlab + 8) * COUT;
             chunk[kcl * COUT + co] = make_float4(hi[0], hi[1], hi[2], hi[3]);
             float4 *b16 = chunk + kKcSlab * COUT + (kcl >> 1) * 2 * COUT;
@@ -579,8 +583,9 @@ extern "C" size_t wm_conv3x3_packed_bytes(int64_t Cin, int64_t Cout, int with_ga
 {
     if (Cin <= 0 || Cout <= 0 || Cin % 32 || Cout % 8) return 0;
     // per (tap, 32-channel K half): 16 * Cout float4 of tf32 hi | lo + 4 * Cout of bf16 (w);
-    // gated: 8 * Cout of tf32 hi + 8 * Cout of bf16 (w | w_lo)
-    return (size_t)(with_gate ? 10 * 16 : 9 * 20) * (Cin / 32) * Cout * sizeof(float4);
+    // gated and Cout >= 96 (Cfg::KC): 8 * Cout of tf32 hi + 8 * Cout of bf16 (w | w_lo)
+    const bool kc = with_gate || Cout >= 96;
+    return (size_t)(with_gate ? 10 : 9) * (kc ? 16 : 20) * (Cin / 32) * Cout * sizeof(float4);
 }
 
 extern "C" int wm_conv3x3_prepack(const float *w3x3, const float *w1x1, void *packed, int64_t Cin,
@@ -594,7 +599,7 @@ extern "C" int wm_conv3x3_prepack(const float *w3x3, const float *w1x1, void *pa
     const int ntaps = w1x1 ? 10 : 9;
     const int total = ntaps * (int)(Cin / 4) * (int)Cout;
     tc5::prepack_tc5_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-        w3x3, w1x1, static_cast<float4 *>(packed), (int)Cin, (int)Cout, ntaps);
+        w3x3, w1x1, static_cast<float4 *>(packed), (int)Cin, (int)Cout, ntaps, w1x1 != nullptr || Cout >= 96);
     WM_LAUNCH_OK("conv3x3 prepack");
     return WM_OK;
 }
