@@ -56,3 +56,8 @@ report("dwt L1", timeit(lambda: ops.dwt_haar(big)), 256, h, w)
 ipw = r(128, 32) * 0.2
 lw, lb = torch.ones(32, device=dev), torch.zeros(32, device=dev)
 report("lfss_z L1", timeit(lambda: ops.lfss_z(x, lw, lb, 1e-6, ipw)), 96, h, w)
+for rr in (2, 4, 8):
+    pw_, pb_ = r(32, 3 * rr * rr, 1, 1) * 0.2, r(32) * 0.1
+    ms = timeit(lambda: ops.ps_down(img, pw_, pb_, rr))
+    gb = (3 + 32.0 / (rr * rr)) * H * W * 4 / 1e9
+    print(f"{'ps_down r=%d 4K' % rr:28s} {ms:7.3f} ms  {gb / ms * 1e3:6.0f} GB/s  {gb / ms * 1e3 / PEAK * 100:5.1f} % of {PEAK:.0f}")

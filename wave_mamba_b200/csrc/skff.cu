@@ -153,77 +153,189 @@ skff_apply_kernel(const float *__restrict__ f0, const float *__restrict__ f1,
 }
 
 // ---------------------------------------------------------------------------------------------
-// PixelUnshuffle(R) + 1x1 conv 3R^2 -> 32 (+bias): thread = output pixel x 8 output channels
+// PixelUnshuffle(R) + 1x1 conv 3R^2 -> 32 (+bias).  Persistent CTAs walk tiles of 256 output pixels of
+// one output row; a step is G input row segments (ci, dy) of the tile, 256*R floats each (G = 2, 4, 6 for
+// R = 8, 4, 2: 384-512 FMAs per thread between barriers), loaded coalesced into registers one step ahead
+// (across tile boundaries) and parked in shared memory as [segment][dx quad][pixel],
+// so the compute threads read them conflict-free.  thread = 4 pixels (pg, pg+64, ...) x 8 output
+// channels: every broadcast weight quad feeds 16 FMAs (a broadcast LDS.128 returns 512 bytes to the warp,
+// DESIGN.md 4.3), the input is read once for all 32 outputs, and the weights are transposed once per CTA.
+// Round 2's first form (thread = pixel x 8 channels, one weight quad per FMA quad, x read by four channel
+// groups) sat at 0.10-0.12 ms per call at 4K whatever R: L1 tag-stage bound.
 // ---------------------------------------------------------------------------------------------
+constexpr int kPsTile = 256;                      // output pixels per tile
+
+// packed FMA (two fp32 FMAs per issue slot; a 3-register FFMA issues every other cycle)
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
+template <int R> struct PsCfg {
+    static constexpr int G = R == 8 ? 2 : R == 4 ? 4 : 6;                 // row segments per step
+    static constexpr int QN = R >= 4 ? R / 4 : 1;                         // float4 per pixel and row (R = 2: half a float4)
+    static constexpr int QPITCH = kPsTile + 4;                            // float4 pitch of a dx quad: the two quads of R = 8 land in different banks
+    static constexpr int SEG = R >= 4 ? QN * QPITCH : kPsTile / 2;        // float4 per parked segment
+    static constexpr int BUF = G * SEG;                                   // float4 per staging buffer
+    static constexpr size_t kSmem = sizeof(float) * (3 * R * R * 32 + 32) + sizeof(float4) * 2 * BUF;
+};
+
 template <int R>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 ps_down_kernel(const float *__restrict__ x, const float *__restrict__ wgt,
-               const float *__restrict__ bias, float *__restrict__ y, int H, int W)
+               const float *__restrict__ bias, float *__restrict__ y, int B, int H, int W)
 {
     // unshuffled channel index = ci * R*R + dy * R + dx   (torch.nn.PixelUnshuffle)
+    static_assert(kThreads == 256, "thread mapping");
     constexpr int CIN = 3 * R * R;
-    constexpr int COG = 8;                        // output channels per thread
-    extern __shared__ float ws[];                 // [CIN][32] transposed weights, then [32] bias
-    for (int i = threadIdx.x; i < 32 * CIN; i += kThreads) {
-        const int co = i / CIN, k = i - co * CIN;
-        ws[k * 32 + co] = __ldg(wgt + i);
+    using C = PsCfg<R>;
+    constexpr int G = C::G, QN = C::QN, QPITCH = C::QPITCH, SEG = C::SEG, BUF = C::BUF;
+    constexpr int STEPS = 3 * R / G;              // steps per tile
+    static_assert(STEPS * G == 3 * R, "G divides 3R");
+    constexpr int F4 = kPsTile * R / 4;           // float4 per row segment
+    constexpr int NLD = G * F4 / kThreads;        // float4 per thread and step: 4, 4, 3
+    static_assert(NLD * kThreads == G * F4, "whole loads");
+    extern __shared__ float4 ps_smem[];
+    float *ws = reinterpret_cast<float *>(ps_smem);           // [CIN][32] transposed weights, then [32] bias
+    float4 *stage = ps_smem + (CIN * 32 + 32) / 4;            // [2][BUF]
+    {
+        const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+        for (int k = wp; k < CIN; k += kThreads / 32) ws[k * 32 + lane] = __ldg(wgt + lane * CIN + k);
+        if (threadIdx.x < 32) ws[CIN * 32 + threadIdx.x] = bias ? __ldg(bias + threadIdx.x) : 0.0f;
     }
-    if (threadIdx.x < 32) ws[CIN * 32 + threadIdx.x] = bias ? __ldg(bias + threadIdx.x) : 0.0f;
-    __syncthreads();
     const int h = H / R, w = W / R;
+    const int tpr = (w + kPsTile - 1) / kPsTile;  // tiles per output row
     const int64_t hw = (int64_t)h * w, HW = (int64_t)H * W;
-    const int b = blockIdx.z;
-    const int cog = blockIdx.y;                   // 0..3: output channels 8*cog ..
-    const int64_t pix = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (pix >= hw) return;
-    const int oy = (int)(pix / w), ox = (int)(pix - (int64_t)oy * w);
-    float acc[COG];
+    const int64_t ntiles = (int64_t)B * h * tpr;
+    const int pg = threadIdx.x & 63, cog = threadIdx.x >> 6;  // a warp = 32 pixel groups of ONE channel group
+
+    float4 ld[NLD];
+    // the loads of step `st` of tile `t` (zeros past the row end / past the last tile)
+    auto fetch = [&](int64_t t, int st) {
 #pragma unroll
-    for (int j = 0; j < COG; ++j) acc[j] = ws[CIN * 32 + cog * COG + j];
-    const float *xb = x + (int64_t)b * 3 * HW + (int64_t)(oy * R) * W + ox * R;
+        for (int i = 0; i < NLD; ++i) ld[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t >= ntiles) return;
+        const int tx = (int)(t % tpr);
+        const int64_t rowi = t / tpr;
+        const int oy = (int)(rowi % h), b = (int)(rowi / h);
+        const int64_t col0 = (int64_t)tx * kPsTile * R;       // first input column of the segments
+#pragma unroll
+        for (int i = 0; i < NLD; ++i) {
+            const int kk = threadIdx.x + i * kThreads;
+            const int sg = st * G + kk / F4, k = kk % F4;     // segment (ci, dy), float4 inside it
+            const int ci = sg / R, dy = sg - ci * R;
+            const float *row = x + ((int64_t)b * 3 + ci) * HW + (int64_t)(oy * R + dy) * W + col0;
+            if (col0 + 4 * k < W) ld[i] = ld_stream4(row + 4 * k);
+        }
+    };
+    auto park = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < NLD; ++i) {
+            const int kk = threadIdx.x + i * kThreads;
+            const int g = kk / F4, k = kk % F4;
+            if (R >= 4) stage[buf * BUF + g * SEG + (k % QN) * QPITCH + k / QN] = ld[i];
+            else stage[buf * BUF + g * SEG + k] = ld[i];      // R = 2: the row as it is, a float2 per pixel
+        }
+    };
+
+    int64_t tile = blockIdx.x;
+    fetch(tile, 0);
+    park(0);
+    __syncthreads();
+    int buf = 0;
+    for (; tile < ntiles; tile += gridDim.x) {
+        f32x2 acc[4][4];                            // [pixel][channel pair]
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                acc[p][j] = pack2(ws[CIN * 32 + cog * 8 + 2 * j], ws[CIN * 32 + cog * 8 + 2 * j + 1]);
 #pragma unroll 1
-    for (int ci = 0; ci < 3; ++ci) {
+        for (int st = 0; st < STEPS; ++st) {
+            // next segment in flight during this one's FMAs
+            if (st + 1 < STEPS) fetch(tile, st + 1);
+            else fetch(tile + gridDim.x, 0);
 #pragma unroll
-        for (int dy = 0; dy < R; ++dy) {
-            const float *row = xb + ci * HW + (int64_t)dy * W;
-            float v[R];
-            if (R >= 4) {
+            for (int g = 0; g < G; ++g) {
+            const float4 *sb = stage + buf * BUF + g * SEG;
+            const float *wrow = ws + (st * G + g) * R * 32 + cog * 8;
 #pragma unroll
-                for (int q = 0; q < R / 4; ++q) {
-                    const float4 t = __ldg(reinterpret_cast<const float4 *>(row) + q);
-                    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+            for (int q = 0; q < QN; ++q) {
+                float v[4][4];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    if (R >= 4) {
+                        const float4 t = sb[q * QPITCH + pg + 64 * p];
+                        v[p][0] = t.x; v[p][1] = t.y; v[p][2] = t.z; v[p][3] = t.w;
+                    } else {
+                        const float2 t = reinterpret_cast<const float2 *>(sb)[pg + 64 * p];
+                        v[p][0] = t.x; v[p][1] = t.y; v[p][2] = 0.f; v[p][3] = 0.f;
+                    }
                 }
-            } else {
-                const float2 t = __ldg(reinterpret_cast<const float2 *>(row));
-                v[0] = t.x; v[1] = t.y;
-            }
 #pragma unroll
-            for (int dx = 0; dx < R; ++dx) {
-                const float *wr = ws + ((ci * R + dy) * R + dx) * 32 + cog * COG;
-                const float4 w0 = *reinterpret_cast<const float4 *>(wr);
-                const float4 w1 = *reinterpret_cast<const float4 *>(wr + 4);
-                acc[0] = fmaf(v[dx], w0.x, acc[0]); acc[1] = fmaf(v[dx], w0.y, acc[1]);
-                acc[2] = fmaf(v[dx], w0.z, acc[2]); acc[3] = fmaf(v[dx], w0.w, acc[3]);
-                acc[4] = fmaf(v[dx], w1.x, acc[4]); acc[5] = fmaf(v[dx], w1.y, acc[5]);
-                acc[6] = fmaf(v[dx], w1.z, acc[6]); acc[7] = fmaf(v[dx], w1.w, acc[7]);
+                for (int d = 0; d < (R >= 4 ? 4 : 2); ++d) {
+                    const ulonglong2 w0 = *reinterpret_cast<const ulonglong2 *>(wrow + (4 * q + d) * 32);
+                    const ulonglong2 w1 = *reinterpret_cast<const ulonglong2 *>(wrow + (4 * q + d) * 32 + 4);
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        const f32x2 t = pack2(v[p][d], v[p][d]);
+                        acc[p][0] = ffma2(t, w0.x, acc[p][0]); acc[p][1] = ffma2(t, w0.y, acc[p][1]);
+                        acc[p][2] = ffma2(t, w1.x, acc[p][2]); acc[p][3] = ffma2(t, w1.y, acc[p][3]);
+                    }
+                }
             }
+            }
+            park(buf ^ 1);          // read by the step before this one: every thread is past that barrier
+            __syncthreads();
+            buf ^= 1;
+        }
+        const int tx = (int)(tile % tpr);
+        const int64_t rowi = tile / tpr;
+        const int oy = (int)(rowi % h), b = (int)(rowi / h);
+        float *yo = y + ((int64_t)b * 32 + cog * 8) * hw + (int64_t)oy * w + tx * kPsTile;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int px = pg + 64 * p;
+            if (tx * kPsTile + px < w)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float lo, hi;
+                    unpack2(acc[p][j], lo, hi);
+                    yo[(int64_t)(2 * j) * hw + px] = lo;
+                    yo[(int64_t)(2 * j + 1) * hw + px] = hi;
+                }
         }
     }
-    float *yo = y + ((int64_t)b * 32 + cog * COG) * hw + pix;
-#pragma unroll
-    for (int j = 0; j < COG; ++j) yo[(int64_t)j * hw] = acc[j];
 }
 
 template <int R>
 int launch_ps_down(const float *x, const float *wgt, const float *bias, float *y, int64_t B,
                    int64_t H, int64_t W, cudaStream_t s)
 {
-    constexpr int CIN = 3 * R * R;
-    const size_t smem = sizeof(float) * (CIN * 32 + 32);
+    const size_t smem = PsCfg<R>::kSmem;
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        WM_CUDA_OK(cudaGetDevice(&dev));
+        WM_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
     WM_CUDA_OK(cudaFuncSetAttribute(ps_down_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t hw = (H / R) * (W / R);
-    dim3 grid((unsigned)((hw + kThreads - 1) / kThreads), 4, (unsigned)B);
-    ps_down_kernel<R><<<grid, kThreads, smem, s>>>(x, wgt, bias, y, (int)H, (int)W);
+    const int64_t tiles = B * (H / R) * ((W / R + kPsTile - 1) / kPsTile);
+    const int grid = (int)(tiles < 2 * sms ? tiles : 2 * sms);
+    ps_down_kernel<R><<<grid, kThreads, smem, s>>>(x, wgt, bias, y, (int)B, (int)H, (int)W);
     WM_LAUNCH_OK("ps_down");
     return WM_OK;
 }
