@@ -31,7 +31,7 @@ extern "C" {
 #define WM_ECUDA (-2)     /* a CUDA runtime call or kernel launch failed               */
 #define WM_ENODEVICE (-3) /* no sm_100-class CUDA device is current                     */
 
-#define WM_ABI_VERSION 14
+#define WM_ABI_VERSION 15
 
 typedef void *wm_stream_t;
 
@@ -304,6 +304,18 @@ int wm_img_u8_to_f32_fwd(const uint8_t *img, float *out, int64_t B, int64_t H, i
  * * 255).  Bit-exact with tensor2img. */
 int wm_img_f32_to_u8_fwd(const float *x, uint8_t *img, int64_t B, int64_t h, int64_t w, int64_t Hs,
                          int64_t Ws, wm_stream_t stream);
+
+/* ---- the two metrics the inference loop prints per image (inference_wavemamba.py:117-118) --------
+ * comput_psnr_ssim.py calculate_psnr :387-438 and calculate_ssim :596-668 with their defaults
+ * (input_order 'HWC', test_y_channel True): img1, img2 (B,H,W,3) uint8 BGR on the device, cropped by
+ * crop_border on every edge, Y channel per to_y_channel :374-385 / bgr2ycbcr :210-238, PSNR from the
+ * fp64 mean of the fp32 squared differences (+inf if 0), SSIM per _ssim_cly :559-592 (11x11 Gaussian
+ * sigma 1.5, replicate border, fp64).  out: (B,2) float64 = [psnr, ssim] per image.  Deterministic.
+ * workspace: wm_psnr_ssim_y_workspace_bytes(B,H,W,crop_border) bytes, 8-byte aligned. */
+size_t wm_psnr_ssim_y_workspace_bytes(int64_t B, int64_t H, int64_t W, int crop_border);
+int wm_psnr_ssim_y_u8(const uint8_t *img1, const uint8_t *img2, double *out, void *workspace,
+                      size_t workspace_bytes, int64_t B, int64_t H, int64_t W, int crop_border,
+                      wm_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -324,26 +324,71 @@ def to_uint8_bgr(t: torch.Tensor):
     return (img * 255.0).round().astype(np.uint8)
 
 
+def _y_channel(im: "np.ndarray") -> "np.ndarray":
+    """to_y_channel (comput_psnr_ssim.py:374-385) of a float64 BGR image in [0,255]: float32 in, fp64 dot
+    with the BT.601 BGR weights (bgr2ycbcr y_only, :210-238), back to float32 in [0,255]."""
+    import numpy as np
+    f = im.astype(np.float32) / 255.0
+    y = np.dot(f, [24.966, 128.553, 65.481]) + 16.0   # BGR order weights
+    y = (y / 255.0).astype(np.float32)                 # _convert_output_type_range(float32)
+    return y * 255.0                                   # to_y_channel: back to [0,255]
+
+
+def _crop_f64(img: "np.ndarray", crop_border: int) -> "np.ndarray":
+    import numpy as np
+    a = img.astype(np.float64)
+    if crop_border:
+        a = a[crop_border:-crop_border, crop_border:-crop_border]
+    return a
+
+
 def psnr_y(img: "np.ndarray", ref: "np.ndarray", crop_border: int = 1) -> float:
     """comput_psnr_ssim.py:387-438 with the inference defaults (crop 1, Y channel).
     Y from BGR uint8 per comput_psnr_ssim.py:210-238 (bgr2ycbcr y_only) / 374-385."""
     import numpy as np
-
-    def y_of(im):
-        f = im.astype(np.float32) / 255.0
-        y = np.dot(f, [24.966, 128.553, 65.481]) + 16.0   # BGR order weights
-        y = (y / 255.0).astype(np.float32)                 # _convert_output_type_range(float32)
-        return y * 255.0                                   # to_y_channel: back to [0,255]
-
-    a, b = img.astype(np.float64), ref.astype(np.float64)
-    if crop_border:
-        a = a[crop_border:-crop_border, crop_border:-crop_border]
-        b = b[crop_border:-crop_border, crop_border:-crop_border]
-    a, b = y_of(a), y_of(b)
+    a, b = _y_channel(_crop_f64(img, crop_border)), _y_channel(_crop_f64(ref, crop_border))
     mse = np.mean((a - b) ** 2)
     if mse == 0:
         return float("inf")
     return float(20.0 * math.log10(255.0 / math.sqrt(mse)))
+
+
+def gaussian_window_11() -> "np.ndarray":
+    """cv2.getGaussianKernel(11, 1.5) (comput_psnr_ssim.py:573): exp(-(i-5)^2 / (2 sigma^2)), normalised."""
+    import numpy as np
+    x = np.arange(11, dtype=np.float64) - 5.0
+    k = np.exp(-0.5 / (1.5 * 1.5) * x * x)
+    return k * (1.0 / k.sum())
+
+
+def ssim_y(img: "np.ndarray", ref: "np.ndarray", crop_border: int = 1) -> float:
+    """comput_psnr_ssim.py:596-668 with the inference defaults -> _ssim_cly :559-592: the 11x11 Gaussian
+    window correlated (cv2.filter2D, BORDER_REPLICATE, same size) with Y1, Y2, Y1^2, Y2^2, Y1*Y2 in fp64,
+    the SSIM map with C1 = (0.01*255)^2, C2 = (0.03*255)^2, its mean.  Plain numpy: the 2-D window is
+    applied tap by tap on an edge-padded copy."""
+    import numpy as np
+    a = _y_channel(_crop_f64(img, crop_border)).astype(np.float64)
+    b = _y_channel(_crop_f64(ref, crop_border)).astype(np.float64)
+    k = gaussian_window_11()
+    window = np.outer(k, k)
+
+    def filt(x):
+        h, w = x.shape
+        p = np.pad(x, 5, mode="edge")
+        out = np.zeros_like(x)
+        for i in range(11):
+            for j in range(11):
+                out += window[i, j] * p[i:i + h, j:j + w]
+        return out
+
+    c1, c2 = (0.01 * 255) ** 2, (0.03 * 255) ** 2
+    mu1, mu2 = filt(a), filt(b)
+    mu1_sq, mu2_sq, mu1_mu2 = mu1 ** 2, mu2 ** 2, mu1 * mu2
+    s1 = filt(a ** 2) - mu1_sq
+    s2 = filt(b ** 2) - mu2_sq
+    s12 = filt(a * b) - mu1_mu2
+    ssim_map = ((2 * mu1_mu2 + c1) * (2 * s12 + c2)) / ((mu1_sq + mu2_sq + c1) * (s1 + s2 + c2))
+    return float(ssim_map.mean())
 
 
 # --------------------------------------------------------------------------------------

@@ -59,6 +59,8 @@ def test_inference_script_runs_unmodified_on_the_plugin(tmp_path, dev, params_ca
     assert run.returncode == 0, run.stderr[-3000:]
     printed = [float(m) for m in re.findall(r"^psnr ([-0-9.einf]+)$", run.stdout, flags=re.M)]
     assert len(printed) == len(cases), run.stdout[-2000:]
+    printed_ssim = [float(m) for m in re.findall(r"^ssim ([-0-9.einf]+)$", run.stdout, flags=re.M)]
+    assert len(printed_ssim) == len(cases), run.stdout[-2000:]
     assert "avg_psnr" in run.stdout
 
     import wave_mamba_b200 as wm
@@ -66,7 +68,7 @@ def test_inference_script_runs_unmodified_on_the_plugin(tmp_path, dev, params_ca
     net = wm.WaveMamba(in_chn=3, wf=32, n_l_blocks=[1, 2, 4], n_h_blocks=[1, 1, 2], ffn_scale=2.0)
     net.load_state_dict(params, strict=True)
     net = net.to(dev).eval()
-    for (name, H, W, _), psnr_script in zip(cases, printed):
+    for (name, H, W, _), psnr_script, ssim_script in zip(cases, printed, printed_ssim):
         img = cv2.imread(str(low / name), cv2.IMREAD_UNCHANGED)
         gt_img = cv2.imread(str(high / name), cv2.IMREAD_UNCHANGED)
         written = cv2.imread(str(outd / name), cv2.IMREAD_UNCHANGED)
@@ -86,6 +88,10 @@ def test_inference_script_runs_unmodified_on_the_plugin(tmp_path, dev, params_ca
         print(f"{name}: script psnr {psnr_script:.5f} dB, oracle {psnr_oracle:.5f} dB, "
               f"differing bytes vs oracle {(yo != written).sum()} of {written.size}")
         assert abs(psnr_script - psnr_oracle) <= 1e-3
+        # the script's two host-side metric calls (:117-118), on the device (wm_psnr_ssim_y_u8)
+        psnr_dev, ssim_dev = wm.metrics.calculate_psnr_ssim(written, gt_img)
+        print(f"{name}: device psnr {psnr_dev:.6f} dB / ssim {ssim_dev:.9f}, script {psnr_script:.6f} / {ssim_script:.9f}")
+        assert abs(psnr_dev - psnr_script) <= 2e-5 and abs(ssim_dev - ssim_script) <= 1e-9
 
 
 @needs_ref

@@ -12,7 +12,7 @@ from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libwavemamba_b200.so")
 
-ABI_VERSION = 14
+ABI_VERSION = 15
 
 # name -> (restype, argtypes); mirrors include/wavemamba_b200.h one to one
 SIGNATURES = {
@@ -66,6 +66,8 @@ SIGNATURES = {
     "wm_layernorm2d_bwd": (c_int, [c_void_p] * 3 + [c_float] + [c_void_p] * 4 + [c_size_t] + [c_int64] * 4 + [c_void_p]),
     "wm_img_u8_to_f32_fwd": (c_int, [c_void_p] * 2 + [c_int64] * 5 + [c_int, c_void_p]),
     "wm_img_f32_to_u8_fwd": (c_int, [c_void_p] * 2 + [c_int64] * 5 + [c_void_p]),
+    "wm_psnr_ssim_y_workspace_bytes": (c_size_t, [c_int64] * 3 + [c_int]),
+    "wm_psnr_ssim_y_u8": (c_int, [c_void_p] * 4 + [c_size_t] + [c_int64] * 3 + [c_int, c_void_p]),
 }
 
 

@@ -23,7 +23,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 # per-file extras: the Haar kernels must not contract mul+add (bit-exact with the reference)
 EXTRA = {"haar.cu": ["-fmad=false"]}
-SOURCES = ["abi.cu", "haar.cu", "ss2d.cu", "ss2d_bwd.cu", "pointwise.cu", "pw_dw_tc5.cu", "spatial32.cu", "pixelwise.cu", "lfss_out_tma.cu", "pw_tma.cu", "gram.cu", "conv3x3_tc5.cu", "skff.cu", "imgio.cu", "train.cu"]
+SOURCES = ["abi.cu", "haar.cu", "ss2d.cu", "ss2d_bwd.cu", "pointwise.cu", "pw_dw_tc5.cu", "spatial32.cu", "pixelwise.cu", "lfss_out_tma.cu", "pw_tma.cu", "gram.cu", "conv3x3_tc5.cu", "skff.cu", "imgio.cu", "metrics.cu", "train.cu"]
 
 
 def _nvcc() -> str:

@@ -750,6 +750,36 @@ def img_f32_to_u8(x: torch.Tensor, h: Optional[int] = None, w: Optional[int] = N
     return img
 
 
+def psnr_ssim_y(img1: torch.Tensor, img2: torch.Tensor, crop_border: int = 1) -> torch.Tensor:
+    """PSNR and SSIM on the Y channel of two (B,H,W,3) uint8 BGR image batches on the device, as
+    comput_psnr_ssim.py calculate_psnr :387-438 / calculate_ssim :596-668 compute them with their
+    defaults.  Returns (B,2) float64 = [psnr, ssim] per image (psnr = +inf for identical Y planes)."""
+    for t, name in ((img1, "img1"), (img2, "img2")):
+        if not t.is_cuda:
+            raise _cabi.WaveMambaNativeError(f"{name}: the B200 path needs a CUDA tensor")
+        if t.dtype != torch.uint8 or t.dim() != 4 or t.shape[-1] != 3 or not t.is_contiguous():
+            raise ValueError(f"{name}: expected a contiguous (B,H,W,3) uint8 tensor, got {t.dtype} {tuple(t.shape)}")
+    if img1.shape != img2.shape:
+        raise ValueError(f"Image shapes are different: {tuple(img1.shape)}, {tuple(img2.shape)}")
+    if img1.device != img2.device:
+        raise ValueError("img1 and img2 live on different devices")
+    B, H, W, _ = img1.shape
+    crop_border = int(crop_border)
+    if crop_border < 0 or H - 2 * crop_border < 1 or W - 2 * crop_border < 1:
+        raise ValueError(f"crop_border={crop_border} leaves nothing of a {H}x{W} image")
+    out = torch.empty(B, 2, dtype=torch.float64, device=img1.device)
+    lib = _cabi.load()
+    nbytes = lib.wm_psnr_ssim_y_workspace_bytes(B, H, W, crop_border)
+    ws = torch.empty(max(nbytes // 8, 1), dtype=torch.float64, device=img1.device)
+    with torch.cuda.device(img1.device):
+        rc = lib.wm_psnr_ssim_y_u8(img1.data_ptr(), img2.data_ptr(), out.data_ptr(), ws.data_ptr(), nbytes,
+                                   B, H, W, crop_border, _stream(img1))
+    _cabi.check(rc, "wm_psnr_ssim_y_u8")
+    if B:
+        _count(2)
+    return out
+
+
 # --------------------------------------------------------------------------------------------
 # training-only kernels (csrc/train.cu)
 # --------------------------------------------------------------------------------------------
