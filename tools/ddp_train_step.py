@@ -2,9 +2,9 @@
 zero_grad -> net_g(lq) -> L1 -> backward -> AdamW step) on N GPUs under DistributedDataParallel, the
 wrap basicsr/models/base_model.py:111-114 applies.
 
-    torchrun --standalone --nnodes=1 --nproc-per-node N tools/ddp_train_step.py [--batch 8 --size 512 --steps 3]
+    torchrun --standalone --nnodes=1 --nproc-per-node N tools/ddp_train_step.py [--batch 8 --size 512 --steps 3 --act-storage bf16]
 
-fp32 (bf16 activation storage is not implemented).  Prints one JSON line on rank 0: step time (CUDA events,
+fp32 compute; --act-storage bf16 keeps the saved feature maps in bf16.  Prints one JSON line on rank 0: step time (CUDA events,
 max over ranks), images/s, and whether the ranks hold identical parameters after the steps (they start
 from the same checkpoint and see different data, so equality proves the gradient all-reduce ran)."""
 import argparse
@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--act-storage", choices=["fp32", "bf16"], default="fp32")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -42,6 +43,7 @@ def main():
     net = wm.WaveMamba(in_chn=3, wf=32, n_l_blocks=[1, 2, 4], n_h_blocks=[1, 1, 2], ffn_scale=2.0)
     net.load_state_dict(params, strict=True)
     net = net.to(dev).train()
+    net.restoration_network.activation_storage = args.act_storage
     model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local]) if world > 1 else net
     opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.0, betas=(0.9, 0.99))
     x, gt = synth_lowlight(args.batch, args.size, args.size, seed=100 + rank)     # a different shard per rank
@@ -79,6 +81,7 @@ def main():
         print(json.dumps({
             "what": "training step (fwd + bwd + AdamW), fp32, DDP" if world > 1 else "training step, fp32, 1 GPU",
             "n_gpus": world, "batch_per_gpu": args.batch, "size": args.size, "steps": args.steps,
+            "activation_storage": args.act_storage,
             "ms_per_step": float(ms.item()), "images_per_s": world * args.batch / (float(ms.item()) * 1e-3),
             "loss": float(loss), "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9,
             "ranks_hold_identical_parameters": same}))

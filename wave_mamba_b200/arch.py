@@ -24,6 +24,7 @@ There is no CPU path: tensors that are not on a CUDA device raise.
 from __future__ import annotations
 
 import math
+import os
 from typing import List, Sequence
 
 import torch
@@ -493,6 +494,19 @@ class upFRG(nn.Module):
         return self.iwt(x_l, x_h)  # IWT of cat([x_l, x_h]) without the cat (:1006)
 
 
+def _activation_storage(module):
+    """``module.activation_storage`` (None | torch.bfloat16 | "bf16"), else the environment variable
+    WM_ACT_STORAGE=bf16 -- the switch for the reference's unmodified basicsr/train.py."""
+    v = getattr(module, "activation_storage", None)
+    if v is None:
+        v = os.environ.get("WM_ACT_STORAGE") or None
+    if v is None or v in ("fp32", "float32", torch.float32):
+        return None
+    if v in ("bf16", "bfloat16", torch.bfloat16):
+        return torch.bfloat16
+    raise ValueError(f"activation_storage: expected None, 'fp32' or 'bf16', got {v!r}")
+
+
 class UNet(nn.Module):
     def __init__(self, in_chn=3, wf=48, n_l_blocks=(1, 1, 2), n_h_blocks=(1, 1, 1), ffn_scale=2):
         super().__init__()
@@ -533,6 +547,9 @@ class UNet(nn.Module):
         if x.dim() != 4 or x.shape[2] % 8 or x.shape[3] % 8:
             raise ValueError(f"input must be (B,C,H,W) with H and W multiples of 8, got {tuple(x.shape)}")
         if _wants_grad(self, x):
+            if _activation_storage(self) is torch.bfloat16:
+                with ag.bf16_activation_storage():
+                    return self.forward_train(x)
             return self.forward_train(x)
         with torch.no_grad():
             x = x.contiguous()

@@ -67,6 +67,40 @@ def pw_data(x: torch.Tensor, w2d: torch.Tensor, bias=None) -> torch.Tensor:
     return ops.pw(_c(x), _c(w2d), bias)
 
 
+# --------------------------------------------------------------------------------------------
+# bf16 activation storage: what autograd keeps for the backward pass is stored in bf16,
+# everything that is computed -- forward values, scan state, gradients, weights -- stays fp32.
+# --------------------------------------------------------------------------------------------
+_BF16_MIN_NUMEL = 1 << 16      # feature maps only: 32x32 matrices, norms, weights and indices stay as they are
+
+
+class _Bf16Saved:
+    __slots__ = ("t",)
+
+    def __init__(self, t):
+        self.t = t
+
+
+def _pack_bf16(t: torch.Tensor):
+    if (t.dtype == torch.float32 and t.is_cuda and t.numel() >= _BF16_MIN_NUMEL
+            and not isinstance(t, torch.nn.Parameter)):
+        return _Bf16Saved(t.to(torch.bfloat16))
+    return t
+
+
+def _unpack_bf16(v):
+    return v.t.to(torch.float32) if isinstance(v, _Bf16Saved) else v
+
+
+def bf16_activation_storage():
+    """Context manager for a training forward: every float32 feature map saved for backward (by the
+    Functions below and by torch's elementwise glue alike) is kept as bf16 and widened again when the
+    backward pass asks for it.  The forward result is unchanged bit for bit; gradients see activations
+    rounded to 8 bits of mantissa (relative 2^-9), i.e. they differ from the fp32-storage gradients at the
+    1e-2 level per element while pointing the same way (tests/test_train_gpu.py measures both)."""
+    return torch.autograd.graph.saved_tensors_hooks(_pack_bf16, _unpack_bf16)
+
+
 class PW(torch.autograd.Function):
     """y = conv1x1(x; w) + b."""
 
