@@ -115,12 +115,16 @@ struct StepIn {
     }
 };
 
-// ysp: &ys[first of my two output channels][position]; the second channel is kYS floats further
+// ysp: &ys[first of my two output channels][position]; the second channel is kYS floats further.
+// Lane l owns channels 2l and 2l+1 and kYS is odd, so "every lane its first channel" would put lanes l and
+// l + 16 on one bank (2-way conflict on both stores, 17 % of the replay pass's shared-memory wavefronts):
+// the upper half-warp stores its second channel first.
 template <bool FINAL>
 __device__ __forceinline__ void scan_step(const StepIn<FINAL> &in, float *ysp, f32x2 (&hst)[kCh][4],
                                           const f32x2 (&A2)[kCh][4], float (&sdt)[kCh],
                                           const float (&my_skip)[2], bool half)
 {
+    const bool swap = (threadIdx.x & 16) != 0;
     const f32x2 bb[4] = {pack2(in.b0.x, in.b0.y), pack2(in.b0.z, in.b0.w), pack2(in.b1.x, in.b1.y),
                          pack2(in.b1.z, in.b1.w)};
     f32x2 cc[4];
@@ -158,8 +162,10 @@ __device__ __forceinline__ void scan_step(const StepIn<FINAL> &in, float *ysp, f
     if (FINAL) {
         const float o0 = __shfl_xor_sync(0xffffffffu, half ? yv[0] : yv[2], 1);
         const float o1 = __shfl_xor_sync(0xffffffffu, half ? yv[1] : yv[3], 1);
-        ysp[0] = fmaf(my_skip[0], half ? uv[2] : uv[0], (half ? yv[2] : yv[0]) + o0);
-        ysp[kYS] = fmaf(my_skip[1], half ? uv[3] : uv[1], (half ? yv[3] : yv[1]) + o1);
+        const float r0 = fmaf(my_skip[0], half ? uv[2] : uv[0], (half ? yv[2] : yv[0]) + o0);
+        const float r1 = fmaf(my_skip[1], half ? uv[3] : uv[1], (half ? yv[3] : yv[1]) + o1);
+        ysp[swap ? kYS : 0] = swap ? r1 : r0;
+        ysp[swap ? 0 : kYS] = swap ? r0 : r1;
     }
 }
 

@@ -287,9 +287,14 @@ struct ChunkMap {
 __device__ __forceinline__ ChunkMap make_chunk_map(const Geom &g, const TileGeom &tg, float *xs)
 {
     ChunkMap cm;
+    // thread -> (16-byte chunk cidx of the 16 per channel row, channel d0 of 16; +16j in the copy loops).
+    // A quarter-warp covers 8 consecutive chunks of ONE channel (128 contiguous bytes: the cp.async / float4
+    // side), a warp 4 adjacent channels: with the odd ys pitch the scalar reads of store_tile then touch 32
+    // different banks (lanes on chunks c and c + 8 of one channel shared a bank).
     const int tid = threadIdx.x;
-    const int cidx = tid & 15;
-    cm.d0 = tid >> 4;
+    const int lane = tid & 31, wp = tid >> 5;
+    const int cidx = (lane & 7) + 8 * (wp & 1);
+    cm.d0 = 4 * (wp >> 1) + (lane >> 3);
     int p0;
     if (!tg.col) {
         // rows: a strand's kTP steps are kTP/4 chunks of 16 bytes
