@@ -225,3 +225,25 @@ def test_cuda_graph_replay_equals_eager_400x600_batch4(dev, params_cache):
     print(f"400x600 batch 4: eager {t_eager:.2f} ms, CUDA graph {t_graph:.2f} ms per step")
     with pytest.raises(ValueError):
         g(x0[:2])
+
+
+def test_enhance_pipeline_equals_enhance_bgr_u8(dev, params_cache):
+    """EnhancePipeline (uploads / downloads on side streams, two staging slots) returns, image by image,
+    the bytes of the one-stream enhance_bgr_u8 -- five different images through two slots, two shapes."""
+    import wave_mamba_b200 as wm
+    net = wm.WaveMamba(in_chn=3, wf=32, n_l_blocks=[1, 2, 4], n_h_blocks=[1, 1, 2], ffn_scale=2.0)
+    net.load_state_dict(params_cache("LOLv1"), strict=True)
+    net = net.to(dev).eval()
+    g = torch.Generator().manual_seed(9)
+    shapes = [(200, 304)] * 3 + [(136, 248)] * 2
+    imgs = [(torch.rand(h, w, 3, generator=g) * 60).to(torch.uint8).pin_memory() for h, w in shapes]
+    outs = [torch.empty_like(i).pin_memory() for i in imgs]
+    pipe = wm.EnhancePipeline(net, window=8)
+    events = [pipe.submit(i, o) for i, o in zip(imgs, outs)]
+    pipe.flush()
+    assert all(e.query() for e in events)
+    for i, o in zip(imgs, outs):
+        want = wm.enhance_bgr_u8(net, i, window=8, sync=True).cpu()
+        assert torch.equal(o, want)
+    with pytest.raises(ValueError):
+        pipe.submit(imgs[0].to(dev), outs[0])

@@ -55,3 +55,75 @@ def enhance_bgr_u8(net, img: torch.Tensor, window: int = 128, out: Optional[torc
     if sync:
         torch.cuda.current_stream(img.device).synchronize()
     return res
+
+
+class EnhancePipeline:
+    """The same per-image body for a stream of images (the reference loop walks a folder,
+    inference_wavemamba.py:92-131): the upload of image i+1 and the download of result i-1 run on their own
+    CUDA streams while image i is in the network -- the side-stream protocol of the reference's
+    ``CUDAPrefetcher`` (basicsr/data/prefetch_dataloader.py:101-118) applied to both PCIe directions.
+
+        pipe = EnhancePipeline(net, window=128)
+        for img, out in zip(pinned_inputs, pinned_outputs):
+            done = pipe.submit(img, out)          # returns at once; ``done`` is a CUDA event
+        pipe.flush()                              # every ``out`` is complete
+
+    ``img`` / ``out``: (H,W,3) uint8 BGR host tensors, pinned for the copies to be asynchronous.  ``img`` may
+    be reused by the caller once the event returned ``depth`` submits later has fired (or after ``flush``);
+    results are bit-identical to ``enhance_bgr_u8``.  Device staging buffers are kept per slot."""
+
+    def __init__(self, net, window: int = 128, cuda_division: bool = False,
+                 device: Optional[torch.device] = None, depth: int = 2):
+        self.fwd = getattr(net, "restoration_network", net)
+        self.device = torch.device(device) if device is not None else next(net.parameters()).device
+        if self.device.type != "cuda":
+            raise ops._cabi.WaveMambaNativeError("EnhancePipeline: the network must live on a CUDA device")
+        self.window, self.cuda_division, self.depth = int(window), bool(cuda_division), max(int(depth), 2)
+        self.h2d = torch.cuda.Stream(self.device)
+        self.d2h = torch.cuda.Stream(self.device)
+        self._in = [None] * self.depth          # device uint8 staging, one per slot
+        self._in_free = [None] * self.depth     # fired when the network no longer reads the staging buffer
+        self._done = [None] * self.depth        # fired when the slot's result has reached the host
+        self._n = 0
+
+    @torch.no_grad()
+    def submit(self, img: torch.Tensor, out: torch.Tensor) -> torch.cuda.Event:
+        if img.dtype != torch.uint8 or img.dim() != 3 or img.shape[-1] != 3 or img.is_cuda:
+            raise ValueError(f"img: expected a (H,W,3) uint8 host tensor, got {tuple(img.shape)} {img.dtype} on {img.device}")
+        if out.shape != img.shape or out.dtype != torch.uint8 or out.is_cuda:
+            raise ValueError("out: expected a host uint8 tensor of the input's shape")
+        slot = self._n % self.depth
+        self._n += 1
+        H, W, _ = img.shape
+        with torch.cuda.device(self.device):
+            cur = torch.cuda.current_stream(self.device)
+            if self._in[slot] is None or self._in[slot].shape != (1, H, W, 3):
+                self._in[slot] = torch.empty(1, H, W, 3, dtype=torch.uint8, device=self.device)
+                self.h2d.wait_stream(cur)                       # the allocation belongs to the current stream
+            with torch.cuda.stream(self.h2d):
+                if self._in_free[slot] is not None:
+                    self.h2d.wait_event(self._in_free[slot])    # the previous user of this slot has been converted
+                self._in[slot][0].copy_(img, non_blocking=True)
+                up = self.h2d.record_event()
+            cur.wait_event(up)
+            x = ops.img_u8_to_f32(self._in[slot], self.window, self.cuda_division)
+            self._in_free[slot] = cur.record_event()
+            res = ops.img_f32_to_u8(self.fwd(x), H, W)[0]
+            ready = cur.record_event()
+            res.record_stream(self.d2h)
+            with torch.cuda.stream(self.d2h):
+                self.d2h.wait_event(ready)
+                out.copy_(res, non_blocking=True)
+                self._done[slot] = self.d2h.record_event()
+        return self._done[slot]
+
+    def flush(self, block: bool = True) -> None:
+        """Make the current stream wait for every pending download; ``block`` also waits on the host."""
+        cur = torch.cuda.current_stream(self.device)
+        for ev in self._done:
+            if ev is not None:
+                cur.wait_event(ev)
+        if block:
+            for ev in self._done:
+                if ev is not None:
+                    ev.synchronize()
