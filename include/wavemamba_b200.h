@@ -71,8 +71,9 @@ int wm_iwt_haar_fwd(const float *low, int64_t low_bstride, const float *high,
  * workspace: >= wm_ss2d_core_workspace_bytes(B,h,w) bytes, 256-byte aligned.
  * Fixed model constants: d_inner 64, d_state 16, dt_rank 2, 4 directions. */
 size_t wm_ss2d_core_workspace_bytes(int64_t B, int64_t h, int64_t w);
-/* Developer aid: non-NULL device buffer of 4096*6 int64 -> every pass kernel CTA writes its phase
- * cycle sums [wait-x, projection, delta, scan, store, tiles] at index blockIdx.x % 4096. */
+/* Developer aid: non-NULL device buffer of 8192*6 int64 -> every pass kernel CTA writes its phase
+ * cycle sums [wait-x, projection, delta, scan, store, tiles] at row blockIdx.x % 4096 (the output pass)
+ * or 4096 + blockIdx.x % 4096 (pass 1). */
 int wm_ss2d_debug_timing(void *device_buffer);
 /* Developer aid: the chunk plan chosen for (B,h,w): out6 = {row chunk steps, row CTAs per
  * direction, column segment steps, segments per column, column CTAs per direction, columns first}. */

@@ -23,15 +23,19 @@ for h, w in sizes:
     ms = e0.elapsed_time(e1) / 5
     geo = (ctypes.c_int * 6)()
     lib.wm_ss2d_debug_geometry(1, h, w, geo)
-    dbg = torch.zeros(4096 * 6, dtype=torch.int64, device=dev)
+    dbg = torch.zeros(8192 * 6, dtype=torch.int64, device=dev)
     lib.wm_ss2d_debug_timing(dbg.data_ptr())
     ops.ss2d_dirs(x, *prm); torch.cuda.synchronize()     # pass 2 is the last writer
     lib.wm_ss2d_debug_timing(None)
-    d = dbg.view(4096, 6).double()
+    d1 = dbg.view(8192, 6)[4096:].double()
+    d1 = d1[d1[:, 5] > 0]
+    pass1 = (d1[:, :5].sum(0) / d1[:, 5].sum()).tolist()
+    d = dbg.view(8192, 6)[:4096].double()
     d = d[d[:, 5] > 0]
     per_tile = (d[:, :5].sum(0) / d[:, 5].sum()).tolist()
     upd = h * w * 4096 * 2
     print(f"{h}x{w}: dirs call {ms:.3f} ms ({upd / ms / 1e6 / (148 * 16 * 1.965):.1%} of the MUFU roofline, two passes) "
           f"plan row_T={geo[0]} row_ctas={geo[1]} col_seg={geo[2]}x{geo[3]} col_ctas={geo[4]} cols_first={geo[5]} | "
           f"pass-2 cycles per tile per CTA:", dict(zip(["wait_x", "projection", "delta", "scan", "store"], [int(v) for v in per_tile])),
-          "sum", int(sum(per_tile)))
+          "sum", int(sum(per_tile)), "| pass 1:", dict(zip(["wait_x", "projection", "delta", "scan"], [int(v) for v in pass1[:4]])),
+          "sum", int(sum(pass1[:4])))

@@ -447,7 +447,7 @@ __device__ __forceinline__ void run_cta(const Params &prm, const Geom &g, const 
     if (dump && tid == 0) bulk_wait_read();        // shared memory must outlive the last store's read
 #undef WM_TICK
     if (timed) {
-        long long *o = prm.dbg + (blockIdx.x & 4095) * 6;
+        long long *o = prm.dbg + ((blockIdx.x & 4095) + (FINAL ? 0 : 4096)) * 6;   // pass 1 -> second half
         for (int i = 0; i < 5; ++i) o[i] = tacc[i];
         o[5] = ntiles;
     }
