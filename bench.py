@@ -481,6 +481,25 @@ def main():
             e4.record()
             barrier()
             ms_root = max_over_ranks(s4.elapsed_time(e4))
+            # the same batches through parallel.ShardedEnhancePipeline: upload + scatter of batch i+1 and
+            # gather + download of batch i-1 on side streams / their own NCCL communicators
+            spipe = parallel.ShardedEnhancePipeline(net, dev, window=8)
+            bshape = (world,) + tuple(img_host.shape)
+            out_b2 = torch.empty_like(out_batch).pin_memory() if rank == 0 else None
+            for i in range(2):
+                spipe.submit(batch_host, out_batch if i % 2 == 0 else out_b2, bshape)
+            spipe.flush()
+            barrier()
+            s5, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s5.record()
+            for i in range(args.steps):
+                spipe.submit(batch_host, out_batch if i % 2 == 0 else out_b2, bshape)
+            spipe.flush(block=False)
+            e5.record()
+            barrier()
+            ms_root_pipe = max_over_ranks(s5.elapsed_time(e5))
+            if rank == 0 and not (torch.equal(out_batch, out_b2) and torch.equal(out_batch[0], out_host)):
+                raise RuntimeError("ShardedEnhancePipeline result differs from enhance_bgr_u8")
             if rank == 0:
                 torch.cuda.synchronize()
                 coll = {k: round(sum(a.elapsed_time(b) for a, b in v) / args.steps, 4)
@@ -492,7 +511,11 @@ def main():
                     "collectives": "ncclScatter of uint8 inputs + ncclGather of uint8 outputs "
                                    "(torch.distributed scatter/gather, NCCL over NVLink)",
                     "rank0_ms_per_step": coll,
-                    "api": "wave_mamba_b200.parallel.sharded_enhance_u8(net, pinned uint8 batch on rank 0)"}
+                    "api": "wave_mamba_b200.parallel.sharded_enhance_u8(net, pinned uint8 batch on rank 0)",
+                    "pipelined": {"value": world * args.steps / (ms_root_pipe * 1e-3), "unit": UNIT,
+                                  "ms_per_step": ms_root_pipe / args.steps,
+                                  "api": "wave_mamba_b200.parallel.ShardedEnhancePipeline: the same copies and "
+                                         "collectives per step, those of neighbouring batches on side streams"}}
         clk = clocks.stop() if rank == 0 else None
     checksum = float(y_host.double().mean())
 

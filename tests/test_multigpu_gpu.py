@@ -27,6 +27,7 @@ def test_sharded_enhance_matches_single_gpu():
     run = _torchrun("sharded_check.py", "--batch", "3", "--size", "128", port=29531)
     assert run.returncode == 0, run.stdout[-1500:] + run.stderr[-1500:]
     assert "identical to the single-GPU result" in run.stdout
+    assert "identical to the single-GPU results (pipelined)" in run.stdout
 
 
 @two_gpus

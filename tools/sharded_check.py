@@ -46,6 +46,21 @@ def main():
         ok = torch.equal(res, alone)
         print(f"sharded_enhance_u8 over {dist.get_world_size()} ranks, batch {args.batch}: "
               f"{'identical to' if ok else 'DIFFERS from'} the single-GPU result")
+    # the same edge path as a pipeline: three different batches through two staging slots
+    shape = (args.batch, args.size, args.size + 64, 3)
+    batches, outs = [None] * 3, [None] * 3
+    if rank == 0:
+        batches = [f32_to_u8_bgr(synth_lowlight(args.batch, args.size, args.size + 64, seed=20 + i)[0]).pin_memory()
+                   for i in range(3)]
+        outs = [torch.empty_like(b).pin_memory() for b in batches]
+    pipe = parallel.ShardedEnhancePipeline(net, dev, window=8)
+    for b, o in zip(batches, outs):
+        pipe.submit(b, o, shape)
+    pipe.flush()
+    if rank == 0:
+        ok2 = all(torch.equal(o, wm.enhance_bgr_u8(net, b, window=8).cpu()) for b, o in zip(batches, outs))
+        print(f"ShardedEnhancePipeline, 3 batches: {'identical to' if ok2 else 'DIFFERS from'} the single-GPU results (pipelined)")
+        ok = ok and ok2
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 

@@ -146,3 +146,114 @@ def sharded_enhance_u8(net, batch: Optional[torch.Tensor], device: torch.device,
         out.copy_(res, non_blocking=True)
         return out
     return res
+
+
+class ShardedEnhancePipeline:
+    """``sharded_enhance_u8`` for a stream of batches (BASELINE configs[3]: every batch of B uint8 images is
+    held by rank ``src``): the upload + NCCL scatter of batch i+1 and the NCCL gather + download of batch i-1
+    run on side streams -- and on two separate NCCL communicators, so that a scatter never queues behind the
+    gather that waits for the forward -- while batch i is in the network.  Collective by construction: every
+    rank calls ``submit`` / ``flush`` the same number of times.
+
+        pipe = ShardedEnhancePipeline(net, device, window=128)
+        for batch, out in batches:              # pinned (B,H,W,3) uint8 on rank src, None elsewhere
+            pipe.submit(batch, out, shape=(B, H, W, 3))
+        pipe.flush()                            # every ``out`` on rank src is complete
+    """
+
+    def __init__(self, net, device: torch.device, window: int = 128, src: int = 0, depth: int = 2):
+        if not dist.is_initialized():
+            raise RuntimeError("ShardedEnhancePipeline needs an initialised torch.distributed process group")
+        self.net, self.device, self.window, self.src = net, torch.device(device), int(window), int(src)
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.depth = max(int(depth), 2)
+        self.pg_up = dist.new_group(backend=dist.get_backend())        # scatter
+        self.pg_down = dist.new_group(backend=dist.get_backend())      # gather
+        self.up = torch.cuda.Stream(self.device)
+        self.down = torch.cuda.Stream(self.device)
+        self._stage = [None] * self.depth       # src: the whole batch on the device; others: this rank's slice
+        self._result = [None] * self.depth      # src: gathered results
+        self._stage_free = [None] * self.depth
+        self._done = [None] * self.depth
+        self._n = 0
+
+    @torch.no_grad()
+    def submit(self, batch: Optional[torch.Tensor], out: Optional[torch.Tensor], shape) -> None:
+        from .imageio import enhance_bgr_u8
+        B = int(shape[0])
+        rest = tuple(int(v) for v in shape[1:])
+        slot = self._n % self.depth
+        self._n += 1
+        begin, end = shard_range(B, self.rank, self.world)
+        is_src = self.rank == self.src
+        want = (B,) + rest if is_src else (end - begin,) + rest
+        with torch.cuda.device(self.device):
+            cur = torch.cuda.current_stream(self.device)
+            if self._stage[slot] is None or tuple(self._stage[slot].shape) != want:
+                self._stage[slot] = torch.empty(want, dtype=torch.uint8, device=self.device)
+                if is_src:
+                    self._result[slot] = torch.empty(want, dtype=torch.uint8, device=self.device)
+                self.up.wait_stream(cur)
+                self.down.wait_stream(cur)
+            stage = self._stage[slot]
+            # ---- upload + scatter on the `up` stream ---------------------------------------------------
+            with torch.cuda.stream(self.up):
+                if self._stage_free[slot] is not None:
+                    self.up.wait_event(self._stage_free[slot])
+                if is_src:
+                    if batch is None or tuple(batch.shape) != want or batch.dtype != torch.uint8:
+                        raise ValueError(f"rank {self.src} must pass the (B,H,W,3) uint8 batch")
+                    stage.copy_(batch, non_blocking=True)
+                    sends = []
+                    for r in range(self.world):
+                        b0, b1 = shard_range(B, r, self.world)
+                        if r != self.src and b1 > b0:
+                            sends.append(dist.P2POp(dist.isend, stage[b0:b1], r, group=self.pg_up))
+                    reqs = _exchange(sends)
+                else:
+                    reqs = _exchange([dist.P2POp(dist.irecv, stage, self.src, group=self.pg_up)] if end > begin else [])
+                for q in reqs:
+                    q.wait()
+                arrived = self.up.record_event()
+            # ---- this rank's shard on the current stream ------------------------------------------------
+            cur.wait_event(arrived)
+            mine = stage[begin:end] if is_src else stage
+            res = enhance_bgr_u8(self.net, mine, window=self.window) if end > begin else mine
+            ready = cur.record_event()
+            # the staging buffer is free once the forward has consumed it AND (on src) the sends have left
+            self._stage_free[slot] = ready
+            res.record_stream(self.down)
+            # ---- gather + download on the `down` stream -------------------------------------------------
+            with torch.cuda.stream(self.down):
+                self.down.wait_event(ready)
+                if self._done[slot] is not None:
+                    self.down.wait_event(self._done[slot])
+                if is_src:
+                    result = self._result[slot]
+                    recvs = []
+                    for r in range(self.world):
+                        b0, b1 = shard_range(B, r, self.world)
+                        if r != self.src and b1 > b0:
+                            recvs.append(dist.P2POp(dist.irecv, result[b0:b1], r, group=self.pg_down))
+                    reqs = _exchange(recvs)
+                    result[begin:end].copy_(res)
+                    for q in reqs:
+                        q.wait()
+                    if out is not None:
+                        out.copy_(result, non_blocking=True)
+                else:
+                    reqs = _exchange([dist.P2POp(dist.isend, res.contiguous(), self.src, group=self.pg_down)]
+                                     if end > begin else [])
+                    for q in reqs:
+                        q.wait()
+                self._done[slot] = self.down.record_event()
+
+    def flush(self, block: bool = True) -> None:
+        cur = torch.cuda.current_stream(self.device)
+        for ev in self._done:
+            if ev is not None:
+                cur.wait_event(ev)
+        if block:
+            for ev in self._done:
+                if ev is not None:
+                    ev.synchronize()
