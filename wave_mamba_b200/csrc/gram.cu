@@ -44,6 +44,32 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
 }
 
 constexpr int kFlushTiles = 8;       // fp32 accumulators are folded into fp64 every 8 tiles
+// The CTAs of a thread-block cluster add their 1088 partial outputs through distributed shared memory (fixed
+// rank order) and only rank 0 writes them: the one-CTA reduce / tail kernel that follows is bound by how fast
+// a single SM can pull the partials (148 x 8.7 KB took ~24 us per call, 24 calls per image), so every halving
+// of the partial count helps.  Pairs pack onto any SM count; clusters of 4 do not (37 of them need a second wave
+// on 148 SMs: match_index 1.03 -> 1.60 ms per image).
+constexpr int kCluster = 2;
+
+__device__ __forceinline__ uint32_t cluster_rank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ double ld_dsmem_f64(const double *p, uint32_t rank)
+{
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    uint32_t ra;
+    double v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+    asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra) : "memory");
+    return v;
+}
 constexpr size_t kSmemBytes = sizeof(double) * 8 * kC * kC;   // 64 KB: cross-warp reduction buffer
 static_assert(kSmemBytes >= sizeof(float) * 2 * kC * kRS, "staging tiles must fit the reduction buffer");
 
@@ -53,7 +79,7 @@ static_assert(kSmemBytes >= sizeof(float) * 2 * kC * kRS, "staging tiles must fi
 // 3xTF32 split on both operands (2 x 4 fragment tiles = the whole 32x32 output, fp32 accumulate),
 // folds its accumulators into fp64 every 8 tiles (= 128 pixels per warp, as the tile sums of the
 // fp32 version), and the eight warps are summed in a fixed order at the end.
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
 gram_partial_kernel(const float *__restrict__ x, int64_t x_bstride, const float *__restrict__ y,
                     int64_t y_bstride, double *__restrict__ partial, int64_t hw, int chunk,
                     int nchunks, int vec)
@@ -172,15 +198,19 @@ gram_partial_kernel(const float *__restrict__ x, int64_t x_bstride, const float 
                 red[warp * kC * kC + row * kC + col] = g64[mt][nt][i];
             }
     __syncthreads();
-    double *out = partial + ((int64_t)b * nchunks + blockIdx.x) * kOut;
+    double tsum[kC * kC / kThreads];
 #pragma unroll
     for (int j = 0; j < kC * kC / kThreads; ++j) {
         const int o = tid + j * kThreads;
         double t = 0.0;
 #pragma unroll
         for (int w = 0; w < kThreads / 32; ++w) t += red[w * kC * kC + o];
-        out[o] = t;
+        tsum[j] = t;
     }
+    __syncthreads();                                           // red is dead: its head becomes this CTA's 1088 outputs
+    double *mine = red;
+#pragma unroll
+    for (int j = 0; j < kC * kC / kThreads; ++j) mine[tid + j * kThreads] = tsum[j];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         double sx = nx[r], sy = ny[r];
@@ -190,10 +220,22 @@ gram_partial_kernel(const float *__restrict__ x, int64_t x_bstride, const float 
             sy += __shfl_xor_sync(0xffffffffu, sy, off);
         }
         if (lane == 0) {
-            out[kC * kC + warp + 8 * r] = sx;
-            out[kC * kC + kC + warp + 8 * r] = sy;
+            mine[kC * kC + warp + 8 * r] = sx;
+            mine[kC * kC + kC + warp + 8 * r] = sy;
         }
     }
+    // ---- fixed-order sum over the CTAs of the cluster, written by rank 0 ------------------------
+    cluster_sync();
+    if (cluster_rank() == 0) {
+        double *out = partial + ((int64_t)b * (nchunks / kCluster) + blockIdx.x / kCluster) * kOut;
+        for (int o = tid; o < kOut; o += kThreads) {
+            double t = mine[o];
+#pragma unroll
+            for (int r = 1; r < kCluster; ++r) t += ld_dsmem_f64(mine + o, (uint32_t)r);
+            out[o] = t;
+        }
+    }
+    cluster_sync();                                            // the peers' shared memory outlives rank 0's reads
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -227,7 +269,7 @@ gram_reduce_tail_kernel(const double *__restrict__ partial, float *__restrict__ 
     __shared__ float attn[kC * kC];
     const int64_t b = blockIdx.x;
     const int tid = threadIdx.x;
-    // one CTA per image sums the 148 x 1088 partials: thread = output, consecutive lanes = consecutive
+    // one CTA per image sums the 74 x 1088 partials (one row per CTA pair of the partial kernel): thread = output, consecutive lanes = consecutive
     // outputs (coalesced 256-byte loads; a warp per output with lanes over the chunks touches one 32-byte
     // sector per lane and took ~90 us), chunks in order => deterministic and equal to gram_reduce_kernel
     for (int i = tid; i < kOut; i += kTailThreads) {
@@ -294,6 +336,7 @@ inline void plan(int64_t hw, int &chunk, int &nchunks)
     if (c < kTile) c = kTile;
     chunk = (int)c;
     nchunks = (int)((hw + c - 1) / c);
+    nchunks = (nchunks + kCluster - 1) / kCluster * kCluster;     // whole clusters (a CTA past the end adds zeros)
 }
 
 }  // namespace gram
@@ -340,13 +383,14 @@ static int gram_launch(const char *who, int mode, const float *x, int64_t x_bstr
                                                   nchunks, vec);
     WM_LAUNCH_OK("gram partial");
     const double *part = static_cast<const double *>(workspace);
+    const int nparts = nchunks / kCluster;                      // one row of partials per cluster
     if (mode == 0) {
         dim3 rgrid((kOut + kThreads - 1) / kThreads, (unsigned)B);
-        gram_reduce_kernel<<<rgrid, kThreads, 0, s>>>(part, out, nchunks);
+        gram_reduce_kernel<<<rgrid, kThreads, 0, s>>>(part, out, nparts);
     } else if (mode == 1) {
-        gram_reduce_tail_kernel<1><<<(unsigned)B, kTailThreads, 0, s>>>(part, out, nchunks, idx_out, nullptr, nullptr, nullptr);
+        gram_reduce_tail_kernel<1><<<(unsigned)B, kTailThreads, 0, s>>>(part, out, nparts, idx_out, nullptr, nullptr, nullptr);
     } else {
-        gram_reduce_tail_kernel<2><<<(unsigned)B, kTailThreads, 0, s>>>(part, out, nchunks, nullptr, temperature, w_po, mixed_out);
+        gram_reduce_tail_kernel<2><<<(unsigned)B, kTailThreads, 0, s>>>(part, out, nparts, nullptr, temperature, w_po, mixed_out);
     }
     WM_LAUNCH_OK("gram reduce");
     return WM_OK;
