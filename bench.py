@@ -411,6 +411,8 @@ def main():
         ms_dev = max_over_ranks(s.elapsed_time(e))
         # ---- per-kernel table: the same K steps again with CUDA events around every op (kept out
         # of the timed region above: ~900 event records per step cost about 1 %) -----------------
+        fwd(x_dev)      # un-instrumented: the device is still busy when the host starts the instrumented steps
+                        # (after a sync the first op's event pair would also span the host's launch latency)
         timer.enabled = True
         for _ in range(args.steps):
             y = fwd(x_dev)
