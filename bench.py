@@ -543,13 +543,13 @@ def main():
                             "tiles (43 KB per 64 positions), pass 2 reads them back instead of recomputing "
                             "the projection + softplus, and writes four direction planes that lfss_out sums; "
                             "bytes are spent on idle bandwidth to buy back instructions of a MUFU-bound kernel "
-                            "(round 1: 6.6 GB traffic, 26.4 ms; now 15.7 GB, 22.4 ms)",
+                            "(round 1: 6.6 GB traffic, 26.4 ms; now 15.7 GB, 21.9 ms)",
             "peak_source": peak_src,
             "bytes_definition": "512*B*L per call (x read once + merged y written once), SURVEY 8d",
             "ms_per_image": round(ss["ms_total"] / args.steps, 4),
             "scan_operand_bytes_frac": round(ss["frac_of_hbm_peak"] * 7.0, 4),
             "note": "MUFU-bound (one ex2 per state update, evaluated in both passes), not HBM-bound: the "
-                    "binding roofline is `binding` (ncu: XU 67 % in pass 1, 76 % in pass 2); see DESIGN.md 4.2",
+                    "binding roofline is `binding` (ncu: XU 67-69 % in pass 1, 76 % in pass 2); see DESIGN.md 4.2",
             "state_updates_per_s": round(L_total * 4096 * args.steps / (ss["ms_total"] * 1e-3), 1),
             # the binding resource: one MUFU ex2 per state update and per pass (two passes)
             # + 2 per (position, channel) for softplus; MUFU peak = 16 lanes/clk/SM
