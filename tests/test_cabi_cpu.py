@@ -177,3 +177,24 @@ def test_uint8_entry_point_validates_and_refuses_cpu(lib_path):
         wm.enhance_bgr_u8(net, torch.zeros(16, 16, 4, dtype=torch.uint8))   # not 3 channels
     with pytest.raises((wm.WaveMambaNativeError, RuntimeError)):
         wm.enhance_bgr_u8(net, torch.zeros(16, 16, 3, dtype=torch.uint8), device=torch.device("cpu"))
+
+
+def test_pipelines_and_metrics_refuse_cpu(lib_path):
+    """EnhancePipeline, ShardedEnhancePipeline and the device metrics fail loudly without a CUDA device /
+    process group -- none of them has a host path; the metric size query needs no GPU."""
+    from wave_mamba_b200 import _cabi, ops, parallel
+    import wave_mamba_b200 as wm
+    lib = _cabi.load()
+    tiles = ((2160 - 2 + 31) // 32) * ((3840 - 2 + 31) // 32)
+    assert lib.wm_psnr_ssim_y_workspace_bytes(1, 2160, 3840, 1) == tiles * 2 * 8
+    assert lib.wm_psnr_ssim_y_workspace_bytes(3, 2, 2, 1) == 0          # nothing left after the crop
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    net = wm.WaveMamba(in_chn=3, wf=32, n_l_blocks=[1, 2, 4], n_h_blocks=[1, 1, 2], ffn_scale=2.0).eval()
+    with pytest.raises(wm.WaveMambaNativeError):
+        wm.EnhancePipeline(net)
+    with pytest.raises(RuntimeError):
+        parallel.ShardedEnhancePipeline(net, torch.device("cpu"))
+    img = torch.zeros(1, 8, 8, 3, dtype=torch.uint8)
+    with pytest.raises(wm.WaveMambaNativeError):
+        ops.psnr_ssim_y(img, img)
